@@ -1,0 +1,152 @@
+/* flownet.h -- C ABI of libflownet.so, the sm_100a implementation of the flow_net hot path.
+ *
+ * The reference (loliverhennigh/Steady-State-Flow-With-Neural-Nets) has no FFI: its hot path
+ * is a set of Python functions that emit TensorFlow ops.  Each entry point below replaces the
+ * TF op group named beside it (file:line in /root/reference); the Python host code in
+ * steady-state-flow-with-neural-nets_b200/model/ keeps the reference's function names and
+ * binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer borrowed from the caller unless the name ends in _host
+ *   - activations: bf16, NHWC, densely packed; final velocity field: fp32 NHWC
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), re-entrant,
+ *     allocates nothing and never synchronises
+ *   - return value: 0 ok; <0 invalid argument / unsupported shape (FN_E_*); >0 a cudaError_t
+ *   - fn_last_error() returns a thread-local message for the last non-zero return
+ *   - no C++ exception crosses this boundary; there is no CPU fallback
+ */
+#ifndef FLOWNET_H_
+#define FLOWNET_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FN_ABI_VERSION 1
+
+/* error codes (negative) */
+#define FN_E_INVAL      (-1)   /* null pointer, bad enum, non-positive dim */
+#define FN_E_UNSUPPORTED (-2)  /* shape/flag combination this build has no kernel for */
+#define FN_E_ALIGN      (-3)   /* pointer not 16-byte aligned / channel count not a multiple of 8 */
+
+/* A-operand prologue: the nonlinearity the reference applies to the conv input
+ * (flow_architecture.py:14-29 set_nonlinearity; res_block :132-135, :142-143) */
+enum fn_prologue {
+  FN_PRO_NONE        = 0,  /* raw input (first block with 1 channel :132-133; last_conv :242; up-convs) */
+  FN_PRO_CONCAT_ELU  = 1,  /* [elu(x), elu(-x)], C -> 2C  (:14-17) */
+  FN_PRO_ELU         = 2,  /* tf.nn.elu   (:22-23) */
+  FN_PRO_CONCAT_RELU = 3,  /* tf.nn.crelu (:24-25) */
+  FN_PRO_RELU        = 4   /* tf.nn.relu  (:26-27) */
+};
+
+/* epilogue fused behind the accumulator */
+enum fn_epilogue {
+  FN_EPI_BIAS     = 0,  /* y = acc + bias                        -> bf16 [.,Cout]      (conv_layer :64-65) */
+  FN_EPI_GATE_RES = 1,  /* y = sc(res) + (u+bu)*sigmoid(v+bv)    -> bf16 [.,Cout/2]    (res_block :149-165) */
+  FN_EPI_RES      = 2,  /* y = sc(res) + acc + bias              -> bf16 [.,Cout]      (res_block :147,:153-165) */
+  FN_EPI_TANH     = 3   /* y = tanh(acc + bias)                  -> fp32 [.,Cout]      (conv_res :242-243) */
+};
+
+/* implementation selector: the tensor-core kernels are the product; the CUDA-core kernels
+ * cover the layers with no GEMM shape (1-channel head, 2-channel tail) and serve as an
+ * on-device cross-check.  FN_IMPL_AUTO picks tcgen05 wherever a kernel exists. */
+enum fn_impl { FN_IMPL_AUTO = 0, FN_IMPL_SIMT = 1, FN_IMPL_TCGEN05 = 2 };
+
+/* One fused convolution launch.
+ *
+ * Computes, for every output pixel p of a TF-'SAME' k x k convolution with stride s
+ * (tf.nn.conv2d, flow_architecture.py:64; padding rule SURVEY App. B.1):
+ *
+ *   acc[p, :] = sum_taps pro(x)[p*s + tap - pad, :] . W[tap]            (K = Keff per tap)
+ *             + pro(skip)[p, :] . Wskip                                 (optional: nin, :136-142)
+ *   y[p, :]   = epilogue(acc[p, :] + bias, res)
+ *
+ * where pro() is the prologue nonlinearity and Keff = Cin (x2 for the concat variants).
+ * `skip` (if non-null) has the OUTPUT spatial size... or smaller: it is zero-padded at the
+ * bottom/right to OH x OW exactly as tf.pad does at :139-141.
+ * `res` is the block's orig_x: [B,RH,RW,Cres]; if res_pool it is 2x2/2 'SAME' average-pooled
+ * (:153-155) and if Cres < F it is zero-padded IN FRONT on the channel axis (:158-163).
+ */
+typedef struct fn_conv_desc {
+  int32_t B, H, W;          /* input spatial size */
+  int32_t Cin;              /* raw input channels (1, or a multiple of 8) */
+  int32_t Cout;             /* accumulator width N (gated: 2F) */
+  int32_t ksize;            /* 3 or 1 */
+  int32_t stride;           /* 1 or 2 */
+  int32_t prologue;         /* enum fn_prologue */
+  int32_t epilogue;         /* enum fn_epilogue */
+  int32_t impl;             /* enum fn_impl */
+  const void*  x;           /* bf16 [B,H,W,Cin] */
+  const void*  w;           /* bf16 [k*k, Keff, Cout]  (== TF HWIO flattened), SIMT layout   */
+  const void*  w_tc;        /* bf16 tensor-core packing of the same weights (fn_pack_conv_weights_tc) or NULL */
+  const float* bias;        /* fp32 [Cout] (conv bias, plus nin bias when skip is used) */
+  void*        y;           /* bf16 [B,OH,OW,Cy]; fp32 for FN_EPI_TANH */
+  const void*  skip;        /* bf16 [B,SH,SW,Cskip] or NULL */
+  const void*  w_skip;      /* bf16 [Kskip_eff, Cout] (== TF [dim,hiddens]) */
+  int32_t Cskip, SH, SW;
+  const void*  res;         /* bf16 [B,RH,RW,Cres] or NULL */
+  int32_t Cres, RH, RW;
+  int32_t res_pool;         /* 1: 2x2 average pool of res */
+  /* training only (tf.nn.dropout on the prologue output, :144-145); keep_prob >= 1 disables */
+  float    keep_prob;
+  uint64_t dropout_seed;
+  uint64_t dropout_offset;
+} fn_conv_desc;
+
+/* One transposed convolution launch: tf.nn.conv2d_transpose(k=3, s=2, 'SAME') + bias
+ * (flow_architecture.py:70-87; phase taps SURVEY App. B.2).  x: bf16 [B,h,w,Cin] ->
+ * y: bf16 [B,2h,2w,Cout].  w: bf16 [9, Cin, Cout] (TF [kh,kw,Cout,Cin] with the last two
+ * axes swapped), w_tc: tensor-core packing or NULL. */
+typedef struct fn_tconv_desc {
+  int32_t B, H, W, Cin, Cout;
+  int32_t impl;
+  const void*  x;
+  const void*  w;
+  const void*  w_tc;
+  const float* bias;
+  void*        y;
+} fn_tconv_desc;
+
+int         fn_abi_version(void);
+/* sizeof the descriptor structs as this library was compiled (binding sanity check) */
+int         fn_sizeof_conv_desc(void);
+int         fn_sizeof_tconv_desc(void);
+const char* fn_last_error(void);
+/* number of kernel launches issued through this library by the calling process */
+uint64_t    fn_launch_count(void);
+/* 1 if the last fn_conv_fwd / fn_tconv_fwd on this thread ran a tcgen05 kernel */
+int         fn_last_used_tcgen05(void);
+
+/* tf.nn.conv2d + bias_add (+ fused neighbours)          flow_architecture.py:57-68, 129-165 */
+int fn_conv_fwd(const fn_conv_desc* d, void* stream);
+/* tf.nn.conv2d_transpose + bias_add                      flow_architecture.py:70-87 */
+int fn_tconv_fwd(const fn_tconv_desc* d, void* stream);
+/* size in bytes of / packer for the tensor-core weight image of a conv (host-side helper
+ * that runs a small device kernel): src = bf16 [T, Keff, Cout] (+ optional [Kskip, Cout]) */
+int64_t fn_conv_weights_tc_bytes(int32_t ksize, int32_t Keff, int32_t Kskip, int32_t Cout, int32_t gated);
+int fn_pack_conv_weights_tc(const void* w, const void* w_skip, void* dst, int32_t ksize,
+                            int32_t Keff, int32_t Kskip, int32_t Cout, int32_t gated, void* stream);
+
+/* standalone nonlinearity (the public concat_elu()/set_nonlinearity() API) :14-29
+ * x: bf16 [n, C] -> y: bf16 [n, C or 2C] */
+int fn_nonlinearity(const void* x, void* y, int64_t n, int32_t C, int32_t kind, void* stream);
+/* dtype plumbing at the boundary: u8/f32 -> bf16 and bf16 -> f32, n elements */
+int fn_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
+int fn_cast_u8_to_bf16(const uint8_t* x, void* y, int64_t n, void* stream);
+int fn_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
+
+/* tf.nn.l2_loss(p - t) = sum((p-t)^2)/2                  flow_net.py:39-42
+ * p, t: fp32 [n]; loss: fp32 [1] (accumulated into: zero it first); grad (optional): fp32 [n] = p - t */
+int fn_l2_loss(const float* p, const float* t, float* loss, float* grad, int64_t n, void* stream);
+
+/* tf.train.AdamOptimizer.apply (TF1 ApplyAdam)           flow_net.py:44-46; SURVEY App. B.10
+ * flat fp32 buffers of n elements; step is the 1-based step count */
+int fn_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, int64_t step,
+                 float lr, float beta1, float beta2, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWNET_H_ */

@@ -1,0 +1,171 @@
+// extern "C" surface of libflownet.so (declared in include/flownet.h): argument validation,
+// error plumbing and dispatch to the tcgen05 (conv_tc.cu) or CUDA-core (conv_simt.cu) kernels.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace fn {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_last_tc = 0;
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+void note_tcgen05(bool used) { g_last_tc = used ? 1 : 0; }
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+// implemented in the other translation units
+int conv_fwd_simt(const fn_conv_desc& d, cudaStream_t stream);
+int tconv_fwd_simt(const fn_tconv_desc& d, cudaStream_t stream);
+bool conv_tc_supported(const fn_conv_desc& d, const char** why);
+int conv_fwd_tc(const fn_conv_desc& d, cudaStream_t stream);
+bool tconv_tc_supported(const fn_tconv_desc& d, const char** why);
+int tconv_fwd_tc(const fn_tconv_desc& d, cudaStream_t stream);
+long long conv_weights_tc_bytes(int ksize, int Keff, int Kskip, int Cout, int gated);
+int pack_conv_weights_tc(const void* w, const void* w_skip, void* dst, int ksize, int Keff, int Kskip, int Cout,
+                         int gated, cudaStream_t stream);
+int nonlinearity(const void* x, void* y, long long n, int C, int kind, cudaStream_t s);
+template <typename TI, typename TO>
+int cast(const TI* x, TO* y, long long n, cudaStream_t s);
+int l2_loss(const float* p, const float* t, float* loss, float* grad, long long n, cudaStream_t s);
+int adam_step(float* param, const float* grad, float* m, float* v, long long n, long long step, float lr, float b1,
+              float b2, float eps, cudaStream_t s);
+
+static int validate_conv(const fn_conv_desc& d) {
+  FN_REQUIRE(d.B > 0 && d.H > 0 && d.W > 0 && d.Cin > 0 && d.Cout > 0, FN_E_INVAL,
+             "fn_conv_fwd: non-positive dimension (B=%d H=%d W=%d Cin=%d Cout=%d)", d.B, d.H, d.W, d.Cin, d.Cout);
+  FN_REQUIRE(d.x && d.w && d.bias && d.y, FN_E_INVAL, "fn_conv_fwd: null x/w/bias/y");
+  FN_REQUIRE(d.ksize == 3 || d.ksize == 1, FN_E_UNSUPPORTED, "fn_conv_fwd: kernel size %d (only 1 and 3)", d.ksize);
+  FN_REQUIRE(d.stride == 1 || d.stride == 2, FN_E_UNSUPPORTED, "fn_conv_fwd: stride %d (only 1 and 2)", d.stride);
+  FN_REQUIRE(d.prologue >= FN_PRO_NONE && d.prologue <= FN_PRO_RELU, FN_E_INVAL, "fn_conv_fwd: bad prologue %d",
+             d.prologue);
+  FN_REQUIRE(d.epilogue >= FN_EPI_BIAS && d.epilogue <= FN_EPI_TANH, FN_E_INVAL, "fn_conv_fwd: bad epilogue %d",
+             d.epilogue);
+  FN_REQUIRE(d.impl >= FN_IMPL_AUTO && d.impl <= FN_IMPL_TCGEN05, FN_E_INVAL, "fn_conv_fwd: bad impl %d", d.impl);
+  FN_REQUIRE(d.Cin == 1 || (d.Cin % 8) == 0, FN_E_ALIGN, "fn_conv_fwd: Cin=%d must be 1 or a multiple of 8", d.Cin);
+  FN_REQUIRE(aligned16(d.x) && aligned16(d.y) && aligned16(d.w), FN_E_ALIGN, "fn_conv_fwd: x/y/w must be 16-byte aligned");
+  if (d.epilogue == FN_EPI_GATE_RES)
+    FN_REQUIRE((d.Cout % 16) == 0, FN_E_ALIGN, "fn_conv_fwd: gated Cout=%d must be a multiple of 16", d.Cout);
+  else if (d.epilogue != FN_EPI_TANH)
+    FN_REQUIRE((d.Cout % 8) == 0, FN_E_ALIGN, "fn_conv_fwd: Cout=%d must be a multiple of 8", d.Cout);
+  if (d.skip) {
+    FN_REQUIRE(d.w_skip && d.Cskip > 0 && (d.Cskip % 8) == 0 && d.SH > 0 && d.SW > 0 && aligned16(d.skip), FN_E_INVAL,
+               "fn_conv_fwd: bad skip operand (Cskip=%d SH=%d SW=%d)", d.Cskip, d.SH, d.SW);
+    const int OH = (d.H + d.stride - 1) / d.stride, OW = (d.W + d.stride - 1) / d.stride;
+    FN_REQUIRE(d.SH <= OH && d.SW <= OW, FN_E_INVAL, "fn_conv_fwd: skip %dx%d larger than output %dx%d", d.SH, d.SW,
+               OH, OW);
+  }
+  if (d.epilogue == FN_EPI_GATE_RES || d.epilogue == FN_EPI_RES) {
+    const int F = d.epilogue == FN_EPI_GATE_RES ? d.Cout / 2 : d.Cout;
+    if (d.res) {
+      FN_REQUIRE(d.Cres > 0 && d.Cres <= F && d.RH > 0 && d.RW > 0, FN_E_INVAL,
+                 "fn_conv_fwd: bad residual operand (Cres=%d F=%d RH=%d RW=%d)", d.Cres, F, d.RH, d.RW);
+    }
+  }
+  return 0;
+}
+
+}  // namespace fn
+
+using namespace fn;
+
+extern "C" {
+
+int fn_abi_version(void) { return FN_ABI_VERSION; }
+int fn_sizeof_conv_desc(void) { return (int)sizeof(fn_conv_desc); }
+int fn_sizeof_tconv_desc(void) { return (int)sizeof(fn_tconv_desc); }
+const char* fn_last_error(void) { return g_err; }
+uint64_t fn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int fn_last_used_tcgen05(void) { return g_last_tc; }
+
+int fn_conv_fwd(const fn_conv_desc* d, void* stream) {
+  FN_REQUIRE(d != nullptr, FN_E_INVAL, "fn_conv_fwd: null descriptor");
+  int rc = validate_conv(*d);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const char* why = "";
+  if (d->impl != FN_IMPL_SIMT && conv_tc_supported(*d, &why)) {
+    note_tcgen05(true);
+    return conv_fwd_tc(*d, s);
+  }
+  FN_REQUIRE(d->impl != FN_IMPL_TCGEN05, FN_E_UNSUPPORTED, "fn_conv_fwd: no tcgen05 kernel for this shape: %s", why);
+  note_tcgen05(false);
+  return conv_fwd_simt(*d, s);
+}
+
+int fn_tconv_fwd(const fn_tconv_desc* d, void* stream) {
+  FN_REQUIRE(d != nullptr, FN_E_INVAL, "fn_tconv_fwd: null descriptor");
+  FN_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, FN_E_INVAL,
+             "fn_tconv_fwd: non-positive dimension");
+  FN_REQUIRE(d->x && d->w && d->bias && d->y, FN_E_INVAL, "fn_tconv_fwd: null x/w/bias/y");
+  FN_REQUIRE((d->Cin % 8) == 0 && (d->Cout % 8) == 0, FN_E_ALIGN, "fn_tconv_fwd: Cin=%d Cout=%d must be multiples of 8",
+             d->Cin, d->Cout);
+  FN_REQUIRE(aligned16(d->x) && aligned16(d->y) && aligned16(d->w), FN_E_ALIGN, "fn_tconv_fwd: x/y/w must be 16-byte aligned");
+  FN_REQUIRE(d->impl >= FN_IMPL_AUTO && d->impl <= FN_IMPL_TCGEN05, FN_E_INVAL, "fn_tconv_fwd: bad impl %d", d->impl);
+  cudaStream_t s = (cudaStream_t)stream;
+  const char* why = "";
+  if (d->impl != FN_IMPL_SIMT && tconv_tc_supported(*d, &why)) {
+    note_tcgen05(true);
+    return tconv_fwd_tc(*d, s);
+  }
+  FN_REQUIRE(d->impl != FN_IMPL_TCGEN05, FN_E_UNSUPPORTED, "fn_tconv_fwd: no tcgen05 kernel for this shape: %s", why);
+  note_tcgen05(false);
+  return tconv_fwd_simt(*d, s);
+}
+
+int64_t fn_conv_weights_tc_bytes(int32_t ksize, int32_t Keff, int32_t Kskip, int32_t Cout, int32_t gated) {
+  return conv_weights_tc_bytes(ksize, Keff, Kskip, Cout, gated);
+}
+
+int fn_pack_conv_weights_tc(const void* w, const void* w_skip, void* dst, int32_t ksize, int32_t Keff, int32_t Kskip,
+                            int32_t Cout, int32_t gated, void* stream) {
+  FN_REQUIRE(w && dst, FN_E_INVAL, "fn_pack_conv_weights_tc: null w/dst");
+  return pack_conv_weights_tc(w, w_skip, dst, ksize, Keff, Kskip, Cout, gated, (cudaStream_t)stream);
+}
+
+int fn_nonlinearity(const void* x, void* y, int64_t n, int32_t C, int32_t kind, void* stream) {
+  FN_REQUIRE(x && y && n >= 0 && C > 0, FN_E_INVAL, "fn_nonlinearity: bad arguments");
+  FN_REQUIRE(kind >= FN_PRO_CONCAT_ELU && kind <= FN_PRO_RELU, FN_E_INVAL, "fn_nonlinearity: bad kind %d", kind);
+  return nonlinearity(x, y, n, C, kind, (cudaStream_t)stream);
+}
+
+int fn_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
+  FN_REQUIRE(x && y && n >= 0, FN_E_INVAL, "fn_cast_f32_to_bf16: bad arguments");
+  return cast<float, __nv_bfloat16>(x, (__nv_bfloat16*)y, n, (cudaStream_t)stream);
+}
+int fn_cast_u8_to_bf16(const uint8_t* x, void* y, int64_t n, void* stream) {
+  FN_REQUIRE(x && y && n >= 0, FN_E_INVAL, "fn_cast_u8_to_bf16: bad arguments");
+  return cast<uint8_t, __nv_bfloat16>(x, (__nv_bfloat16*)y, n, (cudaStream_t)stream);
+}
+int fn_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
+  FN_REQUIRE(x && y && n >= 0, FN_E_INVAL, "fn_cast_bf16_to_f32: bad arguments");
+  return cast<__nv_bfloat16, float>((const __nv_bfloat16*)x, y, n, (cudaStream_t)stream);
+}
+
+int fn_l2_loss(const float* p, const float* t, float* loss, float* grad, int64_t n, void* stream) {
+  FN_REQUIRE(p && t && loss && n >= 0, FN_E_INVAL, "fn_l2_loss: bad arguments");
+  return l2_loss(p, t, loss, grad, n, (cudaStream_t)stream);
+}
+
+int fn_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, int64_t step, float lr, float beta1,
+                 float beta2, float eps, void* stream) {
+  FN_REQUIRE(param && grad && m && v && n >= 0 && step >= 1, FN_E_INVAL, "fn_adam_step: bad arguments");
+  return adam_step(param, grad, m, v, n, step, lr, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
+}  // extern "C"

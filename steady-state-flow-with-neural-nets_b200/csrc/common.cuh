@@ -1,0 +1,76 @@
+// Shared device/host helpers for libflownet.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "flownet.h"
+
+namespace fn {
+
+// ---- error plumbing (thread-local message, no exceptions across the ABI)
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+void note_tcgen05(bool used);
+int check_launch(const char* what);
+
+#define FN_REQUIRE(cond, code, ...)        \
+  do {                                     \
+    if (!(cond)) {                         \
+      fn::set_error(__VA_ARGS__);          \
+      return (code);                       \
+    }                                      \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// TF 'SAME' padding-before for kernel k, stride s on an axis of n
+__host__ __device__ inline int same_pad_before(int n, int k, int s) {
+  int out = (n + s - 1) / s;
+  int tot = (out - 1) * s + k - n;
+  if (tot < 0) tot = 0;
+  return tot / 2;
+}
+
+// ---- nonlinearities (flow_architecture.py:14-29)
+__device__ __forceinline__ float elu_f(float z) { return z > 0.f ? z : (__expf(z) - 1.f); }
+__device__ __forceinline__ float sigmoid_f(float z) { return 1.f / (1.f + __expf(-z)); }
+
+// number of GEMM-K channels produced per raw channel by a prologue
+__host__ __device__ inline int pro_mult(int pro) {
+  return (pro == FN_PRO_CONCAT_ELU || pro == FN_PRO_CONCAT_RELU) ? 2 : 1;
+}
+
+// first (and for concat variants second) prologue output of one raw value
+__device__ __forceinline__ void pro_apply(int pro, float v, float& p0, float& p1) {
+  switch (pro) {
+    case FN_PRO_CONCAT_ELU:  p0 = elu_f(v);       p1 = elu_f(-v);       break;
+    case FN_PRO_ELU:         p0 = elu_f(v);       p1 = 0.f;             break;
+    case FN_PRO_CONCAT_RELU: p0 = fmaxf(v, 0.f);  p1 = fmaxf(-v, 0.f);  break;
+    case FN_PRO_RELU:        p0 = fmaxf(v, 0.f);  p1 = 0.f;             break;
+    default:                 p0 = v;              p1 = 0.f;             break;
+  }
+}
+
+// ---- counter-based dropout mask (tf.nn.dropout, flow_architecture.py:144-145):
+// keep element `idx` iff u(seed, idx) < keep_prob; kept values are scaled by 1/keep_prob.
+__host__ __device__ inline uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ inline float dropout_scale(uint64_t seed, uint64_t idx, float keep_prob) {
+  uint64_t h = mix64(seed ^ mix64(idx));
+  float u = (float)(h >> 40) * (1.0f / 16777216.0f);
+  return u < keep_prob ? 1.0f / keep_prob : 0.0f;
+}
+
+union bf16x8 {
+  uint4 v;
+  __nv_bfloat16 h[8];
+  __nv_bfloat162 h2[4];
+};
+
+}  // namespace fn

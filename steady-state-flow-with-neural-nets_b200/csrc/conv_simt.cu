@@ -1,0 +1,271 @@
+// CUDA-core (SIMT) fused convolution kernels.
+//
+// Role: (1) the layers of flow_net that have no tensor-core GEMM shape -- the 1-channel head
+// (K = 9) and the 2-channel tanh tail (N = 2); (2) an on-device cross-check for the tcgen05
+// kernels (same bf16 storage points, fp32 accumulation), selectable with FN_IMPL_SIMT.
+// Semantics: tf.nn.conv2d / conv2d_transpose 'SAME' + the fused neighbours listed in
+// include/flownet.h (reference: model/flow_architecture.py:57-87, 129-165).
+#include "common.cuh"
+
+namespace fn {
+
+constexpr int SIMT_THREADS = 128;
+constexpr int SIMT_NT = 8;          // output-channel slots per thread
+constexpr int SIMT_MAX_KEFF = 256;  // K per tap staged in shared memory
+
+struct ConvParams {
+  fn_conv_desc d;
+  int OH, OW, pad_t, pad_l;
+  int Keff, Kskip_eff;
+  int slots;   // output channels written (gated: Cout/2)
+};
+
+// accumulate one tap's K range for this thread's pixel
+template <int NACC>
+__device__ __forceinline__ void accumulate_pixel(const __nv_bfloat16* __restrict__ px, int Craw, int pro,
+                                                 const float* __restrict__ wsm, float (&acc)[NACC],
+                                                 bool drop, uint64_t seed, uint64_t base_idx, float keep) {
+  const int mult = pro_mult(pro);
+  if ((Craw & 7) == 0) {
+    for (int c8 = 0; c8 < Craw; c8 += 8) {
+      bf16x8 raw;
+      raw.v = *reinterpret_cast<const uint4*>(px + c8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float p0, p1;
+        pro_apply(pro, __bfloat162float(raw.h[j]), p0, p1);
+        if (pro != FN_PRO_NONE) {   // the stored operand is bf16 on every path
+          p0 = __bfloat162float(__float2bfloat16(p0));
+          p1 = __bfloat162float(__float2bfloat16(p1));
+        }
+        const int c = c8 + j;
+        if (drop) {
+          p0 *= dropout_scale(seed, base_idx + c, keep);
+          if (mult == 2) p1 *= dropout_scale(seed, base_idx + Craw + c, keep);
+        }
+        const float* w0 = wsm + c * NACC;
+#pragma unroll
+        for (int n = 0; n < NACC; ++n) acc[n] = fmaf(p0, w0[n], acc[n]);
+        if (mult == 2) {
+          const float* w1 = wsm + (Craw + c) * NACC;
+#pragma unroll
+          for (int n = 0; n < NACC; ++n) acc[n] = fmaf(p1, w1[n], acc[n]);
+        }
+      }
+    }
+  } else {
+    for (int c = 0; c < Craw; ++c) {
+      float p0, p1;
+      pro_apply(pro, __bfloat162float(px[c]), p0, p1);
+      if (pro != FN_PRO_NONE) {
+        p0 = __bfloat162float(__float2bfloat16(p0));
+        p1 = __bfloat162float(__float2bfloat16(p1));
+      }
+      if (drop) {
+        p0 *= dropout_scale(seed, base_idx + c, keep);
+        if (mult == 2) p1 *= dropout_scale(seed, base_idx + Craw + c, keep);
+      }
+      const float* w0 = wsm + c * NACC;
+#pragma unroll
+      for (int n = 0; n < NACC; ++n) acc[n] = fmaf(p0, w0[n], acc[n]);
+      if (mult == 2) {
+        const float* w1 = wsm + (Craw + c) * NACC;
+#pragma unroll
+        for (int n = 0; n < NACC; ++n) acc[n] = fmaf(p1, w1[n], acc[n]);
+      }
+    }
+  }
+}
+
+// stage W[k][n0 .. n0+8) (and, gated, W[k][F+n0 .. F+n0+8)) of one tap as fp32 [k][NACC]
+template <int NACC>
+__device__ __forceinline__ void stage_weights(const __nv_bfloat16* __restrict__ w, int K, int Cout, int n0,
+                                              int F, float* wsm) {
+  for (int i = threadIdx.x; i < K * NACC; i += SIMT_THREADS) {
+    const int k = i / NACC, j = i % NACC;
+    const int c = n0 + (j % SIMT_NT);            // output slot
+    const int n = (j >= SIMT_NT) ? F + c : c;    // second half of NACC = the gate channel of slot c
+    wsm[i] = (c < F) ? __bfloat162float(w[(size_t)k * Cout + n]) : 0.f;
+  }
+}
+
+template <bool GATED>
+__global__ void __launch_bounds__(SIMT_THREADS) k_conv_simt(const ConvParams p) {
+  constexpr int NACC = GATED ? 2 * SIMT_NT : SIMT_NT;
+  __shared__ float wsm[SIMT_MAX_KEFF * NACC];
+  const fn_conv_desc& d = p.d;
+  const int F = GATED ? d.Cout / 2 : d.Cout;
+  const int n0 = blockIdx.y * SIMT_NT;
+  const long long npix = (long long)d.B * p.OH * p.OW;
+  const long long pix = (long long)blockIdx.x * SIMT_THREADS + threadIdx.x;
+  const bool live = pix < npix;
+  int b = 0, oy = 0, ox = 0;
+  if (live) {
+    b = (int)(pix / ((long long)p.OH * p.OW));
+    int r = (int)(pix % ((long long)p.OH * p.OW));
+    oy = r / p.OW;
+    ox = r % p.OW;
+  }
+  float acc[NACC];
+#pragma unroll
+  for (int n = 0; n < NACC; ++n) acc[n] = 0.f;
+
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(d.x);
+  const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(d.w);
+  const bool drop = d.keep_prob < 1.0f;
+  const int k = d.ksize;
+  for (int tap = 0; tap < k * k; ++tap) {
+    __syncthreads();
+    stage_weights<NACC>(w + (size_t)tap * p.Keff * d.Cout, p.Keff, d.Cout, n0, F, wsm);
+    __syncthreads();
+    const int di = tap / k, dj = tap % k;
+    const int iy = oy * d.stride + di - p.pad_t;
+    const int ix = ox * d.stride + dj - p.pad_l;
+    if (live && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) {
+      const size_t pidx = ((size_t)b * d.H + iy) * d.W + ix;
+      accumulate_pixel<NACC>(x + pidx * d.Cin, d.Cin, d.prologue, wsm, acc, drop, d.dropout_seed,
+                             d.dropout_offset + pidx * p.Keff, d.keep_prob);
+    }
+  }
+  if (d.skip != nullptr) {
+    __syncthreads();
+    stage_weights<NACC>(reinterpret_cast<const __nv_bfloat16*>(d.w_skip), p.Kskip_eff, d.Cout, n0, F, wsm);
+    __syncthreads();
+    if (live && oy < d.SH && ox < d.SW) {
+      const size_t pidx = ((size_t)b * d.SH + oy) * d.SW + ox;
+      accumulate_pixel<NACC>(reinterpret_cast<const __nv_bfloat16*>(d.skip) + pidx * d.Cskip, d.Cskip,
+                             d.prologue, wsm, acc, false, 0, 0, 1.f);
+    }
+  }
+  if (!live) return;
+
+  // ---- epilogue
+  float out[SIMT_NT];
+#pragma unroll
+  for (int j = 0; j < SIMT_NT; ++j) {
+    const int n = n0 + j;
+    float v = 0.f;
+    if (n < F) {
+      if (GATED) {
+        v = (acc[j] + d.bias[n]) * sigmoid_f(acc[SIMT_NT + j] + d.bias[F + n]);
+      } else {
+        v = acc[j] + d.bias[n];
+      }
+      if (d.epilogue == FN_EPI_GATE_RES || d.epilogue == FN_EPI_RES) {
+        const int cr = n - (F - d.Cres);          // channels are zero-padded IN FRONT
+        if (d.res != nullptr && cr >= 0) {
+          const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.res);
+          if (d.res_pool) {
+            float s = 0.f;
+            int cnt = 0;
+            for (int a = 0; a < 2; ++a)
+              for (int c = 0; c < 2; ++c) {
+                const int ry = 2 * oy + a, rx = 2 * ox + c;
+                if (ry < d.RH && rx < d.RW) {
+                  s += __bfloat162float(res[(((size_t)b * d.RH + ry) * d.RW + rx) * d.Cres + cr]);
+                  ++cnt;
+                }
+              }
+            v += s / (float)cnt;
+          } else {
+            v += __bfloat162float(res[(((size_t)b * d.RH + oy) * d.RW + ox) * d.Cres + cr]);
+          }
+        }
+      }
+      if (d.epilogue == FN_EPI_TANH) v = tanhf(v);
+    }
+    out[j] = v;
+  }
+  const size_t obase = (size_t)pix * F + n0;
+  if (d.epilogue == FN_EPI_TANH) {
+    float* y = reinterpret_cast<float*>(d.y);
+    for (int j = 0; j < SIMT_NT && n0 + j < F; ++j) y[obase + j] = out[j];
+  } else {
+    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(d.y);
+    if ((F & 7) == 0) {
+      bf16x8 o;
+#pragma unroll
+      for (int j = 0; j < SIMT_NT; ++j) o.h[j] = __float2bfloat16(out[j]);
+      *reinterpret_cast<uint4*>(y + obase) = o.v;
+    } else {
+      for (int j = 0; j < SIMT_NT && n0 + j < F; ++j) y[obase + j] = __float2bfloat16(out[j]);
+    }
+  }
+}
+
+int conv_fwd_simt(const fn_conv_desc& d, cudaStream_t stream) {
+  ConvParams p;
+  p.d = d;
+  p.OH = (d.H + d.stride - 1) / d.stride;
+  p.OW = (d.W + d.stride - 1) / d.stride;
+  p.pad_t = same_pad_before(d.H, d.ksize, d.stride);
+  p.pad_l = same_pad_before(d.W, d.ksize, d.stride);
+  p.Keff = d.Cin * pro_mult(d.prologue);
+  p.Kskip_eff = d.Cskip * pro_mult(d.prologue);
+  const bool gated = d.epilogue == FN_EPI_GATE_RES;
+  p.slots = gated ? d.Cout / 2 : d.Cout;
+  FN_REQUIRE(p.Keff <= SIMT_MAX_KEFF && p.Kskip_eff <= SIMT_MAX_KEFF, FN_E_UNSUPPORTED,
+             "conv_simt: K per tap %d (skip %d) exceeds %d", p.Keff, p.Kskip_eff, SIMT_MAX_KEFF);
+  const long long npix = (long long)d.B * p.OH * p.OW;
+  dim3 grid((unsigned)((npix + SIMT_THREADS - 1) / SIMT_THREADS), (unsigned)((p.slots + SIMT_NT - 1) / SIMT_NT));
+  if (gated)
+    k_conv_simt<true><<<grid, SIMT_THREADS, 0, stream>>>(p);
+  else
+    k_conv_simt<false><<<grid, SIMT_THREADS, 0, stream>>>(p);
+  count_launch();
+  return check_launch("k_conv_simt");
+}
+
+// ------------------------------------------------------------------ transposed conv (k=3, s=2)
+// out[b, I, J, o] = bias[o] + sum_{di,dj : I-di, J-dj even, in range} x[b,(I-di)/2,(J-dj)/2,:] . W[di,dj,:,o]
+__global__ void __launch_bounds__(SIMT_THREADS) k_tconv_simt(const fn_tconv_desc d) {
+  __shared__ float wsm[SIMT_MAX_KEFF * SIMT_NT];
+  const int OH = 2 * d.H, OW = 2 * d.W;
+  const int n0 = blockIdx.y * SIMT_NT;
+  const long long npix = (long long)d.B * OH * OW;
+  const long long pix = (long long)blockIdx.x * SIMT_THREADS + threadIdx.x;
+  const bool live = pix < npix;
+  int b = 0, I = 0, J = 0;
+  if (live) {
+    b = (int)(pix / ((long long)OH * OW));
+    int r = (int)(pix % ((long long)OH * OW));
+    I = r / OW;
+    J = r % OW;
+  }
+  float acc[SIMT_NT];
+#pragma unroll
+  for (int n = 0; n < SIMT_NT; ++n) acc[n] = 0.f;
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(d.x);
+  const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(d.w);
+  for (int tap = 0; tap < 9; ++tap) {
+    __syncthreads();
+    stage_weights<SIMT_NT>(w + (size_t)tap * d.Cin * d.Cout, d.Cin, d.Cout, n0, d.Cout, wsm);
+    __syncthreads();
+    const int di = tap / 3, dj = tap % 3;
+    const int ti = I - di, tj = J - dj;
+    if (live && ti >= 0 && tj >= 0 && ((ti | tj) & 1) == 0) {
+      const int i = ti >> 1, j = tj >> 1;
+      if (i < d.H && j < d.W) {
+        const size_t pidx = ((size_t)b * d.H + i) * d.W + j;
+        accumulate_pixel<SIMT_NT>(x + pidx * d.Cin, d.Cin, FN_PRO_NONE, wsm, acc, false, 0, 0, 1.f);
+      }
+    }
+  }
+  if (!live) return;
+  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(d.y);
+  bf16x8 o;
+#pragma unroll
+  for (int j = 0; j < SIMT_NT; ++j) o.h[j] = __float2bfloat16(acc[j] + d.bias[n0 + j]);
+  *reinterpret_cast<uint4*>(y + (size_t)pix * d.Cout + n0) = o.v;
+}
+
+int tconv_fwd_simt(const fn_tconv_desc& d, cudaStream_t stream) {
+  FN_REQUIRE(d.Cin <= SIMT_MAX_KEFF, FN_E_UNSUPPORTED, "tconv_simt: Cin %d exceeds %d", d.Cin, SIMT_MAX_KEFF);
+  const long long npix = (long long)d.B * 4 * d.H * d.W;
+  dim3 grid((unsigned)((npix + SIMT_THREADS - 1) / SIMT_THREADS), (unsigned)(d.Cout / SIMT_NT));
+  k_tconv_simt<<<grid, SIMT_THREADS, 0, stream>>>(d);
+  count_launch();
+  return check_launch("k_tconv_simt");
+}
+
+}  // namespace fn

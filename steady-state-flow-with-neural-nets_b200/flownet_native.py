@@ -1,0 +1,231 @@
+"""ctypes binding of libflownet.so (include/flownet.h).  PyTorch is used only for device memory
+and streams; every kernel that runs is ours.  There is NO fallback: if the library is missing or
+a call fails this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libflownet.so")
+
+FN_ABI_VERSION = 1
+# enum fn_prologue
+PRO_NONE, PRO_CONCAT_ELU, PRO_ELU, PRO_CONCAT_RELU, PRO_RELU = 0, 1, 2, 3, 4
+# enum fn_epilogue
+EPI_BIAS, EPI_GATE_RES, EPI_RES, EPI_TANH = 0, 1, 2, 3
+# enum fn_impl
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("Cin", C.c_int32), ("Cout", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
+        ("prologue", C.c_int32), ("epilogue", C.c_int32), ("impl", C.c_int32),
+        ("x", C.c_void_p), ("w", C.c_void_p), ("w_tc", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p),
+        ("skip", C.c_void_p), ("w_skip", C.c_void_p),
+        ("Cskip", C.c_int32), ("SH", C.c_int32), ("SW", C.c_int32),
+        ("res", C.c_void_p),
+        ("Cres", C.c_int32), ("RH", C.c_int32), ("RW", C.c_int32), ("res_pool", C.c_int32),
+        ("keep_prob", C.c_float),
+        ("dropout_seed", C.c_uint64), ("dropout_offset", C.c_uint64),
+    ]
+
+
+class TConvDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
+        ("impl", C.c_int32),
+        ("x", C.c_void_p), ("w", C.c_void_p), ("w_tc", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p),
+    ]
+
+
+# every symbol include/flownet.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = [
+    ("fn_abi_version", C.c_int, []),
+    ("fn_sizeof_conv_desc", C.c_int, []),
+    ("fn_sizeof_tconv_desc", C.c_int, []),
+    ("fn_last_error", C.c_char_p, []),
+    ("fn_launch_count", C.c_uint64, []),
+    ("fn_last_used_tcgen05", C.c_int, []),
+    ("fn_conv_fwd", C.c_int, [C.POINTER(ConvDesc), _P]),
+    ("fn_tconv_fwd", C.c_int, [C.POINTER(TConvDesc), _P]),
+    ("fn_conv_weights_tc_bytes", C.c_int64, [C.c_int32] * 5),
+    ("fn_pack_conv_weights_tc", C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    ("fn_nonlinearity", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    ("fn_cast_f32_to_bf16", C.c_int, [_P, _P, C.c_int64, _P]),
+    ("fn_cast_u8_to_bf16", C.c_int, [_P, _P, C.c_int64, _P]),
+    ("fn_cast_bf16_to_f32", C.c_int, [_P, _P, C.c_int64, _P]),
+    ("fn_l2_loss", C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
+    ("fn_adam_step", C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
+]
+DEBUG_SYMBOLS = [
+    ("fn_debug_set_swap_lbo_sbo", None, [C.c_int]),
+    ("fn_debug_tc_status", C.c_int, []),
+]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+            "flow_net has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS + DEBUG_SYMBOLS:
+        f = getattr(lib, name)          # AttributeError if the symbol is not exported
+        f.restype = res
+        f.argtypes = args
+    v = lib.fn_abi_version()
+    if v != FN_ABI_VERSION:
+        raise RuntimeError(f"libflownet.so ABI {v}, binding expects {FN_ABI_VERSION}")
+    if lib.fn_sizeof_conv_desc() != C.sizeof(ConvDesc) or lib.fn_sizeof_tconv_desc() != C.sizeof(TConvDesc):
+        raise RuntimeError("descriptor struct layout differs between include/flownet.h and the ctypes binding")
+    return lib
+
+
+lib = _load()
+
+
+class FlownetError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc == 0:
+        return
+    msg = lib.fn_last_error().decode("utf-8", "replace")
+    if rc < 0:
+        raise ValueError(f"{what}: {msg} (code {rc})")
+    raise FlownetError(f"{what}: CUDA error {rc}: {msg}")
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise ValueError("flow_net kernels take CUDA tensors; there is no CPU path")
+
+
+def launch_count() -> int:
+    return int(lib.fn_launch_count())
+
+
+def last_used_tcgen05() -> bool:
+    return bool(lib.fn_last_used_tcgen05())
+
+
+def tc_status() -> int:
+    """Synchronises; non-zero means a tcgen05 pipeline wait timed out (debug aid)."""
+    return int(lib.fn_debug_tc_status())
+
+
+def conv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, ksize=3, stride=1, prologue=PRO_NONE, epilogue=EPI_BIAS,
+             impl=IMPL_AUTO, w_tc=None, skip=None, w_skip=None, res=None, res_pool=False, keep_prob=1.0,
+             dropout_seed=0, dropout_offset=0):
+    _require_cuda(x, w, bias, y, skip, w_skip, res, w_tc)
+    d = ConvDesc()
+    d.B, d.H, d.W, d.Cin, d.Cout, d.ksize, d.stride = B, H, W, Cin, Cout, ksize, stride
+    d.prologue, d.epilogue, d.impl = prologue, epilogue, impl
+    d.x, d.w, d.w_tc, d.bias, d.y = x.data_ptr(), w.data_ptr(), (w_tc.data_ptr() if w_tc is not None else None), \
+        bias.data_ptr(), y.data_ptr()
+    if skip is not None:
+        d.skip, d.w_skip = skip.data_ptr(), w_skip.data_ptr()
+        d.Cskip, d.SH, d.SW = skip.shape[3], skip.shape[1], skip.shape[2]
+    if res is not None:
+        d.res = res.data_ptr()
+        d.Cres, d.RH, d.RW = res.shape[3], res.shape[1], res.shape[2]
+        d.res_pool = 1 if res_pool else 0
+    d.keep_prob = float(keep_prob)
+    d.dropout_seed, d.dropout_offset = int(dropout_seed), int(dropout_offset)
+    _check(lib.fn_conv_fwd(C.byref(d), stream_ptr()), "fn_conv_fwd")
+
+
+def tconv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, impl=IMPL_AUTO, w_tc=None):
+    _require_cuda(x, w, bias, y, w_tc)
+    d = TConvDesc()
+    d.B, d.H, d.W, d.Cin, d.Cout, d.impl = B, H, W, Cin, Cout, impl
+    d.x, d.w, d.bias, d.y = x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr()
+    d.w_tc = w_tc.data_ptr() if w_tc is not None else None
+    _check(lib.fn_tconv_fwd(C.byref(d), stream_ptr()), "fn_tconv_fwd")
+
+
+def pack_conv_weights_tc(w, w_skip, ksize, Keff, Kskip, Cout, gated):
+    """w: bf16 [k*k, Keff, Cout] (+ w_skip bf16 [Kskip, Cout]) -> tensor-core image (bf16, 1-D) or None."""
+    nbytes = int(lib.fn_conv_weights_tc_bytes(ksize, Keff, Kskip, Cout, int(gated)))
+    if nbytes == 0:
+        return None
+    dst = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    _check(lib.fn_pack_conv_weights_tc(_ptr(w), _ptr(w_skip), _ptr(dst), ksize, Keff, Kskip, Cout, int(gated),
+                                       stream_ptr()), "fn_pack_conv_weights_tc")
+    return dst
+
+
+def nonlinearity(x, kind):
+    _require_cuda(x)
+    Cc = x.shape[-1]
+    mult = 2 if kind in (PRO_CONCAT_ELU, PRO_CONCAT_RELU) else 1
+    y = torch.empty(tuple(x.shape[:-1]) + (mult * Cc,), dtype=torch.bfloat16, device=x.device)
+    n = x.numel() // Cc
+    _check(lib.fn_nonlinearity(_ptr(x), _ptr(y), n, Cc, kind, stream_ptr()), "fn_nonlinearity")
+    return y
+
+
+def to_bf16(x):
+    """Boundary plumbing: uint8 / float32 / bf16 CUDA tensor -> contiguous bf16."""
+    _require_cuda(x)
+    x = x.contiguous()
+    if x.dtype == torch.bfloat16:
+        return x
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if x.dtype == torch.float32:
+        _check(lib.fn_cast_f32_to_bf16(_ptr(x), _ptr(y), x.numel(), stream_ptr()), "fn_cast_f32_to_bf16")
+    elif x.dtype == torch.uint8:
+        _check(lib.fn_cast_u8_to_bf16(_ptr(x), _ptr(y), x.numel(), stream_ptr()), "fn_cast_u8_to_bf16")
+    else:
+        raise ValueError(f"unsupported boundary dtype {x.dtype} (use uint8, float32 or bfloat16)")
+    return y
+
+
+def to_f32(x):
+    _require_cuda(x)
+    x = x.contiguous()
+    if x.dtype == torch.float32:
+        return x
+    if x.dtype != torch.bfloat16:
+        raise ValueError(f"unsupported dtype {x.dtype}")
+    y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    _check(lib.fn_cast_bf16_to_f32(_ptr(x), _ptr(y), x.numel(), stream_ptr()), "fn_cast_bf16_to_f32")
+    return y
+
+
+def l2_loss(p, t, want_grad=False):
+    """tf.nn.l2_loss(p - t): returns (loss[1] fp32, grad or None)."""
+    _require_cuda(p, t)
+    p = p.contiguous()
+    t = t.contiguous()
+    if p.dtype != torch.float32 or t.dtype != torch.float32 or p.shape != t.shape:
+        raise ValueError("l2_loss takes two float32 tensors of the same shape")
+    loss = torch.zeros(1, dtype=torch.float32, device=p.device)
+    grad = torch.empty_like(p) if want_grad else None
+    _check(lib.fn_l2_loss(_ptr(p), _ptr(t), _ptr(loss), _ptr(grad), p.numel(), stream_ptr()), "fn_l2_loss")
+    return loss, grad
+
+
+def adam_step(param, grad, m, v, step, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8):
+    _require_cuda(param, grad, m, v)
+    for t in (param, grad, m, v):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != param.numel():
+            raise ValueError("adam_step takes flat contiguous float32 buffers of equal size")
+    _check(lib.fn_adam_step(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(), int(step), lr, beta1, beta2,
+                            eps, stream_ptr()), "fn_adam_step")

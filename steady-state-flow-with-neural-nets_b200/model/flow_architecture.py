@@ -1,0 +1,353 @@
+"""functions used to construct different architectures -- B200-native.
+
+Mirrors /root/reference/model/flow_architecture.py name for name (int_shape, concat_elu,
+set_nonlinearity, _variable, conv_layer, transpose_conv_layer, fc_layer, nin, res_block, conv_res)
+but executes eagerly on CUDA tensors: every function launches hand-written sm_100a kernels through
+the C ABI of libflownet.so (include/flownet.h).  Activations are NHWC; they are stored as bf16
+between kernels and accumulated in fp32; the network output is fp32.
+
+Fusion happens where the reference composes ops: res_block() (reference :129-165) issues exactly
+two kernels -- conv_1 with the nonlinearity as A-operand prologue and the nin skip folded in as
+extra GEMM-K, then conv_2 with nonlinearity prologue and gate*sigmoid + shortcut epilogue.  The
+stand-alone layer functions remain available and compute the same values un-fused.
+"""
+from __future__ import annotations
+
+import math
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+import flownet_native as native
+from model.flags import FLAGS  # noqa: F401  (the reference exposes FLAGS here too, :9)
+
+# --------------------------------------------------------------------------- configuration
+_IMPL_NAMES = {"auto": native.IMPL_AUTO, "simt": native.IMPL_SIMT, "tc": native.IMPL_TCGEN05}
+IMPL = _IMPL_NAMES[os.environ.get("FLOWNET_IMPL", "auto")]
+
+
+# when a list, every conv / tconv launch appends a record with CUDA events around it (bench.py's
+# per-kernel roofline pass); None in normal operation
+_PROFILE = None
+
+
+def _profiled(record, launch):
+    if _PROFILE is None:
+        launch()
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launch()
+    e1.record()
+    record["events"] = (e0, e1)
+    record["tcgen05"] = native.last_used_tcgen05()
+    _PROFILE.append(record)
+
+
+def set_impl(name: str):
+    """'auto' (tcgen05 wherever a kernel exists), 'simt' (CUDA-core cross-check), 'tc' (fail if no tcgen05 kernel)."""
+    global IMPL
+    IMPL = _IMPL_NAMES[name]
+
+
+def int_shape(x):
+    """reference :11-12"""
+    return list(map(int, x.shape))
+
+
+# --------------------------------------------------------------------------- variables
+class _VariableStore:
+    """The TF graph's variable collection: name -> fp32 CUDA tensor, created lazily in call order
+    with the reference's initializer (xavier for weights AND biases, reference :61-62,:74-75,:99-100;
+    SURVEY App. B.3).  Names, shapes and layouts are TF's, so a checkpoint dump loads 1:1."""
+
+    def __init__(self, seed=1234):
+        self.reset(seed)
+
+    def reset(self, seed=1234):
+        self.seed = seed
+        self.rng = np.random.default_rng(seed)
+        self.vars = OrderedDict()
+        self.version = 0
+        self._derived = {}
+
+    def get(self, name, shape, device):
+        v = self.vars.get(name)
+        if v is not None:
+            if list(v.shape) != list(shape):
+                raise ValueError(f"variable {name} has shape {list(v.shape)}, requested {list(shape)}")
+            return v
+        lim = xavier_limit(shape)
+        arr = self.rng.uniform(-lim, lim, size=shape).astype(np.float32)
+        v = torch.from_numpy(arr).to(device)
+        self.vars[name] = v
+        return v
+
+    def touch(self):
+        """Call after mutating variables in place (optimizer step, checkpoint load)."""
+        self.version += 1
+        self._derived.clear()
+
+    def derived(self, key, make):
+        ent = self._derived.get(key)
+        if ent is None:
+            ent = make()
+            self._derived[key] = ent
+        return ent
+
+
+def xavier_limit(shape):
+    shape = list(shape)
+    if len(shape) == 1:
+        fan_in = fan_out = shape[0]
+    else:
+        rf = 1
+        for d in shape[:-2]:
+            rf *= d
+        fan_in, fan_out = shape[-2] * rf, shape[-1] * rf
+    return math.sqrt(6.0 / (fan_in + fan_out))
+
+
+VARIABLES = _VariableStore()
+
+
+def reset_variables(seed=1234):
+    """Start a fresh 'graph': forget all variables and re-seed the initializer."""
+    VARIABLES.reset(seed)
+
+
+def global_variables():
+    return VARIABLES.vars
+
+
+def _variable(name, shape, initializer=None, device="cuda"):
+    """reference :44-55 (tf.get_variable).  `initializer` is accepted for signature parity; the
+    reference only ever passes the Xavier initializer, which is what is used."""
+    return VARIABLES.get(name, shape, device)
+
+
+# --------------------------------------------------------------------------- nonlinearities
+def concat_elu(x):
+    """like concatenated ReLU (http://arxiv.org/abs/1603.05201), but then with ELU -- reference :14-17"""
+    return native.nonlinearity(native.to_bf16(x), native.PRO_CONCAT_ELU)
+
+
+def elu(x):
+    return native.nonlinearity(native.to_bf16(x), native.PRO_ELU)
+
+
+def concat_relu(x):
+    return native.nonlinearity(native.to_bf16(x), native.PRO_CONCAT_RELU)
+
+
+def relu(x):
+    return native.nonlinearity(native.to_bf16(x), native.PRO_RELU)
+
+
+_PROLOGUE_OF = {concat_elu: native.PRO_CONCAT_ELU, elu: native.PRO_ELU,
+                concat_relu: native.PRO_CONCAT_RELU, relu: native.PRO_RELU}
+
+
+def set_nonlinearity(name):
+    """reference :19-29"""
+    if name == 'concat_elu':
+        return concat_elu
+    elif name == 'elu':
+        return elu
+    elif name == 'concat_relu':
+        return concat_relu
+    elif name == 'relu':
+        return relu
+    else:
+        raise ValueError('nonlinearity ' + name + ' is not supported')
+
+
+def _pro_mult(pro):
+    return 2 if pro in (native.PRO_CONCAT_ELU, native.PRO_CONCAT_RELU) else 1
+
+
+# --------------------------------------------------------------------------- fused conv launcher
+def _conv_weights(scope, ksize, cin_eff, cout, device, skip_scope=None, kskip_eff=0, gated=False):
+    """bf16 GEMM-B images of a conv's variables (+ the nin it absorbs), cached per variable version."""
+    w = _variable(scope + '/weights', [ksize, ksize, cin_eff, cout], device=device)
+    b = _variable(scope + '/biases', [cout], device=device)
+    ws = bs = None
+    if skip_scope is not None:
+        ws = _variable(skip_scope + '/weights', [kskip_eff, cout], device=device)
+        bs = _variable(skip_scope + '/biases', [cout], device=device)
+
+    def make():
+        w16 = w.reshape(ksize * ksize, cin_eff, cout).to(torch.bfloat16).contiguous()
+        ws16 = ws.to(torch.bfloat16).contiguous() if ws is not None else None
+        bias = (b + bs).contiguous() if bs is not None else b.contiguous()
+        w_tc = None
+        if cin_eff % 16 == 0 and kskip_eff % 16 == 0:
+            w_tc = native.pack_conv_weights_tc(w16, ws16, ksize, cin_eff, kskip_eff, cout, gated)
+        return w16, ws16, bias, w_tc
+
+    return VARIABLES.derived(("conv", scope, skip_scope), make)
+
+
+def _fused_conv(x, scope, ksize, stride, cout, prologue, epilogue, skip=None, skip_scope=None, res=None,
+                res_pool=False, keep_prob=1.0, dropout_seed=0):
+    x = native.to_bf16(x)
+    B, H, W, cin = int_shape(x)
+    mult = _pro_mult(prologue)
+    kskip = 0
+    if skip is not None:
+        skip = native.to_bf16(skip)
+        kskip = skip.shape[3] * mult
+    gated = epilogue == native.EPI_GATE_RES
+    w16, ws16, bias, w_tc = _conv_weights(scope, ksize, cin * mult, cout, x.device, skip_scope, kskip, gated)
+    OH, OW = -(-H // stride), -(-W // stride)
+    cy = cout // 2 if gated else cout
+    y = torch.empty((B, OH, OW, cy), device=x.device,
+                    dtype=torch.float32 if epilogue == native.EPI_TANH else torch.bfloat16)
+    rec = None
+    if _PROFILE is not None:
+        nbytes = x.numel() * 2 + y.numel() * y.element_size()
+        nbytes += skip.numel() * 2 if skip is not None else 0
+        nbytes += res.numel() * 2 if res is not None else 0
+        flops = 2 * B * OH * OW * cout * (ksize * ksize * cin * mult + kskip)
+        rec = dict(name=scope, kind="conv", out_hw=(OH, OW), K_tap=cin * mult, N=cout, stride=stride,
+                   alg_bytes=nbytes, flops=flops)
+    _profiled(rec, lambda: native.conv_fwd(
+        x, w16, bias, y, B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize, stride=stride, prologue=prologue,
+        epilogue=epilogue, impl=IMPL, w_tc=w_tc, skip=skip, w_skip=ws16, res=res, res_pool=res_pool,
+        keep_prob=keep_prob, dropout_seed=dropout_seed))
+    return y
+
+
+# --------------------------------------------------------------------------- public layers
+def conv_layer(inputs, kernel_size, stride, num_features, idx, nonlinearity=None):
+    """reference :57-68 -- tf.nn.conv2d 'SAME' + bias_add (+ nonlinearity)"""
+    y = _fused_conv(inputs, '{0}_conv'.format(idx), kernel_size, stride, num_features, native.PRO_NONE,
+                    native.EPI_BIAS)
+    if nonlinearity is not None:
+        y = nonlinearity(y)
+    return y
+
+
+def transpose_conv_layer(inputs, kernel_size, stride, num_features, idx, nonlinearity=None):
+    """reference :70-87 -- tf.nn.conv2d_transpose 'SAME' + bias_add, output [B, sH, sW, num_features]"""
+    if kernel_size != 3 or stride != 2:
+        raise ValueError("transpose_conv_layer: only kernel_size=3, stride=2 (the reference's only use) is built")
+    x = native.to_bf16(inputs)
+    B, H, W, cin = int_shape(x)
+    scope = '{0}_trans_conv'.format(idx)
+    w = _variable(scope + '/weights', [kernel_size, kernel_size, num_features, cin], device=x.device)
+    b = _variable(scope + '/biases', [num_features], device=x.device)
+
+    def make():
+        # TF [kh,kw,Cout,Cin] -> GEMM-B [tap, Cin, Cout]
+        w16 = w.permute(0, 1, 3, 2).reshape(9, cin, num_features).to(torch.bfloat16).contiguous()
+        return w16, b.contiguous()
+
+    w16, bias = VARIABLES.derived(("tconv", scope), make)
+    y = torch.empty((B, 2 * H, 2 * W, num_features), device=x.device, dtype=torch.bfloat16)
+    rec = None
+    if _PROFILE is not None:
+        rec = dict(name=scope, kind="tconv", out_hw=(2 * H, 2 * W), K_tap=cin, N=num_features, stride=2,
+                   alg_bytes=(x.numel() + y.numel()) * 2, flops=2 * B * H * W * 9 * cin * num_features)
+    _profiled(rec, lambda: native.tconv_fwd(x, w16, bias, y, B=B, H=H, W=W, Cin=cin, Cout=num_features, impl=IMPL))
+    if nonlinearity is not None:
+        y = nonlinearity(y)
+    return y
+
+
+def fc_layer(inputs, hiddens, idx, nonlinearity=None, flat=False):
+    """reference :89-104 -- matmul + bias on [rows, dim].  (The reference's flat=True and
+    nonlinearity branches are dead/buggy, :92-94,:102-103; flat is honoured, nonlinearity applied.)"""
+    x = native.to_bf16(inputs)
+    if flat:
+        x = x.reshape(x.shape[0], -1)
+    rows, dim = x.shape
+    scope = '{0}_fc'.format(idx)
+    # run it as a 1x1 convolution over a [1, rows, 1, dim] image; the variable keeps TF's [dim, hiddens] shape
+    w = _variable(scope + '/weights', [dim, hiddens], device=x.device)
+    b = _variable(scope + '/biases', [hiddens], device=x.device)
+
+    def make():
+        return w.reshape(1, dim, hiddens).to(torch.bfloat16).contiguous(), b.contiguous()
+
+    w16, bias = VARIABLES.derived(("fc", scope), make)
+    y = torch.empty((1, rows, 1, hiddens), device=x.device, dtype=torch.bfloat16)
+    native.conv_fwd(x.reshape(1, rows, 1, dim), w16, bias, y, B=1, H=rows, W=1, Cin=dim, Cout=hiddens, ksize=1,
+                    stride=1, prologue=native.PRO_NONE, epilogue=native.EPI_BIAS, impl=native.IMPL_SIMT)
+    y = y.reshape(rows, hiddens)
+    if nonlinearity is not None:
+        y = nonlinearity(y)
+    return y
+
+
+def nin(x, num_units, idx):
+    """ a network in network layer (1x1 CONV) -- reference :106-111 """
+    s = int_shape(x)
+    x = x.reshape([int(np.prod(s[:-1])), s[-1]])
+    x = fc_layer(x, num_units, idx)
+    return x.reshape(s[:-1] + [num_units])
+
+
+def res_block(x, a=None, filter_size=16, nonlinearity=concat_elu, keep_p=1.0, stride=1, gated=False,
+              name="resnet", dropout_seed=0):
+    """reference :129-165.  Two fused launches (see module docstring)."""
+    pro = _PROLOGUE_OF.get(nonlinearity)
+    if pro is None:
+        return _res_block_unfused(x, a, filter_size, nonlinearity, keep_p, stride, gated, name)
+    orig_x = native.to_bf16(x)
+    cin = orig_x.shape[3]
+    if a is not None and cin == 1:
+        raise ValueError("res_block: a skip input on a 1-channel block is not supported")
+    x_1 = _fused_conv(orig_x, name + '_conv_1_conv', 3, stride, filter_size,
+                      native.PRO_NONE if cin == 1 else pro, native.EPI_BIAS,
+                      skip=a, skip_scope=(name + '_nin_fc') if a is not None else None)
+    pooled = orig_x.shape[2] > x_1.shape[2]
+    return _fused_conv(x_1, name + '_conv_2_conv', 3, 1, filter_size * (2 if gated else 1), pro,
+                       native.EPI_GATE_RES if gated else native.EPI_RES, res=orig_x, res_pool=pooled,
+                       keep_prob=keep_p, dropout_seed=dropout_seed)
+
+
+def _res_block_unfused(x, a, filter_size, nonlinearity, keep_p, stride, gated, name):
+    raise ValueError("res_block: only the reference's four nonlinearities (set_nonlinearity) are supported")
+
+
+def conv_res(inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name='concat_elu', gated=True, filter_size=8,
+             dropout_seed=0):
+    """Builds conv part of net -- reference :167-248.
+    Args:
+      inputs: boundary images [B,H,W,1] (uint8 / float32 / bfloat16, CUDA)
+      keep_prob: dropout keep probability (1.0 = inference)
+      filter_size: base width; hard-coded to 8 in the reference (:174), exposed for wider variants
+    Returns: [B,H,W,2] float32 velocity field in (-1, 1)
+    """
+    nonlinearity = set_nonlinearity(nonlinearity_name)
+    seed = [int(dropout_seed)]
+
+    def block(x, a=None, stride=1, name=""):
+        seed[0] += 1
+        return res_block(x, a=a, filter_size=filter_size, nonlinearity=nonlinearity, keep_p=keep_prob, stride=stride,
+                         gated=gated, name=name, dropout_seed=seed[0])
+
+    # store for as
+    a = []
+    # res_1
+    x = native.to_bf16(inputs)
+    for i in range(nr_res_blocks):
+        x = block(x, name="resnet_1_" + str(i))
+    # res_2 .. res_5
+    for lvl in (2, 3, 4, 5):
+        a.append(x)
+        filter_size = 2 * filter_size
+        x = block(x, stride=2, name="resnet_%d_downsample" % lvl)
+        for i in range(nr_res_blocks):
+            x = block(x, name="resnet_%d_%d" % (lvl, i))
+    # res_up_1 .. res_up_4
+    for k in (1, 2, 3, 4):
+        filter_size = int(filter_size / 2)
+        x = transpose_conv_layer(x, 3, 2, filter_size, "up_conv_%d" % k)
+        for i in range(nr_res_blocks):
+            x = block(x, a=a[-k] if i == 0 else None, name="resnet_up_%d_%d" % (k, i))
+    # last_conv + tanh (reference :242-243), one launch
+    return _fused_conv(x, 'last_conv_conv', 3, 1, 2, native.PRO_NONE, native.EPI_TANH)

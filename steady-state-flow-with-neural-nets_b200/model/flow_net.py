@@ -1,0 +1,104 @@
+"""Builds the flow network -- B200-native facade with the reference's surface
+(/root/reference/model/flow_net.py): flags `model`, `nr_res_blocks`, `gated_res`, `nonlinearity`
+(:20-27) and functions inputs() :29, inference() :33, loss_image() :39, train() :44.
+
+Tensors are CUDA torch tensors, NHWC: boundary [B,H,W,1] (uint8 / float32 / bfloat16, values {0,1}),
+velocity field [B,H,W,2] float32.  All arithmetic runs in libflownet.so (sm_100a); there is no
+CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+import flownet_native as native
+import model.flow_architecture as flow_architecture
+from model import flags
+from model.flags import FLAGS
+
+# Constants describing the training process (reference :20-27)
+flags.DEFINE_string('model', 'res', """ model name to train """)
+flags.DEFINE_integer('nr_res_blocks', 1, """ nr res blocks """)
+flags.DEFINE_bool('gated_res', True, """ gated resnet or not """)
+flags.DEFINE_string('nonlinearity', 'concat_elu',
+                    """ nonlinearity used such as concat_elu, elu, concat_relu, relu """)
+# extension: base filter count, hard-coded to 8 in the reference (flow_architecture.py:174)
+flags.DEFINE_integer('filter_size', 8, """ base number of filters (reference: 8) """)
+
+
+def inputs(batch_size, shape=(128, 256), seed=0, device="cuda"):
+    """reference :29-31 returns a (boundary, sflow) batch from the TFRecord queue.  The dataset is
+    not shipped (and there is no network), so this yields the synthetic stand-in of the same shapes:
+    boundary uint8 [B,H,W,1], sflow float32 [B,H,W,2]."""
+    from utils.synthetic import synth_boundary, synth_sflow
+    b = synth_boundary(batch_size, shape[0], shape[1], seed=seed)
+    s = synth_sflow(b)
+    return torch.from_numpy(b).to(device), torch.from_numpy(s).to(device)
+
+
+def _to_device(boundary):
+    if isinstance(boundary, np.ndarray):
+        boundary = torch.from_numpy(boundary)
+    if not boundary.is_cuda:
+        boundary = boundary.cuda(non_blocking=True)
+    return boundary
+
+
+def inference(boundary, keep_prob, dropout_seed=0):
+    """reference :33-37.  boundary: [B,H,W,1]; returns sflow_p [B,H,W,2] float32 (tanh range)."""
+    if FLAGS.model == "res":
+        sflow_p = flow_architecture.conv_res(_to_device(boundary), nr_res_blocks=FLAGS.nr_res_blocks,
+                                             keep_prob=keep_prob, nonlinearity_name=FLAGS.nonlinearity,
+                                             gated=FLAGS.gated_res, filter_size=FLAGS.filter_size,
+                                             dropout_seed=dropout_seed)
+    else:
+        # the reference falls through to an UnboundLocalError here (:34-37); say what is wrong instead
+        raise ValueError("FLAGS.model=%r: only 'res' exists" % (FLAGS.model,))
+    return sflow_p
+
+
+def loss_image(sflow_p, sflow):
+    """reference :39-42: tf.nn.l2_loss(sflow_p - sflow) = sum((p-t)^2)/2 -> float32 [1] on the device."""
+    loss, _ = native.l2_loss(sflow_p, sflow, want_grad=False)
+    return loss
+
+
+class CompiledInference:
+    """inference() for a fixed (B,H,W), captured once into a CUDA graph and replayed: the ~31 fused
+    kernels of one forward are launch-bound at small batch (hard part 5).
+
+    call(boundary) copies the batch into the static input buffer, replays, and returns the static
+    float32 output buffer (valid until the next call)."""
+
+    def __init__(self, batch_size, shape=(128, 256), keep_prob=1.0, in_dtype=torch.uint8):
+        self.B, (self.H, self.W) = batch_size, shape
+        self.keep_prob = keep_prob
+        self.static_in = torch.zeros((batch_size, shape[0], shape[1], 1), dtype=in_dtype, device="cuda")
+        # warm-up on a side stream (creates variables, packs weights, sizes the allocator pool)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                inference(self.static_in, keep_prob)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = native.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.static_out = inference(self.static_in, keep_prob)
+        self.launches_per_replay = native.launch_count() - n0
+
+    def __call__(self, boundary):
+        self.static_in.copy_(boundary, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+    def replay(self):
+        self.graph.replay()
+        return self.static_out
+
+
+def train(total_loss, lr):
+    """reference :44-46 builds AdamOptimizer(lr).minimize(total_loss).  The B200 training step
+    (backward kernels + flat fused Adam + NCCL all-reduce) lives in model/flow_train_step.py."""
+    raise NotImplementedError("training step: see model/flow_train_step.py (not built in this round)")

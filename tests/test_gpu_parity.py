@@ -1,0 +1,350 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test calls the CUDA path through
+the C ABI (ctypes -> libflownet.so) and compares with the CPU oracle on the same seeded inputs.
+
+Tolerances: whole-net output rel-L2 <= 1e-2 for the bf16-storage /
+fp32-accumulate path vs the fp64 oracle; one fused layer <= 4e-3 when both sides see the same
+bf16-rounded inputs and weights; fp32 elementwise kernels <= 1e-6.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flow_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+LAYER_TOL = 4e-3
+NET_TOL = 1e-2
+
+
+def rel_l2(a, b):
+    a = a.double().cpu()
+    b = b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def native(built_lib):
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    return built_lib
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float64)
+
+
+PRO_FN = {0: lambda x: x, 1: fo.concat_elu, 2: fo.elu, 3: fo.concat_relu, 4: torch.relu}
+
+
+def oracle_fused_conv(x, w, b, stride, pro, epi, skip=None, ws=None, res=None, res_pool=False):
+    """fp64 restatement of one fn_conv_fwd launch on bf16-rounded operands."""
+    f = PRO_FN[pro]
+    a = bf16_round(f(x)) if pro != 0 else x
+    acc = fo.conv2d_same(a, w, stride)
+    if skip is not None:
+        sp = torch.zeros(acc.shape[:3] + (skip.shape[3],), dtype=torch.float64)
+        sp[:, :skip.shape[1], :skip.shape[2], :] = skip
+        acc = acc + bf16_round(f(sp)) @ ws
+    acc = acc + b
+    if epi == 0:
+        return acc
+    if epi == 3:
+        return torch.tanh(acc)
+    F_ = acc.shape[3] // 2 if epi == 1 else acc.shape[3]
+    out = acc[..., :F_] * torch.sigmoid(acc[..., F_:]) if epi == 1 else acc
+    if res is not None:
+        r = fo.avg_pool_2x2_same(res) if res_pool else res
+        if r.shape[3] != F_:
+            r = torch.nn.functional.pad(r, (F_ - r.shape[3], 0))
+        out = out + r
+    return out
+
+
+def run_fused_conv(native, impl, B, H, W, Cin, Cout, stride, pro, epi, with_skip=False, Cres=None, res_pool=False,
+                   seed=0, ksize=3):
+    g = torch.Generator().manual_seed(seed)
+    mult = 2 if pro in (1, 3) else 1
+    x = bf16_round(torch.randn(B, H, W, Cin, generator=g, dtype=torch.float64))
+    lim = (6.0 / (ksize * ksize * (Cin * mult + Cout))) ** 0.5
+    w = bf16_round((torch.rand(ksize, ksize, Cin * mult, Cout, generator=g, dtype=torch.float64) * 2 - 1) * lim * 2)
+    b = (torch.rand(Cout, generator=g, dtype=torch.float64) * 2 - 1).float().double()
+    OH, OW = -(-H // stride), -(-W // stride)
+    skip = ws = res = None
+    if with_skip:
+        Cs = Cin
+        skip = bf16_round(torch.randn(B, OH, OW, Cs, generator=g, dtype=torch.float64))
+        ws = bf16_round((torch.rand(Cs * mult, Cout, generator=g, dtype=torch.float64) * 2 - 1) * 0.3)
+    F_ = Cout // 2 if epi == 1 else Cout
+    if epi in (1, 2):
+        Cres = F_ if Cres is None else Cres
+        RH, RW = (2 * OH, 2 * OW) if res_pool else (OH, OW)
+        res = bf16_round(torch.randn(B, RH, RW, Cres, generator=g, dtype=torch.float64))
+    ref = oracle_fused_conv(x, w, b, stride, pro, epi, skip, ws, res, res_pool)
+
+    dev = "cuda"
+    xd = x.to(dev, torch.bfloat16)
+    w16 = w.reshape(ksize * ksize, Cin * mult, Cout).to(dev, torch.bfloat16).contiguous()
+    ws16 = ws.to(dev, torch.bfloat16).contiguous() if ws is not None else None
+    bd = b.to(dev, torch.float32)
+    w_tc = None
+    if (Cin * mult) % 16 == 0:
+        w_tc = native.pack_conv_weights_tc(w16, ws16, ksize, Cin * mult, (skip.shape[3] * mult) if with_skip else 0,
+                                           Cout, epi == 1)
+    y = torch.empty((B, OH, OW, F_), device=dev, dtype=torch.float32 if epi == 3 else torch.bfloat16)
+    native.conv_fwd(xd, w16, bd, y, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=ksize, stride=stride, prologue=pro,
+                    epilogue=epi, impl=impl, w_tc=w_tc,
+                    skip=skip.to(dev, torch.bfloat16) if with_skip else None, w_skip=ws16,
+                    res=res.to(dev, torch.bfloat16) if res is not None else None, res_pool=res_pool)
+    torch.cuda.synchronize()
+    assert native.tc_status() == 0
+    return y, ref
+
+
+# (name, B,H,W,Cin,Cout,stride,pro,epi,skip,Cres,pool) -- the layer shapes of SURVEY App. A, scaled down
+SIMT_CASES = [
+    ("head_c1", 2, 16, 32, 1, 8, 1, 0, 0, False, None, False),
+    ("conv1_ce", 2, 16, 32, 8, 8, 1, 1, 0, False, None, False),
+    ("conv2_gate", 2, 16, 32, 8, 16, 1, 1, 1, False, None, False),
+    ("conv2_gate_head_res", 2, 16, 32, 8, 16, 1, 1, 1, False, 1, False),
+    ("down_conv1_s2", 2, 16, 32, 8, 16, 2, 1, 0, False, None, False),
+    ("down_conv1_s2_odd", 1, 15, 21, 8, 16, 2, 1, 0, False, None, False),
+    ("down_conv2_gate_pool_pad", 2, 8, 16, 16, 32, 1, 1, 1, False, 8, True),
+    ("up_conv1_skip", 2, 16, 32, 16, 16, 1, 1, 0, True, None, False),
+    ("deep_gate", 1, 8, 16, 64, 128, 1, 1, 1, False, None, False),
+    ("tail_tanh", 2, 16, 32, 8, 2, 1, 0, 3, False, None, False),
+    ("elu_res_ungated", 1, 16, 16, 16, 16, 1, 2, 2, False, None, False),
+    ("crelu_gate", 1, 16, 16, 8, 16, 1, 3, 1, False, None, False),
+    ("relu_bias", 1, 16, 16, 16, 8, 1, 4, 0, False, None, False),
+    ("nin_1x1", 1, 16, 16, 16, 8, 1, 0, 0, False, None, False),
+]
+
+
+@pytest.mark.parametrize("case", SIMT_CASES, ids=[c[0] for c in SIMT_CASES])
+def test_fused_conv_simt_vs_oracle(native, case):
+    name, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool = case
+    k = 1 if name == "nin_1x1" else 3
+    y, ref = run_fused_conv(native, native.IMPL_SIMT, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool, ksize=k)
+    assert rel_l2(y, ref) < LAYER_TOL
+
+
+TC_CASES = [
+    # name, B,H,W,Cin,Cout,stride,pro,epi,skip,Cres,pool
+    ("conv1_ce_k16_n16", 2, 16, 32, 8, 16, 1, 1, 0, False, None, False),
+    ("conv1_ce_n8_padded", 2, 16, 32, 8, 8, 1, 1, 0, False, None, False),
+    ("conv2_gate_f8", 2, 16, 32, 8, 16, 1, 1, 1, False, None, False),
+    ("conv2_gate_head_res", 2, 16, 32, 8, 16, 1, 1, 1, False, 1, False),
+    ("conv2_gate_pool_pad", 2, 16, 16, 16, 32, 1, 1, 1, False, 8, True),
+    ("conv1_skip_nin", 2, 16, 32, 16, 16, 1, 1, 0, True, None, False),
+    ("wide_J4", 1, 32, 64, 8, 16, 1, 1, 1, False, None, False),
+    ("ragged_edges", 1, 20, 28, 8, 16, 1, 1, 0, False, None, False),
+    ("transposed_8x16", 3, 8, 16, 32, 64, 1, 1, 1, False, None, False),
+    ("deep_c64_n128_ring", 2, 16, 16, 64, 128, 1, 1, 1, False, None, False),
+    ("deep_c128_n256_ring", 1, 8, 16, 128, 256, 1, 1, 1, False, None, False),
+    ("deep_c128_n128_skip", 1, 16, 16, 64, 64, 1, 1, 0, True, None, False),
+    ("elu_k16", 1, 16, 16, 16, 16, 1, 2, 2, False, None, False),
+    ("crelu_gate", 1, 16, 16, 8, 16, 1, 3, 1, False, None, False),
+    ("raw_k16", 1, 16, 16, 16, 16, 1, 0, 0, False, None, False),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_fused_conv_tcgen05_vs_oracle(native, case):
+    name, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool = case
+    y, ref = run_fused_conv(native, native.IMPL_TCGEN05, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool)
+    assert native.last_used_tcgen05()
+    assert rel_l2(y, ref) < LAYER_TOL
+
+
+def test_tcgen05_refuses_shapes_it_has_no_kernel_for(native):
+    with pytest.raises(ValueError):
+        run_fused_conv(native, native.IMPL_TCGEN05, 1, 16, 16, 1, 8, 1, 0, 0)     # K = 9: CUDA-core layer
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 8, 16, 16, 8), (1, 4, 8, 128, 64), (2, 5, 7, 8, 8)])
+def test_transposed_conv_vs_oracle(native, B, H, W, Cin, Cout):
+    g = torch.Generator().manual_seed(1)
+    x = bf16_round(torch.randn(B, H, W, Cin, generator=g, dtype=torch.float64))
+    w = bf16_round((torch.rand(3, 3, Cout, Cin, generator=g, dtype=torch.float64) * 2 - 1) * 0.2)
+    b = torch.rand(Cout, generator=g, dtype=torch.float64).float().double()
+    ref = fo.conv2d_transpose_same(x, w, 2) + b
+    w16 = w.permute(0, 1, 3, 2).reshape(9, Cin, Cout).to("cuda", torch.bfloat16).contiguous()
+    y = torch.empty((B, 2 * H, 2 * W, Cout), device="cuda", dtype=torch.bfloat16)
+    native.tconv_fwd(x.to("cuda", torch.bfloat16), w16, b.to("cuda", torch.float32), y, B=B, H=H, W=W, Cin=Cin,
+                     Cout=Cout)
+    torch.cuda.synchronize()
+    assert rel_l2(y, ref) < LAYER_TOL
+
+
+# ------------------------------------------------------------------------------- whole network
+def _net(native, x_np, impl, **flags):
+    import model.flow_architecture as arch
+    import model.flow_net as flow_net
+    arch.reset_variables(1234)
+    arch.set_impl(impl)
+    old = {k: getattr(flow_net.FLAGS, k) for k in flags}
+    try:
+        for k, v in flags.items():
+            setattr(flow_net.FLAGS, k, v)
+        y = flow_net.inference(torch.from_numpy(x_np).cuda(), 1.0)
+        torch.cuda.synchronize()
+        assert native.tc_status() == 0
+        return y
+    finally:
+        for k, v in old.items():
+            setattr(flow_net.FLAGS, k, v)
+        arch.set_impl("auto")
+
+
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_net_vs_golden_tiny(native, golden_dir, impl):
+    z = np.load(os.path.join(golden_dir, "golden_tiny.npz"))
+    y = _net(native, z["x"], impl)
+    assert y.dtype == torch.float32 and tuple(y.shape) == z["y"].shape
+    assert rel_l2(y, torch.from_numpy(z["y"])) < NET_TOL
+    y2 = _net(native, z["x2"], impl)
+    assert rel_l2(y2, torch.from_numpy(z["y2"])) < NET_TOL
+
+
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_net_vs_golden_cars(native, golden_dir, impl):
+    from utils.synthetic import load_car_boundaries
+    z = np.load(os.path.join(golden_dir, "golden_cars.npz"))
+    cars = load_car_boundaries(os.path.join(golden_dir, "cars_128x256.npz"))
+    y = _net(native, cars[list(z["idx"])], impl)
+    e = rel_l2(y, torch.from_numpy(z["y"]))
+    assert e < NET_TOL, e
+    assert (y.cpu() - torch.from_numpy(z["y"])).abs().max().item() < 6e-2
+
+
+def test_net_variables_match_reference_inventory(native):
+    import model.flow_architecture as arch
+    _net(native, fo.synth_boundary(1, 16, 32).astype(np.uint8), "auto")
+    vs = fo.VariableStore(1234, torch.float32)
+    fo.inference(vs, torch.zeros(1, 16, 32, 1), 1.0)
+    gv = arch.global_variables()
+    assert list(gv) == list(vs.vars)
+    assert sum(v.numel() for v in gv.values()) == 2_561_386
+    for k in vs.vars:
+        assert torch.equal(gv[k].cpu(), vs.vars[k]), k
+
+
+def test_net_nondefault_flags(native):
+    """nr_res_blocks=2 + wider filters (BASELINE config 5), and the other nonlinearities / ungated blocks."""
+    x = fo.synth_boundary(1, 32, 64, seed=2)
+    for flags in (dict(nr_res_blocks=2, filter_size=16), dict(nonlinearity="elu"), dict(nonlinearity="concat_relu"),
+                  dict(nonlinearity="relu", gated_res=False)):
+        y = _net(native, x.astype(np.uint8), "auto", **flags)
+        vs = fo.VariableStore(1234, torch.float64)
+        ref = fo.inference(vs, torch.from_numpy(x).double(), 1.0, nr_res_blocks=flags.get("nr_res_blocks", 1),
+                           nonlinearity=flags.get("nonlinearity", "concat_elu"),
+                           gated_res=flags.get("gated_res", True), filter_size=flags.get("filter_size", 8))
+        assert rel_l2(y, ref) < NET_TOL, flags
+
+
+def test_net_input_dtypes_and_zero_input(native):
+    """uint8 / float32 / bf16 boundaries give identical results; the reference's speed test feeds zeros."""
+    x = fo.synth_boundary(2, 32, 64, seed=1)
+    y8 = _net(native, x.astype(np.uint8), "auto")
+    y32 = _net(native, x.astype(np.float32), "auto")
+    assert torch.equal(y8, y32)
+    z = _net(native, np.zeros((1, 32, 64, 1), np.float32), "auto")
+    vs = fo.VariableStore(1234, torch.float64)
+    ref = fo.inference(vs, torch.zeros(1, 32, 64, 1, dtype=torch.float64), 1.0)
+    assert rel_l2(z, ref) < NET_TOL
+
+
+def test_full_size_properties(native, golden_dir):
+    """BASELINE config 2 at full size (28 cars tiled to batch 64, 128x256): determinism, batch-position
+    independence, and the tcgen05 path against the CUDA-core path on the same device."""
+    from utils.synthetic import load_car_boundaries
+    cars = load_car_boundaries(os.path.join(golden_dir, "cars_128x256.npz"))
+    idx = [i % 28 for i in range(64)]
+    x = cars[idx]
+    y1 = _net(native, x, "auto")
+    y2 = _net(native, x, "auto")
+    assert torch.equal(y1, y2)                                   # run-to-run bit-exact
+    assert torch.equal(y1[0], y1[28]) and torch.equal(y1[5], y1[61])   # same car, different batch slot
+    perm = torch.randperm(64, generator=torch.Generator().manual_seed(0))
+    yp = _net(native, x[perm.numpy()], "auto")
+    assert torch.equal(yp, y1[perm.cuda()])                      # images are independent
+    ys = _net(native, x[:8], "simt")
+    assert rel_l2(y1[:8], ys) < 5e-3
+    assert torch.isfinite(y1).all() and y1.abs().max().item() < 1.0
+
+
+def test_high_res_512x1024(native):
+    """BASELINE config 4 shape (one image): fully convolutional, tcgen05 vs CUDA-core agree."""
+    x = fo.synth_boundary(1, 512, 1024, seed=0).astype(np.uint8)
+    ya = _net(native, x, "auto")
+    ys = _net(native, x, "simt")
+    assert tuple(ya.shape) == (1, 512, 1024, 2)
+    assert rel_l2(ya, ys) < 5e-3
+
+
+def test_compiled_inference_graph_matches_eager(native):
+    import model.flow_architecture as arch
+    import model.flow_net as flow_net
+    arch.reset_variables(1234)
+    x = torch.from_numpy(fo.synth_boundary(4, 32, 64, seed=4).astype(np.uint8)).cuda()
+    ye = flow_net.inference(x, 1.0).clone()
+    ci = flow_net.CompiledInference(4, (32, 64))
+    yg = ci(x)
+    torch.cuda.synchronize()
+    assert torch.equal(ye, yg)
+    assert ci.launches_per_replay >= 31
+
+
+# ------------------------------------------------------------------------------- small kernels
+def test_nonlinearity_kernels(native):
+    g = torch.Generator().manual_seed(0)
+    for C in (8, 16, 3):
+        x = torch.randn(5, 7, C, generator=g).to(torch.bfloat16)
+        for kind, f in ((1, fo.concat_elu), (2, fo.elu), (3, fo.concat_relu), (4, torch.relu)):
+            y = native.nonlinearity(x.cuda(), kind)
+            ref = f(x.double())
+            assert tuple(y.shape) == tuple(ref.shape)
+            assert rel_l2(y, ref) < 3e-3
+
+
+def test_casts(native):
+    x = torch.rand(1000) * 4 - 2
+    y = native.to_bf16(x.cuda())
+    assert torch.equal(y.cpu(), x.to(torch.bfloat16))
+    assert torch.equal(native.to_f32(y).cpu(), x.to(torch.bfloat16).float())
+    u = (torch.rand(999) > 0.5).to(torch.uint8)
+    assert torch.equal(native.to_bf16(u.cuda()).cpu().float(), u.float())
+
+
+def test_l2_loss_kernel(native):
+    g = torch.Generator().manual_seed(0)
+    p = torch.randn(2, 32, 64, 2, generator=g)
+    t = torch.randn(2, 32, 64, 2, generator=g)
+    loss, grad = native.l2_loss(p.cuda(), t.cuda(), want_grad=True)
+    ref = fo.loss_image(p.double(), t.double())
+    assert abs(loss.item() - ref.item()) < 1e-5 * ref.item()
+    assert torch.equal(grad.cpu(), p - t)
+    assert torch.equal(native.l2_loss(p.cuda(), p.cuda())[0].cpu(), torch.zeros(1))
+    e = torch.empty(0, device="cuda")
+    assert native.l2_loss(e, e)[0].item() == 0.0                  # empty input
+
+
+def test_adam_kernel_matches_tf1_update(native):
+    g = torch.Generator().manual_seed(0)
+    n = 100_003
+    p0 = torch.randn(n, generator=g)
+    m0 = torch.zeros(n)
+    v0 = torch.zeros(n)
+    pd, md, vd = p0.cuda().clone(), m0.cuda(), v0.cuda()
+    po = {"a": p0.double().clone()}
+    mo = {"a": m0.double().clone()}
+    vo = {"a": v0.double().clone()}
+    for step in (1, 2, 3):
+        gr = torch.randn(n, generator=g)
+        native.adam_step(pd, gr.cuda(), md, vd, step)
+        fo.adam_step_tf1(po, {"a": gr.double()}, mo, vo, t=step)
+    torch.cuda.synchronize()
+    assert (pd.cpu().double() - po["a"]).abs().max().item() < 1e-6
+    assert rel_l2(md, mo["a"]) < 1e-6 and rel_l2(vd, vo["a"]) < 1e-6

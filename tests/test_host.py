@@ -1,0 +1,96 @@
+"""CPU-side tests of the host logic: the C-ABI library builds, loads and exports every symbol
+include/flownet.h declares (no compute calls -- there is no GPU here), the ctypes structs match the
+C layout, argument validation answers without touching the device, and the product's variable
+store / synthetic inputs follow the same conventions as the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flow_oracle as fo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "flownet.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(fn_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    bound = {n for n, _, _ in built_lib.SYMBOLS}
+    assert declared == bound, (declared ^ bound)
+    raw = C.CDLL(built_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+
+
+def test_abi_version_and_struct_sizes(built_lib):
+    assert built_lib.lib.fn_abi_version() == built_lib.FN_ABI_VERSION
+    assert built_lib.lib.fn_sizeof_conv_desc() == C.sizeof(built_lib.ConvDesc)
+    assert built_lib.lib.fn_sizeof_tconv_desc() == C.sizeof(built_lib.TConvDesc)
+
+
+def test_validation_errors_without_device(built_lib):
+    lib = built_lib.lib
+    assert lib.fn_conv_fwd(None, None) == -1
+    assert b"null descriptor" in lib.fn_last_error()
+    d = built_lib.ConvDesc()
+    assert lib.fn_conv_fwd(C.byref(d), None) == -1          # non-positive dims
+    d.B, d.H, d.W, d.Cin, d.Cout, d.ksize, d.stride = 1, 8, 8, 12, 8, 3, 1
+    d.x = d.w = d.bias = d.y = 4096
+    assert lib.fn_conv_fwd(C.byref(d), None) == -3          # Cin not 1 / multiple of 8
+    d.Cin, d.ksize = 8, 5
+    assert lib.fn_conv_fwd(C.byref(d), None) == -2          # unsupported kernel size
+    d.ksize, d.x = 3, 4097
+    assert lib.fn_conv_fwd(C.byref(d), None) == -3          # misaligned pointer
+    assert lib.fn_tconv_fwd(None, None) == -1
+    assert lib.fn_adam_step(None, None, None, None, 1, 1, 1e-4, 0.9, 0.999, 1e-8, None) == -1
+    assert lib.fn_l2_loss(None, None, None, None, 4, None) == -1
+
+
+def test_cpu_tensors_are_rejected_not_silently_computed(built_lib):
+    with pytest.raises(ValueError):
+        built_lib.to_bf16(torch.zeros(4, 8))
+    with pytest.raises(ValueError):
+        built_lib.l2_loss(torch.zeros(4), torch.zeros(4))
+
+
+def test_tc_weight_image_size(built_lib):
+    lib = built_lib.lib
+    # r1_0.conv_2: 3x3, Keff=16, N=16 -> 9 k-steps * 16 * 32 B
+    assert lib.fn_conv_weights_tc_bytes(3, 16, 0, 16, 1) == 9 * 16 * 32
+    # ru4_0.conv_1 + nin: Cout=8 padded to N=16, 9 + 1 k-steps
+    assert lib.fn_conv_weights_tc_bytes(3, 16, 16, 8, 0) == 10 * 16 * 32
+    assert lib.fn_conv_weights_tc_bytes(3, 8, 0, 8, 0) == 0     # K not a multiple of 16: no tcgen05 image
+
+
+def test_product_variable_store_matches_oracle_convention(built_lib):
+    import model.flow_architecture as arch
+    vs = fo.VariableStore(1234, torch.float32)
+    fo.inference(vs, torch.zeros(1, 16, 32, 1), 1.0)
+    arch.reset_variables(1234)
+    for name, v in vs.vars.items():
+        pv = arch._variable(name, list(v.shape), device="cpu")
+        assert torch.equal(pv, v), name
+    assert list(arch.global_variables()) == list(vs.vars)
+    arch.reset_variables(1234)
+
+
+def test_product_synthetic_inputs_match_oracle(built_lib):
+    from utils.synthetic import synth_boundary
+    for (B, H, W, seed) in [(2, 128, 256, 0), (1, 16, 32, 0), (2, 32, 48, 5)]:
+        np.testing.assert_array_equal(synth_boundary(B, H, W, seed)[..., 0],
+                                      fo.synth_boundary(B, H, W, seed)[..., 0].astype(np.uint8))
+
+
+def test_flags_defaults_match_reference(built_lib):
+    import model.flow_net as flow_net
+    F = flow_net.FLAGS
+    assert (F.model, F.nr_res_blocks, F.gated_res, F.nonlinearity) == ("res", 1, True, "concat_elu")
+    import model.flow_architecture as arch
+    with pytest.raises(ValueError):
+        arch.set_nonlinearity("swish")
+    assert arch.set_nonlinearity("concat_elu") is arch.concat_elu
