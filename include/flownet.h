@@ -144,7 +144,7 @@ int fn_l2_loss(const float* p, const float* t, float* loss, float* grad, int64_t
 /* tf.train.AdamOptimizer.apply (TF1 ApplyAdam)           flow_net.py:44-46; SURVEY App. B.10
  * flat fp32 buffers of n elements; step is the 1-based step count */
 int fn_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, int64_t step,
-                 float lr, float beta1, float beta2, float eps, void* stream);
+                 double lr, double beta1, double beta2, double eps, void* stream);
 
 #ifdef __cplusplus
 }

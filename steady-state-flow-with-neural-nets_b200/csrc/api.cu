@@ -43,8 +43,8 @@ int nonlinearity(const void* x, void* y, long long n, int C, int kind, cudaStrea
 template <typename TI, typename TO>
 int cast(const TI* x, TO* y, long long n, cudaStream_t s);
 int l2_loss(const float* p, const float* t, float* loss, float* grad, long long n, cudaStream_t s);
-int adam_step(float* param, const float* grad, float* m, float* v, long long n, long long step, float lr, float b1,
-              float b2, float eps, cudaStream_t s);
+int adam_step(float* param, const float* grad, float* m, float* v, long long n, long long step, double lr, double b1,
+              double b2, double eps, cudaStream_t s);
 
 static int validate_conv(const fn_conv_desc& d) {
   FN_REQUIRE(d.B > 0 && d.H > 0 && d.W > 0 && d.Cin > 0 && d.Cout > 0, FN_E_INVAL,
@@ -158,12 +158,12 @@ int fn_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
 }
 
 int fn_l2_loss(const float* p, const float* t, float* loss, float* grad, int64_t n, void* stream) {
-  FN_REQUIRE(p && t && loss && n >= 0, FN_E_INVAL, "fn_l2_loss: bad arguments");
+  FN_REQUIRE(loss && n >= 0 && ((p && t) || n == 0), FN_E_INVAL, "fn_l2_loss: bad arguments");
   return l2_loss(p, t, loss, grad, n, (cudaStream_t)stream);
 }
 
-int fn_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, int64_t step, float lr, float beta1,
-                 float beta2, float eps, void* stream) {
+int fn_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, int64_t step, double lr, double beta1,
+                 double beta2, double eps, void* stream) {
   FN_REQUIRE(param && grad && m && v && n >= 0 && step >= 1, FN_E_INVAL, "fn_adam_step: bad arguments");
   return adam_step(param, grad, m, v, n, step, lr, beta1, beta2, eps, (cudaStream_t)stream);
 }

@@ -20,56 +20,42 @@ struct ConvParams {
   int slots;   // output channels written (gated: Cout/2)
 };
 
-// accumulate one tap's K range for this thread's pixel
+// accumulate raw channels [c0, c0+CR) of one tap for this thread's pixel; wsm holds the matching
+// weight rows as [r][NACC], r < CR for the first prologue output and CR + r for the second (concat)
 template <int NACC>
-__device__ __forceinline__ void accumulate_pixel(const __nv_bfloat16* __restrict__ px, int Craw, int pro,
+__device__ __forceinline__ void accumulate_pixel(const __nv_bfloat16* __restrict__ px, int Craw, int c0, int CR, int pro,
                                                  const float* __restrict__ wsm, float (&acc)[NACC],
                                                  bool drop, uint64_t seed, uint64_t base_idx, float keep) {
   const int mult = pro_mult(pro);
-  if ((Craw & 7) == 0) {
-    for (int c8 = 0; c8 < Craw; c8 += 8) {
-      bf16x8 raw;
-      raw.v = *reinterpret_cast<const uint4*>(px + c8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float p0, p1;
-        pro_apply(pro, __bfloat162float(raw.h[j]), p0, p1);
-        if (pro != FN_PRO_NONE) {   // the stored operand is bf16 on every path
-          p0 = __bfloat162float(__float2bfloat16(p0));
-          p1 = __bfloat162float(__float2bfloat16(p1));
-        }
-        const int c = c8 + j;
-        if (drop) {
-          p0 *= dropout_scale(seed, base_idx + c, keep);
-          if (mult == 2) p1 *= dropout_scale(seed, base_idx + Craw + c, keep);
-        }
-        const float* w0 = wsm + c * NACC;
-#pragma unroll
-        for (int n = 0; n < NACC; ++n) acc[n] = fmaf(p0, w0[n], acc[n]);
-        if (mult == 2) {
-          const float* w1 = wsm + (Craw + c) * NACC;
-#pragma unroll
-          for (int n = 0; n < NACC; ++n) acc[n] = fmaf(p1, w1[n], acc[n]);
-        }
-      }
+  const bool vec = (Craw & 7) == 0;
+  for (int cb = 0; cb < CR; cb += 8) {
+    bf16x8 raw;
+    int nval = 8;
+    if (vec) {
+      raw.v = *reinterpret_cast<const uint4*>(px + c0 + cb);
+    } else {
+      nval = min(8, CR - cb);
+      for (int j = 0; j < nval; ++j) raw.h[j] = px[c0 + cb + j];
     }
-  } else {
-    for (int c = 0; c < Craw; ++c) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j >= nval) break;
       float p0, p1;
-      pro_apply(pro, __bfloat162float(px[c]), p0, p1);
-      if (pro != FN_PRO_NONE) {
+      pro_apply(pro, __bfloat162float(raw.h[j]), p0, p1);
+      if (pro != FN_PRO_NONE) {   // the stored operand is bf16 on every path
         p0 = __bfloat162float(__float2bfloat16(p0));
         p1 = __bfloat162float(__float2bfloat16(p1));
       }
+      const int cl = cb + j;      // chunk-local raw channel
       if (drop) {
-        p0 *= dropout_scale(seed, base_idx + c, keep);
-        if (mult == 2) p1 *= dropout_scale(seed, base_idx + Craw + c, keep);
+        p0 *= dropout_scale(seed, base_idx + c0 + cl, keep);
+        if (mult == 2) p1 *= dropout_scale(seed, base_idx + Craw + c0 + cl, keep);
       }
-      const float* w0 = wsm + c * NACC;
+      const float* w0 = wsm + cl * NACC;
 #pragma unroll
       for (int n = 0; n < NACC; ++n) acc[n] = fmaf(p0, w0[n], acc[n]);
       if (mult == 2) {
-        const float* w1 = wsm + (Craw + c) * NACC;
+        const float* w1 = wsm + (CR + cl) * NACC;
 #pragma unroll
         for (int n = 0; n < NACC; ++n) acc[n] = fmaf(p1, w1[n], acc[n]);
       }
@@ -77,12 +63,14 @@ __device__ __forceinline__ void accumulate_pixel(const __nv_bfloat16* __restrict
   }
 }
 
-// stage W[k][n0 .. n0+8) (and, gated, W[k][F+n0 .. F+n0+8)) of one tap as fp32 [k][NACC]
+// stage the weight rows of raw channels [c0, c0+CR) of one tap (w: [mult*Craw][Cout]) as fp32 [r][NACC]:
+// columns n0..n0+8 and, gated, F+n0..F+n0+8
 template <int NACC>
-__device__ __forceinline__ void stage_weights(const __nv_bfloat16* __restrict__ w, int K, int Cout, int n0,
-                                              int F, float* wsm) {
-  for (int i = threadIdx.x; i < K * NACC; i += SIMT_THREADS) {
-    const int k = i / NACC, j = i % NACC;
+__device__ __forceinline__ void stage_weights(const __nv_bfloat16* __restrict__ w, int Craw, int c0, int CR, int mult,
+                                              int Cout, int n0, int F, float* wsm) {
+  for (int i = threadIdx.x; i < mult * CR * NACC; i += SIMT_THREADS) {
+    const int r = i / NACC, j = i % NACC;
+    const int k = (r < CR) ? (c0 + r) : (Craw + c0 + (r - CR));
     const int c = n0 + (j % SIMT_NT);            // output slot
     const int n = (j >= SIMT_NT) ? F + c : c;    // second half of NACC = the gate channel of slot c
     wsm[i] = (c < F) ? __bfloat162float(w[(size_t)k * Cout + n]) : 0.f;
@@ -114,27 +102,35 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_conv_simt(const ConvParams p) 
   const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(d.w);
   const bool drop = d.keep_prob < 1.0f;
   const int k = d.ksize;
+  const int mult = pro_mult(d.prologue);
+  const int CRmax = SIMT_MAX_KEFF / mult;       // raw channels per staged chunk
   for (int tap = 0; tap < k * k; ++tap) {
-    __syncthreads();
-    stage_weights<NACC>(w + (size_t)tap * p.Keff * d.Cout, p.Keff, d.Cout, n0, F, wsm);
-    __syncthreads();
     const int di = tap / k, dj = tap % k;
     const int iy = oy * d.stride + di - p.pad_t;
     const int ix = ox * d.stride + dj - p.pad_l;
-    if (live && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) {
-      const size_t pidx = ((size_t)b * d.H + iy) * d.W + ix;
-      accumulate_pixel<NACC>(x + pidx * d.Cin, d.Cin, d.prologue, wsm, acc, drop, d.dropout_seed,
-                             d.dropout_offset + pidx * p.Keff, d.keep_prob);
+    const bool inb = live && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W;
+    const size_t pidx = inb ? ((size_t)b * d.H + iy) * d.W + ix : 0;
+    for (int c0 = 0; c0 < d.Cin; c0 += CRmax) {
+      const int CR = min(CRmax, d.Cin - c0);
+      __syncthreads();
+      stage_weights<NACC>(w + (size_t)tap * p.Keff * d.Cout, d.Cin, c0, CR, mult, d.Cout, n0, F, wsm);
+      __syncthreads();
+      if (inb)
+        accumulate_pixel<NACC>(x + pidx * d.Cin, d.Cin, c0, CR, d.prologue, wsm, acc, drop, d.dropout_seed,
+                               d.dropout_offset + pidx * p.Keff, d.keep_prob);
     }
   }
   if (d.skip != nullptr) {
-    __syncthreads();
-    stage_weights<NACC>(reinterpret_cast<const __nv_bfloat16*>(d.w_skip), p.Kskip_eff, d.Cout, n0, F, wsm);
-    __syncthreads();
-    if (live && oy < d.SH && ox < d.SW) {
-      const size_t pidx = ((size_t)b * d.SH + oy) * d.SW + ox;
-      accumulate_pixel<NACC>(reinterpret_cast<const __nv_bfloat16*>(d.skip) + pidx * d.Cskip, d.Cskip,
-                             d.prologue, wsm, acc, false, 0, 0, 1.f);
+    const bool inb = live && oy < d.SH && ox < d.SW;
+    const size_t pidx = inb ? ((size_t)b * d.SH + oy) * d.SW + ox : 0;
+    for (int c0 = 0; c0 < d.Cskip; c0 += CRmax) {
+      const int CR = min(CRmax, d.Cskip - c0);
+      __syncthreads();
+      stage_weights<NACC>(reinterpret_cast<const __nv_bfloat16*>(d.w_skip), d.Cskip, c0, CR, mult, d.Cout, n0, F, wsm);
+      __syncthreads();
+      if (inb)
+        accumulate_pixel<NACC>(reinterpret_cast<const __nv_bfloat16*>(d.skip) + pidx * d.Cskip, d.Cskip, c0, CR,
+                               d.prologue, wsm, acc, false, 0, 0, 1.f);
     }
   }
   if (!live) return;
@@ -204,8 +200,6 @@ int conv_fwd_simt(const fn_conv_desc& d, cudaStream_t stream) {
   p.Kskip_eff = d.Cskip * pro_mult(d.prologue);
   const bool gated = d.epilogue == FN_EPI_GATE_RES;
   p.slots = gated ? d.Cout / 2 : d.Cout;
-  FN_REQUIRE(p.Keff <= SIMT_MAX_KEFF && p.Kskip_eff <= SIMT_MAX_KEFF, FN_E_UNSUPPORTED,
-             "conv_simt: K per tap %d (skip %d) exceeds %d", p.Keff, p.Kskip_eff, SIMT_MAX_KEFF);
   const long long npix = (long long)d.B * p.OH * p.OW;
   dim3 grid((unsigned)((npix + SIMT_THREADS - 1) / SIMT_THREADS), (unsigned)((p.slots + SIMT_NT - 1) / SIMT_NT));
   if (gated)
@@ -238,17 +232,16 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_tconv_simt(const fn_tconv_desc
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(d.x);
   const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(d.w);
   for (int tap = 0; tap < 9; ++tap) {
-    __syncthreads();
-    stage_weights<SIMT_NT>(w + (size_t)tap * d.Cin * d.Cout, d.Cin, d.Cout, n0, d.Cout, wsm);
-    __syncthreads();
     const int di = tap / 3, dj = tap % 3;
     const int ti = I - di, tj = J - dj;
-    if (live && ti >= 0 && tj >= 0 && ((ti | tj) & 1) == 0) {
-      const int i = ti >> 1, j = tj >> 1;
-      if (i < d.H && j < d.W) {
-        const size_t pidx = ((size_t)b * d.H + i) * d.W + j;
-        accumulate_pixel<SIMT_NT>(x + pidx * d.Cin, d.Cin, FN_PRO_NONE, wsm, acc, false, 0, 0, 1.f);
-      }
+    const bool inb = live && ti >= 0 && tj >= 0 && ((ti | tj) & 1) == 0 && (ti >> 1) < d.H && (tj >> 1) < d.W;
+    const size_t pidx = inb ? ((size_t)b * d.H + (ti >> 1)) * d.W + (tj >> 1) : 0;
+    for (int c0 = 0; c0 < d.Cin; c0 += SIMT_MAX_KEFF) {
+      const int CR = min(SIMT_MAX_KEFF, d.Cin - c0);
+      __syncthreads();
+      stage_weights<SIMT_NT>(w + (size_t)tap * d.Cin * d.Cout, d.Cin, c0, CR, 1, d.Cout, n0, d.Cout, wsm);
+      __syncthreads();
+      if (inb) accumulate_pixel<SIMT_NT>(x + pidx * d.Cin, d.Cin, c0, CR, FN_PRO_NONE, wsm, acc, false, 0, 0, 1.f);
     }
   }
   if (!live) return;
@@ -260,7 +253,6 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_tconv_simt(const fn_tconv_desc
 }
 
 int tconv_fwd_simt(const fn_tconv_desc& d, cudaStream_t stream) {
-  FN_REQUIRE(d.Cin <= SIMT_MAX_KEFF, FN_E_UNSUPPORTED, "tconv_simt: Cin %d exceeds %d", d.Cin, SIMT_MAX_KEFF);
   const long long npix = (long long)d.B * 4 * d.H * d.W;
   dim3 grid((unsigned)((npix + SIMT_THREADS - 1) / SIMT_THREADS), (unsigned)(d.Cout / SIMT_NT));
   k_tconv_simt<<<grid, SIMT_THREADS, 0, stream>>>(d);

@@ -118,22 +118,25 @@ int l2_loss(const float* p, const float* t, float* loss, float* grad, long long 
 
 // TF1 ApplyAdam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v EMA; theta -= lr_t*m/(sqrt(v)+eps)
 __global__ void k_adam(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
-                       float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps) {
+                       float* __restrict__ v, long long n, float lr_t, float b1, float omb1, float b2, float omb2,
+                       float eps) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float g = grad[i];
-    const float mi = b1 * m[i] + (1.f - b1) * g;
-    const float vi = b2 * v[i] + (1.f - b2) * g * g;
+    const float mi = fmaf(b1, m[i], omb1 * g);
+    const float vi = fmaf(b2, v[i], omb2 * g * g);
     m[i] = mi;
     v[i] = vi;
     param[i] -= lr_t * mi / (sqrtf(vi) + eps);
   }
 }
 
-int adam_step(float* param, const float* grad, float* m, float* v, long long n, long long step, float lr, float b1,
-              float b2, float eps, cudaStream_t s) {
+int adam_step(float* param, const float* grad, float* m, float* v, long long n, long long step, double lr, double b1,
+              double b2, double eps, cudaStream_t s) {
   if (n == 0) return 0;
-  const double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step));
-  k_adam<<<ew_grid(n), EW_THREADS, 0, s>>>(param, grad, m, v, n, (float)lr_t, b1, b2, eps);
+  // coefficients are formed in double on the host so (1-beta) is exact to fp32 rounding
+  const double lr_t = lr * sqrt(1.0 - pow(b2, (double)step)) / (1.0 - pow(b1, (double)step));
+  k_adam<<<ew_grid(n), EW_THREADS, 0, s>>>(param, grad, m, v, n, (float)lr_t, (float)b1, (float)(1.0 - b1), (float)b2,
+                                           (float)(1.0 - b2), (float)eps);
   count_launch();
   return check_launch("k_adam");
 }

@@ -61,7 +61,7 @@ SYMBOLS = [
     ("fn_cast_u8_to_bf16", C.c_int, [_P, _P, C.c_int64, _P]),
     ("fn_cast_bf16_to_f32", C.c_int, [_P, _P, C.c_int64, _P]),
     ("fn_l2_loss", C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
-    ("fn_adam_step", C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
+    ("fn_adam_step", C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
 ]
 DEBUG_SYMBOLS = [
     ("fn_debug_set_swap_lbo_sbo", None, [C.c_int]),
