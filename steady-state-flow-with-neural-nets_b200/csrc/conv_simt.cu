@@ -189,7 +189,106 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_conv_simt(const ConvParams p) 
   }
 }
 
+// ------------------------------------------------------------------ head / tail of the network
+// The 1-channel head (boundary -> F, K = 9) and the 2-channel tanh tail (F -> 2) are pure HBM
+// streams with no GEMM shape: one thread per pixel, every output channel in registers, weights as
+// fp32 broadcast reads from shared memory, 3x3 neighbourhood through L1.
+// reference: first res_block conv_1 (flow_architecture.py:132-133) and last_conv + tanh (:242-243).
+template <int CIN, int NOUT, bool TANH>
+__global__ void __launch_bounds__(256) k_direct3x3(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                   const float* __restrict__ bias, void* __restrict__ y, int B, int H,
+                                                   int W) {
+  __shared__ float ws[9 * CIN * NOUT + NOUT];
+  for (int i = threadIdx.x; i < 9 * CIN * NOUT; i += 256) ws[i] = __bfloat162float(w[i]);
+  for (int i = threadIdx.x; i < NOUT; i += 256) ws[9 * CIN * NOUT + i] = bias[i];
+  __syncthreads();
+  const long long npix = (long long)B * H * W;
+  for (long long pix = (long long)blockIdx.x * 256 + threadIdx.x; pix < npix; pix += (long long)gridDim.x * 256) {
+    const int ox = (int)(pix % W);
+    const int oy = (int)((pix / W) % H);
+    float acc[NOUT];
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) acc[n] = ws[9 * CIN * NOUT + n];
+#pragma unroll
+    for (int di = 0; di < 3; ++di) {
+      const int iy = oy + di - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int dj = 0; dj < 3; ++dj) {
+        const int ix = ox + dj - 1;
+        if (ix < 0 || ix >= W) continue;
+        const __nv_bfloat16* px = x + (pix + (long long)(di - 1) * W + (dj - 1)) * CIN;
+        const float* wt = ws + (di * 3 + dj) * CIN * NOUT;
+        if (CIN == 1) {
+          const float v = __bfloat162float(px[0]);
+#pragma unroll
+          for (int n = 0; n < NOUT; ++n) acc[n] = fmaf(v, wt[n], acc[n]);
+        } else {
+#pragma unroll
+          for (int c8 = 0; c8 < CIN; c8 += 8) {
+            bf16x8 raw;
+            raw.v = __ldg(reinterpret_cast<const uint4*>(px + c8));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float v = __bfloat162float(raw.h[j]);
+#pragma unroll
+              for (int n = 0; n < NOUT; ++n) acc[n] = fmaf(v, wt[(c8 + j) * NOUT + n], acc[n]);
+            }
+          }
+        }
+      }
+    }
+    if (TANH) {
+      float* yo = reinterpret_cast<float*>(y) + pix * NOUT;
+      if (NOUT == 2) {
+        *reinterpret_cast<float2*>(yo) = make_float2(tanhf(acc[0]), tanhf(acc[1]));
+      } else {
+#pragma unroll
+        for (int n = 0; n < NOUT; ++n) yo[n] = tanhf(acc[n]);
+      }
+    } else {
+      __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y) + pix * NOUT;
+#pragma unroll
+      for (int n0 = 0; n0 < NOUT; n0 += 8) {
+        bf16x8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.h[j] = __float2bfloat16(acc[n0 + j]);
+        *reinterpret_cast<uint4*>(yo + n0) = o.v;
+      }
+    }
+  }
+}
+
+template <int CIN, int NOUT, bool TANH>
+static int launch_direct(const fn_conv_desc& d, cudaStream_t stream) {
+  const long long npix = (long long)d.B * d.H * d.W;
+  long long grid = (npix + 255) / 256;
+  if (grid > 148LL * 16) grid = 148LL * 16;
+  k_direct3x3<CIN, NOUT, TANH><<<(unsigned)grid, 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d.x), reinterpret_cast<const __nv_bfloat16*>(d.w), d.bias, d.y, d.B, d.H, d.W);
+  count_launch();
+  return check_launch("k_direct3x3");
+}
+
+// returns true (and sets rc) if a specialised head/tail kernel took the launch
+static bool try_direct(const fn_conv_desc& d, cudaStream_t stream, int& rc) {
+  if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_NONE || d.skip || d.keep_prob < 1.0f) return false;
+  if (d.epilogue == FN_EPI_BIAS && d.Cin == 1) {
+    if (d.Cout == 8) { rc = launch_direct<1, 8, false>(d, stream); return true; }
+    if (d.Cout == 16) { rc = launch_direct<1, 16, false>(d, stream); return true; }
+    if (d.Cout == 32) { rc = launch_direct<1, 32, false>(d, stream); return true; }
+  }
+  if (d.epilogue == FN_EPI_TANH && d.Cout == 2) {
+    if (d.Cin == 8) { rc = launch_direct<8, 2, true>(d, stream); return true; }
+    if (d.Cin == 16) { rc = launch_direct<16, 2, true>(d, stream); return true; }
+    if (d.Cin == 32) { rc = launch_direct<32, 2, true>(d, stream); return true; }
+  }
+  return false;
+}
+
 int conv_fwd_simt(const fn_conv_desc& d, cudaStream_t stream) {
+  int rc_direct = 0;
+  if (try_direct(d, stream, rc_direct)) return rc_direct;
   ConvParams p;
   p.d = d;
   p.OH = (d.H + d.stride - 1) / d.stride;

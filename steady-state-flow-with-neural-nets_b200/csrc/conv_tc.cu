@@ -1,25 +1,28 @@
-// tcgen05 / TMEM implicit-GEMM convolution for sm_100a.
+// tcgen05 / TMEM implicit-GEMM convolutions for sm_100a: stride-1 3x3 / 1x1 ('S1'), stride-2 3x3
+// ('S2') and 3x3 stride-2 transposed ('TCONV') share one kernel.
 //
-// One CTA computes a tile of 16 x (8*J) output pixels for all N output channels:
+// One CTA computes 16 x (8*J) GEMM rows ("row pixels": output pixels for S1/S2, INPUT pixels for
+// TCONV whose four output phases are four accumulators) for all N output channels:
 //
-//   gather     all 160 threads read the raw bf16 NHWC halo tile (18 x (8J+2) pixels), apply the
-//              prologue nonlinearity (concat_elu & co, flow_architecture.py:14-29) in registers and
-//              write the UMMA A operand to shared memory as 8-channel planes
-//                   A[q][pv][pu][8]      q = k/8, 16 B per pixel, no swizzle
-//              so that a 3x3 tap is a pure start-address offset of the shared-memory descriptor:
-//              row r = 8*v+u of the M=128 MMA reads pixel (v+dv, u+du) -> byte (v*PU + u)*16 +
-//              (dv*PU+du)*16, i.e. SBO = PU*16, LBO = plane stride.  The 2C-channel concat_elu
-//              tensor and im2col never exist in HBM.
+//   gather     all 160 threads read the raw bf16 NHWC halo tile with 4 independent 16-byte loads in
+//              flight each, apply the prologue nonlinearity (concat_elu & co, reference
+//              flow_architecture.py:14-29) in registers and write the UMMA A operand to shared
+//              memory as 8-channel planes   A[sub][q][pv][pu][8]  (q = k/8; 16 B per pixel; no swizzle)
+//              so that a filter tap is a pure start-address offset of the shared-memory descriptor:
+//              GEMM row r = 8*v+u reads pixel (v+dv, u+du) -> SBO = PU*16, LBO = plane stride.
+//              S2 splits the input tile into its four (row,col)-parity sub-planes so that the
+//              stride-2 taps are again unit-stride; TCONV needs a one-pixel halo before the tile only.
+//              Neither the 2C-channel concat_elu tensor nor an im2col matrix ever exists in HBM.
 //   weights    pre-packed [kstep][2][N][8] bf16 (fn_pack_conv_weights_tc); streamed by the TMA
 //              engine (cp.async.bulk + mbarrier) through a ring of <= 3 chunks of <= 32 KB
 //   mma        one thread issues tcgen05.mma (M=128, N, K=16) per (k-step, sub-tile); fp32
-//              accumulators live in TMEM, J*N columns; the nin skip (flow_architecture.py:136-142)
+//              accumulators live in TMEM (J * phases * N columns); the nin skip (reference :136-142)
 //              is just extra k-steps on a second A operand with the centre tap
 //   epilogue   4 warps read their TMEM quadrant (tcgen05.ld), add bias, apply gate*sigmoid +
-//              shortcut (avg-pool / front channel pad, :150-165) and store bf16 NHWC, 16 B/lane
+//              shortcut (avg-pool / front channel pad, reference :150-165) and store bf16 NHWC, 16 B/lane
 //
-// Reference semantics: tf.nn.conv2d 'SAME' stride 1 (flow_architecture.py:57-68) inside res_block
-// (:129-165).  Stride-2 and transposed convs are in conv_tc_strided.cu (same machinery).
+// Reference semantics: tf.nn.conv2d 'SAME' (flow_architecture.py:57-68), tf.nn.conv2d_transpose
+// 'SAME' (:70-87, phase taps SURVEY App. B.2), res_block (:129-165).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -29,8 +32,12 @@ constexpr int TC_THREADS = 160;      // 4 gather/epilogue warps + 1 MMA/TMA warp
 constexpr int TC_MAX_STAGES = 3;
 constexpr int TC_CHUNK_BYTES = 32768;
 constexpr int TC_SMEM_HEADER = 128;  // mbarriers + TMEM base pointer
+constexpr int TC_GATHER_UNROLL = 4;
+constexpr int TC_SMEM_LIMIT = 200 * 1024;
 
-// debug knobs (tests only): swap the LBO/SBO descriptor fields
+enum { MODE_S1 = 0, MODE_S2 = 1, MODE_TCONV = 2 };
+
+// debug knobs (tests only)
 static int g_tc_swap_lbo_sbo = 0;
 static int* g_tc_status_dev = nullptr;   // device word: 0 ok, else first failing wait code
 
@@ -42,17 +49,27 @@ struct TcParams {
   void* y;
   const __nv_bfloat16* res;
   int* status;
-  int B, H, W, C, Cs, SH, SW;
+  int mode;
+  int B, H, W, C;            // input tensor
+  int OH, OW;                // output tensor spatial size
+  int Cs, SH, SW;            // skip tensor
   int pro, epi;
-  int N, Cout, F;
+  int N, F;                  // MMA N (multiple of 16); channels written per output pixel
   int Cres, RH, RW, res_pool;
   int transposed, J;
-  int EU, EV, tiles_u, tiles_v;
-  int PU, P;
-  int ntaps;            // 9 or 1
-  int ksteps_tap;       // Keff / 16
-  int ksteps_skip;      // Kskip_eff / 16
-  int ksteps_total;
+  int EU, EV, tiles_u, tiles_v;   // GEMM-row image extents along the fast (u) / slow (v) axis
+  int PU, P, Ppad;           // sub-plane row pitch, pixels, padded plane stride (pixels)
+  uint32_t magic_P, magic_PU;
+  int nsub;                  // sub-planes per operand (4 for S2, else 1)
+  int chunk_log2;            // log2(C/8)
+  int planes;                // Keff/8
+  int org_u, org_v;          // sub-plane origin relative to the tile (halo before), S1/TCONV: 1, S2: pad
+  int ntaps, nph;            // taps (9 or 1); accumulator phases (4 for TCONV, else 1)
+  uint32_t tapoff[9];        // byte offset of each tap's A view relative to the operand base
+  int tapcol[9];             // accumulator phase of each tap
+  int tapfirst;              // bitmask: tap is the first one written into its phase
+  uint32_t centre;           // byte offset of the centre view (skip operand)
+  int ksteps_tap, ksteps_skip, ksteps_total;
   int spc, nchunks, nstages;
   int a_main_bytes, a_skip_bytes;
   int tmem_cols;
@@ -62,44 +79,69 @@ struct TcParams {
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, int swap) {
   return swap ? ptx::smem_desc(addr, sbo, lbo) : ptx::smem_desc(addr, lbo, sbo);
 }
+__device__ __forceinline__ uint32_t fastdiv(uint32_t x, uint32_t magic) { return __umulhi(x, magic); }
 
-// gather one operand (main input or skip) into A planes
+// Gather one operand into A planes.  Item order: (sub-plane, pixel, chunk) with the chunk fastest so
+// that a warp reads consecutive 16-byte pieces of consecutive pixels (coalesced); the padded plane
+// stride keeps the 16-byte shared-memory stores of 8 neighbouring lanes on distinct banks.
 __device__ __forceinline__ void gather_operand(const TcParams& p, const __nv_bfloat16* __restrict__ src, int Craw,
-                                               int SHh, int SWw, int b, int u0, int v0, unsigned char* planes) {
+                                               int SHh, int SWw, int mode, int nsub, int b, int u0, int v0,
+                                               unsigned char* planes_base) {
+  const int clog = p.chunk_log2;          // same chunk count for skip and main in every supported layer
   const int chunks = Craw >> 3;
-  const int items = chunks * p.P;
+  const int items = nsub * p.P * chunks;
   const int mult = pro_mult(p.pro);
-  for (int idx = threadIdx.x; idx < items; idx += TC_THREADS) {
-    const int ch = idx / p.P;
-    const int pp = idx - ch * p.P;
-    const int pv = pp / p.PU;
-    const int pu = pp - pv * p.PU;
-    const int cu = u0 + pu - 1, cv = v0 + pv - 1;
-    const int yy = p.transposed ? cu : cv;
-    const int xx = p.transposed ? cv : cu;
-    bf16x8 raw;
-    raw.v = make_uint4(0u, 0u, 0u, 0u);
-    if (cu >= 0 && cv >= 0 && yy < SHh && xx < SWw) {
-      raw.v = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)b * SHh + yy) * SWw + xx) * Craw + ch * 8));
-    }
-    bf16x8 o0, o1;
-    if (p.pro == FN_PRO_NONE) {
-      o0.v = raw.v;
-    } else {
+  const uint32_t sub_bytes = (uint32_t)(mult * chunks) * p.Ppad * 16u;
+  for (int base = threadIdx.x; base < items; base += TC_THREADS * TC_GATHER_UNROLL) {
+    uint4 raw[TC_GATHER_UNROLL];
+    int dst[TC_GATHER_UNROLL];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float a0, a1;
-        pro_apply(p.pro, __bfloat162float(raw.h[j]), a0, a1);
-        o0.h[j] = __float2bfloat16(a0);
-        o1.h[j] = __float2bfloat16(a1);
+    for (int k = 0; k < TC_GATHER_UNROLL; ++k) {
+      const int idx = base + k * TC_THREADS;
+      raw[k] = make_uint4(0u, 0u, 0u, 0u);
+      dst[k] = -1;
+      if (idx < items) {
+        const int ch = idx & (chunks - 1);
+        const uint32_t rest = (uint32_t)idx >> clog;
+        const uint32_t sp = fastdiv(rest, p.magic_P);
+        const uint32_t pp = rest - sp * p.P;
+        const uint32_t pv = fastdiv(pp, p.magic_PU);
+        const uint32_t pu = pp - pv * p.PU;
+        int cu = u0 + (int)pu - p.org_u, cv = v0 + (int)pv - p.org_v;
+        if (mode == MODE_S2) {              // parity sub-plane sp = 2*par_v + par_u holds input 2*pos + par
+          cu = 2 * cu + (int)(sp & 1);
+          cv = 2 * cv + (int)(sp >> 1);
+        }
+        const int yy = p.transposed ? cu : cv;
+        const int xx = p.transposed ? cv : cu;
+        if (cu >= 0 && cv >= 0 && yy < SHh && xx < SWw)
+          raw[k] = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)b * SHh + yy) * SWw + xx) * Craw + ch * 8));
+        dst[k] = (int)(sp * sub_bytes + ((uint32_t)ch * p.Ppad + pp) * 16u);
       }
     }
-    *reinterpret_cast<uint4*>(planes + ((size_t)ch * p.P + pp) * 16) = o0.v;
-    if (mult == 2) *reinterpret_cast<uint4*>(planes + ((size_t)(chunks + ch) * p.P + pp) * 16) = o1.v;
+#pragma unroll
+    for (int k = 0; k < TC_GATHER_UNROLL; ++k) {
+      if (dst[k] < 0) continue;
+      bf16x8 in, o0, o1;
+      in.v = raw[k];
+      if (p.pro == FN_PRO_NONE) {
+        o0.v = in.v;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a0, a1;
+          pro_apply(p.pro, __bfloat162float(in.h[j]), a0, a1);
+          o0.h[j] = __float2bfloat16(a0);
+          o1.h[j] = __float2bfloat16(a1);
+        }
+      }
+      *reinterpret_cast<uint4*>(planes_base + dst[k]) = o0.v;
+      if (mult == 2) *reinterpret_cast<uint4*>(planes_base + dst[k] + (uint32_t)chunks * p.Ppad * 16u) = o1.v;
+    }
   }
 }
 
-// shortcut(res)[pixel, c0..c0+8) added into v[] (avg-pool and front channel pad, :153-165)
+// shortcut(res)[pixel, c0..c0+8) added into v[] (avg-pool and front channel pad, reference :153-165)
 __device__ __forceinline__ void add_shortcut8(const TcParams& p, int b, int oy, int ox, int c0, float (&v)[8]) {
   if (p.res == nullptr) return;
   const int shift = p.F - p.Cres;
@@ -108,6 +150,20 @@ __device__ __forceinline__ void add_shortcut8(const TcParams& p, int b, int oy, 
     r.v = __ldg(reinterpret_cast<const uint4*>(p.res + (((size_t)b * p.RH + oy) * p.RW + ox) * p.Cres + c0));
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(r.h[j]);
+    return;
+  }
+  if (p.res_pool && (p.Cres & 7) == 0 && ((c0 - shift) & 7) == 0 && 2 * oy + 1 < p.RH && 2 * ox + 1 < p.RW) {
+    if (c0 - shift < 0) return;             // front padding: nothing to add
+    const __nv_bfloat16* r00 = p.res + (((size_t)b * p.RH + 2 * oy) * p.RW + 2 * ox) * p.Cres + (c0 - shift);
+    bf16x8 q[4];
+    q[0].v = __ldg(reinterpret_cast<const uint4*>(r00));
+    q[1].v = __ldg(reinterpret_cast<const uint4*>(r00 + p.Cres));
+    q[2].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)p.RW * p.Cres));
+    q[3].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)p.RW * p.Cres + p.Cres));
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] += 0.25f * (__bfloat162float(q[0].h[j]) + __bfloat162float(q[1].h[j]) + __bfloat162float(q[2].h[j]) +
+                       __bfloat162float(q[3].h[j]));
     return;
   }
 #pragma unroll
@@ -134,7 +190,7 @@ __device__ __forceinline__ void add_shortcut8(const TcParams& p, int b, int oy, 
 
 __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  // header: [0]=done, [1..3]=full[s], [4..6]=empty[s] (8 B each), [7*8]=tmem base (4 B)
+  // header: [0]=done, [1..3]=full[s], [4..6]=empty[s] (8 B each), byte 64 = TMEM base (4 B)
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t bar_done = smem_base;
   const uint32_t bar_full = smem_base + 8;
@@ -182,8 +238,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
   }
 
   // ---- gather + prologue: raw NHWC -> A planes
-  gather_operand(p, p.x, p.C, p.H, p.W, b, u0, v0, a_main);
-  if (p.skip != nullptr) gather_operand(p, p.skip, p.Cs, p.SH, p.SW, b, u0, v0, a_skip);
+  gather_operand(p, p.x, p.C, p.H, p.W, p.mode, p.nsub, b, u0, v0, a_main);
+  if (p.skip != nullptr) gather_operand(p, p.skip, p.Cs, p.SH, p.SW, MODE_S1, 1, b, u0, v0, a_skip);
 
   ptx::fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
   ptx::tc_fence_before_sync();
@@ -196,11 +252,11 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
     // ================= MMA issuer + weight-ring producer (one thread) =================
     if (lane == 0) {
       const uint32_t idesc = ptx::idesc_bf16_f32(128, p.N);
-      const uint32_t a_lbo = (uint32_t)p.P * 16u, a_sbo = (uint32_t)p.PU * 16u;
+      const uint32_t a_lbo = (uint32_t)p.Ppad * 16u, a_sbo = (uint32_t)p.PU * 16u;
       const uint32_t b_lbo = (uint32_t)p.N * 16u, b_sbo = 128u;
       const uint32_t a_main_u32 = ptx::smem_u32(a_main), a_skip_u32 = ptx::smem_u32(a_skip);
-      const uint32_t centre = (uint32_t)(p.PU + 1) * 16u;
       const int main_steps = p.ntaps * p.ksteps_tap;
+      const uint32_t jcols = (uint32_t)(p.nph * p.N);     // TMEM columns per sub-tile
       for (int c = 0; c < p.nchunks && ok; ++c) {
         const int s = c % p.nstages;
         ok = ptx::mbar_wait(bar_full + 8 * s, (uint32_t)((c / p.nstages) & 1));
@@ -209,24 +265,22 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
         const int steps = min(p.spc, p.ksteps_total - c * p.spc);
         for (int i = 0; i < steps; ++i) {
           const int ks = c * p.spc + i;
-          uint32_t a_addr;
+          uint32_t a_addr, dcol, acc;
           if (ks < main_steps) {
             const int tap = ks / p.ksteps_tap, kk = ks - tap * p.ksteps_tap;
-            uint32_t tapoff = centre;
-            if (p.ntaps == 9) {
-              const int di = tap / 3, dj = tap - 3 * di;
-              const int dv = p.transposed ? dj : di, du = p.transposed ? di : dj;
-              tapoff = (uint32_t)(dv * p.PU + du) * 16u;
-            }
-            a_addr = a_main_u32 + (uint32_t)(2 * kk) * a_lbo + tapoff;
+            a_addr = a_main_u32 + (uint32_t)(2 * kk) * a_lbo + p.tapoff[tap];
+            dcol = (uint32_t)(p.tapcol[tap] * p.N);
+            acc = (kk > 0 || !((p.tapfirst >> tap) & 1)) ? 1u : 0u;
           } else {
             const int kk = ks - main_steps;
-            a_addr = a_skip_u32 + (uint32_t)(2 * kk) * a_lbo + centre;
+            a_addr = a_skip_u32 + (uint32_t)(2 * kk) * a_lbo + p.centre;
+            dcol = 0u;
+            acc = 1u;
           }
           const uint64_t bdesc = make_desc(b_ring_u32 + s * chunk_bytes + (uint32_t)i * p.N * 32u, b_lbo, b_sbo, p.swap_desc);
           for (int j = 0; j < p.J; ++j) {
             const uint64_t adesc = make_desc(a_addr + (uint32_t)j * 128u, a_lbo, a_sbo, p.swap_desc);
-            ptx::mma_bf16_ss(tmem_base + (uint32_t)(j * p.N), adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+            ptx::mma_bf16_ss(tmem_base + (uint32_t)j * jcols + dcol, adesc, bdesc, idesc, acc);
           }
         }
         ptx::mma_commit(bar_empty + 8 * s);   // frees this ring slot once the MMAs above have read it
@@ -254,40 +308,57 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
     const int r = threadIdx.x;            // accumulator row == TMEM lane
     const int v = r >> 3, u = r & 7;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t jcols = (uint32_t)(p.nph * p.N);
+    __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y);
     for (int j = 0; j < p.J; ++j) {
       const int cu = u0 + 8 * j + u, cv = v0 + v;
       const bool live = ok && cu < p.EU && cv < p.EV;
-      const int oy = p.transposed ? cu : cv, ox = p.transposed ? cv : cu;
-      const size_t pix = ((size_t)b * p.H + oy) * p.W + ox;
-      const uint32_t col0 = lane_base + (uint32_t)(j * p.N);
-      if (p.epi == FN_EPI_GATE_RES) {
+      const int ry = p.transposed ? cu : cv, rx = p.transposed ? cv : cu;    // GEMM-row pixel in image coords
+      const uint32_t col0 = lane_base + (uint32_t)j * jcols;
+      if (p.mode == MODE_TCONV) {
+        for (int ph = 0; ph < 4; ++ph) {
+          const size_t pix = ((size_t)b * p.OH + (2 * ry + (ph >> 1))) * p.OW + (2 * rx + (ph & 1));
+          for (int c0 = 0; c0 < p.F; c0 += 8) {
+            float o[8];
+            ptx::tmem_ld8(col0 + (uint32_t)(ph * p.N + c0), o);
+            if (live) {
+              bf16x8 st;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) st.h[i] = __float2bfloat16(o[i] + __ldg(p.bias + c0 + i));
+              *reinterpret_cast<uint4*>(yb + pix * p.F + c0) = st.v;
+            }
+          }
+        }
+      } else if (p.epi == FN_EPI_GATE_RES) {
+        const size_t pix = ((size_t)b * p.OH + ry) * p.OW + rx;
         for (int c0 = 0; c0 < p.F; c0 += 8) {
           float a[8], g[8];
           ptx::tmem_ld8x2(col0 + c0, col0 + p.F + c0, a, g);
-          float o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            o[i] = (a[i] + __ldg(p.bias + c0 + i)) * sigmoid_f(g[i] + __ldg(p.bias + p.F + c0 + i));
           if (live) {
-            add_shortcut8(p, b, oy, ox, c0, o);
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              o[i] = (a[i] + __ldg(p.bias + c0 + i)) * sigmoid_f(g[i] + __ldg(p.bias + p.F + c0 + i));
+            add_shortcut8(p, b, ry, rx, c0, o);
             bf16x8 st;
 #pragma unroll
             for (int i = 0; i < 8; ++i) st.h[i] = __float2bfloat16(o[i]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.F + c0) = st.v;
+            *reinterpret_cast<uint4*>(yb + pix * p.F + c0) = st.v;
           }
         }
       } else {
+        const size_t pix = ((size_t)b * p.OH + ry) * p.OW + rx;
         for (int c0 = 0; c0 < p.F; c0 += 8) {
           float o[8];
           ptx::tmem_ld8(col0 + c0, o);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += __ldg(p.bias + c0 + i);
           if (live) {
-            if (p.epi == FN_EPI_RES) add_shortcut8(p, b, oy, ox, c0, o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] += __ldg(p.bias + c0 + i);
+            if (p.epi == FN_EPI_RES) add_shortcut8(p, b, ry, rx, c0, o);
             bf16x8 st;
 #pragma unroll
             for (int i = 0; i < 8; ++i) st.h[i] = __float2bfloat16(o[i]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.F + c0) = st.v;
+            *reinterpret_cast<uint4*>(yb + pix * p.F + c0) = st.v;
           }
         }
       }
@@ -310,85 +381,186 @@ static int pow2_cols(int c) {
   while (r < c) r <<= 1;
   return r;
 }
+static int ilog2_exact(int v) {   // -1 unless v is a power of two
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return (1 << l) == v ? l : -1;
+}
+static uint32_t magic_of(int d) { return (uint32_t)((1ull << 32) / (uint32_t)d + 1ull); }
 
-static bool plan_conv_tc(const fn_conv_desc& d, TcParams& p, size_t& smem_bytes, const char** why) {
-  static const char* w_stride = "stride != 1 (handled by the strided kernel)";
-  static const char* w_k = "K per tap not a multiple of 16";
-  static const char* w_epi = "epilogue has no tcgen05 variant";
-  static const char* w_drop = "dropout prologue";
-  static const char* w_n = "N out of range";
-  static const char* w_smem = "tile does not fit shared memory";
+// plane stride (pixels) such that 8 neighbouring gather lanes store to distinct 16-byte bank groups
+static int padded_plane(int P, int chunks) {
+  if (chunks == 1) return P;
+  const int want = chunks >= 8 ? 1 : (chunks == 4 ? 2 : 4);
+  int Pp = P;
+  while ((Pp & 7) != want) ++Pp;
+  return Pp;
+}
+
+struct TcGeom {   // everything plan_tc() needs to know about one launch, independent of the descriptor type
+  int mode, B, H, W, C, OH, OW, Cout, ksize, pro, epi;
+  int Cs, SH, SW;
+  int pad_y, pad_x;   // S2: TF SAME pad-before per image axis
+};
+
+static bool plan_tc(const TcGeom& g, TcParams& p, size_t& smem_bytes, const char** why) {
   const char* dummy;
   if (!why) why = &dummy;
-  if (d.stride != 1) { *why = w_stride; return false; }
-  if (d.epilogue == FN_EPI_TANH) { *why = w_epi; return false; }
-  if (d.keep_prob < 1.0f) { *why = w_drop; return false; }
-  if (d.w_tc == nullptr) { *why = "w_tc is null"; return false; }
-  const int mult = pro_mult(d.prologue);
-  const int Keff = d.Cin * mult;
-  const int Kskip = d.skip ? d.Cskip * mult : 0;
-  if ((d.Cin % 8) != 0 || (Keff % 16) != 0 || (Kskip % 16) != 0) { *why = w_k; return false; }
-  const int N = round_up(d.Cout, 16);
-  if (N < 16 || N > 256) { *why = w_n; return false; }
-  const bool gated = d.epilogue == FN_EPI_GATE_RES;
+  const int mult = pro_mult(g.pro);
+  const int Keff = g.C * mult;
+  const int Kskip = g.Cs * mult;
+  if ((g.C % 8) != 0 || (Keff % 16) != 0 || (Kskip % 16) != 0) { *why = "K per tap not a multiple of 16"; return false; }
+  const int clog = ilog2_exact(g.C / 8);
+  if (clog < 0 || (g.Cs && g.Cs != g.C)) { *why = "channel count not 8 * 2^n (or skip width differs)"; return false; }
+  const int N = round_up(g.Cout, 16);
+  if (N < 16 || N > 256) { *why = "N out of range"; return false; }
+  const bool gated = g.epi == FN_EPI_GATE_RES;
 
-  memset(&p, 0, sizeof(p));
-  p.x = (const __nv_bfloat16*)d.x;
-  p.skip = (const __nv_bfloat16*)d.skip;
-  p.wpk = (const __nv_bfloat16*)d.w_tc;
-  p.bias = d.bias;
-  p.y = d.y;
-  p.res = (const __nv_bfloat16*)d.res;
-  p.B = d.B; p.H = d.H; p.W = d.W; p.C = d.Cin; p.Cs = d.Cskip; p.SH = d.SH; p.SW = d.SW;
-  p.pro = d.prologue; p.epi = d.epilogue;
-  p.N = N; p.Cout = d.Cout; p.F = gated ? d.Cout / 2 : d.Cout;
-  p.Cres = d.Cres; p.RH = d.RH; p.RW = d.RW; p.res_pool = d.res_pool;
-  p.ntaps = d.ksize * d.ksize;
+  p.mode = g.mode;
+  p.B = g.B; p.H = g.H; p.W = g.W; p.C = g.C; p.OH = g.OH; p.OW = g.OW;
+  p.Cs = g.Cs; p.SH = g.SH; p.SW = g.SW;
+  p.pro = g.pro; p.epi = g.epi;
+  p.N = N; p.F = gated ? g.Cout / 2 : g.Cout;
+  p.ntaps = g.ksize * g.ksize;
+  p.nph = g.mode == MODE_TCONV ? 4 : 1;
+  p.nsub = g.mode == MODE_S2 ? 4 : 1;
+  p.chunk_log2 = clog;
+  p.planes = Keff / 8;
   p.ksteps_tap = Keff / 16;
   p.ksteps_skip = Kskip / 16;
   p.ksteps_total = p.ntaps * p.ksteps_tap + p.ksteps_skip;
-  p.spc = TC_CHUNK_BYTES / (N * 32);
-  if (p.spc < 1) p.spc = 1;
-  if (p.spc > p.ksteps_total) p.spc = p.ksteps_total;
-  p.nchunks = (p.ksteps_total + p.spc - 1) / p.spc;
-  p.nstages = p.nchunks < TC_MAX_STAGES ? p.nchunks : TC_MAX_STAGES;
+  auto set_ring = [&](int chunk_budget, int max_stages) {
+    p.spc = chunk_budget / (N * 32);
+    if (p.spc < 1) p.spc = 1;
+    if (p.spc > p.ksteps_total) p.spc = p.ksteps_total;
+    p.nchunks = (p.ksteps_total + p.spc - 1) / p.spc;
+    p.nstages = p.nchunks < max_stages ? p.nchunks : max_stages;
+  };
   p.swap_desc = g_tc_swap_lbo_sbo;
 
-  // orientation: the 8-wide fast axis u runs along x unless the image is too short for 16 rows
-  p.transposed = (d.H < 16 && d.W >= 16) ? 1 : 0;
-  p.EU = p.transposed ? d.H : d.W;
-  p.EV = p.transposed ? d.W : d.H;
+  // GEMM-row image: output pixels (S1/S2) or input pixels (TCONV)
+  const int RHh = g.mode == MODE_TCONV ? g.H : g.OH, RWw = g.mode == MODE_TCONV ? g.W : g.OW;
+  // orientation: the 8-wide fast axis u runs along x unless the row image is too short for 16 rows
+  p.transposed = (RHh < 16 && RWw >= 16) ? 1 : 0;
+  p.EU = p.transposed ? RHh : RWw;
+  p.EV = p.transposed ? RWw : RHh;
   p.tiles_v = (p.EV + 15) / 16;
+  const int pad_u = p.transposed ? g.pad_y : g.pad_x, pad_v = p.transposed ? g.pad_x : g.pad_y;
 
-  const int keff_planes = Keff / 8, kskip_planes = Kskip / 8;
+  const int halo = g.mode == MODE_S1 ? 2 : 1;        // extra sub-plane rows/cols beyond the tile
+  const int PV = 16 + halo;
   const long long want_ctas = 2LL * 148;
   int bestJ = 0;
-  for (int J = 4; J >= 1; J >>= 1) {   // largest J that still gives two waves of CTAs, else the smallest feasible
-    if (J * N > 256) continue;
-    if (J > 1 && (p.EU % (8 * J)) != 0) continue;
-    const int PU = 8 * J + 2, P = 18 * PU;
-    const size_t sm = TC_SMEM_HEADER + (size_t)(keff_planes + kskip_planes) * P * 16 + (size_t)p.nstages * p.spc * N * 32;
-    if (sm > 200 * 1024) continue;
-    bestJ = J;
-    const long long ctas = (long long)d.B * p.tiles_v * ((p.EU + 8 * J - 1) / (8 * J));
-    if (ctas >= want_ctas) break;
+  size_t best_sm = 0;
+  // weight ring: prefer 3 x 32 KB; shrink it before giving up on a tile that would otherwise not fit
+  const int ring_opts[3][2] = {{TC_CHUNK_BYTES, 3}, {TC_CHUNK_BYTES, 2}, {TC_CHUNK_BYTES / 2, 2}};
+  for (int ro = 0; ro < 3 && bestJ == 0; ++ro) {
+    set_ring(ring_opts[ro][0], ring_opts[ro][1]);
+    for (int J = 4; J >= 1; J >>= 1) {   // largest J that still gives two waves of CTAs, else the smallest feasible
+      if (J * p.nph * N > 512) continue;
+      if (J * p.nph * N > 256 && J > 1) continue;
+      if (J > 1 && (p.EU % (8 * J)) != 0) continue;
+      const int PU = 8 * J + halo, P = PV * PU, Pp = padded_plane(P, g.C / 8);
+      const size_t sm = TC_SMEM_HEADER + (size_t)p.nsub * p.planes * Pp * 16 + (size_t)(Kskip / 8) * Pp * 16 +
+                        (size_t)p.nstages * p.spc * N * 32;
+      if (sm > (size_t)TC_SMEM_LIMIT) continue;
+      bestJ = J;
+      best_sm = sm;
+      const long long ctas = (long long)g.B * p.tiles_v * ((p.EU + 8 * J - 1) / (8 * J));
+      if (ctas >= want_ctas) break;
+    }
   }
-  if (bestJ == 0) { *why = w_smem; return false; }
+  if (bestJ == 0) { *why = "tile does not fit shared memory / TMEM"; return false; }
   p.J = bestJ;
-  p.PU = 8 * p.J + 2;
-  p.P = 18 * p.PU;
+  p.PU = 8 * p.J + halo;
+  p.P = PV * p.PU;
+  p.Ppad = padded_plane(p.P, g.C / 8);
+  p.magic_P = magic_of(p.P);
+  p.magic_PU = magic_of(p.PU);
   p.tiles_u = (p.EU + 8 * p.J - 1) / (8 * p.J);
-  p.a_main_bytes = keff_planes * p.P * 16;
-  p.a_skip_bytes = kskip_planes * p.P * 16;
-  p.tmem_cols = pow2_cols(p.J * N);
-  smem_bytes = TC_SMEM_HEADER + (size_t)p.a_main_bytes + p.a_skip_bytes + (size_t)p.nstages * p.spc * N * 32;
+  p.a_main_bytes = p.nsub * p.planes * p.Ppad * 16;
+  p.a_skip_bytes = (Kskip / 8) * p.Ppad * 16;
+  p.tmem_cols = pow2_cols(p.J * p.nph * N);
+  smem_bytes = best_sm;
+
+  // ---- tap program
+  p.tapfirst = 0;
+  p.centre = (uint32_t)(p.PU + 1) * 16u;
+  const uint32_t sub_bytes = (uint32_t)p.planes * p.Ppad * 16u;
+  if (g.mode == MODE_S1) {
+    p.org_u = p.org_v = 1;
+    if (p.ntaps == 1) {
+      p.tapoff[0] = p.centre;
+      p.tapcol[0] = 0;
+    } else {
+      for (int t = 0; t < 9; ++t) {
+        const int di = t / 3, dj = t % 3;
+        const int dv = p.transposed ? dj : di, du = p.transposed ? di : dj;
+        p.tapoff[t] = (uint32_t)(dv * p.PU + du) * 16u;
+        p.tapcol[t] = 0;
+      }
+    }
+    p.tapfirst = 1;
+  } else if (g.mode == MODE_S2) {
+    // input coordinate = 2*o + e, e = d - pad in {-1,0,1,2}: parity e&1, position o + floor(e/2);
+    // the sub-plane origin sits `pad` positions before the tile
+    p.org_u = pad_u;
+    p.org_v = pad_v;
+    for (int t = 0; t < 9; ++t) {
+      const int di = t / 3, dj = t % 3;
+      const int dv = p.transposed ? dj : di, du = p.transposed ? di : dj;
+      const int ev = dv - pad_v, eu = du - pad_u;
+      const int parv = ev & 1, paru = eu & 1;
+      const int lv = (ev >= 0 ? ev / 2 : -1) + pad_v, lu = (eu >= 0 ? eu / 2 : -1) + pad_u;
+      p.tapoff[t] = (uint32_t)(parv * 2 + paru) * sub_bytes + (uint32_t)(lv * p.PU + lu) * 16u;
+      p.tapcol[t] = 0;
+    }
+    p.tapfirst = 1;
+  } else {   // MODE_TCONV: out[2m+d-?]: taps d=0,1 read in[m], d=2 reads in[m-1]; phase = (d==1)
+    p.org_u = p.org_v = 1;
+    int seen = 0;
+    for (int t = 0; t < 9; ++t) {
+      const int di = t / 3, dj = t % 3;
+      const int py = (di == 1), px = (dj == 1);
+      const int sy = (di == 2) ? 0 : 1, sx = (dj == 2) ? 0 : 1;     // sub-plane position of the row pixel's source
+      const int sv = p.transposed ? sx : sy, su = p.transposed ? sy : sx;
+      p.tapoff[t] = (uint32_t)(sv * p.PU + su) * 16u;
+      p.tapcol[t] = py * 2 + px;
+      if (!((seen >> p.tapcol[t]) & 1)) {
+        p.tapfirst |= 1 << t;
+        seen |= 1 << p.tapcol[t];
+      }
+    }
+  }
+  return true;
+}
+
+static bool geom_of_conv(const fn_conv_desc& d, TcGeom& g, const char** why) {
+  const char* dummy;
+  if (!why) why = &dummy;
+  if (d.epilogue == FN_EPI_TANH) { *why = "tanh tail runs on the CUDA-core kernel"; return false; }
+  if (d.keep_prob < 1.0f) { *why = "dropout prologue"; return false; }
+  if (d.w_tc == nullptr) { *why = "w_tc is null"; return false; }
+  if (d.stride == 2 && d.ksize != 3) { *why = "stride 2 needs a 3x3 kernel"; return false; }
+  if (d.stride == 2 && d.skip) { *why = "stride 2 with a skip operand"; return false; }
+  memset(&g, 0, sizeof(g));
+  g.mode = d.stride == 2 ? MODE_S2 : MODE_S1;
+  g.B = d.B; g.H = d.H; g.W = d.W; g.C = d.Cin;
+  g.OH = (d.H + d.stride - 1) / d.stride;
+  g.OW = (d.W + d.stride - 1) / d.stride;
+  g.Cout = d.Cout; g.ksize = d.ksize; g.pro = d.prologue; g.epi = d.epilogue;
+  if (d.skip) { g.Cs = d.Cskip; g.SH = d.SH; g.SW = d.SW; }
+  g.pad_y = same_pad_before(d.H, d.ksize, d.stride);
+  g.pad_x = same_pad_before(d.W, d.ksize, d.stride);
   return true;
 }
 
 bool conv_tc_supported(const fn_conv_desc& d, const char** why) {
+  TcGeom g;
   TcParams p;
   size_t sm;
-  return plan_conv_tc(d, p, sm, why);
+  memset(&p, 0, sizeof(p));
+  return geom_of_conv(d, g, why) && plan_tc(g, p, sm, why);
 }
 
 static int ensure_status_word() {
@@ -401,27 +573,78 @@ static int ensure_status_word() {
   return 0;
 }
 
-int conv_fwd_tc(const fn_conv_desc& d, cudaStream_t stream) {
-  TcParams p;
-  size_t smem_bytes = 0;
-  const char* why = "";
-  if (!plan_conv_tc(d, p, smem_bytes, &why)) {
-    set_error("conv_fwd_tc: unsupported: %s", why);
-    return FN_E_UNSUPPORTED;
-  }
+static int launch_tc(TcParams& p, size_t smem_bytes, cudaStream_t stream) {
   int rc = ensure_status_word();
   if (rc) return rc;
   p.status = g_tc_status_dev;
-  static size_t configured = 0;
-  if (smem_bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    configured = 220 * 1024;
+    configured = true;
   }
-  const unsigned grid = (unsigned)((long long)d.B * p.tiles_u * p.tiles_v);
+  const unsigned grid = (unsigned)((long long)p.B * p.tiles_u * p.tiles_v);
   k_conv_tc<<<grid, TC_THREADS, smem_bytes, stream>>>(p);
   count_launch();
   return check_launch("k_conv_tc");
+}
+
+int conv_fwd_tc(const fn_conv_desc& d, cudaStream_t stream) {
+  TcGeom g;
+  TcParams p;
+  size_t smem_bytes = 0;
+  const char* why = "";
+  memset(&p, 0, sizeof(p));
+  if (!geom_of_conv(d, g, &why) || !plan_tc(g, p, smem_bytes, &why)) {
+    set_error("conv_fwd_tc: unsupported: %s", why);
+    return FN_E_UNSUPPORTED;
+  }
+  p.x = (const __nv_bfloat16*)d.x;
+  p.skip = (const __nv_bfloat16*)d.skip;
+  p.wpk = (const __nv_bfloat16*)d.w_tc;
+  p.bias = d.bias;
+  p.y = d.y;
+  p.res = (const __nv_bfloat16*)d.res;
+  p.Cres = d.Cres; p.RH = d.RH; p.RW = d.RW; p.res_pool = d.res_pool;
+  return launch_tc(p, smem_bytes, stream);
+}
+
+static void geom_of_tconv(const fn_tconv_desc& d, TcGeom& g) {
+  memset(&g, 0, sizeof(g));
+  g.mode = MODE_TCONV;
+  g.B = d.B; g.H = d.H; g.W = d.W; g.C = d.Cin; g.OH = 2 * d.H; g.OW = 2 * d.W;
+  g.Cout = d.Cout; g.ksize = 3; g.pro = FN_PRO_NONE; g.epi = FN_EPI_BIAS;
+}
+
+bool tconv_tc_supported(const fn_tconv_desc& d, const char** why) {
+  if (d.w_tc == nullptr) {
+    if (why) *why = "w_tc is null";
+    return false;
+  }
+  TcGeom g;
+  TcParams p;
+  size_t sm;
+  memset(&p, 0, sizeof(p));
+  geom_of_tconv(d, g);
+  return plan_tc(g, p, sm, why);
+}
+
+int tconv_fwd_tc(const fn_tconv_desc& d, cudaStream_t stream) {
+  TcGeom g;
+  TcParams p;
+  size_t smem_bytes = 0;
+  const char* why = "";
+  memset(&p, 0, sizeof(p));
+  geom_of_tconv(d, g);
+  if (!plan_tc(g, p, smem_bytes, &why)) {
+    set_error("tconv_fwd_tc: unsupported: %s", why);
+    return FN_E_UNSUPPORTED;
+  }
+  p.x = (const __nv_bfloat16*)d.x;
+  p.wpk = (const __nv_bfloat16*)d.w_tc;
+  p.bias = d.bias;
+  p.y = d.y;
+  return launch_tc(p, smem_bytes, stream);
 }
 
 // ---- weight packing: src [T][Keff][Cout] (+ [Kskip][Cout]) bf16 -> dst [kstep][2][N][8] bf16
@@ -471,16 +694,6 @@ int pack_conv_weights_tc(const void* w, const void* w_skip, void* dst, int ksize
                                       ksize * ksize, Keff, Kskip, Cout, N);
   count_launch();
   return check_launch("k_pack_tc");
-}
-
-// transposed / strided tensor-core variants are not built yet: the CUDA-core kernels run them
-bool tconv_tc_supported(const fn_tconv_desc&, const char** why) {
-  if (why) *why = "transposed conv has no tcgen05 kernel yet";
-  return false;
-}
-int tconv_fwd_tc(const fn_tconv_desc&, cudaStream_t) {
-  set_error("tconv_fwd_tc: not built");
-  return FN_E_UNSUPPORTED;
 }
 
 }  // namespace fn

@@ -243,15 +243,17 @@ def transpose_conv_layer(inputs, kernel_size, stride, num_features, idx, nonline
     def make():
         # TF [kh,kw,Cout,Cin] -> GEMM-B [tap, Cin, Cout]
         w16 = w.permute(0, 1, 3, 2).reshape(9, cin, num_features).to(torch.bfloat16).contiguous()
-        return w16, b.contiguous()
+        w_tc = native.pack_conv_weights_tc(w16, None, 3, cin, 0, num_features, False) if cin % 16 == 0 else None
+        return w16, b.contiguous(), w_tc
 
-    w16, bias = VARIABLES.derived(("tconv", scope), make)
+    w16, bias, w_tc = VARIABLES.derived(("tconv", scope), make)
     y = torch.empty((B, 2 * H, 2 * W, num_features), device=x.device, dtype=torch.bfloat16)
     rec = None
     if _PROFILE is not None:
         rec = dict(name=scope, kind="tconv", out_hw=(2 * H, 2 * W), K_tap=cin, N=num_features, stride=2,
                    alg_bytes=(x.numel() + y.numel()) * 2, flops=2 * B * H * W * 9 * cin * num_features)
-    _profiled(rec, lambda: native.tconv_fwd(x, w16, bias, y, B=B, H=H, W=W, Cin=cin, Cout=num_features, impl=IMPL))
+    _profiled(rec, lambda: native.tconv_fwd(x, w16, bias, y, B=B, H=H, W=W, Cin=cin, Cout=num_features, impl=IMPL,
+                                            w_tc=w_tc))
     if nonlinearity is not None:
         y = nonlinearity(y)
     return y

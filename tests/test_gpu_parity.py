@@ -147,6 +147,11 @@ TC_CASES = [
     ("elu_k16", 1, 16, 16, 16, 16, 1, 2, 2, False, None, False),
     ("crelu_gate", 1, 16, 16, 8, 16, 1, 3, 1, False, None, False),
     ("raw_k16", 1, 16, 16, 16, 16, 1, 0, 0, False, None, False),
+    ("s2_c8", 2, 32, 32, 8, 16, 2, 1, 0, False, None, False),
+    ("s2_c16_J", 1, 64, 128, 16, 32, 2, 1, 0, False, None, False),
+    ("s2_odd_dims", 1, 31, 33, 8, 16, 2, 1, 0, False, None, False),
+    ("s2_transposed_out8x16", 2, 16, 32, 32, 64, 2, 1, 0, False, None, False),
+    ("s2_c64", 1, 32, 32, 64, 64, 2, 1, 0, False, None, False),
 ]
 
 
@@ -163,18 +168,25 @@ def test_tcgen05_refuses_shapes_it_has_no_kernel_for(native):
         run_fused_conv(native, native.IMPL_TCGEN05, 1, 16, 16, 1, 8, 1, 0, 0)     # K = 9: CUDA-core layer
 
 
-@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 8, 16, 16, 8), (1, 4, 8, 128, 64), (2, 5, 7, 8, 8)])
-def test_transposed_conv_vs_oracle(native, B, H, W, Cin, Cout):
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 8, 16, 16, 8), (1, 4, 8, 128, 64), (2, 5, 7, 8, 8), (1, 16, 32, 32, 16),
+                                            (2, 32, 64, 16, 8), (1, 20, 12, 64, 32)])
+def test_transposed_conv_vs_oracle(native, impl, B, H, W, Cin, Cout):
+    if impl == "tc" and Cin % 16 != 0:
+        pytest.skip("K per tap not a multiple of 16: CUDA-core layer")
     g = torch.Generator().manual_seed(1)
     x = bf16_round(torch.randn(B, H, W, Cin, generator=g, dtype=torch.float64))
     w = bf16_round((torch.rand(3, 3, Cout, Cin, generator=g, dtype=torch.float64) * 2 - 1) * 0.2)
     b = torch.rand(Cout, generator=g, dtype=torch.float64).float().double()
     ref = fo.conv2d_transpose_same(x, w, 2) + b
     w16 = w.permute(0, 1, 3, 2).reshape(9, Cin, Cout).to("cuda", torch.bfloat16).contiguous()
+    w_tc = native.pack_conv_weights_tc(w16, None, 3, Cin, 0, Cout, False) if Cin % 16 == 0 else None
     y = torch.empty((B, 2 * H, 2 * W, Cout), device="cuda", dtype=torch.bfloat16)
     native.tconv_fwd(x.to("cuda", torch.bfloat16), w16, b.to("cuda", torch.float32), y, B=B, H=H, W=W, Cin=Cin,
-                     Cout=Cout)
+                     Cout=Cout, impl=native.IMPL_TCGEN05 if impl == "tc" else native.IMPL_SIMT, w_tc=w_tc)
     torch.cuda.synchronize()
+    assert native.tc_status() == 0
+    assert native.last_used_tcgen05() == (impl == "tc")
     assert rel_l2(y, ref) < LAYER_TOL
 
 
