@@ -31,7 +31,7 @@ namespace fn {
 constexpr int TC_THREADS = 160;      // 4 gather/epilogue warps + 1 MMA/TMA warp (which also gathers)
 constexpr int TC_MAX_STAGES = 3;
 constexpr int TC_CHUNK_BYTES = 32768;
-constexpr int TC_SMEM_HEADER = 128;  // mbarriers + TMEM base pointer
+constexpr int TC_SMEM_HEADER = 128 + 1024;  // mbarriers + TMEM base pointer, then bias as float[256]
 constexpr int TC_GATHER_UNROLL = 4;
 constexpr int TC_SMEM_LIMIT = 200 * 1024;
 
@@ -40,6 +40,8 @@ enum { MODE_S1 = 0, MODE_S2 = 1, MODE_TCONV = 2 };
 // debug knobs (tests only)
 static int g_tc_swap_lbo_sbo = 0;
 static int* g_tc_status_dev = nullptr;   // device word: 0 ok, else first failing wait code
+static long long* g_tc_timing_dev = nullptr;   // debug phase stamps
+static int g_tc_timing_ctas = 0;
 
 struct TcParams {
   const __nv_bfloat16* x;
@@ -54,7 +56,7 @@ struct TcParams {
   int OH, OW;                // output tensor spatial size
   int Cs, SH, SW;            // skip tensor
   int pro, epi;
-  int N, F;                  // MMA N (multiple of 16); channels written per output pixel
+  int N, F, Cout;            // MMA N (multiple of 16); channels written per output pixel; real accumulator width
   int Cres, RH, RW, res_pool;
   int transposed, J;
   int EU, EV, tiles_u, tiles_v;   // GEMM-row image extents along the fast (u) / slow (v) axis
@@ -74,6 +76,9 @@ struct TcParams {
   int a_main_bytes, a_skip_bytes;
   int tmem_cols;
   int swap_desc;
+  int NI, split_phase;       // issuer warps; 1: issuers split by accumulator phase (TCONV) instead of by sub-tile
+  long long* timing;         // debug: 8 clock64 stamps per CTA (nullptr in production)
+  int timing_ctas;
 };
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, int swap) {
@@ -196,14 +201,17 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
   const uint32_t bar_full = smem_base + 8;
   const uint32_t bar_empty = smem_base + 8 + 8 * TC_MAX_STAGES;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 64);
+  float* sbias = reinterpret_cast<float*>(smem + 128);
   unsigned char* a_main = smem + TC_SMEM_HEADER;
   unsigned char* a_skip = a_main + p.a_main_bytes;
   unsigned char* b_ring = a_skip + p.a_skip_bytes;
   const uint32_t b_ring_u32 = ptx::smem_u32(b_ring);
   const uint32_t chunk_bytes = (uint32_t)p.spc * p.N * 32u;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
+  long long* stamp = (p.timing != nullptr && (int)blockIdx.x < p.timing_ctas) ? p.timing + (size_t)blockIdx.x * 8 : nullptr;
+  if (stamp && threadIdx.x == 0) stamp[0] = clock64();
 
   // ---- tile coordinates
   int t = blockIdx.x;
@@ -218,10 +226,10 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
     ptx::tmem_alloc(smem_base + 64, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
     if (lane == 0) {
-      ptx::mbar_init(bar_done, 1);
+      ptx::mbar_init(bar_done, (uint32_t)p.NI);
       for (int s = 0; s < TC_MAX_STAGES; ++s) {
         ptx::mbar_init(bar_full + 8 * s, 1);
-        ptx::mbar_init(bar_empty + 8 * s, 1);
+        ptx::mbar_init(bar_empty + 8 * s, (uint32_t)p.NI);
       }
       ptx::fence_mbar_init();
       // every ring slot starts empty: fill them all
@@ -237,7 +245,9 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
     __syncwarp();
   }
 
+  if (stamp && threadIdx.x == 0) stamp[1] = clock64();   // setup issued (warp 0 did none of it)
   // ---- gather + prologue: raw NHWC -> A planes
+  for (int i = threadIdx.x; i < p.N; i += TC_THREADS) sbias[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
   gather_operand(p, p.x, p.C, p.H, p.W, p.mode, p.nsub, b, u0, v0, a_main);
   if (p.skip != nullptr) gather_operand(p, p.skip, p.Cs, p.SH, p.SW, MODE_S1, 1, b, u0, v0, a_skip);
 
@@ -246,71 +256,135 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (stamp && threadIdx.x == 0) stamp[2] = clock64();   // gather done, CTA synced
 
   bool ok = true;
   if (warp == 4) {
-    // ================= MMA issuer + weight-ring producer (one thread) =================
+    // ================= weight-ring producer (one elected thread) =================
+    // chunk c lives in slot c % nstages; the first nstages chunks were issued during setup
     if (lane == 0) {
-      const uint32_t idesc = ptx::idesc_bf16_f32(128, p.N);
-      const uint32_t a_lbo = (uint32_t)p.Ppad * 16u, a_sbo = (uint32_t)p.PU * 16u;
-      const uint32_t b_lbo = (uint32_t)p.N * 16u, b_sbo = 128u;
-      const uint32_t a_main_u32 = ptx::smem_u32(a_main), a_skip_u32 = ptx::smem_u32(a_skip);
-      const int main_steps = p.ntaps * p.ksteps_tap;
-      const uint32_t jcols = (uint32_t)(p.nph * p.N);     // TMEM columns per sub-tile
-      for (int c = 0; c < p.nchunks && ok; ++c) {
-        const int s = c % p.nstages;
-        ok = ptx::mbar_wait(bar_full + 8 * s, (uint32_t)((c / p.nstages) & 1));
-        if (!ok) { atomicCAS(p.status, 0, 2); break; }
-        ptx::tc_fence_after_sync();
-        const int steps = min(p.spc, p.ksteps_total - c * p.spc);
-        for (int i = 0; i < steps; ++i) {
-          const int ks = c * p.spc + i;
-          uint32_t a_addr, dcol, acc;
-          if (ks < main_steps) {
-            const int tap = ks / p.ksteps_tap, kk = ks - tap * p.ksteps_tap;
-            a_addr = a_main_u32 + (uint32_t)(2 * kk) * a_lbo + p.tapoff[tap];
-            dcol = (uint32_t)(p.tapcol[tap] * p.N);
-            acc = (kk > 0 || !((p.tapfirst >> tap) & 1)) ? 1u : 0u;
-          } else {
-            const int kk = ks - main_steps;
-            a_addr = a_skip_u32 + (uint32_t)(2 * kk) * a_lbo + p.centre;
-            dcol = 0u;
-            acc = 1u;
-          }
-          const uint64_t bdesc = make_desc(b_ring_u32 + s * chunk_bytes + (uint32_t)i * p.N * 32u, b_lbo, b_sbo, p.swap_desc);
-          for (int j = 0; j < p.J; ++j) {
-            const uint64_t adesc = make_desc(a_addr + (uint32_t)j * 128u, a_lbo, a_sbo, p.swap_desc);
-            ptx::mma_bf16_ss(tmem_base + (uint32_t)j * jcols + dcol, adesc, bdesc, idesc, acc);
-          }
-        }
-        ptx::mma_commit(bar_empty + 8 * s);   // frees this ring slot once the MMAs above have read it
-        // refill the slot of the PREVIOUS chunk (its MMAs are ahead of ours in the pipe) with chunk c-1+nstages
-        const int cp = c - 1, cn = cp + p.nstages;
-        if (cp >= 0 && cn < p.nchunks) {
-          const int sp = cp % p.nstages;
-          ok = ptx::mbar_wait(bar_empty + 8 * sp, (uint32_t)((cp / p.nstages) & 1));
-          if (!ok) { atomicCAS(p.status, 0, 1); break; }
-          const int nsteps = min(p.spc, p.ksteps_total - cn * p.spc);
-          const uint32_t bytes = (uint32_t)nsteps * p.N * 32u;
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * sp, bytes);
-          ptx::bulk_g2s(b_ring_u32 + sp * chunk_bytes,
-                        reinterpret_cast<const unsigned char*>(p.wpk) + (size_t)cn * chunk_bytes, bytes, bar_full + 8 * sp);
-        }
+      int s = 0;
+      uint32_t parity = 0;
+      for (int c = p.nstages; c < p.nchunks; ++c) {
+        ok = ptx::mbar_wait(bar_empty + 8 * s, parity);      // every issuer's MMAs on the old chunk are done
+        if (!ok) { atomicCAS(p.status, 0, 1); break; }
+        const int nsteps = min(p.spc, p.ksteps_total - c * p.spc);
+        const uint32_t bytes = (uint32_t)nsteps * p.N * 32u;
+        ptx::mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+        ptx::bulk_g2s(b_ring_u32 + (uint32_t)s * chunk_bytes,
+                      reinterpret_cast<const unsigned char*>(p.wpk) + (size_t)c * chunk_bytes, bytes, bar_full + 8 * s);
+        if (++s == p.nstages) { s = 0; parity ^= 1u; }
       }
-      ptx::mma_commit(bar_done);              // all MMAs complete -> accumulators readable
     }
     __syncwarp();
   } else {
+    // ================= MMA issue: warps 0..NI-1, one elected lane each, own accumulators =================
+    // The warp runs the loop convergently (descriptor arithmetic stays on the uniform datapath); only
+    // the tcgen05 instructions are predicated on the elected lane.  Issuer w owns sub-tiles j = w, w+NI, ..
+    // (split_phase: accumulator phase w of every sub-tile), so no two issuers ever touch the same
+    // TMEM columns and the accumulation order per output is fixed -> bit-reproducible.
+    if (warp < p.NI) {
+      const uint32_t leader = ptx::elect_one();
+      const uint32_t idesc = ptx::idesc_bf16_f32(128, p.N);
+      const uint32_t a_lbo = (uint32_t)p.Ppad * 16u, a_sbo = (uint32_t)p.PU * 16u;
+      const uint64_t a_tmpl = ptx::smem_desc(ptx::smem_u32(a_main), a_lbo, a_sbo);
+      const uint64_t a_skip_tmpl = ptx::smem_desc(ptx::smem_u32(a_skip) + p.centre, a_lbo, a_sbo);
+      const uint64_t b_tmpl = ptx::smem_desc(b_ring_u32, (uint32_t)p.N * 16u, 128u);
+      const uint32_t kk_step16 = (2u * a_lbo) >> 4;      // two 8-channel planes per k-step
+      const uint32_t b_step16 = ((uint32_t)p.N * 32u) >> 4;
+      const uint32_t chunk16 = chunk_bytes >> 4;
+      const uint32_t jcols = (uint32_t)(p.nph * p.N);     // TMEM columns per sub-tile
+      const int J = p.J, NI = p.NI, split_phase = p.split_phase;
+      const int j_first = split_phase ? 0 : warp, j_step = split_phase ? 1 : NI;
+      int tap = 0, kk = 0;
+      int ksteps_tap = p.ksteps_tap;
+      bool in_skip = false;
+      uint64_t a_desc = a_tmpl + (uint64_t)(p.tapoff[0] >> 4);
+      uint32_t dcol = (uint32_t)(p.tapcol[0] * p.N);
+      uint32_t acc = 0u;                                  // tap 0 is always the first of its phase
+      bool mine = !split_phase || p.tapcol[0] == warp;
+      int s = 0;
+      uint32_t parity = 0;
+      int ks_left = p.ksteps_total;
+      for (int c = 0; c < p.nchunks && ok; ++c) {
+        ok = ptx::mbar_wait(bar_full + 8 * s, parity);
+        if (!ok) { atomicCAS(p.status, 0, 2); break; }
+        ptx::tc_fence_after_sync();
+        const int steps = min(p.spc, ks_left);
+        ks_left -= steps;
+        uint64_t b_desc = b_tmpl + (uint64_t)((uint32_t)s * chunk16);
+        for (int i = 0; i < steps; ++i) {
+          if (mine) {
+            for (int j = j_first; j < J; j += j_step) {
+              if (leader) ptx::mma_bf16_ss(tmem_base + (uint32_t)j * jcols + dcol, a_desc + (uint64_t)(8u * (uint32_t)j), b_desc, idesc, acc);
+            }
+          }
+          b_desc += b_step16;
+          a_desc += kk_step16;
+          acc = 1u;
+          if (++kk == ksteps_tap) {       // next tap (or the skip operand after the last one)
+            kk = 0;
+            ++tap;
+            if (tap < p.ntaps) {
+              a_desc = a_tmpl + (uint64_t)(p.tapoff[tap] >> 4);
+              dcol = (uint32_t)(p.tapcol[tap] * p.N);
+              acc = ((p.tapfirst >> tap) & 1) ? 0u : 1u;
+              mine = !split_phase || p.tapcol[tap] == warp;
+            } else if (!in_skip) {
+              in_skip = true;
+              a_desc = a_skip_tmpl;
+              dcol = 0u;
+              mine = !split_phase || warp == 0;
+              ksteps_tap = 1 << 30;
+            }
+          }
+        }
+        __syncwarp();
+        if (leader) ptx::mma_commit(bar_empty + 8 * s);   // this issuer is done reading ring slot s
+        if (++s == p.nstages) { s = 0; parity ^= 1u; }
+      }
+      if (leader) {
+        ptx::mma_commit(bar_done);                        // all of this issuer's MMAs complete -> arrive
+        if (stamp && warp == 0) stamp[3] = clock64();     // all MMAs issued
+      }
+      __syncwarp();
+    }
     // ================= epilogue: TMEM -> registers -> bf16 NHWC =================
+    const int r = threadIdx.x;            // accumulator row == TMEM lane
+    const int v = r >> 3, u = r & 7;
+    // the shortcut does not depend on the accumulators: fetch it while the MMAs run
+    const bool sc_plain = p.res != nullptr && !p.res_pool && p.Cres == p.F &&
+                          (p.epi == FN_EPI_GATE_RES || p.epi == FN_EPI_RES);
+    const bool sc_regs = sc_plain && p.F == 8;     // the 128x256 level: one 16-byte piece per sub-tile, keep in registers
+    uint4 sc_pre[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sc_pre[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (sc_plain) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j >= p.J) break;
+        const int cu = u0 + 8 * j + u, cv = v0 + v;
+        if (cu < p.EU && cv < p.EV) {
+          const int ry = p.transposed ? cu : cv, rx = p.transposed ? cv : cu;
+          const __nv_bfloat16* rp = p.res + (((size_t)b * p.RH + ry) * p.RW + rx) * p.Cres;
+          if (sc_regs) {
+            sc_pre[j] = __ldg(reinterpret_cast<const uint4*>(rp));
+          } else {
+            for (int c0 = 0; c0 < p.F; c0 += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c0));
+          }
+        }
+      }
+    }
     ok = ptx::mbar_wait(bar_done, 0);
     if (!ok) atomicCAS(p.status, 0, 3);
     ptx::tc_fence_after_sync();
-    const int r = threadIdx.x;            // accumulator row == TMEM lane
-    const int v = r >> 3, u = r & 7;
+    if (stamp && threadIdx.x == 0) stamp[4] = clock64();   // accumulators ready
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t jcols = (uint32_t)(p.nph * p.N);
     __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y);
-    for (int j = 0; j < p.J; ++j) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j >= p.J) break;
       const int cu = u0 + 8 * j + u, cv = v0 + v;
       const bool live = ok && cu < p.EU && cv < p.EV;
       const int ry = p.transposed ? cu : cv, rx = p.transposed ? cv : cu;    // GEMM-row pixel in image coords
@@ -324,7 +398,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
             if (live) {
               bf16x8 st;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) st.h[i] = __float2bfloat16(o[i] + __ldg(p.bias + c0 + i));
+              for (int i = 0; i < 8; ++i) st.h[i] = __float2bfloat16(o[i] + sbias[c0 + i]);
               *reinterpret_cast<uint4*>(yb + pix * p.F + c0) = st.v;
             }
           }
@@ -338,8 +412,15 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
             float o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              o[i] = (a[i] + __ldg(p.bias + c0 + i)) * sigmoid_f(g[i] + __ldg(p.bias + p.F + c0 + i));
-            add_shortcut8(p, b, ry, rx, c0, o);
+              o[i] = (a[i] + sbias[c0 + i]) * sigmoid_f(g[i] + sbias[p.F + c0 + i]);
+            if (sc_regs) {
+              bf16x8 rr;
+              rr.v = sc_pre[j];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] += __bfloat162float(rr.h[i]);
+            } else {
+              add_shortcut8(p, b, ry, rx, c0, o);
+            }
             bf16x8 st;
 #pragma unroll
             for (int i = 0; i < 8; ++i) st.h[i] = __float2bfloat16(o[i]);
@@ -353,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
           ptx::tmem_ld8(col0 + c0, o);
           if (live) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] += __ldg(p.bias + c0 + i);
+            for (int i = 0; i < 8; ++i) o[i] += sbias[c0 + i];
             if (p.epi == FN_EPI_RES) add_shortcut8(p, b, ry, rx, c0, o);
             bf16x8 st;
 #pragma unroll
@@ -366,8 +447,10 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
   }
 
   // ---- teardown
+  if (stamp && threadIdx.x == 0) stamp[5] = clock64();     // epilogue of warp 0 done
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (stamp && threadIdx.x == 0) stamp[6] = clock64();
   if (warp == 4) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -420,7 +503,7 @@ static bool plan_tc(const TcGeom& g, TcParams& p, size_t& smem_bytes, const char
   p.B = g.B; p.H = g.H; p.W = g.W; p.C = g.C; p.OH = g.OH; p.OW = g.OW;
   p.Cs = g.Cs; p.SH = g.SH; p.SW = g.SW;
   p.pro = g.pro; p.epi = g.epi;
-  p.N = N; p.F = gated ? g.Cout / 2 : g.Cout;
+  p.N = N; p.F = gated ? g.Cout / 2 : g.Cout; p.Cout = g.Cout;
   p.ntaps = g.ksize * g.ksize;
   p.nph = g.mode == MODE_TCONV ? 4 : 1;
   p.nsub = g.mode == MODE_S2 ? 4 : 1;
@@ -437,6 +520,8 @@ static bool plan_tc(const TcGeom& g, TcParams& p, size_t& smem_bytes, const char
     p.nstages = p.nchunks < max_stages ? p.nchunks : max_stages;
   };
   p.swap_desc = g_tc_swap_lbo_sbo;
+  p.timing = g_tc_timing_dev;
+  p.timing_ctas = g_tc_timing_ctas;
 
   // GEMM-row image: output pixels (S1/S2) or input pixels (TCONV)
   const int RHh = g.mode == MODE_TCONV ? g.H : g.OH, RWw = g.mode == MODE_TCONV ? g.W : g.OW;
@@ -482,6 +567,8 @@ static bool plan_tc(const TcGeom& g, TcParams& p, size_t& smem_bytes, const char
   p.a_skip_bytes = (Kskip / 8) * p.Ppad * 16;
   p.tmem_cols = pow2_cols(p.J * p.nph * N);
   smem_bytes = best_sm;
+  p.split_phase = (p.nph == 4 && p.J < 4) ? 1 : 0;
+  p.NI = p.split_phase ? 4 : p.J;
 
   // ---- tap program
   p.tapfirst = 0;
@@ -701,6 +788,11 @@ int pack_conv_weights_tc(const void* w, const void* w_skip, void* dst, int ksize
 // ---- debug / test hooks (not part of the drop-in surface, but exported for tests)
 extern "C" {
 void fn_debug_set_swap_lbo_sbo(int v) { fn::g_tc_swap_lbo_sbo = v; }
+// register (or clear with nullptr) a device buffer of 8 int64 clock stamps per CTA for the first `ctas` CTAs
+void fn_debug_set_timing(long long* dev_buf, int ctas) {
+  fn::g_tc_timing_dev = dev_buf;
+  fn::g_tc_timing_ctas = ctas;
+}
 // synchronises the device; returns the tcgen05 protocol status word (0 = ok) and clears it
 int fn_debug_tc_status(void) {
   if (fn::g_tc_status_dev == nullptr) return 0;

@@ -44,6 +44,18 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   return true;
 }
 
+// one lane of a converged warp (the same lane every time): returns 1 in that lane, 0 elsewhere
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %1;\n\t"
+      "@%%px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
+}
+
 // ---- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

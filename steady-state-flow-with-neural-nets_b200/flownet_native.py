@@ -66,6 +66,7 @@ SYMBOLS = [
 DEBUG_SYMBOLS = [
     ("fn_debug_set_swap_lbo_sbo", None, [C.c_int]),
     ("fn_debug_tc_status", C.c_int, []),
+    ("fn_debug_set_timing", None, [C.c_void_p, C.c_int]),
 ]
 
 

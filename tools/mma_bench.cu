@@ -1,0 +1,181 @@
+// Microbenchmark: cycles per tcgen05.mma (M=128, K=16, bf16) as a function of N and of the
+// shared-memory operand layout.  Answers "is the SWIZZLE_NONE tap-shift layout of conv_tc.cu slower
+// to fetch than the canonical layouts?".  One CTA, one issuing thread, R back-to-back MMAs.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I steady-state-flow-with-neural-nets_b200/csrc \
+//        -I include tools/mma_bench.cu -o tools/mma_bench
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "ptx.cuh"
+
+using namespace fn;
+
+__device__ __forceinline__ uint64_t desc_generic(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout_type) {
+  uint64_t d = ptx::smem_desc(addr, lbo, sbo);
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+struct Cfg {
+  int N, R, ctas;
+  uint32_t a_lbo, a_sbo, a_type;
+  uint32_t b_lbo, b_sbo, b_type;
+  uint32_t a_step, b_step;   // address advance per MMA (bytes), to mimic tap shifts / k-steps
+  int J;                     // MMAs that share B per step
+  int mode;                  // 0: rebuild descriptors per MMA under threadIdx==0; 1: base desc + 64-bit add under threadIdx==0;
+                             // 2: whole warp runs the loop, MMA predicated by elect.sync; 3: as 2, unrolled x8
+};
+
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\telect.sync %%rx|%%px, %1;\n\t@%%px mov.s32 %0, 1;\n\t}"
+               : "+r"(pred)
+               : "r"(0xFFFFFFFFu));
+  return pred;
+}
+
+__global__ void __launch_bounds__(128) k_bench(Cfg c, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  // fill smem with small bf16 values (0x3c00 = 0.0078)
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0) {
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), 512);
+    ptx::tmem_relinquish();
+  }
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(ptx::smem_u32(&bar), 1);
+    ptx::fence_mbar_init();
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = ptx::idesc_bf16_f32(128, c.N);
+  const uint32_t a0 = (ptx::smem_u32(smem) + 1023u) & ~1023u, b0 = a0 + 96 * 1024;
+  const uint32_t barp = ptx::smem_u32(&bar);
+  if (c.mode <= 1) {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      if (c.mode == 0) {
+        for (int r = 0; r < c.R; ++r) {
+          const uint64_t bd = desc_generic(b0 + (uint32_t)(r & 7) * c.b_step, c.b_lbo, c.b_sbo, c.b_type);
+          for (int j = 0; j < c.J; ++j) {
+            const uint64_t ad = desc_generic(a0 + (uint32_t)(r & 7) * c.a_step + (uint32_t)j * 128u, c.a_lbo, c.a_sbo, c.a_type);
+            ptx::mma_bf16_ss(tmem + (uint32_t)(j * c.N) % 512u, ad, bd, idesc, 1u);
+          }
+        }
+      } else {
+        const uint64_t abase = desc_generic(a0, c.a_lbo, c.a_sbo, c.a_type);
+        const uint64_t bbase = desc_generic(b0, c.b_lbo, c.b_sbo, c.b_type);
+        const uint64_t astep = c.a_step >> 4, bstep = c.b_step >> 4;
+        for (int r = 0; r < c.R; ++r) {
+          const uint64_t bd = bbase + (uint64_t)(r & 7) * bstep;
+          const uint64_t ad = abase + (uint64_t)(r & 7) * astep;
+          for (int j = 0; j < c.J; ++j) ptx::mma_bf16_ss(tmem + (uint32_t)(j * c.N) % 512u, ad + 8u * j, bd, idesc, 1u);
+        }
+      }
+      const long long t1 = clock64();
+      ptx::mma_commit(barp);
+      ptx::mbar_wait(barp, 0);
+      const long long t2 = clock64();
+      out[blockIdx.x * 2 + 0] = t1 - t0;
+      out[blockIdx.x * 2 + 1] = t2 - t0;
+    }
+  } else if (warp == 1) {
+    const uint32_t leader = elect_one_sync();
+    const uint64_t abase = desc_generic(a0, c.a_lbo, c.a_sbo, c.a_type);
+    const uint64_t bbase = desc_generic(b0, c.b_lbo, c.b_sbo, c.b_type);
+    const uint64_t astep = c.a_step >> 4, bstep = c.b_step >> 4;
+    const long long t0 = clock64();
+    if (c.mode == 2) {
+      for (int r = 0; r < c.R; ++r) {
+        const uint64_t bd = bbase + (uint64_t)(r & 7) * bstep;
+        const uint64_t ad = abase + (uint64_t)(r & 7) * astep;
+        for (int j = 0; j < c.J; ++j)
+          if (leader) ptx::mma_bf16_ss(tmem + (uint32_t)(j * c.N) % 512u, ad + 8u * j, bd, idesc, 1u);
+      }
+    } else {
+      for (int r = 0; r < c.R; r += 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint64_t bd = bbase + (uint64_t)q * bstep;
+          const uint64_t ad = abase + (uint64_t)q * astep;
+          for (int j = 0; j < c.J; ++j)
+            if (leader) ptx::mma_bf16_ss(tmem + (uint32_t)(j * c.N) % 512u, ad + 8u * j, bd, idesc, 1u);
+        }
+      }
+    }
+    __syncwarp();
+    const long long t1 = clock64();
+    if (leader) ptx::mma_commit(barp);
+    __syncwarp();
+    ptx::mbar_wait(barp, 0);
+    const long long t2 = clock64();
+    if (leader) {
+      out[blockIdx.x * 2 + 0] = t1 - t0;
+      out[blockIdx.x * 2 + 1] = t2 - t0;
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+int main() {
+  long long* d_out;
+  cudaMalloc(&d_out, 148 * 2 * sizeof(long long));
+  cudaFuncSetAttribute(k_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  struct Named { const char* name; Cfg c; };
+  const int R = 128;
+  Named cases[] = {
+      // name                                   N   R  ctas  a_lbo a_sbo at  b_lbo  b_sbo bt a_step b_step J
+      {"noswz tapshift PU10 N16 J1",           {16, R, 1, 2880, 160, 0, 16 * 16, 128, 0, 16, 512, 1, 0}},
+      {"noswz tapshift PU34 N16 J4",           {16, R, 1, 9808, 544, 0, 16 * 16, 128, 0, 16, 512, 4, 0}},
+      {"noswz tapshift PU10 N64 J1",           {64, R, 1, 2896, 160, 0, 64 * 16, 128, 0, 16, 2048, 1, 0}},
+      {"noswz tapshift PU10 N128 J1",          {128, R, 1, 2896, 160, 0, 128 * 16, 128, 0, 16, 4096, 1, 0}},
+      {"noswz tapshift PU10 N256 J1",          {256, R, 1, 2896, 160, 0, 256 * 16, 128, 0, 16, 8192, 1, 0}},
+      {"noswz canonical     N16 J1",           {16, R, 1, 2048, 128, 0, 16 * 16, 128, 0, 4096, 512, 1, 0}},
+      {"noswz canonical     N64 J1",           {64, R, 1, 2048, 128, 0, 64 * 16, 128, 0, 4096, 2048, 1, 0}},
+      {"noswz canonical     N256 J1",          {256, R, 1, 2048, 128, 0, 256 * 16, 128, 0, 4096, 8192, 1, 0}},
+      {"swz128 canonical    N16 J1",           {16, R, 1, 16, 1024, 2, 16, 1024, 2, 32, 32, 1, 0}},
+      {"swz128 canonical    N64 J1",           {64, R, 1, 16, 1024, 2, 16, 1024, 2, 32, 32, 1, 0}},
+      {"swz128 canonical    N256 J1",          {256, R, 1, 16, 1024, 2, 16, 1024, 2, 32, 32, 1, 0}},
+      {"swz128 A / noswz B  N16 J1",           {16, R, 1, 16, 1024, 2, 16 * 16, 128, 0, 32, 512, 1, 0}},
+      {"noswz tapshift PU34 N16 J4 x148 CTAs", {16, R, 148, 9808, 544, 0, 16 * 16, 128, 0, 16, 512, 4, 0}},
+      {"noswz tapshift PU10 N256 x148 CTAs",   {256, R, 148, 2896, 160, 0, 256 * 16, 128, 0, 16, 8192, 1, 0}},
+      {"mode1 base+add   PU10 N16 J1",          {16, R, 1, 2880, 160, 0, 16 * 16, 128, 0, 16, 512, 1, 1}},
+      {"mode1 base+add   PU34 N16 J4",          {16, R, 1, 9808, 544, 0, 16 * 16, 128, 0, 16, 512, 4, 1}},
+      {"mode2 elect      PU10 N16 J1",          {16, R, 1, 2880, 160, 0, 16 * 16, 128, 0, 16, 512, 1, 2}},
+      {"mode2 elect      PU34 N16 J4",          {16, R, 1, 9808, 544, 0, 16 * 16, 128, 0, 16, 512, 4, 2}},
+      {"mode3 elect unr8 PU10 N16 J1",          {16, R, 1, 2880, 160, 0, 16 * 16, 128, 0, 16, 512, 1, 3}},
+      {"mode3 elect unr8 PU34 N16 J4",          {16, R, 1, 9808, 544, 0, 16 * 16, 128, 0, 16, 512, 4, 3}},
+      {"mode3 elect unr8 PU10 N32 J1",          {32, R, 1, 2880, 160, 0, 32 * 16, 128, 0, 16, 1024, 1, 3}},
+      {"mode3 elect unr8 PU10 N64 J1",          {64, R, 1, 2896, 160, 0, 64 * 16, 128, 0, 16, 2048, 1, 3}},
+      {"mode3 elect unr8 PU10 N128 J1",         {128, R, 1, 2896, 160, 0, 128 * 16, 128, 0, 16, 4096, 1, 3}},
+      {"mode3 elect unr8 PU10 N256 J1",         {256, R, 1, 2896, 160, 0, 256 * 16, 128, 0, 16, 8192, 1, 3}},
+      {"mode3 elect unr8 canon N16 J1",         {16, R, 1, 2048, 128, 0, 16 * 16, 128, 0, 4096, 512, 1, 3}},
+      {"mode3 elect unr8 canon N256 J1",        {256, R, 1, 2048, 128, 0, 256 * 16, 128, 0, 4096, 8192, 1, 3}},
+      {"mode3 elect unr8 swz128 N16 J1",        {16, R, 1, 16, 1024, 2, 16, 1024, 2, 32, 32, 1, 3}},
+      {"mode3 elect unr8 swz128 N64 J1",        {64, R, 1, 16, 1024, 2, 16, 1024, 2, 32, 32, 1, 3}},
+      {"mode3 elect unr8 swz128 N256 J1",       {256, R, 1, 16, 1024, 2, 16, 1024, 2, 32, 32, 1, 3}},
+      {"mode3 PU34 N16 J4 x148 CTAs",           {16, R, 148, 9808, 544, 0, 16 * 16, 128, 0, 16, 512, 4, 3}},
+  };
+  for (auto& nc : cases) {
+    cudaMemset(d_out, 0, 148 * 2 * sizeof(long long));
+    k_bench<<<nc.c.ctas, 128, 200 * 1024>>>(nc.c, d_out);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h[2];
+    cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+    const int mmas = nc.c.R * nc.c.J;
+    printf("%-40s issue %7.1f clk/MMA   issue+complete %7.1f clk/MMA  (floor N/2 = %d)  %s\n", nc.name,
+           (double)h[0] / mmas, (double)h[1] / mmas, nc.c.N / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    if (e != cudaSuccess) break;
+  }
+  return 0;
+}
