@@ -45,7 +45,12 @@ __host__ __device__ inline int pro_mult(int pro) {
 // first (and for concat variants second) prologue output of one raw value
 __device__ __forceinline__ void pro_apply(int pro, float v, float& p0, float& p1) {
   switch (pro) {
-    case FN_PRO_CONCAT_ELU:  p0 = elu_f(v);       p1 = elu_f(-v);       break;
+    case FN_PRO_CONCAT_ELU: {   // one exponential serves both halves: t = exp(-|v|) - 1
+      const float t = __expf(-fabsf(v)) - 1.f;
+      p0 = v > 0.f ? v : t;
+      p1 = v > 0.f ? t : -v;
+      break;
+    }
     case FN_PRO_ELU:         p0 = elu_f(v);       p1 = 0.f;             break;
     case FN_PRO_CONCAT_RELU: p0 = fmaxf(v, 0.f);  p1 = fmaxf(-v, 0.f);  break;
     case FN_PRO_RELU:        p0 = fmaxf(v, 0.f);  p1 = 0.f;             break;

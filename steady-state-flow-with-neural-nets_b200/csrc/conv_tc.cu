@@ -193,7 +193,7 @@ __device__ __forceinline__ void add_shortcut8(const TcParams& p, int b, int oy, 
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 6) k_conv_tc(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   // header: [0]=done, [1..3]=full[s], [4..6]=empty[s] (8 B each), byte 64 = TMEM base (4 B)
   const uint32_t smem_base = ptx::smem_u32(smem);
