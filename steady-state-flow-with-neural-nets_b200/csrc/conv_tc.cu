@@ -39,6 +39,7 @@ enum { MODE_S1 = 0, MODE_S2 = 1, MODE_TCONV = 2 };
 
 // debug knobs (tests only)
 static int g_tc_swap_lbo_sbo = 0;
+static int g_tc_use_s1p = 1;            // 0: force the generic kernel (tests compare the two)
 static int* g_tc_status_dev = nullptr;   // device word: 0 ok, else first failing wait code
 static long long* g_tc_timing_dev = nullptr;   // debug phase stamps
 static int g_tc_timing_ctas = 0;
@@ -660,6 +661,9 @@ static int ensure_status_word() {
   return 0;
 }
 
+int* tc_status_word() { return ensure_status_word() == 0 ? g_tc_status_dev : nullptr; }
+bool conv_s1p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1p.cu
+
 static int launch_tc(TcParams& p, size_t smem_bytes, cudaStream_t stream) {
   int rc = ensure_status_word();
   if (rc) return rc;
@@ -677,6 +681,8 @@ static int launch_tc(TcParams& p, size_t smem_bytes, cudaStream_t stream) {
 }
 
 int conv_fwd_tc(const fn_conv_desc& d, cudaStream_t stream) {
+  int rc_sp = 0;
+  if (g_tc_use_s1p && conv_s1p_try(d, stream, false, rc_sp)) return rc_sp;
   TcGeom g;
   TcParams p;
   size_t smem_bytes = 0;
@@ -788,6 +794,7 @@ int pack_conv_weights_tc(const void* w, const void* w_skip, void* dst, int ksize
 // ---- debug / test hooks (not part of the drop-in surface, but exported for tests)
 extern "C" {
 void fn_debug_set_swap_lbo_sbo(int v) { fn::g_tc_swap_lbo_sbo = v; }
+void fn_debug_set_use_s1p(int v) { fn::g_tc_use_s1p = v; }
 // register (or clear with nullptr) a device buffer of 8 int64 clock stamps per CTA for the first `ctas` CTAs
 void fn_debug_set_timing(long long* dev_buf, int ctas) {
   fn::g_tc_timing_dev = dev_buf;

@@ -67,6 +67,7 @@ DEBUG_SYMBOLS = [
     ("fn_debug_set_swap_lbo_sbo", None, [C.c_int]),
     ("fn_debug_tc_status", C.c_int, []),
     ("fn_debug_set_timing", None, [C.c_void_p, C.c_int]),
+    ("fn_debug_set_use_s1p", None, [C.c_int]),
 ]
 
 

@@ -163,6 +163,36 @@ def test_fused_conv_tcgen05_vs_oracle(native, case):
     assert rel_l2(y, ref) < LAYER_TOL
 
 
+S1P_CASES = [
+    # shapes the persistent TMA kernel (conv_s1p.cu) takes: concat_elu, C in {8,16}, Cout in {C, 2C gated}
+    ("l1_conv2_gate", 3, 32, 64, 8, 16, 1, 1, 1, False, None, False),
+    ("l1_conv2_head_res", 2, 32, 64, 8, 16, 1, 1, 1, False, 1, False),
+    ("l1_conv1_plain", 2, 32, 64, 8, 8, 1, 1, 0, False, None, False),
+    ("l1_conv1_skip", 2, 32, 64, 8, 8, 1, 1, 0, True, None, False),
+    ("l2_conv2_gate", 2, 32, 64, 16, 32, 1, 1, 1, False, None, False),
+    ("l2_conv2_pool_pad", 2, 32, 32, 16, 32, 1, 1, 1, False, 8, True),
+    ("l2_conv1_skip", 2, 32, 64, 16, 16, 1, 1, 0, True, None, False),
+    ("ragged_gate", 1, 20, 28, 8, 16, 1, 1, 1, False, None, False),
+    ("ragged_skip", 2, 23, 41, 16, 16, 1, 1, 0, True, None, False),
+    ("many_tiles_persistent", 40, 64, 64, 8, 16, 1, 1, 1, False, None, False),
+    ("w16_J2", 2, 16, 16, 8, 16, 1, 1, 1, False, None, False),
+]
+
+
+@pytest.mark.parametrize("case", S1P_CASES, ids=[c[0] for c in S1P_CASES])
+def test_persistent_tma_kernel_vs_generic_and_oracle(native, case):
+    name, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool = case
+    try:
+        native.lib.fn_debug_set_use_s1p(1)
+        y, ref = run_fused_conv(native, native.IMPL_TCGEN05, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool)
+        native.lib.fn_debug_set_use_s1p(0)
+        yg, _ = run_fused_conv(native, native.IMPL_TCGEN05, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool)
+    finally:
+        native.lib.fn_debug_set_use_s1p(1)
+    assert rel_l2(y, ref) < LAYER_TOL
+    assert rel_l2(y, yg) < 1e-4          # same MMA order, same bf16 rounding points
+
+
 def test_tcgen05_refuses_shapes_it_has_no_kernel_for(native):
     with pytest.raises(ValueError):
         run_fused_conv(native, native.IMPL_TCGEN05, 1, 16, 16, 1, 8, 1, 0, 0)     # K = 9: CUDA-core layer
