@@ -1,26 +1,33 @@
-// Persistent, template-specialised tcgen05 kernel for the stride-1 3x3 convolutions of the
-// high-resolution levels of flow_net (concat_elu prologue, C in {8,16,32}); these launches are
-// HBM- and instruction-issue-bound, so everything that can be a compile-time constant is one.
+// Persistent, warp-specialised, template-specialised tcgen05 kernel for the stride-1 3x3
+// convolutions of flow_net with the concat_elu prologue and resident weights (C in {8,16,32}):
+// the 128x256, 64x128 and 32x64 levels.  These launches are HBM- and instruction-issue-bound, so
+// everything that can be a compile-time constant is one and the three phases of a tile run
+// concurrently on different warps:
 //
-// Differences from the generic k_conv_tc (conv_tc.cu), same math and same A/B layouts:
-//   * persistent CTAs: grid = min(tiles, 148 * CTAs/SM); weights (<= 73 KB) are loaded ONCE per CTA by
-//     the TMA engine and stay resident; TMEM is allocated once
-//   * the raw halo tile, the skip tile and the shortcut tile arrive by TMA TENSOR loads
-//     (cp.async.bulk.tensor.4d, out-of-image pixels zero-filled by the hardware = TF 'SAME' padding),
-//     double-buffered so tile t+1 is in flight while tile t is transformed / multiplied / stored
-//   * transform: shared -> registers -> shared, concat_elu with one ex2 per element, straight-line
-//   * MMA issue: one elected lane per sub-tile, fully unrolled k-step program with immediate offsets
-//   * epilogue: compile-time channel counts, shortcut read from the staged tile
+//   warp 8      producer   TMA tensor loads (cp.async.bulk.tensor.4d) of the raw halo tile, the skip
+//                          tile and the shortcut tile, two tiles ahead; out-of-image pixels are
+//                          zero-filled by the hardware (= TF 'SAME' padding); weights once per CTA
+//   warps 0-3   front      stage -> concat_elu (one ex2 per element) -> UMMA A planes (shared ->
+//                          registers -> shared), then one elected lane per sub-tile issues the fully
+//                          unrolled tcgen05.mma program (immediate descriptor offsets) into TMEM
+//   warps 4-7   back       TMEM -> registers -> bias, gate*sigmoid, shortcut -> bf16 NHWC stores
+//
+// Stage buffers, A planes, TMEM accumulators and shortcut tiles are double-buffered; mbarriers carry
+// the hand-offs (X: TMA->front, XF: front->producer, TF: MMA->back and planes-free->front,
+// TE: back->issuers and ->producer, R: shortcut TMA->back).  Same math, A/B layouts and MMA order as
+// the generic k_conv_tc (conv_tc.cu); results are bit-reproducible run to run.
 // reference semantics: res_block conv_1 (+nin) and conv_2 (+gate, +shortcut), flow_architecture.py:129-165
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace fn {
 
-constexpr int SP_THREADS = 160;   // warps 0-3: transform / issue / epilogue; warp 4: TMA producer + TMEM owner
-constexpr int SP_HDR = 128 + 1024;
+constexpr int SP_THREADS = 288;   // 4 front warps, 4 back warps, 1 producer warp
+constexpr int SP_HDR = 256 + 1024;
 
 struct SpParams {
   CUtensorMap tm_x, tm_skip, tm_res;   // 64-byte aligned by the type
@@ -46,41 +53,58 @@ struct SpCfg {
   static constexpr int KS = CH;                  // k-steps per tap (Keff = 2C)
   static constexpr int KSTEPS = 9 * KS + (SKIP ? KS : 0);
   static constexpr int PU = 8 * J + 2, PV = 18, P = PU * PV;
+  // plane stride (pixels) that keeps the 16-byte stores of 8 neighbouring lanes on distinct banks
   static constexpr int PPAD = CH == 1 ? P : (P + ((CH >= 8 ? 1 : (CH == 4 ? 2 : 4)) - (P & 7) + 8) % 8);
   static constexpr int W_BYTES = KSTEPS * N * 32;
-  static constexpr int PLANE_BYTES = 2 * CH * PPAD * 16;          // one operand, 2C channels
+  static constexpr int PLANE_BYTES = (2 * CH * PPAD * 16 + 127) / 128 * 128;   // one operand, 2C channels
   static constexpr int STAGE_BYTES = ((P * C * 2) + 127) / 128 * 128;
   static constexpr int RES_BYTES = GATE ? 128 * J * F * 2 : 0;
   static constexpr int OFF_W = SP_HDR;
-  static constexpr int OFF_PLANES = OFF_W + (W_BYTES + 127) / 128 * 128;
-  static constexpr int OFF_PLANES_S = OFF_PLANES + (PLANE_BYTES + 127) / 128 * 128;
-  static constexpr int OFF_STAGE = OFF_PLANES_S + (SKIP ? (PLANE_BYTES + 127) / 128 * 128 : 0);
-  static constexpr int OFF_STAGE_S = OFF_STAGE + 2 * STAGE_BYTES;
-  static constexpr int OFF_RES = OFF_STAGE_S + (SKIP ? 2 * STAGE_BYTES : 0);
-  static constexpr int SMEM = OFF_RES + RES_BYTES + 128;           // +128: base alignment slack
-  static constexpr int TMEM_COLS = (J * N <= 32) ? 32 : (J * N <= 64) ? 64 : (J * N <= 128) ? 128 : (J * N <= 256) ? 256 : 512;
+  static constexpr int OFF_PLANES = OFF_W + (W_BYTES + 127) / 128 * 128;       // [2]
+  static constexpr int OFF_PLANES_S = OFF_PLANES + 2 * PLANE_BYTES;            // [2] if SKIP
+  static constexpr int OFF_STAGE = OFF_PLANES_S + (SKIP ? 2 * PLANE_BYTES : 0);  // [2]
+  static constexpr int OFF_STAGE_S = OFF_STAGE + 2 * STAGE_BYTES;              // [2] if SKIP
+  static constexpr int OFF_RES = OFF_STAGE_S + (SKIP ? 2 * STAGE_BYTES : 0);   // [2] if GATE
+  static constexpr int SMEM = OFF_RES + 2 * RES_BYTES + 128;                   // +128: base alignment slack
+  static constexpr int ACC_COLS = J * N;                                        // one accumulator buffer
+  static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
+                                   : (2 * ACC_COLS <= 256) ? 256 : 512;
 };
 
-// barriers (8 B each) inside the 128-byte header
-enum { SB_W = 0, SB_X0 = 1, SB_X1 = 2, SB_S0 = 3, SB_S1 = 4, SB_R = 5, SB_DONE = 6, SB_COUNT = 7 };
+// mbarriers (8 B each) inside the header; [2] = one per buffer
+enum { SB_W = 0, SB_X = 1, SB_S = 3, SB_XF = 5, SB_TF = 7, SB_TE = 9, SB_R = 11, SB_COUNT = 13 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void front_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-// stage [pp][C] raw bf16  ->  planes [2C/8][PPAD][8] = [elu(x) | elu(-x)], both bf16
+// stage [pp][C] raw bf16  ->  planes [2C/8][PPAD][8] = [elu(x) | elu(-x)], both bf16 (shared addresses)
 template <typename Cfg>
-__device__ __forceinline__ void transform_tile(const unsigned char* __restrict__ stage, unsigned char* __restrict__ planes,
-                                               int tid) {
+__device__ __forceinline__ void transform_tile(uint32_t stage, uint32_t planes, int tid) {
   constexpr int ITEMS = Cfg::P * Cfg::CH;
+  constexpr int SH = Cfg::CH == 1 ? 0 : (Cfg::CH == 2 ? 1 : (Cfg::CH == 4 ? 2 : 3));
 #pragma unroll 4
   for (int idx = tid; idx < ITEMS; idx += 128) {
     const int ch = idx & (Cfg::CH - 1);
-    const int pp = idx >> (Cfg::CH == 1 ? 0 : (Cfg::CH == 2 ? 1 : (Cfg::CH == 4 ? 2 : 3)));
+    const int pp = idx >> SH;
     bf16x8 in, o0, o1;
-    in.v = *reinterpret_cast<const uint4*>(stage + (size_t)idx * 16);
+    in.v = lds128(stage + (uint32_t)idx * 16u);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float v = __bfloat162float(in.h[j]);
@@ -88,15 +112,29 @@ __device__ __forceinline__ void transform_tile(const unsigned char* __restrict__
       o0.h[j] = __float2bfloat16(v > 0.f ? v : t);
       o1.h[j] = __float2bfloat16(v > 0.f ? t : -v);
     }
-    unsigned char* d0 = planes + ((size_t)ch * Cfg::PPAD + pp) * 16;
-    *reinterpret_cast<uint4*>(d0) = o0.v;
-    *reinterpret_cast<uint4*>(d0 + (size_t)Cfg::CH * Cfg::PPAD * 16) = o1.v;
+    const uint32_t d0 = planes + (uint32_t)(ch * Cfg::PPAD + pp) * 16u;
+    sts128(d0, o0.v);
+    sts128(d0 + (uint32_t)(Cfg::CH * Cfg::PPAD * 16), o1.v);
   }
 }
 
 // generic shortcut (avg-pool and/or front channel pad), 8 channels, global loads; reference :153-165
 __device__ __forceinline__ void sp_shortcut_generic(const SpParams& p, int F, int b, int oy, int ox, int c0, float (&v)[8]) {
   const int shift = F - p.Cres;
+  if (p.res_pool && (p.Cres & 7) == 0 && ((c0 - shift) & 7) == 0 && 2 * oy + 1 < p.RH && 2 * ox + 1 < p.RW) {
+    if (c0 - shift < 0) return;             // front padding: nothing to add
+    const __nv_bfloat16* r00 = p.res + (((size_t)b * p.RH + 2 * oy) * p.RW + 2 * ox) * p.Cres + (c0 - shift);
+    bf16x8 q[4];
+    q[0].v = __ldg(reinterpret_cast<const uint4*>(r00));
+    q[1].v = __ldg(reinterpret_cast<const uint4*>(r00 + p.Cres));
+    q[2].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)p.RW * p.Cres));
+    q[3].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)p.RW * p.Cres + p.Cres));
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] += 0.25f * (__bfloat162float(q[0].h[j]) + __bfloat162float(q[1].h[j]) + __bfloat162float(q[2].h[j]) +
+                       __bfloat162float(q[3].h[j]));
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int cr = c0 + j - shift;
@@ -127,10 +165,8 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const uint32_t sbase = ptx::smem_u32(smem);
   auto bar = [&](int i) { return sbase + 8u * (uint32_t)i; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 64);
-  float* sbias = reinterpret_cast<float*>(smem + 128);
-  unsigned char* planes = smem + Cfg::OFF_PLANES;
-  unsigned char* planes_s = smem + Cfg::OFF_PLANES_S;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 128);
+  float* sbias = reinterpret_cast<float*>(smem + 256);    // [N]; gate: the v half is pre-multiplied by 0.5
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -144,135 +180,159 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
     x0 = tu * 8 * J;
     y0 = tv * 16;
   };
-  auto issue_tile_loads = [&](int t, int buf) {   // producer lane only
-    int b, y0, x0;
-    tile_coords(t, b, y0, x0);
-    ptx::mbar_arrive_expect_tx(bar(SB_X0 + buf), (uint32_t)(Cfg::P * Cfg::C * 2));
-    tma_load_4d(sbase + Cfg::OFF_STAGE + buf * Cfg::STAGE_BYTES, &p.tm_x, bar(SB_X0 + buf), 0, x0 - 1, y0 - 1, b);
-    if (SKIP) {
-      ptx::mbar_arrive_expect_tx(bar(SB_S0 + buf), (uint32_t)(Cfg::P * Cfg::C * 2));
-      tma_load_4d(sbase + Cfg::OFF_STAGE_S + buf * Cfg::STAGE_BYTES, &p.tm_skip, bar(SB_S0 + buf), 0, x0 - 1, y0 - 1, b);
-    }
-  };
+  const int n_local = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   // ---- one-time setup
-  if (warp == 4) {
-    ptx::tmem_alloc(sbase + 64, (uint32_t)Cfg::TMEM_COLS);
+  if (warp == 8) {
+    ptx::tmem_alloc(sbase + 128, (uint32_t)Cfg::TMEM_COLS);
     ptx::tmem_relinquish();
     if (lane == 0) {
-      for (int i = 0; i < SB_COUNT; ++i) ptx::mbar_init(bar(i), i == SB_DONE ? (uint32_t)J : 1u);
+      ptx::mbar_init(bar(SB_W), 1);
+      for (int s = 0; s < 2; ++s) {
+        ptx::mbar_init(bar(SB_X + s), 1);
+        ptx::mbar_init(bar(SB_S + s), 1);
+        ptx::mbar_init(bar(SB_XF + s), 128);
+        ptx::mbar_init(bar(SB_TF + s), (uint32_t)J);
+        ptx::mbar_init(bar(SB_TE + s), 128);
+        ptx::mbar_init(bar(SB_R + s), 1);
+      }
       ptx::fence_mbar_init();
-      ptx::mbar_arrive_expect_tx(bar(SB_W), (uint32_t)Cfg::W_BYTES);
-      ptx::bulk_g2s(sbase + Cfg::OFF_W, p.wpk, (uint32_t)Cfg::W_BYTES, bar(SB_W));
-      if ((int)blockIdx.x < p.ntiles) issue_tile_loads(blockIdx.x, 0);
     }
     __syncwarp();
   }
-  for (int i = tid; i < Cfg::N; i += SP_THREADS) sbias[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
+  for (int i = tid; i < Cfg::N; i += SP_THREADS) {
+    float bv = i < p.Cout ? __ldg(p.bias + i) : 0.f;
+    if (GATE && i >= Cfg::F) bv *= 0.5f;
+    sbias[i] = bv;
+  }
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t leader = ptx::elect_one();
   bool ok = true;
 
-  int it = 0;
-  for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
-    const int buf = it & 1;
-    const uint32_t par_buf = (uint32_t)((it >> 1) & 1), par_it = (uint32_t)(it & 1);
-    int b, y0, x0;
-    tile_coords(t, b, y0, x0);
-
-    if (warp == 4) {
-      // ---- producer: prefetch the next tile into the other buffer; fetch this tile's shortcut
-      if (lane == 0) {
-        const int tn = t + gridDim.x;
-        if (tn < p.ntiles) issue_tile_loads(tn, buf ^ 1);
+  if (warp == 8) {
+    // =========================== producer ===========================
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(bar(SB_W), (uint32_t)Cfg::W_BYTES);
+      ptx::bulk_g2s(sbase + Cfg::OFF_W, p.wpk, (uint32_t)Cfg::W_BYTES, bar(SB_W));
+      for (int it = 0; it < n_local && ok; ++it) {
+        const int s = it & 1;
+        const uint32_t prev = (uint32_t)(((it >> 1) - 1) & 1);    // parity of the previous use of buffer s
+        int b, y0, x0;
+        tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, y0, x0);
+        if (it >= 2) {
+          ok = ptx::mbar_wait(bar(SB_XF + s), prev);               // front finished reading stage[s]
+          if (!ok) { atomicCAS(p.status, 0, 21); break; }
+        }
+        ptx::mbar_arrive_expect_tx(bar(SB_X + s), (uint32_t)(Cfg::P * Cfg::C * 2));
+        tma_load_4d(sbase + Cfg::OFF_STAGE + s * Cfg::STAGE_BYTES, &p.tm_x, bar(SB_X + s), 0, x0 - 1, y0 - 1, b);
+        if (SKIP) {
+          ptx::mbar_arrive_expect_tx(bar(SB_S + s), (uint32_t)(Cfg::P * Cfg::C * 2));
+          tma_load_4d(sbase + Cfg::OFF_STAGE_S + s * Cfg::STAGE_BYTES, &p.tm_skip, bar(SB_S + s), 0, x0 - 1, y0 - 1, b);
+        }
         if (GATE && p.res_mode == 1) {
-          ptx::mbar_arrive_expect_tx(bar(SB_R), (uint32_t)Cfg::RES_BYTES);
-          tma_load_4d(sbase + Cfg::OFF_RES, &p.tm_res, bar(SB_R), 0, x0, y0, b);
+          if (it >= 2) {
+            ok = ptx::mbar_wait(bar(SB_TE + s), prev);             // back finished with res[s]
+            if (!ok) { atomicCAS(p.status, 0, 22); break; }
+          }
+          ptx::mbar_arrive_expect_tx(bar(SB_R + s), (uint32_t)Cfg::RES_BYTES);
+          tma_load_4d(sbase + Cfg::OFF_RES + s * Cfg::RES_BYTES, &p.tm_res, bar(SB_R + s), 0, x0, y0, b);
         }
       }
-      __syncwarp();
-    } else {
-      // ---- transform: raw stage -> concat_elu planes
-      ok = ok && ptx::mbar_wait(bar(SB_X0 + buf), par_buf);
-      if (!ok) atomicCAS(p.status, 0, 11);
-      transform_tile<Cfg>(smem + Cfg::OFF_STAGE + buf * Cfg::STAGE_BYTES, planes, tid);
-      if (SKIP) {
-        ok = ok && ptx::mbar_wait(bar(SB_S0 + buf), par_buf);
-        if (!ok) atomicCAS(p.status, 0, 12);
-        transform_tile<Cfg>(smem + Cfg::OFF_STAGE_S + buf * Cfg::STAGE_BYTES, planes_s, tid);
-      }
-      ptx::fence_proxy_async_smem();
     }
-    ptx::tc_fence_before_sync();
-    __syncthreads();                       // planes complete; stage[buf] consumed
-    ptx::tc_fence_after_sync();
-
-    if (warp < J) {
-      // ---- MMA issue: sub-tile j = warp, fully unrolled program, immediate descriptor offsets
-      if (it == 0) {
-        ok = ok && ptx::mbar_wait(bar(SB_W), 0);
+    __syncwarp();
+  } else if (warp < 4) {
+    // =========================== front: transform + MMA issue ===========================
+    const uint32_t leader = ptx::elect_one();
+    constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, Cfg::N);
+    const uint64_t b_tmpl = ptx::smem_desc(sbase + Cfg::OFF_W, Cfg::N * 16, 128);
+    for (int it = 0; it < n_local; ++it) {
+      const int s = it & 1;
+      const uint32_t cur = (uint32_t)((it >> 1) & 1), prev = cur ^ 1u;
+      const uint32_t planes = sbase + Cfg::OFF_PLANES + s * Cfg::PLANE_BYTES;
+      const uint32_t planes_s = sbase + Cfg::OFF_PLANES_S + s * Cfg::PLANE_BYTES;
+      ok = ok && ptx::mbar_wait(bar(SB_X + s), cur);                // raw tile landed
+      if (it >= 2) ok = ok && ptx::mbar_wait(bar(SB_TF + s), prev); // MMAs of tile it-2 no longer read planes[s]
+      if (!ok) atomicCAS(p.status, 0, 11);
+      transform_tile<Cfg>(sbase + Cfg::OFF_STAGE + s * Cfg::STAGE_BYTES, planes, tid);
+      if (SKIP) {
+        ok = ok && ptx::mbar_wait(bar(SB_S + s), cur);
+        if (!ok) atomicCAS(p.status, 0, 12);
+        transform_tile<Cfg>(sbase + Cfg::OFF_STAGE_S + s * Cfg::STAGE_BYTES, planes_s, tid);
+      }
+      ptx::mbar_arrive(bar(SB_XF + s));                             // stage[s] may be refilled
+      ptx::fence_proxy_async_smem();                                // planes -> visible to the tensor core
+      front_barrier();
+      if (warp < J) {
+        // sub-tile j = warp: fully unrolled k-step program, immediate descriptor offsets
+        if (it == 0) ok = ok && ptx::mbar_wait(bar(SB_W), 0);
+        if (it >= 2) ok = ok && ptx::mbar_wait(bar(SB_TE + s), prev);   // back drained accumulator buffer s
         if (!ok) atomicCAS(p.status, 0, 13);
         ptx::tc_fence_after_sync();
-      }
-      constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, Cfg::N);
-      const uint64_t a_tmpl = ptx::smem_desc(sbase + Cfg::OFF_PLANES, Cfg::PPAD * 16, Cfg::PU * 16) + (uint64_t)(8 * warp);
-      const uint64_t b_tmpl = ptx::smem_desc(sbase + Cfg::OFF_W, Cfg::N * 16, 128);
-      const uint32_t d_tmem = tmem_base + (uint32_t)(warp * Cfg::N);
+        const uint64_t a_tmpl = ptx::smem_desc(planes, Cfg::PPAD * 16, Cfg::PU * 16) + (uint64_t)(8 * warp);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(s * Cfg::ACC_COLS + warp * Cfg::N);
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-        for (int kk = 0; kk < Cfg::KS; ++kk) {
-          const uint32_t a_off = (uint32_t)(((tap / 3) * Cfg::PU + (tap % 3)) * 16 + kk * 2 * Cfg::PPAD * 16) >> 4;
-          const uint32_t b_off = (uint32_t)((tap * Cfg::KS + kk) * Cfg::N * 32) >> 4;
-          if (leader) ptx::mma_bf16_ss(d_tmem, a_tmpl + a_off, b_tmpl + b_off, idesc, (tap | kk) ? 1u : 0u);
+          for (int kk = 0; kk < Cfg::KS; ++kk) {
+            const uint32_t a_off = (uint32_t)(((tap / 3) * Cfg::PU + (tap % 3)) * 16 + kk * 2 * Cfg::PPAD * 16) >> 4;
+            const uint32_t b_off = (uint32_t)((tap * Cfg::KS + kk) * Cfg::N * 32) >> 4;
+            if (leader) ptx::mma_bf16_ss(d_tmem, a_tmpl + a_off, b_tmpl + b_off, idesc, (tap | kk) ? 1u : 0u);
+          }
         }
-      }
-      if (SKIP) {
-        const uint64_t s_tmpl = ptx::smem_desc(sbase + Cfg::OFF_PLANES_S + (Cfg::PU + 1) * 16, Cfg::PPAD * 16, Cfg::PU * 16) +
-                                (uint64_t)(8 * warp);
+        if (SKIP) {
+          const uint64_t s_tmpl = ptx::smem_desc(planes_s + (Cfg::PU + 1) * 16, Cfg::PPAD * 16, Cfg::PU * 16) + (uint64_t)(8 * warp);
 #pragma unroll
-        for (int kk = 0; kk < Cfg::KS; ++kk) {
-          const uint32_t a_off = (uint32_t)(kk * 2 * Cfg::PPAD * 16) >> 4;
-          const uint32_t b_off = (uint32_t)((9 * Cfg::KS + kk) * Cfg::N * 32) >> 4;
-          if (leader) ptx::mma_bf16_ss(d_tmem, s_tmpl + a_off, b_tmpl + b_off, idesc, 1u);
+          for (int kk = 0; kk < Cfg::KS; ++kk) {
+            const uint32_t a_off = (uint32_t)(kk * 2 * Cfg::PPAD * 16) >> 4;
+            const uint32_t b_off = (uint32_t)((9 * Cfg::KS + kk) * Cfg::N * 32) >> 4;
+            if (leader) ptx::mma_bf16_ss(d_tmem, s_tmpl + a_off, b_tmpl + b_off, idesc, 1u);
+          }
         }
+        if (leader) ptx::mma_commit(bar(SB_TF + s));
+        __syncwarp();
       }
-      if (leader) ptx::mma_commit(bar(SB_DONE));
-      __syncwarp();
     }
-
-    if (warp < 4) {
-      // ---- epilogue: TMEM -> registers -> (+bias, gate, shortcut) -> bf16 NHWC
-      ok = ok && ptx::mbar_wait(bar(SB_DONE), par_it);
+  } else {
+    // =========================== back: epilogue ===========================
+    const int r = tid - 128;                 // accumulator row == TMEM lane
+    const int v = r >> 3, u = r & 7;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int it = 0; it < n_local; ++it) {
+      const int s = it & 1;
+      const uint32_t cur = (uint32_t)((it >> 1) & 1);
+      int b, y0, x0;
+      tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, y0, x0);
+      ok = ok && ptx::mbar_wait(bar(SB_TF + s), cur);
       if (!ok) atomicCAS(p.status, 0, 14);
       ptx::tc_fence_after_sync();
       if (GATE && p.res_mode == 1) {
-        ok = ok && ptx::mbar_wait(bar(SB_R), par_it);
+        ok = ok && ptx::mbar_wait(bar(SB_R + s), cur);
         if (!ok) atomicCAS(p.status, 0, 15);
       }
-      const int v = tid >> 3, u = tid & 7;
-      const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
       const int oy = y0 + v;
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         const int ox = x0 + 8 * j + u;
         const bool live = ok && oy < p.H && ox < p.W;
         const size_t pix = ((size_t)b * p.H + oy) * p.W + ox;
-        const uint32_t col0 = lane_base + (uint32_t)(j * Cfg::N);
+        const uint32_t col0 = lane_base + (uint32_t)(s * Cfg::ACC_COLS + j * Cfg::N);
 #pragma unroll
         for (int c0 = 0; c0 < Cfg::F; c0 += 8) {
           float o[8];
           if (GATE) {
             float a[8], g[8];
             ptx::tmem_ld8x2(col0 + c0, col0 + Cfg::F + c0, a, g);
+            // u * sigmoid(v) with sigmoid(z) = 0.5 + 0.5 tanh(z/2); the v bias is stored pre-halved
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = (a[i] + sbias[c0 + i]) * sigmoid_f(g[i] + sbias[Cfg::F + c0 + i]);
+            for (int i = 0; i < 8; ++i) {
+              const float th = tanh_approx(fmaf(g[i], 0.5f, sbias[Cfg::F + c0 + i]));
+              o[i] = (a[i] + sbias[c0 + i]) * fmaf(th, 0.5f, 0.5f);
+            }
             if (p.res_mode == 1) {
               bf16x8 rr;
-              rr.v = *reinterpret_cast<const uint4*>(smem + Cfg::OFF_RES + ((size_t)(v * 8 * J + 8 * j + u) * Cfg::F + c0) * 2);
+              rr.v = lds128(sbase + Cfg::OFF_RES + s * Cfg::RES_BYTES + (uint32_t)((v * 8 * J + 8 * j + u) * Cfg::F + c0) * 2u);
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] += __bfloat162float(rr.h[i]);
             } else if (p.res_mode == 2 && live) {
@@ -291,13 +351,18 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
           }
         }
       }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(bar(SB_TE + s));        // accumulator buffer s and res[s] are free
     }
-    ptx::tc_fence_before_sync();
-    __syncthreads();                       // accumulators drained, planes and shortcut tile reusable
-    ptx::tc_fence_after_sync();
   }
 
-  if (warp == 4) ptx::tmem_dealloc(tmem_base, (uint32_t)Cfg::TMEM_COLS);
+  // ---- teardown
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)Cfg::TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -382,7 +447,7 @@ static int launch_s1p(const fn_conv_desc& d, cudaStream_t stream) {
   int per_sm = (227 * 1024) / (Cfg::SMEM + 1024);
   const int tmem_lim = 512 / Cfg::TMEM_COLS;
   if (per_sm > tmem_lim) per_sm = tmem_lim;
-  if (per_sm > 6) per_sm = 6;
+  if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
   int grid = 148 * per_sm;
   if (grid > p.ntiles) grid = p.ntiles;
@@ -402,13 +467,16 @@ bool conv_s1p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
   if (skip && (gate || d.Cskip != d.Cin)) return false;
   if (d.H < 16) return false;                       // short images use the transposed orientation of k_conv_tc
   if (get_encode() == nullptr) return false;
-  const int clog = d.Cin == 8 ? 0 : d.Cin == 16 ? 1 : -1;
+  const int clog = d.Cin == 8 ? 0 : d.Cin == 16 ? 1 : d.Cin == 32 ? 2 : -1;
   if (clog < 0) return false;
-  // widest tile that divides the row and still leaves room for >= 3 CTAs per SM (cases are ordered by J)
-#define SP_CASE(CL, JJ, G, S)                                                                              \
-  if (clog == CL && ((d.W % (8 * JJ)) == 0 || JJ == 1) && gate == G && skip == S && SpCfg<CL, JJ, G, S>::SMEM <= 75 * 1024) { \
-    if (!dry_run) rc = launch_s1p<CL, JJ, G, S>(d, stream);                                                \
-    return true;                                                                                           \
+  static const int smem_cap_kb = getenv("FLOWNET_S1P_SMEM_KB") ? atoi(getenv("FLOWNET_S1P_SMEM_KB")) : 112;
+  // widest tile that divides the row and still leaves room for 2 CTAs per SM (cases are ordered by J);
+  // C = 32 carries up to 73 KB of weights and runs one CTA per SM
+#define SP_CASE(CL, JJ, G, S)                                                                     \
+  if (clog == CL && ((d.W % (8 * JJ)) == 0 || JJ == 1) && gate == G && skip == S &&               \
+      SpCfg<CL, JJ, G, S>::SMEM <= (CL == 2 ? 200 : smem_cap_kb) * 1024) {                        \
+    if (!dry_run) rc = launch_s1p<CL, JJ, G, S>(d, stream);                                       \
+    return true;                                                                                  \
   }
   SP_CASE(0, 4, true, false) SP_CASE(0, 4, false, false) SP_CASE(0, 4, false, true)
   SP_CASE(0, 2, true, false) SP_CASE(0, 2, false, false) SP_CASE(0, 2, false, true)
@@ -416,6 +484,8 @@ bool conv_s1p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
   SP_CASE(1, 4, true, false) SP_CASE(1, 4, false, false) SP_CASE(1, 4, false, true)
   SP_CASE(1, 2, true, false) SP_CASE(1, 2, false, false) SP_CASE(1, 2, false, true)
   SP_CASE(1, 1, true, false) SP_CASE(1, 1, false, false) SP_CASE(1, 1, false, true)
+  SP_CASE(2, 2, true, false) SP_CASE(2, 2, false, false) SP_CASE(2, 2, false, true)
+  SP_CASE(2, 1, true, false) SP_CASE(2, 1, false, false) SP_CASE(2, 1, false, true)
 #undef SP_CASE
   return false;
 }

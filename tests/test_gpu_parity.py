@@ -176,6 +176,12 @@ S1P_CASES = [
     ("ragged_skip", 2, 23, 41, 16, 16, 1, 1, 0, True, None, False),
     ("many_tiles_persistent", 40, 64, 64, 8, 16, 1, 1, 1, False, None, False),
     ("w16_J2", 2, 16, 16, 8, 16, 1, 1, 1, False, None, False),
+    ("l3_conv2_gate_c32", 4, 32, 64, 32, 64, 1, 1, 1, False, None, False),
+    ("l3_conv1_c32", 4, 32, 64, 32, 32, 1, 1, 0, False, None, False),
+    ("l3_conv1_skip_c32", 3, 32, 64, 32, 32, 1, 1, 0, True, None, False),
+    ("l3_pool_pad_c32", 2, 32, 32, 32, 64, 1, 1, 1, False, 16, True),
+    ("single_tile", 1, 16, 8, 8, 16, 1, 1, 1, False, None, False),
+    ("three_tiles_per_cta", 148 * 3, 16, 32, 8, 16, 1, 1, 1, False, None, False),
 ]
 
 
@@ -190,7 +196,7 @@ def test_persistent_tma_kernel_vs_generic_and_oracle(native, case):
     finally:
         native.lib.fn_debug_set_use_s1p(1)
     assert rel_l2(y, ref) < LAYER_TOL
-    assert rel_l2(y, yg) < 1e-4          # same MMA order, same bf16 rounding points
+    assert rel_l2(y, yg) < 5e-4          # same MMA order; the gate uses tanh.approx here, ex2+rcp there
 
 
 def test_tcgen05_refuses_shapes_it_has_no_kernel_for(native):
