@@ -146,6 +146,35 @@ int fn_l2_loss(const float* p, const float* t, float* loss, float* grad, int64_t
 int fn_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, int64_t step,
                  double lr, double beta1, double beta2, double eps, void* stream);
 
+/* ---- training step: adjoints TF autodiff builds for flow_net.train (model/flow_net.py:44-46).
+ * Data gradients of the convolutions are FORWARD launches on the gradient tensor (fn_conv_fwd with
+ * flipped/transposed weights for stride 1; fn_tconv_fwd <-> stride-2 fn_conv_fwd for the strided pair);
+ * activation gradients are bf16, parameter gradients fp32. */
+
+/* gate y = u*sigmoid(v) (flow_architecture.py:150-151): c2 = [u|v] bf16 [npix,2F], g bf16 [npix,F] -> dc2 bf16 [npix,2F] */
+int fn_gate_bwd(const void* c2, const void* g, void* dc2, int64_t npix, int32_t F, void* stream);
+/* adjoint of the prologue nonlinearity (+dropout mask of the forward): dA bf16 [npix, mult*C], x bf16 [npix,C]
+ * -> dx bf16 [npix,C] (accumulate != 0: added to the existing dx) */
+int fn_prologue_bwd(const void* dA, const void* x, void* dx, int64_t npix, int32_t C, int32_t kind, int32_t accumulate,
+                    float keep_prob, uint64_t seed, void* stream);
+/* adjoint of the res_block shortcut (avg-pool 2x2 'SAME' if pooled, front channel pad; :153-165):
+ * g bf16 [B,OH,OW,F] -> dx bf16 [B,H,W,Cin] */
+int fn_shortcut_bwd(const void* g, void* dx, int32_t B, int32_t OH, int32_t OW, int32_t F, int32_t H, int32_t W,
+                    int32_t Cin, int32_t pooled, int32_t accumulate, void* stream);
+/* loss += sum((p-t)^2)/2 (flow_net.py:39-42) and the gradient w.r.t. the pre-tanh tail output, written as
+ * bf16 [npix, 8] with channels 2..7 zero (so the tail's dgrad/wgrad run as 8-channel launches) */
+int fn_tanh_l2_bwd(const float* p, const float* t, float* loss, void* dpre, int64_t npix, void* stream);
+/* db[n] = sum_pix dY[pix][n]; workspace: fn_bias_grad_workspace() floats */
+int64_t fn_bias_grad_workspace(int64_t npix, int32_t N);
+int fn_bias_grad(const void* dY, float* db, float* workspace, int64_t npix, int32_t N, void* stream);
+/* dW[tap][k][n] = sum_pix pro(x)[pix*s+tap-pad][k] * dY[pix][n]; d describes the FORWARD launch (x, dims, ksize,
+ * stride, prologue, keep_prob, dropout_seed); dW fp32 [k*k, Keff, Cout]; workspace: fn_conv_wgrad_workspace() floats */
+int64_t fn_conv_wgrad_workspace(const fn_conv_desc* d);
+int fn_conv_wgrad(const fn_conv_desc* d, const void* dY, float* dW, float* workspace, void* stream);
+/* transposed conv: dW fp32 [9, Cin, Cout] from x bf16 [B,H,W,Cin] and dY bf16 [B,2H,2W,Cout] */
+int64_t fn_tconv_wgrad_workspace(const fn_tconv_desc* d);
+int fn_tconv_wgrad(const fn_tconv_desc* d, const void* dY, float* dW, float* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

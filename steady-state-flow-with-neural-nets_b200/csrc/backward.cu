@@ -1,0 +1,405 @@
+// Backward pieces of the flow_net training step (reference: flow_net.train -> AdamOptimizer.minimize,
+// model/flow_net.py:44-46, i.e. TF autodiff of flow_architecture.py:129-248).  Data gradients of the
+// convolutions reuse the FORWARD kernels (a stride-1 conv's dgrad is a stride-1 conv with flipped,
+// transposed weights; a stride-2 conv's dgrad is the transposed conv with the same weights and vice
+// versa), so what lives here is:
+//   * the pointwise adjoints of the fused prologues / epilogues (concat_elu & co, gate, shortcut,
+//     tanh + l2 loss),
+//   * the weight / bias gradient reductions (CUDA-core, correctness-first: two-stage, deterministic).
+// Activation gradients are stored bf16 (like activations), parameter gradients fp32.
+#include "common.cuh"
+
+namespace fn {
+
+constexpr int BW_THREADS = 256;
+static inline int bw_grid(long long items) {
+  long long g = (items + BW_THREADS - 1) / BW_THREADS;
+  const long long cap = 148LL * 8;
+  return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+// ---- gate: y = u * sigmoid(v)  ->  du = g*s, dv = g*u*s*(1-s)          (flow_architecture.py:150-151)
+__global__ void k_gate_bwd(const __nv_bfloat16* __restrict__ c2, const __nv_bfloat16* __restrict__ g,
+                           __nv_bfloat16* __restrict__ dc2, long long npix, int F) {
+  const long long total = npix * F;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / F;
+    const int c = (int)(i % F);
+    const float u = __bfloat162float(c2[p * 2 * F + c]);
+    const float v = __bfloat162float(c2[p * 2 * F + F + c]);
+    const float gg = __bfloat162float(g[i]);
+    const float s = 1.f / (1.f + __expf(-v));
+    dc2[p * 2 * F + c] = __float2bfloat16(gg * s);
+    dc2[p * 2 * F + F + c] = __float2bfloat16(gg * u * s * (1.f - s));
+  }
+}
+
+// ---- prologue adjoint: dx (+)= dA0 * f'(x) [- dA1 * f'(-x)]             (flow_architecture.py:14-29, 143-145)
+__device__ __forceinline__ float elu_grad(float z) { return z > 0.f ? 1.f : __expf(z); }
+__global__ void k_prologue_bwd(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ x,
+                               __nv_bfloat16* __restrict__ dx, long long npix, int C, int kind, int accumulate,
+                               float keep_prob, unsigned long long seed) {
+  const int mult = pro_mult(kind);
+  const long long total = npix * C;
+  const bool drop = keep_prob < 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / C;
+    const int c = (int)(i % C);
+    const float xv = __bfloat162float(x[i]);
+    float a0 = __bfloat162float(dA[p * mult * C + c]);
+    float a1 = mult == 2 ? __bfloat162float(dA[p * mult * C + C + c]) : 0.f;
+    if (drop) {   // the forward scaled prologue output k of pixel p by dropout_scale(seed, p*Keff + k)
+      a0 *= dropout_scale(seed, (unsigned long long)(p * mult * C + c), keep_prob);
+      if (mult == 2) a1 *= dropout_scale(seed, (unsigned long long)(p * mult * C + C + c), keep_prob);
+    }
+    float d;
+    switch (kind) {
+      case FN_PRO_CONCAT_ELU:  d = a0 * elu_grad(xv) - a1 * elu_grad(-xv); break;
+      case FN_PRO_ELU:         d = a0 * elu_grad(xv); break;
+      case FN_PRO_CONCAT_RELU: d = (xv > 0.f ? a0 : 0.f) - (xv < 0.f ? a1 : 0.f); break;
+      case FN_PRO_RELU:        d = xv > 0.f ? a0 : 0.f; break;
+      default:                 d = a0; break;
+    }
+    if (accumulate) d += __bfloat162float(dx[i]);
+    dx[i] = __float2bfloat16(d);
+  }
+}
+
+// ---- shortcut adjoint: out = pad_front(avgpool?(x)) + ...  ->  dx (+)= slice(g) [/4 broadcast]   (:153-165)
+__global__ void k_shortcut_bwd(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dx, int B, int OH, int OW,
+                               int F, int H, int W, int Cin, int pooled, int accumulate) {
+  const long long total = (long long)B * H * W * Cin;
+  const int shift = F - Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cin);
+    long long r = i / Cin;
+    const int xw = (int)(r % W);
+    r /= W;
+    const int yh = (int)(r % H);
+    const int b = (int)(r / H);
+    float d;
+    if (pooled) {
+      const int oy = yh >> 1, ox = xw >> 1;
+      const int cnt = (min(2 * oy + 2, H) - 2 * oy) * (min(2 * ox + 2, W) - 2 * ox);   // TF 'SAME' edge windows
+      d = __bfloat162float(g[(((long long)b * OH + oy) * OW + ox) * F + shift + c]) / (float)cnt;
+    } else {
+      d = __bfloat162float(g[(((long long)b * OH + yh) * OW + xw) * F + shift + c]);
+    }
+    if (accumulate) d += __bfloat162float(dx[i]);
+    dx[i] = __float2bfloat16(d);
+  }
+}
+
+// ---- tanh + l2 loss: loss += sum((p-t)^2)/2 ; dpre[pix, 0..1] = (p-t)*(1-p^2), channels 2..7 = 0
+__global__ void k_tanh_l2_bwd(const float* __restrict__ p, const float* __restrict__ t, float* loss,
+                              __nv_bfloat16* __restrict__ dpre, long long npix) {
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    bf16x8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.h[j] = __float2bfloat16(0.f);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float pv = p[i * 2 + c];
+      const float d = pv - t[i * 2 + c];
+      s = fmaf(d, d, s);
+      o.h[c] = __float2bfloat16(d * (1.f - pv * pv));
+    }
+    *reinterpret_cast<uint4*>(dpre + i * 8) = o.v;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float ws[BW_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < BW_THREADS / 32 ? ws[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, 0.5f * s);
+  }
+}
+
+// ---- deterministic second stage: out[i] = sum_s partial[s][i]
+__global__ void k_reduce_partials(const float* __restrict__ partial, float* __restrict__ out, long long n, int S) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < S; ++k) s += partial[(long long)k * n + i];
+    out[i] = s;
+  }
+}
+
+// ---- bias gradient: db[n] = sum_p dY[p][n]; stage 1 writes partial[blockIdx.x][n]
+__global__ void k_bias_grad(const __nv_bfloat16* __restrict__ dY, float* __restrict__ partial, long long npix, int N) {
+  // thread -> column n = tid % N (N <= 256 divides 256 for the network's widths, else tail threads idle)
+  const int per = BW_THREADS / N > 0 ? BW_THREADS / N : 1;
+  const int n = threadIdx.x % N, rg = threadIdx.x / N;
+  float s = 0.f;
+  if (rg < per && threadIdx.x < per * N) {
+    const long long p0 = (long long)blockIdx.x * per + rg;
+    for (long long pp = p0; pp < npix; pp += (long long)gridDim.x * per) s += __bfloat162float(dY[pp * N + n]);
+  }
+  __shared__ float sm[BW_THREADS];
+  sm[threadIdx.x] = (rg < per && threadIdx.x < per * N) ? s : 0.f;
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float a = 0.f;
+    for (int r = 0; r < per; ++r) a += sm[r * N + threadIdx.x];
+    partial[(long long)blockIdx.x * N + threadIdx.x] = a;
+  }
+}
+
+// ---- weight gradient of a 'SAME' conv: dW[tap][k][n] = sum_pix pro(x)[pix*s + tap - pad][k] * dY[pix][n]
+// CTA = one (tap, 16 k, 16 n) tile over one slice of the pixels; thread = one (k, n) pair.
+struct WgradParams {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* dY;
+  float* partial;      // [S][T][Keff][N]
+  int B, H, W, C, OH, OW, N, ksize, stride, pad_t, pad_l, pro, Keff;
+  int transposed;      // 1: transposed conv: x is the INPUT [B,H,W,C] and dY the 2x output [B,OH,OW,N]
+  float keep_prob;
+  unsigned long long seed;
+  int kt, nt;          // number of 16-wide k / n tiles
+};
+
+constexpr int WG_PIX = 32;
+
+__global__ void __launch_bounds__(256) k_conv_wgrad(const WgradParams p) {
+  __shared__ float sa[WG_PIX][17];
+  __shared__ float sd[WG_PIX][17];
+  int tile = blockIdx.x;
+  const int nti = tile % p.nt;
+  tile /= p.nt;
+  const int kti = tile % p.kt;
+  const int tap = tile / p.kt;
+  const int di = tap / p.ksize, dj = tap % p.ksize;
+  const int kl = threadIdx.x >> 4, nl = threadIdx.x & 15;     // (k, n) owned by this thread
+  const int mult = pro_mult(p.pro);
+  // GEMM-row pixels: conv -> output pixels (OH x OW); transposed conv -> input pixels (H x W)
+  const int RH = p.transposed ? p.H : p.OH, RW = p.transposed ? p.W : p.OW;
+  const long long rows = (long long)p.B * RH * RW;
+  const long long per_split = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = (long long)blockIdx.y * per_split;
+  const long long r1 = min(rows, r0 + per_split);
+  float acc = 0.f;
+  for (long long base = r0; base < r1; base += WG_PIX) {
+    // stage WG_PIX rows: 16 activations (k tile) and 16 output-gradient values (n tile) each
+    for (int i = threadIdx.x; i < WG_PIX * 32; i += 256) {
+      const int pr = i >> 5, col = i & 31;
+      const long long row = base + pr;
+      float v = 0.f;
+      if (row < r1) {
+        const int rx = (int)(row % RW);
+        const int ry = (int)((row / RW) % RH);
+        const int b = (int)(row / ((long long)RW * RH));
+        if (col < 16) {                       // activation for k = kti*16 + col
+          const int k = kti * 16 + col;
+          if (k < p.Keff) {
+            int iy, ix;
+            if (p.transposed) { iy = ry; ix = rx; }
+            else { iy = ry * p.stride + di - p.pad_t; ix = rx * p.stride + dj - p.pad_l; }
+            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+              const int c = k >= p.C ? k - p.C : k;
+              const long long pidx = ((long long)b * p.H + iy) * p.W + ix;
+              float p0, p1;
+              pro_apply(p.pro, __bfloat162float(p.x[pidx * p.C + c]), p0, p1);
+              v = (mult == 2 && k >= p.C) ? p1 : p0;
+              if (p.pro != FN_PRO_NONE) v = __bfloat162float(__float2bfloat16(v));   // the forward operand was bf16
+              if (p.keep_prob < 1.0f) v *= dropout_scale(p.seed, (unsigned long long)(pidx * p.Keff + k), p.keep_prob);
+            }
+          }
+          sa[pr][col] = v;
+        } else {                              // output gradient for n = nti*16 + (col-16)
+          const int n = nti * 16 + (col - 16);
+          if (n < p.N) {
+            int oy, ox;
+            bool ok = true;
+            if (p.transposed) {               // out[2i+di, 2j+dj] <- in[i,j] * W[di,dj]   
+              oy = 2 * ry + di; ox = 2 * rx + dj;
+              ok = oy < p.OH && ox < p.OW;
+            } else { oy = ry; ox = rx; }
+            if (ok) v = __bfloat162float(p.dY[(((long long)b * p.OH + oy) * p.OW + ox) * p.N + n]);
+          }
+          sd[pr][col - 16] = v;
+        }
+      } else {
+        if (col < 16) sa[pr][col] = 0.f; else sd[pr][col - 16] = 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int pr = 0; pr < WG_PIX; ++pr) acc = fmaf(sa[pr][kl], sd[pr][nl], acc);
+    __syncthreads();
+  }
+  const int k = kti * 16 + kl, n = nti * 16 + nl;
+  if (k < p.Keff && n < p.N) {
+    const long long T = (long long)p.ksize * p.ksize;
+    p.partial[(((long long)blockIdx.y * T + tap) * p.Keff + k) * p.N + n] = acc;
+  }
+}
+
+static int reduce_partials(const float* partial, float* out, long long n, int S, cudaStream_t s) {
+  k_reduce_partials<<<bw_grid(n), BW_THREADS, 0, s>>>(partial, out, n, S);
+  count_launch();
+  return check_launch("k_reduce_partials");
+}
+
+int gate_bwd(const void* c2, const void* g, void* dc2, long long npix, int F, cudaStream_t s) {
+  if (npix == 0) return 0;
+  k_gate_bwd<<<bw_grid(npix * F), BW_THREADS, 0, s>>>((const __nv_bfloat16*)c2, (const __nv_bfloat16*)g, (__nv_bfloat16*)dc2, npix, F);
+  count_launch();
+  return check_launch("k_gate_bwd");
+}
+
+int prologue_bwd(const void* dA, const void* x, void* dx, long long npix, int C, int kind, int accumulate, float keep_prob,
+                 unsigned long long seed, cudaStream_t s) {
+  if (npix == 0) return 0;
+  k_prologue_bwd<<<bw_grid(npix * C), BW_THREADS, 0, s>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx,
+                                                          npix, C, kind, accumulate, keep_prob, seed);
+  count_launch();
+  return check_launch("k_prologue_bwd");
+}
+
+int shortcut_bwd(const void* g, void* dx, int B, int OH, int OW, int F, int H, int W, int Cin, int pooled, int accumulate,
+                 cudaStream_t s) {
+  const long long total = (long long)B * H * W * Cin;
+  if (total == 0) return 0;
+  k_shortcut_bwd<<<bw_grid(total), BW_THREADS, 0, s>>>((const __nv_bfloat16*)g, (__nv_bfloat16*)dx, B, OH, OW, F, H, W, Cin,
+                                                       pooled, accumulate);
+  count_launch();
+  return check_launch("k_shortcut_bwd");
+}
+
+int tanh_l2_bwd(const float* p, const float* t, float* loss, void* dpre, long long npix, cudaStream_t s) {
+  if (npix == 0) return 0;
+  k_tanh_l2_bwd<<<bw_grid(npix), BW_THREADS, 0, s>>>(p, t, loss, (__nv_bfloat16*)dpre, npix);
+  count_launch();
+  return check_launch("k_tanh_l2_bwd");
+}
+
+long long bias_grad_workspace(long long npix, int N) {
+  (void)npix;
+  return (long long)148 * 2 * N;
+}
+int bias_grad(const void* dY, float* db, float* workspace, long long npix, int N, cudaStream_t s) {
+  FN_REQUIRE(N >= 1 && N <= BW_THREADS, FN_E_UNSUPPORTED, "bias_grad: N=%d out of range", N);
+  const int S = 148 * 2;
+  k_bias_grad<<<S, BW_THREADS, 0, s>>>((const __nv_bfloat16*)dY, workspace, npix, N);
+  count_launch();
+  int rc = check_launch("k_bias_grad");
+  if (rc) return rc;
+  return reduce_partials(workspace, db, N, S, s);
+}
+
+static int wgrad_splits(long long rows) {
+  long long S = rows / 2048;
+  if (S < 1) S = 1;
+  if (S > 64) S = 64;
+  return (int)S;
+}
+long long wgrad_workspace(long long rows, int T, int Keff, int N) { return (long long)wgrad_splits(rows) * T * Keff * N; }
+
+int conv_wgrad_launch(WgradParams& p, float* dW, float* workspace, cudaStream_t s) {
+  const int T = p.ksize * p.ksize;
+  p.kt = (p.Keff + 15) / 16;
+  p.nt = (p.N + 15) / 16;
+  const long long rows = (long long)p.B * (p.transposed ? (long long)p.H * p.W : (long long)p.OH * p.OW);
+  const int S = wgrad_splits(rows);
+  p.partial = workspace;
+  dim3 grid((unsigned)(T * p.kt * p.nt), (unsigned)S);
+  k_conv_wgrad<<<grid, 256, 0, s>>>(p);
+  count_launch();
+  int rc = check_launch("k_conv_wgrad");
+  if (rc) return rc;
+  return reduce_partials(workspace, dW, (long long)T * p.Keff * p.N, S, s);
+}
+
+}  // namespace fn
+
+using namespace fn;
+
+extern "C" {
+
+int fn_gate_bwd(const void* c2, const void* g, void* dc2, int64_t npix, int32_t F, void* stream) {
+  FN_REQUIRE(c2 && g && dc2 && npix >= 0 && F > 0, FN_E_INVAL, "fn_gate_bwd: bad arguments");
+  return gate_bwd(c2, g, dc2, npix, F, (cudaStream_t)stream);
+}
+
+int fn_prologue_bwd(const void* dA, const void* x, void* dx, int64_t npix, int32_t C, int32_t kind, int32_t accumulate,
+                    float keep_prob, uint64_t seed, void* stream) {
+  FN_REQUIRE(dA && x && dx && npix >= 0 && C > 0, FN_E_INVAL, "fn_prologue_bwd: bad arguments");
+  FN_REQUIRE(kind >= FN_PRO_NONE && kind <= FN_PRO_RELU, FN_E_INVAL, "fn_prologue_bwd: bad kind %d", kind);
+  return prologue_bwd(dA, x, dx, npix, C, kind, accumulate, keep_prob, seed, (cudaStream_t)stream);
+}
+
+int fn_shortcut_bwd(const void* g, void* dx, int32_t B, int32_t OH, int32_t OW, int32_t F, int32_t H, int32_t W, int32_t Cin,
+                    int32_t pooled, int32_t accumulate, void* stream) {
+  FN_REQUIRE(g && dx && B > 0 && OH > 0 && OW > 0 && F > 0 && H > 0 && W > 0 && Cin > 0 && Cin <= F, FN_E_INVAL,
+             "fn_shortcut_bwd: bad arguments");
+  return shortcut_bwd(g, dx, B, OH, OW, F, H, W, Cin, pooled, accumulate, (cudaStream_t)stream);
+}
+
+int fn_tanh_l2_bwd(const float* p, const float* t, float* loss, void* dpre, int64_t npix, void* stream) {
+  FN_REQUIRE(p && t && dpre && npix >= 0, FN_E_INVAL, "fn_tanh_l2_bwd: bad arguments");
+  return tanh_l2_bwd(p, t, loss, dpre, npix, (cudaStream_t)stream);
+}
+
+int64_t fn_bias_grad_workspace(int64_t npix, int32_t N) { return bias_grad_workspace(npix, N); }
+int fn_bias_grad(const void* dY, float* db, float* workspace, int64_t npix, int32_t N, void* stream) {
+  FN_REQUIRE(dY && db && workspace && npix >= 0, FN_E_INVAL, "fn_bias_grad: bad arguments");
+  return bias_grad(dY, db, workspace, npix, N, (cudaStream_t)stream);
+}
+
+int64_t fn_conv_wgrad_workspace(const fn_conv_desc* d) {
+  if (!d) return 0;
+  const int OH = (d->H + d->stride - 1) / d->stride, OW = (d->W + d->stride - 1) / d->stride;
+  return wgrad_workspace((long long)d->B * OH * OW, d->ksize * d->ksize, d->Cin * pro_mult(d->prologue), d->Cout);
+}
+
+/* d describes the FORWARD conv (x, dims, ksize, stride, prologue, keep_prob/seed; w, bias, y are ignored);
+ * dY: bf16 [B,OH,OW,Cout]; dW: fp32 [k*k, Keff, Cout] (TF HWIO flattened) */
+int fn_conv_wgrad(const fn_conv_desc* d, const void* dY, float* dW, float* workspace, void* stream) {
+  FN_REQUIRE(d && d->x && dY && dW && workspace, FN_E_INVAL, "fn_conv_wgrad: null argument");
+  FN_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, FN_E_INVAL, "fn_conv_wgrad: bad dims");
+  FN_REQUIRE((d->ksize == 1 || d->ksize == 3) && (d->stride == 1 || d->stride == 2), FN_E_UNSUPPORTED,
+             "fn_conv_wgrad: ksize %d stride %d", d->ksize, d->stride);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = (const __nv_bfloat16*)d->x;
+  p.dY = (const __nv_bfloat16*)dY;
+  p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->Cin;
+  p.OH = (d->H + d->stride - 1) / d->stride;
+  p.OW = (d->W + d->stride - 1) / d->stride;
+  p.N = d->Cout; p.ksize = d->ksize; p.stride = d->stride;
+  p.pad_t = same_pad_before(d->H, d->ksize, d->stride);
+  p.pad_l = same_pad_before(d->W, d->ksize, d->stride);
+  p.pro = d->prologue;
+  p.Keff = d->Cin * pro_mult(d->prologue);
+  p.transposed = 0;
+  p.keep_prob = d->keep_prob;
+  p.seed = d->dropout_seed;
+  return conv_wgrad_launch(p, dW, workspace, (cudaStream_t)stream);
+}
+
+int64_t fn_tconv_wgrad_workspace(const fn_tconv_desc* d) {
+  if (!d) return 0;
+  return wgrad_workspace((long long)d->B * d->H * d->W, 9, d->Cin, d->Cout);
+}
+
+/* d describes the FORWARD transposed conv (x, dims); dY: bf16 [B,2H,2W,Cout]; dW: fp32 [9, Cin, Cout] */
+int fn_tconv_wgrad(const fn_tconv_desc* d, const void* dY, float* dW, float* workspace, void* stream) {
+  FN_REQUIRE(d && d->x && dY && dW && workspace, FN_E_INVAL, "fn_tconv_wgrad: null argument");
+  FN_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, FN_E_INVAL, "fn_tconv_wgrad: bad dims");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = (const __nv_bfloat16*)d->x;
+  p.dY = (const __nv_bfloat16*)dY;
+  p.B = d->B; p.H = d->H; p.W = d->W; p.C = d->Cin;
+  p.OH = 2 * d->H; p.OW = 2 * d->W;
+  p.N = d->Cout; p.ksize = 3; p.stride = 2;
+  p.pro = FN_PRO_NONE;
+  p.Keff = d->Cin;
+  p.transposed = 1;
+  p.keep_prob = 1.0f;
+  return conv_wgrad_launch(p, dW, workspace, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -62,6 +62,16 @@ SYMBOLS = [
     ("fn_cast_bf16_to_f32", C.c_int, [_P, _P, C.c_int64, _P]),
     ("fn_l2_loss", C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     ("fn_adam_step", C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
+    ("fn_gate_bwd", C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
+    ("fn_prologue_bwd", C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _P]),
+    ("fn_shortcut_bwd", C.c_int, [_P, _P] + [C.c_int32] * 9 + [_P]),
+    ("fn_tanh_l2_bwd", C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
+    ("fn_bias_grad_workspace", C.c_int64, [C.c_int64, C.c_int32]),
+    ("fn_bias_grad", C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
+    ("fn_conv_wgrad_workspace", C.c_int64, [C.POINTER(ConvDesc)]),
+    ("fn_conv_wgrad", C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P]),
+    ("fn_tconv_wgrad_workspace", C.c_int64, [C.POINTER(TConvDesc)]),
+    ("fn_tconv_wgrad", C.c_int, [C.POINTER(TConvDesc), _P, _P, _P, _P]),
 ]
 DEBUG_SYMBOLS = [
     ("fn_debug_set_swap_lbo_sbo", None, [C.c_int]),
@@ -231,3 +241,92 @@ def adam_step(param, grad, m, v, step, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8
             raise ValueError("adam_step takes flat contiguous float32 buffers of equal size")
     _check(lib.fn_adam_step(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(), int(step), lr, beta1, beta2,
                             eps, stream_ptr()), "fn_adam_step")
+
+
+# ------------------------------------------------------------------ training-step adjoints
+_ws_cache = {}
+
+
+def _workspace(nfloats, device):
+    """One grow-only fp32 scratch buffer per device for the two-stage reductions."""
+    buf = _ws_cache.get(device)
+    if buf is None or buf.numel() < nfloats:
+        buf = torch.empty(max(int(nfloats), 1 << 20), dtype=torch.float32, device=device)
+        _ws_cache[device] = buf
+    return buf
+
+
+def gate_bwd(c2, g):
+    _require_cuda(c2, g)
+    F = g.shape[-1]
+    dc2 = torch.empty_like(c2)
+    _check(lib.fn_gate_bwd(_ptr(c2), _ptr(g), _ptr(dc2), g.numel() // F, F, stream_ptr()), "fn_gate_bwd")
+    return dc2
+
+
+def prologue_bwd(dA, x, kind, out=None, accumulate=False, keep_prob=1.0, seed=0):
+    _require_cuda(dA, x, out)
+    Cc = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+        accumulate = False
+    _check(lib.fn_prologue_bwd(_ptr(dA), _ptr(x), _ptr(out), x.numel() // Cc, Cc, kind, int(accumulate), float(keep_prob),
+                               int(seed), stream_ptr()), "fn_prologue_bwd")
+    return out
+
+
+def shortcut_bwd(g, x_shape, pooled, out=None, accumulate=False):
+    _require_cuda(g, out)
+    B, H, W, Cin = x_shape
+    _, OH, OW, F = g.shape
+    if out is None:
+        out = torch.empty(tuple(x_shape), dtype=torch.bfloat16, device=g.device)
+        accumulate = False
+    _check(lib.fn_shortcut_bwd(_ptr(g), _ptr(out), B, OH, OW, F, H, W, Cin, int(pooled), int(accumulate), stream_ptr()),
+           "fn_shortcut_bwd")
+    return out
+
+
+def tanh_l2_bwd(p, t):
+    """returns (loss [1] fp32, d(pre-tanh) bf16 [..., 8] with channels 2..7 zero)"""
+    _require_cuda(p, t)
+    p = p.contiguous()
+    t = t.contiguous()
+    npix = p.numel() // 2
+    loss = torch.zeros(1, dtype=torch.float32, device=p.device)
+    dpre = torch.empty(tuple(p.shape[:-1]) + (8,), dtype=torch.bfloat16, device=p.device)
+    _check(lib.fn_tanh_l2_bwd(_ptr(p), _ptr(t), _ptr(loss), _ptr(dpre), npix, stream_ptr()), "fn_tanh_l2_bwd")
+    return loss, dpre
+
+
+def bias_grad(dY, out):
+    _require_cuda(dY, out)
+    N = dY.shape[-1]
+    npix = dY.numel() // N
+    ws = _workspace(lib.fn_bias_grad_workspace(npix, N), dY.device)
+    _check(lib.fn_bias_grad(_ptr(dY), _ptr(out), _ptr(ws), npix, N, stream_ptr()), "fn_bias_grad")
+
+
+def conv_wgrad(x, dY, out, *, ksize, stride, prologue, keep_prob=1.0, dropout_seed=0):
+    """out: fp32 [k*k, Keff, Cout] <- sum over pixels of pro(x) (x) dY"""
+    _require_cuda(x, dY, out)
+    d = ConvDesc()
+    d.B, d.H, d.W, d.Cin = x.shape
+    d.Cout = dY.shape[-1]
+    d.ksize, d.stride, d.prologue = ksize, stride, prologue
+    d.x = x.data_ptr()
+    d.keep_prob = float(keep_prob)
+    d.dropout_seed = int(dropout_seed)
+    ws = _workspace(lib.fn_conv_wgrad_workspace(C.byref(d)), x.device)
+    _check(lib.fn_conv_wgrad(C.byref(d), _ptr(dY), _ptr(out), _ptr(ws), stream_ptr()), "fn_conv_wgrad")
+
+
+def tconv_wgrad(x, dY, out):
+    """out: fp32 [9, Cin, Cout]"""
+    _require_cuda(x, dY, out)
+    d = TConvDesc()
+    d.B, d.H, d.W, d.Cin = x.shape
+    d.Cout = dY.shape[-1]
+    d.x = x.data_ptr()
+    ws = _workspace(lib.fn_tconv_wgrad_workspace(C.byref(d)), x.device)
+    _check(lib.fn_tconv_wgrad(C.byref(d), _ptr(dY), _ptr(out), _ptr(ws), stream_ptr()), "fn_tconv_wgrad")

@@ -46,6 +46,11 @@ def _profiled(record, launch):
     _PROFILE.append(record)
 
 
+# when a list, res_block / transpose_conv_layer / conv_res record what the backward pass needs
+# (model/flow_backward.py); None in inference
+TAPE = None
+
+
 def set_impl(name: str):
     """'auto' (tcgen05 wherever a kernel exists), 'simt' (CUDA-core cross-check), 'tc' (fail if no tcgen05 kernel)."""
     global IMPL
@@ -254,6 +259,8 @@ def transpose_conv_layer(inputs, kernel_size, stride, num_features, idx, nonline
                    alg_bytes=(x.numel() + y.numel()) * 2, flops=2 * B * H * W * 9 * cin * num_features)
     _profiled(rec, lambda: native.tconv_fwd(x, w16, bias, y, B=B, H=H, W=W, Cin=cin, Cout=num_features, impl=IMPL,
                                             w_tc=w_tc))
+    if TAPE is not None:
+        TAPE.append(dict(kind="tconv", scope=scope, x=x, out=y))
     if nonlinearity is not None:
         y = nonlinearity(y)
     return y
@@ -306,9 +313,14 @@ def res_block(x, a=None, filter_size=16, nonlinearity=concat_elu, keep_p=1.0, st
                       native.PRO_NONE if cin == 1 else pro, native.EPI_BIAS,
                       skip=a, skip_scope=(name + '_nin_fc') if a is not None else None)
     pooled = orig_x.shape[2] > x_1.shape[2]
-    return _fused_conv(x_1, name + '_conv_2_conv', 3, 1, filter_size * (2 if gated else 1), pro,
-                       native.EPI_GATE_RES if gated else native.EPI_RES, res=orig_x, res_pool=pooled,
-                       keep_prob=keep_p, dropout_seed=dropout_seed)
+    out = _fused_conv(x_1, name + '_conv_2_conv', 3, 1, filter_size * (2 if gated else 1), pro,
+                      native.EPI_GATE_RES if gated else native.EPI_RES, res=orig_x, res_pool=pooled,
+                      keep_prob=keep_p, dropout_seed=dropout_seed)
+    if TAPE is not None:
+        TAPE.append(dict(kind="block", name=name, x=orig_x, a=native.to_bf16(a) if a is not None else None, x_1=x_1,
+                         out=out, F=filter_size, stride=stride, gated=gated, pro=pro, keep_p=keep_p, seed=dropout_seed,
+                         pooled=pooled))
+    return out
 
 
 def _res_block_unfused(x, a, filter_size, nonlinearity, keep_p, stride, gated, name):
@@ -352,4 +364,7 @@ def conv_res(inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name='concat_e
         for i in range(nr_res_blocks):
             x = block(x, a=a[-k] if i == 0 else None, name="resnet_up_%d_%d" % (k, i))
     # last_conv + tanh (reference :242-243), one launch
-    return _fused_conv(x, 'last_conv_conv', 3, 1, 2, native.PRO_NONE, native.EPI_TANH)
+    y = _fused_conv(x, 'last_conv_conv', 3, 1, 2, native.PRO_NONE, native.EPI_TANH)
+    if TAPE is not None:
+        TAPE.append(dict(kind="last", x=x, out=y))
+    return y

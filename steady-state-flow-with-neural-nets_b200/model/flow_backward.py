@@ -1,0 +1,204 @@
+"""Backward pass + TF1 Adam for flow_net -- what `AdamOptimizer(lr).minimize(loss)` builds in the
+reference (/root/reference/model/flow_net.py:44-46) for the graph of flow_architecture.py:129-248.
+
+Correctness-first: every gradient is computed by kernels of libflownet.so, but the data gradients of
+the convolutions reuse the FORWARD kernels on the gradient tensor (stride-1 conv: flipped, transposed
+weights; stride-2 conv <-> transposed conv with the same weights), the pre-gate tensor is recomputed
+instead of stored, and the weight/bias gradients are two-stage CUDA-core reductions.  Activation
+gradients are bf16, parameter gradients / Adam state fp32 in flat buffers (one all-reduce in
+data-parallel training, SURVEY 8e: gradients of a SUM loss simply add across ranks).
+"""
+from __future__ import annotations
+
+import torch
+
+import flownet_native as native
+import model.flow_architecture as arch
+
+
+class FlatParams:
+    """All variables re-homed as views of ONE flat fp32 buffer (same names / shapes / TF layouts), with
+    matching flat gradient and Adam-slot buffers."""
+
+    def __init__(self):
+        vs = arch.VARIABLES
+        if not vs.vars:
+            raise RuntimeError("run one forward first: variables are created lazily, as in the reference")
+        n = sum(v.numel() for v in vs.vars.values())
+        dev = next(iter(vs.vars.values())).device
+        self.param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.offsets = {}
+        off = 0
+        for name, v in list(vs.vars.items()):
+            k = v.numel()
+            self.param[off:off + k].copy_(v.reshape(-1))
+            vs.vars[name] = self.param[off:off + k].view(v.shape)
+            self.offsets[name] = (off, k, tuple(v.shape))
+            off += k
+        self.n = n
+        self.step = 0
+        vs.touch()
+
+    def grad_view(self, name):
+        off, k, shape = self.offsets[name]
+        return self.grad[off:off + k].view(shape)
+
+
+def _zeros_bias(n, device):
+    return torch.zeros(n, dtype=torch.float32, device=device)
+
+
+def _dgrad_weights_s1(w, ksize):
+    """HWIO [k,k,Keff,N] -> GEMM-B of the data-gradient conv: [tap', N, Keff] with the taps flipped."""
+    keff, n = w.shape[2], w.shape[3]
+    wd = torch.flip(w, dims=(0, 1)).permute(0, 1, 3, 2).reshape(ksize * ksize, n, keff)
+    return wd.to(torch.bfloat16).contiguous()
+
+
+def _conv_plain(x, w16, cout, ksize, stride, device):
+    """bias-free conv through the forward kernels (tcgen05 when the shape allows)."""
+    B, H, W, cin = x.shape
+    OH, OW = -(-H // stride), -(-W // stride)
+    y = torch.empty((B, OH, OW, cout), dtype=torch.bfloat16, device=device)
+    w_tc = native.pack_conv_weights_tc(w16, None, ksize, cin, 0, cout, False) if cin % 16 == 0 else None
+    native.conv_fwd(x, w16, _zeros_bias(cout, device), y, B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize, stride=stride,
+                    prologue=native.PRO_NONE, epilogue=native.EPI_BIAS, impl=arch.IMPL, w_tc=w_tc)
+    return y
+
+
+def _tconv_plain(x, w16, cout, device):
+    B, H, W, cin = x.shape
+    y = torch.empty((B, 2 * H, 2 * W, cout), dtype=torch.bfloat16, device=device)
+    w_tc = native.pack_conv_weights_tc(w16, None, 3, cin, 0, cout, False) if cin % 16 == 0 else None
+    native.tconv_fwd(x, w16, _zeros_bias(cout, device), y, B=B, H=H, W=W, Cin=cin, Cout=cout, impl=arch.IMPL, w_tc=w_tc)
+    return y
+
+
+class _Grads:
+    """Gradient accumulators for activation tensors with more than one consumer (block outputs that
+    also feed a decoder skip): the first writer assigns, later writers accumulate in the kernel."""
+
+    def __init__(self):
+        self.g = {}
+
+    def has(self, t):
+        return id(t) in self.g
+
+    def get(self, t):
+        return self.g[id(t)][1]
+
+    def target(self, t):
+        """returns (buffer, accumulate) for a kernel that writes d(t)"""
+        ent = self.g.get(id(t))
+        if ent is None:
+            buf = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+            self.g[id(t)] = (t, buf)          # keep `t` alive so ids stay unique
+            return buf, False
+        return ent[1], True
+
+
+def backward(tape, sflow_p, sflow, flat: FlatParams):
+    """Fills flat.grad with d(l2_loss)/d(variables); returns the loss (fp32 [1])."""
+    V = arch.VARIABLES.vars
+    dev = sflow_p.device
+    grads = _Grads()
+    loss, dpre = native.tanh_l2_bwd(sflow_p, sflow.to(torch.float32))
+
+    def wgrad_into(name, x, dY, ksize, stride, pro, keep_prob=1.0, seed=0):
+        native.conv_wgrad(x, dY, flat.grad_view(name + '/weights').view(ksize * ksize, -1, dY.shape[-1]), ksize=ksize,
+                          stride=stride, prologue=pro, keep_prob=keep_prob, dropout_seed=seed)
+
+    for rec in reversed(tape):
+        kind = rec["kind"]
+        if kind == "last":
+            x = rec["x"]                                   # [B,H,W,F] raw block output, no prologue
+            cin = x.shape[3]
+            # weights: [3,3,cin,2]; gradients run as 8-channel launches (dpre channels 2..7 are zero)
+            tmp = torch.empty((9, cin, 8), dtype=torch.float32, device=dev)
+            native.conv_wgrad(x, dpre, tmp, ksize=3, stride=1, prologue=native.PRO_NONE)
+            flat.grad_view('last_conv_conv/weights').copy_(tmp[:, :, :2].reshape(3, 3, cin, 2))
+            tmpb = torch.empty(8, dtype=torch.float32, device=dev)
+            native.bias_grad(dpre, tmpb)
+            flat.grad_view('last_conv_conv/biases').copy_(tmpb[:2])
+            w = V['last_conv_conv/weights']
+            w8 = torch.zeros((3, 3, cin, 8), dtype=torch.float32, device=dev)
+            w8[..., :2] = w
+            dx = _conv_plain(dpre, _dgrad_weights_s1(w8, 3), cin, 3, 1, dev)
+            buf, acc = grads.target(x)
+            assert not acc
+            buf.copy_(dx)
+        elif kind == "tconv":
+            x, y, scope = rec["x"], rec["out"], rec["scope"]
+            g = grads.get(y)
+            cin, cout = x.shape[3], y.shape[3]
+            tmp = torch.empty((9, cin, cout), dtype=torch.float32, device=dev)
+            native.tconv_wgrad(x, g, tmp)
+            flat.grad_view(scope + '/weights').copy_(tmp.view(3, 3, cin, cout).permute(0, 1, 3, 2))
+            native.bias_grad(g, flat.grad_view(scope + '/biases'))
+            # d(x) = stride-2 'SAME' conv of d(y) with the same weights read as HWIO [k,k,Cout,Cin]
+            w16 = V[scope + '/weights'].reshape(9, cout, cin).to(torch.bfloat16).contiguous()
+            dx = _conv_plain(g, w16, cin, 3, 2, dev)
+            buf, acc = grads.target(x)
+            assert not acc
+            buf.copy_(dx)
+        elif kind == "block":
+            name, x, a, x_1, out = rec["name"], rec["x"], rec["a"], rec["x_1"], rec["out"]
+            F_, stride, gated, pro = rec["F"], rec["stride"], rec["gated"], rec["pro"]
+            keep_p, seed, pooled = rec["keep_p"], rec["seed"], rec["pooled"]
+            mult = 2 if pro in (native.PRO_CONCAT_ELU, native.PRO_CONCAT_RELU) else 1
+            g = grads.get(out)
+            cin = x.shape[3]
+            s2 = name + '_conv_2_conv'
+            n2 = 2 * F_ if gated else F_
+            # ---- conv_2 (+gate): recompute the pre-gate tensor, then its adjoint
+            if gated:
+                c2 = arch._fused_conv(x_1, s2, 3, 1, n2, pro, native.EPI_BIAS, keep_prob=keep_p, dropout_seed=seed)
+                dc2 = native.gate_bwd(c2, g)
+            else:
+                dc2 = g
+            native.bias_grad(dc2, flat.grad_view(s2 + '/biases'))
+            wgrad_into(s2, x_1, dc2, 3, 1, pro, keep_p, seed)
+            dA2 = _conv_plain(dc2, _dgrad_weights_s1(V[s2 + '/weights'], 3), mult * F_, 3, 1, dev)
+            dx_1 = native.prologue_bwd(dA2, x_1, pro, keep_prob=keep_p, seed=seed)
+            # ---- conv_1 (+nin skip)
+            s1 = name + '_conv_1_conv'
+            pro1 = native.PRO_NONE if cin == 1 else pro
+            native.bias_grad(dx_1, flat.grad_view(s1 + '/biases'))
+            wgrad_into(s1, x, dx_1, 3, stride, pro1)
+            if a is not None:
+                sn = name + '_nin_fc'
+                flat.grad_view(sn + '/biases').copy_(flat.grad_view(s1 + '/biases'))
+                # the skip is zero-padded bottom/right to x_1's size: only the overlapping window contributes
+                if a.shape[1] != dx_1.shape[1] or a.shape[2] != dx_1.shape[2]:
+                    raise ValueError("training with a spatially padded skip (H, W not multiples of 16) is not built")
+                native.conv_wgrad(a, dx_1, flat.grad_view(sn + '/weights').view(1, -1, F_), ksize=1, stride=1, prologue=pro)
+                wn = V[sn + '/weights']                                   # [mult*Ca, F]
+                dAa = _conv_plain(dx_1, wn.t().reshape(1, F_, -1).to(torch.bfloat16).contiguous(), wn.shape[0], 1, 1, dev)
+                buf, acc = grads.target(a)
+                native.prologue_bwd(dAa, a, pro, out=buf, accumulate=acc)
+            if cin > 1:
+                w1 = V[s1 + '/weights']                                   # [3,3,mult*cin,F]
+                if stride == 1:
+                    dA1 = _conv_plain(dx_1, _dgrad_weights_s1(w1, 3), mult * cin, 3, 1, dev)
+                else:
+                    if x.shape[1] % 2 or x.shape[2] % 2:
+                        raise ValueError("training a stride-2 block on odd spatial sizes is not built")
+                    w16 = w1.reshape(9, mult * cin, F_).permute(0, 2, 1).to(torch.bfloat16).contiguous()   # [tap, F, Keff]
+                    dA1 = _tconv_plain(dx_1, w16, mult * cin, dev)
+                buf, acc = grads.target(x)
+                native.prologue_bwd(dA1, x, pro, out=buf, accumulate=acc)
+                native.shortcut_bwd(g, tuple(x.shape), pooled, out=buf, accumulate=True)
+    return loss
+
+
+def adam_update(flat: FlatParams, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """TF1 ApplyAdam on the flat buffers (after the optional gradient all-reduce)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)      # SUM loss => gradients add, no 1/R
+    flat.step += 1
+    native.adam_step(flat.param, flat.grad, flat.m, flat.v, flat.step, lr, beta1, beta2, eps)
+    arch.VARIABLES.touch()

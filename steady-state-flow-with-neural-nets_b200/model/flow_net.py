@@ -98,7 +98,57 @@ class CompiledInference:
         return self.static_out
 
 
+# --------------------------------------------------------------------------- training (reference :44-46)
+_TRAIN = {"flat": None, "last": None}
+
+
+def begin_training():
+    """Switch inference()/loss_image() to recording mode: the next inference() call keeps what the
+    backward pass needs (the eager counterpart of building the gradient graph once)."""
+    flow_architecture.TAPE = []
+
+
+def end_training():
+    flow_architecture.TAPE = None
+    _TRAIN["last"] = None
+
+
+def loss_image_train(sflow_p, sflow):
+    """loss_image() for a recorded forward: remembers (prediction, target) for train()."""
+    _TRAIN["last"] = (sflow_p, sflow)
+    return loss_image(sflow_p, sflow)
+
+
 def train(total_loss, lr):
-    """reference :44-46 builds AdamOptimizer(lr).minimize(total_loss).  The B200 training step
-    (backward kernels + flat fused Adam + NCCL all-reduce) lives in model/flow_train_step.py."""
-    raise NotImplementedError("training step: see model/flow_train_step.py (not built in this round)")
+    """reference :44-46 -- AdamOptimizer(lr).minimize(total_loss), executed eagerly: backward through the
+    recorded forward, one flat fp32 gradient all-reduce when torch.distributed is initialised, TF1 Adam.
+
+    Usage (mirrors train/flow_train.py:34-40,83):
+        flow_net.begin_training()
+        sflow_p = flow_net.inference(boundary, keep_prob)
+        error = flow_net.loss_image_train(sflow_p, sflow)
+        flow_net.train(error, learning_rate)
+    Returns the loss tensor recomputed by the fused tanh+l2 backward kernel (fp32 [1])."""
+    import model.flow_backward as fb
+    tape = flow_architecture.TAPE
+    if tape is None or not tape or _TRAIN["last"] is None:
+        raise RuntimeError("train(): call begin_training(), inference() and loss_image_train() first")
+    if _TRAIN["flat"] is None:
+        _TRAIN["flat"] = fb.FlatParams()
+        # the recorded forward used the pre-flattening tensors for its weights only; activations are unaffected
+    sflow_p, sflow = _TRAIN["last"]
+    loss = fb.backward(tape, sflow_p, sflow, _TRAIN["flat"])
+    fb.adam_update(_TRAIN["flat"], lr)
+    flow_architecture.TAPE = []          # ready for the next step
+    _TRAIN["last"] = None
+    return loss
+
+
+def training_state():
+    """The flat parameter / gradient / Adam buffers (None before the first train() call)."""
+    return _TRAIN["flat"]
+
+
+def reset_training_state():
+    _TRAIN["flat"] = None
+    _TRAIN["last"] = None

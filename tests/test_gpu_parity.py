@@ -396,3 +396,136 @@ def test_adam_kernel_matches_tf1_update(native):
     torch.cuda.synchronize()
     assert (pd.cpu().double() - po["a"]).abs().max().item() < 1e-6
     assert rel_l2(md, mo["a"]) < 1e-6 and rel_l2(vd, vo["a"]) < 1e-6
+
+
+# ------------------------------------------------------------------------------- training step
+def _oracle_grads(x_np, tgt_np, keep_prob=1.0):
+    vt = fo.VariableStore(1234, torch.float64)
+    xb = torch.from_numpy(x_np).double()
+    fo.inference(vt, xb, 1.0)
+    vt.vars = {k: v.clone().requires_grad_(True) for k, v in vt.vars.items()}
+    loss = fo.loss_image(fo.inference(vt, xb, 1.0), torch.from_numpy(tgt_np).double())
+    loss.backward()
+    return loss.item(), vt
+
+
+def test_backward_primitives(native):
+    g = torch.Generator().manual_seed(0)
+    # gate
+    c2 = torch.randn(3, 5, 7, 16, generator=g, dtype=torch.float64).to(torch.bfloat16)
+    gg = torch.randn(3, 5, 7, 8, generator=g, dtype=torch.float64).to(torch.bfloat16)
+    c2r = c2.double().requires_grad_(True)
+    (c2r[..., :8] * torch.sigmoid(c2r[..., 8:]) * gg.double()).sum().backward()
+    assert rel_l2(native.gate_bwd(c2.cuda(), gg.cuda()), c2r.grad) < 5e-3
+    # prologues
+    for kind, f in ((1, fo.concat_elu), (2, fo.elu), (3, fo.concat_relu), (4, torch.relu)):
+        x = torch.randn(2, 6, 5, 8, generator=g, dtype=torch.float64).to(torch.bfloat16)
+        mult = 2 if kind in (1, 3) else 1
+        dA = torch.randn(2, 6, 5, 8 * mult, generator=g, dtype=torch.float64).to(torch.bfloat16)
+        xr = x.double().requires_grad_(True)
+        (f(xr) * dA.double()).sum().backward()
+        assert rel_l2(native.prologue_bwd(dA.cuda(), x.cuda(), kind), xr.grad) < 5e-3
+    # shortcut (pooled + front pad, odd size)
+    x = torch.randn(2, 7, 9, 8, generator=g, dtype=torch.float64)
+    gr = torch.randn(2, 4, 5, 16, generator=g, dtype=torch.float64).to(torch.bfloat16)
+    xr = x.clone().requires_grad_(True)
+    sc = torch.nn.functional.pad(fo.avg_pool_2x2_same(xr), (8, 0))
+    (sc * gr.double()).sum().backward()
+    assert rel_l2(native.shortcut_bwd(gr.cuda(), (2, 7, 9, 8), True), xr.grad) < 5e-3
+    # bias grad
+    dY = torch.randn(4, 9, 11, 32, generator=g, dtype=torch.float64).to(torch.bfloat16)
+    out = torch.empty(32, device="cuda")
+    native.bias_grad(dY.cuda(), out)
+    assert rel_l2(out, dY.double().sum(dim=(0, 1, 2))) < 1e-5
+
+
+@pytest.mark.parametrize("ksize,stride,pro,H,W,C,N", [(3, 1, 1, 12, 20, 8, 16), (3, 2, 1, 16, 24, 16, 32), (1, 1, 1, 8, 8, 16, 8),
+                                                      (3, 1, 0, 9, 13, 1, 8), (3, 2, 2, 15, 17, 8, 8)])
+def test_conv_wgrad_vs_autograd(native, ksize, stride, pro, H, W, C, N):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, H, W, C, generator=g, dtype=torch.float64).to(torch.bfloat16)
+    mult = 2 if pro in (1, 3) else 1
+    w = torch.randn(ksize, ksize, C * mult, N, generator=g, dtype=torch.float64).requires_grad_(True)
+    OH, OW = -(-H // stride), -(-W // stride)
+    dY = torch.randn(3, OH, OW, N, generator=g, dtype=torch.float64).to(torch.bfloat16)
+    a = bf16_round(PRO_FN[pro](x.double())) if pro else x.double()
+    (fo.conv2d_same(a, w, stride) * dY.double()).sum().backward()
+    out = torch.empty(ksize * ksize, C * mult, N, device="cuda")
+    native.conv_wgrad(x.cuda(), dY.cuda(), out, ksize=ksize, stride=stride, prologue=pro)
+    assert rel_l2(out, w.grad.reshape(ksize * ksize, C * mult, N)) < 1e-4
+
+
+def test_tconv_wgrad_vs_autograd(native):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 5, 6, 16, generator=g, dtype=torch.float64).to(torch.bfloat16)
+    w = torch.randn(3, 3, 8, 16, generator=g, dtype=torch.float64).requires_grad_(True)     # TF [k,k,Cout,Cin]
+    dY = torch.randn(2, 10, 12, 8, generator=g, dtype=torch.float64).to(torch.bfloat16)
+    (fo.conv2d_transpose_same(x.double(), w, 2) * dY.double()).sum().backward()
+    out = torch.empty(9, 16, 8, device="cuda")
+    native.tconv_wgrad(x.cuda(), dY.cuda(), out)
+    assert rel_l2(out.view(3, 3, 16, 8).permute(0, 1, 3, 2), w.grad) < 1e-4
+
+
+def test_training_step_vs_oracle(native, golden_dir):
+    """One fwd+bwd+Adam step on the golden 2x32x64 case: loss, every gradient and the updated variables."""
+    import model.flow_architecture as arch
+    import model.flow_net as flow_net
+    z = np.load(os.path.join(golden_dir, "golden_train.npz"))
+    x = fo.synth_boundary(2, 32, 64, seed=3).astype(np.uint8)
+    tgt = z["target"].astype(np.float32)
+    arch.reset_variables(1234)
+    flow_net.reset_training_state()
+    try:
+        flow_net.begin_training()
+        p = flow_net.inference(torch.from_numpy(x).cuda(), 1.0)
+        err = flow_net.loss_image_train(p, torch.from_numpy(tgt).cuda())
+        loss = flow_net.train(err, 1e-4)
+        torch.cuda.synchronize()
+        assert native.tc_status() == 0
+        flat = flow_net.training_state()
+        ref_loss, vt = _oracle_grads(x.astype(np.float64), z["target"])
+        assert abs(ref_loss - float(z["loss"])) < 1e-9 * abs(ref_loss)
+        assert abs(loss.item() - ref_loss) < 2e-2 * abs(ref_loss)
+        assert abs(err.item() - ref_loss) < 2e-2 * abs(ref_loss)
+        worst = 0.0
+        for name, v in vt.vars.items():
+            e = rel_l2(flat.grad_view(name), v.grad)
+            worst = max(worst, e)
+            assert e < 5e-2, (name, e)           # bf16 activations and activation gradients
+        print("worst per-variable gradient rel-L2:", worst)
+        # Adam moved every variable by ~lr in the direction of -sign(g) on the first step
+        pd = {k: v.detach().clone() for k, v in vt.vars.items()}
+        gd = {k: v.grad for k, v in vt.vars.items()}
+        m = {k: torch.zeros_like(v) for k, v in pd.items()}
+        vv = {k: torch.zeros_like(v) for k, v in pd.items()}
+        fo.adam_step_tf1(pd, gd, m, vv, t=1)
+        for name in ("last_conv_conv/weights", "resnet_3_0_conv_2_conv/weights", "up_conv_2_trans_conv/weights"):
+            got = arch.global_variables()[name].cpu().double()
+            step_ref = pd[name] - vt.vars[name].detach()
+            step_got = got - vt.vars[name].detach()
+            assert rel_l2(step_got, step_ref) < 0.15           # sign-like first Adam step; tiny gradients may flip
+    finally:
+        flow_net.end_training()
+        flow_net.reset_training_state()
+        arch.reset_variables(1234)
+
+
+def test_training_loss_decreases(native):
+    import model.flow_architecture as arch
+    import model.flow_net as flow_net
+    arch.reset_variables(1234)
+    flow_net.reset_training_state()
+    b, s = flow_net.inputs(4, shape=(32, 64), seed=0)
+    try:
+        flow_net.begin_training()
+        losses = []
+        for _ in range(8):
+            p = flow_net.inference(b, 1.0)
+            err = flow_net.loss_image_train(p, s)
+            losses.append(flow_net.train(err, 1e-3).item())
+        assert all(np.isfinite(losses))
+        assert losses[-1] < 0.7 * losses[0], losses
+    finally:
+        flow_net.end_training()
+        flow_net.reset_training_state()
+        arch.reset_variables(1234)
