@@ -179,6 +179,55 @@ def layer_profile(x_dev, reps=5):
     return rows
 
 
+def run_train(args, rank, world, dist, native, arch, flow_net):
+    """BASELINE configs[2]: training step (L2 loss, fwd+bwd+Adam), global batch 256 synthetic 128x256,
+    batch-sharded with one NCCL all-reduce of the flat fp32 gradient.  keep_prob = 1.0 (tcgen05 forward)."""
+    global_batch = 256
+    B = global_batch // world
+    arch.reset_variables(1234)
+    flow_net.reset_training_state()
+    boundary, sflow = flow_net.inputs(B, seed=rank * B)
+    flow_net.begin_training()
+
+    def step():
+        p = flow_net.inference(boundary, 1.0)
+        err = flow_net.loss_image_train(p, sflow)
+        return flow_net.train(err, 1e-4)
+
+    for _ in range(max(args.warmup, 2)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    flow_net.end_training()
+    if rank == 0:
+        v = global_batch * args.steps / (ms * 1e-3)
+        print(json.dumps({
+            "metric": "flow_net training images/sec at 128x256 (fwd+bwd+Adam)", "value": v, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 2), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic boundaries and targets",
+            "config": {"workload": "configs[2]: training step, global batch 256, 128x256, L2 loss + TF1 Adam, "
+                                   "keep_prob 1.0; correctness-first backward (CUDA-core wgrad)",
+                       "batch_per_gpu": B, "parallelism": f"dp{world}, one flat fp32 gradient all-reduce"},
+            "gpu_launches": native.launch_count() - n0, "loss": float(loss.item()),
+            "roofline": {"bound": "tensor", "achieved": v * 8.519e9 / 1e12, "peak": load_peaks()["tc_sustained"],
+                         "unit": "TFLOP/s", "frac": v * 8.519e9 / 1e12 / load_peaks()["tc_sustained"], "traffic": None},
+        }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +236,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU per step (default: the configs[1] batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="inference", choices=["inference", "train"],
+                    help="train: BASELINE configs[2], fwd+bwd+Adam at global batch 256 (extra line, not the headline)")
     ap.add_argument("--layers-out", default=None, help="write the per-layer roofline table (JSON) here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -209,6 +260,13 @@ def main():
     import flownet_native as native
     import model.flow_architecture as arch
     import model.flow_net as flow_net
+
+    if args.mode == "train":
+        run_train(args, rank, world, dist, native, arch, flow_net)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     peaks = load_peaks()
     B = args.batch

@@ -194,11 +194,19 @@ def backward(tape, sflow_p, sflow, flat: FlatParams):
     return loss
 
 
-def adam_update(flat: FlatParams, lr, beta1=0.9, beta2=0.999, eps=1e-8):
-    """TF1 ApplyAdam on the flat buffers (after the optional gradient all-reduce)."""
+def allreduce_gradients(flat_grad):
+    """The one collective of data-parallel training: SUM of the flat fp32 gradient over ranks.  The loss
+    is a plain sum over the batch (tf.nn.l2_loss), so shard gradients ADD -- no 1/R scaling --
+    and the reduced gradient equals the single-process full-batch gradient."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)      # SUM loss => gradients add, no 1/R (SURVEY F9, 8e)
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+    return flat_grad
+
+
+def adam_update(flat: FlatParams, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """TF1 ApplyAdam on the flat buffers (after the optional gradient all-reduce)."""
+    allreduce_gradients(flat.grad)
     flat.step += 1
     native.adam_step(flat.param, flat.grad, flat.m, flat.v, flat.step, lr, beta1, beta2, eps)
     arch.VARIABLES.touch()
