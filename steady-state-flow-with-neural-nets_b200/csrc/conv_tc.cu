@@ -663,6 +663,7 @@ static int ensure_status_word() {
 
 int* tc_status_word() { return ensure_status_word() == 0 ? g_tc_status_dev : nullptr; }
 bool conv_s1p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1p.cu
+bool conv_s1d_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1d.cu
 
 static int launch_tc(TcParams& p, size_t smem_bytes, cudaStream_t stream) {
   int rc = ensure_status_word();
@@ -683,6 +684,7 @@ static int launch_tc(TcParams& p, size_t smem_bytes, cudaStream_t stream) {
 int conv_fwd_tc(const fn_conv_desc& d, cudaStream_t stream) {
   int rc_sp = 0;
   if (g_tc_use_s1p && conv_s1p_try(d, stream, false, rc_sp)) return rc_sp;
+  if (g_tc_use_s1p && conv_s1d_try(d, stream, false, rc_sp)) return rc_sp;
   TcGeom g;
   TcParams p;
   size_t smem_bytes = 0;

@@ -180,6 +180,18 @@ S1P_CASES = [
     ("l3_conv1_c32", 4, 32, 64, 32, 32, 1, 1, 0, False, None, False),
     ("l3_conv1_skip_c32", 3, 32, 64, 32, 32, 1, 1, 0, True, None, False),
     ("l3_pool_pad_c32", 2, 32, 32, 32, 64, 1, 1, 1, False, 16, True),
+    # deep levels: streamed weights (conv_s1d.cu)
+    ("l4_conv2_gate_c64", 4, 16, 32, 64, 128, 1, 1, 1, False, None, False),
+    ("l4_conv1_c64", 4, 16, 32, 64, 64, 1, 1, 0, False, None, False),
+    ("l4_conv1_skip_c64", 3, 16, 32, 64, 64, 1, 1, 0, True, None, False),
+    ("l4_pool_pad_c64", 2, 16, 32, 64, 128, 1, 1, 1, False, 32, True),
+    ("l4_two_tiles_per_cta", 160, 16, 16, 64, 128, 1, 1, 1, False, None, False),
+    ("l5_conv2_gate_c128_tr", 5, 8, 16, 128, 256, 1, 1, 1, False, None, False),
+    ("l5_conv1_c128_tr", 5, 8, 16, 128, 128, 1, 1, 0, False, None, False),
+    ("l5_pool_pad_c128_tr", 3, 8, 16, 128, 256, 1, 1, 1, False, 64, True),
+    ("l5_two_tiles_per_cta_tr", 150, 8, 16, 128, 128, 1, 1, 0, False, None, False),
+    ("c128_16x16_gate", 2, 16, 16, 128, 256, 1, 1, 1, False, None, False),
+    ("c64_8x16_tr_skip", 2, 8, 16, 64, 64, 1, 1, 0, True, None, False),
     ("single_tile", 1, 16, 8, 8, 16, 1, 1, 1, False, None, False),
     ("three_tiles_per_cta", 148 * 3, 16, 32, 8, 16, 1, 1, 1, False, None, False),
 ]
