@@ -304,6 +304,17 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
       const uint32_t cur = (uint32_t)((it >> 1) & 1);
       int b, y0, x0;
       tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, y0, x0);
+      // 1-channel shortcut (the boundary image under the first block): one scalar per pixel lands in the
+      // LAST channel (front zero-pad, reference :158-163); fetch it while the MMAs run
+      float r1[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        r1[j] = 0.f;
+        if (GATE && p.res_mode == 3) {
+          const int oy1 = y0 + v, ox1 = x0 + 8 * j + u;
+          if (oy1 < p.H && ox1 < p.W) r1[j] = __bfloat162float(__ldg(p.res + ((size_t)b * p.H + oy1) * p.W + ox1));
+        }
+      }
       ok = ok && ptx::mbar_wait(bar(SB_TF + s), cur);
       if (!ok) atomicCAS(p.status, 0, 14);
       ptx::tc_fence_after_sync();
@@ -337,6 +348,8 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
               for (int i = 0; i < 8; ++i) o[i] += __bfloat162float(rr.h[i]);
             } else if (p.res_mode == 2 && live) {
               sp_shortcut_generic(p, Cfg::F, b, oy, ox, c0, o);
+            } else if (p.res_mode == 3 && c0 == Cfg::F - 8) {
+              o[7] += r1[j];
             }
           } else {
             ptx::tmem_ld8(col0 + c0, o);
@@ -421,7 +434,7 @@ static int launch_s1p(const fn_conv_desc& d, cudaStream_t stream) {
         return FN_E_UNSUPPORTED;
       }
     } else {
-      p.res_mode = 2;
+      p.res_mode = (!d.res_pool && d.Cres == 1 && d.RH == d.H && d.RW == d.W) ? 3 : 2;
       p.res = (const __nv_bfloat16*)d.res;
     }
   }

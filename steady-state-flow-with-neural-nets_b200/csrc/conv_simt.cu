@@ -270,9 +270,79 @@ static int launch_direct(const fn_conv_desc& d, cudaStream_t stream) {
   return check_launch("k_direct3x3");
 }
 
+// Head of the network, 1 channel -> 8: a CTA stages an 8 x 128 pixel tile (+halo) of the boundary image as
+// fp32 in shared memory; each thread produces 4 horizontally adjacent pixels x 8 channels (64 contiguous
+// output bytes), so the 2-byte inputs are read once and the 16 B/pixel output stream is fully coalesced.
+__global__ void __launch_bounds__(256) k_head3x3_c8(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B,
+                                                    int H, int W, int tiles_x, int tiles_y) {
+  __shared__ float ws[72 + 8];
+  __shared__ float tile[10][132];
+  for (int i = threadIdx.x; i < 72; i += 256) ws[i] = __bfloat162float(w[i]);
+  if (threadIdx.x < 8) ws[72 + threadIdx.x] = bias[threadIdx.x];
+  int t = blockIdx.x;
+  const int tx = t % tiles_x;
+  t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int y0 = ty * 8, x0 = tx * 128;
+  for (int i = threadIdx.x; i < 10 * 130; i += 256) {
+    const int r = i / 130, c = i - r * 130;
+    const int iy = y0 + r - 1, ix = x0 + c - 1;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __bfloat162float(x[((size_t)b * H + iy) * W + ix]);
+    tile[r][c] = v;
+  }
+  __syncthreads();
+  const int row = threadIdx.x >> 5, cg = threadIdx.x & 31;
+  const int oy = y0 + row, ox = x0 + 4 * cg;
+  if (oy >= H || ox >= W) return;
+  float in[3][6];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) in[r][c] = tile[row + r][4 * cg + c];
+  float acc[4][8];
+#pragma unroll
+  for (int px = 0; px < 4; ++px)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[px][n] = ws[72 + n];
+#pragma unroll
+  for (int di = 0; di < 3; ++di)
+#pragma unroll
+    for (int dj = 0; dj < 3; ++dj)
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const float wt = ws[(di * 3 + dj) * 8 + n];
+#pragma unroll
+        for (int px = 0; px < 4; ++px) acc[px][n] = fmaf(in[di][px + dj], wt, acc[px][n]);
+      }
+  __nv_bfloat16* yo = y + (((size_t)b * H + oy) * W + ox) * 8;
+#pragma unroll
+  for (int px = 0; px < 4; ++px) {
+    if (ox + px < W) {
+      bf16x8 o;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) o.h[n] = __float2bfloat16(acc[px][n]);
+      *reinterpret_cast<uint4*>(yo + px * 8) = o.v;
+    }
+  }
+}
+
+static int launch_head_c8(const fn_conv_desc& d, cudaStream_t stream) {
+  const int tiles_x = (d.W + 127) / 128, tiles_y = (d.H + 7) / 8;
+  const long long grid = (long long)d.B * tiles_x * tiles_y;
+  k_head3x3_c8<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d.x),
+                                                   reinterpret_cast<const __nv_bfloat16*>(d.w), d.bias,
+                                                   reinterpret_cast<__nv_bfloat16*>(d.y), d.B, d.H, d.W, tiles_x, tiles_y);
+  count_launch();
+  return check_launch("k_head3x3_c8");
+}
+
 // returns true (and sets rc) if a specialised head/tail kernel took the launch
 static bool try_direct(const fn_conv_desc& d, cudaStream_t stream, int& rc) {
   if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_NONE || d.skip || d.keep_prob < 1.0f) return false;
+  if (d.epilogue == FN_EPI_BIAS && d.Cin == 1 && d.Cout == 8) { rc = launch_head_c8(d, stream); return true; }
   if (d.epilogue == FN_EPI_BIAS && d.Cin == 1) {
     if (d.Cout == 8) { rc = launch_direct<1, 8, false>(d, stream); return true; }
     if (d.Cout == 16) { rc = launch_direct<1, 16, false>(d, stream); return true; }

@@ -106,6 +106,8 @@ def run_fused_conv(native, impl, B, H, W, Cin, Cout, stride, pro, epi, with_skip
 # (name, B,H,W,Cin,Cout,stride,pro,epi,skip,Cres,pool) -- the layer shapes of SURVEY App. A, scaled down
 SIMT_CASES = [
     ("head_c1", 2, 16, 32, 1, 8, 1, 0, 0, False, None, False),
+    ("head_c1_ragged", 3, 9, 13, 1, 8, 1, 0, 0, False, None, False),
+    ("head_c1_wide", 2, 24, 300, 1, 8, 1, 0, 0, False, None, False),
     ("conv1_ce", 2, 16, 32, 8, 8, 1, 1, 0, False, None, False),
     ("conv2_gate", 2, 16, 32, 8, 16, 1, 1, 1, False, None, False),
     ("conv2_gate_head_res", 2, 16, 32, 8, 16, 1, 1, 1, False, 1, False),
