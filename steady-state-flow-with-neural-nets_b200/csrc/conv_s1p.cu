@@ -41,6 +41,8 @@ struct SpParams {
   int Cout;                            // real accumulator width (bias entries)
   int res_mode;                        // 0 none, 1 staged plain tile (Cres == F), 2 generic global loads
   int Cres, RH, RW, res_pool;
+  long long* timing;                   // debug: 8 clock64 stamps per CTA for its third tile (nullptr in production)
+  int timing_ctas;
 };
 
 template <int CLOG, int J, bool GATE, bool SKIP>
@@ -252,9 +254,12 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
       const uint32_t cur = (uint32_t)((it >> 1) & 1), prev = cur ^ 1u;
       const uint32_t planes = sbase + Cfg::OFF_PLANES + s * Cfg::PLANE_BYTES;
       const uint32_t planes_s = sbase + Cfg::OFF_PLANES_S + s * Cfg::PLANE_BYTES;
+      long long* stamp = (p.timing != nullptr && it == 2 && (int)blockIdx.x < p.timing_ctas && tid == 0) ? p.timing + (size_t)blockIdx.x * 8 : nullptr;
+      if (stamp) stamp[0] = clock64();
       ok = ok && ptx::mbar_wait(bar(SB_X + s), cur);                // raw tile landed
       if (it >= 2) ok = ok && ptx::mbar_wait(bar(SB_TF + s), prev); // MMAs of tile it-2 no longer read planes[s]
       if (!ok) atomicCAS(p.status, 0, 11);
+      if (stamp) stamp[1] = clock64();                              // waits done
       transform_tile<Cfg>(sbase + Cfg::OFF_STAGE + s * Cfg::STAGE_BYTES, planes, tid);
       if (SKIP) {
         ok = ok && ptx::mbar_wait(bar(SB_S + s), cur);
@@ -263,7 +268,9 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
       }
       ptx::mbar_arrive(bar(SB_XF + s));                             // stage[s] may be refilled
       ptx::fence_proxy_async_smem();                                // planes -> visible to the tensor core
+      if (stamp) stamp[2] = clock64();                              // transform done
       front_barrier();
+      if (stamp) stamp[3] = clock64();                              // front barrier passed
       if (warp < J) {
         // sub-tile j = warp: fully unrolled k-step program, immediate descriptor offsets
         if (it == 0) ok = ok && ptx::mbar_wait(bar(SB_W), 0);
@@ -293,6 +300,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
         if (leader) ptx::mma_commit(bar(SB_TF + s));
         __syncwarp();
       }
+      if (stamp) stamp[4] = clock64();                              // MMAs issued
     }
   } else {
     // =========================== back: epilogue ===========================
@@ -315,6 +323,8 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
           if (oy1 < p.H && ox1 < p.W) r1[j] = __bfloat162float(__ldg(p.res + ((size_t)b * p.H + oy1) * p.W + ox1));
         }
       }
+      long long* bstamp = (p.timing != nullptr && it == 2 && (int)blockIdx.x < p.timing_ctas && tid == 128) ? p.timing + (size_t)blockIdx.x * 8 : nullptr;
+      if (bstamp) bstamp[5] = clock64();
       ok = ok && ptx::mbar_wait(bar(SB_TF + s), cur);
       if (!ok) atomicCAS(p.status, 0, 14);
       ptx::tc_fence_after_sync();
@@ -322,6 +332,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
         ok = ok && ptx::mbar_wait(bar(SB_R + s), cur);
         if (!ok) atomicCAS(p.status, 0, 15);
       }
+      if (bstamp) bstamp[6] = clock64();                            // accumulators (and shortcut) ready
       const int oy = y0 + v;
 #pragma unroll
       for (int j = 0; j < J; ++j) {
@@ -364,6 +375,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
           }
         }
       }
+      if (bstamp) bstamp[7] = clock64();                            // epilogue done
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(bar(SB_TE + s));        // accumulator buffer s and res[s] are free
     }
@@ -411,6 +423,7 @@ static bool make_map_nhwc(CUtensorMap* tm, const void* base, int B, int H, int W
 }
 
 int* tc_status_word();   // conv_tc.cu: lazily allocated device status word
+void tc_timing_buffer(long long** buf, int* ctas);   // conv_tc.cu: debug stamp buffer (fn_debug_set_timing)
 
 template <int CLOG, int J, bool GATE, bool SKIP>
 static int launch_s1p(const fn_conv_desc& d, cudaStream_t stream) {
@@ -449,6 +462,7 @@ static int launch_s1p(const fn_conv_desc& d, cudaStream_t stream) {
   p.ntiles = d.B * p.tiles_u * p.tiles_v;
   p.Cout = d.Cout;
   p.Cres = d.Cres; p.RH = d.RH; p.RW = d.RW; p.res_pool = d.res_pool;
+  tc_timing_buffer(&p.timing, &p.timing_ctas);
 
   auto kern = k_conv_s1p<CLOG, J, GATE, SKIP>;
   static bool configured = false;

@@ -661,6 +661,7 @@ static int ensure_status_word() {
   return 0;
 }
 
+void tc_timing_buffer(long long** buf, int* ctas) { *buf = g_tc_timing_dev; *ctas = g_tc_timing_ctas; }
 int* tc_status_word() { return ensure_status_word() == 0 ? g_tc_status_dev : nullptr; }
 bool conv_s1p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1p.cu
 bool conv_s1d_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1d.cu
