@@ -26,7 +26,8 @@
 
 namespace fn {
 
-constexpr int SP_THREADS = 288;   // 4 front warps, 4 back warps, 1 producer warp
+constexpr int SP_THREADS = 448;   // warps 0-3 front, 4-11 back, 12 TMA producer (+TMEM owner), 13 MMA issuer
+constexpr int SP_WARP_PRODUCER = 12, SP_WARP_ISSUER = 13;
 constexpr int SP_HDR = 256 + 1024;
 
 struct SpParams {
@@ -74,7 +75,7 @@ struct SpCfg {
 };
 
 // mbarriers (8 B each) inside the header; [2] = one per buffer
-enum { SB_W = 0, SB_X = 1, SB_S = 3, SB_XF = 5, SB_TF = 7, SB_TE = 9, SB_R = 11, SB_COUNT = 13 };
+enum { SB_W = 0, SB_X = 1, SB_S = 3, SB_XF = 5, SB_TF = 7, SB_TE = 9, SB_R = 11, SB_PF = 13, SB_COUNT = 15 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -183,9 +184,10 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
     y0 = tv * 16;
   };
   const int n_local = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  long long* stamps = (p.timing != nullptr && (int)blockIdx.x < p.timing_ctas) ? p.timing + (size_t)blockIdx.x * 8 : nullptr;
 
   // ---- one-time setup
-  if (warp == 8) {
+  if (warp == SP_WARP_PRODUCER) {
     ptx::tmem_alloc(sbase + 128, (uint32_t)Cfg::TMEM_COLS);
     ptx::tmem_relinquish();
     if (lane == 0) {
@@ -194,8 +196,9 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
         ptx::mbar_init(bar(SB_X + s), 1);
         ptx::mbar_init(bar(SB_S + s), 1);
         ptx::mbar_init(bar(SB_XF + s), 128);
-        ptx::mbar_init(bar(SB_TF + s), (uint32_t)J);
-        ptx::mbar_init(bar(SB_TE + s), 128);
+        ptx::mbar_init(bar(SB_PF + s), 128);
+        ptx::mbar_init(bar(SB_TF + s), 1);
+        ptx::mbar_init(bar(SB_TE + s), 256);
         ptx::mbar_init(bar(SB_R + s), 1);
       }
       ptx::fence_mbar_init();
@@ -213,8 +216,8 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   bool ok = true;
 
-  if (warp == 8) {
-    // =========================== producer ===========================
+  if (warp == SP_WARP_PRODUCER) {
+    // =========================== producer: TMA ===========================
     if (lane == 0) {
       ptx::mbar_arrive_expect_tx(bar(SB_W), (uint32_t)Cfg::W_BYTES);
       ptx::bulk_g2s(sbase + Cfg::OFF_W, p.wpk, (uint32_t)Cfg::W_BYTES, bar(SB_W));
@@ -244,22 +247,66 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
       }
     }
     __syncwarp();
-  } else if (warp < 4) {
-    // =========================== front: transform + MMA issue ===========================
+  } else if (warp == SP_WARP_ISSUER) {
+    // =========================== issuer: one elected lane feeds the tensor core ===========================
+    // The warp runs the loop convergently so descriptor arithmetic stays on the uniform datapath; the whole
+    // k-step program of a tile (J sub-tiles x 9 taps x KS) is unrolled with immediate descriptor offsets.
     const uint32_t leader = ptx::elect_one();
     constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, Cfg::N);
     const uint64_t b_tmpl = ptx::smem_desc(sbase + Cfg::OFF_W, Cfg::N * 16, 128);
+    ok = ptx::mbar_wait(bar(SB_W), 0);
+    if (!ok) atomicCAS(p.status, 0, 13);
+    for (int it = 0; it < n_local; ++it) {
+      const int s = it & 1;
+      const uint32_t cur = (uint32_t)((it >> 1) & 1), prev = cur ^ 1u;
+      ok = ok && ptx::mbar_wait(bar(SB_PF + s), cur);                    // planes[s] written and fenced
+      if (it >= 2) ok = ok && ptx::mbar_wait(bar(SB_TE + s), prev);      // back drained accumulator buffer s
+      if (!ok) atomicCAS(p.status, 0, 16);
+      ptx::tc_fence_after_sync();
+      if (stamps && it == 2 && lane == 0) stamps[3] = clock64();
+      const uint64_t a_tmpl = ptx::smem_desc(sbase + Cfg::OFF_PLANES + s * Cfg::PLANE_BYTES, Cfg::PPAD * 16, Cfg::PU * 16);
+      const uint64_t s_tmpl = ptx::smem_desc(sbase + Cfg::OFF_PLANES_S + s * Cfg::PLANE_BYTES + (Cfg::PU + 1) * 16, Cfg::PPAD * 16,
+                                             Cfg::PU * 16);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(s * Cfg::ACC_COLS);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+        for (int kk = 0; kk < Cfg::KS; ++kk) {
+          const uint32_t a_off = (uint32_t)(((tap / 3) * Cfg::PU + (tap % 3)) * 16 + kk * 2 * Cfg::PPAD * 16) >> 4;
+          const uint32_t b_off = (uint32_t)((tap * Cfg::KS + kk) * Cfg::N * 32) >> 4;
+#pragma unroll
+          for (int j = 0; j < J; ++j)
+            if (leader) ptx::mma_bf16_ss(d_tmem + (uint32_t)(j * Cfg::N), a_tmpl + a_off + (uint32_t)(8 * j), b_tmpl + b_off, idesc,
+                                         (tap | kk) ? 1u : 0u);
+        }
+      }
+      if (SKIP) {
+#pragma unroll
+        for (int kk = 0; kk < Cfg::KS; ++kk) {
+          const uint32_t a_off = (uint32_t)(kk * 2 * Cfg::PPAD * 16) >> 4;
+          const uint32_t b_off = (uint32_t)((9 * Cfg::KS + kk) * Cfg::N * 32) >> 4;
+#pragma unroll
+          for (int j = 0; j < J; ++j)
+            if (leader) ptx::mma_bf16_ss(d_tmem + (uint32_t)(j * Cfg::N), s_tmpl + a_off + (uint32_t)(8 * j), b_tmpl + b_off, idesc, 1u);
+        }
+      }
+      if (leader) ptx::mma_commit(bar(SB_TF + s));
+      __syncwarp();
+      if (stamps && it == 2 && lane == 0) stamps[4] = clock64();
+    }
+  } else if (warp < 4) {
+    // =========================== front: stage -> concat_elu -> A planes ===========================
     for (int it = 0; it < n_local; ++it) {
       const int s = it & 1;
       const uint32_t cur = (uint32_t)((it >> 1) & 1), prev = cur ^ 1u;
       const uint32_t planes = sbase + Cfg::OFF_PLANES + s * Cfg::PLANE_BYTES;
       const uint32_t planes_s = sbase + Cfg::OFF_PLANES_S + s * Cfg::PLANE_BYTES;
-      long long* stamp = (p.timing != nullptr && it == 2 && (int)blockIdx.x < p.timing_ctas && tid == 0) ? p.timing + (size_t)blockIdx.x * 8 : nullptr;
+      long long* stamp = (stamps && it == 2 && tid == 0) ? stamps : nullptr;
       if (stamp) stamp[0] = clock64();
       ok = ok && ptx::mbar_wait(bar(SB_X + s), cur);                // raw tile landed
       if (it >= 2) ok = ok && ptx::mbar_wait(bar(SB_TF + s), prev); // MMAs of tile it-2 no longer read planes[s]
       if (!ok) atomicCAS(p.status, 0, 11);
-      if (stamp) stamp[1] = clock64();                              // waits done
+      if (stamp) stamp[1] = clock64();
       transform_tile<Cfg>(sbase + Cfg::OFF_STAGE + s * Cfg::STAGE_BYTES, planes, tid);
       if (SKIP) {
         ok = ok && ptx::mbar_wait(bar(SB_S + s), cur);
@@ -267,46 +314,24 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
         transform_tile<Cfg>(sbase + Cfg::OFF_STAGE_S + s * Cfg::STAGE_BYTES, planes_s, tid);
       }
       ptx::mbar_arrive(bar(SB_XF + s));                             // stage[s] may be refilled
-      ptx::fence_proxy_async_smem();                                // planes -> visible to the tensor core
-      if (stamp) stamp[2] = clock64();                              // transform done
-      front_barrier();
-      if (stamp) stamp[3] = clock64();                              // front barrier passed
-      if (warp < J) {
-        // sub-tile j = warp: fully unrolled k-step program, immediate descriptor offsets
-        if (it == 0) ok = ok && ptx::mbar_wait(bar(SB_W), 0);
-        if (it >= 2) ok = ok && ptx::mbar_wait(bar(SB_TE + s), prev);   // back drained accumulator buffer s
-        if (!ok) atomicCAS(p.status, 0, 13);
-        ptx::tc_fence_after_sync();
-        const uint64_t a_tmpl = ptx::smem_desc(planes, Cfg::PPAD * 16, Cfg::PU * 16) + (uint64_t)(8 * warp);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(s * Cfg::ACC_COLS + warp * Cfg::N);
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-#pragma unroll
-          for (int kk = 0; kk < Cfg::KS; ++kk) {
-            const uint32_t a_off = (uint32_t)(((tap / 3) * Cfg::PU + (tap % 3)) * 16 + kk * 2 * Cfg::PPAD * 16) >> 4;
-            const uint32_t b_off = (uint32_t)((tap * Cfg::KS + kk) * Cfg::N * 32) >> 4;
-            if (leader) ptx::mma_bf16_ss(d_tmem, a_tmpl + a_off, b_tmpl + b_off, idesc, (tap | kk) ? 1u : 0u);
-          }
-        }
-        if (SKIP) {
-          const uint64_t s_tmpl = ptx::smem_desc(planes_s + (Cfg::PU + 1) * 16, Cfg::PPAD * 16, Cfg::PU * 16) + (uint64_t)(8 * warp);
-#pragma unroll
-          for (int kk = 0; kk < Cfg::KS; ++kk) {
-            const uint32_t a_off = (uint32_t)(kk * 2 * Cfg::PPAD * 16) >> 4;
-            const uint32_t b_off = (uint32_t)((9 * Cfg::KS + kk) * Cfg::N * 32) >> 4;
-            if (leader) ptx::mma_bf16_ss(d_tmem, s_tmpl + a_off, b_tmpl + b_off, idesc, 1u);
-          }
-        }
-        if (leader) ptx::mma_commit(bar(SB_TF + s));
-        __syncwarp();
-      }
-      if (stamp) stamp[4] = clock64();                              // MMAs issued
+      ptx::fence_proxy_async_smem();                                // this thread's plane writes -> tensor-core proxy
+      ptx::mbar_arrive(bar(SB_PF + s));                             // planes[s] ready (128 arrivals)
+      if (stamp) stamp[2] = clock64();
     }
   } else {
-    // =========================== back: epilogue ===========================
-    const int r = tid - 128;                 // accumulator row == TMEM lane
+    // =========================== back: 8 epilogue warps ===========================
+    // warp wb: TMEM lane quadrant wb & 3; half = wb >> 2 takes the odd / even sub-tiles (J >= 2) or the
+    // upper / lower half of the channels (J == 1)
+    const int wb = warp - 4;
+    const int q = wb & 3, half = wb >> 2;
+    const int r = q * 32 + lane;             // accumulator row == TMEM lane
     const int v = r >> 3, u = r & 7;
-    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int JSTEP = J >= 2 ? 2 : 1;
+    constexpr int CSPAN = J >= 2 ? Cfg::F : (Cfg::F >= 16 ? Cfg::F / 2 : Cfg::F);
+    const int j_first = J >= 2 ? half : 0;
+    const int c_first = J >= 2 ? 0 : (Cfg::F >= 16 ? half * (Cfg::F / 2) : 0);
+    const bool idle = (J == 1 && Cfg::F < 16 && half == 1);   // nothing to split: second half only signals
     for (int it = 0; it < n_local; ++it) {
       const int s = it & 1;
       const uint32_t cur = (uint32_t)((it >> 1) & 1);
@@ -323,7 +348,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
           if (oy1 < p.H && ox1 < p.W) r1[j] = __bfloat162float(__ldg(p.res + ((size_t)b * p.H + oy1) * p.W + ox1));
         }
       }
-      long long* bstamp = (p.timing != nullptr && it == 2 && (int)blockIdx.x < p.timing_ctas && tid == 128) ? p.timing + (size_t)blockIdx.x * 8 : nullptr;
+      long long* bstamp = (stamps && it == 2 && tid == 128) ? stamps : nullptr;
       if (bstamp) bstamp[5] = clock64();
       ok = ok && ptx::mbar_wait(bar(SB_TF + s), cur);
       if (!ok) atomicCAS(p.status, 0, 14);
@@ -332,59 +357,64 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
         ok = ok && ptx::mbar_wait(bar(SB_R + s), cur);
         if (!ok) atomicCAS(p.status, 0, 15);
       }
-      if (bstamp) bstamp[6] = clock64();                            // accumulators (and shortcut) ready
+      if (bstamp) bstamp[6] = clock64();
       const int oy = y0 + v;
+      if (!idle) {
 #pragma unroll
-      for (int j = 0; j < J; ++j) {
-        const int ox = x0 + 8 * j + u;
-        const bool live = ok && oy < p.H && ox < p.W;
-        const size_t pix = ((size_t)b * p.H + oy) * p.W + ox;
-        const uint32_t col0 = lane_base + (uint32_t)(s * Cfg::ACC_COLS + j * Cfg::N);
+        for (int jj = 0; jj < J; jj += JSTEP) {
+          const int j = jj + j_first;
+          if (j >= J) break;
+          const int ox = x0 + 8 * j + u;
+          const bool live = ok && oy < p.H && ox < p.W;
+          const size_t pix = ((size_t)b * p.H + oy) * p.W + ox;
+          const uint32_t col0 = lane_base + (uint32_t)(s * Cfg::ACC_COLS + j * Cfg::N);
 #pragma unroll
-        for (int c0 = 0; c0 < Cfg::F; c0 += 8) {
-          float o[8];
-          if (GATE) {
-            float a[8], g[8];
-            ptx::tmem_ld8x2(col0 + c0, col0 + Cfg::F + c0, a, g);
-            // u * sigmoid(v) with sigmoid(z) = 0.5 + 0.5 tanh(z/2); the v bias is stored pre-halved
+          for (int cc = 0; cc < CSPAN; cc += 8) {
+            const int c0 = c_first + cc;
+            float o[8];
+            if (GATE) {
+              float a[8], g[8];
+              ptx::tmem_ld8x2(col0 + c0, col0 + Cfg::F + c0, a, g);
+              // u * sigmoid(v) with sigmoid(z) = 0.5 + 0.5 tanh(z/2); the v bias is stored pre-halved
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float th = tanh_approx(fmaf(g[i], 0.5f, sbias[Cfg::F + c0 + i]));
-              o[i] = (a[i] + sbias[c0 + i]) * fmaf(th, 0.5f, 0.5f);
+              for (int i = 0; i < 8; ++i) {
+                const float th = tanh_approx(fmaf(g[i], 0.5f, sbias[Cfg::F + c0 + i]));
+                o[i] = (a[i] + sbias[c0 + i]) * fmaf(th, 0.5f, 0.5f);
+              }
+              if (p.res_mode == 1) {
+                bf16x8 rr;
+                rr.v = lds128(sbase + Cfg::OFF_RES + s * Cfg::RES_BYTES + (uint32_t)((v * 8 * J + 8 * j + u) * Cfg::F + c0) * 2u);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] += __bfloat162float(rr.h[i]);
+              } else if (p.res_mode == 2 && live) {
+                sp_shortcut_generic(p, Cfg::F, b, oy, ox, c0, o);
+              } else if (p.res_mode == 3 && c0 == Cfg::F - 8) {
+                o[7] += r1[j];
+              }
+            } else {
+              ptx::tmem_ld8(col0 + c0, o);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] += sbias[c0 + i];
             }
-            if (p.res_mode == 1) {
-              bf16x8 rr;
-              rr.v = lds128(sbase + Cfg::OFF_RES + s * Cfg::RES_BYTES + (uint32_t)((v * 8 * J + 8 * j + u) * Cfg::F + c0) * 2u);
+            if (live) {
+              bf16x8 st;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] += __bfloat162float(rr.h[i]);
-            } else if (p.res_mode == 2 && live) {
-              sp_shortcut_generic(p, Cfg::F, b, oy, ox, c0, o);
-            } else if (p.res_mode == 3 && c0 == Cfg::F - 8) {
-              o[7] += r1[j];
+              for (int i = 0; i < 8; ++i) st.h[i] = __float2bfloat16(o[i]);
+              *reinterpret_cast<uint4*>(p.y + pix * Cfg::F + c0) = st.v;
             }
-          } else {
-            ptx::tmem_ld8(col0 + c0, o);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] += sbias[c0 + i];
-          }
-          if (live) {
-            bf16x8 st;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) st.h[i] = __float2bfloat16(o[i]);
-            *reinterpret_cast<uint4*>(p.y + pix * Cfg::F + c0) = st.v;
           }
         }
       }
-      if (bstamp) bstamp[7] = clock64();                            // epilogue done
+      if (bstamp) bstamp[7] = clock64();
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(bar(SB_TE + s));        // accumulator buffer s and res[s] are free
+      ptx::mbar_arrive(bar(SB_TE + s));        // accumulator buffer s and res[s] are free (256 arrivals)
     }
   }
 
   // ---- teardown
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == SP_WARP_PRODUCER) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, (uint32_t)Cfg::TMEM_COLS);
   }
