@@ -543,3 +543,18 @@ def test_training_loss_decreases(native):
         flow_net.end_training()
         flow_net.reset_training_state()
         arch.reset_variables(1234)
+
+
+def test_stream_host_matches_eager(native):
+    """The overlapped serving loop (pinned host in/out, side-stream copies) returns the same fields."""
+    import model.flow_architecture as arch
+    import model.flow_net as flow_net
+    arch.reset_variables(1234)
+    ci = flow_net.CompiledInference(2, (32, 64))
+    xs = [torch.from_numpy(fo.synth_boundary(2, 32, 64, seed=10 + i).astype(np.uint8)).pin_memory() for i in range(5)]
+    outs = [torch.empty(2, 32, 64, 2).pin_memory() for _ in range(5)]
+    ci.stream_host(xs, outs)
+    torch.cuda.synchronize()
+    for x, o in zip(xs, outs):
+        ref = flow_net.inference(x.cuda(), 1.0)
+        assert torch.equal(ref.cpu(), o)
