@@ -1,0 +1,417 @@
+// Persistent, warp-specialised tcgen05 kernels for the two RESAMPLING convolutions of flow_net with
+// resident weights, built like k_conv_s1p (conv_s1p.cu: TMA producer warp, 4 front warps, 8 back
+// warps, 1 issuer warp, double-buffered stage / planes / TMEM behind mbarriers):
+//
+//   MODE_S2     3x3 stride-2 'SAME' conv with the concat_elu prologue (conv_1 of the down-sampling
+//               res_blocks, reference flow_architecture.py:132-135 with stride=2; TF pads (0,1) on even
+//               sizes).  The 33 x (16J+1) input tile is split by the front warps into its four
+//               (row, column)-parity sub-planes, so that a stride-2 tap is again a unit-stride view:
+//               input 2o+d -> parity d&1, position o + (d>>1).
+//   MODE_TCONV  3x3 stride-2 transposed conv (reference :70-87) as a sub-pixel implicit GEMM over INPUT
+//               pixels: out[2m+p] takes taps d=p (in[m]) and, for p=0, d=2 (in[m-1]);
+//               the four output phases are four TMEM accumulators (4/2/2/1 taps), written by the
+//               epilogue to the four interleaved output pixels.  No prologue: the front warps only
+//               re-lay the tile out as 8-channel planes.
+//
+// Same A/B operand layouts, MMA order and bf16 rounding points as the generic k_conv_tc.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace fn {
+namespace s2t {
+
+constexpr int THREADS = 448;
+constexpr int WARP_PRODUCER = 12, WARP_ISSUER = 13;
+constexpr int HDR = 256 + 1024;
+enum { MODE_S2 = 1, MODE_TCONV = 2 };
+
+struct Params {
+  CUtensorMap tm_x;
+  const __nv_bfloat16* wpk;
+  const float* bias;
+  __nv_bfloat16* y;
+  int* status;
+  int B, H, W;            // input tensor
+  int OH, OW;             // output tensor
+  int RH, RW;             // GEMM-row image: output pixels (S2) or input pixels (TCONV)
+  int tiles_u, tiles_v, ntiles;
+  int Cout;               // real output channels
+};
+
+template <int MODE, int CLOG, int J, int NBUF>
+struct Cfg {
+  static constexpr int CH = 1 << CLOG;                       // 8-channel chunks of the raw input
+  static constexpr int C = 8 * CH;
+  static constexpr bool S2 = MODE == MODE_S2;
+  static constexpr int KPLANES = S2 ? 2 * CH : CH;          // 8-channel planes of one (sub-)operand
+  static constexpr int KS = S2 ? CH : CH / 2;                // k-steps per tap
+  static constexpr int NREAL = S2 ? 2 * C : C / 2;           // Cout
+  static constexpr int N = NREAL < 16 ? 16 : NREAL;
+  static constexpr int NPH = S2 ? 1 : 4;                     // accumulators per sub-tile
+  static constexpr int KSTEPS = 9 * KS;
+  // stage tile (TMA box): S2 33 x (16J+1) input pixels, TCONV 17 x (8J+1)
+  static constexpr int SW_ = S2 ? 16 * J + 1 : 8 * J + 1, SH_ = S2 ? 33 : 17, SP = SW_ * SH_;
+  // (sub-)plane geometry: 17 x (8J+1) positions
+  static constexpr int PU = 8 * J + 1, PV = 17, P = PU * PV;
+  static constexpr int PADW = KPLANES >= 8 ? 1 : (KPLANES == 4 ? 2 : (KPLANES == 2 ? 4 : 0));
+  static constexpr int PPAD = KPLANES == 1 ? P : P + ((PADW - (P & 7)) + 8) % 8;
+  static constexpr int SUB_BYTES = KPLANES * PPAD * 16;
+  static constexpr int NSUB = S2 ? 4 : 1;
+  static constexpr int W_BYTES = KSTEPS * N * 32;
+  static constexpr int PLANE_BYTES = (NSUB * SUB_BYTES + 127) / 128 * 128;
+  static constexpr int STAGE_BYTES = (SP * C * 2 + 127) / 128 * 128;
+  static constexpr int OFF_W = HDR;
+  static constexpr int OFF_PLANES = OFF_W + (W_BYTES + 127) / 128 * 128;
+  static constexpr int OFF_STAGE = OFF_PLANES + NBUF * PLANE_BYTES;
+  static constexpr int SMEM = OFF_STAGE + NBUF * STAGE_BYTES + 128;
+  static constexpr int ACC_COLS = J * NPH * N;
+  static constexpr int TCOLS = NBUF * ACC_COLS;
+  static constexpr int TMEM_COLS = TCOLS <= 32 ? 32 : TCOLS <= 64 ? 64 : TCOLS <= 128 ? 128 : TCOLS <= 256 ? 256 : 512;
+  static_assert(TCOLS <= 512, "accumulators exceed TMEM");
+  static_assert(S2 || CH >= 2, "transposed conv needs C >= 16");
+};
+
+enum { SB_W = 0, SB_X = 1, SB_XF = 3, SB_PF = 5, SB_TF = 7, SB_TE = 9, SB_COUNT = 11 };
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// stage [SH_][SW_][C] raw bf16 -> operand planes
+template <typename CF>
+__device__ __forceinline__ void transform_tile(uint32_t stage, uint32_t planes, int tid) {
+  constexpr int ITEMS = CF::SP * CF::CH;
+  constexpr int SH = CF::CH == 1 ? 0 : (CF::CH == 2 ? 1 : (CF::CH == 4 ? 2 : 3));
+#pragma unroll 2
+  for (int idx = tid; idx < ITEMS; idx += 128) {
+    const int ch = idx & (CF::CH - 1);
+    const int sp = idx >> SH;                        // stage pixel
+    bf16x8 in;
+    in.v = lds128(stage + (uint32_t)idx * 16u);
+    if (CF::S2) {
+      const int r = sp / CF::SW_, c = sp - r * CF::SW_;
+      const int sub = (r & 1) * 2 + (c & 1);
+      const int pp = (r >> 1) * CF::PU + (c >> 1);
+      bf16x8 o0, o1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = __bfloat162float(in.h[j]);
+        const float t = __expf(-fabsf(v)) - 1.f;
+        o0.h[j] = __float2bfloat16(v > 0.f ? v : t);
+        o1.h[j] = __float2bfloat16(v > 0.f ? t : -v);
+      }
+      const uint32_t d0 = planes + (uint32_t)(sub * CF::SUB_BYTES) + (uint32_t)(ch * CF::PPAD + pp) * 16u;
+      sts128(d0, o0.v);
+      sts128(d0 + (uint32_t)(CF::CH * CF::PPAD * 16), o1.v);
+    } else {
+      sts128(planes + (uint32_t)(ch * CF::PPAD + sp) * 16u, in.v);
+    }
+  }
+}
+
+template <int MODE, int CLOG, int J, int NBUF>
+__global__ void __launch_bounds__(THREADS) k_conv_s2t(const __grid_constant__ Params p) {
+  using CF = Cfg<MODE, CLOG, J, NBUF>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const uint32_t sbase = ptx::smem_u32(smem);
+  auto bar = [&](int i) { return sbase + 8u * (uint32_t)i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 128);
+  float* sbias = reinterpret_cast<float*>(smem + 256);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int tid = threadIdx.x;
+
+  auto tile_coords = [&](int t, int& b, int& y0, int& x0) {
+    const int tu = t % p.tiles_u;
+    const int r = t / p.tiles_u;
+    const int tv = r % p.tiles_v;
+    b = r / p.tiles_v;
+    x0 = tu * 8 * J;
+    y0 = tv * 16;
+  };
+  const int n_local = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // buffer index and the parity of its k-th use
+  auto buf_of = [](int it) { return NBUF == 2 ? (it & 1) : 0; };
+  auto use_of = [](int it) { return NBUF == 2 ? (it >> 1) : it; };
+
+  if (warp == WARP_PRODUCER) {
+    ptx::tmem_alloc(sbase + 128, (uint32_t)CF::TMEM_COLS);
+    ptx::tmem_relinquish();
+    if (lane == 0) {
+      ptx::mbar_init(bar(SB_W), 1);
+      for (int s = 0; s < 2; ++s) {
+        ptx::mbar_init(bar(SB_X + s), 1);
+        ptx::mbar_init(bar(SB_XF + s), 128);
+        ptx::mbar_init(bar(SB_PF + s), 128);
+        ptx::mbar_init(bar(SB_TF + s), 1);
+        ptx::mbar_init(bar(SB_TE + s), 256);
+      }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+  }
+  for (int i = tid; i < CF::N; i += THREADS) sbias[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  bool ok = true;
+
+  if (warp == WARP_PRODUCER) {
+    // =========================== producer: TMA ===========================
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(bar(SB_W), (uint32_t)CF::W_BYTES);
+      ptx::bulk_g2s(sbase + CF::OFF_W, p.wpk, (uint32_t)CF::W_BYTES, bar(SB_W));
+      for (int it = 0; it < n_local && ok; ++it) {
+        const int s = buf_of(it), k = use_of(it);
+        int b, y0, x0;
+        tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, y0, x0);
+        if (k >= 1) {
+          ok = ptx::mbar_wait(bar(SB_XF + s), (uint32_t)((k - 1) & 1));       // front finished reading stage[s]
+          if (!ok) { atomicCAS(p.status, 0, 41); break; }
+        }
+        ptx::mbar_arrive_expect_tx(bar(SB_X + s), (uint32_t)(CF::SP * CF::C * 2));
+        if (CF::S2) tma_load_4d(sbase + CF::OFF_STAGE + s * CF::STAGE_BYTES, &p.tm_x, bar(SB_X + s), 0, 2 * x0, 2 * y0, b);
+        else tma_load_4d(sbase + CF::OFF_STAGE + s * CF::STAGE_BYTES, &p.tm_x, bar(SB_X + s), 0, x0 - 1, y0 - 1, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == WARP_ISSUER) {
+    // =========================== issuer ===========================
+    const uint32_t leader = ptx::elect_one();
+    constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, CF::N);
+    const uint64_t b_tmpl = ptx::smem_desc(sbase + CF::OFF_W, CF::N * 16, 128);
+    ok = ptx::mbar_wait(bar(SB_W), 0);
+    if (!ok) atomicCAS(p.status, 0, 42);
+    for (int it = 0; it < n_local; ++it) {
+      const int s = buf_of(it), k = use_of(it);
+      ok = ok && ptx::mbar_wait(bar(SB_PF + s), (uint32_t)(k & 1));            // planes[s] written and fenced
+      if (k >= 1) ok = ok && ptx::mbar_wait(bar(SB_TE + s), (uint32_t)((k - 1) & 1));   // accumulators s drained
+      if (!ok) atomicCAS(p.status, 0, 43);
+      ptx::tc_fence_after_sync();
+      const uint64_t a_tmpl = ptx::smem_desc(sbase + CF::OFF_PLANES + s * CF::PLANE_BYTES, CF::PPAD * 16, CF::PU * 16);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(s * CF::ACC_COLS);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int di = tap / 3, dj = tap % 3;
+        // S2: parity sub-plane + position shift; TCONV: source position of the row pixel and output phase
+        const int sub_off = CF::S2 ? ((di & 1) * 2 + (dj & 1)) * CF::SUB_BYTES + ((di >> 1) * CF::PU + (dj >> 1)) * 16
+                                   : (((di == 2) ? 0 : 1) * CF::PU + ((dj == 2) ? 0 : 1)) * 16;
+        const int ph = CF::S2 ? 0 : ((di == 1) ? 2 : 0) + ((dj == 1) ? 1 : 0);
+        const bool first = CF::S2 ? (tap == 0) : (tap == 0 || tap == 1 || tap == 3 || tap == 4);
+#pragma unroll
+        for (int kk = 0; kk < CF::KS; ++kk) {
+          const uint32_t a_off = (uint32_t)(sub_off + kk * 2 * CF::PPAD * 16) >> 4;
+          const uint32_t b_off = (uint32_t)((tap * CF::KS + kk) * CF::N * 32) >> 4;
+#pragma unroll
+          for (int j = 0; j < J; ++j)
+            if (leader) ptx::mma_bf16_ss(d_tmem + (uint32_t)((j * CF::NPH + ph) * CF::N), a_tmpl + a_off + (uint32_t)(8 * j),
+                                         b_tmpl + b_off, idesc, (first && kk == 0) ? 0u : 1u);
+        }
+      }
+      if (leader) ptx::mma_commit(bar(SB_TF + s));
+      __syncwarp();
+    }
+  } else if (warp < 4) {
+    // =========================== front: stage -> planes ===========================
+    for (int it = 0; it < n_local; ++it) {
+      const int s = buf_of(it), k = use_of(it);
+      ok = ok && ptx::mbar_wait(bar(SB_X + s), (uint32_t)(k & 1));
+      if (k >= 1) ok = ok && ptx::mbar_wait(bar(SB_TF + s), (uint32_t)((k - 1) & 1));   // planes[s] no longer read
+      if (!ok) atomicCAS(p.status, 0, 44);
+      transform_tile<CF>(sbase + CF::OFF_STAGE + s * CF::STAGE_BYTES, sbase + CF::OFF_PLANES + s * CF::PLANE_BYTES, tid);
+      ptx::mbar_arrive(bar(SB_XF + s));
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(bar(SB_PF + s));
+    }
+  } else {
+    // =========================== back: 8 epilogue warps ===========================
+    const int wb = warp - 4;
+    const int q = wb & 3, half = wb >> 2;
+    const int r = q * 32 + lane;
+    const int v = r >> 3, u = r & 7;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    // work items of a tile: (sub-tile j, phase ph); the two halves take alternate items
+    constexpr int ITEMS = J * CF::NPH;
+    for (int it = 0; it < n_local; ++it) {
+      const int s = buf_of(it), k = use_of(it);
+      int b, y0, x0;
+      tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, y0, x0);
+      ok = ok && ptx::mbar_wait(bar(SB_TF + s), (uint32_t)(k & 1));
+      if (!ok) atomicCAS(p.status, 0, 45);
+      ptx::tc_fence_after_sync();
+      const int ry = y0 + v;
+#pragma unroll
+      for (int w0 = 0; w0 < ITEMS; w0 += 2) {
+        const int item = w0 + half;
+        if (ITEMS == 1 && half == 1) break;
+        if (item >= ITEMS) break;
+        const int j = item / CF::NPH, ph = item % CF::NPH;
+        const int rx = x0 + 8 * j + u;
+        const bool live = ok && ry < p.RH && rx < p.RW;
+        const int oy = CF::S2 ? ry : 2 * ry + (ph >> 1);
+        const int ox = CF::S2 ? rx : 2 * rx + (ph & 1);
+        const size_t pix = ((size_t)b * p.OH + oy) * p.OW + ox;
+        const uint32_t col0 = lane_base + (uint32_t)(s * CF::ACC_COLS + (j * CF::NPH + ph) * CF::N);
+#pragma unroll
+        for (int c0 = 0; c0 < CF::NREAL; c0 += 8) {
+          float o[8];
+          ptx::tmem_ld8(col0 + c0, o);
+          if (live) {
+            bf16x8 st;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) st.h[i] = __float2bfloat16(o[i] + sbias[c0 + i]);
+            *reinterpret_cast<uint4*>(p.y + pix * CF::NREAL + c0) = st.v;
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(bar(SB_TE + s));
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == WARP_PRODUCER) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)CF::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+static bool make_map_nhwc(CUtensorMap* tm, const void* base, int B, int H, int W, int C, int bw, int bh) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)bw, (cuuint32_t)bh, 1u};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int MODE, int CLOG, int J, int NBUF>
+static int launch(const void* x, const void* wpk, const float* bias, void* y, int B, int H, int W, int Cout, int* status,
+                  cudaStream_t stream) {
+  using CF = Cfg<MODE, CLOG, J, NBUF>;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  if (!make_map_nhwc(&p.tm_x, x, B, H, W, CF::C, CF::SW_, CF::SH_)) { set_error("conv_s2t: tensor map failed"); return FN_E_UNSUPPORTED; }
+  p.wpk = (const __nv_bfloat16*)wpk;
+  p.bias = bias;
+  p.y = (__nv_bfloat16*)y;
+  p.status = status;
+  p.B = B; p.H = H; p.W = W;
+  if (CF::S2) { p.OH = H / 2; p.OW = W / 2; p.RH = p.OH; p.RW = p.OW; }
+  else { p.OH = 2 * H; p.OW = 2 * W; p.RH = H; p.RW = W; }
+  p.tiles_u = (p.RW + 8 * J - 1) / (8 * J);
+  p.tiles_v = (p.RH + 15) / 16;
+  p.ntiles = B * p.tiles_u * p.tiles_v;
+  p.Cout = Cout;
+  auto kern = k_conv_s2t<MODE, CLOG, J, NBUF>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(s2t): %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  int per_sm = (227 * 1024) / (CF::SMEM + 1024);
+  const int tmem_lim = 512 / CF::TMEM_COLS;
+  if (per_sm > tmem_lim) per_sm = tmem_lim;
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  int grid = 148 * per_sm;
+  if (grid > p.ntiles) grid = p.ntiles;
+  kern<<<grid, THREADS, CF::SMEM, stream>>>(p);
+  count_launch();
+  return check_launch("k_conv_s2t");
+}
+
+}  // namespace s2t
+
+int* tc_status_word();
+
+// stride-2 conv_1 of a down-sampling block
+bool conv_s2p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc) {
+  using namespace s2t;
+  rc = 0;
+  if (d.ksize != 3 || d.stride != 2 || d.prologue != FN_PRO_CONCAT_ELU || d.epilogue != FN_EPI_BIAS || d.skip ||
+      d.keep_prob < 1.0f || d.w_tc == nullptr)
+    return false;
+  if ((d.H & 1) || (d.W & 1) || d.H < 32) return false;       // TF pads (0,1) on even sizes only; short images: generic kernel
+  if (d.Cout != 2 * d.Cin) return false;
+  if (get_encode() == nullptr) return false;
+  const int clog = d.Cin == 8 ? 0 : d.Cin == 16 ? 1 : d.Cin == 32 ? 2 : -1;
+  if (clog < 0) return false;
+  const int OW = d.W / 2;
+#define S2_CASE(CL, JJ, NB, CAP)                                                                              \
+  if (clog == CL && ((OW % (8 * JJ)) == 0 || JJ == 1) && Cfg<MODE_S2, CL, JJ, NB>::SMEM <= CAP * 1024) {       \
+    if (!dry_run) {                                                                                           \
+      int* st = tc_status_word();                                                                             \
+      rc = st ? launch<MODE_S2, CL, JJ, NB>(d.x, d.w_tc, d.bias, d.y, d.B, d.H, d.W, d.Cout, st, stream)      \
+              : (int)cudaErrorMemoryAllocation;                                                               \
+    }                                                                                                         \
+    return true;                                                                                              \
+  }
+  S2_CASE(0, 2, 2, 112) S2_CASE(0, 1, 2, 112)
+  S2_CASE(1, 2, 2, 112) S2_CASE(1, 1, 2, 150)
+  S2_CASE(2, 1, 1, 200)
+#undef S2_CASE
+  return false;
+}
+
+bool tconv_s2p_try(const fn_tconv_desc& d, cudaStream_t stream, bool dry_run, int& rc) {
+  using namespace s2t;
+  rc = 0;
+  if (d.w_tc == nullptr || d.Cout * 2 != d.Cin || d.H < 16) return false;
+  if (get_encode() == nullptr) return false;
+  const int clog = d.Cin == 16 ? 1 : d.Cin == 32 ? 2 : d.Cin == 64 ? 3 : -1;
+  if (clog < 0) return false;
+#define TC_CASE(CL, JJ, NB, CAP)                                                                              \
+  if (clog == CL && ((d.W % (8 * JJ)) == 0 || JJ == 1) && Cfg<MODE_TCONV, CL, JJ, NB>::SMEM <= CAP * 1024) {   \
+    if (!dry_run) {                                                                                           \
+      int* st = tc_status_word();                                                                             \
+      rc = st ? launch<MODE_TCONV, CL, JJ, NB>(d.x, d.w_tc, d.bias, d.y, d.B, d.H, d.W, d.Cout, st, stream)   \
+              : (int)cudaErrorMemoryAllocation;                                                               \
+    }                                                                                                         \
+    return true;                                                                                              \
+  }
+  TC_CASE(1, 4, 2, 112) TC_CASE(1, 2, 2, 112) TC_CASE(1, 1, 2, 112)
+  TC_CASE(2, 2, 2, 112) TC_CASE(2, 1, 2, 112)
+  TC_CASE(3, 2, 2, 112) TC_CASE(3, 1, 2, 150)
+#undef TC_CASE
+  return false;
+}
+
+}  // namespace fn

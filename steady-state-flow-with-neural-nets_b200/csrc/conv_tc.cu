@@ -665,6 +665,8 @@ void tc_timing_buffer(long long** buf, int* ctas) { *buf = g_tc_timing_dev; *cta
 int* tc_status_word() { return ensure_status_word() == 0 ? g_tc_status_dev : nullptr; }
 bool conv_s1p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1p.cu
 bool conv_s1d_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1d.cu
+bool conv_s2p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s2t.cu
+bool tconv_s2p_try(const fn_tconv_desc& d, cudaStream_t stream, bool dry_run, int& rc); // conv_s2t.cu
 
 static int launch_tc(TcParams& p, size_t smem_bytes, cudaStream_t stream) {
   int rc = ensure_status_word();
@@ -686,6 +688,7 @@ int conv_fwd_tc(const fn_conv_desc& d, cudaStream_t stream) {
   int rc_sp = 0;
   if (g_tc_use_s1p && conv_s1p_try(d, stream, false, rc_sp)) return rc_sp;
   if (g_tc_use_s1p && conv_s1d_try(d, stream, false, rc_sp)) return rc_sp;
+  if (g_tc_use_s1p && conv_s2p_try(d, stream, false, rc_sp)) return rc_sp;
   TcGeom g;
   TcParams p;
   size_t smem_bytes = 0;
@@ -726,6 +729,8 @@ bool tconv_tc_supported(const fn_tconv_desc& d, const char** why) {
 }
 
 int tconv_fwd_tc(const fn_tconv_desc& d, cudaStream_t stream) {
+  int rc_sp = 0;
+  if (g_tc_use_s1p && tconv_s2p_try(d, stream, false, rc_sp)) return rc_sp;
   TcGeom g;
   TcParams p;
   size_t smem_bytes = 0;

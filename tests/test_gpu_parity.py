@@ -196,6 +196,14 @@ S1P_CASES = [
     ("c64_8x16_tr_skip", 2, 8, 16, 64, 64, 1, 1, 0, True, None, False),
     ("single_tile", 1, 16, 8, 8, 16, 1, 1, 1, False, None, False),
     ("three_tiles_per_cta", 148 * 3, 16, 32, 8, 16, 1, 1, 1, False, None, False),
+    # stride-2 conv_1 of the down-sampling blocks: parity sub-plane kernel (conv_s2t.cu)
+    ("s2_c8", 3, 64, 64, 8, 16, 2, 1, 0, False, None, False),
+    ("s2_c16", 2, 32, 64, 16, 32, 2, 1, 0, False, None, False),
+    ("s2_c32", 2, 32, 32, 32, 64, 2, 1, 0, False, None, False),
+    ("s2_ragged_even", 2, 36, 44, 8, 16, 2, 1, 0, False, None, False),
+    ("s2_ragged_even_c16", 1, 38, 50, 16, 32, 2, 1, 0, False, None, False),
+    ("s2_many_tiles", 40, 64, 64, 8, 16, 2, 1, 0, False, None, False),
+    ("s2_many_tiles_c32", 80, 32, 32, 32, 64, 2, 1, 0, False, None, False),
 ]
 
 
@@ -238,6 +246,34 @@ def test_transposed_conv_vs_oracle(native, impl, B, H, W, Cin, Cout):
     assert native.tc_status() == 0
     assert native.last_used_tcgen05() == (impl == "tc")
     assert rel_l2(y, ref) < LAYER_TOL
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(3, 64, 128, 16, 8), (2, 32, 64, 32, 16), (2, 16, 32, 64, 32), (1, 20, 12, 64, 32),
+                                            (40, 32, 32, 16, 8), (70, 16, 16, 32, 16), (2, 19, 27, 16, 8)])
+def test_transposed_conv_persistent_vs_generic(native, B, H, W, Cin, Cout):
+    """conv_s2t.cu's sub-pixel kernel against the generic tcgen05 kernel (same MMA order: bit-identical)
+    and the oracle."""
+    g = torch.Generator().manual_seed(2)
+    x = bf16_round(torch.randn(B, H, W, Cin, generator=g, dtype=torch.float64))
+    w = bf16_round((torch.rand(3, 3, Cout, Cin, generator=g, dtype=torch.float64) * 2 - 1) * 0.2)
+    b = torch.rand(Cout, generator=g, dtype=torch.float64).float().double()
+    w16 = w.permute(0, 1, 3, 2).reshape(9, Cin, Cout).to("cuda", torch.bfloat16).contiguous()
+    w_tc = native.pack_conv_weights_tc(w16, None, 3, Cin, 0, Cout, False)
+    ys = []
+    try:
+        for use in (1, 0):
+            native.lib.fn_debug_set_use_s1p(use)
+            y = torch.full((B, 2 * H, 2 * W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+            native.tconv_fwd(x.to("cuda", torch.bfloat16), w16, b.to("cuda", torch.float32), y, B=B, H=H, W=W, Cin=Cin,
+                             Cout=Cout, impl=native.IMPL_TCGEN05, w_tc=w_tc)
+            torch.cuda.synchronize()
+            assert native.tc_status() == 0
+            ys.append(y)
+    finally:
+        native.lib.fn_debug_set_use_s1p(1)
+    if B * H * W <= 8192:
+        assert rel_l2(ys[0], fo.conv2d_transpose_same(x, w, 2) + b) < LAYER_TOL
+    assert torch.equal(ys[0], ys[1])
 
 
 # ------------------------------------------------------------------------------- whole network
