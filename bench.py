@@ -220,7 +220,7 @@ def run_train(args, rank, world, dist, native, arch, flow_net):
             "steps": args.steps, "warmup": max(args.warmup, 2), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic boundaries and targets",
             "config": {"workload": "configs[2]: training step, global batch 256, 128x256, L2 loss + TF1 Adam, "
-                                   "keep_prob 1.0; correctness-first backward (CUDA-core wgrad)",
+                                   "keep_prob 1.0; tcgen05 dgrad + wgrad",
                        "batch_per_gpu": B, "parallelism": f"dp{world}, one flat fp32 gradient all-reduce"},
             "gpu_launches": native.launch_count() - n0, "loss": float(loss.item()),
             "roofline": {"bound": "tensor", "achieved": v * 8.519e9 / 1e12, "peak": load_peaks()["tc_sustained"],

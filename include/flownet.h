@@ -168,10 +168,12 @@ int fn_tanh_l2_bwd(const float* p, const float* t, float* loss, void* dpre, int6
 int64_t fn_bias_grad_workspace(int64_t npix, int32_t N);
 int fn_bias_grad(const void* dY, float* db, float* workspace, int64_t npix, int32_t N, void* stream);
 /* dW[tap][k][n] = sum_pix pro(x)[pix*s+tap-pad][k] * dY[pix][n]; d describes the FORWARD launch (x, dims, ksize,
- * stride, prologue, keep_prob, dropout_seed); dW fp32 [k*k, Keff, Cout]; workspace: fn_conv_wgrad_workspace() floats */
+ * stride, prologue, keep_prob, dropout_seed, impl); dW fp32 [k*k, Keff, Cout]; workspace: fn_conv_wgrad_workspace() floats.
+ * FN_IMPL_AUTO runs the tcgen05 kernel (contraction over pixels, MN-major operands) when Cin, Cout are multiples of 8. */
 int64_t fn_conv_wgrad_workspace(const fn_conv_desc* d);
 int fn_conv_wgrad(const fn_conv_desc* d, const void* dY, float* dW, float* workspace, void* stream);
-/* transposed conv: dW fp32 [9, Cin, Cout] from x bf16 [B,H,W,Cin] and dY bf16 [B,2H,2W,Cout] */
+/* transposed conv: dW fp32 [9, Cout, Cin] (the variable's own [k,k,Cout,Cin] layout, flow_architecture.py:74) from
+ * x bf16 [B,H,W,Cin] and dY bf16 [B,2H,2W,Cout].  d->impl selects the kernel as in the forward calls. */
 int64_t fn_tconv_wgrad_workspace(const fn_tconv_desc* d);
 int fn_tconv_wgrad(const fn_tconv_desc* d, const void* dY, float* dW, float* workspace, void* stream);
 

@@ -232,7 +232,60 @@ __global__ void __launch_bounds__(256) k_conv_wgrad(const WgradParams p) {
   const int k = kti * 16 + kl, n = nti * 16 + nl;
   if (k < p.Keff && n < p.N) {
     const long long T = (long long)p.ksize * p.ksize;
-    p.partial[(((long long)blockIdx.y * T + tap) * p.Keff + k) * p.N + n] = acc;
+    if (p.transposed) p.partial[(((long long)blockIdx.y * T + tap) * p.N + n) * p.Keff + k] = acc;   // TF layout [k,k,Cout,Cin]
+    else p.partial[(((long long)blockIdx.y * T + tap) * p.Keff + k) * p.N + n] = acc;
+  }
+}
+
+// ---- weight gradient of the network's first conv (Cin = 1, no prologue, 3x3 stride 1; flow_architecture.py:177 ->
+// res_block conv_1 on the boundary): dW[tap][n] = sum_pix x[pix + tap - 1] * dY[pix][n].  One thread walks pixels with
+// 9 x 8 accumulators (blockIdx.y = 8-channel chunk of n); block tree reduction, one partial per block.
+constexpr int WG1_BLOCKS = 296;
+__global__ void __launch_bounds__(256) k_wgrad_cin1(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dY,
+                                                    float* __restrict__ partial, int B, int H, int W, int N) {
+  __shared__ float red[8][72];
+  const int n0 = blockIdx.y * 8;
+  const long long npix = (long long)B * H * W;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(pix % W);
+    const int py = (int)((pix / W) % H);
+    bf16x8 g;
+    g.v = *reinterpret_cast<const uint4*>(dY + pix * N + n0);
+    float gv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gv[j] = __bfloat162float(g.h[j]);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int iy = py + t / 3 - 1, ix = px + t % 3 - 1;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        const float xv = __bfloat162float(x[pix + (long long)(t / 3 - 1) * W + (t % 3 - 1)]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(xv, gv[j], acc[t][j]);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[t][j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][t * 8 + j] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < 72) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    const int t = threadIdx.x >> 3, j = threadIdx.x & 7;
+    partial[((long long)blockIdx.x * 9 + t) * N + n0 + j] = v;
   }
 }
 
@@ -297,6 +350,12 @@ static int wgrad_splits(long long rows) {
 }
 long long wgrad_workspace(long long rows, int T, int Keff, int N) { return (long long)wgrad_splits(rows) * T * Keff * N; }
 
+// wgrad_tc.cu
+long long wgrad_tc_workspace(int B, int H, int W, int C, int OH, int OW, int N, int ksize, int stride, int pro);
+bool wgrad_tc_try(const void* x, const void* dY, float* partial, int B, int H, int W, int C, int OH, int OW, int N, int ksize,
+                  int stride, int pro, float keep_prob, unsigned long long seed, int* S_out, cudaStream_t stream, int& rc);
+static long long max_ll(long long a, long long b) { return a > b ? a : b; }
+
 int conv_wgrad_launch(WgradParams& p, float* dW, float* workspace, cudaStream_t s) {
   const int T = p.ksize * p.ksize;
   p.kt = (p.Keff + 15) / 16;
@@ -351,7 +410,9 @@ int fn_bias_grad(const void* dY, float* db, float* workspace, int64_t npix, int3
 int64_t fn_conv_wgrad_workspace(const fn_conv_desc* d) {
   if (!d) return 0;
   const int OH = (d->H + d->stride - 1) / d->stride, OW = (d->W + d->stride - 1) / d->stride;
-  return wgrad_workspace((long long)d->B * OH * OW, d->ksize * d->ksize, d->Cin * pro_mult(d->prologue), d->Cout);
+  return max_ll(max_ll(wgrad_workspace((long long)d->B * OH * OW, d->ksize * d->ksize, d->Cin * pro_mult(d->prologue), d->Cout),
+                       (long long)WG1_BLOCKS * 9 * d->Cout),
+                wgrad_tc_workspace(d->B, d->H, d->W, d->Cin, OH, OW, d->Cout, d->ksize, d->stride, d->prologue));
 }
 
 /* d describes the FORWARD conv (x, dims, ksize, stride, prologue, keep_prob/seed; w, bias, y are ignored);
@@ -361,6 +422,26 @@ int fn_conv_wgrad(const fn_conv_desc* d, const void* dY, float* dW, float* works
   FN_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, FN_E_INVAL, "fn_conv_wgrad: bad dims");
   FN_REQUIRE((d->ksize == 1 || d->ksize == 3) && (d->stride == 1 || d->stride == 2), FN_E_UNSUPPORTED,
              "fn_conv_wgrad: ksize %d stride %d", d->ksize, d->stride);
+  if (d->Cin == 1 && d->prologue == FN_PRO_NONE && d->ksize == 3 && d->stride == 1 && (d->Cout & 7) == 0 && d->impl != FN_IMPL_SIMT) {
+    dim3 grid(WG1_BLOCKS, d->Cout / 8);
+    k_wgrad_cin1<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d->x, (const __nv_bfloat16*)dY, workspace, d->B, d->H,
+                                                          d->W, d->Cout);
+    count_launch();
+    int rc = check_launch("k_wgrad_cin1");
+    if (rc) return rc;
+    return reduce_partials(workspace, dW, 9ll * d->Cout, WG1_BLOCKS, (cudaStream_t)stream);
+  }
+  if (d->impl != FN_IMPL_SIMT) {      // tensor-core kernel when the shape has one
+    const int OH = (d->H + d->stride - 1) / d->stride, OW = (d->W + d->stride - 1) / d->stride;
+    int S = 0, rc = 0;
+    if (wgrad_tc_try(d->x, dY, workspace, d->B, d->H, d->W, d->Cin, OH, OW, d->Cout, d->ksize, d->stride, d->prologue, d->keep_prob,
+                     d->dropout_seed, &S, (cudaStream_t)stream, rc)) {
+      if (rc) return rc;
+      return reduce_partials(workspace, dW, (long long)d->ksize * d->ksize * d->Cin * pro_mult(d->prologue) * d->Cout, S,
+                             (cudaStream_t)stream);
+    }
+    FN_REQUIRE(d->impl != FN_IMPL_TCGEN05, FN_E_UNSUPPORTED, "fn_conv_wgrad: no tcgen05 kernel for this shape");
+  }
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.x = (const __nv_bfloat16*)d->x;
@@ -381,13 +462,25 @@ int fn_conv_wgrad(const fn_conv_desc* d, const void* dY, float* dW, float* works
 
 int64_t fn_tconv_wgrad_workspace(const fn_tconv_desc* d) {
   if (!d) return 0;
-  return wgrad_workspace((long long)d->B * d->H * d->W, 9, d->Cin, d->Cout);
+  return max_ll(wgrad_workspace((long long)d->B * d->H * d->W, 9, d->Cin, d->Cout),
+                wgrad_tc_workspace(d->B, 2 * d->H, 2 * d->W, d->Cout, d->H, d->W, d->Cin, 3, 2, FN_PRO_NONE));
 }
 
-/* d describes the FORWARD transposed conv (x, dims); dY: bf16 [B,2H,2W,Cout]; dW: fp32 [9, Cin, Cout] */
+/* d describes the FORWARD transposed conv (x, dims); dY: bf16 [B,2H,2W,Cout]; dW: fp32 [9, Cout, Cin] = the variable's own
+ * layout [k,k,Cout,Cin] (flow_architecture.py:74).  The adjoint pairs in[i,j] with dY[2i+di, 2j+dj]: exactly the weight
+ * gradient of a stride-2 conv whose input is dY and whose output gradient is x, which is how the tensor-core path runs it. */
 int fn_tconv_wgrad(const fn_tconv_desc* d, const void* dY, float* dW, float* workspace, void* stream) {
   FN_REQUIRE(d && d->x && dY && dW && workspace, FN_E_INVAL, "fn_tconv_wgrad: null argument");
   FN_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, FN_E_INVAL, "fn_tconv_wgrad: bad dims");
+  if (d->impl != FN_IMPL_SIMT) {
+    int S = 0, rc = 0;
+    if (wgrad_tc_try(dY, d->x, workspace, d->B, 2 * d->H, 2 * d->W, d->Cout, d->H, d->W, d->Cin, 3, 2, FN_PRO_NONE, 1.0f, 0, &S,
+                     (cudaStream_t)stream, rc)) {
+      if (rc) return rc;
+      return reduce_partials(workspace, dW, 9ll * d->Cin * d->Cout, S, (cudaStream_t)stream);
+    }
+    FN_REQUIRE(d->impl != FN_IMPL_TCGEN05, FN_E_UNSUPPORTED, "fn_tconv_wgrad: no tcgen05 kernel for this shape");
+  }
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.x = (const __nv_bfloat16*)d->x;

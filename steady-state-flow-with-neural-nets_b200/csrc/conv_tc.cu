@@ -73,6 +73,7 @@ struct TcParams {
   int tapfirst;              // bitmask: tap is the first one written into its phase
   uint32_t centre;           // byte offset of the centre view (skip operand)
   int ksteps_tap, ksteps_skip, ksteps_total;
+  int half_k;
   int spc, nchunks, nstages;
   int a_main_bytes, a_skip_bytes;
   int tmem_cols;
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 6) k_conv_tc(const __grid_constant
     if (warp < p.NI) {
       const uint32_t leader = ptx::elect_one();
       const uint32_t idesc = ptx::idesc_bf16_f32(128, p.N);
-      const uint32_t a_lbo = (uint32_t)p.Ppad * 16u, a_sbo = (uint32_t)p.PU * 16u;
+      const uint32_t a_lbo = p.half_k ? 0u : (uint32_t)p.Ppad * 16u, a_sbo = (uint32_t)p.PU * 16u;
       const uint64_t a_tmpl = ptx::smem_desc(ptx::smem_u32(a_main), a_lbo, a_sbo);
       const uint64_t a_skip_tmpl = ptx::smem_desc(ptx::smem_u32(a_skip) + p.centre, a_lbo, a_sbo);
       const uint64_t b_tmpl = ptx::smem_desc(b_ring_u32, (uint32_t)p.N * 16u, 128u);
@@ -493,7 +494,10 @@ static bool plan_tc(const TcGeom& g, TcParams& p, size_t& smem_bytes, const char
   const int mult = pro_mult(g.pro);
   const int Keff = g.C * mult;
   const int Kskip = g.Cs * mult;
-  if ((g.C % 8) != 0 || (Keff % 16) != 0 || (Kskip % 16) != 0) { *why = "K per tap not a multiple of 16"; return false; }
+  // Keff = 8 (8-channel gradients in the backward pass): one k-step that reads the single plane for both K halves
+  // (LBO = 0) against weights whose second half is zero
+  const bool half_k = Keff == 8 && Kskip == 0;
+  if ((g.C % 8) != 0 || ((Keff % 16) != 0 && !half_k) || (Kskip % 16) != 0) { *why = "K per tap not a multiple of 16"; return false; }
   const int clog = ilog2_exact(g.C / 8);
   if (clog < 0 || (g.Cs && g.Cs != g.C)) { *why = "channel count not 8 * 2^n (or skip width differs)"; return false; }
   const int N = round_up(g.Cout, 16);
@@ -510,7 +514,8 @@ static bool plan_tc(const TcGeom& g, TcParams& p, size_t& smem_bytes, const char
   p.nsub = g.mode == MODE_S2 ? 4 : 1;
   p.chunk_log2 = clog;
   p.planes = Keff / 8;
-  p.ksteps_tap = Keff / 16;
+  p.ksteps_tap = (Keff + 15) / 16;
+  p.half_k = half_k ? 1 : 0;
   p.ksteps_skip = Kskip / 16;
   p.ksteps_total = p.ntaps * p.ksteps_tap + p.ksteps_skip;
   auto set_ring = [&](int chunk_budget, int max_stages) {
@@ -751,7 +756,8 @@ int tconv_fwd_tc(const fn_tconv_desc& d, cudaStream_t stream) {
 // ---- weight packing: src [T][Keff][Cout] (+ [Kskip][Cout]) bf16 -> dst [kstep][2][N][8] bf16
 __global__ void k_pack_tc(const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ ws,
                           __nv_bfloat16* __restrict__ dst, int T, int Keff, int Kskip, int Cout, int N) {
-  const int main_steps = T * (Keff / 16);
+  const int kst = (Keff + 15) / 16;      // Keff = 8: one k-step whose second half is zero (the kernel reads the plane twice)
+  const int main_steps = T * kst;
   const int total = (main_steps + Kskip / 16) * 2 * N * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int e = i & 7;
@@ -763,9 +769,9 @@ __global__ void k_pack_tc(const __nv_bfloat16* __restrict__ w, const __nv_bfloat
     __nv_bfloat16 v = __float2bfloat16(0.f);
     if (n < Cout) {
       if (ks < main_steps) {
-        const int tap = ks / (Keff / 16), kk = ks % (Keff / 16);
+        const int tap = ks / kst, kk = ks % kst;
         const int k = kk * 16 + h * 8 + e;
-        v = w[((size_t)tap * Keff + k) * Cout + n];
+        if (k < Keff) v = w[((size_t)tap * Keff + k) * Cout + n];
       } else {
         const int k = (ks - main_steps) * 16 + h * 8 + e;
         v = ws[(size_t)k * Cout + n];
@@ -777,16 +783,16 @@ __global__ void k_pack_tc(const __nv_bfloat16* __restrict__ w, const __nv_bfloat
 
 long long conv_weights_tc_bytes(int ksize, int Keff, int Kskip, int Cout, int gated) {
   (void)gated;
-  if ((Keff % 16) != 0 || (Kskip % 16) != 0 || Cout <= 0) return 0;
-  const long long steps = (long long)ksize * ksize * (Keff / 16) + Kskip / 16;
+  if (((Keff % 16) != 0 && Keff != 8) || (Kskip % 16) != 0 || Cout <= 0) return 0;
+  const long long steps = (long long)ksize * ksize * ((Keff + 15) / 16) + Kskip / 16;
   return steps * round_up(Cout, 16) * 32;
 }
 
 int pack_conv_weights_tc(const void* w, const void* w_skip, void* dst, int ksize, int Keff, int Kskip, int Cout,
                          int gated, cudaStream_t stream) {
   (void)gated;
-  FN_REQUIRE((Keff % 16) == 0 && (Kskip % 16) == 0, FN_E_ALIGN, "pack_conv_weights_tc: K (%d,%d) must be multiples of 16",
-             Keff, Kskip);
+  FN_REQUIRE(((Keff % 16) == 0 || Keff == 8) && (Kskip % 16) == 0, FN_E_ALIGN,
+             "pack_conv_weights_tc: K (%d,%d) must be multiples of 16 (or K = 8 without a skip operand)", Keff, Kskip);
   FN_REQUIRE(Kskip == 0 || w_skip != nullptr, FN_E_INVAL, "pack_conv_weights_tc: null w_skip");
   const int N = round_up(Cout, 16);
   const long long total = conv_weights_tc_bytes(ksize, Keff, Kskip, Cout, gated) / 2;

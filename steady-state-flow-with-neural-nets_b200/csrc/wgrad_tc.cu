@@ -1,0 +1,448 @@
+// Weight gradient of the 'SAME' convolutions on the tcgen05 tensor cores (what autodiff derives for
+// tf.nn.conv2d / conv2d_transpose / the nin matmul, reference flow_architecture.py:64,78,101 under
+// flow_net.train, model/flow_net.py:44-46):
+//
+//     dW[tap][k][n] = sum_pix  pro(x)[s*pix + tap - pad][k] * dY[pix][n]
+//
+// is, per tap, a GEMM whose CONTRACTION runs over pixels.  Both operands live in shared memory exactly
+// as the forward kernels keep them -- 8-channel planes `[chunk][pixel][8]`, 16 B per pixel -- which is
+// the canonical MN-major (transposed) no-swizzle UMMA layout: 8 consecutive pixels x 8 channels form
+// one 128-byte core matrix, the next 8 pixels follow at LBO = 128 B and the next channel chunk at
+// SBO = plane stride.  One MMA (M = 128 activation channels, N = Cout, K = 16) therefore consumes 16
+// consecutive pixels of one tile row, and a filter tap is once more only a start-address offset into
+// the haloed activation planes (stride 2: parity sub-planes, as in conv_s2t.cu).
+//
+// Persistent CTAs: CTA (g, s) owns one group g of taps / one 128-channel block of K and every S-th
+// pixel tile; its accumulators stay in TMEM for the whole kernel and are written once, as an fp32
+// partial `[s][tap][k][n]`; a second kernel adds the S partials in a fixed order (deterministic).
+// warps 0-3: prologue transform (stage -> planes), later the TMEM read-out; warp 4: TMA producer and
+// TMEM owner; warp 5: MMA issuer.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace fn {
+namespace wg {
+
+constexpr int TV = 8, TU = 16;                 // pixel tile of dY: 8 rows of 16 pixels = 8 K-steps
+constexpr int THREADS = 192;
+constexpr int WARP_PRODUCER = 4, WARP_ISSUER = 5;
+constexpr int HDR = 256;
+constexpr int DY_PLANE = TV * TU * 16;         // bytes of one 8-channel dY plane
+enum { MODE_S1 = 0, MODE_S2 = 1 };
+
+template <int MODE>
+struct Geo {
+  static constexpr bool S2 = MODE == MODE_S2;
+  static constexpr int SW_ = S2 ? 2 * TU + 1 : TU + 2, SH_ = S2 ? 2 * TV + 1 : TV + 2, SP = SW_ * SH_;   // stage tile (TMA box)
+  static constexpr int PU = S2 ? TU + 1 : TU + 2, PV = S2 ? TV + 1 : TV + 2, P = PU * PV;                // one (sub-)plane
+  static constexpr int PPAD = (P & 1) ? P : P + 1;                                                       // odd: planes spread over banks
+  static constexpr int NSUB = S2 ? 4 : 1;
+  static constexpr int ROW_BYTES = PU * 16;                                                              // one K-step down
+};
+
+struct Params {
+  CUtensorMap tm_x;     // 4-D (C, W, H, B)
+  CUtensorMap tm_dy;    // 5-D (8, N/8, OW, OH, B)
+  float* partial;       // [S][T][Keff][N]
+  int* status;
+  int B, H, W, C, OH, OW, N;
+  int CH, chshift;      // raw 8-channel chunks of x
+  int pro, Keff, T;
+  int mblocks;          // blocks of 8*kpl activation channels
+  int kpl;              // activation planes one CTA keeps (16, or 8 when a stride-2 tile would not fit)
+  int tap_groups, S;
+  int tiles_u, tiles_v, ntiles;
+  int Npad, nchunks;
+  uint32_t idesc;
+  int nbuf;
+  uint32_t off_a, a_bytes, off_dy, dy_bytes, off_stage, stage_bytes, sub_bytes;
+  uint32_t tmem_cols;
+  int ksize, swap;
+  float keep_prob;
+  unsigned long long seed;
+};
+
+enum { SB_X = 0, SB_PF = 2, SB_TF = 4, SB_FIN = 6 };
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// instruction descriptor: BF16 x BF16 -> FP32, A and B MN-major (bits 15 / 16)
+static uint32_t idesc_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int MODE, int NT>
+__global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Params p) {
+  using G = Geo<MODE>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const uint32_t sbase = ptx::smem_u32(smem);
+  auto bar = [&](int i) { return sbase + 8u * (uint32_t)i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 128);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int tid = threadIdx.x;
+
+  // CTA -> (pixel split s, tap group, K block)
+  const int s_idx = (int)blockIdx.x % p.S;
+  const int grp = (int)blockIdx.x / p.S;
+  const int mb = grp % p.mblocks;
+  const int kpl = p.kpl;
+  const int tap0 = (grp / p.mblocks) * NT;
+  const int n_local = s_idx < p.ntiles ? (p.ntiles - 1 - s_idx) / p.S + 1 : 0;
+  auto tile_coords = [&](int t, int& b, int& y0, int& x0) {
+    const int tu = t % p.tiles_u;
+    const int r = t / p.tiles_u;
+    const int tv = r % p.tiles_v;
+    b = r / p.tiles_v;
+    x0 = tu * TU;
+    y0 = tv * TV;
+  };
+  const bool two = p.nbuf == 2;
+  auto buf_of = [&](int it) { return two ? (it & 1) : 0; };
+  auto use_of = [&](int it) { return two ? (it >> 1) : it; };
+
+  if (warp == WARP_PRODUCER) {
+    ptx::tmem_alloc(sbase + 128, p.tmem_cols);
+    ptx::tmem_relinquish();
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        ptx::mbar_init(bar(SB_X + s), 1);
+        ptx::mbar_init(bar(SB_PF + s), 128);
+        ptx::mbar_init(bar(SB_TF + s), 1);
+      }
+      ptx::mbar_init(bar(SB_FIN), 1);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  bool ok = true;
+
+  if (warp == WARP_PRODUCER) {
+    // =========================== producer ===========================
+    if (lane == 0) {
+      for (int it = 0; it < n_local && ok; ++it) {
+        const int s = buf_of(it), k = use_of(it);
+        int b, y0, x0;
+        tile_coords(s_idx + it * p.S, b, y0, x0);
+        if (k >= 1) {
+          ok = ptx::mbar_wait(bar(SB_TF + s), (uint32_t)((k - 1) & 1));     // MMAs of the previous use have read planes / dY
+          if (!ok) { atomicCAS(p.status, 0, 61); break; }
+        }
+        ptx::mbar_arrive_expect_tx(bar(SB_X + s), (uint32_t)(G::SP * p.C * 2 + p.nchunks * DY_PLANE));
+        const uint32_t st = sbase + p.off_stage + (uint32_t)s * p.stage_bytes;
+        if (G::S2) tma_load_4d(st, &p.tm_x, bar(SB_X + s), 0, 2 * x0, 2 * y0, b);
+        else tma_load_4d(st, &p.tm_x, bar(SB_X + s), 0, x0 - 1, y0 - 1, b);
+        const uint32_t dy = sbase + p.off_dy + (uint32_t)s * p.dy_bytes;
+        for (int c = 0; c < p.nchunks; ++c) tma_load_5d(dy + (uint32_t)(c * DY_PLANE), &p.tm_dy, bar(SB_X + s), 0, c, x0, y0, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == WARP_ISSUER) {
+    // =========================== issuer ===========================
+    const uint32_t leader = ptx::elect_one();
+    // byte offsets of this CTA's taps inside the activation planes
+    uint32_t tapoff[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int tap = tap0 + t;
+      int di = tap / 3, dj = tap % 3;
+      if (p.ksize == 1) { di = 1; dj = 1; }
+      tapoff[t] = G::S2 ? (uint32_t)((di & 1) * 2 + (dj & 1)) * p.sub_bytes + (uint32_t)(((di >> 1) * G::PU + (dj >> 1)) * 16)
+                        : (uint32_t)((di * G::PU + dj) * 16);
+    }
+    const uint32_t lbo_a = p.swap ? (uint32_t)(G::PPAD * 16) : 128u, sbo_a = p.swap ? 128u : (uint32_t)(G::PPAD * 16);
+    const uint32_t lbo_b = p.swap ? (uint32_t)DY_PLANE : 128u, sbo_b = p.swap ? 128u : (uint32_t)DY_PLANE;
+    for (int it = 0; it < n_local; ++it) {
+      const int s = buf_of(it), k = use_of(it);
+      ok = ok && ptx::mbar_wait(bar(SB_X + s), (uint32_t)(k & 1));
+      ok = ok && ptx::mbar_wait(bar(SB_PF + s), (uint32_t)(k & 1));
+      if (!ok) atomicCAS(p.status, 0, 62);
+      ptx::tc_fence_after_sync();
+      const uint64_t a_tmpl = ptx::smem_desc(sbase + p.off_a + (uint32_t)s * p.a_bytes, lbo_a, sbo_a);
+      const uint64_t b_tmpl = ptx::smem_desc(sbase + p.off_dy + (uint32_t)s * p.dy_bytes, lbo_b, sbo_b);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const uint64_t a_tap = a_tmpl + (uint64_t)(tapoff[t] >> 4);
+        const uint32_t d_col = tmem_base + (uint32_t)(t * p.Npad);
+#pragma unroll
+        for (int v = 0; v < TV; ++v) {
+          if (leader)
+            ptx::mma_bf16_ss(d_col, a_tap + (uint32_t)((v * G::ROW_BYTES) >> 4), b_tmpl + (uint32_t)((v * TU * 16) >> 4), p.idesc,
+                             (it == 0 && v == 0) ? 0u : 1u);
+        }
+      }
+      if (leader) ptx::mma_commit(bar(SB_TF + s));
+      __syncwarp();
+    }
+    if (n_local > 0 && leader) ptx::mma_commit(bar(SB_FIN));
+    __syncwarp();
+  } else {
+    // =========================== front: stage -> planes, then read-out ===========================
+    const int items = G::SP * p.CH;
+    const int mult = pro_mult(p.pro);
+    for (int it = 0; it < n_local; ++it) {
+      const int s = buf_of(it), k = use_of(it);
+      int b, y0, x0;
+      tile_coords(s_idx + it * p.S, b, y0, x0);
+      ok = ok && ptx::mbar_wait(bar(SB_X + s), (uint32_t)(k & 1));
+      if (!ok) atomicCAS(p.status, 0, 63);
+      const uint32_t stage = sbase + p.off_stage + (uint32_t)s * p.stage_bytes;
+      const uint32_t planes = sbase + p.off_a + (uint32_t)s * p.a_bytes;
+      for (int idx = tid; idx < items; idx += 128) {
+        const int ch = idx & (p.CH - 1);
+        const int sp = idx >> p.chshift;
+        bf16x8 in, o0, o1;
+        in.v = lds128(stage + (uint32_t)idx * 16u);
+        const int r = sp / G::SW_, c = sp - r * G::SW_;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a0, a1;
+          pro_apply(p.pro, __bfloat162float(in.h[j]), a0, a1);
+          o0.h[j] = __float2bfloat16(a0);
+          o1.h[j] = __float2bfloat16(a1);
+        }
+        if (p.keep_prob < 1.0f) {     // tf.nn.dropout on the conv input (flow_architecture.py:144-145): same mask as the forward
+          const int iy = G::S2 ? 2 * y0 + r : y0 - 1 + r, ix = G::S2 ? 2 * x0 + c : x0 - 1 + c;
+          const unsigned long long pidx = ((unsigned long long)b * p.H + iy) * p.W + ix;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            o0.h[j] = __float2bfloat16(__bfloat162float(o0.h[j]) * dropout_scale(p.seed, pidx * p.Keff + ch * 8 + j, p.keep_prob));
+            if (mult == 2)
+              o1.h[j] = __float2bfloat16(__bfloat162float(o1.h[j]) * dropout_scale(p.seed, pidx * p.Keff + p.C + ch * 8 + j, p.keep_prob));
+          }
+        }
+        uint32_t dst = planes;
+        int pp = sp;
+        if (G::S2) {
+          dst += (uint32_t)((r & 1) * 2 + (c & 1)) * p.sub_bytes;
+          pp = (r >> 1) * G::PU + (c >> 1);
+        }
+        const int l0 = ch - kpl * mb, l1 = p.CH + ch - kpl * mb;
+        if (l0 >= 0 && l0 < kpl) sts128(dst + (uint32_t)(l0 * G::PPAD + pp) * 16u, o0.v);
+        if (mult == 2 && l1 >= 0 && l1 < kpl) sts128(dst + (uint32_t)(l1 * G::PPAD + pp) * 16u, o1.v);
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(bar(SB_PF + s));
+    }
+    // ---- read-out: TMEM lane = activation channel (row k), column = tap-local Cout index
+    if (n_local > 0) {
+      ok = ok && ptx::mbar_wait(bar(SB_FIN), 0);
+      if (!ok) atomicCAS(p.status, 0, 64);
+      ptx::tc_fence_after_sync();
+    }
+    const int row_local = warp * 32 + lane;
+    const int krow = mb * kpl * 8 + row_local;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int t = 0; t < NT; ++t) {
+      float* dst = p.partial + (((size_t)s_idx * p.T + tap0 + t) * p.Keff + krow) * p.N;
+      for (int n0 = 0; n0 < p.N; n0 += 8) {
+        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (n_local > 0) ptx::tmem_ld8(lane_base + (uint32_t)(t * p.Npad + n0), o);
+        if (row_local < kpl * 8 && krow < p.Keff && ok) {
+          *reinterpret_cast<float4*>(dst + n0) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(dst + n0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == WARP_PRODUCER) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+static int g_swap = 0;
+
+struct Plan {
+  int mode, NT, S, grid, smem;
+  Params p;
+};
+
+// x: bf16 [B,H,W,C] (prologue applied on the fly), dY: bf16 [B,OH,OW,N]; result partial [S][T][Keff][N]
+static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, int ksize, int stride, int pro) {
+  Params& p = pl.p;
+  memset(&p, 0, sizeof(p));
+  if (get_encode() == nullptr) return false;
+  if ((C & 7) || (N & 7) || C > 128 || N > 256 || (C & (C - 1))) return false;
+  if (ksize != 1 && ksize != 3) return false;
+  if (stride == 2 && (ksize != 3 || (H & 1) || (W & 1))) return false;
+  if (stride != 1 && stride != 2) return false;
+  pl.mode = stride == 2 ? MODE_S2 : MODE_S1;
+  p.B = B; p.H = H; p.W = W; p.C = C; p.OH = OH; p.OW = OW; p.N = N;
+  p.CH = C / 8;
+  p.chshift = 0;
+  while ((1 << p.chshift) < p.CH) ++p.chshift;
+  p.pro = pro;
+  p.Keff = C * pro_mult(pro);
+  p.T = ksize * ksize;
+  p.ksize = ksize;
+  p.Npad = (N + 15) / 16 * 16;
+  p.nchunks = N / 8;
+  p.idesc = idesc_mn(128, p.Npad);
+  pl.NT = p.T == 1 ? 1 : (9 * p.Npad <= 512 ? 9 : (3 * p.Npad <= 512 ? 3 : 1));
+  p.tap_groups = p.T / pl.NT;
+  int cols = pl.NT * p.Npad;
+  p.tmem_cols = 32;
+  while ((int)p.tmem_cols < cols) p.tmem_cols *= 2;
+  p.tiles_u = (OW + TU - 1) / TU;
+  p.tiles_v = (OH + TV - 1) / TV;
+  p.ntiles = B * p.tiles_u * p.tiles_v;
+  const int SP = pl.mode == MODE_S2 ? Geo<MODE_S2>::SP : Geo<MODE_S1>::SP;
+  const int PPAD = pl.mode == MODE_S2 ? Geo<MODE_S2>::PPAD : Geo<MODE_S1>::PPAD;
+  const int NSUB = pl.mode == MODE_S2 ? 4 : 1;
+  p.dy_bytes = (uint32_t)(p.nchunks * DY_PLANE);
+  p.stage_bytes = (uint32_t)((SP * C * 2 + 127) / 128 * 128);
+  // an M = 128 MMA always walks 16 plane strides from its start address and an N-padded one a plane past dY:
+  // keep those reads inside the allocation
+  const uint32_t overread = 16u * PPAD * 16u + 4096u;
+  const int tries[3][2] = {{16, 2}, {16, 1}, {8, 1}};      // (planes per CTA, buffers)
+  bool fits = false;
+  for (int i = 0; i < 3 && !fits; ++i) {
+    p.kpl = p.Keff / 8 < tries[i][0] ? p.Keff / 8 : tries[i][0];
+    p.nbuf = tries[i][1];
+    p.mblocks = (p.Keff / 8 + p.kpl - 1) / p.kpl;
+    p.sub_bytes = (uint32_t)(p.kpl * PPAD * 16);
+    p.a_bytes = (NSUB * p.sub_bytes + 127) / 128 * 128;
+    p.off_a = HDR;
+    p.off_dy = p.off_a + p.nbuf * p.a_bytes;
+    p.off_stage = p.off_dy + p.nbuf * p.dy_bytes + DY_PLANE;
+    uint32_t total = p.off_stage + p.nbuf * p.stage_bytes;
+    const uint32_t need = p.off_a + (p.nbuf - 1) * p.a_bytes + (NSUB - 1) * p.sub_bytes + overread;
+    if (total < need) total = need;
+    pl.smem = (int)total + 128;
+    fits = pl.smem <= 220 * 1024;
+  }
+  if (!fits) return false;
+  int per_sm = (227 * 1024) / (pl.smem + 1024);
+  const int tmem_lim = 512 / (int)p.tmem_cols;
+  if (per_sm > tmem_lim) per_sm = tmem_lim;
+  if (per_sm > 3) per_sm = 3;
+  const int groups = p.tap_groups * p.mblocks;
+  int S = (148 * per_sm) / groups;
+  if (S < 1) S = 1;
+  if (S > p.ntiles) S = p.ntiles;
+  p.S = S;
+  pl.S = S;
+  pl.grid = S * groups;
+  p.swap = g_swap;
+  return true;
+}
+
+template <int MODE, int NT>
+static int launch_k(const Plan& pl, cudaStream_t stream) {
+  auto kern = k_wgrad_tc<MODE, NT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad_tc): %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  kern<<<pl.grid, THREADS, pl.smem, stream>>>(pl.p);
+  count_launch();
+  return check_launch("k_wgrad_tc");
+}
+
+}  // namespace wg
+
+int* tc_status_word();
+
+long long wgrad_tc_workspace(int B, int H, int W, int C, int OH, int OW, int N, int ksize, int stride, int pro) {
+  wg::Plan pl;
+  if (!wg::plan(pl, B, H, W, C, OH, OW, N, ksize, stride, pro)) return 0;
+  return (long long)pl.S * pl.p.T * pl.p.Keff * N;
+}
+
+// returns false when this shape has no tensor-core kernel (the caller then runs the CUDA-core one);
+// on success *S_out partials of [T][Keff][N] floats are in `partial`
+bool wgrad_tc_try(const void* x, const void* dY, float* partial, int B, int H, int W, int C, int OH, int OW, int N, int ksize,
+                  int stride, int pro, float keep_prob, unsigned long long seed, int* S_out, cudaStream_t stream, int& rc) {
+  using namespace wg;
+  rc = 0;
+  Plan pl;
+  if (!plan(pl, B, H, W, C, OH, OW, N, ksize, stride, pro)) return false;
+  Params& p = pl.p;
+  PFN_encodeTiled enc = get_encode();
+  {
+    const int bw = pl.mode == MODE_S2 ? Geo<MODE_S2>::SW_ : Geo<MODE_S1>::SW_, bh = pl.mode == MODE_S2 ? Geo<MODE_S2>::SH_ : Geo<MODE_S1>::SH_;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)bw, (cuuint32_t)bh, 1u};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&p.tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  {
+    const cuuint64_t dims[5] = {8, (cuuint64_t)(N / 8), (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)B};
+    const cuuint64_t strides[4] = {16, (cuuint64_t)N * 2, (cuuint64_t)OW * N * 2, (cuuint64_t)OH * OW * N * 2};
+    const cuuint32_t box[5] = {8, 1, (cuuint32_t)TU, (cuuint32_t)TV, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (enc(&p.tm_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dY), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  p.partial = partial;
+  p.keep_prob = keep_prob;
+  p.seed = seed;
+  p.status = tc_status_word();
+  if (!p.status) { rc = (int)cudaErrorMemoryAllocation; return true; }
+  *S_out = pl.S;
+  if (pl.mode == MODE_S1) {
+    rc = pl.NT == 9 ? launch_k<MODE_S1, 9>(pl, stream) : pl.NT == 3 ? launch_k<MODE_S1, 3>(pl, stream) : launch_k<MODE_S1, 1>(pl, stream);
+  } else {
+    rc = pl.NT == 9 ? launch_k<MODE_S2, 9>(pl, stream) : pl.NT == 3 ? launch_k<MODE_S2, 3>(pl, stream) : launch_k<MODE_S2, 1>(pl, stream);
+  }
+  return true;
+}
+
+}  // namespace fn
+
+extern "C" {
+void fn_debug_set_wgrad_swap(int v) { fn::wg::g_swap = v; }
+}

@@ -78,6 +78,7 @@ DEBUG_SYMBOLS = [
     ("fn_debug_tc_status", C.c_int, []),
     ("fn_debug_set_timing", None, [C.c_void_p, C.c_int]),
     ("fn_debug_set_use_s1p", None, [C.c_int]),
+    ("fn_debug_set_wgrad_swap", None, [C.c_int]),
 ]
 
 
@@ -307,10 +308,11 @@ def bias_grad(dY, out):
     _check(lib.fn_bias_grad(_ptr(dY), _ptr(out), _ptr(ws), npix, N, stream_ptr()), "fn_bias_grad")
 
 
-def conv_wgrad(x, dY, out, *, ksize, stride, prologue, keep_prob=1.0, dropout_seed=0):
+def conv_wgrad(x, dY, out, *, ksize, stride, prologue, keep_prob=1.0, dropout_seed=0, impl=IMPL_AUTO):
     """out: fp32 [k*k, Keff, Cout] <- sum over pixels of pro(x) (x) dY"""
     _require_cuda(x, dY, out)
     d = ConvDesc()
+    d.impl = impl
     d.B, d.H, d.W, d.Cin = x.shape
     d.Cout = dY.shape[-1]
     d.ksize, d.stride, d.prologue = ksize, stride, prologue
@@ -321,10 +323,11 @@ def conv_wgrad(x, dY, out, *, ksize, stride, prologue, keep_prob=1.0, dropout_se
     _check(lib.fn_conv_wgrad(C.byref(d), _ptr(dY), _ptr(out), _ptr(ws), stream_ptr()), "fn_conv_wgrad")
 
 
-def tconv_wgrad(x, dY, out):
-    """out: fp32 [9, Cin, Cout]"""
+def tconv_wgrad(x, dY, out, *, impl=IMPL_AUTO):
+    """out: fp32 [9, Cout, Cin] -- the variable's own [k,k,Cout,Cin] layout"""
     _require_cuda(x, dY, out)
     d = TConvDesc()
+    d.impl = impl
     d.B, d.H, d.W, d.Cin = x.shape
     d.Cout = dY.shape[-1]
     d.x = x.data_ptr()

@@ -63,7 +63,7 @@ def _conv_plain(x, w16, cout, ksize, stride, device):
     B, H, W, cin = x.shape
     OH, OW = -(-H // stride), -(-W // stride)
     y = torch.empty((B, OH, OW, cout), dtype=torch.bfloat16, device=device)
-    w_tc = native.pack_conv_weights_tc(w16, None, ksize, cin, 0, cout, False) if cin % 16 == 0 else None
+    w_tc = native.pack_conv_weights_tc(w16, None, ksize, cin, 0, cout, False) if (cin % 16 == 0 or cin == 8) else None
     native.conv_fwd(x, w16, _zeros_bias(cout, device), y, B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize, stride=stride,
                     prologue=native.PRO_NONE, epilogue=native.EPI_BIAS, impl=arch.IMPL, w_tc=w_tc)
     return y
@@ -134,9 +134,7 @@ def backward(tape, sflow_p, sflow, flat: FlatParams):
             x, y, scope = rec["x"], rec["out"], rec["scope"]
             g = grads.get(y)
             cin, cout = x.shape[3], y.shape[3]
-            tmp = torch.empty((9, cin, cout), dtype=torch.float32, device=dev)
-            native.tconv_wgrad(x, g, tmp)
-            flat.grad_view(scope + '/weights').copy_(tmp.view(3, 3, cin, cout).permute(0, 1, 3, 2))
+            native.tconv_wgrad(x, g, flat.grad_view(scope + '/weights').view(9, cout, cin))
             native.bias_grad(g, flat.grad_view(scope + '/biases'))
             # d(x) = stride-2 'SAME' conv of d(y) with the same weights read as HWIO [k,k,Cout,Cin]
             w16 = V[scope + '/weights'].reshape(9, cout, cin).to(torch.bfloat16).contiguous()

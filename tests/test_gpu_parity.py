@@ -90,7 +90,7 @@ def run_fused_conv(native, impl, B, H, W, Cin, Cout, stride, pro, epi, with_skip
     ws16 = ws.to(dev, torch.bfloat16).contiguous() if ws is not None else None
     bd = b.to(dev, torch.float32)
     w_tc = None
-    if (Cin * mult) % 16 == 0:
+    if (Cin * mult) % 16 == 0 or (Cin * mult == 8 and not with_skip):
         w_tc = native.pack_conv_weights_tc(w16, ws16, ksize, Cin * mult, (skip.shape[3] * mult) if with_skip else 0,
                                            Cout, epi == 1)
     y = torch.empty((B, OH, OW, F_), device=dev, dtype=torch.float32 if epi == 3 else torch.bfloat16)
@@ -154,6 +154,10 @@ TC_CASES = [
     ("s2_odd_dims", 1, 31, 33, 8, 16, 2, 1, 0, False, None, False),
     ("s2_transposed_out8x16", 2, 16, 32, 32, 64, 2, 1, 0, False, None, False),
     ("s2_c64", 1, 32, 32, 64, 64, 2, 1, 0, False, None, False),
+    # 8-channel gradients of the backward pass: one k-step with a zero second half
+    ("raw_k8", 2, 32, 64, 8, 16, 1, 0, 0, False, None, False),
+    ("raw_k8_n8", 2, 20, 28, 8, 8, 1, 0, 0, False, None, False),
+    ("raw_k8_s2", 2, 32, 64, 8, 16, 2, 0, 0, False, None, False),
 ]
 
 
@@ -505,15 +509,82 @@ def test_conv_wgrad_vs_autograd(native, ksize, stride, pro, H, W, C, N):
     assert rel_l2(out, w.grad.reshape(ksize * ksize, C * mult, N)) < 1e-4
 
 
-def test_tconv_wgrad_vs_autograd(native):
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 5, 6, 16, 8), (3, 16, 32, 32, 16), (2, 8, 16, 128, 64), (5, 32, 64, 16, 8)])
+def test_tconv_wgrad_vs_autograd(native, impl, B, H, W, Cin, Cout):
     g = torch.Generator().manual_seed(2)
-    x = torch.randn(2, 5, 6, 16, generator=g, dtype=torch.float64).to(torch.bfloat16)
-    w = torch.randn(3, 3, 8, 16, generator=g, dtype=torch.float64).requires_grad_(True)     # TF [k,k,Cout,Cin]
-    dY = torch.randn(2, 10, 12, 8, generator=g, dtype=torch.float64).to(torch.bfloat16)
+    x = torch.randn(B, H, W, Cin, generator=g, dtype=torch.float64).to(torch.bfloat16)
+    w = torch.randn(3, 3, Cout, Cin, generator=g, dtype=torch.float64).requires_grad_(True)     # TF [k,k,Cout,Cin]
+    dY = torch.randn(B, 2 * H, 2 * W, Cout, generator=g, dtype=torch.float64).to(torch.bfloat16)
     (fo.conv2d_transpose_same(x.double(), w, 2) * dY.double()).sum().backward()
-    out = torch.empty(9, 16, 8, device="cuda")
-    native.tconv_wgrad(x.cuda(), dY.cuda(), out)
-    assert rel_l2(out.view(3, 3, 16, 8).permute(0, 1, 3, 2), w.grad) < 1e-4
+    out = torch.full((9, Cout, Cin), float("nan"), device="cuda")
+    native.tconv_wgrad(x.cuda(), dY.cuda(), out, impl=native.IMPL_TCGEN05 if impl == "tc" else native.IMPL_SIMT)
+    torch.cuda.synchronize()
+    assert native.tc_status() == 0
+    assert rel_l2(out.view(3, 3, Cout, Cin), w.grad) < 1e-4
+
+
+WGRAD_TC_CASES = [
+    # (B, H, W, C, N, ksize, stride, pro)
+    (2, 16, 32, 8, 16, 3, 1, 1), (3, 24, 40, 8, 8, 3, 1, 1), (2, 16, 32, 16, 32, 3, 1, 1), (2, 16, 32, 32, 64, 3, 1, 1),
+    (2, 16, 32, 64, 128, 3, 1, 1), (3, 8, 16, 128, 256, 3, 1, 1), (3, 8, 16, 128, 128, 3, 1, 1), (2, 13, 21, 16, 16, 3, 1, 1),
+    (2, 32, 64, 8, 16, 3, 2, 1), (2, 16, 32, 64, 128, 3, 2, 1), (1, 18, 36, 16, 32, 3, 2, 1),
+    (2, 16, 32, 64, 64, 1, 1, 1), (2, 16, 32, 8, 8, 1, 1, 1),
+    (2, 16, 32, 8, 8, 3, 1, 0), (2, 16, 32, 32, 16, 3, 1, 2), (2, 16, 32, 16, 16, 3, 1, 3), (2, 16, 32, 16, 16, 3, 1, 4),
+    (40, 32, 64, 8, 16, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("B,H,W,C,N,ksize,stride,pro", WGRAD_TC_CASES)
+def test_conv_wgrad_tcgen05_vs_autograd(native, B, H, W, C, N, ksize, stride, pro):
+    """wgrad_tc.cu (pixels are the contraction dimension, MN-major operands) against torch autograd in fp64
+    on the bf16-rounded operands, and against the CUDA-core kernel."""
+    g = torch.Generator().manual_seed(11)
+    x = bf16_round(torch.randn(B, H, W, C, generator=g, dtype=torch.float64))
+    OH, OW = -(-H // stride), -(-W // stride)
+    dY = bf16_round(torch.randn(B, OH, OW, N, generator=g, dtype=torch.float64))
+    mult = 2 if pro in (1, 3) else 1
+    w = torch.zeros(ksize, ksize, C * mult, N, dtype=torch.float64, requires_grad=True)
+    a = bf16_round(PRO_FN[pro](x)) if pro else x
+    (fo.conv2d_same(a, w, stride) * dY).sum().backward()
+    outs = []
+    for impl in (native.IMPL_TCGEN05, native.IMPL_SIMT):
+        out = torch.full((ksize * ksize, C * mult, N), float("nan"), device="cuda")
+        native.conv_wgrad(x.to("cuda", torch.bfloat16), dY.to("cuda", torch.bfloat16), out, ksize=ksize, stride=stride,
+                          prologue=pro, impl=impl)
+        torch.cuda.synchronize()
+        assert native.tc_status() == 0
+        outs.append(out)
+    ref = w.grad.reshape(ksize * ksize, C * mult, N)
+    assert rel_l2(outs[0], ref) < 1e-4
+    assert rel_l2(outs[0], outs[1]) < 1e-4
+
+
+def test_first_conv_wgrad_kernel_vs_cuda_core(native):
+    """Cin = 1 (the boundary conv): dedicated reduction kernel vs the generic CUDA-core one."""
+    g = torch.Generator().manual_seed(13)
+    x = (torch.rand(5, 32, 64, 1, generator=g) > 0.7).to("cuda", torch.bfloat16)
+    dY = torch.randn(5, 32, 64, 8, generator=g).to("cuda", torch.bfloat16)
+    outs = []
+    for impl in (native.IMPL_AUTO, native.IMPL_SIMT):
+        out = torch.full((9, 1, 8), float("nan"), device="cuda")
+        native.conv_wgrad(x, dY, out, ksize=3, stride=1, prologue=0, impl=impl)
+        outs.append(out)
+    assert rel_l2(outs[0], outs[1]) < 1e-5
+
+
+def test_conv_wgrad_tcgen05_dropout_mask_matches_cuda_core_kernel(native):
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 16, 32, 16, generator=g).to("cuda", torch.bfloat16)
+    dY = torch.randn(2, 16, 32, 32, generator=g).to("cuda", torch.bfloat16)
+    outs = []
+    for impl in (native.IMPL_TCGEN05, native.IMPL_SIMT):
+        out = torch.empty(9, 32, 32, device="cuda")
+        native.conv_wgrad(x, dY, out, ksize=3, stride=1, prologue=1, keep_prob=0.7, dropout_seed=5, impl=impl)
+        outs.append(out)
+    # same keep mask; the tensor-core operand is rounded to bf16 AFTER the 1/keep_prob scaling (2^-9 per element),
+    # a wrong mask would differ by O(1)
+    assert rel_l2(outs[0], outs[1]) < 5e-3
 
 
 def test_training_step_vs_oracle(native, golden_dir):
