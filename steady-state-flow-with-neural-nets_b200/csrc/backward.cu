@@ -14,7 +14,7 @@ namespace fn {
 constexpr int BW_THREADS = 256;
 static inline int bw_grid(long long items) {
   long long g = (items + BW_THREADS - 1) / BW_THREADS;
-  const long long cap = 148LL * 8;
+  const long long cap = 148LL * 16;
   return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 
@@ -87,6 +87,135 @@ __global__ void k_shortcut_bwd(const __nv_bfloat16* __restrict__ g, __nv_bfloat1
     }
     if (accumulate) d += __bfloat162float(dx[i]);
     dx[i] = __float2bfloat16(d);
+  }
+}
+
+
+// ---- 8-channel (16-byte) variants of the three element-wise adjoints above, used whenever the channel counts allow
+__device__ __forceinline__ void ld8(bf16x8& r, const __nv_bfloat16* p) { r.v = *reinterpret_cast<const uint4*>(p); }
+__global__ void __launch_bounds__(BW_THREADS) k_gate_bwd_v8(const __nv_bfloat16* __restrict__ c2, const __nv_bfloat16* __restrict__ g,
+                                                            __nv_bfloat16* __restrict__ dc2, long long npix, int F) {
+  const int fc = F >> 3;
+  const long long total = npix * fc;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / fc;
+    const int c = (int)(i - p * fc) * 8;
+    bf16x8 u, v, gg, du, dv;
+    ld8(u, c2 + p * 2 * F + c);
+    ld8(v, c2 + p * 2 * F + F + c);
+    ld8(gg, g + p * F + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sg = 1.f / (1.f + __expf(-__bfloat162float(v.h[j])));
+      const float gs = __bfloat162float(gg.h[j]) * sg;
+      du.h[j] = __float2bfloat16(gs);
+      dv.h[j] = __float2bfloat16(gs * __bfloat162float(u.h[j]) * (1.f - sg));
+    }
+    *reinterpret_cast<uint4*>(dc2 + p * 2 * F + c) = du.v;
+    *reinterpret_cast<uint4*>(dc2 + p * 2 * F + F + c) = dv.v;
+  }
+}
+
+__global__ void __launch_bounds__(BW_THREADS) k_prologue_bwd_v8(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ x,
+                                                                __nv_bfloat16* __restrict__ dx, long long npix, int C, int kind,
+                                                                int accumulate, float keep_prob, unsigned long long seed) {
+  const int mult = pro_mult(kind);
+  const int cc = C >> 3;
+  const long long total = npix * cc;
+  const bool drop = keep_prob < 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / cc;
+    const int c = (int)(i - p * cc) * 8;
+    bf16x8 xv, a0, a1, old, o;
+    ld8(xv, x + p * C + c);
+    ld8(a0, dA + p * mult * C + c);
+    if (mult == 2) ld8(a1, dA + p * mult * C + C + c);
+    if (accumulate) ld8(old, dx + p * C + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xf = __bfloat162float(xv.h[j]);
+      float f0 = __bfloat162float(a0.h[j]);
+      float f1 = mult == 2 ? __bfloat162float(a1.h[j]) : 0.f;
+      if (drop) {
+        f0 *= dropout_scale(seed, (unsigned long long)(p * mult * C + c + j), keep_prob);
+        if (mult == 2) f1 *= dropout_scale(seed, (unsigned long long)(p * mult * C + C + c + j), keep_prob);
+      }
+      float d;
+      switch (kind) {
+        case FN_PRO_CONCAT_ELU: {   // elu'(x) = x>0 ? 1 : e^x and elu'(-x) = x<0 ? 1 : e^-x share one exponential
+          const float e = __expf(-fabsf(xf));
+          d = xf > 0.f ? f0 - f1 * e : f0 * e - f1;
+          break;
+        }
+        case FN_PRO_ELU:         d = f0 * elu_grad(xf); break;
+        case FN_PRO_CONCAT_RELU: d = (xf > 0.f ? f0 : 0.f) - (xf < 0.f ? f1 : 0.f); break;
+        case FN_PRO_RELU:        d = xf > 0.f ? f0 : 0.f; break;
+        default:                 d = f0; break;
+      }
+      if (accumulate) d += __bfloat162float(old.h[j]);
+      o.h[j] = __float2bfloat16(d);
+    }
+    *reinterpret_cast<uint4*>(dx + p * C + c) = o.v;
+  }
+}
+
+__global__ void __launch_bounds__(BW_THREADS) k_shortcut_bwd_v8(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dx, int B,
+                                                                int OH, int OW, int F, int H, int W, int Cin, int pooled,
+                                                                int accumulate) {
+  const int cc = Cin >> 3;
+  const long long total = (long long)B * H * W * cc;
+  const int shift = F - Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / cc;
+    const int c = (int)(i - r * cc) * 8;
+    const long long pix = r;
+    const int xw = (int)(r % W);
+    r /= W;
+    const int yh = (int)(r % H);
+    const int b = (int)(r / H);
+    float scale = 1.f;
+    int oy = yh, ox = xw;
+    if (pooled) {
+      oy = yh >> 1; ox = xw >> 1;
+      scale = 1.f / (float)((min(2 * oy + 2, H) - 2 * oy) * (min(2 * ox + 2, W) - 2 * ox));   // TF 'SAME' edge windows
+    }
+    bf16x8 gv, old, o;
+    ld8(gv, g + (((long long)b * OH + oy) * OW + ox) * F + shift + c);
+    if (accumulate) ld8(old, dx + pix * Cin + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float d = __bfloat162float(gv.h[j]) * scale;
+      if (accumulate) d += __bfloat162float(old.h[j]);
+      o.h[j] = __float2bfloat16(d);
+    }
+    *reinterpret_cast<uint4*>(dx + pix * Cin + c) = o.v;
+  }
+}
+
+// bias gradient, 8 channels per thread: blockDim = (N/8) x rows
+__global__ void __launch_bounds__(BW_THREADS) k_bias_grad_v8(const __nv_bfloat16* __restrict__ dY, float* __restrict__ partial,
+                                                             long long npix, int N) {
+  __shared__ float sm[BW_THREADS][9];
+  const int nc = N >> 3;
+  const int per = BW_THREADS / nc;
+  const int c = threadIdx.x % nc, rg = threadIdx.x / nc;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rg < per) {
+    for (long long pp = (long long)blockIdx.x * per + rg; pp < npix; pp += (long long)gridDim.x * per) {
+      bf16x8 v;
+      ld8(v, dY + pp * N + c * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += __bfloat162float(v.h[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[threadIdx.x][j] = s[j];
+  __syncthreads();
+  if (threadIdx.x < N) {
+    const int cc = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float a = 0.f;
+    for (int r = 0; r < per; ++r) a += sm[r * nc + cc][j];
+    partial[(long long)blockIdx.x * N + threadIdx.x] = a;
   }
 }
 
@@ -297,7 +426,11 @@ static int reduce_partials(const float* partial, float* out, long long n, int S,
 
 int gate_bwd(const void* c2, const void* g, void* dc2, long long npix, int F, cudaStream_t s) {
   if (npix == 0) return 0;
-  k_gate_bwd<<<bw_grid(npix * F), BW_THREADS, 0, s>>>((const __nv_bfloat16*)c2, (const __nv_bfloat16*)g, (__nv_bfloat16*)dc2, npix, F);
+  if ((F & 7) == 0)
+    k_gate_bwd_v8<<<bw_grid(npix * (F / 8)), BW_THREADS, 0, s>>>((const __nv_bfloat16*)c2, (const __nv_bfloat16*)g, (__nv_bfloat16*)dc2,
+                                                                   npix, F);
+  else
+    k_gate_bwd<<<bw_grid(npix * F), BW_THREADS, 0, s>>>((const __nv_bfloat16*)c2, (const __nv_bfloat16*)g, (__nv_bfloat16*)dc2, npix, F);
   count_launch();
   return check_launch("k_gate_bwd");
 }
@@ -305,8 +438,12 @@ int gate_bwd(const void* c2, const void* g, void* dc2, long long npix, int F, cu
 int prologue_bwd(const void* dA, const void* x, void* dx, long long npix, int C, int kind, int accumulate, float keep_prob,
                  unsigned long long seed, cudaStream_t s) {
   if (npix == 0) return 0;
-  k_prologue_bwd<<<bw_grid(npix * C), BW_THREADS, 0, s>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx,
-                                                          npix, C, kind, accumulate, keep_prob, seed);
+  if ((C & 7) == 0)
+    k_prologue_bwd_v8<<<bw_grid(npix * (C / 8)), BW_THREADS, 0, s>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)x,
+                                                                       (__nv_bfloat16*)dx, npix, C, kind, accumulate, keep_prob, seed);
+  else
+    k_prologue_bwd<<<bw_grid(npix * C), BW_THREADS, 0, s>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx,
+                                                            npix, C, kind, accumulate, keep_prob, seed);
   count_launch();
   return check_launch("k_prologue_bwd");
 }
@@ -315,8 +452,12 @@ int shortcut_bwd(const void* g, void* dx, int B, int OH, int OW, int F, int H, i
                  cudaStream_t s) {
   const long long total = (long long)B * H * W * Cin;
   if (total == 0) return 0;
-  k_shortcut_bwd<<<bw_grid(total), BW_THREADS, 0, s>>>((const __nv_bfloat16*)g, (__nv_bfloat16*)dx, B, OH, OW, F, H, W, Cin,
-                                                       pooled, accumulate);
+  if ((Cin & 7) == 0 && (F & 7) == 0)
+    k_shortcut_bwd_v8<<<bw_grid(total / 8), BW_THREADS, 0, s>>>((const __nv_bfloat16*)g, (__nv_bfloat16*)dx, B, OH, OW, F, H, W, Cin,
+                                                                  pooled, accumulate);
+  else
+    k_shortcut_bwd<<<bw_grid(total), BW_THREADS, 0, s>>>((const __nv_bfloat16*)g, (__nv_bfloat16*)dx, B, OH, OW, F, H, W, Cin,
+                                                         pooled, accumulate);
   count_launch();
   return check_launch("k_shortcut_bwd");
 }
@@ -335,7 +476,8 @@ long long bias_grad_workspace(long long npix, int N) {
 int bias_grad(const void* dY, float* db, float* workspace, long long npix, int N, cudaStream_t s) {
   FN_REQUIRE(N >= 1 && N <= BW_THREADS, FN_E_UNSUPPORTED, "bias_grad: N=%d out of range", N);
   const int S = 148 * 2;
-  k_bias_grad<<<S, BW_THREADS, 0, s>>>((const __nv_bfloat16*)dY, workspace, npix, N);
+  if ((N & 7) == 0) k_bias_grad_v8<<<S, BW_THREADS, 0, s>>>((const __nv_bfloat16*)dY, workspace, npix, N);
+  else k_bias_grad<<<S, BW_THREADS, 0, s>>>((const __nv_bfloat16*)dY, workspace, npix, N);
   count_launch();
   int rc = check_launch("k_bias_grad");
   if (rc) return rc;

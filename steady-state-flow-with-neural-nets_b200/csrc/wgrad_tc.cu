@@ -28,7 +28,8 @@ namespace wg {
 constexpr int TV = 8, TU = 16;                 // pixel tile of dY: 8 rows of 16 pixels = 8 K-steps
 constexpr int THREADS = 192;
 constexpr int WARP_PRODUCER = 4, WARP_ISSUER = 5;
-constexpr int HDR = 256;
+constexpr int HDR = 512;
+constexpr int MAXBUF = 8;
 constexpr int DY_PLANE = TV * TU * 16;         // bytes of one 8-channel dY plane
 enum { MODE_S1 = 0, MODE_S2 = 1 };
 
@@ -59,12 +60,12 @@ struct Params {
   int nbuf;
   uint32_t off_a, a_bytes, off_dy, dy_bytes, off_stage, stage_bytes, sub_bytes;
   uint32_t tmem_cols;
-  int ksize, swap;
+  int ksize, swap, m64;
   float keep_prob;
   unsigned long long seed;
 };
 
-enum { SB_X = 0, SB_PF = 2, SB_TF = 4, SB_FIN = 6 };
+enum { SB_X = 0, SB_PF = MAXBUF, SB_TF = 2 * MAXBUF, SB_FIN = 3 * MAXBUF };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const uint32_t sbase = ptx::smem_u32(smem);
   auto bar = [&](int i) { return sbase + 8u * (uint32_t)i; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 128);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 256);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -117,15 +118,15 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
     x0 = tu * TU;
     y0 = tv * TV;
   };
-  const bool two = p.nbuf == 2;
-  auto buf_of = [&](int it) { return two ? (it & 1) : 0; };
-  auto use_of = [&](int it) { return two ? (it >> 1) : it; };
+  const int nbuf = p.nbuf;
+  auto buf_of = [&](int it) { return it % nbuf; };
+  auto use_of = [&](int it) { return it / nbuf; };
 
   if (warp == WARP_PRODUCER) {
-    ptx::tmem_alloc(sbase + 128, p.tmem_cols);
+    ptx::tmem_alloc(sbase + 256, p.tmem_cols);
     ptx::tmem_relinquish();
     if (lane == 0) {
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < MAXBUF; ++s) {
         ptx::mbar_init(bar(SB_X + s), 1);
         ptx::mbar_init(bar(SB_PF + s), 128);
         ptx::mbar_init(bar(SB_TF + s), 1);
@@ -152,12 +153,16 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
           ok = ptx::mbar_wait(bar(SB_TF + s), (uint32_t)((k - 1) & 1));     // MMAs of the previous use have read planes / dY
           if (!ok) { atomicCAS(p.status, 0, 61); break; }
         }
-        ptx::mbar_arrive_expect_tx(bar(SB_X + s), (uint32_t)(G::SP * p.C * 2 + p.nchunks * DY_PLANE));
+        const bool skip_x = p.swap & 8, skip_dy = p.swap & 4;     // timing experiments only (results are then garbage)
+        ptx::mbar_arrive_expect_tx(bar(SB_X + s), (uint32_t)((skip_x ? 0 : G::SP * p.C * 2) + (skip_dy ? 0 : p.nchunks * DY_PLANE)));
         const uint32_t st = sbase + p.off_stage + (uint32_t)s * p.stage_bytes;
-        if (G::S2) tma_load_4d(st, &p.tm_x, bar(SB_X + s), 0, 2 * x0, 2 * y0, b);
-        else tma_load_4d(st, &p.tm_x, bar(SB_X + s), 0, x0 - 1, y0 - 1, b);
+        if (!skip_x) {
+          if (G::S2) tma_load_4d(st, &p.tm_x, bar(SB_X + s), 0, 2 * x0, 2 * y0, b);
+          else tma_load_4d(st, &p.tm_x, bar(SB_X + s), 0, x0 - 1, y0 - 1, b);
+        }
         const uint32_t dy = sbase + p.off_dy + (uint32_t)s * p.dy_bytes;
-        for (int c = 0; c < p.nchunks; ++c) tma_load_5d(dy + (uint32_t)(c * DY_PLANE), &p.tm_dy, bar(SB_X + s), 0, c, x0, y0, b);
+        if (!skip_dy)
+          for (int c = 0; c < p.nchunks; ++c) tma_load_5d(dy + (uint32_t)(c * DY_PLANE), &p.tm_dy, bar(SB_X + s), 0, c, x0, y0, b);
       }
     }
     __syncwarp();
@@ -174,8 +179,10 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
       tapoff[t] = G::S2 ? (uint32_t)((di & 1) * 2 + (dj & 1)) * p.sub_bytes + (uint32_t)(((di >> 1) * G::PU + (dj >> 1)) * 16)
                         : (uint32_t)((di * G::PU + dj) * 16);
     }
-    const uint32_t lbo_a = p.swap ? (uint32_t)(G::PPAD * 16) : 128u, sbo_a = p.swap ? 128u : (uint32_t)(G::PPAD * 16);
-    const uint32_t lbo_b = p.swap ? (uint32_t)DY_PLANE : 128u, sbo_b = p.swap ? 128u : (uint32_t)DY_PLANE;
+    const bool swp = p.swap & 1;
+    const uint32_t lbo_a = swp ? (uint32_t)(G::PPAD * 16) : 128u, sbo_a = swp ? 128u : (uint32_t)(G::PPAD * 16);
+    const uint32_t lbo_b = swp ? (uint32_t)DY_PLANE : 128u, sbo_b = swp ? 128u : (uint32_t)DY_PLANE;
+    const uint32_t do_mma = (p.swap & 2) ? 0u : leader;
     for (int it = 0; it < n_local; ++it) {
       const int s = buf_of(it), k = use_of(it);
       ok = ok && ptx::mbar_wait(bar(SB_X + s), (uint32_t)(k & 1));
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
         const uint32_t d_col = tmem_base + (uint32_t)(t * p.Npad);
 #pragma unroll
         for (int v = 0; v < TV; ++v) {
-          if (leader)
+          if (do_mma)
             ptx::mma_bf16_ss(d_col, a_tap + (uint32_t)((v * G::ROW_BYTES) >> 4), b_tmpl + (uint32_t)((v * TU * 16) >> 4), p.idesc,
                              (it == 0 && v == 0) ? 0u : 1u);
         }
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
       if (!ok) atomicCAS(p.status, 0, 63);
       const uint32_t stage = sbase + p.off_stage + (uint32_t)s * p.stage_bytes;
       const uint32_t planes = sbase + p.off_a + (uint32_t)s * p.a_bytes;
-      for (int idx = tid; idx < items; idx += 128) {
+      for (int idx = tid; idx < ((p.swap & 16) ? 0 : items); idx += 128) {
         const int ch = idx & (p.CH - 1);
         const int sp = idx >> p.chshift;
         bf16x8 in, o0, o1;
@@ -254,7 +261,9 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
       if (!ok) atomicCAS(p.status, 0, 64);
       ptx::tc_fence_after_sync();
     }
-    const int row_local = warp * 32 + lane;
+    // M = 128: accumulator row r lives in TMEM lane r; M = 64 (kpl <= 8): row r in lane 32*(r/16) + r%16 (measured,
+    // tools/m64_layout.py)
+    const int row_local = p.m64 ? (lane < 16 ? warp * 16 + lane : 1 << 20) : warp * 32 + lane;
     const int krow = mb * kpl * 8 + row_local;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
@@ -341,9 +350,10 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
   // an M = 128 MMA always walks 16 plane strides from its start address and an N-padded one a plane past dY:
   // keep those reads inside the allocation
   const uint32_t overread = 16u * PPAD * 16u + 4096u;
-  const int tries[3][2] = {{16, 2}, {16, 1}, {8, 1}};      // (planes per CTA, buffers)
+  // (planes per CTA, buffers, shared-memory budget): deep pipelines while two CTAs still share an SM, then whatever fits
+  const int tries[8][3] = {{16, 6, 110}, {16, 4, 110}, {16, 3, 110}, {16, 2, 110}, {16, 3, 220}, {16, 2, 220}, {16, 1, 220}, {8, 1, 220}};
   bool fits = false;
-  for (int i = 0; i < 3 && !fits; ++i) {
+  for (int i = 0; i < 8 && !fits; ++i) {
     p.kpl = p.Keff / 8 < tries[i][0] ? p.Keff / 8 : tries[i][0];
     p.nbuf = tries[i][1];
     p.mblocks = (p.Keff / 8 + p.kpl - 1) / p.kpl;
@@ -356,7 +366,7 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
     const uint32_t need = p.off_a + (p.nbuf - 1) * p.a_bytes + (NSUB - 1) * p.sub_bytes + overread;
     if (total < need) total = need;
     pl.smem = (int)total + 128;
-    fits = pl.smem <= 220 * 1024;
+    fits = pl.smem <= tries[i][2] * 1024;
   }
   if (!fits) return false;
   int per_sm = (227 * 1024) / (pl.smem + 1024);
@@ -371,6 +381,10 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
   pl.S = S;
   pl.grid = S * groups;
   p.swap = g_swap;
+  // the A operand is read from shared memory at 128 rows x 32 B per MMA whatever the real channel count: half of that
+  // (M = 64, N % 8 == 0) when the CTA's channel block is at most 64 wide.  Flag 32 forces M = 128 (experiments).
+  p.m64 = (p.kpl <= 8 && !(g_swap & 32)) ? 1 : 0;
+  p.idesc = idesc_mn(p.m64 ? 64 : 128, p.Npad);
   return true;
 }
 

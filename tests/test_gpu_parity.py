@@ -624,7 +624,11 @@ def test_training_step_vs_oracle(native, golden_dir):
             got = arch.global_variables()[name].cpu().double()
             step_ref = pd[name] - vt.vars[name].detach()
             step_got = got - vt.vars[name].detach()
-            assert rel_l2(step_got, step_ref) < 0.15           # sign-like first Adam step; tiny gradients may flip
+            # first Adam step = -lr * sign(g): compare where the gradient is clearly non-zero (tiny ones may flip sign)
+            gref = vt.vars[name].grad
+            clear = gref.abs() > 0.2 * gref.pow(2).mean().sqrt()
+            assert rel_l2(step_got[clear], step_ref[clear]) < 0.05
+            assert rel_l2(step_got, step_ref) < 0.3
     finally:
         flow_net.end_training()
         flow_net.reset_training_state()
