@@ -77,6 +77,11 @@ class _VariableStore:
         self.vars = OrderedDict()
         self.version = 0
         self._derived = {}
+        self._preload = {}
+
+    def preload(self, values):
+        """Initial values (name -> numpy fp32) for variables the lazy graph has not created yet (checkpoint restore)."""
+        self._preload.update(values)
 
     def get(self, name, shape, device):
         v = self.vars.get(name)
@@ -85,7 +90,12 @@ class _VariableStore:
                 raise ValueError(f"variable {name} has shape {list(v.shape)}, requested {list(shape)}")
             return v
         lim = xavier_limit(shape)
-        arr = self.rng.uniform(-lim, lim, size=shape).astype(np.float32)
+        arr = self.rng.uniform(-lim, lim, size=shape).astype(np.float32)     # always drawn: keeps later draws in step
+        pre = self._preload.pop(name, None)
+        if pre is not None:
+            if list(pre.shape) != list(shape):
+                raise ValueError(f"checkpoint value for {name} has shape {list(pre.shape)}, graph wants {list(shape)}")
+            arr = np.ascontiguousarray(pre, dtype=np.float32)
         v = torch.from_numpy(arr).to(device)
         self.vars[name] = v
         return v

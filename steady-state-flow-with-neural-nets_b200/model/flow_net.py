@@ -183,6 +183,14 @@ def train(total_loss, lr):
     return loss
 
 
+def ensure_training_state():
+    """Create the flat parameter / gradient / Adam buffers now (needs one forward: variables are created lazily)."""
+    import model.flow_backward as fb
+    if _TRAIN["flat"] is None:
+        _TRAIN["flat"] = fb.FlatParams()
+    return _TRAIN["flat"]
+
+
 def training_state():
     """The flat parameter / gradient / Adam buffers (None before the first train() call)."""
     return _TRAIN["flat"]

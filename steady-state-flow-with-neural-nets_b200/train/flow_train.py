@@ -1,7 +1,8 @@
 """Training loop with the reference's flags and shape (/root/reference/train/flow_train.py:15-24, 30-97):
 make inputs, unwrap the network, l2 loss, Adam step; print the loss every 100 steps; NaN check.
 The TFRecord queue is replaced by the synthetic generator (no dataset ships, no network) and the TF
-Saver by a name-keyed torch.save of the variables every 1000 steps (same variable names / layouts).
+Saver by utils/checkpoint.py: an .npz keyed by the TF variable names (+ Adam slots) every 1000 steps and a
+restore-on-start with the reference's fall-back to random init.
 Data-parallel: launch with torchrun, one process per GPU; each rank trains on its own shard of the
 batch and the flat fp32 gradient is summed with one NCCL all-reduce per step.
 
@@ -19,6 +20,8 @@ sys.path.append(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 import model.flow_architecture as flow_architecture  # noqa: E402
 import model.flow_net as flow_net  # noqa: E402
 from model import flags  # noqa: E402
+from utils import checkpoint  # noqa: E402
+from utils.experiment_manager import make_checkpoint_path  # noqa: E402
 
 FLAGS = flags.FLAGS
 flags.DEFINE_string('base_dir', '../checkpoints', """dir to store trained net """)
@@ -26,14 +29,6 @@ flags.DEFINE_integer('batch_size', 8, """ training batch size """)
 flags.DEFINE_integer('max_steps', 500000, """ max number of steps to train """)
 flags.DEFINE_float('keep_prob', 0.7, """ keep probability for dropout """)
 flags.DEFINE_float('learning_rate', 1e-4, """ keep probability for dropout """)
-
-
-def make_checkpoint_path(base_path):
-    """utils/experiment_manager.py:8-16: one directory level per flag value (except base_dir & co)."""
-    for k, v in FLAGS.flag_values_dict().items():
-        if k not in ('base_dir', 'display_test', 'test_set'):
-            base_path = base_path + '/' + k + '_' + str(v)
-    return base_path
 
 
 def train():
@@ -44,17 +39,35 @@ def train():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl")
-    train_dir = make_checkpoint_path(FLAGS.base_dir)
+    train_dir = make_checkpoint_path(FLAGS.base_dir, FLAGS)
     if rank == 0:
         print(train_dir)
     per_rank = max(1, FLAGS.batch_size // world)
     flow_architecture.reset_variables(1234)       # every rank starts from the same variables
+    # init from checkpoint (reference :61-72): every rank reads the same file; a checkpoint that does not fit the
+    # graph is discarded and training starts from the random init
+    start_step = 0
+    ckpt = checkpoint.get_checkpoint_state(train_dir)
+    restored = None
+    if ckpt is not None:
+        if rank == 0:
+            print("init from " + train_dir)
+        restored = checkpoint.load(ckpt)
+        try:
+            start_step = checkpoint.restore(restored, flow_architecture.VARIABLES) + 1
+        except ValueError:
+            restored = None
+            flow_architecture.reset_variables(1234)
+            print("there was a problem using variables in checkpoint, random init will be used instead")
     flow_net.begin_training()
-    for step in range(FLAGS.max_steps):
+    for step in range(start_step, FLAGS.max_steps):
         t = time.time()
         boundary, sflow = flow_net.inputs(per_rank, seed=(step * world + rank) * per_rank)
         sflow_p = flow_net.inference(boundary, FLAGS.keep_prob, dropout_seed=step * 131071 + rank)
         error = flow_net.loss_image_train(sflow_p, sflow)
+        if restored is not None:                  # the Adam slots live in the flat buffers, which need the variables
+            checkpoint.restore(restored, flow_architecture.VARIABLES, flow_net.ensure_training_state(), strict=False)
+            restored = None
         flow_net.train(error, FLAGS.learning_rate)
         loss_value = float(error.item())
         elapsed = time.time() - t
@@ -63,9 +76,7 @@ def train():
             print("loss value at " + str(loss_value))
             print("time per batch is " + str(elapsed))
         if step % 1000 == 0 and rank == 0 and step > 0:
-            os.makedirs(train_dir, exist_ok=True)
-            torch.save({k: v.cpu() for k, v in flow_architecture.global_variables().items()},
-                       os.path.join(train_dir, 'model.ckpt-%d.pt' % step))
+            checkpoint.save(train_dir, step, flow_architecture.global_variables(), flow_net.training_state())
             print("saved to " + train_dir)
     flow_net.end_training()
 

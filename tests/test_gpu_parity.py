@@ -669,3 +669,46 @@ def test_stream_host_matches_eager(native):
     for x, o in zip(xs, outs):
         ref = flow_net.inference(x.cuda(), 1.0)
         assert torch.equal(ref.cpu(), o)
+
+
+def test_checkpoint_resume_continues_bit_exactly(native, tmp_path):
+    """utils/checkpoint.py: stop after 2 steps, restore variables + Adam slots into a fresh
+    graph, continue -- same variables as the uninterrupted run (every reduction in the step is ordered)."""
+    import model.flow_architecture as arch
+    import model.flow_net as flow_net
+    from utils import checkpoint
+
+    def steps(k0, k1):
+        for k in range(k0, k1):
+            b, s = flow_net.inputs(2, shape=(32, 64), seed=10 * k)
+            p = flow_net.inference(b, 1.0)
+            err = flow_net.loss_image_train(p, s)
+            flow_net.train(err, 1e-3)
+
+    try:
+        arch.reset_variables(1234)
+        flow_net.reset_training_state()
+        flow_net.begin_training()
+        steps(0, 2)
+        path = checkpoint.save(str(tmp_path), 2, arch.global_variables(), flow_net.training_state())
+        steps(2, 4)
+        want = {k: v.clone() for k, v in arch.global_variables().items()}
+        flow_net.end_training()
+
+        arch.reset_variables(77)                     # different random init: everything must come from the file
+        flow_net.reset_training_state()
+        assert checkpoint.restore(path, arch.VARIABLES) == 2
+        flow_net.begin_training()
+        b, _ = flow_net.inputs(2, shape=(32, 64), seed=0)
+        flow_net.inference(b, 1.0)                   # creates the variables (from the preloaded values)
+        arch.TAPE.clear()
+        checkpoint.restore(path, arch.VARIABLES, flow_net.ensure_training_state(), strict=False)
+        steps(2, 4)
+        got = arch.global_variables()
+        assert set(got) == set(want)
+        for k in want:
+            assert torch.equal(got[k], want[k]), k
+    finally:
+        flow_net.end_training()
+        flow_net.reset_training_state()
+        arch.reset_variables(1234)

@@ -64,7 +64,9 @@ def test_tc_weight_image_size(built_lib):
     assert lib.fn_conv_weights_tc_bytes(3, 16, 0, 16, 1) == 9 * 16 * 32
     # ru4_0.conv_1 + nin: Cout=8 padded to N=16, 9 + 1 k-steps
     assert lib.fn_conv_weights_tc_bytes(3, 16, 16, 8, 0) == 10 * 16 * 32
-    assert lib.fn_conv_weights_tc_bytes(3, 8, 0, 8, 0) == 0     # K not a multiple of 16: no tcgen05 image
+    # K = 8 (8-channel gradients): one k-step per tap whose second half is zero
+    assert lib.fn_conv_weights_tc_bytes(3, 8, 0, 8, 0) == 9 * 16 * 32
+    assert lib.fn_conv_weights_tc_bytes(3, 24, 0, 8, 0) == 0    # K not a multiple of 16: no tcgen05 image
 
 
 def test_product_variable_store_matches_oracle_convention(built_lib):
@@ -94,3 +96,69 @@ def test_flags_defaults_match_reference(built_lib):
     with pytest.raises(ValueError):
         arch.set_nonlinearity("swish")
     assert arch.set_nonlinearity("concat_elu") is arch.concat_elu
+
+
+# ---------------------------------------------------------------- checkpoints keyed by TF names
+def test_checkpoint_roundtrip_and_lazy_restore(tmp_path):
+    import numpy as np
+    import torch
+    import model.flow_architecture as arch
+    from utils import checkpoint
+
+    class Flat:                      # the fields of flow_backward.FlatParams that a checkpoint touches
+        pass
+
+    arch.reset_variables(7)
+    a = arch._variable('resnet_1_0_conv_1_conv/weights', [3, 3, 1, 8], device="cpu")
+    b = arch._variable('resnet_1_0_conv_1_conv/biases', [8], device="cpu")
+    flat = Flat()
+    flat.offsets = {'resnet_1_0_conv_1_conv/weights': (0, 72, (3, 3, 1, 8)), 'resnet_1_0_conv_1_conv/biases': (72, 8, (8,))}
+    flat.m = torch.arange(80, dtype=torch.float32)
+    flat.v = torch.arange(80, dtype=torch.float32) * 2
+    flat.step = 41
+    path = checkpoint.save(str(tmp_path), 1000, arch.global_variables(), flat)
+    assert checkpoint.get_checkpoint_state(str(tmp_path)) == path
+    ck = checkpoint.load(path)
+    assert set(ck) == {'resnet_1_0_conv_1_conv/weights', 'resnet_1_0_conv_1_conv/biases',
+                       'resnet_1_0_conv_1_conv/weights/Adam', 'resnet_1_0_conv_1_conv/weights/Adam_1',
+                       'resnet_1_0_conv_1_conv/biases/Adam', 'resnet_1_0_conv_1_conv/biases/Adam_1',
+                       'beta1_power', 'beta2_power', 'adam_step', 'global_step'}
+    assert ck['resnet_1_0_conv_1_conv/weights'].shape == (3, 3, 1, 8)          # TF HWIO layout, untouched
+    wa, wb = a.clone(), b.clone()
+
+    # restore into a fresh graph: the first variable exists already, the second is created lazily afterwards
+    arch.reset_variables(99)
+    a2 = arch._variable('resnet_1_0_conv_1_conv/weights', [3, 3, 1, 8], device="cpu")
+    assert not torch.equal(a2, wa)
+    flat2 = Flat()
+    flat2.offsets, flat2.m, flat2.v, flat2.step = flat.offsets, torch.zeros(80), torch.zeros(80), 0
+    step = checkpoint.restore(path, arch.VARIABLES, flat2, strict=False)
+    b2 = arch._variable('resnet_1_0_conv_1_conv/biases', [8], device="cpu")
+    assert step == 1000 and flat2.step == 41
+    assert torch.equal(a2, wa) and torch.equal(b2, wb)
+    assert torch.equal(flat2.m, flat.m) and torch.equal(flat2.v, flat.v)
+
+    # a checkpoint that does not fit the graph is refused (the reference then re-initialises, flow_train.py:66-72)
+    arch.reset_variables(5)
+    arch._variable('resnet_1_0_conv_1_conv/weights', [3, 3, 1, 16], device="cpu")
+    with pytest.raises(ValueError):
+        checkpoint.restore(path, arch.VARIABLES)
+    arch.reset_variables(1234)
+
+
+def test_experiment_manager_paths_follow_the_flags(tmp_path):
+    from model import flags
+    from utils import experiment_manager as em
+    import model.flow_net  # noqa: F401  (registers the model flags)
+    p = em.make_checkpoint_path(str(tmp_path), flags.FLAGS)
+    assert 'nr_res_blocks_1' in p and 'nonlinearity_concat_elu' in p and 'base_dir' not in p
+    import os
+    os.makedirs(p)
+    open(os.path.join(p, 'checkpoint'), 'w').write('model_checkpoint_path: "model.ckpt-0"\n')
+    assert em.list_all_checkpoints(str(tmp_path)) == [p]
+    old = flags.FLAGS.nr_res_blocks
+    try:
+        em.set_flags_given_checkpoint_path(p.replace('nr_res_blocks_1', 'nr_res_blocks_3')[len(str(tmp_path)):], flags.FLAGS)
+        assert flags.FLAGS.nr_res_blocks == 3
+    finally:
+        flags.FLAGS.nr_res_blocks = old
