@@ -100,16 +100,25 @@ class _Grads:
         return ent[1], True
 
 
-def backward(tape, sflow_p, sflow, flat: FlatParams):
-    """Fills flat.grad with d(l2_loss)/d(variables); returns the loss (fp32 [1])."""
+def backward(tape, sflow_p, sflow, flat: FlatParams = None, want_input_grad=False):
+    """Fills flat.grad with d(l2_loss)/d(variables) (skipped when flat is None); returns the loss (fp32 [1]), or
+    (loss, d loss / d boundary [B,H,W,1] bf16) with want_input_grad -- the one data gradient training never needs
+    (the first conv's), which the boundary-optimisation use of the network does (README.md:31-36)."""
     V = arch.VARIABLES.vars
     dev = sflow_p.device
     grads = _Grads()
     loss, dpre = native.tanh_l2_bwd(sflow_p, sflow.to(torch.float32))
+    params = flat is not None
+    d_input = None
 
     def wgrad_into(name, x, dY, ksize, stride, pro, keep_prob=1.0, seed=0):
-        native.conv_wgrad(x, dY, flat.grad_view(name + '/weights').view(ksize * ksize, -1, dY.shape[-1]), ksize=ksize,
-                          stride=stride, prologue=pro, keep_prob=keep_prob, dropout_seed=seed)
+        if params:
+            native.conv_wgrad(x, dY, flat.grad_view(name + '/weights').view(ksize * ksize, -1, dY.shape[-1]), ksize=ksize,
+                              stride=stride, prologue=pro, keep_prob=keep_prob, dropout_seed=seed)
+
+    def bgrad_into(name, dY):
+        if params:
+            native.bias_grad(dY, flat.grad_view(name + '/biases'))
 
     for rec in reversed(tape):
         kind = rec["kind"]
@@ -117,12 +126,13 @@ def backward(tape, sflow_p, sflow, flat: FlatParams):
             x = rec["x"]                                   # [B,H,W,F] raw block output, no prologue
             cin = x.shape[3]
             # weights: [3,3,cin,2]; gradients run as 8-channel launches (dpre channels 2..7 are zero)
-            tmp = torch.empty((9, cin, 8), dtype=torch.float32, device=dev)
-            native.conv_wgrad(x, dpre, tmp, ksize=3, stride=1, prologue=native.PRO_NONE)
-            flat.grad_view('last_conv_conv/weights').copy_(tmp[:, :, :2].reshape(3, 3, cin, 2))
-            tmpb = torch.empty(8, dtype=torch.float32, device=dev)
-            native.bias_grad(dpre, tmpb)
-            flat.grad_view('last_conv_conv/biases').copy_(tmpb[:2])
+            if params:
+                tmp = torch.empty((9, cin, 8), dtype=torch.float32, device=dev)
+                native.conv_wgrad(x, dpre, tmp, ksize=3, stride=1, prologue=native.PRO_NONE)
+                flat.grad_view('last_conv_conv/weights').copy_(tmp[:, :, :2].reshape(3, 3, cin, 2))
+                tmpb = torch.empty(8, dtype=torch.float32, device=dev)
+                native.bias_grad(dpre, tmpb)
+                flat.grad_view('last_conv_conv/biases').copy_(tmpb[:2])
             w = V['last_conv_conv/weights']
             w8 = torch.zeros((3, 3, cin, 8), dtype=torch.float32, device=dev)
             w8[..., :2] = w
@@ -134,8 +144,9 @@ def backward(tape, sflow_p, sflow, flat: FlatParams):
             x, y, scope = rec["x"], rec["out"], rec["scope"]
             g = grads.get(y)
             cin, cout = x.shape[3], y.shape[3]
-            native.tconv_wgrad(x, g, flat.grad_view(scope + '/weights').view(9, cout, cin))
-            native.bias_grad(g, flat.grad_view(scope + '/biases'))
+            if params:
+                native.tconv_wgrad(x, g, flat.grad_view(scope + '/weights').view(9, cout, cin))
+            bgrad_into(scope, g)
             # d(x) = stride-2 'SAME' conv of d(y) with the same weights read as HWIO [k,k,Cout,Cin]
             w16 = V[scope + '/weights'].reshape(9, cout, cin).to(torch.bfloat16).contiguous()
             dx = _conv_plain(g, w16, cin, 3, 2, dev)
@@ -157,22 +168,24 @@ def backward(tape, sflow_p, sflow, flat: FlatParams):
                 dc2 = native.gate_bwd(c2, g)
             else:
                 dc2 = g
-            native.bias_grad(dc2, flat.grad_view(s2 + '/biases'))
+            bgrad_into(s2, dc2)
             wgrad_into(s2, x_1, dc2, 3, 1, pro, keep_p, seed)
             dA2 = _conv_plain(dc2, _dgrad_weights_s1(V[s2 + '/weights'], 3), mult * F_, 3, 1, dev)
             dx_1 = native.prologue_bwd(dA2, x_1, pro, keep_prob=keep_p, seed=seed)
             # ---- conv_1 (+nin skip)
             s1 = name + '_conv_1_conv'
             pro1 = native.PRO_NONE if cin == 1 else pro
-            native.bias_grad(dx_1, flat.grad_view(s1 + '/biases'))
+            bgrad_into(s1, dx_1)
             wgrad_into(s1, x, dx_1, 3, stride, pro1)
             if a is not None:
                 sn = name + '_nin_fc'
-                flat.grad_view(sn + '/biases').copy_(flat.grad_view(s1 + '/biases'))
+                if params:
+                    flat.grad_view(sn + '/biases').copy_(flat.grad_view(s1 + '/biases'))
                 # the skip is zero-padded bottom/right to x_1's size: only the overlapping window contributes
                 if a.shape[1] != dx_1.shape[1] or a.shape[2] != dx_1.shape[2]:
                     raise ValueError("training with a spatially padded skip (H, W not multiples of 16) is not built")
-                native.conv_wgrad(a, dx_1, flat.grad_view(sn + '/weights').view(1, -1, F_), ksize=1, stride=1, prologue=pro)
+                if params:
+                    native.conv_wgrad(a, dx_1, flat.grad_view(sn + '/weights').view(1, -1, F_), ksize=1, stride=1, prologue=pro)
                 wn = V[sn + '/weights']                                   # [mult*Ca, F]
                 dAa = _conv_plain(dx_1, wn.t().reshape(1, F_, -1).to(torch.bfloat16).contiguous(), wn.shape[0], 1, 1, dev)
                 buf, acc = grads.target(a)
@@ -189,7 +202,16 @@ def backward(tape, sflow_p, sflow, flat: FlatParams):
                 buf, acc = grads.target(x)
                 native.prologue_bwd(dA1, x, pro, out=buf, accumulate=acc)
                 native.shortcut_bwd(g, tuple(x.shape), pooled, out=buf, accumulate=True)
-    return loss
+            elif want_input_grad:
+                # the network input (1 channel, no prologue): conv adjoint with the output padded to 8 channels, plus
+                # the shortcut's front-padded identity (channel F-1 of g)
+                w1 = V[s1 + '/weights']                                   # [3,3,1,F]
+                w8 = torch.zeros((3, 3, 8, F_), dtype=torch.float32, device=dev)
+                w8[:, :, :1, :] = w1
+                dA1 = _conv_plain(dx_1, _dgrad_weights_s1(w8, 3), 8, 3, 1, dev)
+                d_input = dA1[..., :1].contiguous()
+                native.shortcut_bwd(g, tuple(x.shape), pooled, out=d_input, accumulate=True)
+    return (loss, d_input) if want_input_grad else loss
 
 
 def allreduce_gradients(flat_grad):

@@ -183,6 +183,21 @@ def train(total_loss, lr):
     return loss
 
 
+def boundary_gradient(boundary, sflow, keep_prob=1.0):
+    """d l2_loss(inference(boundary), sflow) / d boundary -- the gradient the README's boundary-optimisation use needs
+    (/root/reference/README.md:31-36): the training backward pass without the parameter gradients,
+    plus the first conv's data gradient.  Returns (loss fp32 [1], gradient float32 [B,H,W,1])."""
+    import model.flow_backward as fb
+    saved = flow_architecture.TAPE
+    flow_architecture.TAPE = []
+    try:
+        sflow_p = inference(boundary, keep_prob)
+        loss, d_in = fb.backward(flow_architecture.TAPE, sflow_p, sflow, None, want_input_grad=True)
+    finally:
+        flow_architecture.TAPE = saved
+    return loss, d_in.to(torch.float32)
+
+
 def ensure_training_state():
     """Create the flat parameter / gradient / Adam buffers now (needs one forward: variables are created lazily)."""
     import model.flow_backward as fb

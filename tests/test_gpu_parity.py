@@ -712,3 +712,24 @@ def test_checkpoint_resume_continues_bit_exactly(native, tmp_path):
         flow_net.end_training()
         flow_net.reset_training_state()
         arch.reset_variables(1234)
+
+
+def test_boundary_gradient_vs_oracle_autograd(native, golden_dir):
+    """d loss / d boundary (the first conv's data gradient + the front-padded shortcut)."""
+    import model.flow_architecture as arch
+    import model.flow_net as flow_net
+    z = np.load(os.path.join(golden_dir, "golden_train.npz"))
+    x = fo.synth_boundary(2, 32, 64, seed=3).astype(np.float64)
+    tgt = z["target"]
+    vs = fo.VariableStore(1234, torch.float64)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    ref_loss = fo.loss_image(fo.inference(vs, xt, 1.0), torch.from_numpy(tgt))
+    ref_loss.backward()
+    arch.reset_variables(1234)
+    loss, g = flow_net.boundary_gradient(torch.from_numpy(x.astype(np.float32)).cuda(),
+                                         torch.from_numpy(tgt.astype(np.float32)).cuda())
+    torch.cuda.synchronize()
+    assert native.tc_status() == 0
+    assert g.shape == (2, 32, 64, 1) and g.dtype == torch.float32
+    assert abs(loss.item() - ref_loss.item()) < 2e-2 * abs(ref_loss.item())
+    assert rel_l2(g, xt.grad) < 5e-2
