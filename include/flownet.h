@@ -177,6 +177,23 @@ int fn_conv_wgrad(const fn_conv_desc* d, const void* dY, float* dW, float* works
 int64_t fn_tconv_wgrad_workspace(const fn_tconv_desc* d);
 int fn_tconv_wgrad(const fn_tconv_desc* d, const void* dY, float* dW, float* workspace, void* stream);
 
+/* ---- dataset files (host code, no GPU): the TFRecord / tf.train.Example format written by
+ * utils/createTFRecords.py:45-56 and read by input/flow_input.py:14-30 of the reference ------------------------- */
+/* walks a whole TFRecord file image; returns the record count (or FN_E_INVAL on a truncated / corrupt file) and
+ * fills payload offsets / lengths for the first max_records records (both arrays may be NULL to just count).
+ * check_crc != 0 verifies the masked CRC32-C of every length word and payload. */
+int64_t fn_tfrecord_index(const uint8_t* buf, int64_t nbytes, int64_t* offsets, int64_t* lengths, int64_t max_records,
+                          int32_t check_crc);
+/* one Example payload -> 'boundary' (uint8, boundary_bytes = H*W) and 'sflow' (float32, sflow_bytes = H*W*2*4);
+ * FN_E_INVAL when a feature is missing or has another size */
+int fn_tfrecord_parse_flow_example(const uint8_t* payload, int64_t len, uint8_t* boundary, int64_t boundary_bytes, float* sflow,
+                                   int64_t sflow_bytes);
+/* writes one framed record holding such an Example; dst == NULL returns the size needed; returns bytes written */
+int64_t fn_tfrecord_write_flow_example(uint8_t* dst, int64_t capacity, const uint8_t* boundary, int64_t boundary_bytes,
+                                       const float* sflow, int64_t sflow_bytes);
+uint32_t fn_crc32c(const uint8_t* p, int64_t n);          /* SSE4.2 instruction when the CPU has it */
+uint32_t fn_crc32c_portable(const uint8_t* p, int64_t n); /* table-driven */
+
 #ifdef __cplusplus
 }
 #endif

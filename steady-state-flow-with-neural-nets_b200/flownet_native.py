@@ -72,6 +72,11 @@ SYMBOLS = [
     ("fn_conv_wgrad", C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P]),
     ("fn_tconv_wgrad_workspace", C.c_int64, [C.POINTER(TConvDesc)]),
     ("fn_tconv_wgrad", C.c_int, [C.POINTER(TConvDesc), _P, _P, _P, _P]),
+    ("fn_tfrecord_index", C.c_int64, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int32]),
+    ("fn_tfrecord_parse_flow_example", C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64]),
+    ("fn_tfrecord_write_flow_example", C.c_int64, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64]),
+    ("fn_crc32c", C.c_uint32, [_P, C.c_int64]),
+    ("fn_crc32c_portable", C.c_uint32, [_P, C.c_int64]),
 ]
 DEBUG_SYMBOLS = [
     ("fn_debug_set_swap_lbo_sbo", None, [C.c_int]),

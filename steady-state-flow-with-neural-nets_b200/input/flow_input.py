@@ -1,0 +1,178 @@
+"""Input pipeline for the reference's dataset files (/root/reference/input/flow_input.py:14-60).
+
+The reference reads `../data/*.tfrecords` through a TF filename queue, parses each tf.train.Example
+({'boundary': uint8[H*W] bytes, 'sflow': float32[H*W*2] bytes}, utils/createTFRecords.py:45-56) and batches through
+`tf.train.shuffle_batch(capacity = min_queue_examples + 3*batch, min_after_dequeue = min_queue_examples)` with one
+preprocessing thread.  Here the framing / proto parsing is native host code in libflownet.so (csrc/tfrecord.cpp, no
+TensorFlow), the shuffle buffer has the same capacity rule, one background thread fills pinned host batches, and the
+boundary stays uint8 all the way to the GPU (the first conv casts it; 4x fewer bytes than the reference's float32).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob as _glob
+import mmap
+import os
+import queue
+import threading
+
+import numpy as np
+import torch
+
+import flownet_native as native
+from model import flags
+
+FLAGS = flags.FLAGS
+flags.DEFINE_integer('min_queue_examples', 1000, """ min examples to queue up""")
+
+
+class TFRecordFile:
+    """One memory-mapped .tfrecords file with its record index."""
+
+    def __init__(self, path, check_crc=True):
+        self.path = path
+        self._f = open(path, 'rb')
+        size = os.fstat(self._f.fileno()).st_size
+        self._mm = mmap.mmap(self._f.fileno(), 0, access=mmap.ACCESS_READ) if size else None
+        self._buf = np.frombuffer(self._mm, dtype=np.uint8) if size else np.zeros(0, np.uint8)
+        n = native.lib.fn_tfrecord_index(self._buf.ctypes.data, self._buf.size, None, None, 0, int(check_crc))
+        if n < 0:
+            raise ValueError("%s: truncated or corrupt TFRecord file (code %d)" % (path, n))
+        self.offsets = np.zeros(n, np.int64)
+        self.lengths = np.zeros(n, np.int64)
+        if n:
+            native.lib.fn_tfrecord_index(self._buf.ctypes.data, self._buf.size, self.offsets.ctypes.data, self.lengths.ctypes.data, n, 0)
+
+    def __len__(self):
+        return len(self.offsets)
+
+    def read_into(self, i, boundary, sflow):
+        """Parse record i into boundary (uint8 [H,W,1]) and sflow (float32 [H,W,2]) -- numpy views, contiguous."""
+        rc = native.lib.fn_tfrecord_parse_flow_example(self._buf.ctypes.data + int(self.offsets[i]), int(self.lengths[i]),
+                                                        boundary.ctypes.data, boundary.nbytes, sflow.ctypes.data, sflow.nbytes)
+        if rc != 0:
+            raise ValueError("%s record %d: not a {'boundary','sflow'} example of %d / %d bytes" %
+                             (self.path, i, boundary.nbytes, sflow.nbytes))
+
+
+def read_data(path, shape=(128, 256)):
+    """reference :14-30: yields (boundary uint8 [H,W,1], sflow float32 [H,W,2]) for every record of one file."""
+    f = TFRecordFile(path)
+    for i in range(len(f)):
+        b = np.empty((shape[0], shape[1], 1), np.uint8)
+        s = np.empty((shape[0], shape[1], 2), np.float32)
+        f.read_into(i, b, s)
+        yield b, s
+
+
+def write_tfrecords(path, boundaries, sflows):
+    """The writer side (utils/createTFRecords.py:45-56): boundaries uint8 [N,H,W(,1)], sflows float32 [N,H,W,2]."""
+    boundaries = np.ascontiguousarray(boundaries, dtype=np.uint8)
+    sflows = np.ascontiguousarray(sflows, dtype=np.float32)
+    with open(path, 'wb') as f:
+        for b, s in zip(boundaries, sflows):
+            need = native.lib.fn_tfrecord_write_flow_example(None, 0, b.ctypes.data, b.nbytes, s.ctypes.data, s.nbytes)
+            out = np.empty(need, np.uint8)
+            got = native.lib.fn_tfrecord_write_flow_example(out.ctypes.data, need, b.ctypes.data, b.nbytes, s.ctypes.data, s.nbytes)
+            if got != need:
+                raise RuntimeError("fn_tfrecord_write_flow_example failed (%d)" % got)
+            f.write(out.tobytes())
+
+
+class FlowInputQueue:
+    """`tf.train.shuffle_batch` over the records of some .tfrecords files, endlessly (the filename queue of the
+    reference cycles forever): a buffer of parsed examples is kept between min_after_dequeue and capacity, every
+    batch draws uniformly from it.  next() returns CUDA tensors (boundary uint8 [B,H,W,1], sflow float32 [B,H,W,2])
+    whose host->device copies were issued from pinned memory on a side stream."""
+
+    def __init__(self, files, batch_size, shape=(128, 256), min_after_dequeue=None, seed=0, device="cuda", shuffle=True,
+                 prefetch=2):
+        if not files:
+            raise FileNotFoundError("no .tfrecords files")
+        self.files = [TFRecordFile(p) for p in files]
+        self.total = sum(len(f) for f in self.files)
+        if self.total == 0:
+            raise ValueError("the .tfrecords files hold no records")
+        self.B, self.shape = batch_size, shape
+        self.min_after = FLAGS.min_queue_examples if min_after_dequeue is None else min_after_dequeue
+        self.capacity = self.min_after + 3 * batch_size                         # reference :38
+        self.rng = np.random.default_rng(seed)
+        self.shuffle = shuffle
+        self.device = device
+        H, W = shape
+        self._pool_b = np.empty((self.capacity, H, W, 1), np.uint8)
+        self._pool_s = np.empty((self.capacity, H, W, 2), np.float32)
+        self._fill = 0
+        self._cursor = (0, 0)                                                   # (file, record)
+        self._q = queue.Queue(maxsize=prefetch)
+        self._stop = False
+        self._cuda = torch.cuda.is_available() and str(device).startswith("cuda")
+        self._stream = torch.cuda.Stream() if self._cuda else None
+        self._thread = threading.Thread(target=self._producer, daemon=True)     # num_preprocess_threads = 1 (reference :34)
+        self._thread.start()
+
+    def _next_record(self, b, s):
+        fi, ri = self._cursor
+        while ri >= len(self.files[fi]):
+            fi, ri = (fi + 1) % len(self.files), 0
+        self.files[fi].read_into(ri, b, s)
+        self._cursor = (fi, ri + 1)
+
+    def _producer(self):
+        H, W = self.shape
+        try:
+            while not self._stop:
+                want = self.capacity if self.shuffle else self.B
+                while self._fill < want:
+                    self._next_record(self._pool_b[self._fill], self._pool_s[self._fill])
+                    self._fill += 1
+                hb = torch.empty((self.B, H, W, 1), dtype=torch.uint8, pin_memory=self._cuda)
+                hs = torch.empty((self.B, H, W, 2), dtype=torch.float32, pin_memory=self._cuda)
+                nb, ns = hb.numpy(), hs.numpy()
+                for i in range(self.B):
+                    j = int(self.rng.integers(0, self._fill)) if self.shuffle else 0
+                    nb[i], ns[i] = self._pool_b[j], self._pool_s[j]
+                    if self.shuffle:                        # swap-remove: the last buffered example takes slot j
+                        self._fill -= 1
+                        self._pool_b[j], self._pool_s[j] = self._pool_b[self._fill], self._pool_s[self._fill]
+                    else:                                   # FIFO
+                        self._fill -= 1
+                        self._pool_b[:self._fill] = self._pool_b[1:self._fill + 1]
+                        self._pool_s[:self._fill] = self._pool_s[1:self._fill + 1]
+                self._q.put((hb, hs))
+        except BaseException as e:                          # surface parser errors in the consumer
+            self._q.put(e)
+
+    def next(self):
+        item = self._q.get()
+        if isinstance(item, BaseException):
+            raise item
+        hb, hs = item
+        if not self._cuda:
+            return hb, hs
+        with torch.cuda.stream(self._stream):
+            db = hb.to(self.device, non_blocking=True)
+            ds = hs.to(self.device, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(self._stream)
+        db.record_stream(torch.cuda.current_stream())
+        ds.record_stream(torch.cuda.current_stream())
+        self._keep = (hb, hs)                               # pinned sources stay alive until the next batch
+        return db, ds
+
+    __next__ = next
+
+    def __iter__(self):
+        return self
+
+    def close(self):
+        self._stop = True
+        try:
+            while True:
+                self._q.get_nowait()
+        except queue.Empty:
+            pass
+
+
+def flow_inputs(batch_size, data_glob='../data/*.tfrecords', shape=(128, 256), seed=0, device="cuda"):
+    """reference :42-60.  Returns a FlowInputQueue; `boundarys, sflows = q.next()` per training step."""
+    return FlowInputQueue(sorted(_glob.glob(data_glob)), batch_size, shape=shape, seed=seed, device=device)

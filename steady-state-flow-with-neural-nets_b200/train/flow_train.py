@@ -1,6 +1,7 @@
 """Training loop with the reference's flags and shape (/root/reference/train/flow_train.py:15-24, 30-97):
 make inputs, unwrap the network, l2 loss, Adam step; print the loss every 100 steps; NaN check.
-The TFRecord queue is replaced by the synthetic generator (no dataset ships, no network) and the TF
+The TFRecord queue is input/flow_input.py's (native parser, shuffle buffer) when `--data_glob` matches files, else
+the synthetic generator (no dataset ships, no network); the TF
 Saver by utils/checkpoint.py: an .npz keyed by the TF variable names (+ Adam slots) every 1000 steps and a
 restore-on-start with the reference's fall-back to random init.
 Data-parallel: launch with torchrun, one process per GPU; each rank trains on its own shard of the
@@ -29,6 +30,7 @@ flags.DEFINE_integer('batch_size', 8, """ training batch size """)
 flags.DEFINE_integer('max_steps', 500000, """ max number of steps to train """)
 flags.DEFINE_float('keep_prob', 0.7, """ keep probability for dropout """)
 flags.DEFINE_float('learning_rate', 1e-4, """ keep probability for dropout """)
+flags.DEFINE_string('data_glob', '../data/*.tfrecords', """ dataset files (reference: input/flow_input.py:45); synthetic data if none match """)
 
 
 def train():
@@ -59,10 +61,15 @@ def train():
             restored = None
             flow_architecture.reset_variables(1234)
             print("there was a problem using variables in checkpoint, random init will be used instead")
+    import glob
+    data_glob = FLAGS.data_glob if glob.glob(FLAGS.data_glob) else None
+    if rank == 0:
+        print("training on " + (FLAGS.data_glob if data_glob else "synthetic boundaries (no dataset found)"))
     flow_net.begin_training()
     for step in range(start_step, FLAGS.max_steps):
         t = time.time()
-        boundary, sflow = flow_net.inputs(per_rank, seed=(step * world + rank) * per_rank)
+        boundary, sflow = flow_net.inputs(per_rank, seed=(step * world + rank) * per_rank if not data_glob else rank,
+                                          data_glob=data_glob)
         sflow_p = flow_net.inference(boundary, FLAGS.keep_prob, dropout_seed=step * 131071 + rank)
         error = flow_net.loss_image_train(sflow_p, sflow)
         if restored is not None:                  # the Adam slots live in the flat buffers, which need the variables

@@ -733,3 +733,38 @@ def test_boundary_gradient_vs_oracle_autograd(native, golden_dir):
     assert g.shape == (2, 32, 64, 1) and g.dtype == torch.float32
     assert abs(loss.item() - ref_loss.item()) < 2e-2 * abs(ref_loss.item())
     assert rel_l2(g, xt.grad) < 5e-2
+
+
+def test_training_from_tfrecords_queue(native, tmp_path):
+    """dataset file -> native parser -> shuffle queue -> pinned uint8/float32 -> GPU -> train step."""
+    import model.flow_architecture as arch
+    import model.flow_net as flow_net
+    import input.flow_input as fi
+    from utils.synthetic import synth_boundary, synth_sflow
+    b = synth_boundary(12, 32, 64, seed=5)
+    s = synth_sflow(b)
+    path = str(tmp_path / "train.tfrecords")
+    fi.write_tfrecords(path, b, s)
+    pairs = {s[i].tobytes(): b[i].tobytes() for i in range(12)}
+    try:
+        arch.reset_variables(1234)
+        flow_net.reset_training_state()
+        flow_net.begin_training()
+        losses = []
+        for _ in range(3):
+            bd, sd = flow_net.inputs(4, shape=(32, 64), data_glob=path)
+            assert bd.is_cuda and bd.dtype == torch.uint8 and sd.dtype == torch.float32
+            for j in range(4):
+                assert pairs[sd[j].cpu().numpy().tobytes()] == bd[j].cpu().numpy().tobytes()
+            p = flow_net.inference(bd, 1.0)
+            err = flow_net.loss_image_train(p, sd)
+            flow_net.train(err, 1e-3)
+            losses.append(err.item())
+        assert all(np.isfinite(losses))
+    finally:
+        flow_net.end_training()
+        flow_net.reset_training_state()
+        arch.reset_variables(1234)
+        for q in flow_net._QUEUES.values():
+            q.close()
+        flow_net._QUEUES.clear()
