@@ -25,7 +25,7 @@ namespace s2t {
 constexpr int THREADS = 448;
 constexpr int WARP_PRODUCER = 12, WARP_ISSUER = 13;
 constexpr int HDR = 256 + 1024;
-enum { MODE_S2 = 1, MODE_TCONV = 2 };
+enum { MODE_S2 = 1, MODE_TCONV = 2, MODE_S1N = 3 };
 
 struct Params {
   CUtensorMap tm_x;
@@ -40,21 +40,24 @@ struct Params {
   int Cout;               // real output channels
 };
 
-template <int MODE, int CLOG, int J, int NBUF>
+template <int MODE, int CLOG, int J, int NBUF, int R = 1>
 struct Cfg {
   static constexpr int CH = 1 << CLOG;                       // 8-channel chunks of the raw input
   static constexpr int C = 8 * CH;
   static constexpr bool S2 = MODE == MODE_S2;
+  static constexpr bool S1N = MODE == MODE_S1N;              // stride 1, no prologue, Cout = R*C (data gradients)
   static constexpr int KPLANES = S2 ? 2 * CH : CH;          // 8-channel planes of one (sub-)operand
-  static constexpr int KS = S2 ? CH : CH / 2;                // k-steps per tap
-  static constexpr int NREAL = S2 ? 2 * C : C / 2;           // Cout
+  // k-steps per tap; a lone plane (C = 8) is read for both K halves (LBO = 0) against zero-padded weights
+  static constexpr bool HALF_K = !S2 && CH == 1;
+  static constexpr int KS = S2 ? CH : (CH >= 2 ? CH / 2 : 1);
+  static constexpr int NREAL = S2 ? 2 * C : (S1N ? R * C : C / 2);   // Cout
   static constexpr int N = NREAL < 16 ? 16 : NREAL;
-  static constexpr int NPH = S2 ? 1 : 4;                     // accumulators per sub-tile
+  static constexpr int NPH = MODE == MODE_TCONV ? 4 : 1;     // accumulators per sub-tile
   static constexpr int KSTEPS = 9 * KS;
-  // stage tile (TMA box): S2 33 x (16J+1) input pixels, TCONV 17 x (8J+1)
-  static constexpr int SW_ = S2 ? 16 * J + 1 : 8 * J + 1, SH_ = S2 ? 33 : 17, SP = SW_ * SH_;
-  // (sub-)plane geometry: 17 x (8J+1) positions
-  static constexpr int PU = 8 * J + 1, PV = 17, P = PU * PV;
+  // stage tile (TMA box): S2 33 x (16J+1) input pixels, TCONV 17 x (8J+1), S1N 18 x (8J+2)
+  static constexpr int SW_ = S2 ? 16 * J + 1 : (S1N ? 8 * J + 2 : 8 * J + 1), SH_ = S2 ? 33 : (S1N ? 18 : 17), SP = SW_ * SH_;
+  // (sub-)plane geometry
+  static constexpr int PU = S1N ? 8 * J + 2 : 8 * J + 1, PV = S1N ? 18 : 17, P = PU * PV;
   static constexpr int PADW = KPLANES >= 8 ? 1 : (KPLANES == 4 ? 2 : (KPLANES == 2 ? 4 : 0));
   static constexpr int PPAD = KPLANES == 1 ? P : P + ((PADW - (P & 7)) + 8) % 8;
   static constexpr int SUB_BYTES = KPLANES * PPAD * 16;
@@ -70,7 +73,7 @@ struct Cfg {
   static constexpr int TCOLS = NBUF * ACC_COLS;
   static constexpr int TMEM_COLS = TCOLS <= 32 ? 32 : TCOLS <= 64 ? 64 : TCOLS <= 128 ? 128 : TCOLS <= 256 ? 256 : 512;
   static_assert(TCOLS <= 512, "accumulators exceed TMEM");
-  static_assert(S2 || CH >= 2, "transposed conv needs C >= 16");
+  static_assert(MODE != MODE_TCONV || CH >= 2, "transposed conv needs C >= 16");
 };
 
 enum { SB_W = 0, SB_X = 1, SB_XF = 3, SB_PF = 5, SB_TF = 7, SB_TE = 9, SB_COUNT = 11 };
@@ -121,9 +124,9 @@ __device__ __forceinline__ void transform_tile(uint32_t stage, uint32_t planes, 
   }
 }
 
-template <int MODE, int CLOG, int J, int NBUF>
+template <int MODE, int CLOG, int J, int NBUF, int R = 1>
 __global__ void __launch_bounds__(THREADS) k_conv_s2t(const __grid_constant__ Params p) {
-  using CF = Cfg<MODE, CLOG, J, NBUF>;
+  using CF = Cfg<MODE, CLOG, J, NBUF, R>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const uint32_t sbase = ptx::smem_u32(smem);
@@ -203,16 +206,17 @@ __global__ void __launch_bounds__(THREADS) k_conv_s2t(const __grid_constant__ Pa
       if (k >= 1) ok = ok && ptx::mbar_wait(bar(SB_TE + s), (uint32_t)((k - 1) & 1));   // accumulators s drained
       if (!ok) atomicCAS(p.status, 0, 43);
       ptx::tc_fence_after_sync();
-      const uint64_t a_tmpl = ptx::smem_desc(sbase + CF::OFF_PLANES + s * CF::PLANE_BYTES, CF::PPAD * 16, CF::PU * 16);
+      const uint64_t a_tmpl = ptx::smem_desc(sbase + CF::OFF_PLANES + s * CF::PLANE_BYTES, CF::HALF_K ? 0 : CF::PPAD * 16, CF::PU * 16);
       const uint32_t d_tmem = tmem_base + (uint32_t)(s * CF::ACC_COLS);
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         const int di = tap / 3, dj = tap % 3;
         // S2: parity sub-plane + position shift; TCONV: source position of the row pixel and output phase
-        const int sub_off = CF::S2 ? ((di & 1) * 2 + (dj & 1)) * CF::SUB_BYTES + ((di >> 1) * CF::PU + (dj >> 1)) * 16
-                                   : (((di == 2) ? 0 : 1) * CF::PU + ((dj == 2) ? 0 : 1)) * 16;
-        const int ph = CF::S2 ? 0 : ((di == 1) ? 2 : 0) + ((dj == 1) ? 1 : 0);
-        const bool first = CF::S2 ? (tap == 0) : (tap == 0 || tap == 1 || tap == 3 || tap == 4);
+        const int sub_off = CF::S2    ? ((di & 1) * 2 + (dj & 1)) * CF::SUB_BYTES + ((di >> 1) * CF::PU + (dj >> 1)) * 16
+                            : CF::S1N ? (di * CF::PU + dj) * 16
+                                      : (((di == 2) ? 0 : 1) * CF::PU + ((dj == 2) ? 0 : 1)) * 16;
+        const int ph = CF::NPH == 1 ? 0 : ((di == 1) ? 2 : 0) + ((dj == 1) ? 1 : 0);
+        const bool first = CF::NPH == 1 ? (tap == 0) : (tap == 0 || tap == 1 || tap == 3 || tap == 4);
 #pragma unroll
         for (int kk = 0; kk < CF::KS; ++kk) {
           const uint32_t a_off = (uint32_t)(sub_off + kk * 2 * CF::PPAD * 16) >> 4;
@@ -263,8 +267,8 @@ __global__ void __launch_bounds__(THREADS) k_conv_s2t(const __grid_constant__ Pa
         const int j = item / CF::NPH, ph = item % CF::NPH;
         const int rx = x0 + 8 * j + u;
         const bool live = ok && ry < p.RH && rx < p.RW;
-        const int oy = CF::S2 ? ry : 2 * ry + (ph >> 1);
-        const int ox = CF::S2 ? rx : 2 * rx + (ph & 1);
+        const int oy = CF::NPH == 1 ? ry : 2 * ry + (ph >> 1);
+        const int ox = CF::NPH == 1 ? rx : 2 * rx + (ph & 1);
         const size_t pix = ((size_t)b * p.OH + oy) * p.OW + ox;
         const uint32_t col0 = lane_base + (uint32_t)(s * CF::ACC_COLS + (j * CF::NPH + ph) * CF::N);
 #pragma unroll
@@ -321,10 +325,10 @@ static bool make_map_nhwc(CUtensorMap* tm, const void* base, int B, int H, int W
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int MODE, int CLOG, int J, int NBUF>
+template <int MODE, int CLOG, int J, int NBUF, int R = 1>
 static int launch(const void* x, const void* wpk, const float* bias, void* y, int B, int H, int W, int Cout, int* status,
                   cudaStream_t stream) {
-  using CF = Cfg<MODE, CLOG, J, NBUF>;
+  using CF = Cfg<MODE, CLOG, J, NBUF, R>;
   Params p;
   memset(&p, 0, sizeof(p));
   if (!make_map_nhwc(&p.tm_x, x, B, H, W, CF::C, CF::SW_, CF::SH_)) { set_error("conv_s2t: tensor map failed"); return FN_E_UNSUPPORTED; }
@@ -334,12 +338,13 @@ static int launch(const void* x, const void* wpk, const float* bias, void* y, in
   p.status = status;
   p.B = B; p.H = H; p.W = W;
   if (CF::S2) { p.OH = H / 2; p.OW = W / 2; p.RH = p.OH; p.RW = p.OW; }
+  else if (CF::S1N) { p.OH = H; p.OW = W; p.RH = H; p.RW = W; }
   else { p.OH = 2 * H; p.OW = 2 * W; p.RH = H; p.RW = W; }
   p.tiles_u = (p.RW + 8 * J - 1) / (8 * J);
   p.tiles_v = (p.RH + 15) / 16;
   p.ntiles = B * p.tiles_u * p.tiles_v;
   p.Cout = Cout;
-  auto kern = k_conv_s2t<MODE, CLOG, J, NBUF>;
+  auto kern = k_conv_s2t<MODE, CLOG, J, NBUF, R>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM);
@@ -388,6 +393,37 @@ bool conv_s2p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
   S2_CASE(1, 2, 2, 112) S2_CASE(1, 1, 2, 150)
   S2_CASE(2, 1, 1, 200)
 #undef S2_CASE
+  return false;
+}
+
+// stride-1 3x3 conv without prologue, Cout = C or 2C: the data-gradient convs of the backward pass (flipped weights)
+bool conv_s1n_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc) {
+  using namespace s2t;
+  rc = 0;
+  if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_NONE || d.epilogue != FN_EPI_BIAS || d.skip || d.w_tc == nullptr ||
+      d.H < 16)
+    return false;
+  if (get_encode() == nullptr) return false;
+  const int clog = d.Cin == 8 ? 0 : d.Cin == 16 ? 1 : d.Cin == 32 ? 2 : d.Cin == 64 ? 3 : -1;
+  const int r = d.Cout == d.Cin ? 1 : d.Cout == 2 * d.Cin ? 2 : 0;
+  if (clog < 0 || r == 0) return false;
+#define S1N_CASE(CL, RR, JJ, NB, CAP)                                                                            \
+  if (clog == CL && r == RR && ((d.W % (8 * JJ)) == 0 || JJ == 1) && Cfg<MODE_S1N, CL, JJ, NB, RR>::SMEM <= CAP * 1024) { \
+    if (!dry_run) {                                                                                              \
+      int* st = tc_status_word();                                                                                \
+      rc = st ? launch<MODE_S1N, CL, JJ, NB, RR>(d.x, d.w_tc, d.bias, d.y, d.B, d.H, d.W, d.Cout, st, stream)     \
+              : (int)cudaErrorMemoryAllocation;                                                                  \
+    }                                                                                                            \
+    return true;                                                                                                 \
+  }
+  S1N_CASE(0, 1, 4, 2, 112) S1N_CASE(0, 1, 2, 2, 112) S1N_CASE(0, 1, 1, 2, 112)
+  S1N_CASE(0, 2, 4, 2, 112) S1N_CASE(0, 2, 2, 2, 112) S1N_CASE(0, 2, 1, 2, 112)
+  S1N_CASE(1, 1, 4, 2, 112) S1N_CASE(1, 1, 2, 2, 112) S1N_CASE(1, 1, 1, 2, 112)
+  S1N_CASE(1, 2, 4, 2, 112) S1N_CASE(1, 2, 2, 2, 112) S1N_CASE(1, 2, 1, 2, 112)
+  S1N_CASE(2, 1, 2, 2, 112) S1N_CASE(2, 1, 1, 2, 112)
+  S1N_CASE(2, 2, 2, 2, 150) S1N_CASE(2, 2, 1, 2, 150)
+  S1N_CASE(3, 1, 2, 2, 200) S1N_CASE(3, 1, 1, 2, 200)
+#undef S1N_CASE
   return false;
 }
 

@@ -99,10 +99,9 @@ class FlowInputQueue:
         self.rng = np.random.default_rng(seed)
         self.shuffle = shuffle
         self.device = device
-        H, W = shape
-        self._pool_b = np.empty((self.capacity, H, W, 1), np.uint8)
-        self._pool_s = np.empty((self.capacity, H, W, 2), np.float32)
-        self._fill = 0
+        # the buffer holds record REFERENCES (file, index) -- the same sliding shuffle window over the record stream as
+        # buffering parsed examples, but each example is parsed exactly once, straight into its pinned batch slot
+        self._pool = []
         self._cursor = (0, 0)                                                   # (file, record)
         self._q = queue.Queue(maxsize=prefetch)
         self._stop = False
@@ -111,34 +110,31 @@ class FlowInputQueue:
         self._thread = threading.Thread(target=self._producer, daemon=True)     # num_preprocess_threads = 1 (reference :34)
         self._thread.start()
 
-    def _next_record(self, b, s):
+    def _next_ref(self):
         fi, ri = self._cursor
         while ri >= len(self.files[fi]):
             fi, ri = (fi + 1) % len(self.files), 0
-        self.files[fi].read_into(ri, b, s)
         self._cursor = (fi, ri + 1)
+        return fi, ri
 
     def _producer(self):
         H, W = self.shape
         try:
             while not self._stop:
                 want = self.capacity if self.shuffle else self.B
-                while self._fill < want:
-                    self._next_record(self._pool_b[self._fill], self._pool_s[self._fill])
-                    self._fill += 1
+                while len(self._pool) < want:
+                    self._pool.append(self._next_ref())
                 hb = torch.empty((self.B, H, W, 1), dtype=torch.uint8, pin_memory=self._cuda)
                 hs = torch.empty((self.B, H, W, 2), dtype=torch.float32, pin_memory=self._cuda)
                 nb, ns = hb.numpy(), hs.numpy()
                 for i in range(self.B):
-                    j = int(self.rng.integers(0, self._fill)) if self.shuffle else 0
-                    nb[i], ns[i] = self._pool_b[j], self._pool_s[j]
-                    if self.shuffle:                        # swap-remove: the last buffered example takes slot j
-                        self._fill -= 1
-                        self._pool_b[j], self._pool_s[j] = self._pool_b[self._fill], self._pool_s[self._fill]
+                    if self.shuffle:                        # swap-remove a uniformly drawn buffered example
+                        j = int(self.rng.integers(0, len(self._pool)))
+                        self._pool[j], self._pool[-1] = self._pool[-1], self._pool[j]
+                        fi, ri = self._pool.pop()
                     else:                                   # FIFO
-                        self._fill -= 1
-                        self._pool_b[:self._fill] = self._pool_b[1:self._fill + 1]
-                        self._pool_s[:self._fill] = self._pool_s[1:self._fill + 1]
+                        fi, ri = self._pool.pop(0)
+                    self.files[fi].read_into(ri, nb[i], ns[i])
                 self._q.put((hb, hs))
         except BaseException as e:                          # surface parser errors in the consumer
             self._q.put(e)

@@ -208,6 +208,14 @@ S1P_CASES = [
     ("s2_ragged_even_c16", 1, 38, 50, 16, 32, 2, 1, 0, False, None, False),
     ("s2_many_tiles", 40, 64, 64, 8, 16, 2, 1, 0, False, None, False),
     ("s2_many_tiles_c32", 80, 32, 32, 32, 64, 2, 1, 0, False, None, False),
+    # data-gradient convs of the backward pass: no prologue, Cout = C or 2C (conv_s2t.cu MODE_S1N)
+    ("s1n_c8_n8", 2, 32, 64, 8, 8, 1, 0, 0, False, None, False),
+    ("s1n_c8_n16", 40, 32, 64, 8, 16, 1, 0, 0, False, None, False),
+    ("s1n_c16_n16", 2, 32, 64, 16, 16, 1, 0, 0, False, None, False),
+    ("s1n_c16_n32_ragged", 2, 23, 41, 16, 32, 1, 0, 0, False, None, False),
+    ("s1n_c32_n32", 3, 32, 64, 32, 32, 1, 0, 0, False, None, False),
+    ("s1n_c32_n64", 40, 32, 32, 32, 64, 1, 0, 0, False, None, False),
+    ("s1n_c64_n64", 3, 32, 64, 64, 64, 1, 0, 0, False, None, False),
 ]
 
 
