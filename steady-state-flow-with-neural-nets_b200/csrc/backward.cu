@@ -201,7 +201,19 @@ __global__ void __launch_bounds__(BW_THREADS) k_bias_grad_v8(const __nv_bfloat16
   const int c = threadIdx.x % nc, rg = threadIdx.x / nc;
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (rg < per) {
-    for (long long pp = (long long)blockIdx.x * per + rg; pp < npix; pp += (long long)gridDim.x * per) {
+    const long long step = (long long)gridDim.x * per;
+    long long pp = (long long)blockIdx.x * per + rg;
+    for (; pp + 3 * step < npix; pp += 4 * step) {      // four independent 16-byte loads in flight
+      bf16x8 v0, v1, v2, v3;
+      ld8(v0, dY + pp * N + c * 8);
+      ld8(v1, dY + (pp + step) * N + c * 8);
+      ld8(v2, dY + (pp + 2 * step) * N + c * 8);
+      ld8(v3, dY + (pp + 3 * step) * N + c * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        s[j] += (__bfloat162float(v0.h[j]) + __bfloat162float(v1.h[j])) + (__bfloat162float(v2.h[j]) + __bfloat162float(v3.h[j]));
+    }
+    for (; pp < npix; pp += step) {
       bf16x8 v;
       ld8(v, dY + pp * N + c * 8);
 #pragma unroll
@@ -248,10 +260,29 @@ __global__ void k_tanh_l2_bwd(const float* __restrict__ p, const float* __restri
 }
 
 // ---- deterministic second stage: out[i] = sum_s partial[s][i]
-__global__ void k_reduce_partials(const float* __restrict__ partial, float* __restrict__ out, long long n, int S) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+// block = 32 outputs x 8 split lanes: lane y adds partials y, y+8, .. (4 loads in flight), then the 8 lane sums are
+// added in a fixed order -- the result does not depend on the launch geometry of stage 1 beyond S itself.
+__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ partial, float* __restrict__ out, long long n, int S) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + tx;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (i < n) {
+    int k = ty;
+    for (; k + 24 < S; k += 32) {
+      a0 += partial[(long long)k * n + i];
+      a1 += partial[(long long)(k + 8) * n + i];
+      a2 += partial[(long long)(k + 16) * n + i];
+      a3 += partial[(long long)(k + 24) * n + i];
+    }
+    for (; k < S; k += 8) a0 += partial[(long long)k * n + i];
+  }
+  sm[ty][tx] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (ty == 0 && i < n) {
     float s = 0.f;
-    for (int k = 0; k < S; ++k) s += partial[(long long)k * n + i];
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += sm[y][tx];
     out[i] = s;
   }
 }
@@ -419,7 +450,7 @@ __global__ void __launch_bounds__(256) k_wgrad_cin1(const __nv_bfloat16* __restr
 }
 
 static int reduce_partials(const float* partial, float* out, long long n, int S, cudaStream_t s) {
-  k_reduce_partials<<<bw_grid(n), BW_THREADS, 0, s>>>(partial, out, n, S);
+  k_reduce_partials<<<(unsigned)((n + 31) / 32), 256, 0, s>>>(partial, out, n, S);
   count_launch();
   return check_launch("k_reduce_partials");
 }
@@ -471,11 +502,11 @@ int tanh_l2_bwd(const float* p, const float* t, float* loss, void* dpre, long lo
 
 long long bias_grad_workspace(long long npix, int N) {
   (void)npix;
-  return (long long)148 * 2 * N;
+  return (long long)148 * 4 * N;
 }
 int bias_grad(const void* dY, float* db, float* workspace, long long npix, int N, cudaStream_t s) {
   FN_REQUIRE(N >= 1 && N <= BW_THREADS, FN_E_UNSUPPORTED, "bias_grad: N=%d out of range", N);
-  const int S = 148 * 2;
+  const int S = 148 * 4;
   if ((N & 7) == 0) k_bias_grad_v8<<<S, BW_THREADS, 0, s>>>((const __nv_bfloat16*)dY, workspace, npix, N);
   else k_bias_grad<<<S, BW_THREADS, 0, s>>>((const __nv_bfloat16*)dY, workspace, npix, N);
   count_launch();
