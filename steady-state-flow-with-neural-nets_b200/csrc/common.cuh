@@ -4,6 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <utility>
 
 #include "flownet.h"
 
@@ -22,6 +25,33 @@ int check_launch(const char* what);
       return (code);                       \
     }                                      \
   } while (0)
+
+// ---- programmatic dependent launch: a kernel launched with launch_pdl() may become resident while its predecessor in
+// the stream is still running; everything it does before pdl_wait() (barrier init, TMEM allocation) overlaps the
+// predecessor's tail, and nothing before pdl_wait() may touch global memory.  pdl_launch_dependents() comes AFTER the
+// wait, so at most one kernel runs ahead.  Both instructions are no-ops in a kernel launched the ordinary way.
+bool pdl_enabled();        // env FLOWNET_PDL=1 (default off: no measurable gain inside the CUDA graph)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+#endif
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -202,6 +202,8 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
     }
     __syncwarp();
   }
+  pdl_wait();                  // everything above overlapped the previous kernel's tail; global memory from here on
+  pdl_launch_dependents();
   for (int i = tid; i < CF::N; i += THREADS) {
     float bv = i < p.Cout ? __ldg(p.bias + i) : 0.f;
     if (GATE && i >= CF::F) bv *= 0.5f;
@@ -470,7 +472,7 @@ static int launch(const fn_conv_desc& d, int* status, cudaStream_t stream) {
     configured = true;
   }
   int grid = p.ntiles < 148 ? p.ntiles : 148;
-  kern<<<grid, THREADS, CF::SMEM, stream>>>(p);
+  launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)CF::SMEM, stream, p);
   count_launch();
   return check_launch("k_conv_s1d");
 }

@@ -205,6 +205,8 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
     }
     __syncwarp();
   }
+  pdl_wait();                  // everything above overlapped the previous kernel's tail; global memory from here on
+  pdl_launch_dependents();
   for (int i = tid; i < Cfg::N; i += SP_THREADS) {
     float bv = i < p.Cout ? __ldg(p.bias + i) : 0.f;
     if (GATE && i >= Cfg::F) bv *= 0.5f;
@@ -508,7 +510,7 @@ static int launch_s1p(const fn_conv_desc& d, cudaStream_t stream) {
   if (per_sm < 1) per_sm = 1;
   int grid = 148 * per_sm;
   if (grid > p.ntiles) grid = p.ntiles;
-  kern<<<grid, SP_THREADS, Cfg::SMEM, stream>>>(p);
+  launch_pdl(kern, dim3(grid), dim3(SP_THREADS), (size_t)Cfg::SMEM, stream, p);
   count_launch();
   return check_launch("k_conv_s1p");
 }

@@ -167,6 +167,8 @@ __global__ void __launch_bounds__(THREADS) k_conv_s2t(const __grid_constant__ Pa
     }
     __syncwarp();
   }
+  pdl_wait();                  // everything above overlapped the previous kernel's tail; global memory from here on
+  pdl_launch_dependents();
   for (int i = tid; i < CF::N; i += THREADS) sbias[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -358,7 +360,7 @@ static int launch(const void* x, const void* wpk, const float* bias, void* y, in
   if (per_sm < 1) per_sm = 1;
   int grid = 148 * per_sm;
   if (grid > p.ntiles) grid = p.ntiles;
-  kern<<<grid, THREADS, CF::SMEM, stream>>>(p);
+  launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)CF::SMEM, stream, p);
   count_launch();
   return check_launch("k_conv_s2t");
 }
