@@ -270,15 +270,16 @@ static int launch_direct(const fn_conv_desc& d, cudaStream_t stream) {
   return check_launch("k_direct3x3");
 }
 
-// Head of the network, 1 channel -> 8: a CTA stages an 8 x 128 pixel tile (+halo) of the boundary image as
-// fp32 in shared memory; each thread produces 4 horizontally adjacent pixels x 8 channels (64 contiguous
-// output bytes), so the 2-byte inputs are read once and the 16 B/pixel output stream is fully coalesced.
+// Head of the network, 1 channel -> 8 (first res_block conv_1, flow_architecture.py:132-133 on the boundary): a CTA
+// stages an 8 x 128 pixel tile (+halo) of the boundary image as fp32 in shared memory, all loads issued before the
+// first use.  A thread produces the pixels lane, lane+32, lane+64, lane+96 of one tile row, so shared-memory reads are
+// conflict-free and every warp store covers 512 contiguous bytes.
 __global__ void __launch_bounds__(256) k_head3x3_c8(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B,
                                                     int H, int W, int tiles_x, int tiles_y) {
-  __shared__ float ws[72 + 8];
+  __shared__ __align__(16) float ws[72 + 8];
   __shared__ float tile[10][132];
-  for (int i = threadIdx.x; i < 72; i += 256) ws[i] = __bfloat162float(w[i]);
+  if (threadIdx.x < 72) ws[threadIdx.x] = __bfloat162float(w[threadIdx.x]);
   if (threadIdx.x < 8) ws[72 + threadIdx.x] = bias[threadIdx.x];
   int t = blockIdx.x;
   const int tx = t % tiles_x;
@@ -286,22 +287,27 @@ __global__ void __launch_bounds__(256) k_head3x3_c8(const __nv_bfloat16* __restr
   const int ty = t % tiles_y;
   const int b = t / tiles_y;
   const int y0 = ty * 8, x0 = tx * 128;
-  for (int i = threadIdx.x; i < 10 * 130; i += 256) {
-    const int r = i / 130, c = i - r * 130;
-    const int iy = y0 + r - 1, ix = x0 + c - 1;
-    float v = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __bfloat162float(x[((size_t)b * H + iy) * W + ix]);
-    tile[r][c] = v;
+  {
+    float v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      const int r = i / 130, c = i - r * 130;
+      const int iy = y0 + r - 1, ix = x0 + c - 1;
+      v[k] = 0.f;
+      if (i < 1300 && iy >= 0 && iy < H && ix >= 0 && ix < W) v[k] = __bfloat162float(x[((size_t)b * H + iy) * W + ix]);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      const int r = i / 130, c = i - r * 130;
+      if (i < 1300) tile[r][c] = v[k];
+    }
   }
   __syncthreads();
-  const int row = threadIdx.x >> 5, cg = threadIdx.x & 31;
-  const int oy = y0 + row, ox = x0 + 4 * cg;
-  if (oy >= H || ox >= W) return;
-  float in[3][6];
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int c = 0; c < 6; ++c) in[r][c] = tile[row + r][4 * cg + c];
+  const int row = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int oy = y0 + row;
+  if (oy >= H) return;
   float acc[4][8];
 #pragma unroll
   for (int px = 0; px < 4; ++px)
@@ -310,21 +316,27 @@ __global__ void __launch_bounds__(256) k_head3x3_c8(const __nv_bfloat16* __restr
 #pragma unroll
   for (int di = 0; di < 3; ++di)
 #pragma unroll
-    for (int dj = 0; dj < 3; ++dj)
+    for (int dj = 0; dj < 3; ++dj) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&ws[(di * 3 + dj) * 8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&ws[(di * 3 + dj) * 8 + 4]);
 #pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        const float wt = ws[(di * 3 + dj) * 8 + n];
-#pragma unroll
-        for (int px = 0; px < 4; ++px) acc[px][n] = fmaf(in[di][px + dj], wt, acc[px][n]);
+      for (int px = 0; px < 4; ++px) {
+        const float v = tile[row + di][lane + 32 * px + dj];
+        acc[px][0] = fmaf(v, w0.x, acc[px][0]); acc[px][1] = fmaf(v, w0.y, acc[px][1]);
+        acc[px][2] = fmaf(v, w0.z, acc[px][2]); acc[px][3] = fmaf(v, w0.w, acc[px][3]);
+        acc[px][4] = fmaf(v, w1.x, acc[px][4]); acc[px][5] = fmaf(v, w1.y, acc[px][5]);
+        acc[px][6] = fmaf(v, w1.z, acc[px][6]); acc[px][7] = fmaf(v, w1.w, acc[px][7]);
       }
-  __nv_bfloat16* yo = y + (((size_t)b * H + oy) * W + ox) * 8;
+    }
+  __nv_bfloat16* yo = y + (((size_t)b * H + oy) * W + x0) * 8;
 #pragma unroll
   for (int px = 0; px < 4; ++px) {
-    if (ox + px < W) {
+    const int ox = lane + 32 * px;
+    if (x0 + ox < W) {
       bf16x8 o;
 #pragma unroll
       for (int n = 0; n < 8; ++n) o.h[n] = __float2bfloat16(acc[px][n]);
-      *reinterpret_cast<uint4*>(yo + px * 8) = o.v;
+      *reinterpret_cast<uint4*>(yo + (size_t)ox * 8) = o.v;
     }
   }
 }
@@ -339,6 +351,88 @@ static int launch_head_c8(const fn_conv_desc& d, cudaStream_t stream) {
   return check_launch("k_head3x3_c8");
 }
 
+// Tail of the network, 8 channels -> 2 + tanh, fp32 out (last_conv, flow_architecture.py:242-243): the same tiling;
+// the 8 x 128 (+halo) tile is staged as it is in memory (one 16-byte bf16 vector per pixel), a thread owns four pixels
+// 32 apart, reads each tap's 16 weights once for the four of them, and writes float2 per pixel (256 contiguous bytes
+// per warp store).  A third of the instructions of the one-thread-per-pixel kernel above.
+__global__ void __launch_bounds__(256) k_tail3x3_c8(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                    const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W,
+                                                    int tiles_x, int tiles_y) {
+  __shared__ __align__(16) float ws[144 + 4];
+  __shared__ uint4 tile[10][130];
+  if (threadIdx.x < 144) ws[threadIdx.x] = __bfloat162float(w[threadIdx.x]);        // [tap][c][n]
+  if (threadIdx.x < 2) ws[144 + threadIdx.x] = bias[threadIdx.x];
+  int t = blockIdx.x;
+  const int tx = t % tiles_x;
+  t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int y0 = ty * 8, x0 = tx * 128;
+  {
+    uint4 v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      const int r = i / 130, c = i - r * 130;
+      const int iy = y0 + r - 1, ix = x0 + c - 1;
+      v[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < 1300 && iy >= 0 && iy < H && ix >= 0 && ix < W)
+        v[k] = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + iy) * W + ix) * 8));
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      const int r = i / 130, c = i - r * 130;
+      if (i < 1300) tile[r][c] = v[k];
+    }
+  }
+  __syncthreads();
+  const int row = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int oy = y0 + row;
+  if (oy >= H) return;
+  float a0[4], a1[4];
+#pragma unroll
+  for (int px = 0; px < 4; ++px) { a0[px] = ws[144]; a1[px] = ws[145]; }
+#pragma unroll
+  for (int di = 0; di < 3; ++di)
+#pragma unroll
+    for (int dj = 0; dj < 3; ++dj) {
+      float wt[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 f = *reinterpret_cast<const float4*>(&ws[(di * 3 + dj) * 16 + 4 * q]);
+        wt[4 * q] = f.x; wt[4 * q + 1] = f.y; wt[4 * q + 2] = f.z; wt[4 * q + 3] = f.w;
+      }
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        bf16x8 in;
+        in.v = tile[row + di][lane + 32 * px + dj];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float v = __bfloat162float(in.h[c]);
+          a0[px] = fmaf(v, wt[2 * c], a0[px]);
+          a1[px] = fmaf(v, wt[2 * c + 1], a1[px]);
+        }
+      }
+    }
+  float* yo = y + (((size_t)b * H + oy) * W + x0) * 2;
+#pragma unroll
+  for (int px = 0; px < 4; ++px) {
+    const int ox = lane + 32 * px;
+    if (x0 + ox < W) *reinterpret_cast<float2*>(yo + (size_t)ox * 2) = make_float2(tanhf(a0[px]), tanhf(a1[px]));
+  }
+}
+
+static int launch_tail_c8(const fn_conv_desc& d, cudaStream_t stream) {
+  const int tiles_x = (d.W + 127) / 128, tiles_y = (d.H + 7) / 8;
+  const long long grid = (long long)d.B * tiles_x * tiles_y;
+  k_tail3x3_c8<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d.x),
+                                                   reinterpret_cast<const __nv_bfloat16*>(d.w), d.bias,
+                                                   reinterpret_cast<float*>(d.y), d.B, d.H, d.W, tiles_x, tiles_y);
+  count_launch();
+  return check_launch("k_tail3x3_c8");
+}
+
 // returns true (and sets rc) if a specialised head/tail kernel took the launch
 static bool try_direct(const fn_conv_desc& d, cudaStream_t stream, int& rc) {
   if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_NONE || d.skip || d.keep_prob < 1.0f) return false;
@@ -349,7 +443,7 @@ static bool try_direct(const fn_conv_desc& d, cudaStream_t stream, int& rc) {
     if (d.Cout == 32) { rc = launch_direct<1, 32, false>(d, stream); return true; }
   }
   if (d.epilogue == FN_EPI_TANH && d.Cout == 2) {
-    if (d.Cin == 8) { rc = launch_direct<8, 2, true>(d, stream); return true; }
+    if (d.Cin == 8) { rc = launch_tail_c8(d, stream); return true; }
     if (d.Cin == 16) { rc = launch_direct<16, 2, true>(d, stream); return true; }
     if (d.Cin == 32) { rc = launch_direct<32, 2, true>(d, stream); return true; }
   }
