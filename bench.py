@@ -190,10 +190,12 @@ def run_train(args, rank, world, dist, native, arch, flow_net):
     flow_net.begin_training()
 
     def step():
-        p = flow_net.inference(boundary, 1.0)
+        step.k += 1
+        p = flow_net.inference(boundary, args.keep_prob, dropout_seed=step.k)
         err = flow_net.loss_image_train(p, sflow)
         return flow_net.train(err, 1e-4)
 
+    step.k = 0
     for _ in range(max(args.warmup, 2)):
         step()
     if world > 1:
@@ -220,7 +222,7 @@ def run_train(args, rank, world, dist, native, arch, flow_net):
             "steps": args.steps, "warmup": max(args.warmup, 2), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic boundaries and targets",
             "config": {"workload": "configs[2]: training step, global batch 256, 128x256, L2 loss + TF1 Adam, "
-                                   "keep_prob 1.0; tcgen05 dgrad + wgrad",
+                                   "keep_prob %.2f; tcgen05 fwd + dgrad + wgrad" % args.keep_prob,
                        "batch_per_gpu": B, "parallelism": f"dp{world}, one flat fp32 gradient all-reduce"},
             "gpu_launches": native.launch_count() - n0, "loss": float(loss.item()),
             "roofline": {"bound": "tensor", "achieved": v * 8.519e9 / 1e12, "peak": load_peaks()["tc_sustained"],
@@ -238,6 +240,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="inference", choices=["inference", "train"],
                     help="train: BASELINE configs[2], fwd+bwd+Adam at global batch 256 (extra line, not the headline)")
+    ap.add_argument("--keep-prob", type=float, default=1.0,
+                    help="train mode: dropout keep probability (1.0 = the parity setting; the reference trains with 0.7)")
     ap.add_argument("--layers-out", default=None, help="write the per-layer roofline table (JSON) here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

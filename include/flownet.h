@@ -46,7 +46,11 @@ enum fn_epilogue {
   FN_EPI_BIAS     = 0,  /* y = acc + bias                        -> bf16 [.,Cout]      (conv_layer :64-65) */
   FN_EPI_GATE_RES = 1,  /* y = sc(res) + (u+bu)*sigmoid(v+bv)    -> bf16 [.,Cout/2]    (res_block :149-165) */
   FN_EPI_RES      = 2,  /* y = sc(res) + acc + bias              -> bf16 [.,Cout]      (res_block :147,:153-165) */
-  FN_EPI_TANH     = 3   /* y = tanh(acc + bias)                  -> fp32 [.,Cout]      (conv_res :242-243) */
+  FN_EPI_TANH     = 3,  /* y = tanh(acc + bias)                  -> fp32 [.,Cout]      (conv_res :242-243) */
+  /* backward of the gate, fused with the recomputation of its input: with [u|v] = acc + bias and g = res (the
+   * gradient of the block output, bf16 [.,Cout/2]):  y = [g*sigmoid(v) | g*u*sigmoid(v)*(1-sigmoid(v))] -> bf16 [.,Cout],
+   * the gradient of the pre-gate tensor (adjoint of :150-151).  tcgen05 kernels only (concat_elu prologue, stride 1). */
+  FN_EPI_GATE_BWD = 4
 };
 
 /* implementation selector: the tensor-core kernels are the product; the CUDA-core kernels
@@ -121,6 +125,8 @@ int         fn_last_used_tcgen05(void);
 
 /* tf.nn.conv2d + bias_add (+ fused neighbours)          flow_architecture.py:57-68, 129-165 */
 int fn_conv_fwd(const fn_conv_desc* d, void* stream);
+/* 1 if fn_conv_fwd(d) would run on the tensor cores (pointers are not dereferenced, only tested for NULL), else 0 */
+int fn_conv_fwd_has_tcgen05(const fn_conv_desc* d);
 /* tf.nn.conv2d_transpose + bias_add                      flow_architecture.py:70-87 */
 int fn_tconv_fwd(const fn_tconv_desc* d, void* stream);
 /* size in bytes of / packer for the tensor-core weight image of a conv (host-side helper

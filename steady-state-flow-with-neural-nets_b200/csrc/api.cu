@@ -63,12 +63,16 @@ static int validate_conv(const fn_conv_desc& d) {
   FN_REQUIRE(d.stride == 1 || d.stride == 2, FN_E_UNSUPPORTED, "fn_conv_fwd: stride %d (only 1 and 2)", d.stride);
   FN_REQUIRE(d.prologue >= FN_PRO_NONE && d.prologue <= FN_PRO_RELU, FN_E_INVAL, "fn_conv_fwd: bad prologue %d",
              d.prologue);
-  FN_REQUIRE(d.epilogue >= FN_EPI_BIAS && d.epilogue <= FN_EPI_TANH, FN_E_INVAL, "fn_conv_fwd: bad epilogue %d",
+  FN_REQUIRE(d.epilogue >= FN_EPI_BIAS && d.epilogue <= FN_EPI_GATE_BWD, FN_E_INVAL, "fn_conv_fwd: bad epilogue %d",
              d.epilogue);
   FN_REQUIRE(d.impl >= FN_IMPL_AUTO && d.impl <= FN_IMPL_TCGEN05, FN_E_INVAL, "fn_conv_fwd: bad impl %d", d.impl);
   FN_REQUIRE(d.Cin == 1 || (d.Cin % 8) == 0, FN_E_ALIGN, "fn_conv_fwd: Cin=%d must be 1 or a multiple of 8", d.Cin);
   FN_REQUIRE(aligned16(d.x) && aligned16(d.y) && aligned16(d.w), FN_E_ALIGN, "fn_conv_fwd: x/y/w must be 16-byte aligned");
-  if (d.epilogue == FN_EPI_GATE_RES)
+  if (d.epilogue == FN_EPI_GATE_BWD)
+    FN_REQUIRE(d.res && d.Cres == d.Cout / 2 && d.RH == d.H && d.RW == d.W && !d.res_pool && d.stride == 1 && !d.skip &&
+                   d.impl != FN_IMPL_SIMT,
+               FN_E_UNSUPPORTED, "fn_conv_fwd: gate-backward epilogue needs res = gradient [B,H,W,Cout/2], stride 1, no skip, tcgen05");
+  if (d.epilogue == FN_EPI_GATE_RES || d.epilogue == FN_EPI_GATE_BWD)
     FN_REQUIRE((d.Cout % 16) == 0, FN_E_ALIGN, "fn_conv_fwd: gated Cout=%d must be a multiple of 16", d.Cout);
   else if (d.epilogue != FN_EPI_TANH)
     FN_REQUIRE((d.Cout % 8) == 0, FN_E_ALIGN, "fn_conv_fwd: Cout=%d must be a multiple of 8", d.Cout);
@@ -115,6 +119,12 @@ int fn_conv_fwd(const fn_conv_desc* d, void* stream) {
   FN_REQUIRE(d->impl != FN_IMPL_TCGEN05, FN_E_UNSUPPORTED, "fn_conv_fwd: no tcgen05 kernel for this shape: %s", why);
   note_tcgen05(false);
   return conv_fwd_simt(*d, s);
+}
+
+int fn_conv_fwd_has_tcgen05(const fn_conv_desc* d) {
+  if (d == nullptr || validate_conv(*d) != 0 || d->impl == FN_IMPL_SIMT) return 0;
+  const char* why = "";
+  return conv_tc_supported(*d, &why) ? 1 : 0;
 }
 
 int fn_tconv_fwd(const fn_tconv_desc* d, void* stream) {

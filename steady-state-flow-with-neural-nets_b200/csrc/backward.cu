@@ -131,14 +131,19 @@ __global__ void __launch_bounds__(BW_THREADS) k_prologue_bwd_v8(const __nv_bfloa
     ld8(a0, dA + p * mult * C + c);
     if (mult == 2) ld8(a1, dA + p * mult * C + C + c);
     if (accumulate) ld8(old, dx + p * C + c);
+    float sc0[8], sc1[8];
+    if (drop) {
+      dropout_scale8(seed, (unsigned long long)(p * mult * C + c), keep_prob, sc0);
+      if (mult == 2) dropout_scale8(seed, (unsigned long long)(p * mult * C + C + c), keep_prob, sc1);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float xf = __bfloat162float(xv.h[j]);
       float f0 = __bfloat162float(a0.h[j]);
       float f1 = mult == 2 ? __bfloat162float(a1.h[j]) : 0.f;
       if (drop) {
-        f0 *= dropout_scale(seed, (unsigned long long)(p * mult * C + c + j), keep_prob);
-        if (mult == 2) f1 *= dropout_scale(seed, (unsigned long long)(p * mult * C + C + c + j), keep_prob);
+        f0 *= sc0[j];
+        if (mult == 2) f1 *= sc1[j];
       }
       float d;
       switch (kind) {

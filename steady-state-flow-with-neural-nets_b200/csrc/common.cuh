@@ -96,10 +96,27 @@ __host__ __device__ inline uint64_t mix64(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
+// One hash serves 4 elements (16 bits each), so an aligned group of 8 consecutive elements -- what every vector
+// kernel handles at a time -- costs three mix64 instead of sixteen.  Element idx: group q = idx/8, j = idx%8;
+// h1 = mix64(seed ^ mix64(q)), h2 = mix64(h1); u = 16-bit field j%4 of (j < 4 ? h1 : h2); keep iff u < keep_prob*65536.
+__host__ __device__ inline uint32_t dropout_threshold(float keep_prob) { return (uint32_t)(keep_prob * 65536.0f); }
 __host__ __device__ inline float dropout_scale(uint64_t seed, uint64_t idx, float keep_prob) {
-  uint64_t h = mix64(seed ^ mix64(idx));
-  float u = (float)(h >> 40) * (1.0f / 16777216.0f);
-  return u < keep_prob ? 1.0f / keep_prob : 0.0f;
+  uint64_t h = mix64(seed ^ mix64(idx >> 3));
+  if (idx & 4) h = mix64(h);
+  const uint32_t u = (uint32_t)(h >> (16 * (idx & 3))) & 0xFFFFu;
+  return u < dropout_threshold(keep_prob) ? 1.0f / keep_prob : 0.0f;
+}
+// the 8 scales of the aligned group starting at element idx8 (idx8 % 8 == 0)
+__host__ __device__ inline void dropout_scale8(uint64_t seed, uint64_t idx8, float keep_prob, float (&sc)[8]) {
+  const uint64_t h1 = mix64(seed ^ mix64(idx8 >> 3));
+  const uint64_t h2 = mix64(h1);
+  const uint32_t thr = dropout_threshold(keep_prob);
+  const float inv = 1.0f / keep_prob;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = ((uint32_t)(h1 >> (16 * j)) & 0xFFFFu) < thr ? inv : 0.0f;
+    sc[4 + j] = ((uint32_t)(h2 >> (16 * j)) & 0xFFFFu) < thr ? inv : 0.0f;
+  }
 }
 
 union bf16x8 {

@@ -40,6 +40,9 @@ struct Params {
   int B, H, W;
   int tiles_u, tiles_v, ntiles;
   int Cout, res_mode, Cres, RH, RW, res_pool;
+  int gate_bwd;                        // FN_EPI_GATE_BWD (see conv_s1p.cu)
+  float keep_prob;                     // < 1: dropout on the prologue output (training)
+  unsigned long long dropout_seed;
 };
 
 template <int CLOG, int J, bool GATE, bool SKIP, bool TR, int NST>
@@ -114,6 +117,49 @@ __device__ __forceinline__ void transform_tile(uint32_t stage, uint32_t planes, 
       const float t = __expf(-fabsf(v)) - 1.f;
       o0.h[j] = __float2bfloat16(v > 0.f ? v : t);
       o1.h[j] = __float2bfloat16(v > 0.f ? t : -v);
+    }
+    const uint32_t d0 = planes + (uint32_t)(ch * CF::PPAD + pp) * 16u;
+    sts128(d0, o0.v);
+    sts128(d0 + (uint32_t)(CF::CH * CF::PPAD * 16), o1.v);
+  }
+}
+
+// with tf.nn.dropout on the concat_elu output (training): same mask as every other kernel, see conv_s1p.cu
+template <typename CF, bool TR>
+__device__ __forceinline__ void transform_tile_dropout(uint32_t stage, uint32_t planes, int tid, const Params& p, int b, int y0,
+                                                       int x0) {
+  constexpr int ITEMS = CF::P * CF::CH;
+  constexpr int SH = CF::CH == 8 ? 3 : 4;
+  for (int idx = tid; idx < ITEMS; idx += 256) {
+    const int ch = idx & (CF::CH - 1);
+    const int sp = idx >> SH;
+    int pu, pv;
+    if (TR) { pu = sp / CF::PV; pv = sp - pu * CF::PV; }
+    else { pv = sp / CF::PU; pu = sp - pv * CF::PU; }
+    const int pp = pv * CF::PU + pu;
+    // plane axes (pv, pu) are image (y, x), or (x, y) in the transposed orientation
+    const int iy = (TR ? pu : pv) + y0 - 1, ix = (TR ? pv : pu) + x0 - 1;
+    const unsigned long long base = (((unsigned long long)b * p.H + iy) * p.W + ix) * (2 * CF::C) + ch * 8;
+    const bool inside = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+    bf16x8 in, o0, o1;
+    in.v = lds128(stage + (uint32_t)idx * 16u);
+    float sc0[8], sc1[8];
+    if (inside) {
+      dropout_scale8(p.dropout_seed, base, p.keep_prob, sc0);
+      dropout_scale8(p.dropout_seed, base + CF::C, p.keep_prob, sc1);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = __bfloat162float(in.h[j]);
+      const float t = __expf(-fabsf(v)) - 1.f;
+      float a0 = __bfloat162float(__float2bfloat16(v > 0.f ? v : t));
+      float a1 = __bfloat162float(__float2bfloat16(v > 0.f ? t : -v));
+      if (inside) {
+        a0 *= sc0[j];
+        a1 *= sc1[j];
+      }
+      o0.h[j] = __float2bfloat16(a0);
+      o1.h[j] = __float2bfloat16(a1);
     }
     const uint32_t d0 = planes + (uint32_t)(ch * CF::PPAD + pp) * 16u;
     sts128(d0, o0.v);
@@ -281,7 +327,10 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
       // ---- transform
       ok = ok && ptx::mbar_wait(bar(SB_X), par_it);
       if (!ok) atomicCAS(p.status, 0, 34);
-      transform_tile<CF, TR>(sbase + CF::OFF_STAGE, sbase + CF::OFF_PLANES, tid);
+      if (p.keep_prob < 1.0f)
+        transform_tile_dropout<CF, TR>(sbase + CF::OFF_STAGE, sbase + CF::OFF_PLANES, tid, p, b, TR ? u0 : v0, TR ? v0 : u0);
+      else
+        transform_tile<CF, TR>(sbase + CF::OFF_STAGE, sbase + CF::OFF_PLANES, tid);
       if (SKIP) {
         ok = ok && ptx::mbar_wait(bar(SB_S), par_it);
         if (!ok) atomicCAS(p.status, 0, 35);
@@ -356,6 +405,22 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
           if (GATE) {
             float a[8], g[8];
             ptx::tmem_ld8x2(col0 + c0, col0 + CF::F + c0, a, g);
+            if (p.gate_bwd) {          // du = gy*s, dv = gy*u*s*(1-s), gy = the staged "res" tile
+              bf16x8 gy, du, dv;
+              gy.v = lds128(sbase + CF::OFF_STAGE + (res_pix * CF::F + (uint32_t)c0) * 2u);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float sg = fmaf(tanh_approx(fmaf(g[i], 0.5f, sbias[CF::F + c0 + i])), 0.5f, 0.5f);
+                const float gs = __bfloat162float(gy.h[i]) * sg;
+                du.h[i] = __float2bfloat16(gs);
+                dv.h[i] = __float2bfloat16(gs * (a[i] + sbias[c0 + i]) * (1.f - sg));
+              }
+              if (live) {
+                *reinterpret_cast<uint4*>(p.y + pix * (2 * CF::F) + c0) = du.v;
+                *reinterpret_cast<uint4*>(p.y + pix * (2 * CF::F) + CF::F + c0) = dv.v;
+              }
+              continue;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float th = tanh_approx(fmaf(g[i], 0.5f, sbias[CF::F + c0 + i]));
@@ -464,6 +529,9 @@ static int launch(const fn_conv_desc& d, int* status, cudaStream_t stream) {
   p.ntiles = d.B * p.tiles_u * p.tiles_v;
   p.Cout = d.Cout;
   p.Cres = d.Cres; p.RH = d.RH; p.RW = d.RW; p.res_pool = d.res_pool;
+  p.keep_prob = d.keep_prob;
+  p.dropout_seed = d.dropout_seed;
+  p.gate_bwd = d.epilogue == FN_EPI_GATE_BWD ? 1 : 0;
   auto kern = k_conv_s1d<CLOG, J, GATE, SKIP, TR, NST>;
   static bool configured = false;
   if (!configured) {
@@ -485,10 +553,12 @@ int* tc_status_word();
 bool conv_s1d_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc) {
   using namespace s1d;
   rc = 0;
-  if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_CONCAT_ELU || d.keep_prob < 1.0f || d.w_tc == nullptr) return false;
-  const bool gate = d.epilogue == FN_EPI_GATE_RES;
+  if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_CONCAT_ELU || d.w_tc == nullptr) return false;
+  if (d.keep_prob < 1.0f && (d.skip != nullptr || d.dropout_offset != 0)) return false;
+  const bool gate = d.epilogue == FN_EPI_GATE_RES || d.epilogue == FN_EPI_GATE_BWD;
   if (!gate && d.epilogue != FN_EPI_BIAS) return false;
   if (d.Cout != (gate ? 2 * d.Cin : d.Cin)) return false;
+  if (d.epilogue == FN_EPI_GATE_BWD && (d.res == nullptr || d.res_pool || d.Cres != d.Cin)) return false;
   const bool skip = d.skip != nullptr;
   if (skip && (gate || d.Cskip != d.Cin)) return false;
   const int clog = d.Cin == 64 ? 3 : d.Cin == 128 ? 4 : -1;

@@ -42,6 +42,9 @@ struct SpParams {
   int Cout;                            // real accumulator width (bias entries)
   int res_mode;                        // 0 none, 1 staged plain tile (Cres == F), 2 generic global loads
   int Cres, RH, RW, res_pool;
+  int gate_bwd;                        // FN_EPI_GATE_BWD: y = d(pre-gate) [., 2F] from the recomputed [u|v] and g = res
+  float keep_prob;                     // < 1: dropout on the prologue output (training)
+  unsigned long long dropout_seed;
   long long* timing;                   // debug: 8 clock64 stamps per CTA for its third tile (nullptr in production)
   int timing_ctas;
 };
@@ -114,6 +117,46 @@ __device__ __forceinline__ void transform_tile(uint32_t stage, uint32_t planes, 
       const float t = __expf(-fabsf(v)) - 1.f;
       o0.h[j] = __float2bfloat16(v > 0.f ? v : t);
       o1.h[j] = __float2bfloat16(v > 0.f ? t : -v);
+    }
+    const uint32_t d0 = planes + (uint32_t)(ch * Cfg::PPAD + pp) * 16u;
+    sts128(d0, o0.v);
+    sts128(d0 + (uint32_t)(Cfg::CH * Cfg::PPAD * 16), o1.v);
+  }
+}
+
+// the same with tf.nn.dropout on the concat_elu output (flow_architecture.py:144-145; training only): element k of
+// input pixel pidx is scaled by dropout_scale(seed, pidx*2C + k) -- the mask every other kernel of the library uses
+template <typename Cfg>
+__device__ __forceinline__ void transform_tile_dropout(uint32_t stage, uint32_t planes, int tid, const SpParams& p, int b, int y0,
+                                                       int x0) {
+  constexpr int ITEMS = Cfg::P * Cfg::CH;
+  constexpr int SH = Cfg::CH == 1 ? 0 : (Cfg::CH == 2 ? 1 : (Cfg::CH == 4 ? 2 : 3));
+  for (int idx = tid; idx < ITEMS; idx += 128) {
+    const int ch = idx & (Cfg::CH - 1);
+    const int pp = idx >> SH;
+    const int pv = pp / Cfg::PU, pu = pp - pv * Cfg::PU;
+    const int iy = y0 - 1 + pv, ix = x0 - 1 + pu;
+    const unsigned long long base = (((unsigned long long)b * p.H + iy) * p.W + ix) * (2 * Cfg::C) + ch * 8;
+    const bool inside = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+    bf16x8 in, o0, o1;
+    in.v = lds128(stage + (uint32_t)idx * 16u);
+    float sc0[8], sc1[8];
+    if (inside) {
+      dropout_scale8(p.dropout_seed, base, p.keep_prob, sc0);
+      dropout_scale8(p.dropout_seed, base + Cfg::C, p.keep_prob, sc1);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = __bfloat162float(in.h[j]);
+      const float t = __expf(-fabsf(v)) - 1.f;
+      float a0 = __bfloat162float(__float2bfloat16(v > 0.f ? v : t));
+      float a1 = __bfloat162float(__float2bfloat16(v > 0.f ? t : -v));
+      if (inside) {
+        a0 *= sc0[j];
+        a1 *= sc1[j];
+      }
+      o0.h[j] = __float2bfloat16(a0);
+      o1.h[j] = __float2bfloat16(a1);
     }
     const uint32_t d0 = planes + (uint32_t)(ch * Cfg::PPAD + pp) * 16u;
     sts128(d0, o0.v);
@@ -309,7 +352,13 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
       if (it >= 2) ok = ok && ptx::mbar_wait(bar(SB_TF + s), prev); // MMAs of tile it-2 no longer read planes[s]
       if (!ok) atomicCAS(p.status, 0, 11);
       if (stamp) stamp[1] = clock64();
-      transform_tile<Cfg>(sbase + Cfg::OFF_STAGE + s * Cfg::STAGE_BYTES, planes, tid);
+      if (p.keep_prob < 1.0f) {
+        int b, y0, x0;
+        tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, y0, x0);
+        transform_tile_dropout<Cfg>(sbase + Cfg::OFF_STAGE + s * Cfg::STAGE_BYTES, planes, tid, p, b, y0, x0);
+      } else {
+        transform_tile<Cfg>(sbase + Cfg::OFF_STAGE + s * Cfg::STAGE_BYTES, planes, tid);
+      }
       if (SKIP) {
         ok = ok && ptx::mbar_wait(bar(SB_S + s), cur);
         if (!ok) atomicCAS(p.status, 0, 12);
@@ -377,6 +426,23 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
             if (GATE) {
               float a[8], g[8];
               ptx::tmem_ld8x2(col0 + c0, col0 + Cfg::F + c0, a, g);
+              if (p.gate_bwd) {
+                // adjoint of y = u*sigmoid(v): du = gy*s, dv = gy*u*s*(1-s); gy is the staged "res" tile
+                bf16x8 gy, du, dv;
+                gy.v = lds128(sbase + Cfg::OFF_RES + s * Cfg::RES_BYTES + (uint32_t)((v * 8 * J + 8 * j + u) * Cfg::F + c0) * 2u);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float sg = fmaf(tanh_approx(fmaf(g[i], 0.5f, sbias[Cfg::F + c0 + i])), 0.5f, 0.5f);
+                  const float gs = __bfloat162float(gy.h[i]) * sg;
+                  du.h[i] = __float2bfloat16(gs);
+                  dv.h[i] = __float2bfloat16(gs * (a[i] + sbias[c0 + i]) * (1.f - sg));
+                }
+                if (live) {
+                  *reinterpret_cast<uint4*>(p.y + pix * (2 * Cfg::F) + c0) = du.v;
+                  *reinterpret_cast<uint4*>(p.y + pix * (2 * Cfg::F) + Cfg::F + c0) = dv.v;
+                }
+                continue;
+              }
               // u * sigmoid(v) with sigmoid(z) = 0.5 + 0.5 tanh(z/2); the v bias is stored pre-halved
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -494,6 +560,9 @@ static int launch_s1p(const fn_conv_desc& d, cudaStream_t stream) {
   p.ntiles = d.B * p.tiles_u * p.tiles_v;
   p.Cout = d.Cout;
   p.Cres = d.Cres; p.RH = d.RH; p.RW = d.RW; p.res_pool = d.res_pool;
+  p.keep_prob = d.keep_prob;
+  p.dropout_seed = d.dropout_seed;
+  p.gate_bwd = d.epilogue == FN_EPI_GATE_BWD ? 1 : 0;
   tc_timing_buffer(&p.timing, &p.timing_ctas);
 
   auto kern = k_conv_s1p<CLOG, J, GATE, SKIP>;
@@ -518,10 +587,12 @@ static int launch_s1p(const fn_conv_desc& d, cudaStream_t stream) {
 // Returns true if a specialised kernel exists for this launch (and runs it: rc = its return code).
 bool conv_s1p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc) {
   rc = 0;
-  if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_CONCAT_ELU || d.keep_prob < 1.0f || d.w_tc == nullptr) return false;
-  const bool gate = d.epilogue == FN_EPI_GATE_RES;
+  if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_CONCAT_ELU || d.w_tc == nullptr) return false;
+  if (d.keep_prob < 1.0f && (d.skip != nullptr || d.dropout_offset != 0)) return false;   // the dropped operand is the conv input
+  const bool gate = d.epilogue == FN_EPI_GATE_RES || d.epilogue == FN_EPI_GATE_BWD;
   if (!gate && d.epilogue != FN_EPI_BIAS) return false;
   if (d.Cout != (gate ? 2 * d.Cin : d.Cin)) return false;
+  if (d.epilogue == FN_EPI_GATE_BWD && (d.res == nullptr || d.res_pool || d.Cres != d.Cin)) return false;
   const bool skip = d.skip != nullptr;
   if (skip && (gate || d.Cskip != d.Cin)) return false;
   if (d.H < 16) return false;                       // short images use the transposed orientation of k_conv_tc

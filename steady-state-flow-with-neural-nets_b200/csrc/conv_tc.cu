@@ -648,7 +648,19 @@ static bool geom_of_conv(const fn_conv_desc& d, TcGeom& g, const char** why) {
   return true;
 }
 
+bool conv_s1p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1p.cu
+bool conv_s1d_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1d.cu
+
 bool conv_tc_supported(const fn_conv_desc& d, const char** why) {
+  int rc = 0;
+  // the persistent kernels also take the dropout prologue, which the generic kernel below does not
+  if (g_tc_use_s1p && (d.keep_prob < 1.0f || d.epilogue == FN_EPI_GATE_BWD) &&
+      (conv_s1p_try(d, nullptr, true, rc) || conv_s1d_try(d, nullptr, true, rc)))
+    return true;
+  if (d.epilogue == FN_EPI_GATE_BWD) {
+    if (why) *why = "the gate-backward epilogue exists in the persistent kernels only";
+    return false;
+  }
   TcGeom g;
   TcParams p;
   size_t sm;

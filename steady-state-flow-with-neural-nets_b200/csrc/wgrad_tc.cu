@@ -235,11 +235,13 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
         if (p.keep_prob < 1.0f) {     // tf.nn.dropout on the conv input (flow_architecture.py:144-145): same mask as the forward
           const int iy = G::S2 ? 2 * y0 + r : y0 - 1 + r, ix = G::S2 ? 2 * x0 + c : x0 - 1 + c;
           const unsigned long long pidx = ((unsigned long long)b * p.H + iy) * p.W + ix;
+          float sc0[8], sc1[8];
+          dropout_scale8(p.seed, pidx * p.Keff + ch * 8, p.keep_prob, sc0);
+          if (mult == 2) dropout_scale8(p.seed, pidx * p.Keff + p.C + ch * 8, p.keep_prob, sc1);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            o0.h[j] = __float2bfloat16(__bfloat162float(o0.h[j]) * dropout_scale(p.seed, pidx * p.Keff + ch * 8 + j, p.keep_prob));
-            if (mult == 2)
-              o1.h[j] = __float2bfloat16(__bfloat162float(o1.h[j]) * dropout_scale(p.seed, pidx * p.Keff + p.C + ch * 8 + j, p.keep_prob));
+            o0.h[j] = __float2bfloat16(__bfloat162float(o0.h[j]) * sc0[j]);
+            if (mult == 2) o1.h[j] = __float2bfloat16(__bfloat162float(o1.h[j]) * sc1[j]);
           }
         }
         uint32_t dst = planes;

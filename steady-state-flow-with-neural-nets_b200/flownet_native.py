@@ -15,7 +15,7 @@ FN_ABI_VERSION = 1
 # enum fn_prologue
 PRO_NONE, PRO_CONCAT_ELU, PRO_ELU, PRO_CONCAT_RELU, PRO_RELU = 0, 1, 2, 3, 4
 # enum fn_epilogue
-EPI_BIAS, EPI_GATE_RES, EPI_RES, EPI_TANH = 0, 1, 2, 3
+EPI_BIAS, EPI_GATE_RES, EPI_RES, EPI_TANH, EPI_GATE_BWD = 0, 1, 2, 3, 4
 # enum fn_impl
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 
@@ -53,6 +53,7 @@ SYMBOLS = [
     ("fn_launch_count", C.c_uint64, []),
     ("fn_last_used_tcgen05", C.c_int, []),
     ("fn_conv_fwd", C.c_int, [C.POINTER(ConvDesc), _P]),
+    ("fn_conv_fwd_has_tcgen05", C.c_int, [C.POINTER(ConvDesc)]),
     ("fn_tconv_fwd", C.c_int, [C.POINTER(TConvDesc), _P]),
     ("fn_conv_weights_tc_bytes", C.c_int64, [C.c_int32] * 5),
     ("fn_pack_conv_weights_tc", C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
@@ -150,7 +151,8 @@ def tc_status() -> int:
 
 def conv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, ksize=3, stride=1, prologue=PRO_NONE, epilogue=EPI_BIAS,
              impl=IMPL_AUTO, w_tc=None, skip=None, w_skip=None, res=None, res_pool=False, keep_prob=1.0,
-             dropout_seed=0, dropout_offset=0):
+             dropout_seed=0, dropout_offset=0, query=False):
+    """query=True: do not launch, return whether this call would run on the tensor cores."""
     _require_cuda(x, w, bias, y, skip, w_skip, res, w_tc)
     d = ConvDesc()
     d.B, d.H, d.W, d.Cin, d.Cout, d.ksize, d.stride = B, H, W, Cin, Cout, ksize, stride
@@ -166,6 +168,8 @@ def conv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, ksize=3, stride=1, prologue=P
         d.res_pool = 1 if res_pool else 0
     d.keep_prob = float(keep_prob)
     d.dropout_seed, d.dropout_offset = int(dropout_seed), int(dropout_offset)
+    if query:
+        return bool(lib.fn_conv_fwd_has_tcgen05(C.byref(d)))
     _check(lib.fn_conv_fwd(C.byref(d), stream_ptr()), "fn_conv_fwd")
 
 

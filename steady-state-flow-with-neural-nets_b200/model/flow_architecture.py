@@ -206,7 +206,8 @@ def _conv_weights(scope, ksize, cin_eff, cout, device, skip_scope=None, kskip_ef
 
 
 def _fused_conv(x, scope, ksize, stride, cout, prologue, epilogue, skip=None, skip_scope=None, res=None,
-                res_pool=False, keep_prob=1.0, dropout_seed=0):
+                res_pool=False, keep_prob=1.0, dropout_seed=0, query=False):
+    """One fused launch.  query=True returns whether it would run on the tensor cores instead of launching."""
     x = native.to_bf16(x)
     B, H, W, cin = int_shape(x)
     mult = _pro_mult(prologue)
@@ -214,10 +215,14 @@ def _fused_conv(x, scope, ksize, stride, cout, prologue, epilogue, skip=None, sk
     if skip is not None:
         skip = native.to_bf16(skip)
         kskip = skip.shape[3] * mult
-    gated = epilogue == native.EPI_GATE_RES
+    gated = epilogue in (native.EPI_GATE_RES, native.EPI_GATE_BWD)
     w16, ws16, bias, w_tc = _conv_weights(scope, ksize, cin * mult, cout, x.device, skip_scope, kskip, gated)
     OH, OW = -(-H // stride), -(-W // stride)
-    cy = cout // 2 if gated else cout
+    cy = cout // 2 if epilogue == native.EPI_GATE_RES else cout
+    if query:
+        return native.conv_fwd(x, w16, bias, x, B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize, stride=stride,
+                               prologue=prologue, epilogue=epilogue, impl=IMPL, w_tc=w_tc, skip=skip, w_skip=ws16, res=res,
+                               res_pool=res_pool, keep_prob=keep_prob, dropout_seed=dropout_seed, query=True)
     y = torch.empty((B, OH, OW, cy), device=x.device,
                     dtype=torch.float32 if epilogue == native.EPI_TANH else torch.bfloat16)
     rec = None

@@ -164,8 +164,13 @@ def backward(tape, sflow_p, sflow, flat: FlatParams = None, want_input_grad=Fals
             n2 = 2 * F_ if gated else F_
             # ---- conv_2 (+gate): recompute the pre-gate tensor, then its adjoint
             if gated:
-                c2 = arch._fused_conv(x_1, s2, 3, 1, n2, pro, native.EPI_BIAS, keep_prob=keep_p, dropout_seed=seed)
-                dc2 = native.gate_bwd(c2, g)
+                kw = dict(res=g, keep_prob=keep_p, dropout_seed=seed)
+                if arch._fused_conv(x_1, s2, 3, 1, n2, pro, native.EPI_GATE_BWD, query=True, **kw):
+                    # one launch: recompute [u|v] on the tensor cores, apply the gate's adjoint in the epilogue
+                    dc2 = arch._fused_conv(x_1, s2, 3, 1, n2, pro, native.EPI_GATE_BWD, **kw)
+                else:
+                    c2 = arch._fused_conv(x_1, s2, 3, 1, n2, pro, native.EPI_BIAS, keep_prob=keep_p, dropout_seed=seed)
+                    dc2 = native.gate_bwd(c2, g)
             else:
                 dc2 = g
             bgrad_into(s2, dc2)

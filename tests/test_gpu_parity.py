@@ -776,3 +776,75 @@ def test_training_from_tfrecords_queue(native, tmp_path):
         for q in flow_net._QUEUES.values():
             q.close()
         flow_net._QUEUES.clear()
+
+
+@pytest.mark.parametrize("B,H,W,C,gate", [(2, 32, 64, 8, True), (2, 32, 64, 16, True), (2, 32, 32, 32, True), (2, 16, 32, 64, True),
+                                          (3, 8, 16, 128, True), (2, 32, 64, 16, False)])
+def test_dropout_prologue_tcgen05_matches_cuda_core_mask(native, B, H, W, C, gate):
+    """tf.nn.dropout on concat_elu(x_1) (flow_architecture.py:144-145) inside the persistent tcgen05 kernels: the same
+    keep mask as the CUDA-core kernel (a different mask would differ by O(1)); the tensor-core operand is rounded to
+    bf16 after the 1/keep_prob scaling, hence the looser bound."""
+    g = torch.Generator().manual_seed(21)
+    N = 2 * C if gate else C
+    x = torch.randn(B, H, W, C, generator=g).to("cuda", torch.bfloat16)
+    w16 = ((torch.rand(9, 2 * C, N, generator=g) * 2 - 1) * (6.0 / (9 * (2 * C + N))) ** 0.5).to("cuda", torch.bfloat16)
+    bias = torch.rand(N, generator=g).to("cuda")
+    res = torch.randn(B, H, W, C, generator=g).to("cuda", torch.bfloat16) if gate else None
+    w_tc = native.pack_conv_weights_tc(w16, None, 3, 2 * C, 0, N, gate)
+    ys = []
+    for impl in (native.IMPL_TCGEN05, native.IMPL_SIMT):
+        y = torch.empty((B, H, W, C), device="cuda", dtype=torch.bfloat16)
+        native.conv_fwd(x, w16, bias, y, B=B, H=H, W=W, Cin=C, Cout=N, ksize=3, stride=1, prologue=1,
+                        epilogue=1 if gate else 0, impl=impl, w_tc=w_tc, res=res, keep_prob=0.7, dropout_seed=9)
+        torch.cuda.synchronize()
+        assert native.tc_status() == 0
+        assert native.last_used_tcgen05() == (impl == native.IMPL_TCGEN05)
+        ys.append(y)
+    assert rel_l2(ys[0], ys[1]) < 1e-2
+    y1 = torch.empty_like(ys[0])
+    native.conv_fwd(x, w16, bias, y1, B=B, H=H, W=W, Cin=C, Cout=N, ksize=3, stride=1, prologue=1, epilogue=1 if gate else 0,
+                    impl=native.IMPL_TCGEN05, w_tc=w_tc, res=res, keep_prob=0.7, dropout_seed=10)
+    assert rel_l2(y1, ys[0]) > 0.05              # another seed, another mask
+
+
+@pytest.mark.parametrize("B,H,W,C,keep", [(2, 32, 64, 8, 1.0), (2, 32, 64, 16, 0.7), (2, 32, 32, 32, 1.0), (2, 16, 32, 64, 0.7),
+                                          (3, 8, 16, 128, 1.0), (2, 20, 28, 8, 1.0)])
+def test_gate_backward_epilogue_vs_two_step(native, B, H, W, C, keep):
+    """FN_EPI_GATE_BWD (recompute [u|v], gate adjoint in the epilogue) against conv(EPI_BIAS) + fn_gate_bwd."""
+    g = torch.Generator().manual_seed(31)
+    N = 2 * C
+    x = torch.randn(B, H, W, C, generator=g).to("cuda", torch.bfloat16)
+    w16 = ((torch.rand(9, 2 * C, N, generator=g) * 2 - 1) * (6.0 / (9 * (2 * C + N))) ** 0.5).to("cuda", torch.bfloat16)
+    bias = (torch.rand(N, generator=g) - 0.5).to("cuda")
+    gy = torch.randn(B, H, W, C, generator=g).to("cuda", torch.bfloat16)
+    w_tc = native.pack_conv_weights_tc(w16, None, 3, 2 * C, 0, N, True)
+    kw = dict(B=B, H=H, W=W, Cin=C, Cout=N, ksize=3, stride=1, prologue=1, w_tc=w_tc, keep_prob=keep, dropout_seed=4)
+    assert native.conv_fwd(x, w16, bias, x, epilogue=native.EPI_GATE_BWD, res=gy, query=True, **kw)
+    fused = torch.full((B, H, W, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    native.conv_fwd(x, w16, bias, fused, epilogue=native.EPI_GATE_BWD, res=gy, impl=native.IMPL_TCGEN05, **kw)
+    c2 = torch.empty((B, H, W, N), device="cuda", dtype=torch.bfloat16)
+    native.conv_fwd(x, w16, bias, c2, epilogue=native.EPI_BIAS, impl=native.IMPL_SIMT, **kw)
+    two = native.gate_bwd(c2, gy)
+    torch.cuda.synchronize()
+    assert native.tc_status() == 0
+    # the two-step path rounds [u|v] to bf16 before the gate adjoint, the fused one does not
+    assert rel_l2(fused, two) < (1.2e-2 if keep < 1.0 else 8e-3)
+    with pytest.raises(ValueError):
+        native.conv_fwd(x, w16, bias, fused, epilogue=native.EPI_GATE_BWD, res=gy, impl=native.IMPL_SIMT, **kw)
+
+
+def test_dropout_mask_statistics_and_scalar_vector_agreement(native):
+    """keep fraction ~ keep_prob, kept values scaled by 1/keep_prob (tf.nn.dropout, flow_architecture.py:144-145); the
+    8-wide and the scalar mask code (C = 8 vs C = 4 views of the same element stream) agree element by element."""
+    n = 1 << 16
+    ones8 = torch.ones(n, 8, device="cuda", dtype=torch.bfloat16)
+    m8 = native.prologue_bwd(ones8, ones8, 0, keep_prob=0.7, seed=3).float()
+    vals = set(m8.unique().tolist())
+    assert vals == {0.0, float(torch.tensor(1 / 0.7).to(torch.bfloat16))}
+    frac = (m8 > 0).float().mean().item()
+    assert abs(frac - 0.7) < 5e-3
+    ones4 = torch.ones(2 * n, 4, device="cuda", dtype=torch.bfloat16)          # same flat element indices, scalar kernel
+    m4 = native.prologue_bwd(ones4, ones4, 0, keep_prob=0.7, seed=3).float()
+    assert torch.equal(m4.reshape(-1), m8.reshape(-1))
+    m8b = native.prologue_bwd(ones8, ones8, 0, keep_prob=0.7, seed=4).float()
+    assert 0.35 < (m8b.reshape(-1) == m8.reshape(-1)).float().mean().item() < 0.75   # independent masks agree on ~58 %
