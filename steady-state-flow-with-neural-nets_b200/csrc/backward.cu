@@ -116,13 +116,13 @@ __global__ void __launch_bounds__(BW_THREADS) k_gate_bwd_v8(const __nv_bfloat16*
   }
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(BW_THREADS) k_prologue_bwd_v8(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ x,
                                                                 __nv_bfloat16* __restrict__ dx, long long npix, int C, int kind,
                                                                 int accumulate, float keep_prob, unsigned long long seed) {
   const int mult = pro_mult(kind);
   const int cc = C >> 3;
   const long long total = npix * cc;
-  const bool drop = keep_prob < 1.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long p = i / cc;
     const int c = (int)(i - p * cc) * 8;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(BW_THREADS) k_prologue_bwd_v8(const __nv_bfloa
     if (mult == 2) ld8(a1, dA + p * mult * C + C + c);
     if (accumulate) ld8(old, dx + p * C + c);
     float sc0[8], sc1[8];
-    if (drop) {
+    if (DROP) {
       dropout_scale8(seed, (unsigned long long)(p * mult * C + c), keep_prob, sc0);
       if (mult == 2) dropout_scale8(seed, (unsigned long long)(p * mult * C + C + c), keep_prob, sc1);
     }
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(BW_THREADS) k_prologue_bwd_v8(const __nv_bfloa
       const float xf = __bfloat162float(xv.h[j]);
       float f0 = __bfloat162float(a0.h[j]);
       float f1 = mult == 2 ? __bfloat162float(a1.h[j]) : 0.f;
-      if (drop) {
+      if (DROP) {
         f0 *= sc0[j];
         if (mult == 2) f1 *= sc1[j];
       }
@@ -475,8 +475,12 @@ int prologue_bwd(const void* dA, const void* x, void* dx, long long npix, int C,
                  unsigned long long seed, cudaStream_t s) {
   if (npix == 0) return 0;
   if ((C & 7) == 0)
-    k_prologue_bwd_v8<<<bw_grid(npix * (C / 8)), BW_THREADS, 0, s>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)x,
-                                                                       (__nv_bfloat16*)dx, npix, C, kind, accumulate, keep_prob, seed);
+    if (keep_prob < 1.0f)
+      k_prologue_bwd_v8<true><<<bw_grid(npix * (C / 8)), BW_THREADS, 0, s>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)x,
+                                                                               (__nv_bfloat16*)dx, npix, C, kind, accumulate, keep_prob, seed);
+    else
+      k_prologue_bwd_v8<false><<<bw_grid(npix * (C / 8)), BW_THREADS, 0, s>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)x,
+                                                                                (__nv_bfloat16*)dx, npix, C, kind, accumulate, keep_prob, seed);
   else
     k_prologue_bwd<<<bw_grid(npix * C), BW_THREADS, 0, s>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx,
                                                             npix, C, kind, accumulate, keep_prob, seed);

@@ -61,6 +61,7 @@ struct Params {
   uint32_t off_a, a_bytes, off_dy, dy_bytes, off_stage, stage_bytes, sub_bytes;
   uint32_t tmem_cols;
   int ksize, swap, m64;
+  int a3;               // 1: three column-shifted copies of every plane, the 3 taps of a filter row share one MMA
   float keep_prob;
   unsigned long long seed;
 };
@@ -88,6 +89,69 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
 // instruction descriptor: BF16 x BF16 -> FP32, A and B MN-major (bits 15 / 16)
 static uint32_t idesc_mn(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// stage [pixel][C] raw bf16 -> this CTA's operand planes: prologue (CE: the single-exponential concat_elu; else the
+// generic switch), optional dropout mask of the forward pass, parity split (stride 2), three shifted copies (a3)
+template <int MODE, bool CE, bool DROP>
+__device__ __forceinline__ void transform_tile(const Params& p, uint32_t stage, uint32_t planes, int tid, int items, int mb, int b,
+                                               int y0, int x0) {
+  using G = Geo<MODE>;
+  const int kpl = p.kpl;
+  const int mult = CE ? 2 : pro_mult(p.pro);
+#pragma unroll 2
+  for (int idx = tid; idx < items; idx += 128) {
+    const int ch = idx & (p.CH - 1);
+    const int sp = idx >> p.chshift;
+    bf16x8 in, o0, o1;
+    in.v = lds128(stage + (uint32_t)idx * 16u);
+    const int r = sp / G::SW_, c = sp - r * G::SW_;
+    float sc0[8], sc1[8];
+    if (DROP) {     // tf.nn.dropout on the conv input (flow_architecture.py:144-145): same mask as the forward
+      const int iy = G::S2 ? 2 * y0 + r : y0 - 1 + r, ix = G::S2 ? 2 * x0 + c : x0 - 1 + c;
+      const unsigned long long pidx = ((unsigned long long)b * p.H + iy) * p.W + ix;
+      dropout_scale8(p.seed, pidx * p.Keff + ch * 8, p.keep_prob, sc0);
+      if (mult == 2) dropout_scale8(p.seed, pidx * p.Keff + p.C + ch * 8, p.keep_prob, sc1);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = __bfloat162float(in.h[j]);
+      float a0, a1;
+      if (CE) {
+        const float t = __expf(-fabsf(v)) - 1.f;
+        a0 = v > 0.f ? v : t;
+        a1 = v > 0.f ? t : -v;
+      } else {
+        pro_apply(p.pro, v, a0, a1);
+      }
+      if (DROP) {     // the forward rounds the prologue output to bf16 before scaling
+        a0 = __bfloat162float(__float2bfloat16(a0)) * sc0[j];
+        a1 = __bfloat162float(__float2bfloat16(a1)) * sc1[j];
+      }
+      o0.h[j] = __float2bfloat16(a0);
+      o1.h[j] = __float2bfloat16(a1);
+    }
+    uint32_t dst = planes;
+    int pp = sp;
+    if (G::S2) {
+      dst += (uint32_t)((r & 1) * 2 + (c & 1)) * p.sub_bytes;
+      pp = (r >> 1) * G::PU + (c >> 1);
+    }
+    const int l0 = ch - kpl * mb, l1 = p.CH + ch - kpl * mb;
+    if (p.a3) {
+      // copy du holds the plane shifted left by du pixels: copy[du][pp] = plane[pp + du]
+#pragma unroll
+      for (int du = 0; du < 3; ++du) {
+        if (pp >= du) {
+          sts128(dst + (uint32_t)((du * kpl + l0) * G::PPAD + pp - du) * 16u, o0.v);
+          if (mult == 2) sts128(dst + (uint32_t)((du * kpl + l1) * G::PPAD + pp - du) * 16u, o1.v);
+        }
+      }
+    } else {
+      if (l0 >= 0 && l0 < kpl) sts128(dst + (uint32_t)(l0 * G::PPAD + pp) * 16u, o0.v);
+      if (mult == 2 && l1 >= 0 && l1 < kpl) sts128(dst + (uint32_t)(l1 * G::PPAD + pp) * 16u, o1.v);
+    }
+  }
 }
 
 template <int MODE, int NT>
@@ -178,6 +242,7 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
       if (p.ksize == 1) { di = 1; dj = 1; }
       tapoff[t] = G::S2 ? (uint32_t)((di & 1) * 2 + (dj & 1)) * p.sub_bytes + (uint32_t)(((di >> 1) * G::PU + (dj >> 1)) * 16)
                         : (uint32_t)((di * G::PU + dj) * 16);
+      if (p.a3) tapoff[t] = (uint32_t)(t * G::ROW_BYTES);       // accumulator t = filter row t; columns are M groups
     }
     const bool swp = p.swap & 1;
     const uint32_t lbo_a = swp ? (uint32_t)(G::PPAD * 16) : 128u, sbo_a = swp ? 128u : (uint32_t)(G::PPAD * 16);
@@ -219,40 +284,15 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
       if (!ok) atomicCAS(p.status, 0, 63);
       const uint32_t stage = sbase + p.off_stage + (uint32_t)s * p.stage_bytes;
       const uint32_t planes = sbase + p.off_a + (uint32_t)s * p.a_bytes;
-      for (int idx = tid; idx < ((p.swap & 16) ? 0 : items); idx += 128) {
-        const int ch = idx & (p.CH - 1);
-        const int sp = idx >> p.chshift;
-        bf16x8 in, o0, o1;
-        in.v = lds128(stage + (uint32_t)idx * 16u);
-        const int r = sp / G::SW_, c = sp - r * G::SW_;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float a0, a1;
-          pro_apply(p.pro, __bfloat162float(in.h[j]), a0, a1);
-          o0.h[j] = __float2bfloat16(a0);
-          o1.h[j] = __float2bfloat16(a1);
+      if (!(p.swap & 16)) {
+        const bool ce = p.pro == FN_PRO_CONCAT_ELU;
+        if (p.keep_prob < 1.0f) {
+          if (ce) transform_tile<MODE, true, true>(p, stage, planes, tid, items, mb, b, y0, x0);
+          else transform_tile<MODE, false, true>(p, stage, planes, tid, items, mb, b, y0, x0);
+        } else {
+          if (ce) transform_tile<MODE, true, false>(p, stage, planes, tid, items, mb, b, y0, x0);
+          else transform_tile<MODE, false, false>(p, stage, planes, tid, items, mb, b, y0, x0);
         }
-        if (p.keep_prob < 1.0f) {     // tf.nn.dropout on the conv input (flow_architecture.py:144-145): same mask as the forward
-          const int iy = G::S2 ? 2 * y0 + r : y0 - 1 + r, ix = G::S2 ? 2 * x0 + c : x0 - 1 + c;
-          const unsigned long long pidx = ((unsigned long long)b * p.H + iy) * p.W + ix;
-          float sc0[8], sc1[8];
-          dropout_scale8(p.seed, pidx * p.Keff + ch * 8, p.keep_prob, sc0);
-          if (mult == 2) dropout_scale8(p.seed, pidx * p.Keff + p.C + ch * 8, p.keep_prob, sc1);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            o0.h[j] = __float2bfloat16(__bfloat162float(o0.h[j]) * sc0[j]);
-            if (mult == 2) o1.h[j] = __float2bfloat16(__bfloat162float(o1.h[j]) * sc1[j]);
-          }
-        }
-        uint32_t dst = planes;
-        int pp = sp;
-        if (G::S2) {
-          dst += (uint32_t)((r & 1) * 2 + (c & 1)) * p.sub_bytes;
-          pp = (r >> 1) * G::PU + (c >> 1);
-        }
-        const int l0 = ch - kpl * mb, l1 = p.CH + ch - kpl * mb;
-        if (l0 >= 0 && l0 < kpl) sts128(dst + (uint32_t)(l0 * G::PPAD + pp) * 16u, o0.v);
-        if (mult == 2 && l1 >= 0 && l1 < kpl) sts128(dst + (uint32_t)(l1 * G::PPAD + pp) * 16u, o1.v);
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(bar(SB_PF + s));
@@ -266,15 +306,21 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
     // M = 128: accumulator row r lives in TMEM lane r; M = 64 (kpl <= 8): row r in lane 32*(r/16) + r%16 (measured,
     // tools/m64_layout.py)
     const int row_local = p.m64 ? (lane < 16 ? warp * 16 + lane : 1 << 20) : warp * 32 + lane;
-    const int krow = mb * kpl * 8 + row_local;
+    int krow = mb * kpl * 8 + row_local;
+    int du_row = 0;                                   // a3: accumulator row = (column shift du, channel k)
+    if (p.a3) {
+      du_row = row_local / (kpl * 8);
+      krow = row_local - du_row * kpl * 8;
+    }
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int t = 0; t < NT; ++t) {
-      float* dst = p.partial + (((size_t)s_idx * p.T + tap0 + t) * p.Keff + krow) * p.N;
+      const int tap = p.a3 ? 3 * t + du_row : tap0 + t;
+      float* dst = p.partial + (((size_t)s_idx * p.T + tap) * p.Keff + krow) * p.N;
       for (int n0 = 0; n0 < p.N; n0 += 8) {
         float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (n_local > 0) ptx::tmem_ld8(lane_base + (uint32_t)(t * p.Npad + n0), o);
-        if (row_local < kpl * 8 && krow < p.Keff && ok) {
+        if ((p.a3 ? du_row < 3 : row_local < kpl * 8) && krow < p.Keff && ok) {
           *reinterpret_cast<float4*>(dst + n0) = make_float4(o[0], o[1], o[2], o[3]);
           *reinterpret_cast<float4*>(dst + n0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
         }
@@ -336,8 +382,11 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
   p.Npad = (N + 15) / 16 * 16;
   p.nchunks = N / 8;
   p.idesc = idesc_mn(128, p.Npad);
-  pl.NT = p.T == 1 ? 1 : (9 * p.Npad <= 512 ? 9 : (3 * p.Npad <= 512 ? 3 : 1));
-  p.tap_groups = p.T / pl.NT;
+  // narrow stride-1 3x3 layers: stack the three column taps along M (3 shifted plane copies), 3 MMAs per K-step
+  // instead of 9 -- the MMA rate is set by the 64/128 operand rows read from shared memory, mostly padding here
+  p.a3 = (pl.mode == MODE_S1 && ksize == 3 && p.Keff <= 32 && !(g_swap & 64)) ? 1 : 0;
+  pl.NT = p.a3 ? 3 : (p.T == 1 ? 1 : (9 * p.Npad <= 512 ? 9 : (3 * p.Npad <= 512 ? 3 : 1)));
+  p.tap_groups = p.a3 ? 1 : p.T / pl.NT;
   int cols = pl.NT * p.Npad;
   p.tmem_cols = 32;
   while ((int)p.tmem_cols < cols) p.tmem_cols *= 2;
@@ -359,7 +408,7 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
     p.kpl = p.Keff / 8 < tries[i][0] ? p.Keff / 8 : tries[i][0];
     p.nbuf = tries[i][1];
     p.mblocks = (p.Keff / 8 + p.kpl - 1) / p.kpl;
-    p.sub_bytes = (uint32_t)(p.kpl * PPAD * 16);
+    p.sub_bytes = (uint32_t)((p.a3 ? 3 : 1) * p.kpl * PPAD * 16);
     p.a_bytes = (NSUB * p.sub_bytes + 127) / 128 * 128;
     p.off_a = HDR;
     p.off_dy = p.off_a + p.nbuf * p.a_bytes;
@@ -385,7 +434,7 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
   p.swap = g_swap;
   // the A operand is read from shared memory at 128 rows x 32 B per MMA whatever the real channel count: half of that
   // (M = 64, N % 8 == 0) when the CTA's channel block is at most 64 wide.  Flag 32 forces M = 128 (experiments).
-  p.m64 = (p.kpl <= 8 && !(g_swap & 32)) ? 1 : 0;
+  p.m64 = ((p.a3 ? 3 : 1) * p.kpl <= 8 && !(g_swap & 32)) ? 1 : 0;
   p.idesc = idesc_mn(p.m64 ? 64 : 128, p.Npad);
   return true;
 }
