@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FN_ABI_VERSION 1
+#define FN_ABI_VERSION 2
 
 /* error codes (negative) */
 #define FN_E_INVAL      (-1)   /* null pointer, bad enum, non-positive dim */
@@ -50,7 +50,13 @@ enum fn_epilogue {
   /* backward of the gate, fused with the recomputation of its input: with [u|v] = acc + bias and g = res (the
    * gradient of the block output, bf16 [.,Cout/2]):  y = [g*sigmoid(v) | g*u*sigmoid(v)*(1-sigmoid(v))] -> bf16 [.,Cout],
    * the gradient of the pre-gate tensor (adjoint of :150-151).  tcgen05 kernels only (concat_elu prologue, stride 1). */
-  FN_EPI_GATE_BWD = 4
+  FN_EPI_GATE_BWD = 4,
+  /* backward of a prologue nonlinearity fused into the data-gradient conv that produces its input gradient: acc = dA,
+   * the gradient of pro(z) (Cout = mult * Cz channels); res = z, bf16 [.,Cz];
+   *   y[., c] (+)= dA[c] * f'(z[c])  -  dA[Cz + c] * f'(-z[c])        (second term: concat kinds only)
+   * with the forward's dropout mask (keep_prob, dropout_seed) applied to dA; kind = adj_prologue, += if adj_accumulate.
+   * tcgen05 kernels only (stride 1, 3x3, no prologue on x, Cin in {8,16,32,64}, Cout in {Cin, 2 Cin}). */
+  FN_EPI_PRO_BWD = 5
 };
 
 /* implementation selector: the tensor-core kernels are the product; the CUDA-core kernels
@@ -97,6 +103,9 @@ typedef struct fn_conv_desc {
   float    keep_prob;
   uint64_t dropout_seed;
   uint64_t dropout_offset;
+  /* FN_EPI_PRO_BWD only */
+  int32_t  adj_prologue;    /* enum fn_prologue of the nonlinearity being differentiated */
+  int32_t  adj_accumulate;  /* 1: y += ... */
 } fn_conv_desc;
 
 /* One transposed convolution launch: tf.nn.conv2d_transpose(k=3, s=2, 'SAME') + bias

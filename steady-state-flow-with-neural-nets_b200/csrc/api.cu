@@ -63,7 +63,7 @@ static int validate_conv(const fn_conv_desc& d) {
   FN_REQUIRE(d.stride == 1 || d.stride == 2, FN_E_UNSUPPORTED, "fn_conv_fwd: stride %d (only 1 and 2)", d.stride);
   FN_REQUIRE(d.prologue >= FN_PRO_NONE && d.prologue <= FN_PRO_RELU, FN_E_INVAL, "fn_conv_fwd: bad prologue %d",
              d.prologue);
-  FN_REQUIRE(d.epilogue >= FN_EPI_BIAS && d.epilogue <= FN_EPI_GATE_BWD, FN_E_INVAL, "fn_conv_fwd: bad epilogue %d",
+  FN_REQUIRE(d.epilogue >= FN_EPI_BIAS && d.epilogue <= FN_EPI_PRO_BWD, FN_E_INVAL, "fn_conv_fwd: bad epilogue %d",
              d.epilogue);
   FN_REQUIRE(d.impl >= FN_IMPL_AUTO && d.impl <= FN_IMPL_TCGEN05, FN_E_INVAL, "fn_conv_fwd: bad impl %d", d.impl);
   FN_REQUIRE(d.Cin == 1 || (d.Cin % 8) == 0, FN_E_ALIGN, "fn_conv_fwd: Cin=%d must be 1 or a multiple of 8", d.Cin);
@@ -72,6 +72,9 @@ static int validate_conv(const fn_conv_desc& d) {
     FN_REQUIRE(d.res && d.Cres == d.Cout / 2 && d.RH == d.H && d.RW == d.W && !d.res_pool && d.stride == 1 && !d.skip &&
                    d.impl != FN_IMPL_SIMT,
                FN_E_UNSUPPORTED, "fn_conv_fwd: gate-backward epilogue needs res = gradient [B,H,W,Cout/2], stride 1, no skip, tcgen05");
+  if (d.epilogue == FN_EPI_PRO_BWD)
+    FN_REQUIRE(d.res && d.adj_prologue >= FN_PRO_NONE && d.adj_prologue <= FN_PRO_RELU && d.impl != FN_IMPL_SIMT, FN_E_UNSUPPORTED,
+               "fn_conv_fwd: prologue-adjoint epilogue needs res = the differentiated input, a valid adj_prologue, tcgen05");
   if (d.epilogue == FN_EPI_GATE_RES || d.epilogue == FN_EPI_GATE_BWD)
     FN_REQUIRE((d.Cout % 16) == 0, FN_E_ALIGN, "fn_conv_fwd: gated Cout=%d must be a multiple of 16", d.Cout);
   else if (d.epilogue != FN_EPI_TANH)
@@ -116,7 +119,8 @@ int fn_conv_fwd(const fn_conv_desc* d, void* stream) {
     note_tcgen05(true);
     return conv_fwd_tc(*d, s);
   }
-  FN_REQUIRE(d->impl != FN_IMPL_TCGEN05, FN_E_UNSUPPORTED, "fn_conv_fwd: no tcgen05 kernel for this shape: %s", why);
+  FN_REQUIRE(d->impl != FN_IMPL_TCGEN05 && d->epilogue != FN_EPI_GATE_BWD && d->epilogue != FN_EPI_PRO_BWD, FN_E_UNSUPPORTED,
+             "fn_conv_fwd: no tcgen05 kernel for this shape: %s", why);
   note_tcgen05(false);
   return conv_fwd_simt(*d, s);
 }

@@ -38,6 +38,12 @@ struct Params {
   int RH, RW;             // GEMM-row image: output pixels (S2) or input pixels (TCONV)
   int tiles_u, tiles_v, ntiles;
   int Cout;               // real output channels
+  // FN_EPI_PRO_BWD (MODE_S1N): the accumulator is the gradient of a prologue output; y (+)= its adjoint w.r.t. res
+  int adj;                // 0: plain bias epilogue; else 1 + enum fn_prologue of the adjoint
+  int adj_accumulate;
+  const __nv_bfloat16* res;
+  float keep_prob;
+  unsigned long long seed;
 };
 
 template <int MODE, int CLOG, int J, int NBUF, int R = 1>
@@ -257,10 +263,33 @@ __global__ void __launch_bounds__(THREADS) k_conv_s2t(const __grid_constant__ Pa
       const int s = buf_of(it), k = use_of(it);
       int b, y0, x0;
       tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, y0, x0);
+      const int ry = y0 + v;
+      // adjoint epilogue: fetch this thread's z (and old y) vectors while the MMAs still run
+      constexpr int NSLOT = CF::S1N ? ((ITEMS + 1) / 2) * (CF::NREAL / 16 > 0 ? CF::NREAL / 16 : 1) : 1;
+      uint4 pre_z[NSLOT], pre_y[NSLOT];
+      if (CF::S1N && p.adj) {
+        constexpr int CY = CF::NREAL / 2;
+#pragma unroll
+        for (int w0 = 0; w0 < ITEMS; w0 += 2) {
+          const int item = w0 + half;
+          if (item >= ITEMS) break;
+          const int rx = x0 + 8 * item + u;
+          const size_t pix = ((size_t)b * p.OH + ry) * p.OW + rx;
+#pragma unroll
+          for (int cc = 0; cc < CY / 8; ++cc) {
+            const int slot = (w0 / 2) * (CY / 8) + cc;
+            pre_z[slot] = make_uint4(0u, 0u, 0u, 0u);
+            pre_y[slot] = make_uint4(0u, 0u, 0u, 0u);
+            if (ry < p.RH && rx < p.RW) {
+              pre_z[slot] = __ldg(reinterpret_cast<const uint4*>(p.res + pix * CY + cc * 8));
+              if (p.adj_accumulate) pre_y[slot] = *reinterpret_cast<const uint4*>(p.y + pix * CY + cc * 8);
+            }
+          }
+        }
+      }
       ok = ok && ptx::mbar_wait(bar(SB_TF + s), (uint32_t)(k & 1));
       if (!ok) atomicCAS(p.status, 0, 45);
       ptx::tc_fence_after_sync();
-      const int ry = y0 + v;
 #pragma unroll
       for (int w0 = 0; w0 < ITEMS; w0 += 2) {
         const int item = w0 + half;
@@ -273,6 +302,49 @@ __global__ void __launch_bounds__(THREADS) k_conv_s2t(const __grid_constant__ Pa
         const int ox = CF::NPH == 1 ? rx : 2 * rx + (ph & 1);
         const size_t pix = ((size_t)b * p.OH + oy) * p.OW + ox;
         const uint32_t col0 = lane_base + (uint32_t)(s * CF::ACC_COLS + (j * CF::NPH + ph) * CF::N);
+        if (CF::S1N && p.adj) {
+          // y[pix][c] (+)= dA0[c] f'(z[c]) - dA1[c] f'(-z[c]) with [dA0 | dA1] = the two accumulator halves and the
+          // forward's dropout mask on dA (flow_architecture.py:14-29, 143-145); z / old y were fetched before the wait
+          const int kind = p.adj - 1;
+          constexpr int CY = CF::NREAL / 2;
+#pragma unroll
+          for (int cc = 0; cc < CY / 8; ++cc) {
+            const int c0 = cc * 8;
+            const int slot = (w0 / 2) * (CY / 8) + cc;
+            float a0[8], a1[8];
+            ptx::tmem_ld8x2(col0 + c0, col0 + CY + c0, a0, a1);
+            if (live) {
+              bf16x8 xv, old, st;
+              xv.v = pre_z[slot];
+              old.v = pre_y[slot];
+              float sc0[8], sc1[8];
+              const bool drop = p.keep_prob < 1.0f;
+              if (drop) {
+                dropout_scale8(p.seed, (unsigned long long)pix * CF::NREAL + c0, p.keep_prob, sc0);
+                dropout_scale8(p.seed, (unsigned long long)pix * CF::NREAL + CY + c0, p.keep_prob, sc1);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float xf = __bfloat162float(xv.h[i]);
+                // the two-step path stores dA as bf16 before the adjoint; keep that rounding point
+                float f0 = __bfloat162float(__float2bfloat16(a0[i] + sbias[c0 + i]));
+                float f1 = __bfloat162float(__float2bfloat16(a1[i] + sbias[CY + c0 + i]));
+                if (drop) { f0 *= sc0[i]; f1 *= sc1[i]; }
+                float d;
+                if (kind == FN_PRO_CONCAT_ELU) {
+                  const float e = __expf(-fabsf(xf));
+                  d = xf > 0.f ? f0 - f1 * e : f0 * e - f1;
+                } else {   // FN_PRO_CONCAT_RELU
+                  d = (xf > 0.f ? f0 : 0.f) - (xf < 0.f ? f1 : 0.f);
+                }
+                if (p.adj_accumulate) d += __bfloat162float(old.h[i]);
+                st.h[i] = __float2bfloat16(d);
+              }
+              *reinterpret_cast<uint4*>(p.y + pix * CY + c0) = st.v;
+            }
+          }
+          continue;
+        }
 #pragma unroll
         for (int c0 = 0; c0 < CF::NREAL; c0 += 8) {
           float o[8];
@@ -327,9 +399,16 @@ static bool make_map_nhwc(CUtensorMap* tm, const void* base, int B, int H, int W
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+struct AdjArgs {
+  int adj = 0, accumulate = 0;
+  const void* res = nullptr;
+  float keep_prob = 1.0f;
+  unsigned long long seed = 0;
+};
+
 template <int MODE, int CLOG, int J, int NBUF, int R = 1>
 static int launch(const void* x, const void* wpk, const float* bias, void* y, int B, int H, int W, int Cout, int* status,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const AdjArgs& adj = AdjArgs()) {
   using CF = Cfg<MODE, CLOG, J, NBUF, R>;
   Params p;
   memset(&p, 0, sizeof(p));
@@ -346,6 +425,11 @@ static int launch(const void* x, const void* wpk, const float* bias, void* y, in
   p.tiles_v = (p.RH + 15) / 16;
   p.ntiles = B * p.tiles_u * p.tiles_v;
   p.Cout = Cout;
+  p.adj = adj.adj;
+  p.adj_accumulate = adj.accumulate;
+  p.res = (const __nv_bfloat16*)adj.res;
+  p.keep_prob = adj.keep_prob;
+  p.seed = adj.seed;
   auto kern = k_conv_s2t<MODE, CLOG, J, NBUF, R>;
   static bool configured = false;
   if (!configured) {
@@ -402,9 +486,22 @@ bool conv_s2p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
 bool conv_s1n_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc) {
   using namespace s2t;
   rc = 0;
-  if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_NONE || d.epilogue != FN_EPI_BIAS || d.skip || d.w_tc == nullptr ||
-      d.H < 16)
+  const bool adjoint = d.epilogue == FN_EPI_PRO_BWD;
+  if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_NONE || (d.epilogue != FN_EPI_BIAS && !adjoint) || d.skip ||
+      d.w_tc == nullptr || d.H < 16)
     return false;
+  AdjArgs adj;
+  if (adjoint) {
+    if (d.adj_prologue != FN_PRO_CONCAT_ELU && d.adj_prologue != FN_PRO_CONCAT_RELU) return false;   // others: two launches
+    const int cy = d.Cout / 2;
+    if (cy % 8) return false;
+    if (d.res == nullptr || d.res_pool || d.Cres != cy || d.RH != d.H || d.RW != d.W || d.dropout_offset != 0) return false;
+    adj.adj = 1 + d.adj_prologue;
+    adj.accumulate = d.adj_accumulate;
+    adj.res = d.res;
+    adj.keep_prob = d.keep_prob;
+    adj.seed = d.dropout_seed;
+  }
   if (get_encode() == nullptr) return false;
   const int clog = d.Cin == 8 ? 0 : d.Cin == 16 ? 1 : d.Cin == 32 ? 2 : d.Cin == 64 ? 3 : -1;
   const int r = d.Cout == d.Cin ? 1 : d.Cout == 2 * d.Cin ? 2 : 0;
@@ -413,7 +510,7 @@ bool conv_s1n_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
   if (clog == CL && r == RR && ((d.W % (8 * JJ)) == 0 || JJ == 1) && Cfg<MODE_S1N, CL, JJ, NB, RR>::SMEM <= CAP * 1024) { \
     if (!dry_run) {                                                                                              \
       int* st = tc_status_word();                                                                                \
-      rc = st ? launch<MODE_S1N, CL, JJ, NB, RR>(d.x, d.w_tc, d.bias, d.y, d.B, d.H, d.W, d.Cout, st, stream)     \
+      rc = st ? launch<MODE_S1N, CL, JJ, NB, RR>(d.x, d.w_tc, d.bias, d.y, d.B, d.H, d.W, d.Cout, st, stream, adj) \
               : (int)cudaErrorMemoryAllocation;                                                                  \
     }                                                                                                            \
     return true;                                                                                                 \

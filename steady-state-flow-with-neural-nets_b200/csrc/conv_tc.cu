@@ -650,6 +650,7 @@ static bool geom_of_conv(const fn_conv_desc& d, TcGeom& g, const char** why) {
 
 bool conv_s1p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1p.cu
 bool conv_s1d_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1d.cu
+bool conv_s1n_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s2t.cu
 
 bool conv_tc_supported(const fn_conv_desc& d, const char** why) {
   int rc = 0;
@@ -659,6 +660,11 @@ bool conv_tc_supported(const fn_conv_desc& d, const char** why) {
     return true;
   if (d.epilogue == FN_EPI_GATE_BWD) {
     if (why) *why = "the gate-backward epilogue exists in the persistent kernels only";
+    return false;
+  }
+  if (d.epilogue == FN_EPI_PRO_BWD) {
+    if (g_tc_use_s1p && conv_s1n_try(d, nullptr, true, rc)) return true;
+    if (why) *why = "the prologue-adjoint epilogue exists in the persistent data-gradient kernel only";
     return false;
   }
   TcGeom g;

@@ -11,11 +11,11 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FLOWNET_LIB", os.path.join(_HERE, "libflownet.so"))   # override: A/B builds
 
-FN_ABI_VERSION = 1
+FN_ABI_VERSION = 2
 # enum fn_prologue
 PRO_NONE, PRO_CONCAT_ELU, PRO_ELU, PRO_CONCAT_RELU, PRO_RELU = 0, 1, 2, 3, 4
 # enum fn_epilogue
-EPI_BIAS, EPI_GATE_RES, EPI_RES, EPI_TANH, EPI_GATE_BWD = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_GATE_RES, EPI_RES, EPI_TANH, EPI_GATE_BWD, EPI_PRO_BWD = 0, 1, 2, 3, 4, 5
 # enum fn_impl
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 
@@ -32,6 +32,7 @@ class ConvDesc(C.Structure):
         ("Cres", C.c_int32), ("RH", C.c_int32), ("RW", C.c_int32), ("res_pool", C.c_int32),
         ("keep_prob", C.c_float),
         ("dropout_seed", C.c_uint64), ("dropout_offset", C.c_uint64),
+        ("adj_prologue", C.c_int32), ("adj_accumulate", C.c_int32),
     ]
 
 
@@ -151,7 +152,7 @@ def tc_status() -> int:
 
 def conv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, ksize=3, stride=1, prologue=PRO_NONE, epilogue=EPI_BIAS,
              impl=IMPL_AUTO, w_tc=None, skip=None, w_skip=None, res=None, res_pool=False, keep_prob=1.0,
-             dropout_seed=0, dropout_offset=0, query=False):
+             dropout_seed=0, dropout_offset=0, adj_prologue=0, adj_accumulate=False, query=False):
     """query=True: do not launch, return whether this call would run on the tensor cores."""
     _require_cuda(x, w, bias, y, skip, w_skip, res, w_tc)
     d = ConvDesc()
@@ -168,6 +169,7 @@ def conv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, ksize=3, stride=1, prologue=P
         d.res_pool = 1 if res_pool else 0
     d.keep_prob = float(keep_prob)
     d.dropout_seed, d.dropout_offset = int(dropout_seed), int(dropout_offset)
+    d.adj_prologue, d.adj_accumulate = int(adj_prologue), int(bool(adj_accumulate))
     if query:
         return bool(lib.fn_conv_fwd_has_tcgen05(C.byref(d)))
     _check(lib.fn_conv_fwd(C.byref(d), stream_ptr()), "fn_conv_fwd")

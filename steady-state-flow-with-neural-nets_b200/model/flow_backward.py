@@ -69,6 +69,26 @@ def _conv_plain(x, w16, cout, ksize, stride, device):
     return y
 
 
+def _conv_dgrad_adjoint(g, w16, cout, z, pro, device, out=None, accumulate=False, keep_prob=1.0, seed=0):
+    """d(z) (+)= adjoint_of_prologue(conv3x3(g, w16), z): the data-gradient conv with the prologue's adjoint (and the
+    forward's dropout mask) applied in its epilogue when the persistent kernel takes the shape (FN_EPI_PRO_BWD), else the
+    conv followed by fn_prologue_bwd.  Returns the d(z) tensor."""
+    B, H, W, cin = g.shape
+    if out is None:
+        out = torch.empty(tuple(z.shape), dtype=torch.bfloat16, device=device)
+        accumulate = False
+    w_tc = native.pack_conv_weights_tc(w16, None, 3, cin, 0, cout, False) if (cin % 16 == 0 or cin == 8) else None
+    kw = dict(B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=3, stride=1, prologue=native.PRO_NONE, epilogue=native.EPI_PRO_BWD,
+              impl=arch.IMPL, w_tc=w_tc, res=z, keep_prob=keep_prob, dropout_seed=seed, adj_prologue=pro,
+              adj_accumulate=accumulate)
+    bias = _zeros_bias(cout, device)
+    if w_tc is not None and arch.IMPL != native.IMPL_SIMT and native.conv_fwd(g, w16, bias, out, query=True, **kw):
+        native.conv_fwd(g, w16, bias, out, **kw)
+        return out
+    dA = _conv_plain(g, w16, cout, 3, 1, device)
+    return native.prologue_bwd(dA, z, pro, out=out, accumulate=accumulate, keep_prob=keep_prob, seed=seed)
+
+
 def _tconv_plain(x, w16, cout, device):
     B, H, W, cin = x.shape
     y = torch.empty((B, 2 * H, 2 * W, cout), dtype=torch.bfloat16, device=device)
@@ -175,8 +195,8 @@ def backward(tape, sflow_p, sflow, flat: FlatParams = None, want_input_grad=Fals
                 dc2 = g
             bgrad_into(s2, dc2)
             wgrad_into(s2, x_1, dc2, 3, 1, pro, keep_p, seed)
-            dA2 = _conv_plain(dc2, _dgrad_weights_s1(V[s2 + '/weights'], 3), mult * F_, 3, 1, dev)
-            dx_1 = native.prologue_bwd(dA2, x_1, pro, keep_prob=keep_p, seed=seed)
+            dx_1 = _conv_dgrad_adjoint(dc2, _dgrad_weights_s1(V[s2 + '/weights'], 3), mult * F_, x_1, pro, dev,
+                                       keep_prob=keep_p, seed=seed)
             # ---- conv_1 (+nin skip)
             s1 = name + '_conv_1_conv'
             pro1 = native.PRO_NONE if cin == 1 else pro
@@ -197,15 +217,15 @@ def backward(tape, sflow_p, sflow, flat: FlatParams = None, want_input_grad=Fals
                 native.prologue_bwd(dAa, a, pro, out=buf, accumulate=acc)
             if cin > 1:
                 w1 = V[s1 + '/weights']                                   # [3,3,mult*cin,F]
+                buf, acc = grads.target(x)
                 if stride == 1:
-                    dA1 = _conv_plain(dx_1, _dgrad_weights_s1(w1, 3), mult * cin, 3, 1, dev)
+                    _conv_dgrad_adjoint(dx_1, _dgrad_weights_s1(w1, 3), mult * cin, x, pro, dev, out=buf, accumulate=acc)
                 else:
                     if x.shape[1] % 2 or x.shape[2] % 2:
                         raise ValueError("training a stride-2 block on odd spatial sizes is not built")
                     w16 = w1.reshape(9, mult * cin, F_).permute(0, 2, 1).to(torch.bfloat16).contiguous()   # [tap, F, Keff]
                     dA1 = _tconv_plain(dx_1, w16, mult * cin, dev)
-                buf, acc = grads.target(x)
-                native.prologue_bwd(dA1, x, pro, out=buf, accumulate=acc)
+                    native.prologue_bwd(dA1, x, pro, out=buf, accumulate=acc)
                 native.shortcut_bwd(g, tuple(x.shape), pooled, out=buf, accumulate=True)
             elif want_input_grad:
                 # the network input (1 channel, no prologue): conv adjoint with the output padded to 8 channels, plus

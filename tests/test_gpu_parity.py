@@ -848,3 +848,31 @@ def test_dropout_mask_statistics_and_scalar_vector_agreement(native):
     assert torch.equal(m4.reshape(-1), m8.reshape(-1))
     m8b = native.prologue_bwd(ones8, ones8, 0, keep_prob=0.7, seed=4).float()
     assert 0.35 < (m8b.reshape(-1) == m8.reshape(-1)).float().mean().item() < 0.75   # independent masks agree on ~58 %
+
+
+@pytest.mark.parametrize("B,H,W,C,N,kind,acc,keep", [(2, 32, 64, 16, 16, 1, False, 1.0), (2, 32, 64, 8, 16, 1, True, 1.0),
+                                                     (2, 32, 32, 32, 64, 1, True, 0.7), (2, 20, 28, 64, 64, 1, False, 0.7),
+                                                     (2, 32, 64, 16, 32, 3, True, 1.0), (40, 32, 64, 16, 16, 1, True, 1.0)])
+def test_prologue_adjoint_epilogue_vs_two_step(native, B, H, W, C, N, kind, acc, keep):
+    """FN_EPI_PRO_BWD (data-gradient conv + prologue adjoint + dropout mask in one launch) against the conv followed
+    by fn_prologue_bwd."""
+    g = torch.Generator().manual_seed(41)
+    mult = 2 if kind in (1, 3) else 1
+    cy = N // mult
+    gx = torch.randn(B, H, W, C, generator=g).to("cuda", torch.bfloat16)
+    w16 = ((torch.rand(9, C, N, generator=g) * 2 - 1) * 0.2).to("cuda", torch.bfloat16)
+    z = torch.randn(B, H, W, cy, generator=g).to("cuda", torch.bfloat16)
+    base = torch.randn(B, H, W, cy, generator=g).to("cuda", torch.bfloat16)
+    bias = torch.zeros(N, device="cuda")
+    w_tc = native.pack_conv_weights_tc(w16, None, 3, C, 0, N, False)
+    kw = dict(B=B, H=H, W=W, Cin=C, Cout=N, ksize=3, stride=1, prologue=0, w_tc=w_tc)
+    fused = base.clone()
+    akw = dict(epilogue=native.EPI_PRO_BWD, res=z, keep_prob=keep, dropout_seed=6, adj_prologue=kind, adj_accumulate=acc)
+    assert native.conv_fwd(gx, w16, bias, fused, query=True, **kw, **akw)
+    native.conv_fwd(gx, w16, bias, fused, impl=native.IMPL_TCGEN05, **kw, **akw)
+    dA = torch.empty((B, H, W, N), device="cuda", dtype=torch.bfloat16)
+    native.conv_fwd(gx, w16, bias, dA, epilogue=native.EPI_BIAS, impl=native.IMPL_TCGEN05, **kw)
+    two = native.prologue_bwd(dA, z, kind, out=base.clone(), accumulate=acc, keep_prob=keep, seed=6)
+    torch.cuda.synchronize()
+    assert native.tc_status() == 0
+    assert rel_l2(fused, two) < 2e-3
