@@ -203,7 +203,7 @@ __device__ __forceinline__ void sp_shortcut_generic(const SpParams& p, int F, in
   }
 }
 
-template <int CLOG, int J, bool GATE, bool SKIP>
+template <int CLOG, int J, bool GATE, bool SKIP, bool DROP = false>
 __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__ SpParams p) {
   using Cfg = SpCfg<CLOG, J, GATE, SKIP>;
   extern __shared__ unsigned char smem_raw[];
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
       if (it >= 2) ok = ok && ptx::mbar_wait(bar(SB_TF + s), prev); // MMAs of tile it-2 no longer read planes[s]
       if (!ok) atomicCAS(p.status, 0, 11);
       if (stamp) stamp[1] = clock64();
-      if (p.keep_prob < 1.0f) {
+      if (DROP) {          // a separate instantiation: the mask hashing must not cost the inference kernels registers
         int b, y0, x0;
         tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, y0, x0);
         transform_tile_dropout<Cfg>(sbase + Cfg::OFF_STAGE + s * Cfg::STAGE_BYTES, planes, tid, p, b, y0, x0);
@@ -523,7 +523,7 @@ static bool make_map_nhwc(CUtensorMap* tm, const void* base, int B, int H, int W
 int* tc_status_word();   // conv_tc.cu: lazily allocated device status word
 void tc_timing_buffer(long long** buf, int* ctas);   // conv_tc.cu: debug stamp buffer (fn_debug_set_timing)
 
-template <int CLOG, int J, bool GATE, bool SKIP>
+template <int CLOG, int J, bool GATE, bool SKIP, bool DROP = false>
 static int launch_s1p(const fn_conv_desc& d, cudaStream_t stream) {
   using Cfg = SpCfg<CLOG, J, GATE, SKIP>;
   SpParams p;
@@ -565,7 +565,7 @@ static int launch_s1p(const fn_conv_desc& d, cudaStream_t stream) {
   p.gate_bwd = d.epilogue == FN_EPI_GATE_BWD ? 1 : 0;
   tc_timing_buffer(&p.timing, &p.timing_ctas);
 
-  auto kern = k_conv_s1p<CLOG, J, GATE, SKIP>;
+  auto kern = k_conv_s1p<CLOG, J, GATE, SKIP, DROP>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
@@ -605,7 +605,8 @@ bool conv_s1p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
 #define SP_CASE(CL, JJ, G, S)                                                                     \
   if (clog == CL && ((d.W % (8 * JJ)) == 0 || JJ == 1) && gate == G && skip == S &&               \
       SpCfg<CL, JJ, G, S>::SMEM <= (CL == 2 ? 200 : smem_cap_kb) * 1024) {                        \
-    if (!dry_run) rc = launch_s1p<CL, JJ, G, S>(d, stream);                                       \
+    if (!dry_run) rc = (!S && d.keep_prob < 1.0f) ? launch_s1p<CL, JJ, G, false, true>(d, stream)   \
+                                                  : launch_s1p<CL, JJ, G, S>(d, stream);            \
     return true;                                                                                  \
   }
   SP_CASE(0, 4, true, false) SP_CASE(0, 4, false, false) SP_CASE(0, 4, false, true)
