@@ -158,6 +158,12 @@ def run_reference(args, rank, world):
     }))
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of this command
+# (profiles/r1_prof_v9_k_conv_s1p_summary.csv: 67.17 MB read + 5.69 MB written back so far; the rest of the 33.5 MB
+# output was still in L2 when the kernel ended).  Keyed by (layer, batch): other shapes report null.
+NCU_TRAFFIC_BYTES = {("resnet_up_4_0_conv_1_conv", 64): 72.85e6}
+
+
 def layer_profile(x_dev, reps=5):
     """Per-launch CUDA-event times of every kernel of one eager forward (median over reps)."""
     import model.flow_architecture as arch
@@ -349,7 +355,7 @@ def main():
             "achieved": top["tflops"] if top["bound"] == "tensor" else top["gbs"],
             "peak": peaks["tc_burst"] if top["bound"] == "tensor" else peaks["hbm"],
             "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s",
-            "frac": top["frac"], "traffic": None,
+            "frac": top["frac"], "traffic": NCU_TRAFFIC_BYTES.get((top["name"], B)),
             "kernel": top["name"], "kernel_ms": top["ms"], "share_of_step": top["ms"] / total_ms,
             "tcgen05": top["tcgen05"], "peak_source": peaks["source"] + " (burst; kernel timed alone)",
             "whole_net": {
