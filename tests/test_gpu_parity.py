@@ -876,3 +876,46 @@ def test_prologue_adjoint_epilogue_vs_two_step(native, B, H, W, C, N, kind, acc,
     torch.cuda.synchronize()
     assert native.tc_status() == 0
     assert rel_l2(fused, two) < 2e-3
+
+
+def test_flow_test_script_on_a_trained_checkpoint(native, tmp_path, monkeypatch):
+    """test/flow_test.py (reference test/flow_test.py:52-100): restores the flag-named checkpoint, runs image by image,
+    builds the [true | generated | difference] display image.  Uses a TFRecords test set written on the spot."""
+    import importlib.util
+    import model.flow_architecture as arch
+    import model.flow_net as flow_net
+    import input.flow_input as fi
+    from model import flags
+    from utils import checkpoint
+    from utils.experiment_manager import make_checkpoint_path
+    from utils.synthetic import synth_boundary, synth_sflow
+    spec = importlib.util.spec_from_file_location(
+        "flow_test_script", os.path.join(os.path.dirname(os.path.abspath(native.__file__)), "test", "flow_test.py"))
+    ft = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ft)
+    b = synth_boundary(3, 128, 256, seed=8)
+    s = synth_sflow(b)
+    rec = str(tmp_path / "test.tfrecords")
+    fi.write_tfrecords(rec, b, s)
+    old = {k: getattr(flags.FLAGS, k) for k in ("base_dir", "data_glob", "out_dir")}
+    try:
+        flags.FLAGS.base_dir = str(tmp_path / "ckpt")
+        flags.FLAGS.data_glob = rec
+        flags.FLAGS.out_dir = str(tmp_path / "out")
+        monkeypatch.chdir(tmp_path)                  # no ../data/computed_car_flow here
+        arch.reset_variables(4321)
+        flow_net.inference(torch.from_numpy(b[:1]).cuda(), 1.0)          # create the variables of a "trained" net
+        want = flow_net.inference(torch.from_numpy(b).cuda(), 1.0).cpu().numpy()
+        checkpoint.save(make_checkpoint_path(flags.FLAGS.base_dir, flags.FLAGS), 7, arch.global_variables())
+        arch.reset_variables(1234)
+        results = ft.evaluate()
+        assert len(results) == 3
+        for i, (name, err) in enumerate(results):
+            ref = np.linalg.norm(s[i] - want[i]) / np.linalg.norm(s[i])
+            assert abs(err - ref) < 1e-3 * ref, (name, err, ref)        # the restored net produced these fields
+            img = np.load(os.path.join(flags.FLAGS.out_dir, "flow_%04d.npy" % i))
+            assert img.shape == (128, 3 * 256)
+    finally:
+        for k, v in old.items():
+            setattr(flags.FLAGS, k, v)
+        arch.reset_variables(1234)
