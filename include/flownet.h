@@ -209,6 +209,24 @@ int64_t fn_tfrecord_write_flow_example(uint8_t* dst, int64_t capacity, const uin
 uint32_t fn_crc32c(const uint8_t* p, int64_t n);          /* SSE4.2 instruction when the CPU has it */
 uint32_t fn_crc32c_portable(const uint8_t* p, int64_t n); /* table-driven */
 
+/* ---- labelled-data generator: D2Q9 BGK lattice-Boltzmann channel flow (replaces the MechSys program
+ * fluid_generator/generate_xiao_fluid_flow.cpp: Zou-He parabolic inlet :147-165, density outlet :170-187, bounce-back
+ * solids, tau = 3 nu + 1/2 with nu = u_max*200/Re :222-231, start at rho0 = 1, v0 = (0.08, 0) :355-363, 10000 steps) -- */
+typedef struct fn_lbm_desc {
+  int32_t B, nx, ny;        /* B independent simulations on nx x ny lattices (reference: nx = 2*ny + 128 = 384, ny = 128) */
+  int32_t dtype;            /* 0: fp32 populations, 1: fp64 (MechSys computes in double) */
+  double  tau;              /* BGK relaxation time (reference: 0.65) */
+  double  u_max;            /* peak of the parabolic inlet profile (reference: 0.1) */
+  double  rho_out;          /* outlet density (reference: 1.0) */
+  const uint8_t* solid;     /* [B, ny, nx], 1 = solid */
+  void*   f_a;              /* populations [B, 9, ny, nx] (current state) */
+  void*   f_b;              /* second lattice of the same size */
+} fn_lbm_desc;
+int fn_lbm_init(const fn_lbm_desc* d, double rho0, double vx0, double vy0, void* stream);   /* f_a <- equilibrium */
+int fn_lbm_steps(const fn_lbm_desc* d, int32_t nsteps, void* stream);                       /* nsteps even; result in f_a */
+/* vel: fp32 [B, ny, nx, 2] (and rho: fp32 [B, ny, nx] or NULL) of the current state; solid cells report 0 */
+int fn_lbm_fields(const fn_lbm_desc* d, float* vel, float* rho, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

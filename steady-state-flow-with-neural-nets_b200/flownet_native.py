@@ -36,6 +36,14 @@ class ConvDesc(C.Structure):
     ]
 
 
+class LbmDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("dtype", C.c_int32),
+        ("tau", C.c_double), ("u_max", C.c_double), ("rho_out", C.c_double),
+        ("solid", C.c_void_p), ("f_a", C.c_void_p), ("f_b", C.c_void_p),
+    ]
+
+
 class TConvDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
@@ -77,6 +85,9 @@ SYMBOLS = [
     ("fn_tfrecord_index", C.c_int64, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int32]),
     ("fn_tfrecord_parse_flow_example", C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64]),
     ("fn_tfrecord_write_flow_example", C.c_int64, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64]),
+    ("fn_lbm_init", C.c_int, [C.POINTER(LbmDesc), C.c_double, C.c_double, C.c_double, _P]),
+    ("fn_lbm_steps", C.c_int, [C.POINTER(LbmDesc), C.c_int32, _P]),
+    ("fn_lbm_fields", C.c_int, [C.POINTER(LbmDesc), _P, _P, _P]),
     ("fn_crc32c", C.c_uint32, [_P, C.c_int64]),
     ("fn_crc32c_portable", C.c_uint32, [_P, C.c_int64]),
 ]

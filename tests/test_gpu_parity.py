@@ -919,3 +919,57 @@ def test_flow_test_script_on_a_trained_checkpoint(native, tmp_path, monkeypatch)
         for k, v in old.items():
             setattr(flags.FLAGS, k, v)
         arch.reset_variables(1234)
+
+
+# ---------------------------------------------------------------- lattice-Boltzmann data generator
+def _lbm_case(B, ny, nx, seed):
+    rng = np.random.default_rng(seed)
+    solid = np.zeros((B, ny, nx), np.uint8)
+    solid[:, 0, :] = solid[:, -1, :] = 1
+    for b in range(B):
+        cy, cx = rng.integers(6, ny - 6), rng.integers(8, nx // 2)
+        yy, xx = np.mgrid[0:ny, 0:nx]
+        solid[b][(yy - cy) ** 2 + (xx - cx) ** 2 < rng.integers(3, 6) ** 2] = 1
+    return solid
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-11), (torch.float32, 2e-4)])
+def test_lbm_kernel_vs_oracle(native, dtype, tol):
+    """csrc/lbm.cu against oracle/lbm_oracle.py: same operations in the same order, so fp64 agrees to rounding."""
+    from oracle import lbm_oracle as lo
+    from fluid_generator import lbm
+    solid = _lbm_case(2, 24, 40, seed=1)
+    steps = 60
+    sim = lbm.ChannelFlow(solid, dtype=dtype)
+    sim.step(steps)
+    vel, rho = sim.fields(want_rho=True)
+    torch.cuda.synchronize()
+    r, vx, vy = lo.run(solid.astype(bool), steps)
+    ref = np.stack([vx, vy], axis=-1)
+    assert np.isfinite(vel.cpu().numpy()).all()
+    if dtype == torch.float64:      # fields() rounds to fp32 on output: compare the populations' moments in fp64
+        f = sim.f_a.cpu().numpy().transpose(1, 0, 2, 3).copy()
+        lo.apply_bc(f, lo.inlet_profile(24, 0.1), 1.0)
+        r2, vx2, vy2 = lo.macroscopic(f, solid.astype(bool))
+        assert np.abs(vx2 - vx).max() < tol and np.abs(vy2 - vy).max() < tol and np.abs(r2 - r).max() < tol
+    assert np.abs(vel.cpu().numpy() - ref).max() < max(tol, 1e-6)
+    assert np.abs(rho.cpu().numpy() - r).max() < max(tol, 1e-6)
+    assert (vel.cpu().numpy()[solid.astype(bool)] == 0).all()
+
+
+def test_lbm_generates_dataset_records(native, tmp_path):
+    """boundary -> simulation domain (walls, 128 spare columns) -> flow -> cropped dataset pair -> TFRecords."""
+    from fluid_generator import lbm
+    import input.flow_input as fi
+    from utils.synthetic import synth_boundary
+    b = synth_boundary(2, 128, 256, seed=3)
+    bb, s = lbm.simulate(b, steps=400)
+    assert bb.shape == (2, 128, 256, 1) and tuple(s.shape) == (2, 128, 256, 2)
+    s = s.cpu().numpy()
+    assert np.isfinite(s).all() and 0.03 < s[..., 0].mean() < 0.12      # the channel carries the inlet's flux
+    assert (s[bb[..., 0] == 1] == 0).all()                              # no flow inside solids
+    assert (bb[:, 0] == 1).all() and (bb[:, -1] == 1).all()             # channel walls (:345-352)
+    path = str(tmp_path / "lbm.tfrecords")
+    fi.write_tfrecords(path, bb, s)
+    got = list(fi.read_data(path))
+    assert np.array_equal(got[1][0], bb[1]) and np.array_equal(got[1][1], s[1])
