@@ -54,49 +54,69 @@ __device__ __forceinline__ void boundary_columns(T (&f)[9], int ix, int iy, cons
 template <typename T>
 __device__ __forceinline__ T weight(int k) { return k == 0 ? (T)4 / (T)9 : (k < 5 ? (T)1 / (T)9 : (T)1 / (T)36); }
 
+// collision of one cell (after the boundary columns were closed): BGK for fluid, full bounce-back for solids
 template <typename T>
-__global__ void __launch_bounds__(256) k_lbm_step(const Args<T> a) {
+__device__ __forceinline__ void collide(const T (&f)[9], bool is_solid, T inv_tau, T (&post)[9]) {
+  if (is_solid) {
+    const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+#pragma unroll
+    for (int k = 0; k < 9; ++k) post[k] = f[opp[k]];
+    return;
+  }
+  T rho = 0, mx = 0, my = 0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    rho += f[k];
+    mx += (T)c_cx[k] * f[k];
+    my += (T)c_cy[k] * f[k];
+  }
+  const T vx = mx / rho, vy = my / rho;
+  const T vv = vx * vx + vy * vy;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const T cu = (T)c_cx[k] * vx + (T)c_cy[k] * vy;
+    const T feq = weight<T>(k) * rho * ((T)1 + (T)3 * cu + (T)4.5 * cu * cu - (T)1.5 * vv);
+    post[k] = f[k] - (f[k] - feq) * inv_tau;
+  }
+}
+
+// grid = (ceil(nx / (128 * CELLS)), ny, B): no index division; a thread owns CELLS cells 128 columns apart, so every
+// load / store of a warp stays contiguous and CELLS x 9 loads are in flight per thread (fp32 needs the second cell to
+// keep enough bytes in flight; fp64 does not)
+template <typename T, int CELLS>
+__global__ void __launch_bounds__(128) k_lbm_step(const Args<T> a) {
+  const int iy = blockIdx.y;
+  const long long b = blockIdx.z;
   const long long plane = (long long)a.ny * a.nx;
-  const long long cells = (long long)a.B * plane;
-  for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < cells; cell += (long long)gridDim.x * blockDim.x) {
-    const int ix = (int)(cell % a.nx);
-    const int iy = (int)((cell / a.nx) % a.ny);
-    const long long b = cell / plane;
-    const T* fi = a.fin + b * 9 * plane + (long long)iy * a.nx + ix;
-    T f[9];
+  const long long row = b * plane + (long long)iy * a.nx;
+  const T* __restrict__ fi = a.fin + b * 9 * plane + (long long)iy * a.nx;
+  T f[CELLS][9];
+  int ixs[CELLS];
+  bool sol[CELLS];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) f[k] = fi[k * plane];
-    boundary_columns<T>(f, ix, iy, a);
+  for (int c = 0; c < CELLS; ++c) {
+    ixs[c] = (blockIdx.x * CELLS + c) * 128 + threadIdx.x;
+    sol[c] = false;
+    if (ixs[c] < a.nx) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) f[c][k] = __ldg(fi + k * plane + ixs[c]);
+      sol[c] = a.solid[row + ixs[c]] != 0;
+    }
+  }
+  T* __restrict__ fo = a.fout + b * 9 * plane;
+  const int ym = iy == 0 ? a.ny - 1 : iy - 1, yp = iy == a.ny - 1 ? 0 : iy + 1;
+  const int tys[3] = {ym, iy, yp};
+#pragma unroll
+  for (int c = 0; c < CELLS; ++c) {
+    const int ix = ixs[c];
+    if (ix >= a.nx) continue;
+    boundary_columns<T>(f[c], ix, iy, a);
     T post[9];
-    if (a.solid[cell]) {
-      const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+    collide<T>(f[c], sol[c], a.inv_tau, post);
+    const int xm = ix == 0 ? a.nx - 1 : ix - 1, xp = ix == a.nx - 1 ? 0 : ix + 1;
+    const int txs[3] = {xm, ix, xp};
 #pragma unroll
-      for (int k = 0; k < 9; ++k) post[k] = f[opp[k]];
-    } else {
-      T rho = 0, mx = 0, my = 0;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        rho += f[k];
-        mx += (T)c_cx[k] * f[k];
-        my += (T)c_cy[k] * f[k];
-      }
-      const T vx = mx / rho, vy = my / rho;
-      const T vv = vx * vx + vy * vy;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const T cu = (T)c_cx[k] * vx + (T)c_cy[k] * vy;
-        const T feq = weight<T>(k) * rho * ((T)1 + (T)3 * cu + (T)4.5 * cu * cu - (T)1.5 * vv);
-        post[k] = f[k] - (f[k] - feq) * a.inv_tau;
-      }
-    }
-    T* fo = a.fout + b * 9 * plane;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      int tx = ix + c_cx[k], ty = iy + c_cy[k];
-      tx = tx < 0 ? a.nx - 1 : (tx >= a.nx ? 0 : tx);
-      ty = ty < 0 ? a.ny - 1 : (ty >= a.ny ? 0 : ty);
-      fo[k * plane + (long long)ty * a.nx + tx] = post[k];
-    }
+    for (int k = 0; k < 9; ++k) fo[k * plane + (long long)tys[c_cy[k] + 1] * a.nx + txs[c_cx[k] + 1]] = post[k];
   }
 }
 
@@ -155,13 +175,13 @@ static int steps(const fn_lbm_desc& d, int nsteps, cudaStream_t s) {
   a.inv_tau = (T)(1.0 / d.tau);
   a.u_max = (T)d.u_max;
   a.rho_out = (T)d.rho_out;
-  const long long cells = (long long)d.B * d.nx * d.ny;
   T* fa = (T*)d.f_a;
   T* fb = (T*)d.f_b;
   for (int i = 0; i < nsteps; ++i) {
     a.fin = (i & 1) ? fb : fa;
     a.fout = (i & 1) ? fa : fb;
-    k_lbm_step<T><<<grid_for(cells), 256, 0, s>>>(a);
+    constexpr int CELLS = sizeof(T) == 4 ? 3 : 1;
+    k_lbm_step<T, CELLS><<<dim3((unsigned)((d.nx + 128 * CELLS - 1) / (128 * CELLS)), (unsigned)d.ny, (unsigned)d.B), 128, 0, s>>>(a);
   }
   count_launch(nsteps);
   return check_launch("k_lbm_step");
@@ -186,7 +206,8 @@ static int fields(const fn_lbm_desc& d, float* vel, float* rho, cudaStream_t s) 
 
 static int validate(const fn_lbm_desc* d) {
   FN_REQUIRE(d != nullptr, FN_E_INVAL, "fn_lbm: null descriptor");
-  FN_REQUIRE(d->B > 0 && d->nx >= 3 && d->ny >= 3, FN_E_INVAL, "fn_lbm: bad lattice %d x %d x %d", d->B, d->ny, d->nx);
+  FN_REQUIRE(d->B > 0 && d->B <= 65535 && d->nx >= 3 && d->ny >= 3 && d->ny <= 65535, FN_E_INVAL, "fn_lbm: bad lattice %d x %d x %d",
+             d->B, d->ny, d->nx);
   FN_REQUIRE(d->dtype == 0 || d->dtype == 1, FN_E_INVAL, "fn_lbm: dtype %d (0 = fp32, 1 = fp64)", d->dtype);
   FN_REQUIRE(d->tau > 0.5, FN_E_INVAL, "fn_lbm: tau = %g must exceed 1/2", d->tau);
   FN_REQUIRE(d->solid && d->f_a && d->f_b, FN_E_INVAL, "fn_lbm: null solid / lattice buffers");
