@@ -23,25 +23,31 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) runs out, so a waiting warp
+// issues one instruction per hint period instead of spinning through the scheduler (ncu: 40 % of the instructions of a
+// persistent conv kernel were SYNCS / CS2R / ISETP / BRA of such spin loops before)
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
-// bounded wait: returns false after ~2^31 clocks (about a second) so a protocol bug cannot hang the GPU
+// bounded wait: returns false after ~2^31 clocks (about a second) so a protocol bug cannot hang the GPU; the clock is
+// read once per 32 unsuccessful tries
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 32; ++i)
+      if (mbar_try_wait(bar, parity)) return true;
     if (clock64() - t0 > (1ll << 31)) return false;
   }
-  return true;
 }
 
 // one lane of a converged warp (the same lane every time): returns 1 in that lane, 0 elsewhere
