@@ -187,6 +187,9 @@ int fn_bias_grad(const void* dY, float* db, float* workspace, int64_t npix, int3
  * FN_IMPL_AUTO runs the tcgen05 kernel (contraction over pixels, MN-major operands) when Cin, Cout are multiples of 8. */
 int64_t fn_conv_wgrad_workspace(const fn_conv_desc* d);
 int fn_conv_wgrad(const fn_conv_desc* d, const void* dY, float* dW, float* workspace, void* stream);
+/* the same plus db[n] = sum_pix dY[pix][n] (fp32 [Cout]); on the tcgen05 path the bias gradient is one more accumulator of
+ * the same kernel, fed by a plane of ones */
+int fn_conv_wgrad_bias(const fn_conv_desc* d, const void* dY, float* dW, float* db, float* workspace, void* stream);
 /* transposed conv: dW fp32 [9, Cout, Cin] (the variable's own [k,k,Cout,Cin] layout, flow_architecture.py:74) from
  * x bf16 [B,H,W,Cin] and dY bf16 [B,2H,2W,Cout].  d->impl selects the kernel as in the forward calls. */
 int64_t fn_tconv_wgrad_workspace(const fn_tconv_desc* d);

@@ -535,7 +535,8 @@ long long wgrad_workspace(long long rows, int T, int Keff, int N) { return (long
 // wgrad_tc.cu
 long long wgrad_tc_workspace(int B, int H, int W, int C, int OH, int OW, int N, int ksize, int stride, int pro);
 bool wgrad_tc_try(const void* x, const void* dY, float* partial, int B, int H, int W, int C, int OH, int OW, int N, int ksize,
-                  int stride, int pro, float keep_prob, unsigned long long seed, int* S_out, cudaStream_t stream, int& rc);
+                  int stride, int pro, float keep_prob, unsigned long long seed, int* S_out, cudaStream_t stream, int& rc,
+                  bool want_bias = false, float** bias_partial_out = nullptr);
 static long long max_ll(long long a, long long b) { return a > b ? a : b; }
 
 int conv_wgrad_launch(WgradParams& p, float* dW, float* workspace, cudaStream_t s) {
@@ -592,14 +593,28 @@ int fn_bias_grad(const void* dY, float* db, float* workspace, int64_t npix, int3
 int64_t fn_conv_wgrad_workspace(const fn_conv_desc* d) {
   if (!d) return 0;
   const int OH = (d->H + d->stride - 1) / d->stride, OW = (d->W + d->stride - 1) / d->stride;
-  return max_ll(max_ll(wgrad_workspace((long long)d->B * OH * OW, d->ksize * d->ksize, d->Cin * pro_mult(d->prologue), d->Cout),
-                       (long long)WG1_BLOCKS * 9 * d->Cout),
+  return max_ll(max_ll(max_ll(wgrad_workspace((long long)d->B * OH * OW, d->ksize * d->ksize, d->Cin * pro_mult(d->prologue), d->Cout),
+                              (long long)WG1_BLOCKS * 9 * d->Cout),
+                       bias_grad_workspace((long long)d->B * OH * OW, d->Cout)),
                 wgrad_tc_workspace(d->B, d->H, d->W, d->Cin, OH, OW, d->Cout, d->ksize, d->stride, d->prologue));
 }
 
 /* d describes the FORWARD conv (x, dims, ksize, stride, prologue, keep_prob/seed; w, bias, y are ignored);
  * dY: bf16 [B,OH,OW,Cout]; dW: fp32 [k*k, Keff, Cout] (TF HWIO flattened) */
+static int conv_wgrad_impl(const fn_conv_desc* d, const void* dY, float* dW, float* db, float* workspace, void* stream);
+
 int fn_conv_wgrad(const fn_conv_desc* d, const void* dY, float* dW, float* workspace, void* stream) {
+  return conv_wgrad_impl(d, dY, dW, nullptr, workspace, stream);
+}
+
+/* the same plus the bias gradient db[n] = sum_pix dY[pix][n] (fp32 [Cout]): on the tensor-core path it is one more
+ * accumulator of the same kernel (a plane of ones as the A operand), otherwise the bias kernel runs after it */
+int fn_conv_wgrad_bias(const fn_conv_desc* d, const void* dY, float* dW, float* db, float* workspace, void* stream) {
+  FN_REQUIRE(db != nullptr, FN_E_INVAL, "fn_conv_wgrad_bias: null db");
+  return conv_wgrad_impl(d, dY, dW, db, workspace, stream);
+}
+
+static int conv_wgrad_impl(const fn_conv_desc* d, const void* dY, float* dW, float* db, float* workspace, void* stream) {
   FN_REQUIRE(d && d->x && dY && dW && workspace, FN_E_INVAL, "fn_conv_wgrad: null argument");
   FN_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, FN_E_INVAL, "fn_conv_wgrad: bad dims");
   FN_REQUIRE((d->ksize == 1 || d->ksize == 3) && (d->stride == 1 || d->stride == 2), FN_E_UNSUPPORTED,
@@ -611,16 +626,22 @@ int fn_conv_wgrad(const fn_conv_desc* d, const void* dY, float* dW, float* works
     count_launch();
     int rc = check_launch("k_wgrad_cin1");
     if (rc) return rc;
-    return reduce_partials(workspace, dW, 9ll * d->Cout, WG1_BLOCKS, (cudaStream_t)stream);
+    rc = reduce_partials(workspace, dW, 9ll * d->Cout, WG1_BLOCKS, (cudaStream_t)stream);
+    if (rc || !db) return rc;
+    return bias_grad(dY, db, workspace, (long long)d->B * d->H * d->W, d->Cout, (cudaStream_t)stream);
   }
   if (d->impl != FN_IMPL_SIMT) {      // tensor-core kernel when the shape has one
     const int OH = (d->H + d->stride - 1) / d->stride, OW = (d->W + d->stride - 1) / d->stride;
     int S = 0, rc = 0;
+    float* bias_partial = nullptr;
     if (wgrad_tc_try(d->x, dY, workspace, d->B, d->H, d->W, d->Cin, OH, OW, d->Cout, d->ksize, d->stride, d->prologue, d->keep_prob,
-                     d->dropout_seed, &S, (cudaStream_t)stream, rc)) {
+                     d->dropout_seed, &S, (cudaStream_t)stream, rc, db != nullptr, &bias_partial)) {
       if (rc) return rc;
-      return reduce_partials(workspace, dW, (long long)d->ksize * d->ksize * d->Cin * pro_mult(d->prologue) * d->Cout, S,
-                             (cudaStream_t)stream);
+      rc = reduce_partials(workspace, dW, (long long)d->ksize * d->ksize * d->Cin * pro_mult(d->prologue) * d->Cout, S,
+                           (cudaStream_t)stream);
+      if (rc || !db) return rc;
+      if (bias_partial) return reduce_partials(bias_partial, db, d->Cout, S, (cudaStream_t)stream);
+      return bias_grad(dY, db, workspace, (long long)d->B * OH * OW, d->Cout, (cudaStream_t)stream);
     }
     FN_REQUIRE(d->impl != FN_IMPL_TCGEN05, FN_E_UNSUPPORTED, "fn_conv_wgrad: no tcgen05 kernel for this shape");
   }
@@ -639,7 +660,11 @@ int fn_conv_wgrad(const fn_conv_desc* d, const void* dY, float* dW, float* works
   p.transposed = 0;
   p.keep_prob = d->keep_prob;
   p.seed = d->dropout_seed;
-  return conv_wgrad_launch(p, dW, workspace, (cudaStream_t)stream);
+  {
+    int rc = conv_wgrad_launch(p, dW, workspace, (cudaStream_t)stream);
+    if (rc || !db) return rc;
+    return bias_grad(dY, db, workspace, (long long)p.B * p.OH * p.OW, p.N, (cudaStream_t)stream);
+  }
 }
 
 int64_t fn_tconv_wgrad_workspace(const fn_tconv_desc* d) {

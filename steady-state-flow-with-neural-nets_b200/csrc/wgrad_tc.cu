@@ -28,7 +28,8 @@ namespace wg {
 constexpr int TV = 8, TU = 16;                 // pixel tile of dY: 8 rows of 16 pixels = 8 K-steps
 constexpr int THREADS = 192;
 constexpr int WARP_PRODUCER = 4, WARP_ISSUER = 5;
-constexpr int HDR = 512;
+constexpr int HDR = 1024;           // mbarriers [0,256), TMEM slot at 256, 256 B of bf16 ones at 512
+constexpr int OFF_ONES = 512;
 constexpr int MAXBUF = 8;
 constexpr int DY_PLANE = TV * TU * 16;         // bytes of one 8-channel dY plane
 enum { MODE_S1 = 0, MODE_S2 = 1 };
@@ -47,6 +48,7 @@ struct Params {
   CUtensorMap tm_x;     // 4-D (C, W, H, B)
   CUtensorMap tm_dy;    // 5-D (8, N/8, OW, OH, B)
   float* partial;       // [S][T][Keff][N]
+  float* bias_partial;  // [S][N] or null: db[n] = sum_pix dY[pix][n] as one more accumulator fed by a plane of ones
   int* status;
   int B, H, W, C, OH, OW, N;
   int CH, chshift;      // raw 8-channel chunks of x
@@ -182,6 +184,9 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
     }
     __syncwarp();
   }
+  const bool do_bias = p.bias_partial != nullptr && grp == 0;
+  if (tid < 16) sts128(sbase + OFF_ONES + (uint32_t)tid * 16u, make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u));
+  ptx::fence_proxy_async_smem();
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
@@ -249,6 +254,15 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
                              (it == 0 && v == 0) ? 0u : 1u);
         }
       }
+      if (do_bias) {
+        // bias gradient: A = 16 pixels x 8 "channels" of ones (every M group reads the same 256 bytes, SBO = 0), so every
+        // accumulator row is sum_pix dY[pix][:]; dY is zero outside the image (TMA fill), no masking needed
+        const uint64_t ones = ptx::smem_desc(sbase + OFF_ONES, 128u, 0u);
+        const uint32_t d_col = tmem_base + (uint32_t)(NT * p.Npad);
+#pragma unroll
+        for (int v = 0; v < TV; ++v)
+          if (do_mma) ptx::mma_bf16_ss(d_col, ones, b_tmpl + (uint32_t)((v * TU * 16) >> 4), p.idesc, (it == 0 && v == 0) ? 0u : 1u);
+      }
       if (leader) ptx::mma_commit(bar(SB_TF + s));
       __syncwarp();
     }
@@ -295,6 +309,17 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
       krow = row_local - du_row * kpl * 8;
     }
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if (do_bias && warp == 0) {          // accumulator row 0 = TMEM lane 0 for M = 128 and M = 64 alike
+      for (int n0 = 0; n0 < p.N; n0 += 8) {
+        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (n_local > 0) ptx::tmem_ld8(tmem_base + (uint32_t)(NT * p.Npad + n0), o);
+        if (lane == 0 && ok) {
+          float* dst = p.bias_partial + (size_t)s_idx * p.N + n0;
+          *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
 #pragma unroll 1
     for (int t = 0; t < NT; ++t) {
       const int tap = p.a3 ? 3 * t + du_row : tap0 + t;
@@ -324,6 +349,7 @@ static int g_swap = 0;
 
 struct Plan {
   int mode, NT, S, grid, smem;
+  bool bias_fits;
   Params p;
 };
 
@@ -353,7 +379,8 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
   p.a3 = (pl.mode == MODE_S1 && ksize == 3 && p.Keff <= 32 && !(g_swap & 64)) ? 1 : 0;
   pl.NT = p.a3 ? 3 : (p.T == 1 ? 1 : (9 * p.Npad <= 512 ? 9 : (3 * p.Npad <= 512 ? 3 : 1)));
   p.tap_groups = p.a3 ? 1 : p.T / pl.NT;
-  int cols = pl.NT * p.Npad;
+  pl.bias_fits = (pl.NT + 1) * p.Npad <= 512;             // room for the bias accumulator next to the tap accumulators
+  int cols = (pl.NT + (pl.bias_fits ? 1 : 0)) * p.Npad;
   p.tmem_cols = 32;
   while ((int)p.tmem_cols < cols) p.tmem_cols *= 2;
   p.tiles_u = (OW + TU - 1) / TU;
@@ -426,13 +453,16 @@ int* tc_status_word();
 long long wgrad_tc_workspace(int B, int H, int W, int C, int OH, int OW, int N, int ksize, int stride, int pro) {
   wg::Plan pl;
   if (!wg::plan(pl, B, H, W, C, OH, OW, N, ksize, stride, pro)) return 0;
-  return (long long)pl.S * pl.p.T * pl.p.Keff * N;
+  return (long long)pl.S * pl.p.T * pl.p.Keff * N + (long long)pl.S * N;      // weight partials, then bias partials
 }
 
 // returns false when this shape has no tensor-core kernel (the caller then runs the CUDA-core one);
 // on success *S_out partials of [T][Keff][N] floats are in `partial`
+// want_bias: also reduce dY over pixels; *bias_partial_out then points at [S][N] partials inside `partial`'s buffer (or is
+// null when the extra accumulator does not fit TMEM and the caller has to run the bias kernel)
 bool wgrad_tc_try(const void* x, const void* dY, float* partial, int B, int H, int W, int C, int OH, int OW, int N, int ksize,
-                  int stride, int pro, float keep_prob, unsigned long long seed, int* S_out, cudaStream_t stream, int& rc) {
+                  int stride, int pro, float keep_prob, unsigned long long seed, int* S_out, cudaStream_t stream, int& rc,
+                  bool want_bias, float** bias_partial_out) {
   using namespace wg;
   rc = 0;
   Plan pl;
@@ -459,6 +489,8 @@ bool wgrad_tc_try(const void* x, const void* dY, float* partial, int B, int H, i
       return false;
   }
   p.partial = partial;
+  p.bias_partial = (want_bias && pl.bias_fits) ? partial + (size_t)pl.S * p.T * p.Keff * N : nullptr;
+  if (bias_partial_out) *bias_partial_out = p.bias_partial;
   p.keep_prob = keep_prob;
   p.seed = seed;
   p.status = tc_status_word();

@@ -80,6 +80,7 @@ SYMBOLS = [
     ("fn_bias_grad", C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
     ("fn_conv_wgrad_workspace", C.c_int64, [C.POINTER(ConvDesc)]),
     ("fn_conv_wgrad", C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P]),
+    ("fn_conv_wgrad_bias", C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P]),
     ("fn_tconv_wgrad_workspace", C.c_int64, [C.POINTER(TConvDesc)]),
     ("fn_tconv_wgrad", C.c_int, [C.POINTER(TConvDesc), _P, _P, _P, _P]),
     ("fn_tfrecord_index", C.c_int64, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int32]),
@@ -330,9 +331,9 @@ def bias_grad(dY, out):
     _check(lib.fn_bias_grad(_ptr(dY), _ptr(out), _ptr(ws), npix, N, stream_ptr()), "fn_bias_grad")
 
 
-def conv_wgrad(x, dY, out, *, ksize, stride, prologue, keep_prob=1.0, dropout_seed=0, impl=IMPL_AUTO):
-    """out: fp32 [k*k, Keff, Cout] <- sum over pixels of pro(x) (x) dY"""
-    _require_cuda(x, dY, out)
+def conv_wgrad(x, dY, out, *, ksize, stride, prologue, keep_prob=1.0, dropout_seed=0, impl=IMPL_AUTO, db=None):
+    """out: fp32 [k*k, Keff, Cout] <- sum over pixels of pro(x) (x) dY; db (fp32 [Cout], optional) <- sum over pixels of dY"""
+    _require_cuda(x, dY, out, db)
     d = ConvDesc()
     d.impl = impl
     d.B, d.H, d.W, d.Cin = x.shape
@@ -342,7 +343,10 @@ def conv_wgrad(x, dY, out, *, ksize, stride, prologue, keep_prob=1.0, dropout_se
     d.keep_prob = float(keep_prob)
     d.dropout_seed = int(dropout_seed)
     ws = _workspace(lib.fn_conv_wgrad_workspace(C.byref(d)), x.device)
-    _check(lib.fn_conv_wgrad(C.byref(d), _ptr(dY), _ptr(out), _ptr(ws), stream_ptr()), "fn_conv_wgrad")
+    if db is not None:
+        _check(lib.fn_conv_wgrad_bias(C.byref(d), _ptr(dY), _ptr(out), _ptr(db), _ptr(ws), stream_ptr()), "fn_conv_wgrad_bias")
+    else:
+        _check(lib.fn_conv_wgrad(C.byref(d), _ptr(dY), _ptr(out), _ptr(ws), stream_ptr()), "fn_conv_wgrad")
 
 
 def tconv_wgrad(x, dY, out, *, impl=IMPL_AUTO):

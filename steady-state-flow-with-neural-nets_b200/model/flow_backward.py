@@ -131,10 +131,12 @@ def backward(tape, sflow_p, sflow, flat: FlatParams = None, want_input_grad=Fals
     params = flat is not None
     d_input = None
 
-    def wgrad_into(name, x, dY, ksize, stride, pro, keep_prob=1.0, seed=0):
+    def wgrad_into(name, x, dY, ksize, stride, pro, keep_prob=1.0, seed=0, bias=False):
+        """weight gradient (and, with bias=True, the bias gradient of the same dY in the same launch)"""
         if params:
             native.conv_wgrad(x, dY, flat.grad_view(name + '/weights').view(ksize * ksize, -1, dY.shape[-1]), ksize=ksize,
-                              stride=stride, prologue=pro, keep_prob=keep_prob, dropout_seed=seed)
+                              stride=stride, prologue=pro, keep_prob=keep_prob, dropout_seed=seed,
+                              db=flat.grad_view(name + '/biases') if bias else None)
 
     def bgrad_into(name, dY):
         if params:
@@ -193,15 +195,13 @@ def backward(tape, sflow_p, sflow, flat: FlatParams = None, want_input_grad=Fals
                     dc2 = native.gate_bwd(c2, g)
             else:
                 dc2 = g
-            bgrad_into(s2, dc2)
-            wgrad_into(s2, x_1, dc2, 3, 1, pro, keep_p, seed)
+            wgrad_into(s2, x_1, dc2, 3, 1, pro, keep_p, seed, bias=True)
             dx_1 = _conv_dgrad_adjoint(dc2, _dgrad_weights_s1(V[s2 + '/weights'], 3), mult * F_, x_1, pro, dev,
                                        keep_prob=keep_p, seed=seed)
             # ---- conv_1 (+nin skip)
             s1 = name + '_conv_1_conv'
             pro1 = native.PRO_NONE if cin == 1 else pro
-            bgrad_into(s1, dx_1)
-            wgrad_into(s1, x, dx_1, 3, stride, pro1)
+            wgrad_into(s1, x, dx_1, 3, stride, pro1, bias=True)
             if a is not None:
                 sn = name + '_nin_fc'
                 if params:

@@ -973,3 +973,31 @@ def test_lbm_generates_dataset_records(native, tmp_path):
     fi.write_tfrecords(path, bb, s)
     got = list(fi.read_data(path))
     assert np.array_equal(got[1][0], bb[1]) and np.array_equal(got[1][1], s[1])
+
+
+@pytest.mark.parametrize("B,H,W,C,N,ksize,stride,pro", [(2, 16, 32, 8, 16, 3, 1, 1), (3, 24, 40, 16, 32, 3, 1, 1), (2, 16, 32, 64, 128, 3, 1, 1),
+                                                        (3, 8, 16, 128, 256, 3, 1, 1), (2, 32, 64, 8, 16, 3, 2, 1), (2, 16, 32, 64, 64, 1, 1, 1),
+                                                        (40, 32, 64, 8, 8, 3, 1, 1), (2, 16, 32, 1, 8, 3, 1, 0)])
+def test_bias_gradient_fused_into_wgrad(native, B, H, W, C, N, ksize, stride, pro):
+    """fn_conv_wgrad_bias: db as one more accumulator of the tcgen05 wgrad kernel (A = a plane of ones) against the
+    stand-alone bias kernel; dW unchanged by the extra accumulator."""
+    g = torch.Generator().manual_seed(61)
+    if C == 1:
+        x = (torch.rand(B, H, W, C, generator=g) > 0.5).to("cuda", torch.bfloat16)
+    else:
+        x = torch.randn(B, H, W, C, generator=g).to("cuda", torch.bfloat16)
+    OH, OW = -(-H // stride), -(-W // stride)
+    dY = torch.randn(B, OH, OW, N, generator=g).to("cuda", torch.bfloat16)
+    mult = 2 if pro in (1, 3) else 1
+    dW0 = torch.empty((ksize * ksize, C * mult, N), device="cuda")
+    dW1 = torch.empty_like(dW0)
+    db = torch.full((N,), float("nan"), device="cuda")
+    native.conv_wgrad(x, dY, dW0, ksize=ksize, stride=stride, prologue=pro)
+    native.conv_wgrad(x, dY, dW1, ksize=ksize, stride=stride, prologue=pro, db=db)
+    ref = torch.empty(N, device="cuda")
+    native.bias_grad(dY, ref)
+    torch.cuda.synchronize()
+    assert native.tc_status() == 0
+    assert torch.equal(dW0, dW1)
+    assert rel_l2(db, ref) < 1e-5
+    assert rel_l2(db, dY.double().sum(dim=(0, 1, 2))) < 1e-5
