@@ -172,6 +172,11 @@ int fn_gate_bwd(const void* c2, const void* g, void* dc2, int64_t npix, int32_t 
  * -> dx bf16 [npix,C] (accumulate != 0: added to the existing dx) */
 int fn_prologue_bwd(const void* dA, const void* x, void* dx, int64_t npix, int32_t C, int32_t kind, int32_t accumulate,
                     float keep_prob, uint64_t seed, void* stream);
+/* data gradient of the nin skip (flow_architecture.py:136-142) fused with the adjoint of its concat prologue:
+ * dA[k] = sum_f dy[f] w[k][f]; da[c] (+)= dA[c] f'(a[c]) - dA[Ca+c] f'(-a[c]).  dy bf16 [npix,F] (F in 8,16,32,64),
+ * w fp32 [2 Ca, F] = the '{idx}_fc/weights' variable itself, a bf16 [npix,Ca] -> da bf16 [npix,Ca] */
+int fn_nin_bwd(const void* dy, const float* w, const void* a, void* da, int64_t npix, int32_t F, int32_t Ca, int32_t kind,
+               int32_t accumulate, void* stream);
 /* adjoint of the res_block shortcut (avg-pool 2x2 'SAME' if pooled, front channel pad; :153-165):
  * g bf16 [B,OH,OW,F] -> dx bf16 [B,H,W,Cin] */
 int fn_shortcut_bwd(const void* g, void* dx, int32_t B, int32_t OH, int32_t OW, int32_t F, int32_t H, int32_t W,

@@ -236,6 +236,77 @@ __global__ void __launch_bounds__(BW_THREADS) k_bias_grad_v8(const __nv_bfloat16
   }
 }
 
+
+// ---- data gradient of the nin skip (x_1 += nin(pro(a)), flow_architecture.py:136-142) fused with the adjoint of its
+// prologue: dA[k] = sum_f dy[f] * Wn[k][f] (k < 2 Ca), d(a)[c] (+)= dA[c] f'(a[c]) - dA[Ca + c] f'(-a[c]).
+// A 1x1 conv with at most 64 x 128 weights: CUDA cores; a warp = 32 pixels of one 8-channel chunk, so the fp32 weights
+// (staged in shared memory) are broadcast reads and every thread keeps its pixel's dy row in registers.
+template <int F>
+__global__ void __launch_bounds__(256) k_nin_bwd(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ w,
+                                                 const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ da, long long npix,
+                                                 int Ca, int kind, int accumulate) {
+  extern __shared__ float ws[];                       // [2 Ca][F]
+  for (int i = threadIdx.x; i < 2 * Ca * F; i += 256) ws[i] = w[i];
+  __syncthreads();
+  const int chunks = Ca >> 3;
+  const long long total = npix * chunks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int chunk = (int)(i / npix);
+    const long long pix = i - (long long)chunk * npix;
+    float g[F];
+#pragma unroll
+    for (int f8 = 0; f8 < F; f8 += 8) {
+      bf16x8 v;
+      ld8(v, dy + pix * F + f8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[f8 + j] = __bfloat162float(v.h[j]);
+    }
+    bf16x8 av, old, out;
+    ld8(av, a + pix * Ca + chunk * 8);
+    if (accumulate) ld8(old, da + pix * Ca + chunk * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* w0 = ws + (chunk * 8 + j) * F;
+      const float* w1 = ws + (Ca + chunk * 8 + j) * F;
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        d0 = fmaf(g[f], w0[f], d0);
+        d1 = fmaf(g[f], w1[f], d1);
+      }
+      d0 = __bfloat162float(__float2bfloat16(d0));    // the two-launch path stores dA as bf16
+      d1 = __bfloat162float(__float2bfloat16(d1));
+      const float xf = __bfloat162float(av.h[j]);
+      float d;
+      if (kind == FN_PRO_CONCAT_ELU) {
+        const float e = __expf(-fabsf(xf));
+        d = xf > 0.f ? d0 - d1 * e : d0 * e - d1;
+      } else {                                        // FN_PRO_CONCAT_RELU
+        d = (xf > 0.f ? d0 : 0.f) - (xf < 0.f ? d1 : 0.f);
+      }
+      if (accumulate) d += __bfloat162float(old.h[j]);
+      out.h[j] = __float2bfloat16(d);
+    }
+    *reinterpret_cast<uint4*>(da + pix * Ca + chunk * 8) = out.v;
+  }
+}
+
+template <int F>
+static int nin_bwd_launch(const void* dy, const float* w, const void* a, void* da, long long npix, int Ca, int kind, int accumulate,
+                          cudaStream_t s) {
+  const size_t smem = (size_t)2 * Ca * F * sizeof(float);
+  static bool configured = false;
+  if (!configured && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_nin_bwd<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(nin_bwd): %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  k_nin_bwd<F><<<bw_grid(npix * (Ca / 8)), 256, smem, s>>>((const __nv_bfloat16*)dy, w, (const __nv_bfloat16*)a, (__nv_bfloat16*)da, npix,
+                                                            Ca, kind, accumulate);
+  count_launch();
+  return check_launch("k_nin_bwd");
+}
+
 // ---- tanh + l2 loss: loss += sum((p-t)^2)/2 ; dpre[pix, 0..1] = (p-t)*(1-p^2), channels 2..7 = 0
 __global__ void k_tanh_l2_bwd(const float* __restrict__ p, const float* __restrict__ t, float* loss,
                               __nv_bfloat16* __restrict__ dpre, long long npix) {
@@ -570,6 +641,24 @@ int fn_prologue_bwd(const void* dA, const void* x, void* dx, int64_t npix, int32
   FN_REQUIRE(dA && x && dx && npix >= 0 && C > 0, FN_E_INVAL, "fn_prologue_bwd: bad arguments");
   FN_REQUIRE(kind >= FN_PRO_NONE && kind <= FN_PRO_RELU, FN_E_INVAL, "fn_prologue_bwd: bad kind %d", kind);
   return prologue_bwd(dA, x, dx, npix, C, kind, accumulate, keep_prob, seed, (cudaStream_t)stream);
+}
+
+/* data gradient of the nin skip fused with the adjoint of its prologue (concat kinds): dy bf16 [npix,F], w fp32 [2 Ca, F]
+ * (the variable itself, TF [dim, hiddens]), a bf16 [npix,Ca] -> da bf16 [npix,Ca] (+= if accumulate) */
+int fn_nin_bwd(const void* dy, const float* w, const void* a, void* da, int64_t npix, int32_t F, int32_t Ca, int32_t kind,
+               int32_t accumulate, void* stream) {
+  FN_REQUIRE(dy && w && a && da && npix >= 0, FN_E_INVAL, "fn_nin_bwd: bad arguments");
+  FN_REQUIRE(kind == FN_PRO_CONCAT_ELU || kind == FN_PRO_CONCAT_RELU, FN_E_UNSUPPORTED, "fn_nin_bwd: concat prologues only (kind %d)", kind);
+  FN_REQUIRE((Ca & 7) == 0 && Ca >= 8 && (size_t)2 * Ca * F * 4 <= 64 * 1024, FN_E_UNSUPPORTED, "fn_nin_bwd: Ca=%d F=%d", Ca, F);
+  if (npix == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (F) {
+    case 8: return nin_bwd_launch<8>(dy, w, a, da, npix, Ca, kind, accumulate, s);
+    case 16: return nin_bwd_launch<16>(dy, w, a, da, npix, Ca, kind, accumulate, s);
+    case 32: return nin_bwd_launch<32>(dy, w, a, da, npix, Ca, kind, accumulate, s);
+    case 64: return nin_bwd_launch<64>(dy, w, a, da, npix, Ca, kind, accumulate, s);
+    default: set_error("fn_nin_bwd: F=%d (8, 16, 32, 64)", F); return FN_E_UNSUPPORTED;
+  }
 }
 
 int fn_shortcut_bwd(const void* g, void* dx, int32_t B, int32_t OH, int32_t OW, int32_t F, int32_t H, int32_t W, int32_t Cin,

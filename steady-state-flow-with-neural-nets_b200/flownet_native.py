@@ -74,6 +74,7 @@ SYMBOLS = [
     ("fn_adam_step", C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
     ("fn_gate_bwd", C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
     ("fn_prologue_bwd", C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _P]),
+    ("fn_nin_bwd", C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     ("fn_shortcut_bwd", C.c_int, [_P, _P] + [C.c_int32] * 9 + [_P]),
     ("fn_tanh_l2_bwd", C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     ("fn_bias_grad_workspace", C.c_int64, [C.c_int64, C.c_int32]),
@@ -296,6 +297,18 @@ def prologue_bwd(dA, x, kind, out=None, accumulate=False, keep_prob=1.0, seed=0)
         accumulate = False
     _check(lib.fn_prologue_bwd(_ptr(dA), _ptr(x), _ptr(out), x.numel() // Cc, Cc, kind, int(accumulate), float(keep_prob),
                                int(seed), stream_ptr()), "fn_prologue_bwd")
+    return out
+
+
+def nin_bwd(dy, w, a, kind, out=None, accumulate=False):
+    """d(a) (+)= adjoint of pro(a) applied to dy @ w^T; w: the fp32 [2*Ca, F] nin variable"""
+    _require_cuda(dy, w, a, out)
+    if out is None:
+        out = torch.empty_like(a)
+        accumulate = False
+    Ca, F = a.shape[-1], dy.shape[-1]
+    _check(lib.fn_nin_bwd(_ptr(dy), _ptr(w), _ptr(a), _ptr(out), a.numel() // Ca, F, Ca, kind, int(accumulate), stream_ptr()),
+           "fn_nin_bwd")
     return out
 
 

@@ -212,9 +212,12 @@ def backward(tape, sflow_p, sflow, flat: FlatParams = None, want_input_grad=Fals
                 if params:
                     native.conv_wgrad(a, dx_1, flat.grad_view(sn + '/weights').view(1, -1, F_), ksize=1, stride=1, prologue=pro)
                 wn = V[sn + '/weights']                                   # [mult*Ca, F]
-                dAa = _conv_plain(dx_1, wn.t().reshape(1, F_, -1).to(torch.bfloat16).contiguous(), wn.shape[0], 1, 1, dev)
                 buf, acc = grads.target(a)
-                native.prologue_bwd(dAa, a, pro, out=buf, accumulate=acc)
+                if mult == 2 and F_ in (8, 16, 32, 64) and wn.numel() * 4 <= 64 * 1024 and wn.is_contiguous():
+                    native.nin_bwd(dx_1, wn, a, pro, out=buf, accumulate=acc)       # 1x1 conv + prologue adjoint, one launch
+                else:
+                    dAa = _conv_plain(dx_1, wn.t().reshape(1, F_, -1).to(torch.bfloat16).contiguous(), wn.shape[0], 1, 1, dev)
+                    native.prologue_bwd(dAa, a, pro, out=buf, accumulate=acc)
             if cin > 1:
                 w1 = V[s1 + '/weights']                                   # [3,3,mult*cin,F]
                 buf, acc = grads.target(x)

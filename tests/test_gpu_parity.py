@@ -1001,3 +1001,20 @@ def test_bias_gradient_fused_into_wgrad(native, B, H, W, C, N, ksize, stride, pr
     assert torch.equal(dW0, dW1)
     assert rel_l2(db, ref) < 1e-5
     assert rel_l2(db, dY.double().sum(dim=(0, 1, 2))) < 1e-5
+
+
+@pytest.mark.parametrize("npix_shape,F,Ca,kind,acc", [((3, 32, 64), 8, 8, 1, True), ((2, 16, 32), 16, 16, 1, False), ((2, 16, 32), 32, 32, 1, True),
+                                                      ((2, 8, 16), 64, 64, 1, True), ((2, 16, 32), 16, 16, 3, True)])
+def test_nin_backward_kernel_vs_two_step(native, npix_shape, F, Ca, kind, acc):
+    """fn_nin_bwd (1x1 data gradient of the skip + adjoint of its concat prologue) vs conv(ksize=1) + fn_prologue_bwd."""
+    g = torch.Generator().manual_seed(71)
+    B, H, W = npix_shape
+    dy = torch.randn(B, H, W, F, generator=g).to("cuda", torch.bfloat16)
+    wn = ((torch.rand(2 * Ca, F, generator=g) * 2 - 1) * 0.3).to("cuda")
+    a = torch.randn(B, H, W, Ca, generator=g).to("cuda", torch.bfloat16)
+    base = torch.randn(B, H, W, Ca, generator=g).to("cuda", torch.bfloat16)
+    fused = native.nin_bwd(dy, wn, a, kind, out=base.clone(), accumulate=acc)
+    dA = (dy.double().reshape(-1, F) @ wn.double().t()).reshape(B, H, W, 2 * Ca).to(torch.bfloat16)
+    two = native.prologue_bwd(dA, a, kind, out=base.clone(), accumulate=acc)
+    torch.cuda.synchronize()
+    assert rel_l2(fused, two) < 3e-3
