@@ -245,7 +245,7 @@ template <int F>
 __global__ void __launch_bounds__(256) k_nin_bwd(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ w,
                                                  const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ da, long long npix,
                                                  int Ca, int kind, int accumulate) {
-  extern __shared__ float ws[];                       // [2 Ca][F]
+  extern __shared__ __align__(16) float ws[];         // [2 Ca][F]
   for (int i = threadIdx.x; i < 2 * Ca * F; i += 256) ws[i] = w[i];
   __syncthreads();
   const int chunks = Ca >> 3;
@@ -266,13 +266,14 @@ __global__ void __launch_bounds__(256) k_nin_bwd(const __nv_bfloat16* __restrict
     if (accumulate) ld8(old, da + pix * Ca + chunk * 8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float* w0 = ws + (chunk * 8 + j) * F;
-      const float* w1 = ws + (Ca + chunk * 8 + j) * F;
+      const float4* w0 = reinterpret_cast<const float4*>(ws + (chunk * 8 + j) * F);       // rows are 32-byte aligned
+      const float4* w1 = reinterpret_cast<const float4*>(ws + (Ca + chunk * 8 + j) * F);
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-      for (int f = 0; f < F; ++f) {
-        d0 = fmaf(g[f], w0[f], d0);
-        d1 = fmaf(g[f], w1[f], d1);
+      for (int f4 = 0; f4 < F / 4; ++f4) {
+        const float4 u = w0[f4], v = w1[f4];
+        d0 = fmaf(g[4 * f4], u.x, d0); d0 = fmaf(g[4 * f4 + 1], u.y, d0); d0 = fmaf(g[4 * f4 + 2], u.z, d0); d0 = fmaf(g[4 * f4 + 3], u.w, d0);
+        d1 = fmaf(g[4 * f4], v.x, d1); d1 = fmaf(g[4 * f4 + 1], v.y, d1); d1 = fmaf(g[4 * f4 + 2], v.z, d1); d1 = fmaf(g[4 * f4 + 3], v.w, d1);
       }
       d0 = __bfloat162float(__float2bfloat16(d0));    // the two-launch path stores dA as bf16
       d1 = __bfloat162float(__float2bfloat16(d1));

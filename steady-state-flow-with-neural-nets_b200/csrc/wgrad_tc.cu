@@ -25,18 +25,20 @@ namespace fn {
 using namespace tma;
 namespace wg {
 
-constexpr int TV = 8, TU = 16;                 // pixel tile of dY: 8 rows of 16 pixels = 8 K-steps
+constexpr int TV = 8;                          // pixel tile of dY: 8 rows of TU = 16 (or 32) pixels = 8 (16) K-steps
 constexpr int THREADS = 192;
 constexpr int WARP_PRODUCER = 4, WARP_ISSUER = 5;
 constexpr int HDR = 1024;           // mbarriers [0,256), TMEM slot at 256, 256 B of bf16 ones at 512
 constexpr int OFF_ONES = 512;
 constexpr int MAXBUF = 8;
-constexpr int DY_PLANE = TV * TU * 16;         // bytes of one 8-channel dY plane
 enum { MODE_S1 = 0, MODE_S2 = 1 };
 
-template <int MODE>
+template <int MODE, int TU = 16>
 struct Geo {
   static constexpr bool S2 = MODE == MODE_S2;
+  static constexpr int TUX = TU;
+  static constexpr int KSU = TU / 16;                                                                     // K-steps per tile row
+  static constexpr int DY_PLANE = TV * TU * 16;                                                           // bytes of one 8-channel dY plane
   static constexpr int SW_ = S2 ? 2 * TU + 1 : TU + 2, SH_ = S2 ? 2 * TV + 1 : TV + 2, SP = SW_ * SH_;   // stage tile (TMA box)
   static constexpr int PU = S2 ? TU + 1 : TU + 2, PV = S2 ? TV + 1 : TV + 2, P = PU * PV;                // one (sub-)plane
   static constexpr int PPAD = (P & 1) ? P : P + 1;                                                       // odd: planes spread over banks
@@ -77,10 +79,9 @@ static uint32_t idesc_mn(int M, int N) {
 
 // stage [pixel][C] raw bf16 -> this CTA's operand planes: prologue (CE: the single-exponential concat_elu; else the
 // generic switch), optional dropout mask of the forward pass, parity split (stride 2), three shifted copies (a3)
-template <int MODE, bool CE, bool DROP>
+template <typename G, bool CE, bool DROP>
 __device__ __forceinline__ void transform_tile(const Params& p, uint32_t stage, uint32_t planes, int tid, int items, int mb, int b,
                                                int y0, int x0) {
-  using G = Geo<MODE>;
   const int kpl = p.kpl;
   const int mult = CE ? 2 : pro_mult(p.pro);
 #pragma unroll 2
@@ -138,9 +139,10 @@ __device__ __forceinline__ void transform_tile(const Params& p, uint32_t stage, 
   }
 }
 
-template <int MODE, int NT>
+template <int MODE, int NT, int TU = 16>
 __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Params p) {
-  using G = Geo<MODE>;
+  using G = Geo<MODE, TU>;
+  constexpr int DY_PLANE = G::DY_PLANE;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const uint32_t sbase = ptx::smem_u32(smem);
@@ -248,11 +250,12 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
         const uint64_t a_tap = a_tmpl + (uint64_t)(tapoff[t] >> 4);
         const uint32_t d_col = tmem_base + (uint32_t)(t * p.Npad);
 #pragma unroll
-        for (int v = 0; v < TV; ++v) {
-          if (do_mma)
-            ptx::mma_bf16_ss(d_col, a_tap + (uint32_t)((v * G::ROW_BYTES) >> 4), b_tmpl + (uint32_t)((v * TU * 16) >> 4), p.idesc,
-                             (it == 0 && v == 0) ? 0u : 1u);
-        }
+        for (int v = 0; v < TV; ++v)
+#pragma unroll
+          for (int ub = 0; ub < G::KSU; ++ub)
+            if (do_mma)
+              ptx::mma_bf16_ss(d_col, a_tap + (uint32_t)((v * G::ROW_BYTES + ub * 256) >> 4),
+                               b_tmpl + (uint32_t)(((v * TU + ub * 16) * 16) >> 4), p.idesc, (it == 0 && v == 0 && ub == 0) ? 0u : 1u);
       }
       if (do_bias) {
         // bias gradient: A = 16 pixels x 8 "channels" of ones (every M group reads the same 256 bytes, SBO = 0), so every
@@ -261,7 +264,11 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
         const uint32_t d_col = tmem_base + (uint32_t)(NT * p.Npad);
 #pragma unroll
         for (int v = 0; v < TV; ++v)
-          if (do_mma) ptx::mma_bf16_ss(d_col, ones, b_tmpl + (uint32_t)((v * TU * 16) >> 4), p.idesc, (it == 0 && v == 0) ? 0u : 1u);
+#pragma unroll
+          for (int ub = 0; ub < G::KSU; ++ub)
+            if (do_mma)
+              ptx::mma_bf16_ss(d_col, ones, b_tmpl + (uint32_t)(((v * TU + ub * 16) * 16) >> 4), p.idesc,
+                               (it == 0 && v == 0 && ub == 0) ? 0u : 1u);
       }
       if (leader) ptx::mma_commit(bar(SB_TF + s));
       __syncwarp();
@@ -283,11 +290,11 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
       if (!(p.swap & 16)) {
         const bool ce = p.pro == FN_PRO_CONCAT_ELU;
         if (p.keep_prob < 1.0f) {
-          if (ce) transform_tile<MODE, true, true>(p, stage, planes, tid, items, mb, b, y0, x0);
-          else transform_tile<MODE, false, true>(p, stage, planes, tid, items, mb, b, y0, x0);
+          if (ce) transform_tile<G, true, true>(p, stage, planes, tid, items, mb, b, y0, x0);
+          else transform_tile<G, false, true>(p, stage, planes, tid, items, mb, b, y0, x0);
         } else {
-          if (ce) transform_tile<MODE, true, false>(p, stage, planes, tid, items, mb, b, y0, x0);
-          else transform_tile<MODE, false, false>(p, stage, planes, tid, items, mb, b, y0, x0);
+          if (ce) transform_tile<G, true, false>(p, stage, planes, tid, items, mb, b, y0, x0);
+          else transform_tile<G, false, false>(p, stage, planes, tid, items, mb, b, y0, x0);
         }
       }
       ptx::fence_proxy_async_smem();
@@ -348,7 +355,7 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
 static int g_swap = 0;
 
 struct Plan {
-  int mode, NT, S, grid, smem;
+  int mode, NT, S, grid, smem, tu;
   bool bias_fits;
   Params p;
 };
@@ -383,17 +390,22 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
   int cols = (pl.NT + (pl.bias_fits ? 1 : 0)) * p.Npad;
   p.tmem_cols = 32;
   while ((int)p.tmem_cols < cols) p.tmem_cols *= 2;
+  // narrow stride-1 layers on wide images: 8 x 32 tiles halve the per-tile hand-shakes, which is what those launches
+  // are bound by once the MMAs are few (tools/wgrad_phases.py)
+  pl.tu = (pl.mode == MODE_S1 && p.Keff <= 16 && (OW % 32) == 0 && !(g_swap & 128)) ? 32 : 16;   // Keff = 32: 71 vs 66 us, not worth it
+  const int TU = pl.tu;
   p.tiles_u = (OW + TU - 1) / TU;
   p.tiles_v = (OH + TV - 1) / TV;
   p.ntiles = B * p.tiles_u * p.tiles_v;
-  const int SP = pl.mode == MODE_S2 ? Geo<MODE_S2>::SP : Geo<MODE_S1>::SP;
-  const int PPAD = pl.mode == MODE_S2 ? Geo<MODE_S2>::PPAD : Geo<MODE_S1>::PPAD;
+  const int SP = pl.mode == MODE_S2 ? Geo<MODE_S2>::SP : (TU == 32 ? Geo<MODE_S1, 32>::SP : Geo<MODE_S1>::SP);
+  const int PPAD = pl.mode == MODE_S2 ? Geo<MODE_S2>::PPAD : (TU == 32 ? Geo<MODE_S1, 32>::PPAD : Geo<MODE_S1>::PPAD);
   const int NSUB = pl.mode == MODE_S2 ? 4 : 1;
+  const int DY_PLANE = TV * TU * 16;
   p.dy_bytes = (uint32_t)(p.nchunks * DY_PLANE);
   p.stage_bytes = (uint32_t)((SP * C * 2 + 127) / 128 * 128);
   // an M = 128 MMA always walks 16 plane strides from its start address and an N-padded one a plane past dY:
   // keep those reads inside the allocation
-  const uint32_t overread = 16u * PPAD * 16u + 4096u;
+  // (8 strides for the M = 64 form)
   // (planes per CTA, buffers, shared-memory budget): deep pipelines while two CTAs still share an SM, then whatever fits
   const int tries[8][3] = {{16, 6, 110}, {16, 4, 110}, {16, 3, 110}, {16, 2, 110}, {16, 3, 220}, {16, 2, 220}, {16, 1, 220}, {8, 1, 220}};
   bool fits = false;
@@ -407,6 +419,8 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
     p.off_dy = p.off_a + p.nbuf * p.a_bytes;
     p.off_stage = p.off_dy + p.nbuf * p.dy_bytes + DY_PLANE;
     uint32_t total = p.off_stage + p.nbuf * p.stage_bytes;
+    const bool m64 = (p.a3 ? 3 : 1) * p.kpl <= 8 && !(g_swap & 32);
+    const uint32_t overread = (m64 ? 8u : 16u) * PPAD * 16u + 4096u;
     const uint32_t need = p.off_a + (p.nbuf - 1) * p.a_bytes + (NSUB - 1) * p.sub_bytes + overread;
     if (total < need) total = need;
     pl.smem = (int)total + 128;
@@ -432,9 +446,9 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
   return true;
 }
 
-template <int MODE, int NT>
+template <int MODE, int NT, int TU = 16>
 static int launch_k(const Plan& pl, cudaStream_t stream) {
-  auto kern = k_wgrad_tc<MODE, NT>;
+  auto kern = k_wgrad_tc<MODE, NT, TU>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
@@ -470,7 +484,7 @@ bool wgrad_tc_try(const void* x, const void* dY, float* partial, int B, int H, i
   Params& p = pl.p;
   PFN_encodeTiled enc = get_encode();
   {
-    const int bw = pl.mode == MODE_S2 ? Geo<MODE_S2>::SW_ : Geo<MODE_S1>::SW_, bh = pl.mode == MODE_S2 ? Geo<MODE_S2>::SH_ : Geo<MODE_S1>::SH_;
+    const int bw = pl.mode == MODE_S2 ? Geo<MODE_S2>::SW_ : pl.tu + 2, bh = pl.mode == MODE_S2 ? Geo<MODE_S2>::SH_ : Geo<MODE_S1>::SH_;
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
     const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)bw, (cuuint32_t)bh, 1u};
@@ -482,7 +496,7 @@ bool wgrad_tc_try(const void* x, const void* dY, float* partial, int B, int H, i
   {
     const cuuint64_t dims[5] = {8, (cuuint64_t)(N / 8), (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)B};
     const cuuint64_t strides[4] = {16, (cuuint64_t)N * 2, (cuuint64_t)OW * N * 2, (cuuint64_t)OH * OW * N * 2};
-    const cuuint32_t box[5] = {8, 1, (cuuint32_t)TU, (cuuint32_t)TV, 1};
+    const cuuint32_t box[5] = {8, 1, (cuuint32_t)pl.tu, (cuuint32_t)TV, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     if (enc(&p.tm_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dY), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -496,7 +510,9 @@ bool wgrad_tc_try(const void* x, const void* dY, float* partial, int B, int H, i
   p.status = tc_status_word();
   if (!p.status) { rc = (int)cudaErrorMemoryAllocation; return true; }
   *S_out = pl.S;
-  if (pl.mode == MODE_S1) {
+  if (pl.mode == MODE_S1 && pl.tu == 32) {
+    rc = pl.NT == 3 ? launch_k<MODE_S1, 3, 32>(pl, stream) : pl.NT == 1 ? launch_k<MODE_S1, 1, 32>(pl, stream) : FN_E_UNSUPPORTED;
+  } else if (pl.mode == MODE_S1) {
     rc = pl.NT == 9 ? launch_k<MODE_S1, 9>(pl, stream) : pl.NT == 3 ? launch_k<MODE_S1, 3>(pl, stream) : launch_k<MODE_S1, 1>(pl, stream);
   } else {
     rc = pl.NT == 9 ? launch_k<MODE_S2, 9>(pl, stream) : pl.NT == 3 ? launch_k<MODE_S2, 3>(pl, stream) : launch_k<MODE_S2, 1>(pl, stream);
