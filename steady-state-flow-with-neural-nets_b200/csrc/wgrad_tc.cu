@@ -65,6 +65,7 @@ struct Params {
   uint32_t off_a, a_bytes, off_dy, dy_bytes, off_stage, stage_bytes, sub_bytes;
   uint32_t tmem_cols;
   int ksize, swap, m64;
+  int nt;               // accumulators per CTA
   int a3;               // 1: three column-shifted copies of every plane, the 3 taps of a filter row share one MMA
   float keep_prob;
   unsigned long long seed;
@@ -139,7 +140,7 @@ __device__ __forceinline__ void transform_tile(const Params& p, uint32_t stage, 
   }
 }
 
-template <int MODE, int NT, int TU = 16>
+template <int MODE, int TU = 16>
 __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Params p) {
   using G = Geo<MODE, TU>;
   constexpr int DY_PLANE = G::DY_PLANE;
@@ -158,7 +159,9 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
   const int grp = (int)blockIdx.x / p.S;
   const int mb = grp % p.mblocks;
   const int kpl = p.kpl;
+  const int NT = p.nt;                              // accumulators (taps, or filter rows with a3) of this CTA
   const int tap0 = (grp / p.mblocks) * NT;
+  const int ntaps = min(NT, p.T - tap0);            // the last tap group may be short
   const int n_local = s_idx < p.ntiles ? (p.ntiles - 1 - s_idx) / p.S + 1 : 0;
   auto tile_coords = [&](int t, int& b, int& y0, int& x0) {
     const int tu = t % p.tiles_u;
@@ -223,9 +226,9 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
     // =========================== issuer ===========================
     const uint32_t leader = ptx::elect_one();
     // byte offsets of this CTA's taps inside the activation planes
-    uint32_t tapoff[NT];
+    uint32_t tapoff[9];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
+    for (int t = 0; t < 9; ++t) {
       const int tap = tap0 + t;
       int di = tap / 3, dj = tap % 3;
       if (p.ksize == 1) { di = 1; dj = 1; }
@@ -246,7 +249,8 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
       const uint64_t a_tmpl = ptx::smem_desc(sbase + p.off_a + (uint32_t)s * p.a_bytes, lbo_a, sbo_a);
       const uint64_t b_tmpl = ptx::smem_desc(sbase + p.off_dy + (uint32_t)s * p.dy_bytes, lbo_b, sbo_b);
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
+      for (int t = 0; t < 9; ++t) {
+        if (t >= ntaps) break;
         const uint64_t a_tap = a_tmpl + (uint64_t)(tapoff[t] >> 4);
         const uint32_t d_col = tmem_base + (uint32_t)(t * p.Npad);
 #pragma unroll
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
       }
     }
 #pragma unroll 1
-    for (int t = 0; t < NT; ++t) {
+    for (int t = 0; t < ntaps; ++t) {
       const int tap = p.a3 ? 3 * t + du_row : tap0 + t;
       float* dst = p.partial + (((size_t)s_idx * p.T + tap) * p.Keff + krow) * p.N;
       for (int n0 = 0; n0 < p.N; n0 += 8) {
@@ -384,8 +388,20 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
   // narrow stride-1 3x3 layers: stack the three column taps along M (3 shifted plane copies), 3 MMAs per K-step
   // instead of 9 -- the MMA rate is set by the 64/128 operand rows read from shared memory, mostly padding here
   p.a3 = (pl.mode == MODE_S1 && ksize == 3 && p.Keff <= 32 && !(g_swap & 64)) ? 1 : 0;
-  pl.NT = p.a3 ? 3 : (p.T == 1 ? 1 : (9 * p.Npad <= 512 ? 9 : (3 * p.Npad <= 512 ? 3 : 1)));
-  p.tap_groups = p.a3 ? 1 : p.T / pl.NT;
+  // taps per CTA: as many accumulators as TMEM holds next to the bias accumulator (every tap group re-loads and
+  // re-transforms the tile, so fewer groups is what counts), evened out over the groups; N = 256 gives the bias up
+  if (p.a3) {
+    pl.NT = 3;
+    p.tap_groups = 1;
+  } else {
+    int cap = 512 / p.Npad - 1;
+    if (cap < 2 && p.T > 1) cap = 512 / p.Npad;
+    if (cap > p.T) cap = p.T;
+    if (cap < 1) cap = 1;
+    p.tap_groups = (p.T + cap - 1) / cap;
+    pl.NT = (p.T + p.tap_groups - 1) / p.tap_groups;
+  }
+  p.nt = pl.NT;
   pl.bias_fits = (pl.NT + 1) * p.Npad <= 512;             // room for the bias accumulator next to the tap accumulators
   int cols = (pl.NT + (pl.bias_fits ? 1 : 0)) * p.Npad;
   p.tmem_cols = 32;
@@ -446,9 +462,9 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
   return true;
 }
 
-template <int MODE, int NT, int TU = 16>
+template <int MODE, int TU = 16>
 static int launch_k(const Plan& pl, cudaStream_t stream) {
-  auto kern = k_wgrad_tc<MODE, NT, TU>;
+  auto kern = k_wgrad_tc<MODE, TU>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
@@ -510,13 +526,9 @@ bool wgrad_tc_try(const void* x, const void* dY, float* partial, int B, int H, i
   p.status = tc_status_word();
   if (!p.status) { rc = (int)cudaErrorMemoryAllocation; return true; }
   *S_out = pl.S;
-  if (pl.mode == MODE_S1 && pl.tu == 32) {
-    rc = pl.NT == 3 ? launch_k<MODE_S1, 3, 32>(pl, stream) : pl.NT == 1 ? launch_k<MODE_S1, 1, 32>(pl, stream) : FN_E_UNSUPPORTED;
-  } else if (pl.mode == MODE_S1) {
-    rc = pl.NT == 9 ? launch_k<MODE_S1, 9>(pl, stream) : pl.NT == 3 ? launch_k<MODE_S1, 3>(pl, stream) : launch_k<MODE_S1, 1>(pl, stream);
-  } else {
-    rc = pl.NT == 9 ? launch_k<MODE_S2, 9>(pl, stream) : pl.NT == 3 ? launch_k<MODE_S2, 3>(pl, stream) : launch_k<MODE_S2, 1>(pl, stream);
-  }
+  if (pl.mode == MODE_S1 && pl.tu == 32) rc = launch_k<MODE_S1, 32>(pl, stream);
+  else if (pl.mode == MODE_S1) rc = launch_k<MODE_S1>(pl, stream);
+  else rc = launch_k<MODE_S2>(pl, stream);
   return true;
 }
 
