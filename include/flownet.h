@@ -136,6 +136,11 @@ int         fn_last_used_tcgen05(void);
 int fn_conv_fwd(const fn_conv_desc* d, void* stream);
 /* 1 if fn_conv_fwd(d) would run on the tensor cores (pointers are not dereferenced, only tested for NULL), else 0 */
 int fn_conv_fwd_has_tcgen05(const fn_conv_desc* d);
+/* tensor-core weight image (as fn_pack_conv_weights_tc, fn_conv_weights_tc_bytes(ksize, K, 0, Cout, 0) bytes) straight from an
+ * fp32 variable: logical weights W'[tap][k][n] = src[flip_taps ? T-1-tap : tap][k][n], or src[..][n][k] if transpose.
+ * (flip, transpose) = (1, 1) on an HWIO variable gives the B operand of that conv's data gradient. */
+int fn_pack_conv_weights_tc_f32(const float* w, void* dst, int32_t ksize, int32_t K, int32_t Cout, int32_t flip_taps,
+                                int32_t transpose, void* stream);
 /* tf.nn.conv2d_transpose + bias_add                      flow_architecture.py:70-87 */
 int fn_tconv_fwd(const fn_tconv_desc* d, void* stream);
 /* size in bytes of / packer for the tensor-core weight image of a conv (host-side helper

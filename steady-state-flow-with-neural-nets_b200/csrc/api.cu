@@ -46,6 +46,7 @@ int conv_fwd_tc(const fn_conv_desc& d, cudaStream_t stream);
 bool tconv_tc_supported(const fn_tconv_desc& d, const char** why);
 int tconv_fwd_tc(const fn_tconv_desc& d, cudaStream_t stream);
 long long conv_weights_tc_bytes(int ksize, int Keff, int Kskip, int Cout, int gated);
+int pack_conv_weights_tc_f32(const float* w, void* dst, int ksize, int K, int Cout, int flip, int transpose, cudaStream_t stream);
 int pack_conv_weights_tc(const void* w, const void* w_skip, void* dst, int ksize, int Keff, int Kskip, int Cout,
                          int gated, cudaStream_t stream);
 int nonlinearity(const void* x, void* y, long long n, int C, int kind, cudaStream_t s);
@@ -123,6 +124,12 @@ int fn_conv_fwd(const fn_conv_desc* d, void* stream) {
              "fn_conv_fwd: no tcgen05 kernel for this shape: %s", why);
   note_tcgen05(false);
   return conv_fwd_simt(*d, s);
+}
+
+int fn_pack_conv_weights_tc_f32(const float* w, void* dst, int32_t ksize, int32_t K, int32_t Cout, int32_t flip_taps,
+                                int32_t transpose, void* stream) {
+  FN_REQUIRE(w && dst && (ksize == 1 || ksize == 3) && K > 0 && Cout > 0, FN_E_INVAL, "fn_pack_conv_weights_tc_f32: bad arguments");
+  return pack_conv_weights_tc_f32(w, dst, ksize, K, Cout, flip_taps, transpose, (cudaStream_t)stream);
 }
 
 int fn_conv_fwd_has_tcgen05(const fn_conv_desc* d) {

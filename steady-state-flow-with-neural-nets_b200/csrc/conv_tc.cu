@@ -801,6 +801,40 @@ __global__ void k_pack_tc(const __nv_bfloat16* __restrict__ w, const __nv_bfloat
   }
 }
 
+// the same image straight from an fp32 variable [T][A][B] with the taps optionally reversed and the two channel axes
+// optionally swapped -- the B operands of the data-gradient convs (stride-1 conv: flipped taps, K and N exchanged) without
+// the flip / permute / cast / contiguous round trip through bf16 temporaries
+__global__ void k_pack_tc_f32(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int T, int K, int Cout, int N, int flip,
+                              int transpose) {
+  const int kst = (K + 15) / 16;
+  const int total = T * kst * 2 * N * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 7;
+    int r = i >> 3;
+    const int n = r % N;
+    r /= N;
+    const int h = r & 1;
+    const int ks = r >> 1;
+    const int tap = ks / kst, kk = ks % kst;
+    const int k = kk * 16 + h * 8 + e;
+    float v = 0.f;
+    if (n < Cout && k < K) {
+      const int st = flip ? T - 1 - tap : tap;
+      v = transpose ? w[((size_t)st * Cout + n) * K + k] : w[((size_t)st * K + k) * Cout + n];
+    }
+    dst[i] = __float2bfloat16(v);
+  }
+}
+
+int pack_conv_weights_tc_f32(const float* w, void* dst, int ksize, int K, int Cout, int flip, int transpose, cudaStream_t stream) {
+  FN_REQUIRE((K % 16) == 0 || K == 8, FN_E_ALIGN, "pack_conv_weights_tc_f32: K = %d must be a multiple of 16 (or 8)", K);
+  const int N = round_up(Cout, 16);
+  const long long total = (long long)ksize * ksize * ((K + 15) / 16) * 2 * N * 8;
+  k_pack_tc_f32<<<(int)((total + 255) / 256), 256, 0, stream>>>(w, (__nv_bfloat16*)dst, ksize * ksize, K, Cout, N, flip, transpose);
+  count_launch();
+  return check_launch("k_pack_tc_f32");
+}
+
 long long conv_weights_tc_bytes(int ksize, int Keff, int Kskip, int Cout, int gated) {
   (void)gated;
   if (((Keff % 16) != 0 && Keff != 8) || (Kskip % 16) != 0 || Cout <= 0) return 0;

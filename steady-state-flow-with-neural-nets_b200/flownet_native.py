@@ -63,6 +63,7 @@ SYMBOLS = [
     ("fn_last_used_tcgen05", C.c_int, []),
     ("fn_conv_fwd", C.c_int, [C.POINTER(ConvDesc), _P]),
     ("fn_conv_fwd_has_tcgen05", C.c_int, [C.POINTER(ConvDesc)]),
+    ("fn_pack_conv_weights_tc_f32", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     ("fn_tconv_fwd", C.c_int, [C.POINTER(TConvDesc), _P]),
     ("fn_conv_weights_tc_bytes", C.c_int64, [C.c_int32] * 5),
     ("fn_pack_conv_weights_tc", C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
@@ -205,6 +206,18 @@ def pack_conv_weights_tc(w, w_skip, ksize, Keff, Kskip, Cout, gated):
     dst = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
     _check(lib.fn_pack_conv_weights_tc(_ptr(w), _ptr(w_skip), _ptr(dst), ksize, Keff, Kskip, Cout, int(gated),
                                        stream_ptr()), "fn_pack_conv_weights_tc")
+    return dst
+
+
+def pack_conv_weights_tc_f32(w, ksize, K, Cout, flip_taps=False, transpose=False):
+    """tensor-core weight image from an fp32 variable [k*k (or k,k), A, B]; see fn_pack_conv_weights_tc_f32"""
+    _require_cuda(w)
+    nbytes = lib.fn_conv_weights_tc_bytes(ksize, K, 0, Cout, 0)
+    if nbytes <= 0:
+        raise ValueError(f"no tensor-core weight image for K={K}")
+    dst = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    _check(lib.fn_pack_conv_weights_tc_f32(_ptr(w), _ptr(dst), ksize, K, Cout, int(flip_taps), int(transpose), stream_ptr()),
+           "fn_pack_conv_weights_tc_f32")
     return dst
 
 

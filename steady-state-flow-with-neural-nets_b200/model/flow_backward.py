@@ -51,48 +51,89 @@ def _zeros_bias(n, device):
     return torch.zeros(n, dtype=torch.float32, device=device)
 
 
+class _BwdWeights:
+    """B operand of a backward conv, made on demand from an fp32 variable viewed as [T][A][B]: logical weights
+    W'[tap][k][n] = src[flip ? T-1-tap : tap][k][n] (or src[..][n][k] with transpose).  On the tensor-core path one
+    native kernel writes the packed image straight from the variable (fn_pack_conv_weights_tc_f32); the bf16 [T,K,N]
+    tensor the CUDA-core path reads is only built when that path runs."""
+
+    def __init__(self, src, ksize, K, N, flip=False, transpose=False):
+        self.src = src.contiguous()
+        self.ksize, self.K, self.N, self.flip, self.transpose = ksize, K, N, flip, transpose
+
+    def tc(self):
+        if self.K % 16 and self.K != 8:
+            return None
+        return native.pack_conv_weights_tc_f32(self.src, self.ksize, self.K, self.N, self.flip, self.transpose)
+
+    def w16(self):
+        T = self.ksize * self.ksize
+        w = self.src.reshape(T, self.N, self.K) if self.transpose else self.src.reshape(T, self.K, self.N)
+        if self.flip:
+            w = torch.flip(w, dims=(0,))
+        if self.transpose:
+            w = w.permute(0, 2, 1)
+        return w.to(torch.bfloat16).contiguous()
+
+
 def _dgrad_weights_s1(w, ksize):
-    """HWIO [k,k,Keff,N] -> GEMM-B of the data-gradient conv: [tap', N, Keff] with the taps flipped."""
+    """HWIO [k,k,Keff,N] -> GEMM-B of the data-gradient conv: W'[tap'][n][keff] = W[T-1-tap'][keff][n]."""
     keff, n = w.shape[2], w.shape[3]
-    wd = torch.flip(w, dims=(0, 1)).permute(0, 1, 3, 2).reshape(ksize * ksize, n, keff)
-    return wd.to(torch.bfloat16).contiguous()
+    return _BwdWeights(w, ksize, n, keff, flip=True, transpose=True)
 
 
-def _conv_plain(x, w16, cout, ksize, stride, device):
+def _conv_call(x, wts, y, **kw):
+    """native.conv_fwd with the weights of a _BwdWeights: tensor cores if a kernel exists (the `w` argument is then a
+    placeholder nobody reads), else the CUDA-core path on the bf16 [T,K,N] tensor.  Returns False if `tc_only` and no
+    tensor-core kernel exists."""
+    tc_only = kw.pop("tc_only", False)
+    bias = _zeros_bias(wts.N, x.device)
+    w_tc = wts.tc() if arch.IMPL != native.IMPL_SIMT else None
+    if w_tc is not None and native.conv_fwd(x, w_tc, bias, y, w_tc=w_tc, query=True, **kw):
+        native.conv_fwd(x, w_tc, bias, y, w_tc=w_tc, **kw)
+        return True
+    if tc_only:
+        return False
+    native.conv_fwd(x, wts.w16(), bias, y, w_tc=None, **kw)
+    return True
+
+
+def _conv_plain(x, wts, cout, ksize, stride, device):
     """bias-free conv through the forward kernels (tcgen05 when the shape allows)."""
     B, H, W, cin = x.shape
     OH, OW = -(-H // stride), -(-W // stride)
     y = torch.empty((B, OH, OW, cout), dtype=torch.bfloat16, device=device)
-    w_tc = native.pack_conv_weights_tc(w16, None, ksize, cin, 0, cout, False) if (cin % 16 == 0 or cin == 8) else None
-    native.conv_fwd(x, w16, _zeros_bias(cout, device), y, B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize, stride=stride,
-                    prologue=native.PRO_NONE, epilogue=native.EPI_BIAS, impl=arch.IMPL, w_tc=w_tc)
+    if not isinstance(wts, _BwdWeights):            # a ready bf16 [T, K, N] tensor
+        w_tc = native.pack_conv_weights_tc(wts, None, ksize, cin, 0, cout, False) if (cin % 16 == 0 or cin == 8) else None
+        native.conv_fwd(x, wts, _zeros_bias(cout, device), y, B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize, stride=stride,
+                        prologue=native.PRO_NONE, epilogue=native.EPI_BIAS, impl=arch.IMPL, w_tc=w_tc)
+        return y
+    _conv_call(x, wts, y, B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize, stride=stride, prologue=native.PRO_NONE,
+               epilogue=native.EPI_BIAS, impl=arch.IMPL)
     return y
 
 
-def _conv_dgrad_adjoint(g, w16, cout, z, pro, device, out=None, accumulate=False, keep_prob=1.0, seed=0):
-    """d(z) (+)= adjoint_of_prologue(conv3x3(g, w16), z): the data-gradient conv with the prologue's adjoint (and the
+def _conv_dgrad_adjoint(g, wts, cout, z, pro, device, out=None, accumulate=False, keep_prob=1.0, seed=0):
+    """d(z) (+)= adjoint_of_prologue(conv3x3(g, W'), z): the data-gradient conv with the prologue's adjoint (and the
     forward's dropout mask) applied in its epilogue when the persistent kernel takes the shape (FN_EPI_PRO_BWD), else the
     conv followed by fn_prologue_bwd.  Returns the d(z) tensor."""
     B, H, W, cin = g.shape
     if out is None:
         out = torch.empty(tuple(z.shape), dtype=torch.bfloat16, device=device)
         accumulate = False
-    w_tc = native.pack_conv_weights_tc(w16, None, 3, cin, 0, cout, False) if (cin % 16 == 0 or cin == 8) else None
-    kw = dict(B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=3, stride=1, prologue=native.PRO_NONE, epilogue=native.EPI_PRO_BWD,
-              impl=arch.IMPL, w_tc=w_tc, res=z, keep_prob=keep_prob, dropout_seed=seed, adj_prologue=pro,
-              adj_accumulate=accumulate)
-    bias = _zeros_bias(cout, device)
-    if w_tc is not None and arch.IMPL != native.IMPL_SIMT and native.conv_fwd(g, w16, bias, out, query=True, **kw):
-        native.conv_fwd(g, w16, bias, out, **kw)
+    if _conv_call(g, wts, out, tc_only=True, B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=3, stride=1, prologue=native.PRO_NONE,
+                  epilogue=native.EPI_PRO_BWD, impl=arch.IMPL, res=z, keep_prob=keep_prob, dropout_seed=seed, adj_prologue=pro,
+                  adj_accumulate=accumulate):
         return out
-    dA = _conv_plain(g, w16, cout, 3, 1, device)
+    dA = _conv_plain(g, wts, cout, 3, 1, device)
     return native.prologue_bwd(dA, z, pro, out=out, accumulate=accumulate, keep_prob=keep_prob, seed=seed)
 
 
-def _tconv_plain(x, w16, cout, device):
+def _tconv_plain(x, wts, cout, device):
     B, H, W, cin = x.shape
     y = torch.empty((B, 2 * H, 2 * W, cout), dtype=torch.bfloat16, device=device)
-    w_tc = native.pack_conv_weights_tc(w16, None, 3, cin, 0, cout, False) if cin % 16 == 0 else None
+    w_tc = wts.tc() if (cin % 16 == 0 and arch.IMPL != native.IMPL_SIMT) else None
+    w16 = w_tc if w_tc is not None else wts.w16()      # with a tensor-core image `w` is a placeholder nobody reads
     native.tconv_fwd(x, w16, _zeros_bias(cout, device), y, B=B, H=H, W=W, Cin=cin, Cout=cout, impl=arch.IMPL, w_tc=w_tc)
     return y
 
@@ -170,8 +211,7 @@ def backward(tape, sflow_p, sflow, flat: FlatParams = None, want_input_grad=Fals
                 native.tconv_wgrad(x, g, flat.grad_view(scope + '/weights').view(9, cout, cin))
             bgrad_into(scope, g)
             # d(x) = stride-2 'SAME' conv of d(y) with the same weights read as HWIO [k,k,Cout,Cin]
-            w16 = V[scope + '/weights'].reshape(9, cout, cin).to(torch.bfloat16).contiguous()
-            dx = _conv_plain(g, w16, cin, 3, 2, dev)
+            dx = _conv_plain(g, _BwdWeights(V[scope + '/weights'], 3, cout, cin), cin, 3, 2, dev)
             buf, acc = grads.target(x)
             assert not acc
             buf.copy_(dx)
@@ -226,8 +266,7 @@ def backward(tape, sflow_p, sflow, flat: FlatParams = None, want_input_grad=Fals
                 else:
                     if x.shape[1] % 2 or x.shape[2] % 2:
                         raise ValueError("training a stride-2 block on odd spatial sizes is not built")
-                    w16 = w1.reshape(9, mult * cin, F_).permute(0, 2, 1).to(torch.bfloat16).contiguous()   # [tap, F, Keff]
-                    dA1 = _tconv_plain(dx_1, w16, mult * cin, dev)
+                    dA1 = _tconv_plain(dx_1, _BwdWeights(w1, 3, F_, mult * cin, transpose=True), mult * cin, dev)  # [tap, F, Keff]
                     native.prologue_bwd(dA1, x, pro, out=buf, accumulate=acc)
                 native.shortcut_bwd(g, tuple(x.shape), pooled, out=buf, accumulate=True)
             elif want_input_grad:
