@@ -171,6 +171,9 @@ def layer_profile(x_dev, reps=5):
     runs = []
     for _ in range(reps + 1):
         arch._PROFILE = []
+        # hold the GPU for ~2 ms so that the host enqueues the whole forward (launches + events) ahead of it: each event
+        # pair then brackets its kernel alone, without the host's per-call latency in between
+        torch.cuda._sleep(4_000_000)
         flow_net.inference(x_dev, 1.0)
         torch.cuda.synchronize()
         runs.append(arch._PROFILE)
