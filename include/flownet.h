@@ -216,6 +216,9 @@ int64_t fn_tfrecord_index(const uint8_t* buf, int64_t nbytes, int64_t* offsets, 
  * FN_E_INVAL when a feature is missing or has another size */
 int fn_tfrecord_parse_flow_example(const uint8_t* payload, int64_t len, uint8_t* boundary, int64_t boundary_bytes, float* sflow,
                                    int64_t sflow_bytes);
+/* n records (payload offsets / lengths into one file image) -> consecutive slots of a batch, on up to nthreads host threads */
+int fn_tfrecord_parse_flow_batch(const uint8_t* buf, const int64_t* offsets, const int64_t* lengths, int64_t n, uint8_t* boundary,
+                                 int64_t boundary_bytes, float* sflow, int64_t sflow_bytes, int32_t nthreads);
 /* writes one framed record holding such an Example; dst == NULL returns the size needed; returns bytes written */
 int64_t fn_tfrecord_write_flow_example(uint8_t* dst, int64_t capacity, const uint8_t* boundary, int64_t boundary_bytes,
                                        const float* sflow, int64_t sflow_bytes);

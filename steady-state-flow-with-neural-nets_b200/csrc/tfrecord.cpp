@@ -8,6 +8,10 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #include "flownet.h"
 
 namespace {
@@ -239,6 +243,34 @@ int64_t fn_tfrecord_write_flow_example(uint8_t* dst, int64_t capacity, const uin
   const uint32_t dcrc = masked_crc(body, (int64_t)example);
   memcpy(p, &dcrc, 4);
   return total;
+}
+
+/* n records of one file image -> consecutive slots of a batch (boundary: n x boundary_bytes, sflow: n x sflow_bytes),
+ * parsed by up to nthreads host threads (each record is one 0.3 MB copy: memory-bandwidth work that one thread cannot
+ * saturate).  Returns 0, or FN_E_INVAL if any record is not a {'boundary','sflow'} example of these sizes. */
+int fn_tfrecord_parse_flow_batch(const uint8_t* buf, const int64_t* offsets, const int64_t* lengths, int64_t n, uint8_t* boundary,
+                                 int64_t boundary_bytes, float* sflow, int64_t sflow_bytes, int32_t nthreads) {
+  if (!buf || !offsets || !lengths || n < 0 || !boundary || !sflow) return FN_E_INVAL;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > n) nthreads = (int32_t)(n > 0 ? n : 1);
+  std::atomic<int> err(0);
+  auto work = [&](int t) {
+    for (int64_t i = t; i < n; i += nthreads) {
+      const int rc = fn_tfrecord_parse_flow_example(buf + offsets[i], lengths[i], boundary + i * boundary_bytes, boundary_bytes,
+                                                    reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sflow) + i * sflow_bytes),
+                                                    sflow_bytes);
+      if (rc != 0) err.store(rc);
+    }
+  };
+  if (nthreads == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+  }
+  return err.load();
 }
 
 uint32_t fn_crc32c(const uint8_t* p, int64_t n) { return crc32c(p, n); }

@@ -87,6 +87,7 @@ SYMBOLS = [
     ("fn_tconv_wgrad", C.c_int, [C.POINTER(TConvDesc), _P, _P, _P, _P]),
     ("fn_tfrecord_index", C.c_int64, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int32]),
     ("fn_tfrecord_parse_flow_example", C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64]),
+    ("fn_tfrecord_parse_flow_batch", C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int32]),
     ("fn_tfrecord_write_flow_example", C.c_int64, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64]),
     ("fn_lbm_init", C.c_int, [C.POINTER(LbmDesc), C.c_double, C.c_double, C.c_double, _P]),
     ("fn_lbm_steps", C.c_int, [C.POINTER(LbmDesc), C.c_int32, _P]),

@@ -46,6 +46,18 @@ class TFRecordFile:
     def __len__(self):
         return len(self.offsets)
 
+    def read_batch_into(self, indices, boundary, sflow, nthreads=4):
+        """Parse records `indices` into boundary[k], sflow[k] (contiguous numpy batches) with native host threads."""
+        idx = np.asarray(indices, dtype=np.int64)
+        offs = np.ascontiguousarray(self.offsets[idx])
+        lens = np.ascontiguousarray(self.lengths[idx])
+        rc = native.lib.fn_tfrecord_parse_flow_batch(self._buf.ctypes.data, offs.ctypes.data, lens.ctypes.data, len(idx),
+                                                      boundary.ctypes.data, boundary[0].nbytes, sflow.ctypes.data, sflow[0].nbytes,
+                                                      int(nthreads))
+        if rc != 0:
+            raise ValueError("%s: a record is not a {'boundary','sflow'} example of %d / %d bytes" %
+                             (self.path, boundary[0].nbytes, sflow[0].nbytes))
+
     def read_into(self, i, boundary, sflow):
         """Parse record i into boundary (uint8 [H,W,1]) and sflow (float32 [H,W,2]) -- numpy views, contiguous."""
         rc = native.lib.fn_tfrecord_parse_flow_example(self._buf.ctypes.data + int(self.offsets[i]), int(self.lengths[i]),
@@ -86,7 +98,7 @@ class FlowInputQueue:
     whose host->device copies were issued from pinned memory on a side stream."""
 
     def __init__(self, files, batch_size, shape=(128, 256), min_after_dequeue=None, seed=0, device="cuda", shuffle=True,
-                 prefetch=2):
+                 prefetch=2, parse_threads=8):
         if not files:
             raise FileNotFoundError("no .tfrecords files")
         self.files = [TFRecordFile(p) for p in files]
@@ -99,12 +111,14 @@ class FlowInputQueue:
         self.rng = np.random.default_rng(seed)
         self.shuffle = shuffle
         self.device = device
+        self.parse_threads = parse_threads
         # the buffer holds record REFERENCES (file, index) -- the same sliding shuffle window over the record stream as
         # buffering parsed examples, but each example is parsed exactly once, straight into its pinned batch slot
         self._pool = []
         self._cursor = (0, 0)                                                   # (file, record)
         self._q = queue.Queue(maxsize=prefetch)
         self._stop = False
+        self._copy_done = {}
         self._cuda = torch.cuda.is_available() and str(device).startswith("cuda")
         self._stream = torch.cuda.Stream() if self._cuda else None
         self._thread = threading.Thread(target=self._producer, daemon=True)     # num_preprocess_threads = 1 (reference :34)
@@ -119,22 +133,38 @@ class FlowInputQueue:
 
     def _producer(self):
         H, W = self.shape
+        ring, turn = [], 0
         try:
             while not self._stop:
                 want = self.capacity if self.shuffle else self.B
                 while len(self._pool) < want:
                     self._pool.append(self._next_ref())
-                hb = torch.empty((self.B, H, W, 1), dtype=torch.uint8, pin_memory=self._cuda)
-                hs = torch.empty((self.B, H, W, 2), dtype=torch.float32, pin_memory=self._cuda)
+                # pinned staging buffers are recycled: queue depth + the batch being copied + the one being filled
+                if len(ring) < self._q.maxsize + 3:
+                    ring.append((torch.empty((self.B, H, W, 1), dtype=torch.uint8, pin_memory=self._cuda),
+                                 torch.empty((self.B, H, W, 2), dtype=torch.float32, pin_memory=self._cuda)))
+                hb, hs = ring[turn % len(ring)] if len(ring) == self._q.maxsize + 3 else ring[-1]
+                turn += 1
+                done = self._copy_done.pop(id(hb), None)
+                if done is not None:
+                    done.synchronize()                      # the upload that last read this buffer has finished
                 nb, ns = hb.numpy(), hs.numpy()
+                refs = []
                 for i in range(self.B):
                     if self.shuffle:                        # swap-remove a uniformly drawn buffered example
                         j = int(self.rng.integers(0, len(self._pool)))
                         self._pool[j], self._pool[-1] = self._pool[-1], self._pool[j]
-                        fi, ri = self._pool.pop()
+                        refs.append(self._pool.pop())
                     else:                                   # FIFO
-                        fi, ri = self._pool.pop(0)
-                    self.files[fi].read_into(ri, nb[i], ns[i])
+                        refs.append(self._pool.pop(0))
+                # parse runs of consecutive slots that come from the same file in one multi-threaded native call
+                i = 0
+                while i < self.B:
+                    j = i
+                    while j < self.B and refs[j][0] == refs[i][0]:
+                        j += 1
+                    self.files[refs[i][0]].read_batch_into([r for _, r in refs[i:j]], nb[i:j], ns[i:j], self.parse_threads)
+                    i = j
                 self._q.put((hb, hs))
         except BaseException as e:                          # surface parser errors in the consumer
             self._q.put(e)
@@ -149,6 +179,9 @@ class FlowInputQueue:
         with torch.cuda.stream(self._stream):
             db = hb.to(self.device, non_blocking=True)
             ds = hs.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._stream)
+            self._copy_done[id(hb)] = ev
         torch.cuda.current_stream().wait_stream(self._stream)
         db.record_stream(torch.cuda.current_stream())
         ds.record_stream(torch.cuda.current_stream())

@@ -127,3 +127,18 @@ def test_mechsys_crop_rule():
     g = flow_reader.crop_boundary(gam, (H, W))
     assert f.shape == (H, W, 2) and g.shape == (H, W, 1)
     assert f[1, 2, 1] == vel[(1 * (W + 128) + 2) * 3 + 1] and g[3, 5, 0] == gam[3 * (W + 128) + 5]
+
+
+def test_native_batch_parse_matches_single_record_parse(fi, tmp_path):
+    b, s = _examples(9, seed=7)
+    path = str(tmp_path / "c.tfrecords")
+    fi.write_tfrecords(path, b, s)
+    f = fi.TFRecordFile(path)
+    idx = [8, 0, 3, 3, 7, 1]
+    for threads in (1, 3, 16):
+        nb = np.zeros((len(idx), 6, 10, 1), np.uint8)
+        ns = np.zeros((len(idx), 6, 10, 2), np.float32)
+        f.read_batch_into(idx, nb, ns, threads)
+        assert np.array_equal(nb, b[idx]) and np.array_equal(ns, s[idx])
+    with pytest.raises(ValueError):
+        f.read_batch_into([0, 1], np.zeros((2, 8, 8, 1), np.uint8), np.zeros((2, 8, 8, 2), np.float32), 2)

@@ -34,6 +34,13 @@ for crc in (1, 0):
     out["index_crc%d_MBps" % crc] = size / 1e6 / t_idx
     out["parse_records_per_s"] = N / t_parse
     out["parse_MBps"] = size / 1e6 / t_parse
+f = fi.TFRecordFile(path, check_crc=False)
+nb = np.empty((min(N, 64), 128, 256, 1), np.uint8); ns = np.empty((min(N, 64), 128, 256, 2), np.float32)
+for th in (1, 4, 8, 16):
+    t0 = time.time(); reps = 0
+    while time.time() - t0 < 0.5:
+        f.read_batch_into(np.arange(len(nb)) % len(f), nb, ns, th); reps += 1
+    out["batch_parse_records_per_s_%dthreads" % th] = reps * len(nb) / (time.time() - t0)
 raw = open(path, "rb").read()
 t0 = time.time()
 k = 0
