@@ -1018,3 +1018,16 @@ def test_nin_backward_kernel_vs_two_step(native, npix_shape, F, Ca, kind, acc):
     two = native.prologue_bwd(dA, a, kind, out=base.clone(), accumulate=acc)
     torch.cuda.synchronize()
     assert rel_l2(fused, two) < 3e-3
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 48, 80), (3, 64, 96), (2, 80, 144)])
+def test_net_vs_oracle_on_sizes_that_are_not_powers_of_two(native, B, H, W):
+    """The network is fully convolutional for H, W multiples of 16 (four stride-2 levels); tiles at the right / bottom
+    edges are ragged for every kernel family at these sizes."""
+    x = fo.synth_boundary(B, H, W, seed=4)
+    vs = fo.VariableStore(1234, torch.float64)
+    ref = fo.inference(vs, torch.from_numpy(x).double(), 1.0)
+    for impl in ("auto", "simt"):
+        y = _net(native, x.astype(np.uint8), impl)
+        assert tuple(y.shape) == (B, H, W, 2)
+        assert rel_l2(y, ref) < NET_TOL, impl
