@@ -651,6 +651,7 @@ static bool geom_of_conv(const fn_conv_desc& d, TcGeom& g, const char** why) {
 bool conv_s1p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1p.cu
 bool conv_s1d_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1d.cu
 bool conv_s1n_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s2t.cu
+bool conv_s1w_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1w.cu
 
 bool conv_tc_supported(const fn_conv_desc& d, const char** why) {
   int rc = 0;
@@ -658,6 +659,7 @@ bool conv_tc_supported(const fn_conv_desc& d, const char** why) {
   if (g_tc_use_s1p && (d.keep_prob < 1.0f || d.epilogue == FN_EPI_GATE_BWD) &&
       (conv_s1p_try(d, nullptr, true, rc) || conv_s1d_try(d, nullptr, true, rc)))
     return true;
+  if (g_tc_use_s1p && conv_s1w_try(d, nullptr, true, rc)) return true;      // C = 256: two-pass kernel, pass-major weights
   if (d.epilogue == FN_EPI_GATE_BWD) {
     if (why) *why = "the gate-backward epilogue exists in the persistent kernels only";
     return false;
@@ -712,6 +714,7 @@ int conv_fwd_tc(const fn_conv_desc& d, cudaStream_t stream) {
   int rc_sp = 0;
   if (g_tc_use_s1p && conv_s1p_try(d, stream, false, rc_sp)) return rc_sp;
   if (g_tc_use_s1p && conv_s1d_try(d, stream, false, rc_sp)) return rc_sp;
+  if (g_tc_use_s1p && conv_s1w_try(d, stream, false, rc_sp)) return rc_sp;
   if (g_tc_use_s1p && conv_s2p_try(d, stream, false, rc_sp)) return rc_sp;
   if (g_tc_use_s1p && conv_s1n_try(d, stream, false, rc_sp)) return rc_sp;
   TcGeom g;

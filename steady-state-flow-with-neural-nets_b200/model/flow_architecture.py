@@ -184,8 +184,10 @@ def _pro_mult(pro):
 
 
 # --------------------------------------------------------------------------- fused conv launcher
-def _conv_weights(scope, ksize, cin_eff, cout, device, skip_scope=None, kskip_eff=0, gated=False):
-    """bf16 GEMM-B images of a conv's variables (+ the nin it absorbs), cached per variable version."""
+def _conv_weights(scope, ksize, cin_eff, cout, device, skip_scope=None, kskip_eff=0, gated=False, pass_major=False):
+    """bf16 GEMM-B images of a conv's variables (+ the nin it absorbs), cached per variable version.
+    pass_major: the 512-row (C = 256, concat) weights of the two-pass kernel conv_s1w.cu -- the tensor-core image is
+    that of the K rows {0..127, 256..383} followed by that of {128..255, 384..511}."""
     w = _variable(scope + '/weights', [ksize, ksize, cin_eff, cout], device=device)
     b = _variable(scope + '/biases', [cout], device=device)
     ws = bs = None
@@ -198,7 +200,14 @@ def _conv_weights(scope, ksize, cin_eff, cout, device, skip_scope=None, kskip_ef
         ws16 = ws.to(torch.bfloat16).contiguous() if ws is not None else None
         bias = (b + bs).contiguous() if bs is not None else b.contiguous()
         w_tc = None
-        if cin_eff % 16 == 0 and kskip_eff % 16 == 0:
+        if pass_major:
+            half, quarter = cin_eff // 2, cin_eff // 4
+            parts = []
+            for ps in range(2):
+                rows = torch.cat([w16[:, ps * quarter:(ps + 1) * quarter], w16[:, half + ps * quarter:half + (ps + 1) * quarter]], dim=1)
+                parts.append(native.pack_conv_weights_tc(rows.contiguous(), None, ksize, half, 0, cout, gated))
+            w_tc = torch.cat(parts)
+        elif cin_eff % 16 == 0 and kskip_eff % 16 == 0:
             w_tc = native.pack_conv_weights_tc(w16, ws16, ksize, cin_eff, kskip_eff, cout, gated)
         return w16, ws16, bias, w_tc
 
@@ -216,7 +225,9 @@ def _fused_conv(x, scope, ksize, stride, cout, prologue, epilogue, skip=None, sk
         skip = native.to_bf16(skip)
         kskip = skip.shape[3] * mult
     gated = epilogue in (native.EPI_GATE_RES, native.EPI_GATE_BWD)
-    w16, ws16, bias, w_tc = _conv_weights(scope, ksize, cin * mult, cout, x.device, skip_scope, kskip, gated)
+    pass_major = (cin * mult == 512 and ksize == 3 and stride == 1 and skip is None and prologue == native.PRO_CONCAT_ELU
+                  and cout in (256, 512) and H % 8 == 0 and W >= 16)
+    w16, ws16, bias, w_tc = _conv_weights(scope, ksize, cin * mult, cout, x.device, skip_scope, kskip, gated, pass_major)
     OH, OW = -(-H // stride), -(-W // stride)
     cy = cout // 2 if epilogue == native.EPI_GATE_RES else cout
     if query:

@@ -1031,3 +1031,47 @@ def test_net_vs_oracle_on_sizes_that_are_not_powers_of_two(native, B, H, W):
         y = _net(native, x.astype(np.uint8), impl)
         assert tuple(y.shape) == (B, H, W, 2)
         assert rel_l2(y, ref) < NET_TOL, impl
+
+
+def _pack_pass_major(native, w16, N, gated):
+    half, quarter = w16.shape[1] // 2, w16.shape[1] // 4
+    parts = []
+    for ps in range(2):
+        rows = torch.cat([w16[:, ps * quarter:(ps + 1) * quarter], w16[:, half + ps * quarter:half + (ps + 1) * quarter]], dim=1)
+        parts.append(native.pack_conv_weights_tc(rows.contiguous(), None, 3, half, 0, N, gated))
+    return torch.cat(parts)
+
+
+@pytest.mark.parametrize("B,H,W,gate,Cres,pool", [(3, 8, 16, True, None, False), (2, 8, 16, False, None, False), (2, 16, 32, True, None, False),
+                                                  (2, 8, 16, True, 128, True), (70, 8, 16, True, None, False), (1, 24, 40, False, None, False)])
+def test_two_pass_c256_kernel_vs_cuda_core_and_oracle(native, B, H, W, gate, Cres, pool):
+    """conv_s1w.cu (C = 256: two K passes of 128 channels, N = 512 as two MMAs) against the fp64 oracle and the CUDA-core
+    kernel -- the 8x16 level of the filter_size = 16 variant."""
+    g = torch.Generator().manual_seed(81)
+    C = 256
+    N = 2 * C if gate else C
+    x = bf16_round(torch.randn(B, H, W, C, generator=g, dtype=torch.float64))
+    lim = (6.0 / (9 * (2 * C + N))) ** 0.5
+    w = bf16_round((torch.rand(3, 3, 2 * C, N, generator=g, dtype=torch.float64) * 2 - 1) * lim * 2)
+    b = (torch.rand(N, generator=g, dtype=torch.float64) * 2 - 1).float().double()
+    res = None
+    if gate:
+        Cres = C if Cres is None else Cres
+        RH, RW = (2 * H, 2 * W) if pool else (H, W)
+        res = bf16_round(torch.randn(B, RH, RW, Cres, generator=g, dtype=torch.float64))
+    w16 = w.reshape(9, 2 * C, N).to("cuda", torch.bfloat16).contiguous()
+    w_tc = _pack_pass_major(native, w16, N, gate)
+    ys = []
+    for impl in (native.IMPL_TCGEN05, native.IMPL_SIMT):
+        y = torch.full((B, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+        native.conv_fwd(x.to("cuda", torch.bfloat16), w16, b.to("cuda", torch.float32), y, B=B, H=H, W=W, Cin=C, Cout=N, ksize=3, stride=1,
+                        prologue=1, epilogue=1 if gate else 0, impl=impl, w_tc=w_tc,
+                        res=res.to("cuda", torch.bfloat16) if res is not None else None, res_pool=pool)
+        torch.cuda.synchronize()
+        assert native.tc_status() == 0
+        assert native.last_used_tcgen05() == (impl == native.IMPL_TCGEN05)
+        ys.append(y)
+    assert rel_l2(ys[0], ys[1]) < 5e-3
+    if B * H * W <= 1024:
+        ref = oracle_fused_conv(x, w, b, 1, 1, 1 if gate else 0, None, None, res, pool)
+        assert rel_l2(ys[0], ref) < LAYER_TOL
