@@ -9,6 +9,9 @@
 //     accumulating into the same TMEM columns.  The packed weights are pass-major (the host packs the two K halves
 //     separately and concatenates them).
 //   * N = 512 is two MMAs of N = 256 per k-step (u columns, v columns), 512 TMEM columns.
+// VAR_SKIP reuses the pass mechanism for conv_1 + nin skip at C = 128 (two 32-plane operands do not fit either): pass 0 =
+// the 3x3 taps over x, pass 1 = the centre tap over the skip tensor `a` (x_1 += nin(concat_elu(a)), :136-142); the
+// standard packed image [main k-steps | skip k-steps] is already pass-major.
 // reference semantics: res_block conv_1 / conv_2 (+gate, +shortcut), flow_architecture.py:129-165.
 #include <cuda.h>
 
@@ -26,10 +29,10 @@ constexpr int CHUNK_BYTES = 32768;
 constexpr int NST = 2;                             // weight ring stages
 constexpr int KP = 2;                              // passes over the input channels
 constexpr int CP = 128, CHP = CP / 8;              // raw channels / 8-channel chunks per pass
-constexpr int C = KP * CP, F = C;
+enum { VAR_WIDE = 0, VAR_SKIP = 1 };
 
 struct Params {
-  CUtensorMap tm_x, tm_res;
+  CUtensorMap tm_x, tm_res, tm_skip;
   const __nv_bfloat16* wpk;
   const float* bias;
   __nv_bfloat16* y;
@@ -41,16 +44,21 @@ struct Params {
   int gate_bwd;
 };
 
-template <bool GATE>
+template <bool GATE, int VAR>
 struct Cfg {
-  static constexpr int N = GATE ? 2 * C : C;                       // 512 / 256
-  static constexpr int NM = N / 256;                               // MMAs per k-step
+  static constexpr bool SKIPV = VAR == VAR_SKIP;
+  static constexpr int C = SKIPV ? CP : KP * CP;                   // raw channels of x (the tensor-map extent)
+  static constexpr int F = C;                                      // output channels
+  static constexpr int N = GATE ? 2 * C : C;                       // 512 / 256 (wide), 128 (skip variant)
+  static constexpr int NMMA = N <= 256 ? N : 256;                  // columns of one MMA
+  static constexpr int NM = N / NMMA;                              // MMAs per k-step
   static constexpr int KS = CHP;                                   // k-steps per tap and pass (2 * 128 / 16)
-  static constexpr int KSTEPS_P = 9 * KS;                          // k-steps of one pass
+  static constexpr int KSTEPS_P0 = 9 * KS;                         // pass 0: all taps
+  static constexpr int KSTEPS_P1 = SKIPV ? KS : 9 * KS;            // pass 1: the other channel half, or the skip's centre tap
   static constexpr int PU = 10, PV = 18, P = PU * PV;              // transposed tile: u = 8 rows (+halo) of y, v = 16 (+halo) of x
   static constexpr int PPAD = P + ((1 - (P & 7)) + 8) % 8;
-  static constexpr int SPC = CHUNK_BYTES / (N * 32);               // k-steps per weight chunk (2 / 4)
-  static constexpr int NCHUNKS_P = (KSTEPS_P + SPC - 1) / SPC;     // chunks per pass
+  static constexpr int SPC = CHUNK_BYTES / (N * 32);               // k-steps per weight chunk
+  static constexpr int NCHUNKS_P0 = KSTEPS_P0 / SPC, NCHUNKS_P1 = KSTEPS_P1 / SPC;
   static constexpr int PLANE_BYTES = (2 * CHP * PPAD * 16 + 127) / 128 * 128;
   static constexpr int STAGE_BYTES = ((P * CP * 2) + 127) / 128 * 128;
   static constexpr int RES_BYTES = GATE ? 128 * F * 2 : 0;
@@ -59,8 +67,9 @@ struct Cfg {
   static constexpr int OFF_STAGE = OFF_PLANES + PLANE_BYTES;
   static constexpr int OFF_RING = OFF_STAGE + STAGE_REGION;
   static constexpr int SMEM = OFF_RING + NST * CHUNK_BYTES + 128;
-  static constexpr int TMEM_COLS = N;                              // 256 or 512 (powers of two)
-  static_assert(KSTEPS_P % SPC == 0, "a weight chunk must not straddle two passes");
+  static constexpr int TMEM_COLS = N;                              // 128, 256 or 512 (powers of two)
+  static_assert(KSTEPS_P0 % SPC == 0 && KSTEPS_P1 % SPC == 0, "a weight chunk must not straddle two passes");
+  static_assert(!(SKIPV && GATE), "the skip operand belongs to conv_1 (no gate)");
   static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
@@ -98,9 +107,10 @@ __device__ __forceinline__ void transform_tile(uint32_t stage, uint32_t planes, 
   }
 }
 
-template <bool GATE>
+template <bool GATE, int VAR>
 __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Params p) {
-  using CF = Cfg<GATE>;
+  using CF = Cfg<GATE, VAR>;
+  constexpr int F = CF::F;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const uint32_t sbase = ptx::smem_u32(smem);
@@ -169,8 +179,10 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
             if (!ok) { atomicCAS(p.status, 0, 72); break; }
           }
           ptx::mbar_arrive_expect_tx(bar(SB_X), (uint32_t)(CF::P * CP * 2));
-          tma_load_4d(sbase + CF::OFF_STAGE, &p.tm_x, bar(SB_X), ps * CP, v0 - 1, u0 - 1, b);
-          for (int c = 0; c < CF::NCHUNKS_P && ok; ++c, ++gchunk) {
+          if (CF::SKIPV && ps == 1) tma_load_4d(sbase + CF::OFF_STAGE, &p.tm_skip, bar(SB_X), 0, v0 - 1, u0 - 1, b);
+          else tma_load_4d(sbase + CF::OFF_STAGE, &p.tm_x, bar(SB_X), ps * CP, v0 - 1, u0 - 1, b);
+          const int nchunks = ps == 0 ? CF::NCHUNKS_P0 : CF::NCHUNKS_P1;
+          for (int c = 0; c < nchunks && ok; ++c, ++gchunk) {
             const int s = gchunk % NST;
             if (gchunk >= NST) {
               ok = ptx::mbar_wait(bar(SB_EMPTY + s), (uint32_t)(((gchunk / NST) - 1) & 1));
@@ -179,7 +191,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
             const uint32_t bytes = (uint32_t)(CF::SPC * CF::N * 32);
             ptx::mbar_arrive_expect_tx(bar(SB_FULL + s), bytes);
             ptx::bulk_g2s(sbase + CF::OFF_RING + s * CHUNK_BYTES,
-                          reinterpret_cast<const unsigned char*>(p.wpk) + (size_t)(ps * CF::NCHUNKS_P + c) * CF::SPC * CF::N * 32, bytes,
+                          reinterpret_cast<const unsigned char*>(p.wpk) + (size_t)(ps * CF::NCHUNKS_P0 + c) * CF::SPC * CF::N * 32, bytes,
                           bar(SB_FULL + s));
           }
         }
@@ -195,7 +207,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
   } else {
     // =========================== workers ===========================
     const uint32_t leader = ptx::elect_one();
-    constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, 256);
+    constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, CF::NMMA);
     const int q4 = warp & 3, half = warp >> 2;
     const int r = q4 * 32 + lane;                     // accumulator row == TMEM lane
     const int v = r >> 3, u = r & 7;
@@ -221,8 +233,10 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
           ptx::tc_fence_after_sync();
           const uint64_t a_tmpl = ptx::smem_desc(sbase + CF::OFF_PLANES, CF::PPAD * 16, CF::PU * 16);
           const uint64_t b_tmpl = ptx::smem_desc(sbase + CF::OFF_RING, CF::N * 16, 128);
+          const int nchunks = ps == 0 ? CF::NCHUNKS_P0 : CF::NCHUNKS_P1;
+          const bool centre_only = CF::SKIPV && ps == 1;
 #pragma unroll 1
-          for (int c = 0; c < CF::NCHUNKS_P; ++c) {
+          for (int c = 0; c < nchunks; ++c) {
             const int gc = gchunk + c;
             const int s = gc % NST;
             ok = ok && ptx::mbar_wait(bar(SB_FULL + s), (uint32_t)((gc / NST) & 1));
@@ -232,7 +246,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
 #pragma unroll
             for (int i = 0; i < CF::SPC; ++i) {
               const int ks = c * CF::SPC + i;                       // k-step inside this pass
-              const int tap = ks / CF::KS, kk = ks % CF::KS;
+              const int tap = centre_only ? 4 : ks / CF::KS, kk = ks % CF::KS;
               const int di = tap / 3, dj = tap % 3;
               const int dv = dj, du = di;                           // transposed tile: u along y
               const uint32_t a_off = (uint32_t)((dv * CF::PU + du) * 16 + kk * 2 * CF::PPAD * 16) >> 4;
@@ -241,14 +255,15 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
 #pragma unroll
               for (int m = 0; m < CF::NM; ++m)
                 if (leader)
-                  ptx::mma_bf16_ss(tmem_base + (uint32_t)(m * 256), a_tmpl + a_off, b_chunk + b_off + (uint32_t)((m * 256 * 16) >> 4), idesc, acc);
+                  ptx::mma_bf16_ss(tmem_base + (uint32_t)(m * CF::NMMA), a_tmpl + a_off, b_chunk + b_off + (uint32_t)((m * CF::NMMA * 16) >> 4), idesc,
+                                   acc);
             }
             if (leader) ptx::mma_commit(bar(SB_EMPTY + s));
           }
           if (leader) ptx::mma_commit(bar(ps == KP - 1 ? SB_TF : SB_PD));
           __syncwarp();
         }
-        gchunk += CF::NCHUNKS_P;
+        gchunk += ps == 0 ? CF::NCHUNKS_P0 : CF::NCHUNKS_P1;
       }
       // ---- epilogue: quadrant q4, channel half `half`
       ok = ok && ptx::mbar_wait(bar(SB_TF), par_it);
@@ -350,25 +365,25 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
   }
 }
 
-template <bool GATE>
+template <bool GATE, int VAR>
 static int launch(const fn_conv_desc& d, int* status, cudaStream_t stream) {
-  using CF = Cfg<GATE>;
+  using CF = Cfg<GATE, VAR>;
+  constexpr int C = CF::C, F = CF::F;
   Params p;
   memset(&p, 0, sizeof(p));
   // transposed tile: the box is (channels, x-extent = PV, y-extent = PU)
   PFN_encodeTiled enc = get_encode();
-  {
-    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
-    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)d.W * C * 2, (cuuint64_t)d.H * d.W * C * 2};
+  auto map_cp = [&](CUtensorMap* tm, const void* base, int c_total, int H, int W) {
+    const cuuint64_t dims[4] = {(cuuint64_t)c_total, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)d.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)c_total * 2, (cuuint64_t)W * c_total * 2, (cuuint64_t)H * W * c_total * 2};
     const cuuint32_t box[4] = {(cuuint32_t)CP, (cuuint32_t)CF::PV, (cuuint32_t)CF::PU, 1u};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    if (!enc || enc(&p.tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.x), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
-      set_error("conv_s1w: tensor map (x) failed");
-      return FN_E_UNSUPPORTED;
-    }
-  }
+    return enc && enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  if (!map_cp(&p.tm_x, d.x, C, d.H, d.W)) { set_error("conv_s1w: tensor map (x) failed"); return FN_E_UNSUPPORTED; }
+  if (CF::SKIPV && !map_cp(&p.tm_skip, d.skip, CP, d.SH, d.SW)) { set_error("conv_s1w: tensor map (skip) failed"); return FN_E_UNSUPPORTED; }
   p.res_mode = 0;
   if (GATE && d.res != nullptr) {
     if (!d.res_pool && d.Cres == F) {
@@ -390,7 +405,7 @@ static int launch(const fn_conv_desc& d, int* status, cudaStream_t stream) {
   p.Cout = d.Cout;
   p.Cres = d.Cres; p.RH = d.RH; p.RW = d.RW; p.res_pool = d.res_pool;
   p.gate_bwd = d.epilogue == FN_EPI_GATE_BWD ? 1 : 0;
-  auto kern = k_conv_s1w<GATE>;
+  auto kern = k_conv_s1w<GATE, VAR>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM);
@@ -413,17 +428,26 @@ int* tc_status_word();
 bool conv_s1w_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc) {
   using namespace s1w;
   rc = 0;
-  if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_CONCAT_ELU || d.w_tc == nullptr || d.skip != nullptr ||
-      d.keep_prob < 1.0f || d.Cin != C)
-    return false;
+  if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_CONCAT_ELU || d.w_tc == nullptr || d.keep_prob < 1.0f) return false;
+  if ((d.H % 8) != 0 || d.W < 16 || get_encode() == nullptr) return false;
+  if (d.skip != nullptr) {
+    // conv_1 + nin skip at C = 128: x pass + skip pass
+    if (d.Cin != CP || d.Cskip != CP || d.Cout != CP || d.epilogue != FN_EPI_BIAS) return false;
+    if (!dry_run) {
+      int* st = tc_status_word();
+      rc = !st ? (int)cudaErrorMemoryAllocation : launch<false, VAR_SKIP>(d, st, stream);
+    }
+    return true;
+  }
+  constexpr int C = KP * CP;
+  if (d.Cin != C) return false;
   const bool gate = d.epilogue == FN_EPI_GATE_RES || d.epilogue == FN_EPI_GATE_BWD;
   if (!gate && d.epilogue != FN_EPI_BIAS) return false;
   if (d.Cout != (gate ? 2 * C : C)) return false;
   if (d.epilogue == FN_EPI_GATE_BWD && (d.res == nullptr || d.res_pool || d.Cres != C)) return false;
-  if ((d.H % 8) != 0 || d.W < 16 || get_encode() == nullptr) return false;
   if (!dry_run) {
     int* st = tc_status_word();
-    rc = !st ? (int)cudaErrorMemoryAllocation : (gate ? launch<true>(d, st, stream) : launch<false>(d, st, stream));
+    rc = !st ? (int)cudaErrorMemoryAllocation : (gate ? launch<true, VAR_WIDE>(d, st, stream) : launch<false, VAR_WIDE>(d, st, stream));
   }
   return true;
 }

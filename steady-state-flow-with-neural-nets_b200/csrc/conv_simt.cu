@@ -274,13 +274,14 @@ static int launch_direct(const fn_conv_desc& d, cudaStream_t stream) {
 // stages an 8 x 128 pixel tile (+halo) of the boundary image as fp32 in shared memory, all loads issued before the
 // first use.  A thread produces the pixels lane, lane+32, lane+64, lane+96 of one tile row, so shared-memory reads are
 // conflict-free and every warp store covers 512 contiguous bytes.
-__global__ void __launch_bounds__(256) k_head3x3_c8(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+template <int NOUT>
+__global__ void __launch_bounds__(256) k_head3x3(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B,
                                                     int H, int W, int tiles_x, int tiles_y) {
-  __shared__ __align__(16) float ws[72 + 8];
+  __shared__ __align__(16) float ws[9 * NOUT + NOUT];
   __shared__ float tile[10][132];
-  if (threadIdx.x < 72) ws[threadIdx.x] = __bfloat162float(w[threadIdx.x]);
-  if (threadIdx.x < 8) ws[72 + threadIdx.x] = bias[threadIdx.x];
+  if (threadIdx.x < 9 * NOUT) ws[threadIdx.x] = __bfloat162float(w[threadIdx.x]);
+  if (threadIdx.x < NOUT) ws[9 * NOUT + threadIdx.x] = bias[threadIdx.x];
   int t = blockIdx.x;
   const int tx = t % tiles_x;
   t /= tiles_x;
@@ -308,67 +309,73 @@ __global__ void __launch_bounds__(256) k_head3x3_c8(const __nv_bfloat16* __restr
   const int row = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int oy = y0 + row;
   if (oy >= H) return;
-  float acc[4][8];
+  float acc[4][NOUT];
 #pragma unroll
   for (int px = 0; px < 4; ++px)
 #pragma unroll
-    for (int n = 0; n < 8; ++n) acc[px][n] = ws[72 + n];
+    for (int n = 0; n < NOUT; ++n) acc[px][n] = ws[9 * NOUT + n];
 #pragma unroll
   for (int di = 0; di < 3; ++di)
 #pragma unroll
     for (int dj = 0; dj < 3; ++dj) {
-      const float4 w0 = *reinterpret_cast<const float4*>(&ws[(di * 3 + dj) * 8]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&ws[(di * 3 + dj) * 8 + 4]);
 #pragma unroll
-      for (int px = 0; px < 4; ++px) {
-        const float v = tile[row + di][lane + 32 * px + dj];
-        acc[px][0] = fmaf(v, w0.x, acc[px][0]); acc[px][1] = fmaf(v, w0.y, acc[px][1]);
-        acc[px][2] = fmaf(v, w0.z, acc[px][2]); acc[px][3] = fmaf(v, w0.w, acc[px][3]);
-        acc[px][4] = fmaf(v, w1.x, acc[px][4]); acc[px][5] = fmaf(v, w1.y, acc[px][5]);
-        acc[px][6] = fmaf(v, w1.z, acc[px][6]); acc[px][7] = fmaf(v, w1.w, acc[px][7]);
+      for (int n4 = 0; n4 < NOUT; n4 += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(&ws[(di * 3 + dj) * NOUT + n4]);
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          const float v = tile[row + di][lane + 32 * px + dj];
+          acc[px][n4] = fmaf(v, wv.x, acc[px][n4]); acc[px][n4 + 1] = fmaf(v, wv.y, acc[px][n4 + 1]);
+          acc[px][n4 + 2] = fmaf(v, wv.z, acc[px][n4 + 2]); acc[px][n4 + 3] = fmaf(v, wv.w, acc[px][n4 + 3]);
+        }
       }
     }
-  __nv_bfloat16* yo = y + (((size_t)b * H + oy) * W + x0) * 8;
+  __nv_bfloat16* yo = y + (((size_t)b * H + oy) * W + x0) * NOUT;
 #pragma unroll
   for (int px = 0; px < 4; ++px) {
     const int ox = lane + 32 * px;
     if (x0 + ox < W) {
-      bf16x8 o;
 #pragma unroll
-      for (int n = 0; n < 8; ++n) o.h[n] = __float2bfloat16(acc[px][n]);
-      *reinterpret_cast<uint4*>(yo + (size_t)ox * 8) = o.v;
+      for (int n0 = 0; n0 < NOUT; n0 += 8) {
+        bf16x8 o;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) o.h[n] = __float2bfloat16(acc[px][n0 + n]);
+        *reinterpret_cast<uint4*>(yo + (size_t)ox * NOUT + n0) = o.v;
+      }
     }
   }
 }
 
-static int launch_head_c8(const fn_conv_desc& d, cudaStream_t stream) {
+template <int NOUT>
+static int launch_head(const fn_conv_desc& d, cudaStream_t stream) {
   const int tiles_x = (d.W + 127) / 128, tiles_y = (d.H + 7) / 8;
   const long long grid = (long long)d.B * tiles_x * tiles_y;
-  k_head3x3_c8<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d.x),
+  k_head3x3<NOUT><<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d.x),
                                                    reinterpret_cast<const __nv_bfloat16*>(d.w), d.bias,
                                                    reinterpret_cast<__nv_bfloat16*>(d.y), d.B, d.H, d.W, tiles_x, tiles_y);
   count_launch();
-  return check_launch("k_head3x3_c8");
+  return check_launch("k_head3x3");
 }
 
 // Tail of the network, 8 channels -> 2 + tanh, fp32 out (last_conv, flow_architecture.py:242-243): the same tiling;
 // the 8 x 128 (+halo) tile is staged as it is in memory (one 16-byte bf16 vector per pixel), a thread owns four pixels
 // 32 apart, reads each tap's 16 weights once for the four of them, and writes float2 per pixel (256 contiguous bytes
 // per warp store).  A third of the instructions of the one-thread-per-pixel kernel above.
-__global__ void __launch_bounds__(256) k_tail3x3_c8(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+template <int CIN>
+__global__ void __launch_bounds__(256) k_tail3x3(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                                     const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W,
                                                     int tiles_x, int tiles_y) {
-  __shared__ __align__(16) float ws[144 + 4];
-  __shared__ uint4 tile[10][130];
-  if (threadIdx.x < 144) ws[threadIdx.x] = __bfloat162float(w[threadIdx.x]);        // [tap][c][n]
-  if (threadIdx.x < 2) ws[144 + threadIdx.x] = bias[threadIdx.x];
+  constexpr int CH = CIN / 8;
+  __shared__ __align__(16) float ws[18 * CIN + 4];
+  __shared__ uint4 tile[10][130][CH];
+  for (int i = threadIdx.x; i < 18 * CIN; i += 256) ws[i] = __bfloat162float(w[i]);        // [tap][c][n]
+  if (threadIdx.x < 2) ws[18 * CIN + threadIdx.x] = bias[threadIdx.x];
   int t = blockIdx.x;
   const int tx = t % tiles_x;
   t /= tiles_x;
   const int ty = t % tiles_y;
   const int b = t / tiles_y;
   const int y0 = ty * 8, x0 = tx * 128;
-  {
+  for (int q = 0; q < CH; ++q) {
     uint4 v[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -377,13 +384,13 @@ __global__ void __launch_bounds__(256) k_tail3x3_c8(const __nv_bfloat16* __restr
       const int iy = y0 + r - 1, ix = x0 + c - 1;
       v[k] = make_uint4(0u, 0u, 0u, 0u);
       if (i < 1300 && iy >= 0 && iy < H && ix >= 0 && ix < W)
-        v[k] = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + iy) * W + ix) * 8));
+        v[k] = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + iy) * W + ix) * CIN + q * 8));
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const int i = threadIdx.x + 256 * k;
       const int r = i / 130, c = i - r * 130;
-      if (i < 1300) tile[r][c] = v[k];
+      if (i < 1300) tile[r][c][q] = v[k];
     }
   }
   __syncthreads();
@@ -392,26 +399,29 @@ __global__ void __launch_bounds__(256) k_tail3x3_c8(const __nv_bfloat16* __restr
   if (oy >= H) return;
   float a0[4], a1[4];
 #pragma unroll
-  for (int px = 0; px < 4; ++px) { a0[px] = ws[144]; a1[px] = ws[145]; }
+  for (int px = 0; px < 4; ++px) { a0[px] = ws[18 * CIN]; a1[px] = ws[18 * CIN + 1]; }
 #pragma unroll
   for (int di = 0; di < 3; ++di)
 #pragma unroll
     for (int dj = 0; dj < 3; ++dj) {
-      float wt[16];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 f = *reinterpret_cast<const float4*>(&ws[(di * 3 + dj) * 16 + 4 * q]);
-        wt[4 * q] = f.x; wt[4 * q + 1] = f.y; wt[4 * q + 2] = f.z; wt[4 * q + 3] = f.w;
-      }
+      for (int q = 0; q < CH; ++q) {
+        float wt[16];
 #pragma unroll
-      for (int px = 0; px < 4; ++px) {
-        bf16x8 in;
-        in.v = tile[row + di][lane + 32 * px + dj];
+        for (int f = 0; f < 4; ++f) {
+          const float4 wv = *reinterpret_cast<const float4*>(&ws[((di * 3 + dj) * CIN + q * 8) * 2 + 4 * f]);
+          wt[4 * f] = wv.x; wt[4 * f + 1] = wv.y; wt[4 * f + 2] = wv.z; wt[4 * f + 3] = wv.w;
+        }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float v = __bfloat162float(in.h[c]);
-          a0[px] = fmaf(v, wt[2 * c], a0[px]);
-          a1[px] = fmaf(v, wt[2 * c + 1], a1[px]);
+        for (int px = 0; px < 4; ++px) {
+          bf16x8 in;
+          in.v = tile[row + di][lane + 32 * px + dj][q];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float v = __bfloat162float(in.h[c]);
+            a0[px] = fmaf(v, wt[2 * c], a0[px]);
+            a1[px] = fmaf(v, wt[2 * c + 1], a1[px]);
+          }
         }
       }
     }
@@ -423,28 +433,30 @@ __global__ void __launch_bounds__(256) k_tail3x3_c8(const __nv_bfloat16* __restr
   }
 }
 
-static int launch_tail_c8(const fn_conv_desc& d, cudaStream_t stream) {
+template <int CIN>
+static int launch_tail(const fn_conv_desc& d, cudaStream_t stream) {
   const int tiles_x = (d.W + 127) / 128, tiles_y = (d.H + 7) / 8;
   const long long grid = (long long)d.B * tiles_x * tiles_y;
-  k_tail3x3_c8<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d.x),
+  k_tail3x3<CIN><<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d.x),
                                                    reinterpret_cast<const __nv_bfloat16*>(d.w), d.bias,
                                                    reinterpret_cast<float*>(d.y), d.B, d.H, d.W, tiles_x, tiles_y);
   count_launch();
-  return check_launch("k_tail3x3_c8");
+  return check_launch("k_tail3x3");
 }
 
 // returns true (and sets rc) if a specialised head/tail kernel took the launch
 static bool try_direct(const fn_conv_desc& d, cudaStream_t stream, int& rc) {
   if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_NONE || d.skip || d.keep_prob < 1.0f) return false;
-  if (d.epilogue == FN_EPI_BIAS && d.Cin == 1 && d.Cout == 8) { rc = launch_head_c8(d, stream); return true; }
+  if (d.epilogue == FN_EPI_BIAS && d.Cin == 1 && d.Cout == 8) { rc = launch_head<8>(d, stream); return true; }
+  if (d.epilogue == FN_EPI_BIAS && d.Cin == 1 && d.Cout == 16) { rc = launch_head<16>(d, stream); return true; }
   if (d.epilogue == FN_EPI_BIAS && d.Cin == 1) {
     if (d.Cout == 8) { rc = launch_direct<1, 8, false>(d, stream); return true; }
     if (d.Cout == 16) { rc = launch_direct<1, 16, false>(d, stream); return true; }
     if (d.Cout == 32) { rc = launch_direct<1, 32, false>(d, stream); return true; }
   }
   if (d.epilogue == FN_EPI_TANH && d.Cout == 2) {
-    if (d.Cin == 8) { rc = launch_tail_c8(d, stream); return true; }
-    if (d.Cin == 16) { rc = launch_direct<16, 2, true>(d, stream); return true; }
+    if (d.Cin == 8) { rc = launch_tail<8>(d, stream); return true; }
+    if (d.Cin == 16) { rc = launch_tail<16>(d, stream); return true; }
     if (d.Cin == 32) { rc = launch_direct<32, 2, true>(d, stream); return true; }
   }
   return false;

@@ -108,6 +108,8 @@ SIMT_CASES = [
     ("head_c1", 2, 16, 32, 1, 8, 1, 0, 0, False, None, False),
     ("head_c1_ragged", 3, 9, 13, 1, 8, 1, 0, 0, False, None, False),
     ("head_c1_wide", 2, 24, 300, 1, 8, 1, 0, 0, False, None, False),
+    ("head_c1_n16", 2, 24, 140, 1, 16, 1, 0, 0, False, None, False),
+    ("tail_tanh_c16", 2, 20, 150, 16, 2, 1, 0, 3, False, None, False),
     ("conv1_ce", 2, 16, 32, 8, 8, 1, 1, 0, False, None, False),
     ("conv2_gate", 2, 16, 32, 8, 16, 1, 1, 1, False, None, False),
     ("conv2_gate_head_res", 2, 16, 32, 8, 16, 1, 1, 1, False, 1, False),
@@ -1075,3 +1077,32 @@ def test_two_pass_c256_kernel_vs_cuda_core_and_oracle(native, B, H, W, gate, Cre
     if B * H * W <= 1024:
         ref = oracle_fused_conv(x, w, b, 1, 1, 1 if gate else 0, None, None, res, pool)
         assert rel_l2(ys[0], ref) < LAYER_TOL
+
+
+@pytest.mark.parametrize("B,H,W,SH,SW", [(2, 16, 32, 16, 32), (3, 8, 16, 8, 16), (1, 24, 48, 20, 40)])
+def test_skip_pass_kernel_c128_vs_cuda_core_and_oracle(native, B, H, W, SH, SW):
+    """conv_s1w.cu VAR_SKIP: conv_1 + nin skip at C = 128 (x pass + centre-tap skip pass), incl. a skip tensor smaller than
+    the output (zero-padded bottom / right, flow_architecture.py:139-141)."""
+    g = torch.Generator().manual_seed(91)
+    C = 128
+    x = bf16_round(torch.randn(B, H, W, C, generator=g, dtype=torch.float64))
+    a = bf16_round(torch.randn(B, SH, SW, C, generator=g, dtype=torch.float64))
+    lim = (6.0 / (9 * (2 * C + C))) ** 0.5
+    w = bf16_round((torch.rand(3, 3, 2 * C, C, generator=g, dtype=torch.float64) * 2 - 1) * lim * 2)
+    ws = bf16_round((torch.rand(2 * C, C, generator=g, dtype=torch.float64) * 2 - 1) * 0.1)
+    b = (torch.rand(C, generator=g, dtype=torch.float64) * 2 - 1).float().double()
+    w16 = w.reshape(9, 2 * C, C).to("cuda", torch.bfloat16).contiguous()
+    ws16 = ws.to("cuda", torch.bfloat16).contiguous()
+    w_tc = native.pack_conv_weights_tc(w16, ws16, 3, 2 * C, 2 * C, C, False)
+    ys = []
+    for impl in (native.IMPL_TCGEN05, native.IMPL_SIMT):
+        y = torch.full((B, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+        native.conv_fwd(x.to("cuda", torch.bfloat16), w16, b.to("cuda", torch.float32), y, B=B, H=H, W=W, Cin=C, Cout=C, ksize=3, stride=1,
+                        prologue=1, epilogue=0, impl=impl, w_tc=w_tc, skip=a.to("cuda", torch.bfloat16), w_skip=ws16)
+        torch.cuda.synchronize()
+        assert native.tc_status() == 0
+        assert native.last_used_tcgen05() == (impl == native.IMPL_TCGEN05)
+        ys.append(y)
+    assert rel_l2(ys[0], ys[1]) < 5e-3
+    ref = oracle_fused_conv(x, w, b, 1, 1, 0, a, ws)
+    assert rel_l2(ys[0], ref) < LAYER_TOL
