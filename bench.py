@@ -198,8 +198,15 @@ def run_train(args, rank, world, dist, native, arch, flow_net):
     boundary, sflow = flow_net.inputs(B, seed=rank * B)
     flow_net.begin_training()
 
+    compiled = None
+    if args.keep_prob >= 1.0 and not args.eager_train:
+        # forward + backward replayed from one CUDA graph; all-reduce and Adam stay eager (flow_net.CompiledTraining)
+        compiled = flow_net.CompiledTraining(B, SHAPE)
+
     def step():
         step.k += 1
+        if compiled is not None:
+            return compiled.step(boundary, sflow, 1e-4)
         p = flow_net.inference(boundary, args.keep_prob, dropout_seed=step.k)
         err = flow_net.loss_image_train(p, sflow)
         return flow_net.train(err, 1e-4)
@@ -231,7 +238,8 @@ def run_train(args, rank, world, dist, native, arch, flow_net):
             "steps": args.steps, "warmup": max(args.warmup, 2), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic boundaries and targets",
             "config": {"workload": "configs[2]: training step, global batch 256, 128x256, L2 loss + TF1 Adam, "
-                                   "keep_prob %.2f; tcgen05 fwd + dgrad + wgrad" % args.keep_prob,
+                                   "keep_prob %.2f; tcgen05 fwd + dgrad + wgrad; %s" % (
+                                       args.keep_prob, "fwd+bwd replayed from a CUDA graph" if compiled is not None else "eager launches"),
                        "batch_per_gpu": B, "parallelism": f"dp{world}, one flat fp32 gradient all-reduce"},
             "gpu_launches": native.launch_count() - n0, "loss": float(loss.item()),
             "roofline": {"bound": "tensor", "achieved": v * 8.519e9 / 1e12, "peak": load_peaks()["tc_sustained"],
@@ -251,6 +259,7 @@ def main():
                     help="train: BASELINE configs[2], fwd+bwd+Adam at global batch 256 (extra line, not the headline)")
     ap.add_argument("--keep-prob", type=float, default=1.0,
                     help="train mode: dropout keep probability (1.0 = the parity setting; the reference trains with 0.7)")
+    ap.add_argument("--eager-train", action="store_true", help="train mode: launch every kernel eagerly instead of replaying a graph")
     ap.add_argument("--layers-out", default=None, help="write the per-layer roofline table (JSON) here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

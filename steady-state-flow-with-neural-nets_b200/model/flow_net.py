@@ -194,6 +194,54 @@ def train(total_loss, lr):
     return loss
 
 
+class CompiledTraining:
+    """One training step (forward + backward through the ~370 kernels of libflownet.so, incl. the re-packing of the
+    weights Adam just changed) captured into a CUDA graph for a fixed (B, H, W) and replayed; the gradient all-reduce
+    and the Adam update stay outside (two more launches).  At small per-GPU batches -- BASELINE configs[2] sharded over
+    4-8 GPUs -- the eager step is bound by the host's launch rate, the replay is not.
+
+    keep_prob must be 1.0: the dropout seed is a launch argument and would repeat on every replay."""
+
+    def __init__(self, batch_size, shape=(128, 256), keep_prob=1.0, in_dtype=torch.uint8):
+        import model.flow_backward as fb
+        if keep_prob < 1.0:
+            raise ValueError("CompiledTraining: keep_prob < 1 needs a fresh dropout seed per step; use the eager step")
+        self.fb = fb
+        self.static_boundary = torch.zeros((batch_size, shape[0], shape[1], 1), dtype=in_dtype, device="cuda")
+        self.static_sflow = torch.zeros((batch_size, shape[0], shape[1], 2), dtype=torch.float32, device="cuda")
+        begin_training()
+        # warm-up: creates the variables, the flat buffers, the workspace and the allocator pool; gradients only (no
+        # Adam), so the parameters are exactly what they were
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        flow_architecture.VARIABLES.touch()              # the capture must contain the weight-packing kernels
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = native.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._fwd_bwd()
+        self.launches_per_replay = native.launch_count() - n0
+        flow_architecture.TAPE = []
+
+    def _fwd_bwd(self):
+        flow_architecture.TAPE = []
+        sflow_p = inference(self.static_boundary, 1.0)
+        flat = ensure_training_state()
+        return self.fb.backward(flow_architecture.TAPE, sflow_p, self.static_sflow, flat)
+
+    def step(self, boundary, sflow, lr):
+        """boundary / sflow: CUDA or pinned host tensors of the captured shape.  Returns the loss (fp32 [1], device)."""
+        self.static_boundary.copy_(boundary, non_blocking=True)
+        self.static_sflow.copy_(sflow, non_blocking=True)
+        self.graph.replay()
+        self.fb.adam_update(ensure_training_state(), lr)
+        return self.loss
+
+
 def boundary_gradient(boundary, sflow, keep_prob=1.0):
     """d l2_loss(inference(boundary), sflow) / d boundary -- the gradient the README's boundary-optimisation use needs
     (/root/reference/README.md:31-36): the training backward pass without the parameter gradients,

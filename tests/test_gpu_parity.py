@@ -1106,3 +1106,44 @@ def test_skip_pass_kernel_c128_vs_cuda_core_and_oracle(native, B, H, W, SH, SW):
     assert rel_l2(ys[0], ys[1]) < 5e-3
     ref = oracle_fused_conv(x, w, b, 1, 1, 0, a, ws)
     assert rel_l2(ys[0], ref) < LAYER_TOL
+
+
+def test_compiled_training_step_matches_eager(native):
+    """flow_net.CompiledTraining (forward + backward replayed from a CUDA graph, Adam outside) follows the eager step
+    bit for bit over several steps (every reduction is ordered, the graph holds the same launches)."""
+    import model.flow_architecture as arch
+    import model.flow_net as flow_net
+
+    def data(k):
+        return flow_net.inputs(2, shape=(32, 64), seed=100 + k)
+
+    try:
+        arch.reset_variables(1234)
+        flow_net.reset_training_state()
+        flow_net.begin_training()
+        eager_losses = []
+        for k in range(3):
+            b, s = data(k)
+            p = flow_net.inference(b, 1.0)
+            err = flow_net.loss_image_train(p, s)
+            eager_losses.append(flow_net.train(err, 1e-3).item())
+        want = {k: v.clone() for k, v in arch.global_variables().items()}
+        flow_net.end_training()
+
+        arch.reset_variables(1234)
+        flow_net.reset_training_state()
+        ct = flow_net.CompiledTraining(2, (32, 64))
+        assert ct.launches_per_replay > 100
+        losses = []
+        for k in range(3):
+            b, s = data(k)
+            losses.append(ct.step(b, s, 1e-3).item())
+        got = arch.global_variables()
+        for a, b in zip(losses, eager_losses):           # the loss scalar is an atomicAdd over blocks: order-dependent rounding
+            assert abs(a - b) <= 1e-6 * abs(b)
+        for k in want:
+            assert torch.equal(got[k], want[k]), k
+    finally:
+        flow_net.end_training()
+        flow_net.reset_training_state()
+        arch.reset_variables(1234)
