@@ -199,9 +199,9 @@ def run_train(args, rank, world, dist, native, arch, flow_net):
     flow_net.begin_training()
 
     compiled = None
-    if args.keep_prob >= 1.0 and not args.eager_train:
+    if not args.eager_train:
         # forward + backward replayed from one CUDA graph; all-reduce and Adam stay eager (flow_net.CompiledTraining)
-        compiled = flow_net.CompiledTraining(B, SHAPE)
+        compiled = flow_net.CompiledTraining(B, SHAPE, keep_prob=args.keep_prob, dropout_seed=1 + rank)
 
     def step():
         step.k += 1

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FN_ABI_VERSION 2
+#define FN_ABI_VERSION 3
 
 /* error codes (negative) */
 #define FN_E_INVAL      (-1)   /* null pointer, bad enum, non-positive dim */
@@ -103,6 +103,9 @@ typedef struct fn_conv_desc {
   float    keep_prob;
   uint64_t dropout_seed;
   uint64_t dropout_offset;
+  /* optional device-resident addend to dropout_seed (NULL: none): a captured CUDA graph of the training step gets a new
+   * mask on every replay by bumping this counter instead of changing a launch argument */
+  const uint64_t* dropout_seed_dev;
   /* FN_EPI_PRO_BWD only */
   int32_t  adj_prologue;    /* enum fn_prologue of the nonlinearity being differentiated */
   int32_t  adj_accumulate;  /* 1: y += ... */
@@ -177,6 +180,9 @@ int fn_gate_bwd(const void* c2, const void* g, void* dc2, int64_t npix, int32_t 
  * -> dx bf16 [npix,C] (accumulate != 0: added to the existing dx) */
 int fn_prologue_bwd(const void* dA, const void* x, void* dx, int64_t npix, int32_t C, int32_t kind, int32_t accumulate,
                     float keep_prob, uint64_t seed, void* stream);
+/* the same with a device-resident addend to the seed (see fn_conv_desc.dropout_seed_dev) */
+int fn_prologue_bwd_dev(const void* dA, const void* x, void* dx, int64_t npix, int32_t C, int32_t kind, int32_t accumulate,
+                        float keep_prob, uint64_t seed, const uint64_t* seed_dev, void* stream);
 /* data gradient of the nin skip (flow_architecture.py:136-142) fused with the adjoint of its concat prologue:
  * dA[k] = sum_f dy[f] w[k][f]; da[c] (+)= dA[c] f'(a[c]) - dA[Ca+c] f'(-a[c]).  dy bf16 [npix,F] (F in 8,16,32,64),
  * w fp32 [2 Ca, F] = the '{idx}_fc/weights' variable itself, a bf16 [npix,Ca] -> da bf16 [npix,Ca] */

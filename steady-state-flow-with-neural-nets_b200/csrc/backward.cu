@@ -38,7 +38,8 @@ __global__ void k_gate_bwd(const __nv_bfloat16* __restrict__ c2, const __nv_bflo
 __device__ __forceinline__ float elu_grad(float z) { return z > 0.f ? 1.f : __expf(z); }
 __global__ void k_prologue_bwd(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ x,
                                __nv_bfloat16* __restrict__ dx, long long npix, int C, int kind, int accumulate,
-                               float keep_prob, unsigned long long seed) {
+                               float keep_prob, unsigned long long seed, const unsigned long long* seed_dev) {
+  if (seed_dev) seed += *seed_dev;
   const int mult = pro_mult(kind);
   const long long total = npix * C;
   const bool drop = keep_prob < 1.0f;
@@ -119,7 +120,9 @@ __global__ void __launch_bounds__(BW_THREADS) k_gate_bwd_v8(const __nv_bfloat16*
 template <bool DROP>
 __global__ void __launch_bounds__(BW_THREADS) k_prologue_bwd_v8(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ x,
                                                                 __nv_bfloat16* __restrict__ dx, long long npix, int C, int kind,
-                                                                int accumulate, float keep_prob, unsigned long long seed) {
+                                                                int accumulate, float keep_prob, unsigned long long seed,
+                                                                const unsigned long long* seed_dev) {
+  if (DROP && seed_dev) seed += *seed_dev;
   const int mult = pro_mult(kind);
   const int cc = C >> 3;
   const long long total = npix * cc;
@@ -394,6 +397,7 @@ struct WgradParams {
   int transposed;      // 1: transposed conv: x is the INPUT [B,H,W,C] and dY the 2x output [B,OH,OW,N]
   float keep_prob;
   unsigned long long seed;
+  const unsigned long long* seed_dev;
   int kt, nt;          // number of 16-wide k / n tiles
 };
 
@@ -440,7 +444,8 @@ __global__ void __launch_bounds__(256) k_conv_wgrad(const WgradParams p) {
               pro_apply(p.pro, __bfloat162float(p.x[pidx * p.C + c]), p0, p1);
               v = (mult == 2 && k >= p.C) ? p1 : p0;
               if (p.pro != FN_PRO_NONE) v = __bfloat162float(__float2bfloat16(v));   // the forward operand was bf16
-              if (p.keep_prob < 1.0f) v *= dropout_scale(p.seed, (unsigned long long)(pidx * p.Keff + k), p.keep_prob);
+              if (p.keep_prob < 1.0f)
+                v *= dropout_scale(p.seed + (p.seed_dev ? *p.seed_dev : 0ull), (unsigned long long)(pidx * p.Keff + k), p.keep_prob);
             }
           }
           sa[pr][col] = v;
@@ -544,18 +549,18 @@ int gate_bwd(const void* c2, const void* g, void* dc2, long long npix, int F, cu
 }
 
 int prologue_bwd(const void* dA, const void* x, void* dx, long long npix, int C, int kind, int accumulate, float keep_prob,
-                 unsigned long long seed, cudaStream_t s) {
+                 unsigned long long seed, const unsigned long long* seed_dev, cudaStream_t s) {
   if (npix == 0) return 0;
   if ((C & 7) == 0)
     if (keep_prob < 1.0f)
       k_prologue_bwd_v8<true><<<bw_grid(npix * (C / 8)), BW_THREADS, 0, s>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)x,
-                                                                               (__nv_bfloat16*)dx, npix, C, kind, accumulate, keep_prob, seed);
+                                                                               (__nv_bfloat16*)dx, npix, C, kind, accumulate, keep_prob, seed, seed_dev);
     else
       k_prologue_bwd_v8<false><<<bw_grid(npix * (C / 8)), BW_THREADS, 0, s>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)x,
-                                                                                (__nv_bfloat16*)dx, npix, C, kind, accumulate, keep_prob, seed);
+                                                                                (__nv_bfloat16*)dx, npix, C, kind, accumulate, keep_prob, seed, seed_dev);
   else
     k_prologue_bwd<<<bw_grid(npix * C), BW_THREADS, 0, s>>>((const __nv_bfloat16*)dA, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx,
-                                                            npix, C, kind, accumulate, keep_prob, seed);
+                                                            npix, C, kind, accumulate, keep_prob, seed, seed_dev);
   count_launch();
   return check_launch("k_prologue_bwd");
 }
@@ -608,7 +613,7 @@ long long wgrad_workspace(long long rows, int T, int Keff, int N) { return (long
 long long wgrad_tc_workspace(int B, int H, int W, int C, int OH, int OW, int N, int ksize, int stride, int pro);
 bool wgrad_tc_try(const void* x, const void* dY, float* partial, int B, int H, int W, int C, int OH, int OW, int N, int ksize,
                   int stride, int pro, float keep_prob, unsigned long long seed, int* S_out, cudaStream_t stream, int& rc,
-                  bool want_bias = false, float** bias_partial_out = nullptr);
+                  bool want_bias = false, float** bias_partial_out = nullptr, const unsigned long long* seed_dev = nullptr);
 static long long max_ll(long long a, long long b) { return a > b ? a : b; }
 
 int conv_wgrad_launch(WgradParams& p, float* dW, float* workspace, cudaStream_t s) {
@@ -641,7 +646,14 @@ int fn_prologue_bwd(const void* dA, const void* x, void* dx, int64_t npix, int32
                     float keep_prob, uint64_t seed, void* stream) {
   FN_REQUIRE(dA && x && dx && npix >= 0 && C > 0, FN_E_INVAL, "fn_prologue_bwd: bad arguments");
   FN_REQUIRE(kind >= FN_PRO_NONE && kind <= FN_PRO_RELU, FN_E_INVAL, "fn_prologue_bwd: bad kind %d", kind);
-  return prologue_bwd(dA, x, dx, npix, C, kind, accumulate, keep_prob, seed, (cudaStream_t)stream);
+  return prologue_bwd(dA, x, dx, npix, C, kind, accumulate, keep_prob, seed, nullptr, (cudaStream_t)stream);
+}
+
+int fn_prologue_bwd_dev(const void* dA, const void* x, void* dx, int64_t npix, int32_t C, int32_t kind, int32_t accumulate,
+                        float keep_prob, uint64_t seed, const uint64_t* seed_dev, void* stream) {
+  FN_REQUIRE(dA && x && dx && npix >= 0 && C > 0, FN_E_INVAL, "fn_prologue_bwd_dev: bad arguments");
+  FN_REQUIRE(kind >= FN_PRO_NONE && kind <= FN_PRO_RELU, FN_E_INVAL, "fn_prologue_bwd_dev: bad kind %d", kind);
+  return prologue_bwd(dA, x, dx, npix, C, kind, accumulate, keep_prob, seed, (const unsigned long long*)seed_dev, (cudaStream_t)stream);
 }
 
 /* data gradient of the nin skip fused with the adjoint of its prologue (concat kinds): dy bf16 [npix,F], w fp32 [2 Ca, F]
@@ -725,7 +737,8 @@ static int conv_wgrad_impl(const fn_conv_desc* d, const void* dY, float* dW, flo
     int S = 0, rc = 0;
     float* bias_partial = nullptr;
     if (wgrad_tc_try(d->x, dY, workspace, d->B, d->H, d->W, d->Cin, OH, OW, d->Cout, d->ksize, d->stride, d->prologue, d->keep_prob,
-                     d->dropout_seed, &S, (cudaStream_t)stream, rc, db != nullptr, &bias_partial)) {
+                     d->dropout_seed, &S, (cudaStream_t)stream, rc, db != nullptr, &bias_partial,
+                     (const unsigned long long*)d->dropout_seed_dev)) {
       if (rc) return rc;
       rc = reduce_partials(workspace, dW, (long long)d->ksize * d->ksize * d->Cin * pro_mult(d->prologue) * d->Cout, S,
                            (cudaStream_t)stream);
@@ -750,6 +763,7 @@ static int conv_wgrad_impl(const fn_conv_desc* d, const void* dY, float* dW, flo
   p.transposed = 0;
   p.keep_prob = d->keep_prob;
   p.seed = d->dropout_seed;
+  p.seed_dev = (const unsigned long long*)d->dropout_seed_dev;
   {
     int rc = conv_wgrad_launch(p, dW, workspace, (cudaStream_t)stream);
     if (rc || !db) return rc;

@@ -45,6 +45,7 @@ struct Params {
   int gate_bwd;                        // FN_EPI_GATE_BWD (see conv_s1p.cu)
   float keep_prob;                     // < 1: dropout on the prologue output (training)
   unsigned long long dropout_seed;
+  const unsigned long long* dropout_seed_dev;
 };
 
 template <int CLOG, int J, bool GATE, bool SKIP, bool TR, int NST>
@@ -119,6 +120,7 @@ __device__ __forceinline__ void transform_tile_dropout(uint32_t stage, uint32_t 
                                                        int x0) {
   constexpr int ITEMS = CF::P * CF::CH;
   constexpr int SH = CF::CH == 8 ? 3 : 4;
+  const unsigned long long seed = p.dropout_seed + (p.dropout_seed_dev ? *p.dropout_seed_dev : 0ull);
   for (int idx = tid; idx < ITEMS; idx += 256) {
     const int ch = idx & (CF::CH - 1);
     const int sp = idx >> SH;
@@ -134,8 +136,8 @@ __device__ __forceinline__ void transform_tile_dropout(uint32_t stage, uint32_t 
     in.v = lds128(stage + (uint32_t)idx * 16u);
     float sc0[8], sc1[8];
     if (inside) {
-      dropout_scale8(p.dropout_seed, base, p.keep_prob, sc0);
-      dropout_scale8(p.dropout_seed, base + CF::C, p.keep_prob, sc1);
+      dropout_scale8(seed, base, p.keep_prob, sc0);
+      dropout_scale8(seed, base + CF::C, p.keep_prob, sc1);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -493,6 +495,7 @@ static int launch(const fn_conv_desc& d, int* status, cudaStream_t stream) {
   p.Cres = d.Cres; p.RH = d.RH; p.RW = d.RW; p.res_pool = d.res_pool;
   p.keep_prob = d.keep_prob;
   p.dropout_seed = d.dropout_seed;
+  p.dropout_seed_dev = (const unsigned long long*)d.dropout_seed_dev;
   p.gate_bwd = d.epilogue == FN_EPI_GATE_BWD ? 1 : 0;
   auto kern = k_conv_s1d<CLOG, J, GATE, SKIP, TR, NST>;
   static bool configured = false;

@@ -47,6 +47,7 @@ struct SpParams {
   int gate_bwd;                        // FN_EPI_GATE_BWD: y = d(pre-gate) [., 2F] from the recomputed [u|v] and g = res
   float keep_prob;                     // < 1: dropout on the prologue output (training)
   unsigned long long dropout_seed;
+  const unsigned long long* dropout_seed_dev;   // optional device-resident addend (graph replays)
   long long* timing;                   // debug: 8 clock64 stamps per CTA for its third tile (nullptr in production)
   int timing_ctas;
 };
@@ -120,6 +121,7 @@ __device__ __forceinline__ void transform_tile_dropout(uint32_t stage, uint32_t 
                                                        int x0) {
   constexpr int ITEMS = Cfg::P * Cfg::CH;
   constexpr int SH = Cfg::CH == 1 ? 0 : (Cfg::CH == 2 ? 1 : (Cfg::CH == 4 ? 2 : 3));
+  const unsigned long long seed = p.dropout_seed + (p.dropout_seed_dev ? *p.dropout_seed_dev : 0ull);
   for (int idx = tid; idx < ITEMS; idx += 128) {
     const int ch = idx & (Cfg::CH - 1);
     const int pp = idx >> SH;
@@ -131,8 +133,8 @@ __device__ __forceinline__ void transform_tile_dropout(uint32_t stage, uint32_t 
     in.v = lds128(stage + (uint32_t)idx * 16u);
     float sc0[8], sc1[8];
     if (inside) {
-      dropout_scale8(p.dropout_seed, base, p.keep_prob, sc0);
-      dropout_scale8(p.dropout_seed, base + Cfg::C, p.keep_prob, sc1);
+      dropout_scale8(seed, base, p.keep_prob, sc0);
+      dropout_scale8(seed, base + Cfg::C, p.keep_prob, sc1);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -523,6 +525,7 @@ static int launch_s1p(const fn_conv_desc& d, cudaStream_t stream) {
   p.Cres = d.Cres; p.RH = d.RH; p.RW = d.RW; p.res_pool = d.res_pool;
   p.keep_prob = d.keep_prob;
   p.dropout_seed = d.dropout_seed;
+  p.dropout_seed_dev = (const unsigned long long*)d.dropout_seed_dev;
   p.gate_bwd = d.epilogue == FN_EPI_GATE_BWD ? 1 : 0;
   tc_timing_buffer(&p.timing, &p.timing_ctas);
 

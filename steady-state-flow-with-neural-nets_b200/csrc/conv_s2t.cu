@@ -44,6 +44,7 @@ struct Params {
   const __nv_bfloat16* res;
   float keep_prob;
   unsigned long long seed;
+  const unsigned long long* seed_dev;
 };
 
 template <int MODE, int CLOG, int J, int NBUF, int R = 1>
@@ -307,8 +308,9 @@ __global__ void __launch_bounds__(THREADS) k_conv_s2t(const __grid_constant__ Pa
               float sc0[8], sc1[8];
               const bool drop = p.keep_prob < 1.0f;
               if (drop) {
-                dropout_scale8(p.seed, (unsigned long long)pix * CF::NREAL + c0, p.keep_prob, sc0);
-                dropout_scale8(p.seed, (unsigned long long)pix * CF::NREAL + CY + c0, p.keep_prob, sc1);
+                const unsigned long long seed = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
+                dropout_scale8(seed, (unsigned long long)pix * CF::NREAL + c0, p.keep_prob, sc0);
+                dropout_scale8(seed, (unsigned long long)pix * CF::NREAL + CY + c0, p.keep_prob, sc1);
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -364,6 +366,7 @@ struct AdjArgs {
   const void* res = nullptr;
   float keep_prob = 1.0f;
   unsigned long long seed = 0;
+  const unsigned long long* seed_dev = nullptr;
 };
 
 template <int MODE, int CLOG, int J, int NBUF, int R = 1>
@@ -390,6 +393,7 @@ static int launch(const void* x, const void* wpk, const float* bias, void* y, in
   p.res = (const __nv_bfloat16*)adj.res;
   p.keep_prob = adj.keep_prob;
   p.seed = adj.seed;
+  p.seed_dev = adj.seed_dev;
   auto kern = k_conv_s2t<MODE, CLOG, J, NBUF, R>;
   static bool configured = false;
   if (!configured) {
@@ -461,6 +465,7 @@ bool conv_s1n_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
     adj.res = d.res;
     adj.keep_prob = d.keep_prob;
     adj.seed = d.dropout_seed;
+    adj.seed_dev = (const unsigned long long*)d.dropout_seed_dev;
   }
   if (get_encode() == nullptr) return false;
   const int clog = d.Cin == 8 ? 0 : d.Cin == 16 ? 1 : d.Cin == 32 ? 2 : d.Cin == 64 ? 3 : -1;

@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_conv_simt(const ConvParams p) 
       stage_weights<NACC>(w + (size_t)tap * p.Keff * d.Cout, d.Cin, c0, CR, mult, d.Cout, n0, F, wsm);
       __syncthreads();
       if (inb)
-        accumulate_pixel<NACC>(x + pidx * d.Cin, d.Cin, c0, CR, d.prologue, wsm, acc, drop, d.dropout_seed,
+        accumulate_pixel<NACC>(x + pidx * d.Cin, d.Cin, c0, CR, d.prologue, wsm, acc, drop,
+                               d.dropout_seed + (d.dropout_seed_dev ? *d.dropout_seed_dev : 0ull),
                                d.dropout_offset + pidx * p.Keff, d.keep_prob);
     }
   }

@@ -69,6 +69,7 @@ struct Params {
   int a3;               // 1: three column-shifted copies of every plane, the 3 taps of a filter row share one MMA
   float keep_prob;
   unsigned long long seed;
+  const unsigned long long* seed_dev;
 };
 
 enum { SB_X = 0, SB_PF = MAXBUF, SB_TF = 2 * MAXBUF, SB_FIN = 3 * MAXBUF };
@@ -96,8 +97,9 @@ __device__ __forceinline__ void transform_tile(const Params& p, uint32_t stage, 
     if (DROP) {     // tf.nn.dropout on the conv input (flow_architecture.py:144-145): same mask as the forward
       const int iy = G::S2 ? 2 * y0 + r : y0 - 1 + r, ix = G::S2 ? 2 * x0 + c : x0 - 1 + c;
       const unsigned long long pidx = ((unsigned long long)b * p.H + iy) * p.W + ix;
-      dropout_scale8(p.seed, pidx * p.Keff + ch * 8, p.keep_prob, sc0);
-      if (mult == 2) dropout_scale8(p.seed, pidx * p.Keff + p.C + ch * 8, p.keep_prob, sc1);
+      const unsigned long long seed = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
+      dropout_scale8(seed, pidx * p.Keff + ch * 8, p.keep_prob, sc0);
+      if (mult == 2) dropout_scale8(seed, pidx * p.Keff + p.C + ch * 8, p.keep_prob, sc1);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -492,7 +494,7 @@ long long wgrad_tc_workspace(int B, int H, int W, int C, int OH, int OW, int N, 
 // null when the extra accumulator does not fit TMEM and the caller has to run the bias kernel)
 bool wgrad_tc_try(const void* x, const void* dY, float* partial, int B, int H, int W, int C, int OH, int OW, int N, int ksize,
                   int stride, int pro, float keep_prob, unsigned long long seed, int* S_out, cudaStream_t stream, int& rc,
-                  bool want_bias, float** bias_partial_out) {
+                  bool want_bias, float** bias_partial_out, const unsigned long long* seed_dev) {
   using namespace wg;
   rc = 0;
   Plan pl;
@@ -523,6 +525,7 @@ bool wgrad_tc_try(const void* x, const void* dY, float* partial, int B, int H, i
   if (bias_partial_out) *bias_partial_out = p.bias_partial;
   p.keep_prob = keep_prob;
   p.seed = seed;
+  p.seed_dev = seed_dev;
   p.status = tc_status_word();
   if (!p.status) { rc = (int)cudaErrorMemoryAllocation; return true; }
   *S_out = pl.S;

@@ -11,11 +11,14 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FLOWNET_LIB", os.path.join(_HERE, "libflownet.so"))   # override: A/B builds
 
-FN_ABI_VERSION = 2
+FN_ABI_VERSION = 3
 # enum fn_prologue
 PRO_NONE, PRO_CONCAT_ELU, PRO_ELU, PRO_CONCAT_RELU, PRO_RELU = 0, 1, 2, 3, 4
 # enum fn_epilogue
 EPI_BIAS, EPI_GATE_RES, EPI_RES, EPI_TANH, EPI_GATE_BWD, EPI_PRO_BWD = 0, 1, 2, 3, 4, 5
+# device int64 [1] added to every dropout seed inside the kernels (None: none) -- set by flow_net.CompiledTraining so that
+# replays of the captured step draw a new mask
+DROPOUT_SEED_DEV = None
 # enum fn_impl
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 
@@ -32,6 +35,7 @@ class ConvDesc(C.Structure):
         ("Cres", C.c_int32), ("RH", C.c_int32), ("RW", C.c_int32), ("res_pool", C.c_int32),
         ("keep_prob", C.c_float),
         ("dropout_seed", C.c_uint64), ("dropout_offset", C.c_uint64),
+        ("dropout_seed_dev", C.c_void_p),
         ("adj_prologue", C.c_int32), ("adj_accumulate", C.c_int32),
     ]
 
@@ -74,6 +78,7 @@ SYMBOLS = [
     ("fn_l2_loss", C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     ("fn_adam_step", C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
     ("fn_gate_bwd", C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
+    ("fn_prologue_bwd_dev", C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _P, _P]),
     ("fn_prologue_bwd", C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _P]),
     ("fn_nin_bwd", C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     ("fn_shortcut_bwd", C.c_int, [_P, _P] + [C.c_int32] * 9 + [_P]),
@@ -168,6 +173,7 @@ def tc_status() -> int:
 def conv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, ksize=3, stride=1, prologue=PRO_NONE, epilogue=EPI_BIAS,
              impl=IMPL_AUTO, w_tc=None, skip=None, w_skip=None, res=None, res_pool=False, keep_prob=1.0,
              dropout_seed=0, dropout_offset=0, adj_prologue=0, adj_accumulate=False, query=False):
+    # DROPOUT_SEED_DEV (module level): optional device int64 [1] added to every dropout seed inside the kernels
     """query=True: do not launch, return whether this call would run on the tensor cores."""
     _require_cuda(x, w, bias, y, skip, w_skip, res, w_tc)
     d = ConvDesc()
@@ -184,6 +190,7 @@ def conv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, ksize=3, stride=1, prologue=P
         d.res_pool = 1 if res_pool else 0
     d.keep_prob = float(keep_prob)
     d.dropout_seed, d.dropout_offset = int(dropout_seed), int(dropout_offset)
+    d.dropout_seed_dev = DROPOUT_SEED_DEV.data_ptr() if DROPOUT_SEED_DEV is not None else None
     d.adj_prologue, d.adj_accumulate = int(adj_prologue), int(bool(adj_accumulate))
     if query:
         return bool(lib.fn_conv_fwd_has_tcgen05(C.byref(d)))
@@ -309,8 +316,8 @@ def prologue_bwd(dA, x, kind, out=None, accumulate=False, keep_prob=1.0, seed=0)
     if out is None:
         out = torch.empty_like(x)
         accumulate = False
-    _check(lib.fn_prologue_bwd(_ptr(dA), _ptr(x), _ptr(out), x.numel() // Cc, Cc, kind, int(accumulate), float(keep_prob),
-                               int(seed), stream_ptr()), "fn_prologue_bwd")
+    _check(lib.fn_prologue_bwd_dev(_ptr(dA), _ptr(x), _ptr(out), x.numel() // Cc, Cc, kind, int(accumulate), float(keep_prob),
+                                   int(seed), _ptr(DROPOUT_SEED_DEV), stream_ptr()), "fn_prologue_bwd")
     return out
 
 
@@ -369,6 +376,7 @@ def conv_wgrad(x, dY, out, *, ksize, stride, prologue, keep_prob=1.0, dropout_se
     d.x = x.data_ptr()
     d.keep_prob = float(keep_prob)
     d.dropout_seed = int(dropout_seed)
+    d.dropout_seed_dev = DROPOUT_SEED_DEV.data_ptr() if DROPOUT_SEED_DEV is not None else None
     ws = _workspace(lib.fn_conv_wgrad_workspace(C.byref(d)), x.device)
     if db is not None:
         _check(lib.fn_conv_wgrad_bias(C.byref(d), _ptr(dY), _ptr(out), _ptr(db), _ptr(ws), stream_ptr()), "fn_conv_wgrad_bias")

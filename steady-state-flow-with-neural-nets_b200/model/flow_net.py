@@ -200,13 +200,14 @@ class CompiledTraining:
     and the Adam update stay outside (two more launches).  At small per-GPU batches -- BASELINE configs[2] sharded over
     4-8 GPUs -- the eager step is bound by the host's launch rate, the replay is not.
 
-    keep_prob must be 1.0: the dropout seed is a launch argument and would repeat on every replay."""
+    With keep_prob < 1 the kernels add a device-resident counter to their dropout seeds (fn_conv_desc.dropout_seed_dev);
+    step() bumps it before every replay, so each replay draws a new mask although the launch arguments are frozen."""
 
-    def __init__(self, batch_size, shape=(128, 256), keep_prob=1.0, in_dtype=torch.uint8):
+    def __init__(self, batch_size, shape=(128, 256), keep_prob=1.0, in_dtype=torch.uint8, dropout_seed=0):
         import model.flow_backward as fb
-        if keep_prob < 1.0:
-            raise ValueError("CompiledTraining: keep_prob < 1 needs a fresh dropout seed per step; use the eager step")
         self.fb = fb
+        self.keep_prob, self.dropout_seed = keep_prob, dropout_seed
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device="cuda") if keep_prob < 1.0 else None
         self.static_boundary = torch.zeros((batch_size, shape[0], shape[1], 1), dtype=in_dtype, device="cuda")
         self.static_sflow = torch.zeros((batch_size, shape[0], shape[1], 2), dtype=torch.float32, device="cuda")
         begin_training()
@@ -229,14 +230,20 @@ class CompiledTraining:
 
     def _fwd_bwd(self):
         flow_architecture.TAPE = []
-        sflow_p = inference(self.static_boundary, 1.0)
-        flat = ensure_training_state()
-        return self.fb.backward(flow_architecture.TAPE, sflow_p, self.static_sflow, flat)
+        native.DROPOUT_SEED_DEV = self.seed_dev
+        try:
+            sflow_p = inference(self.static_boundary, self.keep_prob, dropout_seed=self.dropout_seed)
+            flat = ensure_training_state()
+            return self.fb.backward(flow_architecture.TAPE, sflow_p, self.static_sflow, flat)
+        finally:
+            native.DROPOUT_SEED_DEV = None
 
     def step(self, boundary, sflow, lr):
         """boundary / sflow: CUDA or pinned host tensors of the captured shape.  Returns the loss (fp32 [1], device)."""
         self.static_boundary.copy_(boundary, non_blocking=True)
         self.static_sflow.copy_(sflow, non_blocking=True)
+        if self.seed_dev is not None:
+            self.seed_dev.add_(0x1E3779B97F4A7C15)           # new mask for this replay
         self.graph.replay()
         self.fb.adam_update(ensure_training_state(), lr)
         return self.loss

@@ -1147,3 +1147,34 @@ def test_compiled_training_step_matches_eager(native):
         flow_net.end_training()
         flow_net.reset_training_state()
         arch.reset_variables(1234)
+
+
+def test_compiled_training_with_dropout_draws_a_new_mask_per_replay(native):
+    """keep_prob < 1 inside the captured step: the device-resident seed counter changes the mask on every replay (same
+    inputs, different gradients), and the same counter value reproduces the same gradients."""
+    import model.flow_architecture as arch
+    import model.flow_net as flow_net
+    try:
+        arch.reset_variables(1234)
+        flow_net.reset_training_state()
+        ct = flow_net.CompiledTraining(2, (32, 64), keep_prob=0.7, dropout_seed=3)
+        b, s = flow_net.inputs(2, shape=(32, 64), seed=5)
+        flat = flow_net.ensure_training_state()
+        grads = []
+        for counter in (11, 12, 11):
+            ct.static_boundary.copy_(b)
+            ct.static_sflow.copy_(s)
+            ct.seed_dev.fill_(counter)
+            ct.graph.replay()
+            torch.cuda.synchronize()
+            grads.append(flat.grad.clone())
+        assert native.tc_status() == 0
+        assert torch.isfinite(grads[0]).all()
+        assert torch.equal(grads[0], grads[2])
+        assert rel_l2(grads[1], grads[0]) > 0.01          # another mask: measurably different gradients
+        l0 = ct.step(b, s, 1e-3).item()
+        assert np.isfinite(l0)
+    finally:
+        flow_net.end_training()
+        flow_net.reset_training_state()
+        arch.reset_variables(1234)
