@@ -30,6 +30,7 @@ flags.DEFINE_integer('batch_size', 8, """ training batch size """)
 flags.DEFINE_integer('max_steps', 500000, """ max number of steps to train """)
 flags.DEFINE_float('keep_prob', 0.7, """ keep probability for dropout """)
 flags.DEFINE_float('learning_rate', 1e-4, """ keep probability for dropout """)
+flags.DEFINE_bool('cuda_graph', True, """ replay forward + backward from one CUDA graph (flow_net.CompiledTraining) """)
 flags.DEFINE_string('data_glob', '../data/*.tfrecords', """ dataset files (reference: input/flow_input.py:45); synthetic data if none match """)
 
 
@@ -66,16 +67,27 @@ def train():
     if rank == 0:
         print("training on " + (FLAGS.data_glob if data_glob else "synthetic boundaries (no dataset found)"))
     flow_net.begin_training()
+    compiled = None
+    if FLAGS.cuda_graph:
+        # captures one step for this (batch, shape); its warm-up creates the variables and the flat buffers without
+        # changing the parameters, so the checkpoint's Adam slots can be restored right away
+        compiled = flow_net.CompiledTraining(per_rank, (128, 256), keep_prob=FLAGS.keep_prob, dropout_seed=1 + rank)
+        if restored is not None:
+            checkpoint.restore(restored, flow_architecture.VARIABLES, flow_net.ensure_training_state(), strict=False)
+            restored = None
     for step in range(start_step, FLAGS.max_steps):
         t = time.time()
         boundary, sflow = flow_net.inputs(per_rank, seed=(step * world + rank) * per_rank if not data_glob else rank,
                                           data_glob=data_glob)
-        sflow_p = flow_net.inference(boundary, FLAGS.keep_prob, dropout_seed=step * 131071 + rank)
-        error = flow_net.loss_image_train(sflow_p, sflow)
-        if restored is not None:                  # the Adam slots live in the flat buffers, which need the variables
-            checkpoint.restore(restored, flow_architecture.VARIABLES, flow_net.ensure_training_state(), strict=False)
-            restored = None
-        flow_net.train(error, FLAGS.learning_rate)
+        if compiled is not None:
+            error = compiled.step(boundary, sflow, FLAGS.learning_rate)
+        else:
+            sflow_p = flow_net.inference(boundary, FLAGS.keep_prob, dropout_seed=step * 131071 + rank)
+            error = flow_net.loss_image_train(sflow_p, sflow)
+            if restored is not None:              # the Adam slots live in the flat buffers, which need the variables
+                checkpoint.restore(restored, flow_architecture.VARIABLES, flow_net.ensure_training_state(), strict=False)
+                restored = None
+            flow_net.train(error, FLAGS.learning_rate)
         loss_value = float(error.item())
         elapsed = time.time() - t
         assert not np.isnan(loss_value), 'Model diverged with loss = NaN'

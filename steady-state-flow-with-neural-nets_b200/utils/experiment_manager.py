@@ -4,7 +4,7 @@ flag combination trains into its own directory."""
 import fnmatch
 import os
 
-NOT_PATH = ['base_dir', 'display_test', 'test_set', 'data_glob', 'min_queue_examples']
+NOT_PATH = ['base_dir', 'display_test', 'test_set', 'data_glob', 'min_queue_examples', 'cuda_graph', 'out_dir', 'num_runs']
 
 
 def make_checkpoint_path(base_path, FLAGS):
