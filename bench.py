@@ -396,7 +396,7 @@ def main():
                        "launch": "CUDA graph, %d kernels per step" % compiled.launches_per_replay},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel()) * world,
                     "d2h_bytes_per_step": int(out_host.numel() * 4) * world, "ms_per_step": ms_e2e / args.steps,
-                    "how": "CompiledInference.stream_host: copies on two side streams overlapped with compute",
+                    "how": "CompiledInference.stream_host: two alternating graphs, uploads / downloads on side streams straight into / out of their static buffers",
                     "serial_value": world * B * args.steps / (ms_e2e_serial * 1e-3)},
             "gpu_launches": compiled.launches_per_replay * args.steps * 3,
             "clocks": clocks,
