@@ -1,5 +1,5 @@
 """Measures the dataset path: native TFRecord/Example parse rate (single thread, CRC on and off),
-the pure-Python oracle parser beside it, and images/s delivered by the shuffle queue into GPU memory."""
+and images/s delivered by the shuffle queue into GPU memory."""
 import json
 import os
 import sys
@@ -13,7 +13,6 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, os.path.join(ROOT, "steady-state-flow-with-neural-nets_b200"))
 sys.path.insert(0, ROOT)
 import input.flow_input as fi  # noqa: E402
-from oracle import tfrecord_oracle as tfo  # noqa: E402
 from utils.synthetic import synth_boundary, synth_sflow  # noqa: E402
 
 N = int(os.environ.get("N", "512"))
@@ -41,12 +40,6 @@ for th in (1, 4, 8, 16):
     while time.time() - t0 < 0.5:
         f.read_batch_into(np.arange(len(nb)) % len(f), nb, ns, th); reps += 1
     out["batch_parse_records_per_s_%dthreads" % th] = reps * len(nb) / (time.time() - t0)
-raw = open(path, "rb").read()
-t0 = time.time()
-k = 0
-for payload in tfo.read_records(raw[: (size // N) * 8], check_crc=False):
-    tfo.decode_example(payload); k += 1
-out["oracle_python_records_per_s_nocrc"] = k / (time.time() - t0)
 if torch.cuda.is_available():
     q = fi.FlowInputQueue([path], 64, min_after_dequeue=256, device="cuda")
     for _ in range(3):
