@@ -2,7 +2,7 @@
 """GPU bring-up diagnostic for the tcgen05 conv kernel: runs a few fused-conv cases with both
 shared-memory-descriptor conventions (LBO/SBO as documented vs swapped), each in its own process
 (a faulting kernel poisons its CUDA context), and prints the error of each against the fp64 oracle
-and against the CUDA-core kernel.  Usage: python tools/diag_tc.py [> gpurun_out/diag_tc.txt]"""
+and against the CUDA-core kernel.  Usage: python tests/diag_tc.py [> gpurun_out/diag_tc.txt]"""
 import os
 import subprocess
 import sys
