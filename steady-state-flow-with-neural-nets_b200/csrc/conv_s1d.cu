@@ -34,6 +34,7 @@ constexpr int CHUNK_BYTES = 32768;
 
 struct Params {
   CUtensorMap tm_x, tm_skip, tm_res;
+  CUtensorMap tm_w;                    // NSPLIT = 2: the packed weights as 8-byte units (2 FL, parts, 2 K halves, k-steps)
   const __nv_bfloat16* wpk;
   const float* bias;
   __nv_bfloat16* y;
@@ -48,15 +49,20 @@ struct Params {
   const unsigned long long* dropout_seed_dev;
 };
 
-template <int CLOG, int J, bool GATE, bool SKIP, bool TR, int NST>
+// NSPLIT = 2: two CTAs share a tile, each computes half of the output channels (for the gate: the u and the v columns of
+// the same channels) and streams only its half of the weights -- the 8x16 level at batch 64 is 64 tiles for 148 SMs
+template <int CLOG, int J, bool GATE, bool SKIP, bool TR, int NST, int NSPLIT = 1>
 struct Cfg {
   static constexpr int CH = 1 << CLOG, C = 8 * CH, F = C;
   static constexpr int N = GATE ? 2 * C : C;
+  static constexpr int FL = F / NSPLIT;            // output channels of one CTA
+  static constexpr int NL = N / NSPLIT;            // accumulator columns of one CTA (u part, then v part)
+  static constexpr int PARTS = GATE ? 2 : 1;
   static constexpr int KS = CH;
   static constexpr int KSTEPS = 9 * KS + (SKIP ? KS : 0);
   static constexpr int PU = 8 * J + 2, PV = 18, P = PU * PV;
   static constexpr int PPAD = P + ((1 - (P & 7)) + 8) % 8;          // CH >= 8: stride = 1 (mod 8) pixels
-  static constexpr int SPC = CHUNK_BYTES / (N * 32);                 // k-steps per weight chunk
+  static constexpr int SPC = CHUNK_BYTES / (NL * 32);                // k-steps per weight chunk
   static constexpr int NCHUNKS = (KSTEPS + SPC - 1) / SPC;
   static constexpr int PLANE_BYTES = (2 * CH * PPAD * 16 + 127) / 128 * 128;
   static constexpr int STAGE_BYTES = ((P * C * 2) + 127) / 128 * 128;
@@ -68,10 +74,11 @@ struct Cfg {
   static constexpr int OFF_STAGE_S = OFF_STAGE + STAGE_REGION;
   static constexpr int OFF_RING = OFF_STAGE_S + (SKIP ? STAGE_BYTES : 0);
   static constexpr int SMEM = OFF_RING + NST * CHUNK_BYTES + 128;
-  static constexpr int ACC_COLS = J * N;
+  static constexpr int ACC_COLS = J * NL;
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(SPC >= 1, "chunk smaller than one k-step");
+  static_assert(NSPLIT == 1 || (!SKIP && FL % 16 == 0 && KSTEPS % SPC == 0), "channel split: no skip operand, whole chunks");
 };
 
 // mbarriers: X stage full, S skip stage full, R shortcut full, TF accumulators full, TE accumulators drained,
@@ -196,9 +203,9 @@ __device__ __forceinline__ void shortcut_generic(const Params& p, int F, int b, 
   }
 }
 
-template <int CLOG, int J, bool GATE, bool SKIP, bool TR, int NST>
+template <int CLOG, int J, bool GATE, bool SKIP, bool TR, int NST, int NSPLIT = 1>
 __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Params p) {
-  using CF = Cfg<CLOG, J, GATE, SKIP, TR, NST>;
+  using CF = Cfg<CLOG, J, GATE, SKIP, TR, NST, NSPLIT>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const uint32_t sbase = ptx::smem_u32(smem);
@@ -219,7 +226,10 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
     u0 = tu * 8 * J;
     v0 = tv * 16;
   };
-  const int n_local = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // CTA -> (tile slot, channel half)
+  const int nh = (int)blockIdx.x % NSPLIT;
+  const int cta = (int)blockIdx.x / NSPLIT, ncta = (int)gridDim.x / NSPLIT;
+  const int n_local = (cta < p.ntiles) ? (p.ntiles - 1 - cta) / ncta + 1 : 0;
 
   if (warp == 8) {
     ptx::tmem_alloc(sbase + 128, (uint32_t)CF::TMEM_COLS);
@@ -259,7 +269,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
       for (int it = 0; it < n_local && ok; ++it) {
         const uint32_t par_it = (uint32_t)(it & 1), par_prev = par_it ^ 1u;
         int b, u0, v0;
-        tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, u0, v0);
+        tile_coords(cta + it * ncta, b, u0, v0);
         const int x0 = TR ? v0 : u0, y0 = TR ? u0 : v0;
         if (it >= 1) {                                  // stage region (aliased by the shortcut tile) free again
           ok = ptx::mbar_wait(bar(SB_TE), par_prev);
@@ -278,11 +288,18 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
             ok = ptx::mbar_wait(bar(SB_EMPTY + s), (uint32_t)(((gchunk / NST) - 1) & 1));
             if (!ok) { atomicCAS(p.status, 0, 32); break; }
           }
-          const int steps = (c == CF::NCHUNKS - 1) ? (CF::KSTEPS - c * CF::SPC) : CF::SPC;
-          const uint32_t bytes = (uint32_t)(steps * CF::N * 32);
-          ptx::mbar_arrive_expect_tx(bar(SB_FULL + s), bytes);
-          ptx::bulk_g2s(sbase + CF::OFF_RING + s * CHUNK_BYTES,
-                        reinterpret_cast<const unsigned char*>(p.wpk) + (size_t)c * CF::SPC * CF::N * 32, bytes, bar(SB_FULL + s));
+          if (NSPLIT == 1) {
+            const int steps = (c == CF::NCHUNKS - 1) ? (CF::KSTEPS - c * CF::SPC) : CF::SPC;
+            const uint32_t bytes = (uint32_t)(steps * CF::N * 32);
+            ptx::mbar_arrive_expect_tx(bar(SB_FULL + s), bytes);
+            ptx::bulk_g2s(sbase + CF::OFF_RING + s * CHUNK_BYTES,
+                          reinterpret_cast<const unsigned char*>(p.wpk) + (size_t)c * CF::SPC * CF::N * 32, bytes, bar(SB_FULL + s));
+          } else {
+            // one tensor copy per chunk: this CTA's FL rows of the u block (and of the v block) for both K halves of SPC
+            // k-steps, rows of FL * 16 contiguous bytes, landing as [kstep][khalf][u rows | v rows][16 B]
+            ptx::mbar_arrive_expect_tx(bar(SB_FULL + s), (uint32_t)(CF::SPC * CF::NL * 32));
+            tma_load_4d(sbase + CF::OFF_RING + s * CHUNK_BYTES, &p.tm_w, bar(SB_FULL + s), 2 * nh * CF::FL, 0, 0, c * CF::SPC);
+          }
           if (!res_issued && c >= NST - 1) {            // ring primed: now fetch the shortcut once the stage is consumed
             ok = ptx::mbar_wait(bar(SB_ST), par_it);
             if (!ok) { atomicCAS(p.status, 0, 33); break; }
@@ -305,7 +322,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
   } else {
     // =========================== workers ===========================
     const uint32_t leader = ptx::elect_one();
-    constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, CF::N);
+    constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, CF::NL);
     const int q = warp & 3, half = warp >> 2;
     const int r = q * 32 + lane;                      // accumulator row == TMEM lane
     const int v = r >> 3, u = r & 7;
@@ -314,7 +331,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
     for (int it = 0; it < n_local; ++it) {
       const uint32_t par_it = (uint32_t)(it & 1);
       int b, u0, v0;
-      tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, u0, v0);
+      tile_coords(cta + it * ncta, b, u0, v0);
       // ---- transform
       ok = ok && ptx::mbar_wait(bar(SB_X), par_it);
       if (!ok) atomicCAS(p.status, 0, 34);
@@ -336,8 +353,8 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
         const uint64_t a_tmpl = ptx::smem_desc(sbase + CF::OFF_PLANES, CF::PPAD * 16, CF::PU * 16) + (uint64_t)(8 * warp);
         const uint64_t s_tmpl = ptx::smem_desc(sbase + CF::OFF_PLANES_S + (CF::PU + 1) * 16, CF::PPAD * 16, CF::PU * 16) +
                                 (uint64_t)(8 * warp);
-        const uint64_t b_tmpl = ptx::smem_desc(sbase + CF::OFF_RING, CF::N * 16, 128);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(warp * CF::N);
+        const uint64_t b_tmpl = ptx::smem_desc(sbase + CF::OFF_RING, CF::NL * 16, 128);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(warp * CF::NL);
 #pragma unroll
         for (int c = 0; c < CF::NCHUNKS; ++c) {
           const int gc = gchunk + c;
@@ -352,7 +369,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
 
             const int ks = c * CF::SPC + i;
             if (ks < CF::KSTEPS) {
-              const uint32_t b_off = (uint32_t)(i * CF::N * 32) >> 4;
+              const uint32_t b_off = (uint32_t)(i * CF::NL * 32) >> 4;
               if (ks < 9 * CF::KS) {
                 const int tap = ks / CF::KS, kk = ks % CF::KS;
                 const int di = tap / 3, dj = tap % 3;
@@ -386,16 +403,17 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
         const int oy = TR ? cu : cv, ox = TR ? cv : cu;
         const bool live = ok && oy < p.H && ox < p.W;
         const size_t pix = ((size_t)b * p.H + oy) * p.W + ox;
-        const uint32_t col0 = lane_base + (uint32_t)(j * CF::N);
+        const uint32_t col0 = lane_base + (uint32_t)(j * CF::NL);
         // shortcut tile layout = TMA box order: [16 rows of v][8J of u] or, TR, [8J of u][16 of v]
         const uint32_t res_pix = TR ? (uint32_t)((8 * j + u) * 16 + v) : (uint32_t)(v * 8 * J + 8 * j + u);
 #pragma unroll 2
-        for (int g8 = 0; g8 < CF::F / 16; ++g8) {
-          const int c0 = half * (CF::F / 2) + g8 * 8;
+        for (int g8 = 0; g8 < CF::FL / 16; ++g8) {
+          const int cl = half * (CF::FL / 2) + g8 * 8;      // column inside this CTA's accumulator
+          const int c0 = nh * CF::FL + cl;                  // output channel
           float o[8];
           if (GATE) {
             float a[8], g[8];
-            ptx::tmem_ld8x2(col0 + c0, col0 + CF::F + c0, a, g);
+            ptx::tmem_ld8x2(col0 + cl, col0 + CF::FL + cl, a, g);
             if (p.gate_bwd) {          // du = gy*s, dv = gy*u*s*(1-s), gy = the staged "res" tile
               bf16x8 gy, du, dv;
               gy.v = lds128(sbase + CF::OFF_STAGE + (res_pix * CF::F + (uint32_t)c0) * 2u);
@@ -426,7 +444,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
               shortcut_generic(p, CF::F, b, oy, ox, c0, o);
             }
           } else {
-            ptx::tmem_ld8(col0 + c0, o);
+            ptx::tmem_ld8(col0 + cl, o);
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] += sbias[c0 + i];
           }
@@ -457,9 +475,9 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
 
 // ------------------------------------------------------------------------------------ host side
 
-template <int CLOG, int J, bool GATE, bool SKIP, bool TR, int NST>
+template <int CLOG, int J, bool GATE, bool SKIP, bool TR, int NST, int NSPLIT = 1>
 static int launch(const fn_conv_desc& d, int* status, cudaStream_t stream) {
-  using CF = Cfg<CLOG, J, GATE, SKIP, TR, NST>;
+  using CF = Cfg<CLOG, J, GATE, SKIP, TR, NST, NSPLIT>;
   Params p;
   memset(&p, 0, sizeof(p));
   // box order is (C, W-extent, H-extent): the fast tile axis u lies along x unless TR
@@ -497,18 +515,34 @@ static int launch(const fn_conv_desc& d, int* status, cudaStream_t stream) {
   p.dropout_seed = d.dropout_seed;
   p.dropout_seed_dev = (const unsigned long long*)d.dropout_seed_dev;
   p.gate_bwd = d.epilogue == FN_EPI_GATE_BWD ? 1 : 0;
-  auto kern = k_conv_s1d<CLOG, J, GATE, SKIP, TR, NST>;
+  auto kern = k_conv_s1d<CLOG, J, GATE, SKIP, TR, NST, NSPLIT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(s1d): %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
-  int grid = p.ntiles < 148 ? p.ntiles : 148;
+  if (NSPLIT > 1) {
+    // packed weights [kstep][khalf][N rows][8 bf16] seen as 8-byte units: (2 F per block of F rows, N / F blocks, 2, ksteps)
+    PFN_encodeTiled enc = get_encode();
+    const cuuint64_t dims[4] = {(cuuint64_t)(2 * CF::F), (cuuint64_t)CF::PARTS, 2, (cuuint64_t)CF::KSTEPS};
+    const cuuint64_t strides[3] = {(cuuint64_t)CF::F * 16, (cuuint64_t)CF::N * 16, (cuuint64_t)CF::N * 32};
+    const cuuint32_t box[4] = {(cuuint32_t)(2 * CF::FL), (cuuint32_t)CF::PARTS, 2, (cuuint32_t)CF::SPC};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (!enc || enc(&p.tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(d.w_tc), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_error("conv_s1d: tensor map (weights) failed");
+      return FN_E_UNSUPPORTED;
+    }
+  }
+  int grid = (p.ntiles < 148 / NSPLIT ? p.ntiles : 148 / NSPLIT) * NSPLIT;
   launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)CF::SMEM, stream, p);
   count_launch();
   return check_launch("k_conv_s1d");
 }
+
+static int g_nsplit = 1;    // debug: 0 disables the channel split (A/B timing, tests)
 
 }  // namespace s1d
 
@@ -538,7 +572,10 @@ bool conv_s1d_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
       Cfg<CL, JJ, G, S, T, NS>::SMEM <= 226 * 1024) {                                                    \
     if (!dry_run) {                                                                                      \
       int* st = tc_status_word();                                                                        \
-      rc = st ? launch<CL, JJ, G, S, T, NS>(d, st, stream) : (int)cudaErrorMemoryAllocation;             \
+      constexpr int SPL = (CL == 4 && T && !S) ? 2 : 1;   /* 8x16 level: channel split when under half a wave */ \
+      const bool split = SPL == 2 && g_nsplit && d.B * ((d.W + 15) / 16) * ((d.H + 8 * JJ - 1) / (8 * JJ)) <= 74;     \
+      rc = !st ? (int)cudaErrorMemoryAllocation                                                          \
+               : split ? launch<CL, JJ, G, S, T, NS, SPL>(d, st, stream) : launch<CL, JJ, G, S, T, NS>(d, st, stream); \
     }                                                                                                    \
     return true;                                                                                         \
   }
@@ -559,3 +596,8 @@ bool conv_s1d_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
 }
 
 }  // namespace fn
+
+extern "C" {
+// test / timing hook: 0 disables the two-CTA channel split of the 8x16 level
+void fn_debug_set_nsplit(int v) { fn::s1d::g_nsplit = v; }
+}

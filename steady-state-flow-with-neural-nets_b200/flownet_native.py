@@ -106,6 +106,7 @@ DEBUG_SYMBOLS = [
     ("fn_debug_set_timing", None, [C.c_void_p, C.c_int]),
     ("fn_debug_set_use_s1p", None, [C.c_int]),
     ("fn_debug_set_wgrad_swap", None, [C.c_int]),
+    ("fn_debug_set_nsplit", None, [C.c_int]),
 ]
 
 

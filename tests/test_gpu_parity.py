@@ -1178,3 +1178,34 @@ def test_compiled_training_with_dropout_draws_a_new_mask_per_replay(native):
         flow_net.end_training()
         flow_net.reset_training_state()
         arch.reset_variables(1234)
+
+
+@pytest.mark.parametrize("B,gate,keep", [(5, True, 1.0), (5, False, 1.0), (64, True, 1.0), (3, True, 0.7), (4, "bwd", 1.0)])
+def test_deep_level_channel_split_is_bit_identical(native, B, gate, keep):
+    """conv_s1d NSPLIT = 2 (two CTAs per 8x16 tile, half of the output channels and of the weight stream each) against
+    the unsplit kernel: same MMA order per output -> identical bits."""
+    g = torch.Generator().manual_seed(51)
+    C, H, W = 128, 8, 16
+    gated = bool(gate)
+    N = 2 * C if gated else C
+    x = torch.randn(B, H, W, C, generator=g).to("cuda", torch.bfloat16)
+    w16 = ((torch.rand(9, 2 * C, N, generator=g) * 2 - 1) * 0.03).to("cuda", torch.bfloat16)
+    bias = (torch.rand(N, generator=g) - 0.5).to("cuda")
+    res = torch.randn(B, H, W, C, generator=g).to("cuda", torch.bfloat16) if gated else None
+    w_tc = native.pack_conv_weights_tc(w16, None, 3, 2 * C, 0, N, gated)
+    epi = native.EPI_GATE_BWD if gate == "bwd" else (native.EPI_GATE_RES if gated else native.EPI_BIAS)
+    cy = N if gate == "bwd" else C
+    ys = []
+    try:
+        for split in (1, 0):
+            native.lib.fn_debug_set_nsplit(split)
+            y = torch.full((B, H, W, cy), float("nan"), device="cuda", dtype=torch.bfloat16)
+            native.conv_fwd(x, w16, bias, y, B=B, H=H, W=W, Cin=C, Cout=N, ksize=3, stride=1, prologue=1, epilogue=epi,
+                            impl=native.IMPL_TCGEN05, w_tc=w_tc, res=res, keep_prob=keep, dropout_seed=2)
+            torch.cuda.synchronize()
+            assert native.tc_status() == 0
+            ys.append(y)
+    finally:
+        native.lib.fn_debug_set_nsplit(1)
+    assert not torch.isnan(ys[0].float()).any()
+    assert torch.equal(ys[0], ys[1])
