@@ -33,6 +33,7 @@ enum { VAR_WIDE = 0, VAR_SKIP = 1 };
 
 struct Params {
   CUtensorMap tm_x, tm_res, tm_skip;
+  CUtensorMap tm_w;                    // NSPLIT = 2: packed weights as 8-byte units (2 F, parts, 2 K halves, k-steps)
   const __nv_bfloat16* wpk;
   const float* bias;
   __nv_bfloat16* y;
@@ -44,20 +45,24 @@ struct Params {
   int gate_bwd;
 };
 
-template <bool GATE, int VAR>
+// NSPLIT = 2 (wide variant): two CTAs share a tile, each owns half of the output channels and of the weight stream
+// (conv_s1d.cu has the same option; here a CTA's stream is 4.7 MB per tile without it)
+template <bool GATE, int VAR, int NSPLIT = 1>
 struct Cfg {
   static constexpr bool SKIPV = VAR == VAR_SKIP;
   static constexpr int C = SKIPV ? CP : KP * CP;                   // raw channels of x (the tensor-map extent)
   static constexpr int F = C;                                      // output channels
   static constexpr int N = GATE ? 2 * C : C;                       // 512 / 256 (wide), 128 (skip variant)
-  static constexpr int NMMA = N <= 256 ? N : 256;                  // columns of one MMA
-  static constexpr int NM = N / NMMA;                              // MMAs per k-step
+  static constexpr int FL = F / NSPLIT, NL = N / NSPLIT;           // output channels / accumulator columns of one CTA
+  static constexpr int PARTS = GATE ? 2 : 1;                       // row blocks of F rows in the packed image (u, v)
+  static constexpr int NMMA = NL <= 256 ? NL : 256;                // columns of one MMA
+  static constexpr int NM = NL / NMMA;                             // MMAs per k-step
   static constexpr int KS = CHP;                                   // k-steps per tap and pass (2 * 128 / 16)
   static constexpr int KSTEPS_P0 = 9 * KS;                         // pass 0: all taps
   static constexpr int KSTEPS_P1 = SKIPV ? KS : 9 * KS;            // pass 1: the other channel half, or the skip's centre tap
   static constexpr int PU = 10, PV = 18, P = PU * PV;              // transposed tile: u = 8 rows (+halo) of y, v = 16 (+halo) of x
   static constexpr int PPAD = P + ((1 - (P & 7)) + 8) % 8;
-  static constexpr int SPC = CHUNK_BYTES / (N * 32);               // k-steps per weight chunk
+  static constexpr int SPC = CHUNK_BYTES / (NL * 32);              // k-steps per weight chunk
   static constexpr int NCHUNKS_P0 = KSTEPS_P0 / SPC, NCHUNKS_P1 = KSTEPS_P1 / SPC;
   static constexpr int PLANE_BYTES = (2 * CHP * PPAD * 16 + 127) / 128 * 128;
   static constexpr int STAGE_BYTES = ((P * CP * 2) + 127) / 128 * 128;
@@ -67,9 +72,10 @@ struct Cfg {
   static constexpr int OFF_STAGE = OFF_PLANES + PLANE_BYTES;
   static constexpr int OFF_RING = OFF_STAGE + STAGE_REGION;
   static constexpr int SMEM = OFF_RING + NST * CHUNK_BYTES + 128;
-  static constexpr int TMEM_COLS = N;                              // 128, 256 or 512 (powers of two)
+  static constexpr int TMEM_COLS = NL;                             // 128, 256 or 512 (powers of two)
   static_assert(KSTEPS_P0 % SPC == 0 && KSTEPS_P1 % SPC == 0, "a weight chunk must not straddle two passes");
   static_assert(!(SKIPV && GATE), "the skip operand belongs to conv_1 (no gate)");
+  static_assert(NSPLIT == 1 || (!SKIPV && 2 * FL <= 256), "channel split: wide variant, box of at most 256 8-byte units");
   static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
@@ -107,9 +113,9 @@ __device__ __forceinline__ void transform_tile(uint32_t stage, uint32_t planes, 
   }
 }
 
-template <bool GATE, int VAR>
+template <bool GATE, int VAR, int NSPLIT = 1>
 __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Params p) {
-  using CF = Cfg<GATE, VAR>;
+  using CF = Cfg<GATE, VAR, NSPLIT>;
   constexpr int F = CF::F;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -131,7 +137,9 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
     u0 = tu * 8;
     v0 = tv * 16;
   };
-  const int n_local = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int nh = (int)blockIdx.x % NSPLIT;                  // channel half of this CTA
+  const int cta = (int)blockIdx.x / NSPLIT, ncta = (int)gridDim.x / NSPLIT;
+  const int n_local = (cta < p.ntiles) ? (p.ntiles - 1 - cta) / ncta + 1 : 0;
 
   if (warp == 8) {
     ptx::tmem_alloc(sbase + 128, (uint32_t)CF::TMEM_COLS);
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
       int gchunk = 0;
       for (int it = 0; it < n_local && ok; ++it) {
         int b, u0, v0;
-        tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, u0, v0);
+        tile_coords(cta + it * ncta, b, u0, v0);
         for (int ps = 0; ps < KP && ok; ++ps) {
           const int q = it * KP + ps;                   // running (tile, pass) index: parities of X and ST
           if (ps == 0 && it >= 1) {                     // stage region (aliased by the shortcut tile) free: epilogue done
@@ -188,11 +196,15 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
               ok = ptx::mbar_wait(bar(SB_EMPTY + s), (uint32_t)(((gchunk / NST) - 1) & 1));
               if (!ok) { atomicCAS(p.status, 0, 73); break; }
             }
-            const uint32_t bytes = (uint32_t)(CF::SPC * CF::N * 32);
+            const uint32_t bytes = (uint32_t)(CF::SPC * CF::NL * 32);
             ptx::mbar_arrive_expect_tx(bar(SB_FULL + s), bytes);
-            ptx::bulk_g2s(sbase + CF::OFF_RING + s * CHUNK_BYTES,
-                          reinterpret_cast<const unsigned char*>(p.wpk) + (size_t)(ps * CF::NCHUNKS_P0 + c) * CF::SPC * CF::N * 32, bytes,
-                          bar(SB_FULL + s));
+            if (NSPLIT == 1)
+              ptx::bulk_g2s(sbase + CF::OFF_RING + s * CHUNK_BYTES,
+                            reinterpret_cast<const unsigned char*>(p.wpk) + (size_t)(ps * CF::NCHUNKS_P0 + c) * CF::SPC * CF::N * 32, bytes,
+                            bar(SB_FULL + s));
+            else       // this CTA's rows of the u (and v) block, both K halves, SPC k-steps: [kstep][khalf][u rows | v rows]
+              tma_load_4d(sbase + CF::OFF_RING + s * CHUNK_BYTES, &p.tm_w, bar(SB_FULL + s), 2 * nh * CF::FL, 0, 0,
+                          (ps * CF::NCHUNKS_P0 + c) * CF::SPC);
           }
         }
         if (ok && GATE && p.res_mode == 1) {            // last pass's transform has consumed the stage: fetch the shortcut tile
@@ -216,7 +228,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
     for (int it = 0; it < n_local; ++it) {
       const uint32_t par_it = (uint32_t)(it & 1);
       int b, u0, v0;
-      tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, u0, v0);
+      tile_coords(cta + it * ncta, b, u0, v0);
       for (int ps = 0; ps < KP; ++ps) {
         const int q = it * KP + ps;
         ok = ok && ptx::mbar_wait(bar(SB_X), (uint32_t)(q & 1));
@@ -232,7 +244,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
         if (warp == 0) {
           ptx::tc_fence_after_sync();
           const uint64_t a_tmpl = ptx::smem_desc(sbase + CF::OFF_PLANES, CF::PPAD * 16, CF::PU * 16);
-          const uint64_t b_tmpl = ptx::smem_desc(sbase + CF::OFF_RING, CF::N * 16, 128);
+          const uint64_t b_tmpl = ptx::smem_desc(sbase + CF::OFF_RING, CF::NL * 16, 128);
           const int nchunks = ps == 0 ? CF::NCHUNKS_P0 : CF::NCHUNKS_P1;
           const bool centre_only = CF::SKIPV && ps == 1;
 #pragma unroll 1
@@ -250,7 +262,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
               const int di = tap / 3, dj = tap % 3;
               const int dv = dj, du = di;                           // transposed tile: u along y
               const uint32_t a_off = (uint32_t)((dv * CF::PU + du) * 16 + kk * 2 * CF::PPAD * 16) >> 4;
-              const uint32_t b_off = (uint32_t)(i * CF::N * 32) >> 4;
+              const uint32_t b_off = (uint32_t)(i * CF::NL * 32) >> 4;
               const uint32_t acc = (ps == 0 && ks == 0) ? 0u : 1u;
 #pragma unroll
               for (int m = 0; m < CF::NM; ++m)
@@ -279,12 +291,13 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
         const size_t pix = ((size_t)b * p.H + oy) * p.W + ox;
         const uint32_t res_pix = (uint32_t)(u * 16 + v);          // shortcut tile = TMA box order [8 of u][16 of v]
 #pragma unroll 2
-        for (int g8 = 0; g8 < F / 16; ++g8) {
-          const int c0 = half * (F / 2) + g8 * 8;
+        for (int g8 = 0; g8 < CF::FL / 16; ++g8) {
+          const int cl = half * (CF::FL / 2) + g8 * 8;      // column inside this CTA's accumulator
+          const int c0 = nh * CF::FL + cl;                  // output channel
           float o[8];
           if (GATE) {
             float a[8], g[8];
-            ptx::tmem_ld8x2(lane_base + c0, lane_base + F + c0, a, g);
+            ptx::tmem_ld8x2(lane_base + cl, lane_base + CF::FL + cl, a, g);
             if (p.gate_bwd) {
               bf16x8 gy, du, dv;
               gy.v = lds128(sbase + CF::OFF_STAGE + (res_pix * F + (uint32_t)c0) * 2u);
@@ -336,7 +349,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
               }
             }
           } else {
-            ptx::tmem_ld8(lane_base + c0, o);
+            ptx::tmem_ld8(lane_base + cl, o);
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] += sbias[c0 + i];
           }
@@ -365,9 +378,9 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1w(const __grid_constant__ Pa
   }
 }
 
-template <bool GATE, int VAR>
+template <bool GATE, int VAR, int NSPLIT = 1>
 static int launch(const fn_conv_desc& d, int* status, cudaStream_t stream) {
-  using CF = Cfg<GATE, VAR>;
+  using CF = Cfg<GATE, VAR, NSPLIT>;
   constexpr int C = CF::C, F = CF::F;
   Params p;
   memset(&p, 0, sizeof(p));
@@ -405,14 +418,26 @@ static int launch(const fn_conv_desc& d, int* status, cudaStream_t stream) {
   p.Cout = d.Cout;
   p.Cres = d.Cres; p.RH = d.RH; p.RW = d.RW; p.res_pool = d.res_pool;
   p.gate_bwd = d.epilogue == FN_EPI_GATE_BWD ? 1 : 0;
-  auto kern = k_conv_s1w<GATE, VAR>;
+  if (NSPLIT > 1) {
+    const cuuint64_t dims[4] = {(cuuint64_t)(2 * F), (cuuint64_t)CF::PARTS, 2, (cuuint64_t)(CF::KSTEPS_P0 + CF::KSTEPS_P1)};
+    const cuuint64_t strides[3] = {(cuuint64_t)F * 16, (cuuint64_t)CF::N * 16, (cuuint64_t)CF::N * 32};
+    const cuuint32_t box[4] = {(cuuint32_t)(2 * CF::FL), (cuuint32_t)CF::PARTS, 2, (cuuint32_t)CF::SPC};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (!enc || enc(&p.tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(d.w_tc), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_error("conv_s1w: tensor map (weights) failed");
+      return FN_E_UNSUPPORTED;
+    }
+  }
+  auto kern = k_conv_s1w<GATE, VAR, NSPLIT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(s1w): %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
-  const int grid = p.ntiles < 148 ? p.ntiles : 148;
+  const int grid = (p.ntiles < 148 / NSPLIT ? p.ntiles : 148 / NSPLIT) * NSPLIT;
   kern<<<grid, THREADS, CF::SMEM, stream>>>(p);
   count_launch();
   return check_launch("k_conv_s1w");
@@ -447,7 +472,10 @@ bool conv_s1w_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
   if (d.epilogue == FN_EPI_GATE_BWD && (d.res == nullptr || d.res_pool || d.Cres != C)) return false;
   if (!dry_run) {
     int* st = tc_status_word();
-    rc = !st ? (int)cudaErrorMemoryAllocation : (gate ? launch<true, VAR_WIDE>(d, st, stream) : launch<false, VAR_WIDE>(d, st, stream));
+    const bool split = d.B * ((d.H + 7) / 8) * ((d.W + 15) / 16) <= 74;       // under half a wave of tiles: two CTAs per tile
+    rc = !st ? (int)cudaErrorMemoryAllocation
+             : split ? (gate ? launch<true, VAR_WIDE, 2>(d, st, stream) : launch<false, VAR_WIDE, 2>(d, st, stream))
+                     : (gate ? launch<true, VAR_WIDE>(d, st, stream) : launch<false, VAR_WIDE>(d, st, stream));
   }
   return true;
 }

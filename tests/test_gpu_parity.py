@@ -1045,7 +1045,8 @@ def _pack_pass_major(native, w16, N, gated):
 
 
 @pytest.mark.parametrize("B,H,W,gate,Cres,pool", [(3, 8, 16, True, None, False), (2, 8, 16, False, None, False), (2, 16, 32, True, None, False),
-                                                  (2, 8, 16, True, 128, True), (70, 8, 16, True, None, False), (1, 24, 40, False, None, False)])
+                                                  (2, 8, 16, True, 128, True), (70, 8, 16, True, None, False), (1, 24, 40, False, None, False),
+                                                  (80, 8, 16, True, None, False), (76, 8, 16, False, None, False)])
 def test_two_pass_c256_kernel_vs_cuda_core_and_oracle(native, B, H, W, gate, Cres, pool):
     """conv_s1w.cu (C = 256: two K passes of 128 channels, N = 512 as two MMAs) against the fp64 oracle and the CUDA-core
     kernel -- the 8x16 level of the filter_size = 16 variant."""
