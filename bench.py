@@ -241,7 +241,9 @@ def run_train(args, rank, world, dist, native, arch, flow_net):
                                    "keep_prob %.2f; tcgen05 fwd + dgrad + wgrad; %s" % (
                                        args.keep_prob, "fwd+bwd replayed from a CUDA graph" if compiled is not None else "eager launches"),
                        "batch_per_gpu": B, "parallelism": f"dp{world}, one flat fp32 gradient all-reduce"},
-            "gpu_launches": native.launch_count() - n0, "loss": float(loss.item()),
+            # kernels of this library per step: those replayed from the graph + the eager ones (Adam) the counter saw
+            "gpu_launches": native.launch_count() - n0 + (compiled.launches_per_replay * args.steps if compiled is not None else 0),
+            "loss": float(loss.item()),
             "roofline": {"bound": "tensor", "achieved": v * 8.519e9 / 1e12, "peak": load_peaks()["tc_sustained"],
                          "unit": "TFLOP/s", "frac": v * 8.519e9 / 1e12 / load_peaks()["tc_sustained"], "traffic": None},
         }))
