@@ -25,7 +25,7 @@ namespace s2t {
 constexpr int THREADS = 448;
 constexpr int WARP_PRODUCER = 12, WARP_ISSUER = 13;
 constexpr int HDR = 256 + 1024;
-enum { MODE_S2 = 1, MODE_TCONV = 2, MODE_S1N = 3 };
+enum { MODE_S2 = 1, MODE_TCONV = 2, MODE_S1N = 3, MODE_S2N = 4 };
 
 struct Params {
   CUtensorMap tm_x;
@@ -51,13 +51,14 @@ template <int MODE, int CLOG, int J, int NBUF, int R = 1>
 struct Cfg {
   static constexpr int CH = 1 << CLOG;                       // 8-channel chunks of the raw input
   static constexpr int C = 8 * CH;
-  static constexpr bool S2 = MODE == MODE_S2;
+  static constexpr bool S2 = MODE == MODE_S2 || MODE == MODE_S2N;
+  static constexpr bool S2RAW = MODE == MODE_S2N;            // stride 2, no prologue (data gradient of a transposed conv)
   static constexpr bool S1N = MODE == MODE_S1N;              // stride 1, no prologue, Cout = R*C (data gradients)
-  static constexpr int KPLANES = S2 ? 2 * CH : CH;          // 8-channel planes of one (sub-)operand
+  static constexpr int KPLANES = (S2 && !S2RAW) ? 2 * CH : CH;   // 8-channel planes of one (sub-)operand
   // k-steps per tap; a lone plane (C = 8) is read for both K halves (LBO = 0) against zero-padded weights
-  static constexpr bool HALF_K = !S2 && CH == 1;
-  static constexpr int KS = S2 ? CH : (CH >= 2 ? CH / 2 : 1);
-  static constexpr int NREAL = S2 ? 2 * C : (S1N ? R * C : C / 2);   // Cout
+  static constexpr bool HALF_K = (!S2 || S2RAW) && CH == 1;
+  static constexpr int KS = (S2 && !S2RAW) ? CH : (CH >= 2 ? CH / 2 : 1);
+  static constexpr int NREAL = S2 ? 2 * C : (S1N ? R * C : R * C / 2);   // Cout (TCONV, R = 2: the data gradient of a stride-2 conv)
   static constexpr int N = NREAL < 16 ? 16 : NREAL;
   static constexpr int NPH = MODE == MODE_TCONV ? 4 : 1;     // accumulators per sub-tile
   static constexpr int KSTEPS = 9 * KS;
@@ -101,17 +102,21 @@ __device__ __forceinline__ void transform_tile(uint32_t stage, uint32_t planes, 
       const int r = sp / CF::SW_, c = sp - r * CF::SW_;
       const int sub = (r & 1) * 2 + (c & 1);
       const int pp = (r >> 1) * CF::PU + (c >> 1);
-      bf16x8 o0, o1;
+      if (CF::S2RAW) {
+        sts128(planes + (uint32_t)(sub * CF::SUB_BYTES) + (uint32_t)(ch * CF::PPAD + pp) * 16u, in.v);
+      } else {
+        bf16x8 o0, o1;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float v = __bfloat162float(in.h[j]);
-        const float t = __expf(-fabsf(v)) - 1.f;
-        o0.h[j] = __float2bfloat16(v > 0.f ? v : t);
-        o1.h[j] = __float2bfloat16(v > 0.f ? t : -v);
+        for (int j = 0; j < 8; ++j) {
+          const float v = __bfloat162float(in.h[j]);
+          const float t = __expf(-fabsf(v)) - 1.f;
+          o0.h[j] = __float2bfloat16(v > 0.f ? v : t);
+          o1.h[j] = __float2bfloat16(v > 0.f ? t : -v);
+        }
+        const uint32_t d0 = planes + (uint32_t)(sub * CF::SUB_BYTES) + (uint32_t)(ch * CF::PPAD + pp) * 16u;
+        sts128(d0, o0.v);
+        sts128(d0 + (uint32_t)(CF::CH * CF::PPAD * 16), o1.v);
       }
-      const uint32_t d0 = planes + (uint32_t)(sub * CF::SUB_BYTES) + (uint32_t)(ch * CF::PPAD + pp) * 16u;
-      sts128(d0, o0.v);
-      sts128(d0 + (uint32_t)(CF::CH * CF::PPAD * 16), o1.v);
     } else {
       sts128(planes + (uint32_t)(ch * CF::PPAD + sp) * 16u, in.v);
     }
@@ -446,6 +451,35 @@ bool conv_s2p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
   return false;
 }
 
+// stride-2 3x3 conv without prologue, Cout = 2 Cin: the data gradient of a transposed conv (conv2d_transpose is defined as
+// the gradient of this conv, flow_architecture.py:84-98), raw dY in, K = Cin
+bool conv_s2n_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc) {
+  using namespace s2t;
+  rc = 0;
+  if (d.ksize != 3 || d.stride != 2 || d.prologue != FN_PRO_NONE || d.epilogue != FN_EPI_BIAS || d.skip || d.w_tc == nullptr)
+    return false;
+  if ((d.H & 1) || (d.W & 1) || d.H < 32) return false;
+  if (d.Cout != 2 * d.Cin) return false;
+  if (get_encode() == nullptr) return false;
+  const int clog = d.Cin == 8 ? 0 : d.Cin == 16 ? 1 : d.Cin == 32 ? 2 : -1;
+  if (clog < 0) return false;
+  const int OW = d.W / 2;
+#define S2N_CASE(CL, JJ, NB, CAP)                                                                             \
+  if (clog == CL && ((OW % (8 * JJ)) == 0 || JJ == 1) && Cfg<MODE_S2N, CL, JJ, NB>::SMEM <= CAP * 1024) {      \
+    if (!dry_run) {                                                                                           \
+      int* st = tc_status_word();                                                                             \
+      rc = st ? launch<MODE_S2N, CL, JJ, NB>(d.x, d.w_tc, d.bias, d.y, d.B, d.H, d.W, d.Cout, st, stream)     \
+              : (int)cudaErrorMemoryAllocation;                                                               \
+    }                                                                                                         \
+    return true;                                                                                              \
+  }
+  S2N_CASE(0, 2, 2, 112) S2N_CASE(0, 1, 2, 112)
+  S2N_CASE(1, 2, 2, 112) S2N_CASE(1, 1, 2, 112)
+  S2N_CASE(2, 2, 2, 150) S2N_CASE(2, 1, 2, 150) S2N_CASE(2, 1, 1, 200)
+#undef S2N_CASE
+  return false;
+}
+
 // stride-1 3x3 conv without prologue, Cout = C or 2C: the data-gradient convs of the backward pass (flipped weights)
 bool conv_s1n_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc) {
   using namespace s2t;
@@ -494,22 +528,27 @@ bool conv_s1n_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
 bool tconv_s2p_try(const fn_tconv_desc& d, cudaStream_t stream, bool dry_run, int& rc) {
   using namespace s2t;
   rc = 0;
-  if (d.w_tc == nullptr || d.Cout * 2 != d.Cin || d.H < 16) return false;
+  const int r = d.Cout * 2 == d.Cin ? 1 : d.Cout == d.Cin ? 2 : 0;
+  if (d.w_tc == nullptr || r == 0 || d.H < 16) return false;
   if (get_encode() == nullptr) return false;
   const int clog = d.Cin == 16 ? 1 : d.Cin == 32 ? 2 : d.Cin == 64 ? 3 : -1;
   if (clog < 0) return false;
-#define TC_CASE(CL, JJ, NB, CAP)                                                                              \
-  if (clog == CL && ((d.W % (8 * JJ)) == 0 || JJ == 1) && Cfg<MODE_TCONV, CL, JJ, NB>::SMEM <= CAP * 1024) {   \
+#define TC_CASE(CL, RR, JJ, NB, CAP)                                                                          \
+  if (clog == CL && r == RR && ((d.W % (8 * JJ)) == 0 || JJ == 1) && Cfg<MODE_TCONV, CL, JJ, NB, RR>::SMEM <= CAP * 1024) { \
     if (!dry_run) {                                                                                           \
       int* st = tc_status_word();                                                                             \
-      rc = st ? launch<MODE_TCONV, CL, JJ, NB>(d.x, d.w_tc, d.bias, d.y, d.B, d.H, d.W, d.Cout, st, stream)   \
+      rc = st ? launch<MODE_TCONV, CL, JJ, NB, RR>(d.x, d.w_tc, d.bias, d.y, d.B, d.H, d.W, d.Cout, st, stream) \
               : (int)cudaErrorMemoryAllocation;                                                               \
     }                                                                                                         \
     return true;                                                                                              \
   }
-  TC_CASE(1, 4, 2, 112) TC_CASE(1, 2, 2, 112) TC_CASE(1, 1, 2, 112)
-  TC_CASE(2, 2, 2, 112) TC_CASE(2, 1, 2, 112)
-  TC_CASE(3, 2, 2, 112) TC_CASE(3, 1, 2, 150)
+  TC_CASE(1, 1, 4, 2, 112) TC_CASE(1, 1, 2, 2, 112) TC_CASE(1, 1, 1, 2, 112)
+  TC_CASE(2, 1, 2, 2, 112) TC_CASE(2, 1, 1, 2, 112)
+  TC_CASE(3, 1, 2, 2, 112) TC_CASE(3, 1, 1, 2, 150)
+  // Cout = Cin: data gradients of the stride-2 convs (dY of 2C channels -> d concat_elu(x) of 2C channels)
+  TC_CASE(1, 2, 2, 2, 112) TC_CASE(1, 2, 1, 2, 112)
+  TC_CASE(2, 2, 2, 2, 150) TC_CASE(2, 2, 1, 2, 150)
+  TC_CASE(3, 2, 1, 2, 200)
 #undef TC_CASE
   return false;
 }

@@ -692,6 +692,7 @@ bool conv_s1p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
 bool conv_s1d_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1d.cu
 bool conv_s2p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s2t.cu
 bool conv_s1n_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s2t.cu
+bool conv_s2n_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s2t.cu
 bool tconv_s2p_try(const fn_tconv_desc& d, cudaStream_t stream, bool dry_run, int& rc); // conv_s2t.cu
 
 static int launch_tc(TcParams& p, size_t smem_bytes, cudaStream_t stream) {
@@ -717,6 +718,7 @@ int conv_fwd_tc(const fn_conv_desc& d, cudaStream_t stream) {
   if (g_tc_use_s1p && conv_s1w_try(d, stream, false, rc_sp)) return rc_sp;
   if (g_tc_use_s1p && conv_s2p_try(d, stream, false, rc_sp)) return rc_sp;
   if (g_tc_use_s1p && conv_s1n_try(d, stream, false, rc_sp)) return rc_sp;
+  if (g_tc_use_s1p && conv_s2n_try(d, stream, false, rc_sp)) return rc_sp;
   TcGeom g;
   TcParams p;
   size_t smem_bytes = 0;

@@ -160,6 +160,11 @@ TC_CASES = [
     ("raw_k8", 2, 32, 64, 8, 16, 1, 0, 0, False, None, False),
     ("raw_k8_n8", 2, 20, 28, 8, 8, 1, 0, 0, False, None, False),
     ("raw_k8_s2", 2, 32, 64, 8, 16, 2, 0, 0, False, None, False),
+    # data gradients of the transposed convs: stride 2 on raw dY (conv_s2t.cu MODE_S2N)
+    ("raw_s2_c16", 2, 32, 64, 16, 32, 2, 0, 0, False, None, False),
+    ("raw_s2_c32", 3, 32, 32, 32, 64, 2, 0, 0, False, None, False),
+    ("raw_s2_c8_ragged_even", 2, 36, 44, 8, 16, 2, 0, 0, False, None, False),
+    ("raw_s2_c16_many_tiles", 40, 64, 64, 16, 32, 2, 0, 0, False, None, False),
 ]
 
 
@@ -242,7 +247,8 @@ def test_tcgen05_refuses_shapes_it_has_no_kernel_for(native):
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 8, 16, 16, 8), (1, 4, 8, 128, 64), (2, 5, 7, 8, 8), (1, 16, 32, 32, 16),
-                                            (2, 32, 64, 16, 8), (1, 20, 12, 64, 32)])
+                                            (2, 32, 64, 16, 8), (1, 20, 12, 64, 32),
+                                            (2, 32, 64, 16, 16), (1, 16, 32, 32, 32), (1, 20, 12, 64, 64)])
 def test_transposed_conv_vs_oracle(native, impl, B, H, W, Cin, Cout):
     if impl == "tc" and Cin % 16 != 0:
         pytest.skip("K per tap not a multiple of 16: CUDA-core layer")
@@ -263,7 +269,10 @@ def test_transposed_conv_vs_oracle(native, impl, B, H, W, Cin, Cout):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(3, 64, 128, 16, 8), (2, 32, 64, 32, 16), (2, 16, 32, 64, 32), (1, 20, 12, 64, 32),
-                                            (40, 32, 32, 16, 8), (70, 16, 16, 32, 16), (2, 19, 27, 16, 8)])
+                                            (40, 32, 32, 16, 8), (70, 16, 16, 32, 16), (2, 19, 27, 16, 8),
+                                            # Cout = Cin: data gradients of the stride-2 convs
+                                            (3, 64, 128, 16, 16), (2, 32, 64, 32, 32), (2, 16, 32, 64, 64), (40, 32, 32, 16, 16),
+                                            (70, 16, 16, 32, 32), (2, 19, 27, 16, 16), (150, 16, 16, 64, 64)])
 def test_transposed_conv_persistent_vs_generic(native, B, H, W, Cin, Cout):
     """conv_s2t.cu's sub-pixel kernel against the generic tcgen05 kernel (same MMA order: bit-identical)
     and the oracle."""
@@ -287,6 +296,31 @@ def test_transposed_conv_persistent_vs_generic(native, B, H, W, Cin, Cout):
         native.lib.fn_debug_set_use_s1p(1)
     if B * H * W <= 8192:
         assert rel_l2(ys[0], fo.conv2d_transpose_same(x, w, 2) + b) < LAYER_TOL
+    assert torch.equal(ys[0], ys[1])
+
+
+@pytest.mark.parametrize("B,H,W,C", [(3, 128, 256, 8), (2, 64, 128, 16), (2, 32, 64, 32), (2, 36, 44, 8), (40, 64, 64, 16),
+                                     (150, 32, 32, 32)])
+def test_raw_stride2_persistent_vs_generic(native, B, H, W, C):
+    """conv_s2t.cu MODE_S2N (data gradient of a transposed conv: stride 2, no prologue, Cout = 2 Cin) against the generic
+    tcgen05 kernel: same MMA order, bit-identical."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, H, W, C, generator=g).to("cuda", torch.bfloat16)
+    w16 = ((torch.rand(9, C, 2 * C, generator=g) * 2 - 1) * 0.2).to("cuda", torch.bfloat16)
+    b = torch.rand(2 * C, generator=g).to("cuda")
+    w_tc = native.pack_conv_weights_tc(w16, None, 3, C, 0, 2 * C, False)
+    ys = []
+    try:
+        for use in (1, 0):
+            native.lib.fn_debug_set_use_s1p(use)
+            y = torch.full((B, H // 2, W // 2, 2 * C), float("nan"), device="cuda", dtype=torch.bfloat16)
+            native.conv_fwd(x, w16, b, y, B=B, H=H, W=W, Cin=C, Cout=2 * C, ksize=3, stride=2, prologue=native.PRO_NONE,
+                            epilogue=native.EPI_BIAS, impl=native.IMPL_TCGEN05, w_tc=w_tc)
+            torch.cuda.synchronize()
+            assert native.tc_status() == 0
+            ys.append(y)
+    finally:
+        native.lib.fn_debug_set_use_s1p(1)
     assert torch.equal(ys[0], ys[1])
 
 

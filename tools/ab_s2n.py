@@ -1,0 +1,36 @@
+"""A/B: data gradients of the transposed convs (stride-2 conv on raw dY) at batch 256 -- persistent MODE_S2N kernel
+against the generic tcgen05 kernel (CUDA events, 20 launches back to back)."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "steady-state-flow-with-neural-nets_b200"))
+import flownet_native as native
+g = torch.Generator().manual_seed(1)
+B = 256
+for C, H, W in ((8, 128, 256), (16, 64, 128), (32, 32, 64), (64, 16, 32)):
+    N = 2 * C
+    x = torch.randn(B, H, W, C, generator=g).to("cuda", torch.bfloat16)
+    w16 = (torch.rand(9, C, N, generator=g) * 0.03).to("cuda", torch.bfloat16)
+    bias = torch.zeros(N, device="cuda")
+    w_tc = native.pack_conv_weights_tc(w16, None, 3, C, 0, N, False)
+    y = torch.empty((B, H // 2, W // 2, N), device="cuda", dtype=torch.bfloat16)
+    out, ys = [], []
+    for special in (0, 1):
+        native.lib.fn_debug_set_use_s1p(special)
+        def run():
+            native.conv_fwd(x, w16, bias, y, B=B, H=H, W=W, Cin=C, Cout=N, ksize=3, stride=2, prologue=0,
+                            epilogue=0, impl=native.IMPL_TCGEN05, w_tc=w_tc)
+        for _ in range(3):
+            run()
+        torch.cuda._sleep(4_000_000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        out.append(e0.elapsed_time(e1) / 20 * 1000)
+        ys.append(y.float().clone())
+    native.lib.fn_debug_set_use_s1p(1)
+    d = (ys[0] - ys[1]).norm() / ys[0].norm()
+    gb = (x.numel() + y.numel()) * 2 / 1e9
+    print("C=%d %dx%d  generic %.1f us  persistent %.1f us (%.0f GB/s)  rel diff %.1e" % (C, H, W, out[0], out[1], gb / (out[1] * 1e-6), d.item()), flush=True)
