@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FN_ABI_VERSION 3
+#define FN_ABI_VERSION 4
 
 /* error codes (negative) */
 #define FN_E_INVAL      (-1)   /* null pointer, bad enum, non-positive dim */
@@ -123,6 +123,14 @@ typedef struct fn_tconv_desc {
   const void*  w_tc;
   const float* bias;
   void*        y;
+  /* FN_EPI_BIAS, or FN_EPI_PRO_BWD (Cout == Cin only, tensor cores only): this transposed conv is the data gradient of a
+   * stride-2 conv whose input went through prologue `adj_prologue` (concat kinds); y: bf16 [B,2h,2w,Cout/2] (+)= the
+   * prologue's adjoint at res = the differentiated tensor (same shape as y), in the epilogue -- fn_prologue_bwd fused */
+  int32_t epilogue;
+  int32_t adj_prologue;
+  int32_t adj_accumulate;
+  int32_t reserved;
+  const void*  res;
 } fn_tconv_desc;
 
 int         fn_abi_version(void);
@@ -146,6 +154,8 @@ int fn_pack_conv_weights_tc_f32(const float* w, void* dst, int32_t ksize, int32_
                                 int32_t transpose, void* stream);
 /* tf.nn.conv2d_transpose + bias_add                      flow_architecture.py:70-87 */
 int fn_tconv_fwd(const fn_tconv_desc* d, void* stream);
+/* 1 if fn_tconv_fwd(d) would run on the tensor cores (for FN_EPI_PRO_BWD: if the fused kernel exists), else 0 */
+int fn_tconv_fwd_has_tcgen05(const fn_tconv_desc* d);
 /* size in bytes of / packer for the tensor-core weight image of a conv (host-side helper
  * that runs a small device kernel): src = bf16 [T, Keff, Cout] (+ optional [Kskip, Cout]) */
 int64_t fn_conv_weights_tc_bytes(int32_t ksize, int32_t Keff, int32_t Kskip, int32_t Cout, int32_t gated);

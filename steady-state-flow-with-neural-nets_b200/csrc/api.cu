@@ -138,7 +138,7 @@ int fn_conv_fwd_has_tcgen05(const fn_conv_desc* d) {
   return conv_tc_supported(*d, &why) ? 1 : 0;
 }
 
-int fn_tconv_fwd(const fn_tconv_desc* d, void* stream) {
+static int validate_tconv(const fn_tconv_desc* d) {
   FN_REQUIRE(d != nullptr, FN_E_INVAL, "fn_tconv_fwd: null descriptor");
   FN_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, FN_E_INVAL,
              "fn_tconv_fwd: non-positive dimension");
@@ -147,15 +147,35 @@ int fn_tconv_fwd(const fn_tconv_desc* d, void* stream) {
              d->Cin, d->Cout);
   FN_REQUIRE(aligned16(d->x) && aligned16(d->y) && aligned16(d->w), FN_E_ALIGN, "fn_tconv_fwd: x/y/w must be 16-byte aligned");
   FN_REQUIRE(d->impl >= FN_IMPL_AUTO && d->impl <= FN_IMPL_TCGEN05, FN_E_INVAL, "fn_tconv_fwd: bad impl %d", d->impl);
+  FN_REQUIRE(d->epilogue == FN_EPI_BIAS || d->epilogue == FN_EPI_PRO_BWD, FN_E_INVAL, "fn_tconv_fwd: bad epilogue %d", d->epilogue);
+  if (d->epilogue == FN_EPI_PRO_BWD)
+    FN_REQUIRE(d->res && aligned16(d->res) && d->Cout == d->Cin && d->impl != FN_IMPL_SIMT &&
+                   (d->adj_prologue == FN_PRO_CONCAT_ELU || d->adj_prologue == FN_PRO_CONCAT_RELU),
+               FN_E_UNSUPPORTED, "fn_tconv_fwd: prologue-adjoint epilogue needs res, Cout == Cin, a concat prologue, tcgen05");
+  return 0;
+}
+
+int fn_tconv_fwd(const fn_tconv_desc* d, void* stream) {
+  int rc = validate_tconv(d);
+  if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const char* why = "";
   if (d->impl != FN_IMPL_SIMT && tconv_tc_supported(*d, &why)) {
     note_tcgen05(true);
     return tconv_fwd_tc(*d, s);
   }
-  FN_REQUIRE(d->impl != FN_IMPL_TCGEN05, FN_E_UNSUPPORTED, "fn_tconv_fwd: no tcgen05 kernel for this shape: %s", why);
+  FN_REQUIRE(d->impl != FN_IMPL_TCGEN05 && d->epilogue != FN_EPI_PRO_BWD, FN_E_UNSUPPORTED,
+             "fn_tconv_fwd: no tcgen05 kernel for this shape: %s", why);
   note_tcgen05(false);
   return tconv_fwd_simt(*d, s);
+}
+
+int fn_tconv_fwd_has_tcgen05(const fn_tconv_desc* d) {
+  if (d == nullptr || d->impl == FN_IMPL_SIMT) return 0;
+  const int quiet = validate_tconv(d);
+  if (quiet != 0) return 0;
+  const char* why = "";
+  return tconv_tc_supported(*d, &why) ? 1 : 0;
 }
 
 int64_t fn_conv_weights_tc_bytes(int32_t ksize, int32_t Keff, int32_t Kskip, int32_t Cout, int32_t gated) {

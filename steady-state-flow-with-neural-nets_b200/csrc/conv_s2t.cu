@@ -258,16 +258,20 @@ __global__ void __launch_bounds__(THREADS) k_conv_s2t(const __grid_constant__ Pa
       tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, y0, x0);
       const int ry = y0 + v;
       // adjoint epilogue: fetch this thread's z (and old y) vectors while the MMAs still run
-      constexpr int NSLOT = CF::S1N ? ((ITEMS + 1) / 2) * (CF::NREAL / 16 > 0 ? CF::NREAL / 16 : 1) : 1;
+      constexpr bool ADJ = CF::S1N || (MODE == MODE_TCONV && R == 2);     // kernels with the prologue-adjoint epilogue
+      constexpr int NSLOT = ADJ ? ((ITEMS + 1) / 2) * (CF::NREAL / 16 > 0 ? CF::NREAL / 16 : 1) : 1;
       uint4 pre_z[NSLOT], pre_y[NSLOT];
-      if (CF::S1N && p.adj) {
+      if (ADJ && p.adj) {
         constexpr int CY = CF::NREAL / 2;
 #pragma unroll
         for (int w0 = 0; w0 < ITEMS; w0 += 2) {
           const int item = w0 + half;
           if (item >= ITEMS) break;
-          const int rx = x0 + 8 * item + u;
-          const size_t pix = ((size_t)b * p.OH + ry) * p.OW + rx;
+          const int pj = item / CF::NPH, pph = item % CF::NPH;
+          const int rx = x0 + 8 * pj + u;
+          const int poy = CF::NPH == 1 ? ry : 2 * ry + (pph >> 1);
+          const int pox = CF::NPH == 1 ? rx : 2 * rx + (pph & 1);
+          const size_t pix = ((size_t)b * p.OH + poy) * p.OW + pox;
 #pragma unroll
           for (int cc = 0; cc < CY / 8; ++cc) {
             const int slot = (w0 / 2) * (CY / 8) + cc;
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s2t(const __grid_constant__ Pa
         const int ox = CF::NPH == 1 ? rx : 2 * rx + (ph & 1);
         const size_t pix = ((size_t)b * p.OH + oy) * p.OW + ox;
         const uint32_t col0 = lane_base + (uint32_t)(s * CF::ACC_COLS + (j * CF::NPH + ph) * CF::N);
-        if (CF::S1N && p.adj) {
+        if (ADJ && p.adj) {
           // y[pix][c] (+)= dA0[c] f'(z[c]) - dA1[c] f'(-z[c]) with [dA0 | dA1] = the two accumulator halves and the
           // forward's dropout mask on dA (flow_architecture.py:14-29, 143-145); z / old y were fetched before the wait
           const int kind = p.adj - 1;
@@ -530,6 +534,13 @@ bool tconv_s2p_try(const fn_tconv_desc& d, cudaStream_t stream, bool dry_run, in
   rc = 0;
   const int r = d.Cout * 2 == d.Cin ? 1 : d.Cout == d.Cin ? 2 : 0;
   if (d.w_tc == nullptr || r == 0 || d.H < 16) return false;
+  AdjArgs adj;
+  if (d.epilogue == FN_EPI_PRO_BWD) {
+    if (r != 2 || d.res == nullptr || (d.adj_prologue != FN_PRO_CONCAT_ELU && d.adj_prologue != FN_PRO_CONCAT_RELU)) return false;
+    adj.adj = 1 + d.adj_prologue;
+    adj.accumulate = d.adj_accumulate;
+    adj.res = d.res;
+  }
   if (get_encode() == nullptr) return false;
   const int clog = d.Cin == 16 ? 1 : d.Cin == 32 ? 2 : d.Cin == 64 ? 3 : -1;
   if (clog < 0) return false;
@@ -537,7 +548,7 @@ bool tconv_s2p_try(const fn_tconv_desc& d, cudaStream_t stream, bool dry_run, in
   if (clog == CL && r == RR && ((d.W % (8 * JJ)) == 0 || JJ == 1) && Cfg<MODE_TCONV, CL, JJ, NB, RR>::SMEM <= CAP * 1024) { \
     if (!dry_run) {                                                                                           \
       int* st = tc_status_word();                                                                             \
-      rc = st ? launch<MODE_TCONV, CL, JJ, NB, RR>(d.x, d.w_tc, d.bias, d.y, d.B, d.H, d.W, d.Cout, st, stream) \
+      rc = st ? launch<MODE_TCONV, CL, JJ, NB, RR>(d.x, d.w_tc, d.bias, d.y, d.B, d.H, d.W, d.Cout, st, stream, adj) \
               : (int)cudaErrorMemoryAllocation;                                                               \
     }                                                                                                         \
     return true;                                                                                              \

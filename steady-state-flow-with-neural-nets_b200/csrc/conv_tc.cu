@@ -750,6 +750,12 @@ bool tconv_tc_supported(const fn_tconv_desc& d, const char** why) {
     if (why) *why = "w_tc is null";
     return false;
   }
+  if (d.epilogue == FN_EPI_PRO_BWD) {
+    int rc = 0;
+    if (g_tc_use_s1p && tconv_s2p_try(d, nullptr, true, rc)) return true;
+    if (why) *why = "the prologue-adjoint epilogue exists in the persistent sub-pixel kernel only";
+    return false;
+  }
   TcGeom g;
   TcParams p;
   size_t sm;

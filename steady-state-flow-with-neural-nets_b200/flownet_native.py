@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FLOWNET_LIB", os.path.join(_HERE, "libflownet.so"))   # override: A/B builds
 
-FN_ABI_VERSION = 3
+FN_ABI_VERSION = 4
 # enum fn_prologue
 PRO_NONE, PRO_CONCAT_ELU, PRO_ELU, PRO_CONCAT_RELU, PRO_RELU = 0, 1, 2, 3, 4
 # enum fn_epilogue
@@ -53,6 +53,8 @@ class TConvDesc(C.Structure):
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
         ("impl", C.c_int32),
         ("x", C.c_void_p), ("w", C.c_void_p), ("w_tc", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p),
+        ("epilogue", C.c_int32), ("adj_prologue", C.c_int32), ("adj_accumulate", C.c_int32), ("reserved", C.c_int32),
+        ("res", C.c_void_p),
     ]
 
 
@@ -69,6 +71,7 @@ SYMBOLS = [
     ("fn_conv_fwd_has_tcgen05", C.c_int, [C.POINTER(ConvDesc)]),
     ("fn_pack_conv_weights_tc_f32", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     ("fn_tconv_fwd", C.c_int, [C.POINTER(TConvDesc), _P]),
+    ("fn_tconv_fwd_has_tcgen05", C.c_int, [C.POINTER(TConvDesc)]),
     ("fn_conv_weights_tc_bytes", C.c_int64, [C.c_int32] * 5),
     ("fn_pack_conv_weights_tc", C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     ("fn_nonlinearity", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
@@ -198,12 +201,18 @@ def conv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, ksize=3, stride=1, prologue=P
     _check(lib.fn_conv_fwd(C.byref(d), stream_ptr()), "fn_conv_fwd")
 
 
-def tconv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, impl=IMPL_AUTO, w_tc=None):
-    _require_cuda(x, w, bias, y, w_tc)
+def tconv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, impl=IMPL_AUTO, w_tc=None, epilogue=EPI_BIAS, res=None,
+              adj_prologue=PRO_NONE, adj_accumulate=False, query=False):
+    """query=True: return whether a tensor-core kernel takes this call (for EPI_PRO_BWD: the fused one), run nothing."""
+    _require_cuda(x, w, bias, y, w_tc, res)
     d = TConvDesc()
     d.B, d.H, d.W, d.Cin, d.Cout, d.impl = B, H, W, Cin, Cout, impl
     d.x, d.w, d.bias, d.y = x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr()
     d.w_tc = w_tc.data_ptr() if w_tc is not None else None
+    d.epilogue, d.adj_prologue, d.adj_accumulate = epilogue, adj_prologue, int(bool(adj_accumulate))
+    d.res = res.data_ptr() if res is not None else None
+    if query:
+        return bool(lib.fn_tconv_fwd_has_tcgen05(C.byref(d)))
     _check(lib.fn_tconv_fwd(C.byref(d), stream_ptr()), "fn_tconv_fwd")
 
 

@@ -129,6 +129,22 @@ def _conv_dgrad_adjoint(g, wts, cout, z, pro, device, out=None, accumulate=False
     return native.prologue_bwd(dA, z, pro, out=out, accumulate=accumulate, keep_prob=keep_prob, seed=seed)
 
 
+def _tconv_dgrad_adjoint(g, wts, cout, z, pro, device, out, accumulate):
+    """d(z) (+)= adjoint_of_prologue(conv2d_transpose(g, W), z): the data gradient of a stride-2 conv with the prologue's
+    adjoint in the epilogue of the sub-pixel kernel (FN_EPI_PRO_BWD) when it takes the shape, else two launches."""
+    B, H, W, cin = g.shape
+    w_tc = wts.tc() if (cin % 16 == 0 and arch.IMPL != native.IMPL_SIMT) else None
+    if w_tc is not None:
+        kw = dict(B=B, H=H, W=W, Cin=cin, Cout=cout, impl=arch.IMPL, w_tc=w_tc, epilogue=native.EPI_PRO_BWD, res=z,
+                  adj_prologue=pro, adj_accumulate=accumulate)
+        bias = _zeros_bias(cout, device)
+        if cout == cin and pro in (native.PRO_CONCAT_ELU, native.PRO_CONCAT_RELU) and native.tconv_fwd(g, w_tc, bias, out, query=True, **kw):
+            native.tconv_fwd(g, w_tc, bias, out, **kw)
+            return out
+    dA = _tconv_plain(g, wts, cout, device)
+    return native.prologue_bwd(dA, z, pro, out=out, accumulate=accumulate)
+
+
 def _tconv_plain(x, wts, cout, device):
     B, H, W, cin = x.shape
     y = torch.empty((B, 2 * H, 2 * W, cout), dtype=torch.bfloat16, device=device)
@@ -266,8 +282,8 @@ def backward(tape, sflow_p, sflow, flat: FlatParams = None, want_input_grad=Fals
                 else:
                     if x.shape[1] % 2 or x.shape[2] % 2:
                         raise ValueError("training a stride-2 block on odd spatial sizes is not built")
-                    dA1 = _tconv_plain(dx_1, _BwdWeights(w1, 3, F_, mult * cin, transpose=True), mult * cin, dev)  # [tap, F, Keff]
-                    native.prologue_bwd(dA1, x, pro, out=buf, accumulate=acc)
+                    _tconv_dgrad_adjoint(dx_1, _BwdWeights(w1, 3, F_, mult * cin, transpose=True), mult * cin, x, pro, dev,
+                                         buf, acc)                                 # weights as [tap, F, Keff]
                 native.shortcut_bwd(g, tuple(x.shape), pooled, out=buf, accumulate=True)
             elif want_input_grad:
                 # the network input (1 channel, no prologue): conv adjoint with the output padded to 8 channels, plus

@@ -914,6 +914,35 @@ def test_prologue_adjoint_epilogue_vs_two_step(native, B, H, W, C, N, kind, acc,
     assert rel_l2(fused, two) < 2e-3
 
 
+@pytest.mark.parametrize("B,H,W,C,kind,acc", [(3, 64, 128, 16, 1, True), (2, 32, 64, 32, 1, False), (2, 16, 32, 64, 1, True),
+                                              (2, 19, 27, 16, 3, True), (70, 16, 16, 32, 1, True), (150, 16, 16, 64, 3, False)])
+def test_transposed_conv_prologue_adjoint_vs_two_step(native, B, H, W, C, kind, acc):
+    """fn_tconv_fwd with FN_EPI_PRO_BWD (data gradient of a stride-2 conv + the prologue's adjoint in one launch) against
+    the transposed conv followed by fn_prologue_bwd."""
+    g = torch.Generator().manual_seed(43)
+    gx = torch.randn(B, H, W, C, generator=g).to("cuda", torch.bfloat16)
+    w16 = ((torch.rand(9, C, C, generator=g) * 2 - 1) * 0.2).to("cuda", torch.bfloat16)
+    z = torch.randn(B, 2 * H, 2 * W, C // 2, generator=g).to("cuda", torch.bfloat16)
+    base = torch.randn(B, 2 * H, 2 * W, C // 2, generator=g).to("cuda", torch.bfloat16)
+    bias = torch.zeros(C, device="cuda")
+    w_tc = native.pack_conv_weights_tc(w16, None, 3, C, 0, C, False)
+    kw = dict(B=B, H=H, W=W, Cin=C, Cout=C, w_tc=w_tc, impl=native.IMPL_TCGEN05)
+    akw = dict(epilogue=native.EPI_PRO_BWD, res=z, adj_prologue=kind, adj_accumulate=acc)
+    fused = base.clone()
+    assert native.tconv_fwd(gx, w16, bias, fused, query=True, **kw, **akw)
+    native.tconv_fwd(gx, w16, bias, fused, **kw, **akw)
+    dA = torch.empty((B, 2 * H, 2 * W, C), device="cuda", dtype=torch.bfloat16)
+    native.tconv_fwd(gx, w16, bias, dA, **kw)
+    two = native.prologue_bwd(dA, z, kind, out=base.clone(), accumulate=acc)
+    torch.cuda.synchronize()
+    assert native.tc_status() == 0
+    assert rel_l2(fused, two) < 2e-3
+    # no kernel for it: the query says so and the call refuses instead of dropping the adjoint
+    assert not native.tconv_fwd(gx, w16, bias, fused, query=True, **kw, epilogue=native.EPI_PRO_BWD, res=z, adj_prologue=native.PRO_ELU)
+    with pytest.raises(ValueError):
+        native.tconv_fwd(gx, w16, bias, fused, **kw, epilogue=native.EPI_PRO_BWD, res=z, adj_prologue=native.PRO_ELU)
+
+
 def test_flow_test_script_on_a_trained_checkpoint(native, tmp_path, monkeypatch):
     """test/flow_test.py (reference test/flow_test.py:52-100): restores the flag-named checkpoint, runs image by image,
     builds the [true | generated | difference] display image.  Uses a TFRecords test set written on the spot."""

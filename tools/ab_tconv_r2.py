@@ -31,5 +31,26 @@ for C, H, W in ((16, 64, 128), (32, 32, 64), (64, 16, 32)):
     native.lib.fn_debug_set_use_s1p(1)
     d = (ys[0] - ys[1]).norm() / ys[0].norm()
     gb = (x.numel() + y.numel()) * 2 / 1e9
+    # the same with the concat_elu adjoint: one launch against transposed conv + fn_prologue_bwd
+    z = torch.randn(B, 2 * H, 2 * W, C // 2, generator=g).to("cuda", torch.bfloat16)
+    out2 = torch.zeros(B, 2 * H, 2 * W, C // 2, device="cuda", dtype=torch.bfloat16)
+    def fused():
+        native.tconv_fwd(x, w16, bias, out2, B=B, H=H, W=W, Cin=C, Cout=C, impl=native.IMPL_TCGEN05, w_tc=w_tc,
+                         epilogue=native.EPI_PRO_BWD, res=z, adj_prologue=native.PRO_CONCAT_ELU, adj_accumulate=True)
+    def two():
+        native.tconv_fwd(x, w16, bias, y, B=B, H=H, W=W, Cin=C, Cout=C, impl=native.IMPL_TCGEN05, w_tc=w_tc)
+        native.prologue_bwd(y, z, native.PRO_CONCAT_ELU, out=out2, accumulate=True)
+    for fn in (two, fused):
+        for _ in range(3):
+            fn()
+        torch.cuda._sleep(4_000_000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out.append(e0.elapsed_time(e1) / 20 * 1000)
+    print("   with the prologue adjoint: two launches %.1f us, fused %.1f us" % (out[2], out[3]))
     print("C=%d %dx%d  generic %.1f us  persistent %.1f us (%.0f GB/s)  rel diff %.1e  status %d" % (
         C, H, W, out[0], out[1], gb / (out[1] * 1e-6), d.item(), native.tc_status()), flush=True)
