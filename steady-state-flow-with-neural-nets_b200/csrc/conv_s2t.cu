@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s2t(const __grid_constant__ Pa
               xv.v = pre_z[slot];
               old.v = pre_y[slot];
               float sc0[8], sc1[8];
-              const bool drop = p.keep_prob < 1.0f;
+              const bool drop = CF::S1N && p.keep_prob < 1.0f;     // the stride-2 convs have no dropout on their input
               if (drop) {
                 const unsigned long long seed = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
                 dropout_scale8(seed, (unsigned long long)pix * CF::NREAL + c0, p.keep_prob, sc0);
@@ -545,7 +545,8 @@ bool tconv_s2p_try(const fn_tconv_desc& d, cudaStream_t stream, bool dry_run, in
   const int clog = d.Cin == 16 ? 1 : d.Cin == 32 ? 2 : d.Cin == 64 ? 3 : -1;
   if (clog < 0) return false;
 #define TC_CASE(CL, RR, JJ, NB, CAP)                                                                          \
-  if (clog == CL && r == RR && ((d.W % (8 * JJ)) == 0 || JJ == 1) && Cfg<MODE_TCONV, CL, JJ, NB, RR>::SMEM <= CAP * 1024) { \
+  if (clog == CL && r == RR && ((d.W % (8 * JJ)) == 0 || JJ == 1) && !(adj.adj && JJ > 1 && CL == 1) &&        \
+      Cfg<MODE_TCONV, CL, JJ, NB, RR>::SMEM <= CAP * 1024) {                                                  \
     if (!dry_run) {                                                                                           \
       int* st = tc_status_word();                                                                             \
       rc = st ? launch<MODE_TCONV, CL, JJ, NB, RR>(d.x, d.w_tc, d.bias, d.y, d.B, d.H, d.W, d.Cout, st, stream, adj) \
