@@ -220,6 +220,33 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
   const int n_local = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   long long* stamps = (p.timing != nullptr && (int)blockIdx.x < p.timing_ctas) ? p.timing + (size_t)blockIdx.x * 8 : nullptr;
 
+  // producer lane: wait for tile it's buffers (it >= 2), then start its tensor copies
+  auto issue_tile = [&](int it) -> bool {
+    const int s = it & 1;
+    const uint32_t prev = (uint32_t)(((it >> 1) - 1) & 1);    // parity of the previous use of buffer s
+    int b, y0, x0;
+    tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, y0, x0);
+    if (it >= 2 && !ptx::mbar_wait(bar(SB_XF + s), prev)) {    // front finished reading stage[s]
+      atomicCAS(p.status, 0, 21);
+      return false;
+    }
+    ptx::mbar_arrive_expect_tx(bar(SB_X + s), (uint32_t)(Cfg::P * Cfg::C * 2));
+    tma_load_4d(sbase + Cfg::OFF_STAGE + s * Cfg::STAGE_BYTES, &p.tm_x, bar(SB_X + s), 0, x0 - 1, y0 - 1, b);
+    if (SKIP) {
+      ptx::mbar_arrive_expect_tx(bar(SB_S + s), (uint32_t)(Cfg::P * Cfg::C * 2));
+      tma_load_4d(sbase + Cfg::OFF_STAGE_S + s * Cfg::STAGE_BYTES, &p.tm_skip, bar(SB_S + s), 0, x0 - 1, y0 - 1, b);
+    }
+    if (GATE && p.res_mode == 1) {
+      if (it >= 2 && !ptx::mbar_wait(bar(SB_TE + s), prev)) {  // back finished with res[s]
+        atomicCAS(p.status, 0, 22);
+        return false;
+      }
+      ptx::mbar_arrive_expect_tx(bar(SB_R + s), (uint32_t)Cfg::RES_BYTES);
+      tma_load_4d(sbase + Cfg::OFF_RES + s * Cfg::RES_BYTES, &p.tm_res, bar(SB_R + s), 0, x0, y0, b);
+    }
+    return true;
+  };
+
   // ---- one-time setup
   if (warp == SP_WARP_PRODUCER) {
     ptx::tmem_alloc(sbase + 128, (uint32_t)Cfg::TMEM_COLS);
@@ -236,6 +263,12 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
         ptx::mbar_init(bar(SB_R + s), 1);
       }
       ptx::fence_mbar_init();
+      // the weights and the first two tiles need no hand-shake: start them now, under the rest of the set-up
+      // (bias staging, TMEM address exchange, the block barrier), instead of after it
+      pdl_wait();
+      ptx::mbar_arrive_expect_tx(bar(SB_W), (uint32_t)Cfg::W_BYTES);
+      ptx::bulk_g2s(sbase + Cfg::OFF_W, p.wpk, (uint32_t)Cfg::W_BYTES, bar(SB_W));
+      for (int it = 0; it < 2 && it < n_local; ++it) issue_tile(it);
     }
     __syncwarp();
   }
@@ -255,32 +288,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
   if (warp == SP_WARP_PRODUCER) {
     // =========================== producer: TMA ===========================
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(bar(SB_W), (uint32_t)Cfg::W_BYTES);
-      ptx::bulk_g2s(sbase + Cfg::OFF_W, p.wpk, (uint32_t)Cfg::W_BYTES, bar(SB_W));
-      for (int it = 0; it < n_local && ok; ++it) {
-        const int s = it & 1;
-        const uint32_t prev = (uint32_t)(((it >> 1) - 1) & 1);    // parity of the previous use of buffer s
-        int b, y0, x0;
-        tile_coords((int)blockIdx.x + it * (int)gridDim.x, b, y0, x0);
-        if (it >= 2) {
-          ok = ptx::mbar_wait(bar(SB_XF + s), prev);               // front finished reading stage[s]
-          if (!ok) { atomicCAS(p.status, 0, 21); break; }
-        }
-        ptx::mbar_arrive_expect_tx(bar(SB_X + s), (uint32_t)(Cfg::P * Cfg::C * 2));
-        tma_load_4d(sbase + Cfg::OFF_STAGE + s * Cfg::STAGE_BYTES, &p.tm_x, bar(SB_X + s), 0, x0 - 1, y0 - 1, b);
-        if (SKIP) {
-          ptx::mbar_arrive_expect_tx(bar(SB_S + s), (uint32_t)(Cfg::P * Cfg::C * 2));
-          tma_load_4d(sbase + Cfg::OFF_STAGE_S + s * Cfg::STAGE_BYTES, &p.tm_skip, bar(SB_S + s), 0, x0 - 1, y0 - 1, b);
-        }
-        if (GATE && p.res_mode == 1) {
-          if (it >= 2) {
-            ok = ptx::mbar_wait(bar(SB_TE + s), prev);             // back finished with res[s]
-            if (!ok) { atomicCAS(p.status, 0, 22); break; }
-          }
-          ptx::mbar_arrive_expect_tx(bar(SB_R + s), (uint32_t)Cfg::RES_BYTES);
-          tma_load_4d(sbase + Cfg::OFF_RES + s * Cfg::RES_BYTES, &p.tm_res, bar(SB_R + s), 0, x0, y0, b);
-        }
-      }
+      for (int it = 2; it < n_local && ok; ++it) ok = issue_tile(it);     // tiles 0 and 1 went out during set-up
     }
     __syncwarp();
   } else if (warp == SP_WARP_ISSUER) {
