@@ -47,6 +47,15 @@ def test_validation_errors_without_device(built_lib):
     d.ksize, d.x = 3, 4097
     assert lib.fn_conv_fwd(C.byref(d), None) == -3          # misaligned pointer
     assert lib.fn_tconv_fwd(None, None) == -1
+    t = built_lib.TConvDesc()
+    t.B, t.H, t.W, t.Cin, t.Cout = 1, 16, 16, 16, 8
+    t.x = t.w = t.bias = t.y = 4096
+    t.epilogue = 7
+    assert lib.fn_tconv_fwd(C.byref(t), None) == -1         # unknown epilogue
+    t.epilogue, t.adj_prologue = built_lib.EPI_PRO_BWD, built_lib.PRO_CONCAT_ELU
+    assert lib.fn_tconv_fwd(C.byref(t), None) == -2         # prologue-adjoint epilogue without res / with Cout != Cin
+    assert lib.fn_tconv_fwd_has_tcgen05(C.byref(t)) == 0
+    assert lib.fn_tconv_fwd_has_tcgen05(None) == 0
     assert lib.fn_adam_step(None, None, None, None, 1, 1, 1e-4, 0.9, 0.999, 1e-8, None) == -1
     assert lib.fn_l2_loss(None, None, None, None, 4, None) == -1
 
