@@ -711,8 +711,11 @@ static int launch_tc(TcParams& p, size_t smem_bytes, cudaStream_t stream) {
   return check_launch("k_conv_tc");
 }
 
+bool conv_wg_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);    // conv_wg.cu
+
 int conv_fwd_tc(const fn_conv_desc& d, cudaStream_t stream) {
   int rc_sp = 0;
+  if (g_tc_use_s1p && conv_wg_try(d, stream, false, rc_sp)) return rc_sp;
   if (g_tc_use_s1p && conv_s1p_try(d, stream, false, rc_sp)) return rc_sp;
   if (g_tc_use_s1p && conv_s1d_try(d, stream, false, rc_sp)) return rc_sp;
   if (g_tc_use_s1p && conv_s1w_try(d, stream, false, rc_sp)) return rc_sp;

@@ -110,6 +110,8 @@ DEBUG_SYMBOLS = [
     ("fn_debug_set_use_s1p", None, [C.c_int]),
     ("fn_debug_set_wgrad_swap", None, [C.c_int]),
     ("fn_debug_set_nsplit", None, [C.c_int]),
+    ("fn_debug_set_wg", None, [C.c_int]),
+    ("fn_debug_set_wg_j16", None, [C.c_int]),
 ]
 
 

@@ -240,6 +240,31 @@ def test_persistent_tma_kernel_vs_generic_and_oracle(native, case):
     assert rel_l2(y, yg) < 5e-4          # same MMA order; the gate uses tanh.approx here, ex2+rcp there
 
 
+WG_CASES = [c for c in S1P_CASES if c[6] == 1 and c[7] == 1 and c[4] in (8, 16, 32) and not (c[4] == 32 and c[8] == 1)]
+
+
+@pytest.mark.parametrize("j16", [1, 2])
+@pytest.mark.parametrize("case", WG_CASES, ids=[c[0] for c in WG_CASES])
+def test_warpgroup_kernel_matches_the_role_pipelined_kernel(native, case, j16):
+    """conv_wg.cu re-orchestrates k_conv_s1p (same operands, same MMA order per accumulator): the outputs agree up to
+    the fused multiply-add the compiler forms in the warpgroup kernel's shortcut add, for both tile widths of the
+    16-channel level."""
+    name, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool = case
+    if j16 == 2 and Cin != 16:
+        pytest.skip("tile-width switch only exists on the 16-channel level")
+    try:
+        native.lib.fn_debug_set_wg(1)
+        native.lib.fn_debug_set_wg_j16(j16)
+        y, ref = run_fused_conv(native, native.IMPL_TCGEN05, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool)
+        native.lib.fn_debug_set_wg(0)
+        y0, _ = run_fused_conv(native, native.IMPL_TCGEN05, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool)
+    finally:
+        native.lib.fn_debug_set_wg(1)
+        native.lib.fn_debug_set_wg_j16(1)
+    assert rel_l2(y, ref) < LAYER_TOL
+    assert rel_l2(y, y0) < 5e-4
+
+
 def test_tcgen05_refuses_shapes_it_has_no_kernel_for(native):
     with pytest.raises(ValueError):
         run_fused_conv(native, native.IMPL_TCGEN05, 1, 16, 16, 1, 8, 1, 0, 0)     # K = 9: CUDA-core layer
