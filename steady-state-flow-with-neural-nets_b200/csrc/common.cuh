@@ -67,6 +67,26 @@ __host__ __device__ inline int same_pad_before(int n, int k, int s) {
 __device__ __forceinline__ float elu_f(float z) { return z > 0.f ? z : (__expf(z) - 1.f); }
 __device__ __forceinline__ float sigmoid_f(float z) { return 1.f / (1.f + __expf(-z)); }
 
+// [elu(x) | elu(-x)] of two packed bf16 values (flow_architecture.py:14-17).  t = exp(-|v|) - 1 is computed in fp32 and
+// rounded once, exactly as the scalar form (v > 0 ? v : t, v > 0 ? t : -v); the selects are packed maxima: t >= min(v, -v)
+// and t <= 0 <= max(v, -v) hold after rounding too (rounding is monotonic and v is a bf16 value), so the results are
+// the same values (up to the sign of a zero) for 5.5 instead of 9.5 instructions per element.
+__device__ __forceinline__ void concat_elu2(uint32_t xw, uint32_t& o0, uint32_t& o1) {
+  const float lo = __uint_as_float(xw << 16), hi = __uint_as_float(xw & 0xffff0000u);
+  const float tl = __expf(-fabsf(lo)) - 1.f, th = __expf(-fabsf(hi)) - 1.f;
+  const __nv_bfloat162 t2 = __floats2bfloat162_rn(tl, th);
+  const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&xw);
+  const __nv_bfloat162 a = __hmax2(x2, t2), b = __hmax2(__hneg2(x2), t2);
+  o0 = *reinterpret_cast<const uint32_t*>(&a);
+  o1 = *reinterpret_cast<const uint32_t*>(&b);
+}
+__device__ __forceinline__ void concat_elu8(const uint4& in, uint4& o0, uint4& o1) {
+  concat_elu2(in.x, o0.x, o1.x);
+  concat_elu2(in.y, o0.y, o1.y);
+  concat_elu2(in.z, o0.z, o1.z);
+  concat_elu2(in.w, o0.w, o1.w);
+}
+
 // number of GEMM-K channels produced per raw channel by a prologue
 __host__ __device__ inline int pro_mult(int pro) {
   return (pro == FN_PRO_CONCAT_ELU || pro == FN_PRO_CONCAT_RELU) ? 2 : 1;

@@ -108,13 +108,7 @@ __device__ __forceinline__ void transform_tile(uint32_t stage, uint32_t planes, 
     }
     bf16x8 in, o0, o1;
     in.v = lds128(stage + (uint32_t)idx * 16u);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float v = __bfloat162float(in.h[j]);
-      const float t = __expf(-fabsf(v)) - 1.f;
-      o0.h[j] = __float2bfloat16(v > 0.f ? v : t);
-      o1.h[j] = __float2bfloat16(v > 0.f ? t : -v);
-    }
+    concat_elu8(in.v, o0.v, o1.v);
     const uint32_t d0 = planes + (uint32_t)(ch * CF::PPAD + pp) * 16u;
     sts128(d0, o0.v);
     sts128(d0 + (uint32_t)(CF::CH * CF::PPAD * 16), o1.v);
@@ -206,8 +200,9 @@ __device__ __forceinline__ void shortcut_generic(const Params& p, int F, int b, 
 template <int CLOG, int J, bool GATE, bool SKIP, bool TR, int NST, int NSPLIT = 1>
 __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Params p) {
   using CF = Cfg<CLOG, J, GATE, SKIP, TR, NST, NSPLIT>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  // no static shared memory in these kernels: the dynamic window starts on a 1024-byte boundary, so the base is a
+  // compile-time constant of the shared state space (TMA destinations want 128-byte alignment)
+  extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = ptx::smem_u32(smem);
   auto bar = [&](int i) { return sbase + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 128);

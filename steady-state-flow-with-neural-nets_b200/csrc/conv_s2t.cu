@@ -106,13 +106,7 @@ __device__ __forceinline__ void transform_tile(uint32_t stage, uint32_t planes, 
         sts128(planes + (uint32_t)(sub * CF::SUB_BYTES) + (uint32_t)(ch * CF::PPAD + pp) * 16u, in.v);
       } else {
         bf16x8 o0, o1;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float v = __bfloat162float(in.h[j]);
-          const float t = __expf(-fabsf(v)) - 1.f;
-          o0.h[j] = __float2bfloat16(v > 0.f ? v : t);
-          o1.h[j] = __float2bfloat16(v > 0.f ? t : -v);
-        }
+        concat_elu8(in.v, o0.v, o1.v);
         const uint32_t d0 = planes + (uint32_t)(sub * CF::SUB_BYTES) + (uint32_t)(ch * CF::PPAD + pp) * 16u;
         sts128(d0, o0.v);
         sts128(d0 + (uint32_t)(CF::CH * CF::PPAD * 16), o1.v);
@@ -126,8 +120,9 @@ __device__ __forceinline__ void transform_tile(uint32_t stage, uint32_t planes, 
 template <int MODE, int CLOG, int J, int NBUF, int R = 1>
 __global__ void __launch_bounds__(THREADS) k_conv_s2t(const __grid_constant__ Params p) {
   using CF = Cfg<MODE, CLOG, J, NBUF, R>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  // no static shared memory in these kernels: the dynamic window starts on a 1024-byte boundary, so the base is a
+  // compile-time constant of the shared state space (TMA destinations want 128-byte alignment)
+  extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = ptx::smem_u32(smem);
   auto bar = [&](int i) { return sbase + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 128);

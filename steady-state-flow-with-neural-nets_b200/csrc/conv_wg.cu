@@ -83,20 +83,6 @@ __device__ __forceinline__ float tanh_approx(float x) {
   return y;
 }
 
-// [elu(x) | elu(-x)] of two packed bf16 values.  t = exp(-|v|) - 1 is computed in fp32 and rounded once, exactly as the
-// scalar form (v > 0 ? v : t, v > 0 ? t : -v) of the other kernels; the selects are packed maxima: t >= min(v, -v) and
-// t <= 0 <= max(v, -v) hold after rounding too (rounding is monotonic and v is a bf16 value), so the results are the same
-// values (up to the sign of a zero) for 5.5 instead of 9.5 instructions per element.
-__device__ __forceinline__ void concat_elu2(uint32_t xw, uint32_t& o0, uint32_t& o1) {
-  const float lo = __uint_as_float(xw << 16), hi = __uint_as_float(xw & 0xffff0000u);
-  const float tl = __expf(-fabsf(lo)) - 1.f, th = __expf(-fabsf(hi)) - 1.f;
-  const __nv_bfloat162 t2 = __floats2bfloat162_rn(tl, th);
-  const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&xw);
-  const __nv_bfloat162 a = __hmax2(x2, t2), b = __hmax2(__hneg2(x2), t2);
-  o0 = *reinterpret_cast<const uint32_t*>(&a);
-  o1 = *reinterpret_cast<const uint32_t*>(&b);
-}
-
 // stage [pp][C] raw bf16 (TMA box order) -> planes [2C/8][PAD][8] = [elu(x) | elu(-x)]; 128 threads
 template <int ITEMS, int CH, int PAD>
 __device__ __forceinline__ void transform(uint32_t stage, uint32_t planes, int t128) {
@@ -111,10 +97,7 @@ __device__ __forceinline__ void transform(uint32_t stage, uint32_t planes, int t
     const int pp = idx >> SH;
     const uint4 in = lds128(stage + (uint32_t)idx * 16u);
     uint4 o0, o1;
-    concat_elu2(in.x, o0.x, o1.x);
-    concat_elu2(in.y, o0.y, o1.y);
-    concat_elu2(in.z, o0.z, o1.z);
-    concat_elu2(in.w, o0.w, o1.w);
+    concat_elu8(in, o0, o1);
     const uint32_t d0 = planes + (uint32_t)(ch * PAD + pp) * 16u;
     sts128(d0, o0);
     sts128(d0 + (uint32_t)(CH * PAD * 16), o1);
@@ -383,7 +366,7 @@ __global__ void __launch_bounds__(NWG * 128, MINB) k_conv_wg(const __grid_consta
 
 // ------------------------------------------------------------------------------------ host side
 
-static int g_enable = -1;     // -1: read FLOWNET_WG on first use (default on); 0 off; 1 on
+static int g_enable = -1;     // -1: read FLOWNET_WG on first use (default 1); 0 off; 1 where measured faster than k_conv_s1p; 2 every shape it has
 static int g_j16 = -1;        // sub-tiles per warpgroup tile on the 16-channel level (FLOWNET_WG_J16, default 1)
 
 template <int CLOG, int J, bool GATE, bool SKIP, int NWG, int MINB, int RESM>
@@ -453,7 +436,7 @@ bool conv_wg_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& 
   rc = 0;
   if (g_enable < 0) {
     const char* e = getenv("FLOWNET_WG");
-    g_enable = (e && e[0] == '0') ? 0 : 1;
+    g_enable = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
   }
   if (g_j16 < 0) {
     const char* e = getenv("FLOWNET_WG_J16");
@@ -472,6 +455,8 @@ bool conv_wg_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& 
   const int clog = d.Cin == 8 ? 0 : d.Cin == 16 ? 1 : d.Cin == 32 ? 2 : -1;
   if (clog < 0) return false;
   if (clog == 2 && gate) return false;                        // 147 KB of weights: k_conv_s1p (one CTA per SM)
+  // A/B at batch 64 (tools/ab_wg.py, profiles/): the plain 16-channel conv_1 and the 32-channel level stay on k_conv_s1p
+  if (g_enable == 1 && ((clog == 1 && !gate && !skip) || clog == 2)) return false;
   const int j = clog == 0 ? 2 : clog == 1 ? g_j16 : 1;
 #define WG_CASE(CL, JJ, G, S, NW, MB)                                                   \
   if (clog == CL && j == JJ && gate == G && skip == S) {                                 \
@@ -493,6 +478,7 @@ bool conv_wg_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& 
 
 extern "C" {
 // test / timing hook: 0 sends the stride-1 concat_elu convolutions back to k_conv_s1p, 1 (default) uses the warpgroup kernel
-void fn_debug_set_wg(int v) { fn::wg::g_enable = v ? 1 : 0; }
+// where it measured faster, 2 wherever it has an instantiation
+void fn_debug_set_wg(int v) { fn::wg::g_enable = v < 0 ? 0 : v > 2 ? 2 : v; }
 void fn_debug_set_wg_j16(int v) { fn::wg::g_j16 = v == 2 ? 2 : 1; }
 }

@@ -146,8 +146,9 @@ template <int MODE, int TU = 16>
 __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Params p) {
   using G = Geo<MODE, TU>;
   constexpr int DY_PLANE = G::DY_PLANE;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  // no static shared memory in these kernels: the dynamic window starts on a 1024-byte boundary, so the base is a
+  // compile-time constant of the shared state space (TMA destinations want 128-byte alignment)
+  extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = ptx::smem_u32(smem);
   auto bar = [&](int i) { return sbase + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 256);

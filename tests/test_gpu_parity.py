@@ -253,7 +253,7 @@ def test_warpgroup_kernel_matches_the_role_pipelined_kernel(native, case, j16):
     if j16 == 2 and Cin != 16:
         pytest.skip("tile-width switch only exists on the 16-channel level")
     try:
-        native.lib.fn_debug_set_wg(1)
+        native.lib.fn_debug_set_wg(2)          # every shape the kernel has, not only the ones it is the default for
         native.lib.fn_debug_set_wg_j16(j16)
         y, ref = run_fused_conv(native, native.IMPL_TCGEN05, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool)
         native.lib.fn_debug_set_wg(0)

@@ -20,7 +20,7 @@ for (H, W, C, gate, skip) in CASES:
     w_tc = native.pack_conv_weights_tc(w16, ws16, 3, 2 * C, 2 * C if skip else 0, N, gate)
     y = torch.empty((B, H, W, C), device="cuda", dtype=torch.bfloat16)
     out = {}
-    for name, wgon, j16 in (("s1p", 0, 1), ("wg", 1, 1), ("wg_j16=2", 1, 2)):
+    for name, wgon, j16 in (("s1p", 0, 1), ("wg", 2, 1), ("wg_j16=2", 2, 2)):
         if j16 == 2 and C != 16:
             continue
         native.lib.fn_debug_set_wg(wgon)

@@ -15,7 +15,7 @@ bias = torch.zeros(N, device="cuda")
 res = torch.randn(B, H, W, C, generator=g).to("cuda", torch.bfloat16) if gate else None
 w_tc = native.pack_conv_weights_tc(w16, ws16, 3, 2 * C, 2 * C if skip else 0, N, bool(gate))
 y = torch.empty((B, H, W, C), device="cuda", dtype=torch.bfloat16)
-native.lib.fn_debug_set_wg(int(os.environ.get("PROF_WG", "1")))
+native.lib.fn_debug_set_wg(int(os.environ.get("PROF_WG", "2")))
 native.lib.fn_debug_set_wg_j16(int(os.environ.get("PROF_J16", "1")))
 for _ in range(int(os.environ.get("PROF_N", "4"))):
     native.conv_fwd(x, w16, bias, y, B=B, H=H, W=W, Cin=C, Cout=N, ksize=3, stride=1, prologue=1,
