@@ -161,7 +161,7 @@ int64_t fn_tfrecord_index(const uint8_t* buf, int64_t nbytes, int64_t* offsets, 
   if (!buf || nbytes < 0) return FN_E_INVAL;
   int64_t pos = 0, n = 0;
   while (pos < nbytes) {
-    if (nbytes - pos < 12) return FN_E_INVAL;                       // truncated header
+    if (nbytes - pos < 16) return FN_E_INVAL;                       // truncated header / footer: a record is >= 16 bytes
     uint64_t len;
     uint32_t lcrc;
     memcpy(&len, buf + pos, 8);

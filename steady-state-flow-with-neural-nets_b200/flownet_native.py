@@ -303,13 +303,17 @@ def adam_step(param, grad, m, v, step, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8
 
 # ------------------------------------------------------------------ training-step adjoints
 _ws_cache = {}
+_ws_retired = []     # outgrown buffers are kept: a captured CUDA graph may have their address baked in
 
 
 def _workspace(nfloats, device):
-    """One grow-only fp32 scratch buffer per device for the two-stage reductions."""
+    """One grow-only fp32 scratch buffer per device for the two-stage reductions.  A buffer that is outgrown is retired,
+    never freed: replays of a graph captured earlier (flow_net.CompiledTraining) keep writing through the old pointer."""
     buf = _ws_cache.get(device)
     if buf is None or buf.numel() < nfloats:
-        buf = torch.empty(max(int(nfloats), 1 << 20), dtype=torch.float32, device=device)
+        if buf is not None:
+            _ws_retired.append(buf)
+        buf = torch.empty(max(int(nfloats) * 3 // 2, 1 << 20), dtype=torch.float32, device=device)
         _ws_cache[device] = buf
     return buf
 

@@ -211,7 +211,7 @@ def _conv_weights(scope, ksize, cin_eff, cout, device, skip_scope=None, kskip_ef
             w_tc = native.pack_conv_weights_tc(w16, ws16, ksize, cin_eff, kskip_eff, cout, gated)
         return w16, ws16, bias, w_tc
 
-    return VARIABLES.derived(("conv", scope, skip_scope), make)
+    return VARIABLES.derived(("conv", scope, skip_scope, bool(pass_major), bool(gated)), make)
 
 
 def _fused_conv(x, scope, ksize, stride, cout, prologue, epilogue, skip=None, skip_scope=None, res=None,

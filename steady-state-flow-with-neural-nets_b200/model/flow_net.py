@@ -85,26 +85,42 @@ class CompiledInference:
         self.B, (self.H, self.W) = batch_size, shape
         self.keep_prob = keep_prob
         self.static_in = torch.zeros((batch_size, shape[0], shape[1], 1), dtype=in_dtype, device="cuda")
+        self._capture()
+
+    def _capture(self):
+        """(Re-)capture the forward.  The graph has the addresses of the packed weight images baked in; those live in
+        VARIABLES' derived cache, which an optimizer step / checkpoint restore clears -- so the object holds its own
+        references to them and re-captures when the variables have changed since (VARIABLES.version)."""
+        V = flow_architecture.VARIABLES
         # warm-up on a side stream (creates variables, packs weights, sizes the allocator pool)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(2):
-                inference(self.static_in, keep_prob)
+                inference(self.static_in, self.keep_prob)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = native.launch_count()
         with torch.cuda.graph(self.graph):
-            self.static_out = inference(self.static_in, keep_prob)
+            self.static_out = inference(self.static_in, self.keep_prob)
         self.launches_per_replay = native.launch_count() - n0
+        self._version = V.version
+        self._keepalive = list(V._derived.values())
+        self.__dict__.pop("_pipe", None)              # the two-graph serving pipeline is rebuilt on demand
+
+    def _fresh(self):
+        if flow_architecture.VARIABLES.version != self._version:
+            self._capture()
 
     def __call__(self, boundary):
+        self._fresh()
         self.static_in.copy_(boundary, non_blocking=True)
         self.graph.replay()
         return self.static_out
 
     def replay(self):
+        self._fresh()
         self.graph.replay()
         return self.static_out
 
@@ -114,7 +130,8 @@ class CompiledInference:
         stream.  Two captured graphs with their own static input / output buffers alternate, so uploads land directly
         in a graph's input and downloads read directly from a graph's output (no device-to-device staging copies).
         host_inputs / host_outputs: equally long sequences of pinned CPU tensors ([B,H,W,1] / float32 [B,H,W,2]).
-        Returns after every output has landed on the host."""
+        Returns after every output has landed on the host (the download stream is synchronised)."""
+        self._fresh()
         if not hasattr(self, "_pipe"):
             # second buffer set + graph (the first is the one __init__ captured)
             in2 = torch.zeros_like(self.static_in)
@@ -148,6 +165,7 @@ class CompiledInference:
                 host_outputs[i].copy_(P["dout"][k], non_blocking=True)
                 P["down"][k].record(P["d2h"])
         main.wait_stream(P["d2h"])
+        P["d2h"].synchronize()                 # the pinned outputs are complete when this returns
 
 
 # --------------------------------------------------------------------------- training (reference :44-46)

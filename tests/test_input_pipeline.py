@@ -89,6 +89,32 @@ def test_native_reader_rejects_corrupt_truncated_and_mis_sized(fi, tmp_path):
     assert len(fi.TFRecordFile(p3)) == 0
 
 
+def test_index_rejects_a_file_cut_at_every_offset_of_the_last_record(built_lib):
+    """A dataset file cut off mid-write must be a clean FN_E_INVAL at every cut point -- in particular inside the 12-byte
+    header and the 4-byte footer, where a 12..15-byte remainder used to pass the length check -- and must
+    never read past the buffer: the image is placed flush against the end of its allocation, with and without CRC checks."""
+    b, s = _examples(2, H=3, W=4, seed=3)
+    recs = [tfo.frame(tfo.encode_example({"boundary": b[i].tobytes(), "sflow": s[i].tobytes()})) for i in range(2)]
+    good = recs[0] + recs[1]
+    lib = built_lib.lib
+    for cut in range(len(recs[0]), len(good) + 1):
+        data = np.frombuffer(good[:cut], np.uint8).copy()            # exactly `cut` bytes: no slack behind the image
+        for crc in (0, 1):
+            n = lib.fn_tfrecord_index(data.ctypes.data if cut else None, cut, None, None, 0, crc)
+            if cut == len(recs[0]):
+                assert n == 1
+            elif cut == len(good):
+                assert n == 2
+            else:
+                assert n == -1, (cut, crc, n)
+    # a 14-byte image with a valid length CRC and a huge length: header complete, footer missing
+    import struct as _st
+    hdr = _st.pack("<Q", 1 << 20)
+    img = np.frombuffer(hdr + _st.pack("<I", tfo.masked_crc(hdr)) + b"\0\0", np.uint8).copy()
+    for crc in (0, 1):
+        assert lib.fn_tfrecord_index(img.ctypes.data, img.size, None, None, 0, crc) == -1
+
+
 def test_input_queue_fifo_and_shuffle(fi, tmp_path):
     b, s = _examples(10, seed=3)
     p1, p2 = str(tmp_path / "1.tfrecords"), str(tmp_path / "2.tfrecords")
