@@ -134,7 +134,7 @@ def run_reference(args, rank, world):
     from oracle import flow_oracle as fo
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    b = 8
+    b = args.batch                       # the same configuration as the repo arm: the whole 64-image batch per step
     x = torch.from_numpy(car_batch(b).astype(np.float32))
     vs = fo.VariableStore(1234, torch.float32)
     with torch.no_grad():
@@ -145,23 +145,29 @@ def run_reference(args, rank, world):
             fo.inference(vs, x, 1.0)
         dt = time.perf_counter() - t0
     v = b * args.steps / dt
-    sample = (f"each step = one forward of the first {b} images of the {BATCH}-image workload; oracle/flow_oracle.py "
+    sample = (f"each step = one forward of the {b}-image workload batch; oracle/flow_oracle.py "
               f"torch-CPU fp32, {cores} threads (TF-1.x reference not installable: SURVEY F11)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": v / PUBLISHED_IMG_S, "dtype": "f32", "data": "bundled car masks (fixture), random-init weights",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": b, "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of this command
-# (profiles/r1_prof_v12_k_conv_s1p_summary.csv: 67.19 MB read + 7.31 MB written back so far; the rest of the 33.5 MB
-# output was still in L2 when the kernel ended).  Keyed by (layer, batch): other shapes report null.
-NCU_TRAFFIC_BYTES = {("resnet_up_4_0_conv_1_conv", 64): 74.50e6}
+def ncu_evidence():
+    """profiles/r2_ncu_summary.json: per conv launch of the default forward at batch 64, from the committed
+    `ncu --set full` capture of this command (tools/ncu_summary.py writes it): DRAM bytes read + written, tensor-pipe
+    and tensor-memory-pipe activity.  Read at run time, keyed by (layer, batch); absent file or key -> None."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_summary.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
 
 
 def layer_profile(x_dev, reps=5):
@@ -188,10 +194,12 @@ def layer_profile(x_dev, reps=5):
     return rows
 
 
-def run_train(args, rank, world, dist, native, arch, flow_net):
+def run_train(args, rank, world, dist, native, arch, flow_net, steps=None):
     """BASELINE configs[2]: training step (L2 loss, fwd+bwd+Adam), global batch 256 synthetic 128x256,
-    batch-sharded with one NCCL all-reduce of the flat fp32 gradient.  keep_prob = 1.0 (tcgen05 forward)."""
+    batch-sharded with one NCCL all-reduce of the flat fp32 gradient.  keep_prob = 1.0 (the parity setting) unless
+    --keep-prob.  Returns the record (rank 0) or None."""
     global_batch = 256
+    steps = steps or args.steps
     B = global_batch // world
     arch.reset_variables(1234)
     flow_net.reset_training_state()
@@ -212,7 +220,8 @@ def run_train(args, rank, world, dist, native, arch, flow_net):
         return flow_net.train(err, 1e-4)
 
     step.k = 0
-    for _ in range(max(args.warmup, 2)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     if world > 1:
         dist.barrier()
@@ -220,7 +229,7 @@ def run_train(args, rank, world, dist, native, arch, flow_net):
     n0 = native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = step()
     e1.record()
     if world > 1:
@@ -231,22 +240,29 @@ def run_train(args, rank, world, dist, native, arch, flow_net):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
     flow_net.end_training()
-    if rank == 0:
-        v = global_batch * args.steps / (ms * 1e-3)
-        print(json.dumps({
-            "metric": "flow_net training images/sec at 128x256 (fwd+bwd+Adam)", "value": v, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 2), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic boundaries and targets",
-            "config": {"workload": "configs[2]: training step, global batch 256, 128x256, L2 loss + TF1 Adam, "
-                                   "keep_prob %.2f; tcgen05 fwd + dgrad + wgrad; %s" % (
-                                       args.keep_prob, "fwd+bwd replayed from a CUDA graph" if compiled is not None else "eager launches"),
-                       "batch_per_gpu": B, "parallelism": f"dp{world}, one flat fp32 gradient all-reduce"},
-            # kernels of this library per step: those replayed from the graph + the eager ones (Adam) the counter saw
-            "gpu_launches": native.launch_count() - n0 + (compiled.launches_per_replay * args.steps if compiled is not None else 0),
-            "loss": float(loss.item()),
-            "roofline": {"bound": "tensor", "achieved": v * 8.519e9 / 1e12, "peak": load_peaks()["tc_sustained"],
-                         "unit": "TFLOP/s", "frac": v * 8.519e9 / 1e12 / load_peaks()["tc_sustained"], "traffic": None},
-        }))
+    flow_net.reset_training_state()
+    arch.reset_variables(1234)
+    if rank != 0:
+        return None
+    v = global_batch * steps / (ms * 1e-3)
+    peaks = load_peaks()
+    per_gpu_tflops = v / world * 8.519e9 / 1e12         # 3x the forward's 2.841 GFLOP per image, on ONE GPU's share
+    return {
+        "metric": "flow_net training images/sec at 128x256 (fwd+bwd+Adam)", "value": v, "unit": UNIT, "n_gpus": world,
+        "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic boundaries and targets",
+        "config": {"workload": "configs[2]: training step, global batch 256, 128x256, L2 loss + TF1 Adam, "
+                               "keep_prob %.2f; tcgen05 fwd + dgrad + wgrad; %s" % (
+                                   args.keep_prob, "fwd+bwd replayed from a CUDA graph" if compiled is not None else "eager launches"),
+                   "batch_per_gpu": B,
+                   "parallelism": f"dp{world}, one flat fp32 gradient all-reduce (%s)" % ("NCCL" if world > 1 else "single GPU: none")},
+        # kernels of this library per step: those replayed from the graph + the eager ones (Adam) the counter saw
+        "gpu_launches": native.launch_count() - n0 + (compiled.launches_per_replay * steps if compiled is not None else 0),
+        "loss": float(loss.item()),
+        "roofline": {"bound": "tensor", "achieved": per_gpu_tflops, "peak": peaks["tc_sustained"],
+                     "unit": "TFLOP/s per GPU", "frac": per_gpu_tflops / peaks["tc_sustained"], "traffic": None,
+                     "peak_source": peaks["source"] + " (sustained; whole step)"},
+    }
 
 
 def main():
@@ -258,7 +274,9 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU per step (default: the configs[1] batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="inference", choices=["inference", "train"],
-                    help="train: BASELINE configs[2], fwd+bwd+Adam at global batch 256 (extra line, not the headline)")
+                    help="train: only BASELINE configs[2] (fwd+bwd+Adam at global batch 256); the default run carries it as the `train` sub-record")
+    ap.add_argument("--no-train", action="store_true", help="skip the `train` sub-record of the default run")
+    ap.add_argument("--train-steps", type=int, default=10, help="timed steps of the `train` sub-record")
     ap.add_argument("--keep-prob", type=float, default=1.0,
                     help="train mode: dropout keep probability (1.0 = the parity setting; the reference trains with 0.7)")
     ap.add_argument("--eager-train", action="store_true", help="train mode: launch every kernel eagerly instead of replaying a graph")
@@ -286,7 +304,9 @@ def main():
     import model.flow_net as flow_net
 
     if args.mode == "train":
-        run_train(args, rank, world, dist, native, arch, flow_net)
+        rec = run_train(args, rank, world, dist, native, arch, flow_net)
+        if rec is not None:
+            print(json.dumps(rec))
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -311,6 +331,7 @@ def main():
     for _ in range(args.warmup):
         compiled.replay()
     barrier()
+    replays0 = compiled.replays                                      # graph replays inside the three timed regions
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -344,6 +365,8 @@ def main():
     g1.record()
     barrier()
     ms_e2e_serial = g0.elapsed_time(g1)
+    timed_replays = compiled.replays - replays0 - 3                  # minus the e2e loop's three untimed warm-up steps
+    launches_per_replay = compiled.launches_per_replay
     clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
@@ -364,12 +387,18 @@ def main():
             r["frac"] = (r["tflops"] / peaks["tc_burst"]) if r["bound"] == "tensor" else (r["gbs"] / peaks["hbm"])
         total_ms = sum(r["ms"] for r in rows)
         top = max(rows, key=lambda r: r["ms"])
+        ev = ncu_evidence() or {}
+        ev_top = (ev.get("launches", {}).get("%s@b%d" % (top["name"], B)) or {})
         roofline = {
             "bound": top["bound"],
             "achieved": top["tflops"] if top["bound"] == "tensor" else top["gbs"],
             "peak": peaks["tc_burst"] if top["bound"] == "tensor" else peaks["hbm"],
             "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s",
-            "frac": top["frac"], "traffic": NCU_TRAFFIC_BYTES.get((top["name"], B)),
+            "frac": top["frac"], "traffic": ev_top.get("dram_bytes"),
+            "traffic_source": ev.get("source") if ev_top else None,
+            # BASELINE metric, second half: tensor-pipe activity of the conv launches (ncu sm__pipe_tensor_cycles_active
+            # and sm__mem_tensor_cycles_active, % of elapsed), read from the committed capture of this command
+            "tensor_pipe_util": ev.get("tensor_pipe_util"),
             "kernel": top["name"], "kernel_ms": top["ms"], "share_of_step": top["ms"] / total_ms,
             "tcgen05": top["tcgen05"], "peak_source": peaks["source"] + " (burst; kernel timed alone)",
             "whole_net": {
@@ -386,6 +415,13 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_oracle_rate()
+    # ---------------- BASELINE configs[2] beside it: the training step with its gradient all-reduce (every rank takes part)
+    train = None
+    if not args.no_train:
+        del compiled
+        torch.cuda.empty_cache()
+        train = run_train(args, rank, world, dist, native, arch, flow_net, steps=args.train_steps)
+    if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -395,17 +431,21 @@ def main():
                        "l2_policy": "no flush: one step moves ~1 GB of activations per GPU, 8x the 126 MB L2",
                        "baseline_note": "vs_baseline divides by the reference README's 348 img/s (GTX 1080, batch 8, "
                                         "incl. feed/fetch); compare e2e for like with like",
-                       "launch": "CUDA graph, %d kernels per step" % compiled.launches_per_replay},
+                       "launch": "CUDA graph, %d kernels per step" % launches_per_replay},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel()) * world,
                     "d2h_bytes_per_step": int(out_host.numel() * 4) * world, "ms_per_step": ms_e2e / args.steps,
                     "how": "CompiledInference.stream_host: two alternating graphs, uploads / downloads on side streams straight into / out of their static buffers",
                     "serial_value": world * B * args.steps / (ms_e2e_serial * 1e-3)},
-            "gpu_launches": compiled.launches_per_replay * args.steps * 3,
+            # kernels of libflownet.so launched inside the three timed regions (value, e2e, serial e2e): counted graph
+            # replays x the launches the C ABI's counter saw while the graph was captured
+            "gpu_launches": launches_per_replay * timed_replays,
             "clocks": clocks,
             "roofline": roofline,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if train is not None:
+            line["train"] = train
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

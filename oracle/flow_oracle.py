@@ -222,8 +222,9 @@ def dropout_tf1(x, keep_prob, gen):
 
 
 def res_block(vs, x, a=None, filter_size=16, nonlinearity=concat_elu, keep_p=1.0, stride=1,
-              gated=False, name="resnet", gen=None):
-    """flow_architecture.py:129-165"""
+              gated=False, name="resnet", gen=None, mask_seed=None):
+    """flow_architecture.py:129-165.  mask_seed: use the CUDA path's counter-based dropout mask with this seed
+    (oracle/dropout_oracle.py) instead of a torch RNG draw, so both sides drop the same elements."""
     orig_x = x
     if x.shape[3] == 1:
         x_1 = conv_layer(vs, x, 3, stride, filter_size, name + "_conv_1")
@@ -237,7 +238,11 @@ def res_block(vs, x, a=None, filter_size=16, nonlinearity=concat_elu, keep_p=1.0
         x_1 = x_1 + nin(vs, nonlinearity(a), filter_size, name + "_nin")
     x_1 = nonlinearity(x_1)
     if keep_p < 1.0:
-        x_1 = dropout_tf1(x_1, keep_p, gen)
+        if mask_seed is not None:
+            from oracle import dropout_oracle
+            x_1 = x_1 * torch.from_numpy(dropout_oracle.dropout_scale(mask_seed, tuple(x_1.shape), keep_p)).to(x_1.dtype)
+        else:
+            x_1 = dropout_tf1(x_1, keep_p, gen)
     if not gated:
         x_2 = conv_layer(vs, x_1, 3, 1, filter_size, name + "_conv_2")
     else:
@@ -254,11 +259,16 @@ def res_block(vs, x, a=None, filter_size=16, nonlinearity=concat_elu, keep_p=1.0
 
 
 def conv_res(vs, inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name="concat_elu",
-             gated=True, filter_size=8, gen=None, taps=None):
+             gated=True, filter_size=8, gen=None, taps=None, dropout_seed=None):
     """flow_architecture.py:167-248.  `filter_size` (hard-coded 8 upstream, :174) is exposed
     for BASELINE config 5.  `taps`, if a dict, receives named intermediate activations."""
     nonlinearity = set_nonlinearity(nonlinearity_name)
     kw = dict(nonlinearity=nonlinearity, keep_p=keep_prob, gated=gated, gen=gen)
+    nblock = [0]
+
+    def block(vs, x, **k):                         # numbers the blocks: block n drops with seed dropout_seed + n
+        nblock[0] += 1
+        return res_block(vs, x, mask_seed=None if dropout_seed is None else dropout_seed + nblock[0], **k)
 
     def tap(name, t):
         if taps is not None:
@@ -268,32 +278,32 @@ def conv_res(vs, inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name="conc
     a = []
     x = inputs
     for i in range(nr_res_blocks):
-        x = tap(f"resnet_1_{i}", res_block(vs, x, filter_size=filter_size, name=f"resnet_1_{i}", **kw))
+        x = tap(f"resnet_1_{i}", block(vs, x, filter_size=filter_size, name=f"resnet_1_{i}", **kw))
     for lvl in (2, 3, 4, 5):
         a.append(x)
         filter_size = 2 * filter_size
         x = tap(f"resnet_{lvl}_downsample",
-                res_block(vs, x, filter_size=filter_size, stride=2, name=f"resnet_{lvl}_downsample", **kw))
+                block(vs, x, filter_size=filter_size, stride=2, name=f"resnet_{lvl}_downsample", **kw))
         for i in range(nr_res_blocks):
             x = tap(f"resnet_{lvl}_{i}",
-                    res_block(vs, x, filter_size=filter_size, name=f"resnet_{lvl}_{i}", **kw))
+                    block(vs, x, filter_size=filter_size, name=f"resnet_{lvl}_{i}", **kw))
     for k in (1, 2, 3, 4):
         filter_size = int(filter_size / 2)
         x = tap(f"up_conv_{k}", transpose_conv_layer(vs, x, 3, 2, filter_size, f"up_conv_{k}"))
         for i in range(nr_res_blocks):
             x = tap(f"resnet_up_{k}_{i}",
-                    res_block(vs, x, a=a[-k] if i == 0 else None, filter_size=filter_size,
+                    block(vs, x, a=a[-k] if i == 0 else None, filter_size=filter_size,
                               name=f"resnet_up_{k}_{i}", **kw))
     x = conv_layer(vs, x, 3, 1, 2, "last_conv")
     return torch.tanh(x)
 
 
 def inference(vs, boundary, keep_prob, nr_res_blocks=1, nonlinearity="concat_elu",
-              gated_res=True, filter_size=8, gen=None, taps=None):
+              gated_res=True, filter_size=8, gen=None, taps=None, dropout_seed=None):
     """flow_net.py:33-37 with FLAGS.model == 'res' and the model flags as keywords."""
     return conv_res(vs, boundary, nr_res_blocks=nr_res_blocks, keep_prob=keep_prob,
                     nonlinearity_name=nonlinearity, gated=gated_res, filter_size=filter_size,
-                    gen=gen, taps=taps)
+                    gen=gen, taps=taps, dropout_seed=dropout_seed)
 
 
 def loss_image(sflow_p, sflow):
