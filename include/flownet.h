@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FN_ABI_VERSION 4
+#define FN_ABI_VERSION 5
 
 /* error codes (negative) */
 #define FN_E_INVAL      (-1)   /* null pointer, bad enum, non-positive dim */
@@ -161,6 +161,26 @@ int fn_tconv_fwd_has_tcgen05(const fn_tconv_desc* d);
 int64_t fn_conv_weights_tc_bytes(int32_t ksize, int32_t Keff, int32_t Kskip, int32_t Cout, int32_t gated);
 int fn_pack_conv_weights_tc(const void* w, const void* w_skip, void* dst, int32_t ksize,
                             int32_t Keff, int32_t Kskip, int32_t Cout, int32_t gated, void* stream);
+
+/* The whole 8x16 level of the default network in ONE launch (csrc/conv_l5.cu): res_block "resnet_5_downsample"
+ * (stride 2), res_block "resnet_5_0" and transpose_conv_layer "up_conv_1" -- flow_architecture.py:207-215 with the
+ * reference's flags (nr_res_blocks 1, gated, concat_elu, keep_prob 1) at the 128x256 grid, where an image is one
+ * 128-pixel tile at this level and the activations stay in shared memory between the five convolutions.
+ *   x: bf16 [B,16,32,64] (output of "resnet_4_0")  ->  y: bf16 [B,16,32,64] (output of "up_conv_1")
+ *   w_stream: the tensor-core images (fn_pack_conv_weights_tc) of resnet_5_downsample_conv_1 / _conv_2,
+ *             resnet_5_0_conv_1 / _conv_2 and up_conv_1 ([9,128,64] GEMM-B form), back to back: fn_level5_weight_bytes()
+ *   bias:     fp32 [128 | 256 | 128 | 256 | 64], the five bias vectors back to back
+ * Inference only; any other shape: FN_E_UNSUPPORTED (the layer-by-layer calls above are the general path). */
+typedef struct fn_level5_desc {
+  int32_t B, H, W, C;       /* input: H = 16, W = 32, C = 64 */
+  const void*  x;
+  const void*  w_stream;
+  const float* bias;
+  void*        y;
+} fn_level5_desc;
+int64_t fn_level5_weight_bytes(void);
+int fn_level5_supported(int32_t H, int32_t W, int32_t C);
+int fn_level5_fwd(const fn_level5_desc* d, void* stream);
 
 /* standalone nonlinearity (the public concat_elu()/set_nonlinearity() API) :14-29
  * x: bf16 [n, C] -> y: bf16 [n, C or 2C] */

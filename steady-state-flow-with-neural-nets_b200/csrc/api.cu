@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace fn {
 
@@ -55,6 +56,8 @@ int cast(const TI* x, TO* y, long long n, cudaStream_t s);
 int l2_loss(const float* p, const float* t, float* loss, float* grad, long long n, cudaStream_t s);
 int adam_step(float* param, const float* grad, float* m, float* v, long long n, long long step, double lr, double b1,
               double b2, double eps, cudaStream_t s);
+int level5_fwd(const fn_level5_desc& d, cudaStream_t stream);      // conv_l5.cu
+long long level5_weight_bytes();
 
 static int validate_conv(const fn_conv_desc& d) {
   FN_REQUIRE(d.B > 0 && d.H > 0 && d.W > 0 && d.Cin > 0 && d.Cout > 0, FN_E_INVAL,
@@ -186,6 +189,17 @@ int fn_pack_conv_weights_tc(const void* w, const void* w_skip, void* dst, int32_
                             int32_t Cout, int32_t gated, void* stream) {
   FN_REQUIRE(w && dst, FN_E_INVAL, "fn_pack_conv_weights_tc: null w/dst");
   return pack_conv_weights_tc(w, w_skip, dst, ksize, Keff, Kskip, Cout, gated, (cudaStream_t)stream);
+}
+
+int64_t fn_level5_weight_bytes(void) { return level5_weight_bytes(); }
+int fn_level5_supported(int32_t H, int32_t W, int32_t C) { return (H == 16 && W == 32 && C == 64 && tma::get_encode() != nullptr) ? 1 : 0; }
+int fn_level5_fwd(const fn_level5_desc* d, void* stream) {
+  FN_REQUIRE(d != nullptr, FN_E_INVAL, "fn_level5_fwd: null descriptor");
+  FN_REQUIRE(d->B > 0 && d->x && d->w_stream && d->bias && d->y, FN_E_INVAL, "fn_level5_fwd: null pointer or B = %d", d->B);
+  FN_REQUIRE(d->H == 16 && d->W == 32 && d->C == 64, FN_E_UNSUPPORTED,
+             "fn_level5_fwd: built for the 128x256 grid's level-5 input [B,16,32,64], got [B,%d,%d,%d]", d->H, d->W, d->C);
+  FN_REQUIRE(aligned16(d->x) && aligned16(d->y) && aligned16(d->w_stream), FN_E_ALIGN, "fn_level5_fwd: x/y/w_stream must be 16-byte aligned");
+  return level5_fwd(*d, (cudaStream_t)stream);
 }
 
 int fn_nonlinearity(const void* x, void* y, int64_t n, int32_t C, int32_t kind, void* stream) {

@@ -1,0 +1,431 @@
+// The whole 8x16 level of flow_net in ONE launch: res_block "resnet_5_downsample" (stride-2 conv_1, gated conv_2 with the
+// pooled / front-padded shortcut), res_block "resnet_5_0" and the transposed conv "up_conv_1"
+// (reference flow_architecture.py:207-215 at the 128x256 grid: x4 [B,16,32,64] -> [B,8,16,128] x 4 convs -> [B,16,32,64]).
+//
+// Why: at this level an image is 128 pixels = ONE M=128 UMMA tile with nothing but zero padding around it, so no CTA ever
+// needs another CTA's pixels.  Layer by layer the five launches cost 115 us at batch 64 (r5_down.conv_1 and up_conv_1 on
+// the generic kernel at 0.05 of their roofline, every launch paying the 6-13 us floor, the tensor pipe 20 % busy).  Here
+// one CTA carries one image through all five convolutions with the activations resident in shared memory:
+//
+//   warp 8      producer   streams the five packed weight images (3.39 MB, one contiguous buffer) through a 2 x 32 KB
+//                          ring (cp.async.bulk + mbarrier), running ahead across stage boundaries
+//   warps 0-7   workers    build the A planes of the next stage, warp 0 elects one lane to issue that stage's
+//                          unrolled tcgen05.mma program (M = 128, N = 128 / 256 / 4 x 64, fp32 accumulators in TMEM),
+//                          then all eight warps run the epilogue: TMEM -> bias / gate / shortcut -> bf16 ->
+//                          [elu(x) | elu(-x)] planes of the NEXT stage, written straight from registers
+//
+// The stages see exactly the operands the separate launches see (every intermediate is rounded to bf16 where it would
+// have been stored), in the same MMA order, so the result is the same up to fused-multiply-add contraction.
+// Tile orientation: TMEM lane r = 8 x + y (8 rows of the image per UMMA row group), planes [plane][x + 1][y + 1][8].
+#include <cuda.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tma.cuh"
+
+namespace fn {
+using namespace tma;
+namespace l5 {
+
+constexpr int THREADS = 288;
+constexpr int NST = 2, CHUNK = 32768;
+constexpr int HDR = 4096;                      // [0,64) mbarriers, [256] TMEM base, [512, 512 + 832*4) biases
+constexpr int C4 = 64, C5 = 128, IH = 16, IW = 32, OH5 = 8, OW5 = 16;
+// stage 1 operand: the four (row, column)-parity sub-planes of concat_elu(x4), each [16 planes][17 x][9 y][8]
+constexpr int PU1 = 9, PV1 = 17, P1 = PU1 * PV1;                 // 153 = 1 (mod 8): conflict-free plane stride
+constexpr int SUB1_BYTES = 16 * P1 * 16;
+// stages 2-5 operand: [32 planes][18 x][10 y][8] with a zero border (TF 'SAME'), plane stride padded to 1 (mod 8)
+constexpr int PU = 10, PV = 18, P = PU * PV, PPAD = 185;
+constexpr int PLANES_BYTES = 32 * PPAD * 16;
+constexpr int OFF_RING = HDR;
+constexpr int OFF_A = OFF_RING + NST * CHUNK;
+constexpr int OFF_R1 = OFF_A + PLANES_BYTES;                    // raw block output of resnet_5_downsample [128 px][128 ch], 16-byte units swizzled
+constexpr int SMEM = OFF_A + 4 * SUB1_BYTES;
+static_assert(OFF_R1 + 128 * 256 <= SMEM, "shortcut copy must fit behind the planes");
+// biases, floats: conv_1 down, conv_2 down (v half pre-halved), conv_1, conv_2 (v half pre-halved), up_conv
+constexpr int B1 = 0, B2 = 128, B3 = 384, B4 = 512, B5 = 768, NBIAS = 832;
+// weight stream, bytes per stage
+constexpr int W1 = 72 * 128 * 32, W2 = 144 * 256 * 32, W3 = 144 * 128 * 32, W4 = 144 * 256 * 32, W5 = 72 * 64 * 32;
+__host__ __device__ constexpr int chunks_of(int bytes) { return (bytes + CHUNK - 1) / CHUNK; }
+constexpr int G1 = 0, G2 = G1 + chunks_of(W1), G3 = G2 + chunks_of(W2), G4 = G3 + chunks_of(W3), G5 = G4 + chunks_of(W4),
+              GEND = G5 + chunks_of(W5);
+
+enum { SB_FULL = 0, SB_EMPTY = 2, SB_TF = 4 };
+
+struct Params {
+  const __nv_bfloat16* x;       // [B,16,32,64]
+  const unsigned char* wstream; // the five tensor-core weight images back to back
+  const float* bias;            // [832]
+  __nv_bfloat16* y;             // [B,16,32,64]
+  int* status;
+  int B;
+};
+
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void lds_f8(uint32_t addr, float (&f)[8]) {
+  const uint4 a = lds128(addr), b = lds128(addr + 16u);
+  f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+  f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&o)[8]) {
+  bf16x8 st;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) st.h[i] = __float2bfloat16(o[i]);
+  return st.v;
+}
+
+__global__ void __launch_bounds__(THREADS) k_level5(const __grid_constant__ Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = ptx::smem_u32(smem);
+  auto bar = [&](int i) { return sbase + 8u * (uint32_t)i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 256);
+  float* sbias = reinterpret_cast<float*>(smem + 512);
+  const uint32_t sb = sbase + 512u;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int tid = threadIdx.x;
+  const int b = (int)blockIdx.x;
+
+  if (warp == 8) {
+    ptx::tmem_alloc(sbase + 256, 256u);
+    ptx::tmem_relinquish();
+    if (lane == 0) {
+      for (int s = 0; s < NST; ++s) {
+        ptx::mbar_init(bar(SB_FULL + s), 1);
+        ptx::mbar_init(bar(SB_EMPTY + s), 1);
+      }
+      ptx::mbar_init(bar(SB_TF), 1);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+  }
+  for (int i = tid; i < NBIAS; i += THREADS) {
+    float bv = __ldg(p.bias + i);
+    if ((i >= B2 + C5 && i < B3) || (i >= B4 + C5 && i < B5)) bv *= 0.5f;      // sigmoid(z) = 0.5 + 0.5 tanh(z / 2)
+    sbias[i] = bv;
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  bool ok = true;
+
+  if (warp == 8) {
+    // =========================== producer: the weight stream ===========================
+    if (lane == 0) {
+      const int stage_bytes[5] = {W1, W2, W3, W4, W5};
+      int gc = 0;
+      size_t off = 0;
+      for (int st = 0; st < 5 && ok; ++st) {
+        for (int rem = stage_bytes[st]; rem > 0 && ok; ++gc) {
+          const int bytes = rem < CHUNK ? rem : CHUNK;
+          const int s = gc % NST;
+          if (gc >= NST) {
+            ok = ptx::mbar_wait(bar(SB_EMPTY + s), (uint32_t)(((gc / NST) - 1) & 1));
+            if (!ok) { atomicCAS(p.status, 0, 51); break; }
+          }
+          ptx::mbar_arrive_expect_tx(bar(SB_FULL + s), (uint32_t)bytes);
+          ptx::bulk_g2s(sbase + OFF_RING + s * CHUNK, p.wstream + off, (uint32_t)bytes, bar(SB_FULL + s));
+          off += (size_t)bytes;
+          rem -= bytes;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== workers ===========================
+    const uint32_t leader = ptx::elect_one();
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;                      // accumulator row == TMEM lane
+    const int py = r & 7, px = r >> 3;                // pixel (y, x) of the 8 x 16 image
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t A = sbase + OFF_A;
+    const uint32_t pp16 = (uint32_t)((px + 1) * PU + (py + 1)) * 16u;        // this pixel inside a stage-2..5 plane
+    const uint32_t r1_row = sbase + OFF_R1 + (uint32_t)r * 256u;
+    uint32_t tf_par = 0;
+
+    // wait for weight chunk gc, return its B descriptor template (N given by the caller through lbo)
+    auto chunk_ready = [&](int gc, uint32_t lbo) -> uint64_t {
+      const int s = gc % NST;
+      ok = ok && ptx::mbar_wait(bar(SB_FULL + s), (uint32_t)((gc / NST) & 1));
+      if (!ok) atomicCAS(p.status, 0, 52);
+      ptx::tc_fence_after_sync();
+      return ptx::smem_desc(sbase + OFF_RING + s * CHUNK, lbo, 128);
+    };
+    auto stage_done = [&]() {       // everybody: this stage's accumulators are complete
+      ok = ok && ptx::mbar_wait(bar(SB_TF), tf_par);
+      if (!ok) atomicCAS(p.status, 0, 53);
+      tf_par ^= 1u;
+      ptx::tc_fence_after_sync();
+    };
+    auto planes_ready = [&]() {     // everybody: A planes written, TMEM drained -> the issuer may go on
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before_sync();
+      worker_barrier();
+    };
+
+    // ---- stage 1 operand: x4 -> concat_elu -> parity sub-planes (row 16 / column 32 are TF's zero padding)
+    {
+      const __nv_bfloat16* xb = p.x + (size_t)b * IH * IW * C4;
+      constexpr int ITEMS = (IH + 1) * (IW + 1) * 8;
+      for (int base = tid; base < ITEMS; base += 256 * 4) {
+        uint4 in[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int idx = base + 256 * k;
+          const int ch = idx & 7, sp = idx >> 3;
+          const int h = sp / (IW + 1), w = sp - h * (IW + 1);
+          in[k] = make_uint4(0u, 0u, 0u, 0u);
+          if (idx < ITEMS && h < IH && w < IW) in[k] = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)h * IW + w) * C4 + ch * 8));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int idx = base + 256 * k;
+          if (idx >= ITEMS) break;
+          const int ch = idx & 7, sp = idx >> 3;
+          const int h = sp / (IW + 1), w = sp - h * (IW + 1);
+          uint4 o0, o1;
+          concat_elu8(in[k], o0, o1);
+          const uint32_t d0 = A + (uint32_t)(((h & 1) * 2 + (w & 1)) * SUB1_BYTES) + (uint32_t)(ch * P1 + (w >> 1) * PU1 + (h >> 1)) * 16u;
+          sts128(d0, o0);
+          sts128(d0 + (uint32_t)(8 * P1 * 16), o1);
+        }
+      }
+    }
+    planes_ready();
+
+    // ---- stage 1 MMAs: stride-2 conv, K = 9 x 128, N = 128
+    if (warp == 0) {
+      ptx::tc_fence_after_sync();
+      constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, 128);
+      const uint64_t a_tmpl = ptx::smem_desc(A, P1 * 16, PU1 * 16);
+#pragma unroll
+      for (int c = 0; c < chunks_of(W1); ++c) {
+        const uint64_t b_chunk = chunk_ready(G1 + c, 128 * 16);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ks = c * 8 + i, tap = ks >> 3, kk = ks & 7;
+          const int di = tap / 3, dj = tap % 3;
+          const uint32_t a_off = (uint32_t)(((di & 1) * 2 + (dj & 1)) * SUB1_BYTES + ((dj >> 1) * PU1 + (di >> 1)) * 16 + kk * 2 * P1 * 16) >> 4;
+          if (leader) ptx::mma_bf16_ss(tmem_base, a_tmpl + a_off, b_chunk + (uint32_t)((i * 128 * 32) >> 4), idesc, ks ? 1u : 0u);
+        }
+        if (leader) ptx::mma_commit(bar(SB_EMPTY + (G1 + c) % NST));
+      }
+      if (leader) ptx::mma_commit(bar(SB_TF));
+      __syncwarp();
+    }
+    stage_done();
+
+    // ---- epilogue of a plain conv (N = 128): acc + bias -> bf16 -> [elu | elu(-.)] planes of the next stage
+    auto epilogue_plain = [&](int boff) {
+#pragma unroll 2
+      for (int g = 0; g < 8; ++g) {
+        const int c0 = half * 64 + g * 8;
+        float o[8], bv[8];
+        lds_f8(sb + 4u * (uint32_t)(boff + c0), bv);
+        ptx::tmem_ld8(lane_base + (uint32_t)c0, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += bv[i];
+        uint4 o0, o1;
+        concat_elu8(pack8(o), o0, o1);
+        const uint32_t d0 = A + (uint32_t)((c0 >> 3) * PPAD * 16) + pp16;
+        sts128(d0, o0);
+        sts128(d0 + (uint32_t)(16 * PPAD * 16), o1);
+      }
+    };
+    // the zero border of the stage-2..5 planes (the region held stage 1's sub-planes until now)
+    for (int idx = tid; idx < P * 32; idx += 256) {
+      const int pl = idx / P, pp = idx - pl * P;
+      const int pv = pp / PU, pu = pp - pv * PU;
+      if (pu == 0 || pu == PU - 1 || pv == 0 || pv == PV - 1) sts128(A + (uint32_t)(pl * PPAD + pp) * 16u, make_uint4(0u, 0u, 0u, 0u));
+    }
+    epilogue_plain(B1);
+    planes_ready();
+
+    // ---- MMAs of a stride-1 3x3 conv on the 256-channel concat planes (stages 2, 3, 4)
+    auto issue_s1 = [&](auto nconst, int g0) {
+      constexpr int N = decltype(nconst)::value;
+      constexpr int SPC = CHUNK / (N * 32);
+      constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, N);
+      ptx::tc_fence_after_sync();
+      const uint64_t a_tmpl = ptx::smem_desc(A, PPAD * 16, PU * 16);
+#pragma unroll
+      for (int c = 0; c < 144 / SPC; ++c) {
+        const uint64_t b_chunk = chunk_ready(g0 + c, N * 16);
+#pragma unroll
+        for (int i = 0; i < SPC; ++i) {
+          const int ks = c * SPC + i, tap = ks >> 4, kk = ks & 15;
+          const int di = tap / 3, dj = tap % 3;
+          const uint32_t a_off = (uint32_t)((dj * PU + di) * 16 + kk * 2 * PPAD * 16) >> 4;
+          if (leader) ptx::mma_bf16_ss(tmem_base, a_tmpl + a_off, b_chunk + (uint32_t)((i * N * 32) >> 4), idesc, ks ? 1u : 0u);
+        }
+        if (leader) ptx::mma_commit(bar(SB_EMPTY + (g0 + c) % NST));
+      }
+      if (leader) ptx::mma_commit(bar(SB_TF));
+      __syncwarp();
+    };
+    using N128 = std::integral_constant<int, 128>;
+    using N256 = std::integral_constant<int, 256>;
+
+    // ---- stage 2: conv_2 of the down block, gate, shortcut = 2x2 average pool of x4 in the LAST 64 channels
+    if (warp == 0) issue_s1(N256{}, G2);
+    stage_done();
+    {
+      const __nv_bfloat16* xb = p.x + (size_t)b * IH * IW * C4;
+#pragma unroll 1
+      for (int g = 0; g < 8; ++g) {
+        const int c0 = half * 64 + g * 8;
+        float a[8], gt[8], bu[8], bv[8], o[8];
+        lds_f8(sb + 4u * (uint32_t)(B2 + c0), bu);
+        lds_f8(sb + 4u * (uint32_t)(B2 + C5 + c0), bv);
+        ptx::tmem_ld8x2(lane_base + (uint32_t)c0, lane_base + (uint32_t)(C5 + c0), a, gt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float th = tanh_approx(fmaf(gt[i], 0.5f, bv[i]));
+          o[i] = (a[i] + bu[i]) * fmaf(th, 0.5f, 0.5f);
+        }
+        if (c0 >= C5 - C4) {             // front channel pad (reference :158-163): channels 64.. take the pooled x4
+          const __nv_bfloat16* r00 = xb + ((size_t)(2 * py) * IW + 2 * px) * C4 + (c0 - (C5 - C4));
+          bf16x8 q4[4];
+          q4[0].v = __ldg(reinterpret_cast<const uint4*>(r00));
+          q4[1].v = __ldg(reinterpret_cast<const uint4*>(r00 + C4));
+          q4[2].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)IW * C4));
+          q4[3].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)IW * C4 + C4));
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            o[i] += 0.25f * (__bfloat162float(q4[0].h[i]) + __bfloat162float(q4[1].h[i]) + __bfloat162float(q4[2].h[i]) +
+                             __bfloat162float(q4[3].h[i]));
+        }
+        const uint4 raw = pack8(o);
+        sts128(r1_row + (uint32_t)(((c0 >> 3) ^ (r & 7)) * 16), raw);           // kept for stage 4's shortcut
+        uint4 o0, o1;
+        concat_elu8(raw, o0, o1);
+        const uint32_t d0 = A + (uint32_t)((c0 >> 3) * PPAD * 16) + pp16;
+        sts128(d0, o0);
+        sts128(d0 + (uint32_t)(16 * PPAD * 16), o1);
+      }
+    }
+    planes_ready();
+
+    // ---- stage 3: conv_1 of resnet_5_0
+    if (warp == 0) issue_s1(N128{}, G3);
+    stage_done();
+    epilogue_plain(B3);
+    planes_ready();
+
+    // ---- stage 4: conv_2 of resnet_5_0, gate, shortcut = the block input kept in shared memory; the result feeds the
+    // transposed conv RAW (no nonlinearity, reference :213): 16 planes
+    if (warp == 0) issue_s1(N256{}, G4);
+    stage_done();
+#pragma unroll 1
+    for (int g = 0; g < 8; ++g) {
+      const int c0 = half * 64 + g * 8;
+      float a[8], gt[8], bu[8], bv[8], o[8];
+      lds_f8(sb + 4u * (uint32_t)(B4 + c0), bu);
+      lds_f8(sb + 4u * (uint32_t)(B4 + C5 + c0), bv);
+      ptx::tmem_ld8x2(lane_base + (uint32_t)c0, lane_base + (uint32_t)(C5 + c0), a, gt);
+      bf16x8 rv;
+      rv.v = lds128(r1_row + (uint32_t)(((c0 >> 3) ^ (r & 7)) * 16));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float th = tanh_approx(fmaf(gt[i], 0.5f, bv[i]));
+        // product and shortcut add rounded separately, as in the layer-by-layer kernels
+        o[i] = __fadd_rn(__fmul_rn(a[i] + bu[i], fmaf(th, 0.5f, 0.5f)), __bfloat162float(rv.h[i]));
+      }
+      sts128(A + (uint32_t)((c0 >> 3) * PPAD * 16) + pp16, pack8(o));
+    }
+    planes_ready();
+
+    // ---- stage 5: transposed conv as four output phases, K = 128 per tap, N = 64 each
+    if (warp == 0) {
+      ptx::tc_fence_after_sync();
+      constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, 64);
+      const uint64_t a_tmpl = ptx::smem_desc(A, PPAD * 16, PU * 16);
+#pragma unroll
+      for (int c = 0; c < chunks_of(W5); ++c) {
+        const uint64_t b_chunk = chunk_ready(G5 + c, 64 * 16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int ks = c * 16 + i;
+          if (ks < 72) {
+            const int tap = ks >> 3, kk = ks & 7;
+            const int di = tap / 3, dj = tap % 3;
+            // out[2m + p] takes tap d = p from in[m] and, for p = 0, tap d = 2 from in[m - 1]
+            const uint32_t a_off = (uint32_t)((((dj == 2) ? 0 : 1) * PU + ((di == 2) ? 0 : 1)) * 16 + kk * 2 * PPAD * 16) >> 4;
+            const int ph = ((di == 1) ? 2 : 0) + ((dj == 1) ? 1 : 0);
+            const bool first = (tap == 0 || tap == 1 || tap == 3 || tap == 4) && kk == 0;
+            if (leader) ptx::mma_bf16_ss(tmem_base + (uint32_t)(ph * 64), a_tmpl + a_off, b_chunk + (uint32_t)((i * 64 * 32) >> 4), idesc,
+                                         first ? 0u : 1u);
+          }
+        }
+        if (leader) ptx::mma_commit(bar(SB_EMPTY + (G5 + c) % NST));
+      }
+      if (leader) ptx::mma_commit(bar(SB_TF));
+      __syncwarp();
+    }
+    stage_done();
+    {
+      __nv_bfloat16* yb = p.y + (size_t)b * IH * IW * C4;
+#pragma unroll 1
+      for (int ph = 0; ph < 4; ++ph) {
+        const int oy = 2 * py + (ph >> 1), ox = 2 * px + (ph & 1);
+        __nv_bfloat16* dst = yb + ((size_t)oy * IW + ox) * C4;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int c0 = half * 32 + g * 8;
+          float o[8], bv[8];
+          lds_f8(sb + 4u * (uint32_t)(B5 + c0), bv);
+          ptx::tmem_ld8(lane_base + (uint32_t)(ph * 64 + c0), o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += bv[i];
+          if (ok) *reinterpret_cast<uint4*>(dst + c0) = pack8(o);
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 256u);
+  }
+}
+
+}  // namespace l5
+
+int* tc_status_word();   // conv_tc.cu
+
+int level5_fwd(const fn_level5_desc& d, cudaStream_t stream) {
+  using namespace l5;
+  Params p;
+  p.x = (const __nv_bfloat16*)d.x;
+  p.wstream = (const unsigned char*)d.w_stream;
+  p.bias = d.bias;
+  p.y = (__nv_bfloat16*)d.y;
+  p.status = tc_status_word();
+  if (p.status == nullptr) return (int)cudaErrorMemoryAllocation;
+  p.B = d.B;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_level5, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(level5): %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  k_level5<<<d.B, THREADS, SMEM, stream>>>(p);
+  count_launch();
+  note_tcgen05(true);
+  return check_launch("k_level5");
+}
+
+long long level5_weight_bytes() { return (long long)l5::W1 + l5::W2 + l5::W3 + l5::W4 + l5::W5; }
+
+}  // namespace fn

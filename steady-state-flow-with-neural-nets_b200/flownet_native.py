@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FLOWNET_LIB", os.path.join(_HERE, "libflownet.so"))   # override: A/B builds
 
-FN_ABI_VERSION = 4
+FN_ABI_VERSION = 5
 # enum fn_prologue
 PRO_NONE, PRO_CONCAT_ELU, PRO_ELU, PRO_CONCAT_RELU, PRO_RELU = 0, 1, 2, 3, 4
 # enum fn_epilogue
@@ -48,6 +48,11 @@ class LbmDesc(C.Structure):
     ]
 
 
+class Level5Desc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+                ("x", C.c_void_p), ("w_stream", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p)]
+
+
 class TConvDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
@@ -74,6 +79,9 @@ SYMBOLS = [
     ("fn_tconv_fwd_has_tcgen05", C.c_int, [C.POINTER(TConvDesc)]),
     ("fn_conv_weights_tc_bytes", C.c_int64, [C.c_int32] * 5),
     ("fn_pack_conv_weights_tc", C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    ("fn_level5_weight_bytes", C.c_int64, []),
+    ("fn_level5_supported", C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    ("fn_level5_fwd", C.c_int, [C.POINTER(Level5Desc), _P]),
     ("fn_nonlinearity", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     ("fn_cast_f32_to_bf16", C.c_int, [_P, _P, C.c_int64, _P]),
     ("fn_cast_u8_to_bf16", C.c_int, [_P, _P, C.c_int64, _P]),
@@ -216,6 +224,21 @@ def tconv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, impl=IMPL_AUTO, w_tc=None, e
     if query:
         return bool(lib.fn_tconv_fwd_has_tcgen05(C.byref(d)))
     _check(lib.fn_tconv_fwd(C.byref(d), stream_ptr()), "fn_tconv_fwd")
+
+
+def level5_supported(H, W, Cc):
+    return bool(lib.fn_level5_supported(int(H), int(W), int(Cc)))
+
+
+def level5_fwd(x, w_stream, bias, y):
+    """x: bf16 [B,16,32,64] -> y: bf16 [B,16,32,64]: the 8x16 level in one launch (fn_level5_fwd)"""
+    _require_cuda(x, w_stream, bias, y)
+    if w_stream.numel() * w_stream.element_size() != int(lib.fn_level5_weight_bytes()) or bias.numel() != 832:
+        raise ValueError("level5_fwd: weight stream / bias size")
+    d = Level5Desc()
+    d.B, d.H, d.W, d.C = x.shape
+    d.x, d.w_stream, d.bias, d.y = x.data_ptr(), w_stream.data_ptr(), bias.data_ptr(), y.data_ptr()
+    _check(lib.fn_level5_fwd(C.byref(d), stream_ptr()), "fn_level5_fwd")
 
 
 def pack_conv_weights_tc(w, w_skip, ksize, Keff, Kskip, Cout, gated):

@@ -353,6 +353,54 @@ def _res_block_unfused(x, a, filter_size, nonlinearity, keep_p, stride, gated, n
     raise ValueError("res_block: only the reference's four nonlinearities (set_nonlinearity) are supported")
 
 
+# --------------------------------------------------------------------------- the 8x16 level in one launch
+LEVEL5_FUSED = os.environ.get("FLOWNET_L5", "1") != "0"
+
+
+def _level5_fusable(x, nr_res_blocks, keep_prob, nonlinearity, gated, filter_size):
+    """fn_level5_fwd takes the reference's flags at the 128x256 grid (x = resnet_4_0's output [B,16,32,64]) in inference."""
+    return (LEVEL5_FUSED and TAPE is None and IMPL == native.IMPL_AUTO and nr_res_blocks == 1 and keep_prob >= 1.0 and
+            nonlinearity is concat_elu and gated and filter_size == 128 and
+            native.level5_supported(x.shape[1], x.shape[2], x.shape[3]))
+
+
+def _level5_fused(x):
+    """resnet_5_downsample, resnet_5_0 and up_conv_1 (reference :207-215).  Variables are created in the reference's
+    order; the five tensor-core weight images and biases are concatenated once per variable version."""
+    dev = x.device
+    names = ("resnet_5_downsample_conv_1_conv", "resnet_5_downsample_conv_2_conv", "resnet_5_0_conv_1_conv",
+             "resnet_5_0_conv_2_conv")
+    shapes = ((128, 128, False), (256, 256, True), (256, 128, False), (256, 256, True))
+    parts = [_conv_weights(n, 3, k, c, dev, gated=g) for n, (k, c, g) in zip(names, shapes)]
+    scope = "up_conv_1_trans_conv"
+    wt = _variable(scope + '/weights', [3, 3, 64, 128], device=dev)
+    bt = _variable(scope + '/biases', [64], device=dev)
+
+    def make_t():
+        w16 = wt.permute(0, 1, 3, 2).reshape(9, 128, 64).to(torch.bfloat16).contiguous()
+        return w16, bt.contiguous(), native.pack_conv_weights_tc(w16, None, 3, 128, 0, 64, False)
+
+    tpart = VARIABLES.derived(("tconv", scope), make_t)
+
+    def make():
+        wstream = torch.cat([pt[3] for pt in parts] + [tpart[2]])
+        bias = torch.cat([pt[2] for pt in parts] + [tpart[1]]).to(torch.float32).contiguous()
+        return wstream, bias
+
+    wstream, bias = VARIABLES.derived(("level5",), make)
+    x = native.to_bf16(x)
+    B = x.shape[0]
+    y = torch.empty((B, 16, 32, 64), device=dev, dtype=torch.bfloat16)
+    rec = None
+    if _PROFILE is not None:
+        # algorithmic bytes: x read by the stride-2 conv and by the pooled shortcut counts once, y once; flops: the five convs
+        macs = B * 128 * (9 * 128 * 128 + 9 * 256 * 256 + 9 * 256 * 128 + 9 * 256 * 256 + 9 * 128 * 64)
+        rec = dict(name="level5_fused(resnet_5_downsample+resnet_5_0+up_conv_1)", kind="fused", out_hw=(16, 32), K_tap=256, N=256,
+                   stride=1, alg_bytes=(x.numel() + y.numel()) * 2, flops=2 * macs)
+    _profiled(rec, lambda: native.level5_fwd(x, wstream, bias, y))
+    return y
+
+
 def conv_res(inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name='concat_elu', gated=True, filter_size=8,
              dropout_seed=0):
     """Builds conv part of net -- reference :167-248.
@@ -377,16 +425,24 @@ def conv_res(inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name='concat_e
     for i in range(nr_res_blocks):
         x = block(x, name="resnet_1_" + str(i))
     # res_2 .. res_5
+    fused5 = False
     for lvl in (2, 3, 4, 5):
         a.append(x)
         filter_size = 2 * filter_size
+        if lvl == 5 and _level5_fusable(x, nr_res_blocks, keep_prob, nonlinearity, gated, filter_size):
+            # the whole 8x16 level (down block, block, up_conv_1) in one launch: csrc/conv_l5.cu
+            x = _level5_fused(x)
+            seed[0] += 2                           # the two blocks it contains keep their dropout-seed numbers
+            fused5 = True
+            continue
         x = block(x, stride=2, name="resnet_%d_downsample" % lvl)
         for i in range(nr_res_blocks):
             x = block(x, name="resnet_%d_%d" % (lvl, i))
     # res_up_1 .. res_up_4
     for k in (1, 2, 3, 4):
         filter_size = int(filter_size / 2)
-        x = transpose_conv_layer(x, 3, 2, filter_size, "up_conv_%d" % k)
+        if not (k == 1 and fused5):
+            x = transpose_conv_layer(x, 3, 2, filter_size, "up_conv_%d" % k)
         for i in range(nr_res_blocks):
             x = block(x, a=a[-k] if i == 0 else None, name="resnet_up_%d_%d" % (k, i))
     # last_conv + tanh (reference :242-243), one launch

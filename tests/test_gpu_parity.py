@@ -473,6 +473,55 @@ def test_deeper_wider_variant_at_128x256_vs_oracle(native):
     assert rel_l2(y, ref) < NET_TOL
 
 
+@pytest.mark.parametrize("B", [1, 5, 150])
+def test_level5_fused_kernel_vs_layer_by_layer_and_oracle(native, B):
+    """csrc/conv_l5.cu: resnet_5_downsample + resnet_5_0 + up_conv_1 in one launch against the same five convolutions as
+    separate launches (same operands, same bf16 rounding points, same MMA order) and against the fp64 oracle on
+    bf16-rounded inputs."""
+    import model.flow_architecture as arch
+    arch.reset_variables(77)
+    g = torch.Generator().manual_seed(B)
+    x = torch.randn(B, 16, 32, 64, generator=g).to(torch.bfloat16)
+    xd = x.cuda()
+    conc = arch.concat_elu
+
+    def layers(xin):
+        t = arch.res_block(xin, filter_size=128, nonlinearity=conc, stride=2, gated=True, name="resnet_5_downsample")
+        t = arch.res_block(t, filter_size=128, nonlinearity=conc, gated=True, name="resnet_5_0")
+        return arch.transpose_conv_layer(t, 3, 2, 64, "up_conv_1")
+
+    y_ref = layers(xd)
+    assert arch._level5_fusable(xd, 1, 1.0, conc, True, 128)
+    y = arch._level5_fused(xd)
+    torch.cuda.synchronize()
+    assert native.tc_status() == 0
+    assert tuple(y.shape) == (B, 16, 32, 64)
+    assert rel_l2(y, y_ref) < 1e-3
+    if B <= 5:
+        vs = fo.VariableStore(77, torch.float64)
+        # same creation order as the device graph above -> same variables
+        xo = x.double()
+        t = fo.res_block(vs, xo, filter_size=128, stride=2, gated=True, name="resnet_5_downsample")
+        t = fo.res_block(vs, t, filter_size=128, gated=True, name="resnet_5_0")
+        ref = fo.transpose_conv_layer(vs, t, 3, 2, 64, "up_conv_1")
+        for k, v in vs.vars.items():
+            assert torch.equal(arch.global_variables()[k].cpu().double(), v), k
+        assert rel_l2(y, ref) < NET_TOL
+    arch.reset_variables(1234)
+
+
+def test_net_with_and_without_the_fused_level5_kernel(native):
+    import model.flow_architecture as arch
+    x = fo.synth_boundary(3, 128, 256, seed=12).astype(np.uint8)
+    y1 = _net(native, x, "auto")
+    try:
+        arch.LEVEL5_FUSED = False
+        y0 = _net(native, x, "auto")
+    finally:
+        arch.LEVEL5_FUSED = True
+    assert rel_l2(y1, y0) < 2e-3
+
+
 def test_compiled_inference_graph_matches_eager(native):
     import model.flow_architecture as arch
     import model.flow_net as flow_net
