@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FN_ABI_VERSION 5
+#define FN_ABI_VERSION 6
 
 /* error codes (negative) */
 #define FN_E_INVAL      (-1)   /* null pointer, bad enum, non-positive dim */
@@ -109,6 +109,15 @@ typedef struct fn_conv_desc {
   /* FN_EPI_PRO_BWD only */
   int32_t  adj_prologue;    /* enum fn_prologue of the nonlinearity being differentiated */
   int32_t  adj_accumulate;  /* 1: y += ... */
+  /* MMA-ready activations ("planes", inference fast path, csrc/conv_pl.cu).  The planes form of a raw tensor
+   * t = bf16 [B,H,W,C] is bf16 [B, 2C/8, H, W, 8] = concat_elu(t) (flow_architecture.py:14-17) in 8-channel groups:
+   * plane q < C/8 holds elu(t[..., 8q:8q+8]), plane C/8 + q holds elu(-t[..., 8q:8q+8]).  A producer's epilogue writes it
+   * once; the consuming convolution's tensor copies then land the tensor-core A operand in shared memory directly. */
+  int32_t  x_planes;        /* 1: x is given in planes form (prologue must be FN_PRO_CONCAT_ELU -- it has been applied);
+                                  stride 1, 3x3, Cin in {8,16,32}, keep_prob 1, FN_EPI_BIAS / FN_EPI_GATE_RES only */
+  int32_t  skip_planes;     /* 1: skip likewise (required with x_planes) */
+  void*    y_planes;        /* optional second output: concat_elu(y) in planes form [B, 2Cy/8, OH, OW, 8]; y may then be
+                                  NULL.  Taken by the planes kernel, the stride-2 tensor-core kernels and the 1-channel head */
 } fn_conv_desc;
 
 /* One transposed convolution launch: tf.nn.conv2d_transpose(k=3, s=2, 'SAME') + bias
@@ -131,6 +140,7 @@ typedef struct fn_tconv_desc {
   int32_t adj_accumulate;
   int32_t reserved;
   const void*  res;
+  void*        y_planes;    /* optional second output (FN_EPI_BIAS, tensor cores only): concat_elu(y) in planes form, see fn_conv_desc */
 } fn_tconv_desc;
 
 int         fn_abi_version(void);
@@ -177,6 +187,7 @@ typedef struct fn_level5_desc {
   const void*  w_stream;
   const float* bias;
   void*        y;
+  void*        y_planes;    /* optional: concat_elu(y) in planes form [B,16,16,32,8] (see fn_conv_desc) */
 } fn_level5_desc;
 int64_t fn_level5_weight_bytes(void);
 int fn_level5_supported(int32_t H, int32_t W, int32_t C);

@@ -62,7 +62,11 @@ long long level5_weight_bytes();
 static int validate_conv(const fn_conv_desc& d) {
   FN_REQUIRE(d.B > 0 && d.H > 0 && d.W > 0 && d.Cin > 0 && d.Cout > 0, FN_E_INVAL,
              "fn_conv_fwd: non-positive dimension (B=%d H=%d W=%d Cin=%d Cout=%d)", d.B, d.H, d.W, d.Cin, d.Cout);
-  FN_REQUIRE(d.x && d.w && d.bias && d.y, FN_E_INVAL, "fn_conv_fwd: null x/w/bias/y");
+  FN_REQUIRE(d.x && d.w && d.bias && (d.y || d.y_planes), FN_E_INVAL, "fn_conv_fwd: null x/w/bias/y");
+  FN_REQUIRE(aligned16(d.y_planes), FN_E_ALIGN, "fn_conv_fwd: y_planes must be 16-byte aligned");
+  if (d.x_planes || d.skip_planes)
+    FN_REQUIRE(d.x_planes && (!d.skip || d.skip_planes) && d.prologue == FN_PRO_CONCAT_ELU && d.impl != FN_IMPL_SIMT, FN_E_UNSUPPORTED,
+               "fn_conv_fwd: planes operands need x_planes (and skip_planes with a skip), the concat_elu prologue, tcgen05");
   FN_REQUIRE(d.ksize == 3 || d.ksize == 1, FN_E_UNSUPPORTED, "fn_conv_fwd: kernel size %d (only 1 and 3)", d.ksize);
   FN_REQUIRE(d.stride == 1 || d.stride == 2, FN_E_UNSUPPORTED, "fn_conv_fwd: stride %d (only 1 and 2)", d.stride);
   FN_REQUIRE(d.prologue >= FN_PRO_NONE && d.prologue <= FN_PRO_RELU, FN_E_INVAL, "fn_conv_fwd: bad prologue %d",
@@ -123,8 +127,13 @@ int fn_conv_fwd(const fn_conv_desc* d, void* stream) {
     note_tcgen05(true);
     return conv_fwd_tc(*d, s);
   }
-  FN_REQUIRE(d->impl != FN_IMPL_TCGEN05 && d->epilogue != FN_EPI_GATE_BWD && d->epilogue != FN_EPI_PRO_BWD, FN_E_UNSUPPORTED,
-             "fn_conv_fwd: no tcgen05 kernel for this shape: %s", why);
+  FN_REQUIRE(d->impl != FN_IMPL_TCGEN05 && d->epilogue != FN_EPI_GATE_BWD && d->epilogue != FN_EPI_PRO_BWD && !d->x_planes &&
+                 !d->skip_planes,
+             FN_E_UNSUPPORTED, "fn_conv_fwd: no tcgen05 kernel for this shape: %s", why);
+  if (d->y_planes || !d->y)     // CUDA cores: only the 1-channel head writes planes
+    FN_REQUIRE(d->Cin == 1 && (d->Cout == 8 || d->Cout == 16) && d->ksize == 3 && d->stride == 1 && d->epilogue == FN_EPI_BIAS &&
+                   d->prologue == FN_PRO_NONE && !d->skip && d->keep_prob >= 1.0f,
+               FN_E_UNSUPPORTED, "fn_conv_fwd: no kernel writes a planes output for this shape: %s", why);
   note_tcgen05(false);
   return conv_fwd_simt(*d, s);
 }
@@ -146,6 +155,8 @@ static int validate_tconv(const fn_tconv_desc* d) {
   FN_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, FN_E_INVAL,
              "fn_tconv_fwd: non-positive dimension");
   FN_REQUIRE(d->x && d->w && d->bias && d->y, FN_E_INVAL, "fn_tconv_fwd: null x/w/bias/y");
+  FN_REQUIRE(aligned16(d->y_planes) && !(d->y_planes && (d->epilogue != FN_EPI_BIAS || d->impl == FN_IMPL_SIMT)), FN_E_UNSUPPORTED,
+             "fn_tconv_fwd: y_planes needs 16-byte alignment, the bias epilogue and a tensor-core kernel");
   FN_REQUIRE((d->Cin % 8) == 0 && (d->Cout % 8) == 0, FN_E_ALIGN, "fn_tconv_fwd: Cin=%d Cout=%d must be multiples of 8",
              d->Cin, d->Cout);
   FN_REQUIRE(aligned16(d->x) && aligned16(d->y) && aligned16(d->w), FN_E_ALIGN, "fn_tconv_fwd: x/y/w must be 16-byte aligned");
@@ -167,7 +178,7 @@ int fn_tconv_fwd(const fn_tconv_desc* d, void* stream) {
     note_tcgen05(true);
     return tconv_fwd_tc(*d, s);
   }
-  FN_REQUIRE(d->impl != FN_IMPL_TCGEN05 && d->epilogue != FN_EPI_PRO_BWD, FN_E_UNSUPPORTED,
+  FN_REQUIRE(d->impl != FN_IMPL_TCGEN05 && d->epilogue != FN_EPI_PRO_BWD && !d->y_planes, FN_E_UNSUPPORTED,
              "fn_tconv_fwd: no tcgen05 kernel for this shape: %s", why);
   note_tcgen05(false);
   return tconv_fwd_simt(*d, s);

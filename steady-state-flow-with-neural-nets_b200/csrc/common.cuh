@@ -145,4 +145,60 @@ union bf16x8 {
   __nv_bfloat162 h2[4];
 };
 
+#ifdef __CUDACC__
+// ---- generic shortcut of a res_block (flow_architecture.py:153-165): v[0..8) += sc(res)[b, oy, ox, c0 .. c0+8) where sc is
+// the optional 2x2/2 'SAME' average pool followed by the FRONT channel pad from Cres to F channels.  The common case
+// (pooled, whole 8-channel groups, all four source pixels inside) is inline; everything else (ragged edges, odd channel
+// counts, un-pooled channel pads) is one out-of-line scalar routine, so that the tensor-core kernels do not carry a copy
+// of it per unrolled epilogue item -- their start-up is bound by instruction fetch.
+static __device__ __noinline__ void shortcut_add8_slow(const __nv_bfloat16* res, int Cres, int RH, int RW, int res_pool, int F, int b,
+                                                int oy, int ox, int c0, float* v) {
+  const int shift = F - Cres;
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    const int cr = c0 + j - shift;
+    if (cr < 0) continue;
+    if (res_pool) {
+      float s = 0.f;
+      int cnt = 0;
+      for (int a = 0; a < 2; ++a)
+        for (int c = 0; c < 2; ++c) {
+          const int ry = 2 * oy + a, rx = 2 * ox + c;
+          if (ry < RH && rx < RW) {
+            s += __bfloat162float(res[(((size_t)b * RH + ry) * RW + rx) * Cres + cr]);
+            ++cnt;
+          }
+        }
+      v[j] += s / (float)cnt;
+    } else {
+      v[j] += __bfloat162float(res[(((size_t)b * RH + oy) * RW + ox) * Cres + cr]);
+    }
+  }
+}
+__device__ __forceinline__ void shortcut_add8(const __nv_bfloat16* res, int Cres, int RH, int RW, int res_pool, int F, int b, int oy,
+                                              int ox, int c0, float (&v)[8]) {
+  const int shift = F - Cres;
+  if (res_pool && (Cres & 7) == 0 && ((c0 - shift) & 7) == 0 && 2 * oy + 1 < RH && 2 * ox + 1 < RW) {
+    if (c0 - shift < 0) return;             // front padding: nothing to add
+    const __nv_bfloat16* r00 = res + (((size_t)b * RH + 2 * oy) * RW + 2 * ox) * Cres + (c0 - shift);
+    bf16x8 q[4];
+    q[0].v = __ldg(reinterpret_cast<const uint4*>(r00));
+    q[1].v = __ldg(reinterpret_cast<const uint4*>(r00 + Cres));
+    q[2].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)RW * Cres));
+    q[3].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)RW * Cres + Cres));
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] += 0.25f * (__bfloat162float(q[0].h[j]) + __bfloat162float(q[1].h[j]) + __bfloat162float(q[2].h[j]) +
+                       __bfloat162float(q[3].h[j]));
+    return;
+  }
+  float t[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t[j] = v[j];
+  shortcut_add8_slow(res, Cres, RH, RW, res_pool, F, b, oy, ox, c0, t);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = t[j];
+}
+#endif
+
 }  // namespace fn

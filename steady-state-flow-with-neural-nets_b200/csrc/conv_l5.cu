@@ -59,6 +59,7 @@ struct Params {
   const unsigned char* wstream; // the five tensor-core weight images back to back
   const float* bias;            // [832]
   __nv_bfloat16* y;             // [B,16,32,64]
+  __nv_bfloat16* yp;            // optional planes form of y
   int* status;
   int B;
 };
@@ -122,18 +123,26 @@ __global__ void __launch_bounds__(THREADS) k_level5(const __grid_constant__ Para
     // =========================== producer: the weight stream ===========================
     if (lane == 0) {
       const int stage_bytes[5] = {W1, W2, W3, W4, W5};
+      constexpr size_t TOTAL = (size_t)W1 + W2 + W3 + W4 + W5;
+      // the stream is cold in L2 when the kernel starts (the rest of the network evicted it): keep PF_AHEAD bytes
+      // of it requested ahead of the ring, so that a chunk copy is an L2 hit
+      constexpr size_t PF_AHEAD = 16 * (size_t)CHUNK;
+      for (size_t o = 0; o < PF_AHEAD && o < TOTAL; o += CHUNK) ptx::prefetch_l2(p.wstream + o, (uint32_t)(TOTAL - o < CHUNK ? TOTAL - o : CHUNK));
+      const uint64_t pol = ptx::policy_evict_last();
       int gc = 0;
       size_t off = 0;
       for (int st = 0; st < 5 && ok; ++st) {
         for (int rem = stage_bytes[st]; rem > 0 && ok; ++gc) {
           const int bytes = rem < CHUNK ? rem : CHUNK;
           const int s = gc % NST;
+          if (off + PF_AHEAD < TOTAL)
+            ptx::prefetch_l2(p.wstream + off + PF_AHEAD, (uint32_t)(TOTAL - off - PF_AHEAD < CHUNK ? TOTAL - off - PF_AHEAD : CHUNK));
           if (gc >= NST) {
             ok = ptx::mbar_wait(bar(SB_EMPTY + s), (uint32_t)(((gc / NST) - 1) & 1));
             if (!ok) { atomicCAS(p.status, 0, 51); break; }
           }
           ptx::mbar_arrive_expect_tx(bar(SB_FULL + s), (uint32_t)bytes);
-          ptx::bulk_g2s(sbase + OFF_RING + s * CHUNK, p.wstream + off, (uint32_t)bytes, bar(SB_FULL + s));
+          ptx::bulk_g2s_hint(sbase + OFF_RING + s * CHUNK, p.wstream + off, (uint32_t)bytes, bar(SB_FULL + s), pol);
           off += (size_t)bytes;
           rem -= bytes;
         }
@@ -207,15 +216,17 @@ __global__ void __launch_bounds__(THREADS) k_level5(const __grid_constant__ Para
       ptx::tc_fence_after_sync();
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, 128);
       const uint64_t a_tmpl = ptx::smem_desc(A, P1 * 16, PU1 * 16);
-#pragma unroll
+      // one chunk = the 8 k-steps of one tap; the chunk loop stays a LOOP: the kernel runs its program once per CTA, so
+      // every unrolled instruction is an instruction-cache miss served from L2 / HBM (the code is cold at launch)
+#pragma unroll 1
       for (int c = 0; c < chunks_of(W1); ++c) {
         const uint64_t b_chunk = chunk_ready(G1 + c, 128 * 16);
+        const int di = c / 3, dj = c - 3 * di;
+        const uint64_t a_tap = a_tmpl + (uint64_t)((uint32_t)(((di & 1) * 2 + (dj & 1)) * SUB1_BYTES + ((dj >> 1) * PU1 + (di >> 1)) * 16) >> 4);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int ks = c * 8 + i, tap = ks >> 3, kk = ks & 7;
-          const int di = tap / 3, dj = tap % 3;
-          const uint32_t a_off = (uint32_t)(((di & 1) * 2 + (dj & 1)) * SUB1_BYTES + ((dj >> 1) * PU1 + (di >> 1)) * 16 + kk * 2 * P1 * 16) >> 4;
-          if (leader) ptx::mma_bf16_ss(tmem_base, a_tmpl + a_off, b_chunk + (uint32_t)((i * 128 * 32) >> 4), idesc, ks ? 1u : 0u);
+          if (leader) ptx::mma_bf16_ss(tmem_base, a_tap + (uint32_t)((i * 2 * P1 * 16) >> 4), b_chunk + (uint32_t)((i * 128 * 32) >> 4), idesc,
+                                       (c | i) ? 1u : 0u);
         }
         if (leader) ptx::mma_commit(bar(SB_EMPTY + (G1 + c) % NST));
       }
@@ -257,15 +268,17 @@ __global__ void __launch_bounds__(THREADS) k_level5(const __grid_constant__ Para
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, N);
       ptx::tc_fence_after_sync();
       const uint64_t a_tmpl = ptx::smem_desc(A, PPAD * 16, PU * 16);
-#pragma unroll
+      constexpr int CPT = 16 / SPC;            // chunks per tap (16 k-steps)
+#pragma unroll 1
       for (int c = 0; c < 144 / SPC; ++c) {
         const uint64_t b_chunk = chunk_ready(g0 + c, N * 16);
+        const int tap = c / CPT, kk0 = (c - tap * CPT) * SPC;
+        const int di = tap / 3, dj = tap - 3 * di;
+        const uint64_t a_tap = a_tmpl + (uint64_t)((uint32_t)((dj * PU + di) * 16 + kk0 * 2 * PPAD * 16) >> 4);
 #pragma unroll
         for (int i = 0; i < SPC; ++i) {
-          const int ks = c * SPC + i, tap = ks >> 4, kk = ks & 15;
-          const int di = tap / 3, dj = tap % 3;
-          const uint32_t a_off = (uint32_t)((dj * PU + di) * 16 + kk * 2 * PPAD * 16) >> 4;
-          if (leader) ptx::mma_bf16_ss(tmem_base, a_tmpl + a_off, b_chunk + (uint32_t)((i * N * 32) >> 4), idesc, ks ? 1u : 0u);
+          if (leader) ptx::mma_bf16_ss(tmem_base, a_tap + (uint32_t)((i * 2 * PPAD * 16) >> 4), b_chunk + (uint32_t)((i * N * 32) >> 4), idesc,
+                                       (c | i) ? 1u : 0u);
         }
         if (leader) ptx::mma_commit(bar(SB_EMPTY + (g0 + c) % NST));
       }
@@ -349,21 +362,23 @@ __global__ void __launch_bounds__(THREADS) k_level5(const __grid_constant__ Para
       ptx::tc_fence_after_sync();
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, 64);
       const uint64_t a_tmpl = ptx::smem_desc(A, PPAD * 16, PU * 16);
-#pragma unroll
-      for (int c = 0; c < chunks_of(W5); ++c) {
+#pragma unroll 1
+      for (int c = 0; c < chunks_of(W5); ++c) {            // a chunk = two taps of 8 k-steps (the last chunk: one)
         const uint64_t b_chunk = chunk_ready(G5 + c, 64 * 16);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int ks = c * 16 + i;
-          if (ks < 72) {
-            const int tap = ks >> 3, kk = ks & 7;
-            const int di = tap / 3, dj = tap % 3;
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int tap = 2 * c + h2;
+          if (tap < 9) {
+            const int di = tap / 3, dj = tap - 3 * di;
             // out[2m + p] takes tap d = p from in[m] and, for p = 0, tap d = 2 from in[m - 1]
-            const uint32_t a_off = (uint32_t)((((dj == 2) ? 0 : 1) * PU + ((di == 2) ? 0 : 1)) * 16 + kk * 2 * PPAD * 16) >> 4;
-            const int ph = ((di == 1) ? 2 : 0) + ((dj == 1) ? 1 : 0);
-            const bool first = (tap == 0 || tap == 1 || tap == 3 || tap == 4) && kk == 0;
-            if (leader) ptx::mma_bf16_ss(tmem_base + (uint32_t)(ph * 64), a_tmpl + a_off, b_chunk + (uint32_t)((i * 64 * 32) >> 4), idesc,
-                                         first ? 0u : 1u);
+            const uint64_t a_tap = a_tmpl + (uint64_t)((uint32_t)((((dj == 2) ? 0 : 1) * PU + ((di == 2) ? 0 : 1)) * 16) >> 4);
+            const uint32_t d_tmem = tmem_base + (uint32_t)((((di == 1) ? 2 : 0) + ((dj == 1) ? 1 : 0)) * 64);
+            const bool first_tap = tap == 0 || tap == 1 || tap == 3 || tap == 4;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              if (leader) ptx::mma_bf16_ss(d_tmem, a_tap + (uint32_t)((kk * 2 * PPAD * 16) >> 4),
+                                           b_chunk + (uint32_t)(((h2 * 8 + kk) * 64 * 32) >> 4), idesc, (first_tap && kk == 0) ? 0u : 1u);
+            }
           }
         }
         if (leader) ptx::mma_commit(bar(SB_EMPTY + (G5 + c) % NST));
@@ -386,7 +401,17 @@ __global__ void __launch_bounds__(THREADS) k_level5(const __grid_constant__ Para
           ptx::tmem_ld8(lane_base + (uint32_t)(ph * 64 + c0), o);
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] += bv[i];
-          if (ok) *reinterpret_cast<uint4*>(dst + c0) = pack8(o);
+          if (ok) {
+            const uint4 st = pack8(o);
+            *reinterpret_cast<uint4*>(dst + c0) = st;
+            if (p.yp) {     // planes form of the output (fn_level5_desc.y_planes): [B][16][IH][IW][8] = concat_elu(y)
+              uint4 e0, e1;
+              concat_elu8(st, e0, e1);
+              __nv_bfloat16* d0 = p.yp + ((((size_t)b * 16 + (c0 >> 3)) * IH + oy) * IW + ox) * 8;
+              *reinterpret_cast<uint4*>(d0) = e0;
+              *reinterpret_cast<uint4*>(d0 + (size_t)8 * IH * IW * 8) = e1;
+            }
+          }
         }
       }
     }
@@ -411,6 +436,7 @@ int level5_fwd(const fn_level5_desc& d, cudaStream_t stream) {
   p.wstream = (const unsigned char*)d.w_stream;
   p.bias = d.bias;
   p.y = (__nv_bfloat16*)d.y;
+  p.yp = (__nv_bfloat16*)d.y_planes;
   p.status = tc_status_word();
   if (p.status == nullptr) return (int)cudaErrorMemoryAllocation;
   p.B = d.B;

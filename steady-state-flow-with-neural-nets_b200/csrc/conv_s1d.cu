@@ -159,43 +159,6 @@ __device__ __forceinline__ void transform_tile_dropout(uint32_t stage, uint32_t 
   }
 }
 
-__device__ __forceinline__ void shortcut_generic(const Params& p, int F, int b, int oy, int ox, int c0, float (&v)[8]) {
-  const int shift = F - p.Cres;
-  if (p.res_pool && (p.Cres & 7) == 0 && ((c0 - shift) & 7) == 0 && 2 * oy + 1 < p.RH && 2 * ox + 1 < p.RW) {
-    if (c0 - shift < 0) return;
-    const __nv_bfloat16* r00 = p.res + (((size_t)b * p.RH + 2 * oy) * p.RW + 2 * ox) * p.Cres + (c0 - shift);
-    bf16x8 q[4];
-    q[0].v = __ldg(reinterpret_cast<const uint4*>(r00));
-    q[1].v = __ldg(reinterpret_cast<const uint4*>(r00 + p.Cres));
-    q[2].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)p.RW * p.Cres));
-    q[3].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)p.RW * p.Cres + p.Cres));
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      v[j] += 0.25f * (__bfloat162float(q[0].h[j]) + __bfloat162float(q[1].h[j]) + __bfloat162float(q[2].h[j]) +
-                       __bfloat162float(q[3].h[j]));
-    return;
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int cr = c0 + j - shift;
-    if (cr < 0) continue;
-    if (p.res_pool) {
-      float s = 0.f;
-      int cnt = 0;
-      for (int a = 0; a < 2; ++a)
-        for (int c = 0; c < 2; ++c) {
-          const int ry = 2 * oy + a, rx = 2 * ox + c;
-          if (ry < p.RH && rx < p.RW) {
-            s += __bfloat162float(p.res[(((size_t)b * p.RH + ry) * p.RW + rx) * p.Cres + cr]);
-            ++cnt;
-          }
-        }
-      v[j] += s / (float)cnt;
-    } else {
-      v[j] += __bfloat162float(p.res[(((size_t)b * p.RH + oy) * p.RW + ox) * p.Cres + cr]);
-    }
-  }
-}
 
 template <int CLOG, int J, bool GATE, bool SKIP, bool TR, int NST, int NSPLIT = 1>
 __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Params p) {
@@ -260,6 +223,13 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
   if (warp == 8) {
     // =========================== producer ===========================
     if (lane == 0) {
+      // the packed weights are cold in L2 at kernel start (evicted by the activation traffic of the other levels):
+      // request the whole image now, the ring's chunk copies then hit L2
+      for (int o = 0; o < CF::KSTEPS * CF::N * 32; o += 32768) {
+        const int n = CF::KSTEPS * CF::N * 32 - o;
+        ptx::prefetch_l2(reinterpret_cast<const unsigned char*>(p.wpk) + o, (uint32_t)(n < 32768 ? n : 32768));
+      }
+      const uint64_t pol = ptx::policy_evict_last();
       int gchunk = 0;                                   // running weight-chunk counter across tiles
       for (int it = 0; it < n_local && ok; ++it) {
         const uint32_t par_it = (uint32_t)(it & 1), par_prev = par_it ^ 1u;
@@ -287,8 +257,8 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
             const int steps = (c == CF::NCHUNKS - 1) ? (CF::KSTEPS - c * CF::SPC) : CF::SPC;
             const uint32_t bytes = (uint32_t)(steps * CF::N * 32);
             ptx::mbar_arrive_expect_tx(bar(SB_FULL + s), bytes);
-            ptx::bulk_g2s(sbase + CF::OFF_RING + s * CHUNK_BYTES,
-                          reinterpret_cast<const unsigned char*>(p.wpk) + (size_t)c * CF::SPC * CF::N * 32, bytes, bar(SB_FULL + s));
+            ptx::bulk_g2s_hint(sbase + CF::OFF_RING + s * CHUNK_BYTES,
+                               reinterpret_cast<const unsigned char*>(p.wpk) + (size_t)c * CF::SPC * CF::N * 32, bytes, bar(SB_FULL + s), pol);
           } else {
             // one tensor copy per chunk: this CTA's FL rows of the u block (and of the v block) for both K halves of SPC
             // k-steps, rows of FL * 16 contiguous bytes, landing as [kstep][khalf][u rows | v rows][16 B]
@@ -436,7 +406,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_s1d(const __grid_constant__ Pa
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] += __bfloat162float(rr.h[i]);
             } else if (p.res_mode == 2 && live) {
-              shortcut_generic(p, CF::F, b, oy, ox, c0, o);
+              shortcut_add8(p.res, p.Cres, p.RH, p.RW, p.res_pool, CF::F, b, oy, ox, c0, o);
             }
           } else {
             ptx::tmem_ld8(col0 + cl, o);

@@ -149,44 +149,6 @@ __device__ __forceinline__ void transform_tile_dropout(uint32_t stage, uint32_t 
   }
 }
 
-// generic shortcut (avg-pool and/or front channel pad), 8 channels, global loads; reference :153-165
-__device__ __forceinline__ void sp_shortcut_generic(const SpParams& p, int F, int b, int oy, int ox, int c0, float (&v)[8]) {
-  const int shift = F - p.Cres;
-  if (p.res_pool && (p.Cres & 7) == 0 && ((c0 - shift) & 7) == 0 && 2 * oy + 1 < p.RH && 2 * ox + 1 < p.RW) {
-    if (c0 - shift < 0) return;             // front padding: nothing to add
-    const __nv_bfloat16* r00 = p.res + (((size_t)b * p.RH + 2 * oy) * p.RW + 2 * ox) * p.Cres + (c0 - shift);
-    bf16x8 q[4];
-    q[0].v = __ldg(reinterpret_cast<const uint4*>(r00));
-    q[1].v = __ldg(reinterpret_cast<const uint4*>(r00 + p.Cres));
-    q[2].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)p.RW * p.Cres));
-    q[3].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)p.RW * p.Cres + p.Cres));
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      v[j] += 0.25f * (__bfloat162float(q[0].h[j]) + __bfloat162float(q[1].h[j]) + __bfloat162float(q[2].h[j]) +
-                       __bfloat162float(q[3].h[j]));
-    return;
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int cr = c0 + j - shift;
-    if (cr < 0) continue;
-    if (p.res_pool) {
-      float s = 0.f;
-      int cnt = 0;
-      for (int a = 0; a < 2; ++a)
-        for (int c = 0; c < 2; ++c) {
-          const int ry = 2 * oy + a, rx = 2 * ox + c;
-          if (ry < p.RH && rx < p.RW) {
-            s += __bfloat162float(p.res[(((size_t)b * p.RH + ry) * p.RW + rx) * p.Cres + cr]);
-            ++cnt;
-          }
-        }
-      v[j] += s / (float)cnt;
-    } else {
-      v[j] += __bfloat162float(p.res[(((size_t)b * p.RH + oy) * p.RW + ox) * p.Cres + cr]);
-    }
-  }
-}
 
 template <int CLOG, int J, bool GATE, bool SKIP, bool DROP = false>
 __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__ SpParams p) {
@@ -448,7 +410,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] += __bfloat162float(rr.h[i]);
               } else if (p.res_mode == 2 && live) {
-                sp_shortcut_generic(p, Cfg::F, b, oy, ox, c0, o);
+                shortcut_add8(p.res, p.Cres, p.RH, p.RW, p.res_pool, Cfg::F, b, oy, ox, c0, o);
               } else if (p.res_mode == 3 && c0 == Cfg::F - 8) {
                 o[7] += r1[j];
               }

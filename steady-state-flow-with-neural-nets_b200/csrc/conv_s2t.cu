@@ -31,7 +31,8 @@ struct Params {
   CUtensorMap tm_x;
   const __nv_bfloat16* wpk;
   const float* bias;
-  __nv_bfloat16* y;
+  __nv_bfloat16* y;       // raw NHWC output (null: planes only)
+  __nv_bfloat16* yp;      // optional planes form of the output (fn_conv_desc.y_planes), plain bias epilogue only
   int* status;
   int B, H, W;            // input tensor
   int OH, OW;             // output tensor
@@ -346,7 +347,15 @@ __global__ void __launch_bounds__(THREADS) k_conv_s2t(const __grid_constant__ Pa
             bf16x8 st;
 #pragma unroll
             for (int i = 0; i < 8; ++i) st.h[i] = __float2bfloat16(o[i] + sbias[c0 + i]);
-            *reinterpret_cast<uint4*>(p.y + pix * CF::NREAL + c0) = st.v;
+            if (p.y) *reinterpret_cast<uint4*>(p.y + pix * CF::NREAL + c0) = st.v;
+            if (p.yp) {   // [B][2 NREAL/8][OH][OW][8] = concat_elu of the bf16 output
+              uint4 e0, e1;
+              concat_elu8(st.v, e0, e1);
+              const size_t plane_px = (size_t)p.OH * p.OW;
+              __nv_bfloat16* d0 = p.yp + (((size_t)b * (CF::NREAL / 4) + c0 / 8) * plane_px + (size_t)oy * p.OW + ox) * 8;
+              *reinterpret_cast<uint4*>(d0) = e0;
+              *reinterpret_cast<uint4*>(d0 + (size_t)(CF::NREAL / 8) * plane_px * 8) = e1;
+            }
           }
         }
       }
@@ -371,6 +380,7 @@ struct AdjArgs {
   float keep_prob = 1.0f;
   unsigned long long seed = 0;
   const unsigned long long* seed_dev = nullptr;
+  void* y_planes = nullptr;
 };
 
 template <int MODE, int CLOG, int J, int NBUF, int R = 1>
@@ -383,6 +393,7 @@ static int launch(const void* x, const void* wpk, const float* bias, void* y, in
   p.wpk = (const __nv_bfloat16*)wpk;
   p.bias = bias;
   p.y = (__nv_bfloat16*)y;
+  p.yp = (__nv_bfloat16*)adj.y_planes;
   p.status = status;
   p.B = B; p.H = H; p.W = W;
   if (CF::S2) { p.OH = H / 2; p.OW = W / 2; p.RH = p.OH; p.RW = p.OW; }
@@ -438,7 +449,9 @@ bool conv_s2p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
   if (clog == CL && ((OW % (8 * JJ)) == 0 || JJ == 1) && Cfg<MODE_S2, CL, JJ, NB>::SMEM <= CAP * 1024) {       \
     if (!dry_run) {                                                                                           \
       int* st = tc_status_word();                                                                             \
-      rc = st ? launch<MODE_S2, CL, JJ, NB>(d.x, d.w_tc, d.bias, d.y, d.B, d.H, d.W, d.Cout, st, stream)      \
+      AdjArgs out;                                                                                            \
+      out.y_planes = d.y_planes;                                                                              \
+      rc = st ? launch<MODE_S2, CL, JJ, NB>(d.x, d.w_tc, d.bias, d.y, d.B, d.H, d.W, d.Cout, st, stream, out) \
               : (int)cudaErrorMemoryAllocation;                                                               \
     }                                                                                                         \
     return true;                                                                                              \
@@ -536,6 +549,8 @@ bool tconv_s2p_try(const fn_tconv_desc& d, cudaStream_t stream, bool dry_run, in
     adj.accumulate = d.adj_accumulate;
     adj.res = d.res;
   }
+  adj.y_planes = d.y_planes;
+  if (adj.adj && d.y_planes) return false;
   if (get_encode() == nullptr) return false;
   const int clog = d.Cin == 16 ? 1 : d.Cin == 32 ? 2 : d.Cin == 64 ? 3 : -1;
   if (clog < 0) return false;

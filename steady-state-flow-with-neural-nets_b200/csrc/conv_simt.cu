@@ -277,8 +277,9 @@ static int launch_direct(const fn_conv_desc& d, cudaStream_t stream) {
 // conflict-free and every warp store covers 512 contiguous bytes.
 template <int NOUT>
 __global__ void __launch_bounds__(256) k_head3x3(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
-                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B,
-                                                    int H, int W, int tiles_x, int tiles_y) {
+                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                    __nv_bfloat16* __restrict__ yp, int B, int H, int W, int tiles_x,
+                                                    int tiles_y) {
   __shared__ __align__(16) float ws[9 * NOUT + NOUT];
   __shared__ float tile[10][132];
   if (threadIdx.x < 9 * NOUT) ws[threadIdx.x] = __bfloat162float(w[threadIdx.x]);
@@ -340,7 +341,14 @@ __global__ void __launch_bounds__(256) k_head3x3(const __nv_bfloat16* __restrict
         bf16x8 o;
 #pragma unroll
         for (int n = 0; n < 8; ++n) o.h[n] = __float2bfloat16(acc[px][n0 + n]);
-        *reinterpret_cast<uint4*>(yo + (size_t)ox * NOUT + n0) = o.v;
+        if (y) *reinterpret_cast<uint4*>(yo + (size_t)ox * NOUT + n0) = o.v;
+        if (yp) {    // planes form of the output (fn_conv_desc.y_planes): [B][2 NOUT/8][H][W][8] = concat_elu(y)
+          uint4 e0, e1;
+          concat_elu8(o.v, e0, e1);
+          __nv_bfloat16* d0 = yp + ((((size_t)b * (NOUT / 4) + n0 / 8) * H + oy) * W + x0 + ox) * 8;
+          *reinterpret_cast<uint4*>(d0) = e0;
+          *reinterpret_cast<uint4*>(d0 + (size_t)(NOUT / 8) * H * W * 8) = e1;
+        }
       }
     }
   }
@@ -352,7 +360,8 @@ static int launch_head(const fn_conv_desc& d, cudaStream_t stream) {
   const long long grid = (long long)d.B * tiles_x * tiles_y;
   k_head3x3<NOUT><<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d.x),
                                                    reinterpret_cast<const __nv_bfloat16*>(d.w), d.bias,
-                                                   reinterpret_cast<__nv_bfloat16*>(d.y), d.B, d.H, d.W, tiles_x, tiles_y);
+                                                   reinterpret_cast<__nv_bfloat16*>(d.y),
+                                                   reinterpret_cast<__nv_bfloat16*>(d.y_planes), d.B, d.H, d.W, tiles_x, tiles_y);
   count_launch();
   return check_launch("k_head3x3");
 }

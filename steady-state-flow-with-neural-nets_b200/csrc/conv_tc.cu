@@ -653,8 +653,21 @@ bool conv_s1d_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int&
 bool conv_s1n_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s2t.cu
 bool conv_s1w_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s1w.cu
 
+bool conv_pl_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);    // conv_pl.cu
+bool conv_s2p_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);   // conv_s2t.cu
+
 bool conv_tc_supported(const fn_conv_desc& d, const char** why) {
   int rc = 0;
+  if (d.x_planes || d.skip_planes) {       // MMA-ready operands: the planes kernel or nothing
+    if (conv_pl_try(d, nullptr, true, rc)) return true;
+    if (why) *why = "planes operands are taken by stride-1 3x3 concat_elu convs with 8/16/32 channels only (conv_pl.cu)";
+    return false;
+  }
+  if (d.y_planes || d.y == nullptr) {      // planes output from raw input: the persistent stride-2 kernel (the head runs on CUDA cores)
+    if (g_tc_use_s1p && conv_s2p_try(d, nullptr, true, rc)) return true;
+    if (why) *why = "a planes output is written by conv_pl.cu, the persistent stride-2 kernel and the 1-channel head only";
+    return false;
+  }
   // the persistent kernels also take the dropout prologue, which the generic kernel below does not
   if (g_tc_use_s1p && (d.keep_prob < 1.0f || d.epilogue == FN_EPI_GATE_BWD) &&
       (conv_s1p_try(d, nullptr, true, rc) || conv_s1d_try(d, nullptr, true, rc)))
@@ -715,6 +728,16 @@ bool conv_wg_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& 
 
 int conv_fwd_tc(const fn_conv_desc& d, cudaStream_t stream) {
   int rc_sp = 0;
+  if (d.x_planes || d.skip_planes) {
+    if (conv_pl_try(d, stream, false, rc_sp)) return rc_sp;
+    set_error("conv_fwd_tc: no kernel for these planes operands");
+    return FN_E_UNSUPPORTED;
+  }
+  if (d.y_planes || d.y == nullptr) {
+    if (g_tc_use_s1p && conv_s2p_try(d, stream, false, rc_sp)) return rc_sp;
+    set_error("conv_fwd_tc: no kernel writes a planes output for this shape");
+    return FN_E_UNSUPPORTED;
+  }
   if (g_tc_use_s1p && conv_wg_try(d, stream, false, rc_sp)) return rc_sp;
   if (g_tc_use_s1p && conv_s1p_try(d, stream, false, rc_sp)) return rc_sp;
   if (g_tc_use_s1p && conv_s1d_try(d, stream, false, rc_sp)) return rc_sp;
@@ -759,6 +782,12 @@ bool tconv_tc_supported(const fn_tconv_desc& d, const char** why) {
     if (why) *why = "the prologue-adjoint epilogue exists in the persistent sub-pixel kernel only";
     return false;
   }
+  if (d.y_planes) {
+    int rc = 0;
+    if (g_tc_use_s1p && tconv_s2p_try(d, nullptr, true, rc)) return true;
+    if (why) *why = "a planes output is written by the persistent sub-pixel kernel only";
+    return false;
+  }
   TcGeom g;
   TcParams p;
   size_t sm;
@@ -770,6 +799,10 @@ bool tconv_tc_supported(const fn_tconv_desc& d, const char** why) {
 int tconv_fwd_tc(const fn_tconv_desc& d, cudaStream_t stream) {
   int rc_sp = 0;
   if (g_tc_use_s1p && tconv_s2p_try(d, stream, false, rc_sp)) return rc_sp;
+  if (d.y_planes) {
+    set_error("tconv_fwd_tc: no kernel writes a planes output for this shape");
+    return FN_E_UNSUPPORTED;
+  }
   TcGeom g;
   TcParams p;
   size_t smem_bytes = 0;

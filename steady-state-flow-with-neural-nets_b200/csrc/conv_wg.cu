@@ -110,44 +110,6 @@ __device__ __forceinline__ void lds_f8(uint32_t addr, float (&f)[8]) {
   f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
 }
 
-// generic shortcut (avg-pool and/or front channel pad), 8 channels, global loads; reference :153-165
-__device__ __forceinline__ void shortcut_generic(const Params& p, int F, int b, int oy, int ox, int c0, float (&v)[8]) {
-  const int shift = F - p.Cres;
-  if (p.res_pool && (p.Cres & 7) == 0 && ((c0 - shift) & 7) == 0 && 2 * oy + 1 < p.RH && 2 * ox + 1 < p.RW) {
-    if (c0 - shift < 0) return;             // front padding: nothing to add
-    const __nv_bfloat16* r00 = p.res + (((size_t)b * p.RH + 2 * oy) * p.RW + 2 * ox) * p.Cres + (c0 - shift);
-    bf16x8 q[4];
-    q[0].v = __ldg(reinterpret_cast<const uint4*>(r00));
-    q[1].v = __ldg(reinterpret_cast<const uint4*>(r00 + p.Cres));
-    q[2].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)p.RW * p.Cres));
-    q[3].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)p.RW * p.Cres + p.Cres));
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      v[j] += 0.25f * (__bfloat162float(q[0].h[j]) + __bfloat162float(q[1].h[j]) + __bfloat162float(q[2].h[j]) +
-                       __bfloat162float(q[3].h[j]));
-    return;
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int cr = c0 + j - shift;
-    if (cr < 0) continue;
-    if (p.res_pool) {
-      float s = 0.f;
-      int cnt = 0;
-      for (int a = 0; a < 2; ++a)
-        for (int c = 0; c < 2; ++c) {
-          const int ry = 2 * oy + a, rx = 2 * ox + c;
-          if (ry < p.RH && rx < p.RW) {
-            s += __bfloat162float(p.res[(((size_t)b * p.RH + ry) * p.RW + rx) * p.Cres + cr]);
-            ++cnt;
-          }
-        }
-      v[j] += s / (float)cnt;
-    } else {
-      v[j] += __bfloat162float(p.res[(((size_t)b * p.RH + oy) * p.RW + ox) * p.Cres + cr]);
-    }
-  }
-}
 
 template <int CLOG, int J, bool GATE, bool SKIP, int NWG, int MINB, int RESM>
 __global__ void __launch_bounds__(NWG * 128, MINB) k_conv_wg(const __grid_constant__ Params p) {
@@ -334,7 +296,7 @@ __global__ void __launch_bounds__(NWG * 128, MINB) k_conv_wg(const __grid_consta
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] += __bfloat162float(rv.h[i]);
           } else if (RESM == 2) {
-            if (live) shortcut_generic(p, CF::F, b, oy, ox, c0, o);
+            if (live) shortcut_add8(p.res, p.Cres, p.RH, p.RW, p.res_pool, CF::F, b, oy, ox, c0, o);
           } else if (RESM == 3) {
             if (c0 == CF::F - 8) o[7] += r1[j];
           }

@@ -39,8 +39,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // bounded wait: returns false after ~2^31 clocks (about a second) so a protocol bug cannot hang the GPU; the clock is
 // read once per 32 unsuccessful tries
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return true;
+// (the retry loop is a function call: inlined at the ~10 wait sites of a kernel it was several KB of code that is
+// fetched cold from L2 / HBM at every launch -- the kernels of this library are bound by instruction fetch at start-up)
+static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   for (;;) {
 #pragma unroll 1
@@ -48,6 +49,10 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
       if (mbar_try_wait(bar, parity)) return true;
     if (clock64() - t0 > (1ll << 31)) return false;
   }
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  return mbar_wait_slow(bar, parity);
 }
 
 // one lane of a converged warp (the same lane every time): returns 1 in that lane, 0 elsewhere
@@ -78,6 +83,26 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// Weights are re-read by every CTA of every launch of every step while ~1 GB of activations streams through the 126 MB
+// L2 in between: loading them with an evict_last policy keeps the ~5 MB of packed weights L2-resident across launches
+// and graph replays (activations use the default evict_normal policy and are evicted first).
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+               : "memory");
+}
+
+// L2 prefetch of a global range (bytes: multiple of 16): the weight streams of the deep levels are evicted between
+// launches by ~1 GB of activation traffic per step; a 2 x 32 KB ring alone cannot cover DRAM latency at 50+ B/clk
+__device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 // ---- TMEM allocation (one full warp executes these)

@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FLOWNET_LIB", os.path.join(_HERE, "libflownet.so"))   # override: A/B builds
 
-FN_ABI_VERSION = 5
+FN_ABI_VERSION = 6
 # enum fn_prologue
 PRO_NONE, PRO_CONCAT_ELU, PRO_ELU, PRO_CONCAT_RELU, PRO_RELU = 0, 1, 2, 3, 4
 # enum fn_epilogue
@@ -37,6 +37,7 @@ class ConvDesc(C.Structure):
         ("dropout_seed", C.c_uint64), ("dropout_offset", C.c_uint64),
         ("dropout_seed_dev", C.c_void_p),
         ("adj_prologue", C.c_int32), ("adj_accumulate", C.c_int32),
+        ("x_planes", C.c_int32), ("skip_planes", C.c_int32), ("y_planes", C.c_void_p),
     ]
 
 
@@ -50,7 +51,8 @@ class LbmDesc(C.Structure):
 
 class Level5Desc(C.Structure):
     _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
-                ("x", C.c_void_p), ("w_stream", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p)]
+                ("x", C.c_void_p), ("w_stream", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p),
+                ("y_planes", C.c_void_p)]
 
 
 class TConvDesc(C.Structure):
@@ -59,7 +61,7 @@ class TConvDesc(C.Structure):
         ("impl", C.c_int32),
         ("x", C.c_void_p), ("w", C.c_void_p), ("w_tc", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p),
         ("epilogue", C.c_int32), ("adj_prologue", C.c_int32), ("adj_accumulate", C.c_int32), ("reserved", C.c_int32),
-        ("res", C.c_void_p),
+        ("res", C.c_void_p), ("y_planes", C.c_void_p),
     ]
 
 
@@ -120,6 +122,12 @@ DEBUG_SYMBOLS = [
     ("fn_debug_set_nsplit", None, [C.c_int]),
     ("fn_debug_set_wg", None, [C.c_int]),
     ("fn_debug_set_wg_j16", None, [C.c_int]),
+    ("fn_debug_set_pl", None, [C.c_int]),
+    ("fn_debug_set_pl_grid_cap", None, [C.c_int]),
+    ("fn_debug_set_pl_ne", None, [C.c_int]),
+    ("fn_debug_set_pl_j", None, [C.c_int]),
+    ("fn_debug_set_pl_ni", None, [C.c_int]),
+    ("fn_debug_set_pl_knock", None, [C.c_int]),
 ]
 
 
@@ -186,18 +194,26 @@ def tc_status() -> int:
 
 def conv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, ksize=3, stride=1, prologue=PRO_NONE, epilogue=EPI_BIAS,
              impl=IMPL_AUTO, w_tc=None, skip=None, w_skip=None, res=None, res_pool=False, keep_prob=1.0,
-             dropout_seed=0, dropout_offset=0, adj_prologue=0, adj_accumulate=False, query=False):
+             dropout_seed=0, dropout_offset=0, adj_prologue=0, adj_accumulate=False, query=False, x_planes=False,
+             skip_planes=False, y_planes=None):
     # DROPOUT_SEED_DEV (module level): optional device int64 [1] added to every dropout seed inside the kernels
     """query=True: do not launch, return whether this call would run on the tensor cores."""
-    _require_cuda(x, w, bias, y, skip, w_skip, res, w_tc)
+    # x_planes / skip_planes: x / skip are planes tensors [B, 2C/8, H, W, 8] (include/flownet.h); y_planes: optional planes
+    # output, y may then be None
+    _require_cuda(x, w, bias, y, skip, w_skip, res, w_tc, y_planes)
     d = ConvDesc()
     d.B, d.H, d.W, d.Cin, d.Cout, d.ksize, d.stride = B, H, W, Cin, Cout, ksize, stride
     d.prologue, d.epilogue, d.impl = prologue, epilogue, impl
     d.x, d.w, d.w_tc, d.bias, d.y = x.data_ptr(), w.data_ptr(), (w_tc.data_ptr() if w_tc is not None else None), \
-        bias.data_ptr(), y.data_ptr()
+        bias.data_ptr(), (y.data_ptr() if y is not None else None)
+    d.x_planes, d.skip_planes = int(bool(x_planes)), int(bool(skip_planes))
+    d.y_planes = y_planes.data_ptr() if y_planes is not None else None
     if skip is not None:
         d.skip, d.w_skip = skip.data_ptr(), w_skip.data_ptr()
-        d.Cskip, d.SH, d.SW = skip.shape[3], skip.shape[1], skip.shape[2]
+        if skip_planes:
+            d.Cskip, d.SH, d.SW = skip.shape[1] * 4, skip.shape[2], skip.shape[3]
+        else:
+            d.Cskip, d.SH, d.SW = skip.shape[3], skip.shape[1], skip.shape[2]
     if res is not None:
         d.res = res.data_ptr()
         d.Cres, d.RH, d.RW = res.shape[3], res.shape[1], res.shape[2]
@@ -212,7 +228,7 @@ def conv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, ksize=3, stride=1, prologue=P
 
 
 def tconv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, impl=IMPL_AUTO, w_tc=None, epilogue=EPI_BIAS, res=None,
-              adj_prologue=PRO_NONE, adj_accumulate=False, query=False):
+              adj_prologue=PRO_NONE, adj_accumulate=False, query=False, y_planes=None):
     """query=True: return whether a tensor-core kernel takes this call (for EPI_PRO_BWD: the fused one), run nothing."""
     _require_cuda(x, w, bias, y, w_tc, res)
     d = TConvDesc()
@@ -221,6 +237,7 @@ def tconv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, impl=IMPL_AUTO, w_tc=None, e
     d.w_tc = w_tc.data_ptr() if w_tc is not None else None
     d.epilogue, d.adj_prologue, d.adj_accumulate = epilogue, adj_prologue, int(bool(adj_accumulate))
     d.res = res.data_ptr() if res is not None else None
+    d.y_planes = y_planes.data_ptr() if y_planes is not None else None
     if query:
         return bool(lib.fn_tconv_fwd_has_tcgen05(C.byref(d)))
     _check(lib.fn_tconv_fwd(C.byref(d), stream_ptr()), "fn_tconv_fwd")
@@ -230,14 +247,15 @@ def level5_supported(H, W, Cc):
     return bool(lib.fn_level5_supported(int(H), int(W), int(Cc)))
 
 
-def level5_fwd(x, w_stream, bias, y):
+def level5_fwd(x, w_stream, bias, y, y_planes=None):
     """x: bf16 [B,16,32,64] -> y: bf16 [B,16,32,64]: the 8x16 level in one launch (fn_level5_fwd)"""
-    _require_cuda(x, w_stream, bias, y)
+    _require_cuda(x, w_stream, bias, y, y_planes)
     if w_stream.numel() * w_stream.element_size() != int(lib.fn_level5_weight_bytes()) or bias.numel() != 832:
         raise ValueError("level5_fwd: weight stream / bias size")
     d = Level5Desc()
     d.B, d.H, d.W, d.C = x.shape
     d.x, d.w_stream, d.bias, d.y = x.data_ptr(), w_stream.data_ptr(), bias.data_ptr(), y.data_ptr()
+    d.y_planes = y_planes.data_ptr() if y_planes is not None else None
     _check(lib.fn_level5_fwd(C.byref(d), stream_ptr()), "fn_level5_fwd")
 
 

@@ -401,6 +401,152 @@ def _level5_fused(x):
     return y
 
 
+# --------------------------------------------------------------------------- inference on MMA-ready activations
+# "planes" form of an activation t [B,H,W,C] (include/flownet.h, csrc/conv_pl.cu): bf16 [B, 2C/8, H, W, 8] = concat_elu(t)
+# in 8-channel groups.  In inference every producer's epilogue writes what its consumers read: the planes for a stride-1
+# 3x3 conv (whose tensor copies then land the tensor-core A operand directly: no transform stage), the raw NHWC tensor
+# for shortcuts, resampling convs and the tail.  x_1 = conv_1's output exists in planes form only.
+# Opt-in (FLOWNET_PLANES=1): measured at batch 64 the planes kernels are 10-30 % faster per launch than the raw-input
+# kernels, but every planes tensor is twice the bytes of its raw form and its producers' epilogues store three 16-byte
+# vectors per pixel group instead of one -- the whole forward came out 6 % slower.
+PLANES = os.environ.get("FLOWNET_PLANES", "0") == "1"
+_PL_CHANNELS = (8, 16, 32)       # levels whose stride-1 convs have a planes kernel
+
+
+def _planes_usable(x, keep_prob, nonlinearity, gated, filter_size):
+    B, H, W, cin = x.shape
+    return (PLANES and TAPE is None and IMPL == native.IMPL_AUTO and keep_prob >= 1.0 and nonlinearity is concat_elu and gated
+            and cin == 1 and filter_size in (8, 16) and H % 16 == 0 and W % 16 == 0 and H >= 128 and W >= 128)
+
+
+def _planes_empty(B, H, W, C, device):
+    return torch.empty((B, 2 * C // 8, H, W, 8), device=device, dtype=torch.bfloat16)
+
+
+def _conv_planes(scope, cout, epilogue, x=None, xp=None, stride=1, skip_p=None, skip_scope=None, res=None,
+                 res_pool=False, want_raw=True, want_planes=False):
+    """One fused 3x3 conv launch of the planes path.  Input: raw `x` [B,H,W,C] (1-channel head, stride-2 convs) or planes
+    `xp`; optional planes skip; outputs (raw or None, planes or None)."""
+    if xp is not None:
+        B, cin, H, W = xp.shape[0], xp.shape[1] * 4, xp.shape[2], xp.shape[3]
+        src, pro = xp, native.PRO_CONCAT_ELU
+    else:
+        B, H, W, cin = int_shape(x)
+        src, pro = x, (native.PRO_NONE if cin == 1 else native.PRO_CONCAT_ELU)
+    mult = _pro_mult(pro)
+    kskip = skip_p.shape[1] * 8 if skip_p is not None else 0
+    gated = epilogue == native.EPI_GATE_RES
+    w16, ws16, bias, w_tc = _conv_weights(scope, 3, cin * mult, cout, src.device, skip_scope, kskip, gated)
+    OH, OW = H // stride, W // stride
+    cy = cout // 2 if gated else cout
+    y = torch.empty((B, OH, OW, cy), device=src.device, dtype=torch.bfloat16) if want_raw else None
+    yp = _planes_empty(B, OH, OW, cy, src.device) if want_planes else None
+    rec = None
+    if _PROFILE is not None:
+        # algorithmic bytes are counted on the RAW form of every tensor (2 bytes per channel), so the figures compare
+        # with the layer-fused byte count of SURVEY App. C; `moved_bytes` is what this launch really reads and writes
+        raw_in = B * H * W * cin * 2
+        nbytes = raw_in + B * OH * OW * cy * 2
+        moved = (raw_in * (2 if xp is not None else 1) + (y.numel() * 2 if y is not None else 0) +
+                 (yp.numel() * 2 if yp is not None else 0))
+        if skip_p is not None:
+            nbytes += skip_p.numel()
+            moved += skip_p.numel() * 2
+        if res is not None:
+            nbytes += res.numel() * 2
+            moved += res.numel() * 2
+        flops = 2 * B * OH * OW * cout * (9 * cin * mult + kskip)
+        rec = dict(name=scope, kind="conv", out_hw=(OH, OW), K_tap=cin * mult, N=cout, stride=stride,
+                   alg_bytes=nbytes, moved_bytes=moved, flops=flops)
+    _profiled(rec, lambda: native.conv_fwd(
+        src, w16, bias, y, B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=3, stride=stride, prologue=pro, epilogue=epilogue,
+        impl=IMPL, w_tc=w_tc, skip=skip_p, w_skip=ws16, res=res, res_pool=res_pool, x_planes=xp is not None,
+        skip_planes=skip_p is not None, y_planes=yp))
+    return y, yp
+
+
+def _tconv_planes(x, num_features, idx, want_planes):
+    """transpose_conv_layer (reference :70-87) writing the raw output and, if asked, its planes form in the same launch"""
+    B, H, W, cin = int_shape(x)
+    scope = '{0}_trans_conv'.format(idx)
+    w = _variable(scope + '/weights', [3, 3, num_features, cin], device=x.device)
+    b = _variable(scope + '/biases', [num_features], device=x.device)
+
+    def make():
+        w16 = w.permute(0, 1, 3, 2).reshape(9, cin, num_features).to(torch.bfloat16).contiguous()
+        w_tc = native.pack_conv_weights_tc(w16, None, 3, cin, 0, num_features, False) if cin % 16 == 0 else None
+        return w16, b.contiguous(), w_tc
+
+    w16, bias, w_tc = VARIABLES.derived(("tconv", scope), make)
+    y = torch.empty((B, 2 * H, 2 * W, num_features), device=x.device, dtype=torch.bfloat16)
+    yp = _planes_empty(B, 2 * H, 2 * W, num_features, x.device) if want_planes else None
+    rec = None
+    if _PROFILE is not None:
+        rec = dict(name=scope, kind="tconv", out_hw=(2 * H, 2 * W), K_tap=cin, N=num_features, stride=2,
+                   alg_bytes=(x.numel() + y.numel()) * 2,
+                   moved_bytes=(x.numel() + y.numel() + (yp.numel() if yp is not None else 0)) * 2,
+                   flops=2 * B * H * W * 9 * cin * num_features)
+    _profiled(rec, lambda: native.tconv_fwd(x, w16, bias, y, B=B, H=H, W=W, Cin=cin, Cout=num_features, impl=IMPL,
+                                            w_tc=w_tc, y_planes=yp))
+    return y, yp
+
+
+def _conv_res_planes(inputs, nr_res_blocks, filter_size):
+    """conv_res (reference :167-248) for inference with the reference's flags (gated, concat_elu, keep_prob 1): the same
+    launches in the same order with the same variables, the activations of the 8/16/32-channel levels in planes form.
+    Deeper levels run the kernels of the general path on raw tensors."""
+    conc = concat_elu
+
+    def cap(C):
+        return C in _PL_CHANNELS
+
+    def block(x, xp, F, name, stride=1, a_p=None, a=None, out_planes=False):
+        """res_block (:129-165): x raw (always needed: shortcut), xp = its planes or None; returns (raw, planes or None)"""
+        cin = x.shape[3]
+        if not cap(F):                 # no planes kernel at this width: the general two-launch block on raw tensors
+            return res_block(x, a=a, filter_size=F, nonlinearity=conc, stride=stride, gated=True, name=name), None
+        skip_scope = (name + '_nin_fc') if a_p is not None else None
+        if stride == 2 or cin == 1:
+            _, x1p = _conv_planes(name + '_conv_1_conv', F, native.EPI_BIAS, x=x, stride=stride, want_raw=False, want_planes=True)
+        else:
+            _, x1p = _conv_planes(name + '_conv_1_conv', F, native.EPI_BIAS, xp=xp, skip_p=a_p, skip_scope=skip_scope,
+                                  want_raw=False, want_planes=True)
+        return _conv_planes(name + '_conv_2_conv', 2 * F, native.EPI_GATE_RES, xp=x1p, res=x, res_pool=(stride == 2),
+                            want_raw=True, want_planes=out_planes)
+
+    a = []
+    F = filter_size
+    x, xp = native.to_bf16(inputs), None
+    # res_1
+    for i in range(nr_res_blocks):
+        x, xp = block(x, xp, F, "resnet_1_" + str(i), out_planes=cap(F))
+    # res_2 .. res_5
+    fused5 = False
+    for lvl in (2, 3, 4, 5):
+        a.append((x, xp))
+        F = 2 * F
+        if lvl == 5 and _level5_fusable(x, nr_res_blocks, 1.0, conc, True, F):
+            x, xp = _level5_fused(x), None
+            fused5 = True
+            continue
+        x, xp = block(x, xp, F, "resnet_%d_downsample" % lvl, stride=2, out_planes=cap(F))
+        for i in range(nr_res_blocks):
+            x, xp = block(x, xp, F, "resnet_%d_%d" % (lvl, i), out_planes=cap(F))
+    # res_up_1 .. res_up_4
+    for k in (1, 2, 3, 4):
+        F = F // 2
+        if not (k == 1 and fused5):
+            if cap(F):
+                x, xp = _tconv_planes(x, F, "up_conv_%d" % k, want_planes=True)
+            else:
+                x, xp = transpose_conv_layer(x, 3, 2, F, "up_conv_%d" % k), None
+        for i in range(nr_res_blocks):
+            ar, ap = a[-k] if i == 0 else (None, None)
+            x, xp = block(x, xp, F, "resnet_up_%d_%d" % (k, i), a_p=ap, a=ar,
+                          out_planes=cap(F) and i + 1 < nr_res_blocks)
+    return _fused_conv(x, 'last_conv_conv', 3, 1, 2, native.PRO_NONE, native.EPI_TANH)
+
+
 def conv_res(inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name='concat_elu', gated=True, filter_size=8,
              dropout_seed=0):
     """Builds conv part of net -- reference :167-248.
@@ -411,6 +557,8 @@ def conv_res(inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name='concat_e
     Returns: [B,H,W,2] float32 velocity field in (-1, 1)
     """
     nonlinearity = set_nonlinearity(nonlinearity_name)
+    if _planes_usable(inputs, keep_prob, nonlinearity, gated, filter_size):
+        return _conv_res_planes(inputs, nr_res_blocks, filter_size)
     seed = [int(dropout_seed)]
 
     def block(x, a=None, stride=1, name=""):

@@ -63,8 +63,33 @@ def oracle_fused_conv(x, w, b, stride, pro, epi, skip=None, ws=None, res=None, r
     return out
 
 
+def to_planes(native, t):
+    """planes form (include/flownet.h) of a raw bf16 NHWC CUDA tensor, built from the standalone concat_elu kernel:
+    [B,H,W,2C] -> [B, 2C/8, H, W, 8]"""
+    a = native.nonlinearity(t.contiguous(), native.PRO_CONCAT_ELU)
+    B, H, W, C2 = a.shape
+    return a.reshape(B, H, W, C2 // 8, 8).permute(0, 3, 1, 2, 4).contiguous()
+
+
+def planes_match(native, yp, y):
+    """yp == concat_elu(y) in planes form.  The kernels' epilogues and the standalone concat_elu kernel evaluate
+    exp(-|v|) - 1 with different instruction schedules, so single elements near v = 0 (cancellation: the fp32 error of
+    exp, ~1e-7, against |v|) may differ by a bf16 ulp or two; everything else is bit-identical."""
+    t = to_planes(native, y).float()
+    d = (yp.float() - t).abs()
+    assert not torch.isnan(yp.float()).any()
+    bad = d > 2.0 ** -6 * t.abs() + 2e-7
+    frac = (d != 0).float().mean().item()
+    if bad.any() or frac >= 1e-3:
+        ix = tuple(bad.nonzero()[0].tolist()) if bad.any() else tuple((d != 0).nonzero()[0].tolist())
+        print("planes mismatch: %d beyond one ulp, %.2e differ; first at %s: %g vs %g" % (
+            int(bad.sum()), frac, ix, yp[ix].item(), t[ix].item()))
+        return False
+    return True
+
+
 def run_fused_conv(native, impl, B, H, W, Cin, Cout, stride, pro, epi, with_skip=False, Cres=None, res_pool=False,
-                   seed=0, ksize=3):
+                   seed=0, ksize=3, planes_in=False, planes_out=False, raw_out=True):
     g = torch.Generator().manual_seed(seed)
     mult = 2 if pro in (1, 3) else 1
     x = bf16_round(torch.randn(B, H, W, Cin, generator=g, dtype=torch.float64))
@@ -93,13 +118,20 @@ def run_fused_conv(native, impl, B, H, W, Cin, Cout, stride, pro, epi, with_skip
     if (Cin * mult) % 16 == 0 or (Cin * mult == 8 and not with_skip):
         w_tc = native.pack_conv_weights_tc(w16, ws16, ksize, Cin * mult, (skip.shape[3] * mult) if with_skip else 0,
                                            Cout, epi == 1)
-    y = torch.empty((B, OH, OW, F_), device=dev, dtype=torch.float32 if epi == 3 else torch.bfloat16)
+    y = torch.empty((B, OH, OW, F_), device=dev, dtype=torch.float32 if epi == 3 else torch.bfloat16) if raw_out else None
+    yp = torch.full((B, 2 * F_ // 8, OH, OW, 8), float("nan"), device=dev, dtype=torch.bfloat16) if planes_out else None
+    sd = skip.to(dev, torch.bfloat16) if with_skip else None
+    if planes_in:        # the operands in MMA-ready form (csrc/conv_pl.cu)
+        xd = to_planes(native, xd)
+        sd = to_planes(native, sd) if sd is not None else None
     native.conv_fwd(xd, w16, bd, y, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=ksize, stride=stride, prologue=pro,
-                    epilogue=epi, impl=impl, w_tc=w_tc,
-                    skip=skip.to(dev, torch.bfloat16) if with_skip else None, w_skip=ws16,
-                    res=res.to(dev, torch.bfloat16) if res is not None else None, res_pool=res_pool)
+                    epilogue=epi, impl=impl, w_tc=w_tc, skip=sd, w_skip=ws16,
+                    res=res.to(dev, torch.bfloat16) if res is not None else None, res_pool=res_pool,
+                    x_planes=planes_in, skip_planes=planes_in and with_skip, y_planes=yp)
     torch.cuda.synchronize()
     assert native.tc_status() == 0
+    if planes_out:
+        return y, ref, yp
     return y, ref
 
 
@@ -265,6 +297,53 @@ def test_warpgroup_kernel_matches_the_role_pipelined_kernel(native, case, j16):
     assert rel_l2(y, y0) < 5e-4
 
 
+PL_CASES = [c for c in S1P_CASES if c[6] == 1 and c[7] == 1 and c[4] in (8, 16, 32)] + [
+    ("pl_wide_partial_tiles", 3, 48, 200, 8, 16, 1, 1, 1, False, None, False),
+    ("pl_c16_skip_partial", 2, 40, 72, 16, 16, 1, 1, 0, True, None, False),
+    ("pl_c32_many", 70, 32, 64, 32, 64, 1, 1, 1, False, None, False),
+    ("pl_c8_many_skip", 33, 64, 128, 8, 8, 1, 1, 0, True, None, False),
+]
+
+
+@pytest.mark.parametrize("case", PL_CASES, ids=[c[0] for c in PL_CASES])
+def test_planes_kernel_is_bit_identical_to_the_raw_input_kernels(native, case):
+    """csrc/conv_pl.cu: the same convolution with its operands given in planes form (concat_elu applied by the producer)
+    -- same weights image, same MMA order, same epilogue arithmetic as k_conv_wg / k_conv_s1p on the raw tensor, so the raw
+    output is bit-identical; the planes output is concat_elu of that bf16 output."""
+    name, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool = case
+    y, ref, yp = run_fused_conv(native, native.IMPL_TCGEN05, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool,
+                                planes_in=True, planes_out=True)
+    y0, _ = run_fused_conv(native, native.IMPL_TCGEN05, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool)
+    assert rel_l2(y, ref) < LAYER_TOL
+    assert rel_l2(y, y0) < 5e-4
+    assert planes_match(native, yp, y)
+    # planes only (what conv_1 writes in the network)
+    _, _, yp2 = run_fused_conv(native, native.IMPL_TCGEN05, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool,
+                               planes_in=True, planes_out=True, raw_out=False)
+    assert torch.equal(yp2, yp)
+
+
+@pytest.mark.parametrize("case", [c for c in S1P_CASES if c[0].startswith("s2_")] + [SIMT_CASES[0], SIMT_CASES[2], SIMT_CASES[3]],
+                         ids=lambda c: c[0])
+def test_planes_output_of_the_stride2_and_head_kernels(native, case):
+    name, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool = case
+    impl = native.IMPL_AUTO if Cin == 1 else native.IMPL_TCGEN05
+    y, ref, yp = run_fused_conv(native, impl, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool, planes_out=True)
+    assert rel_l2(y, ref) < LAYER_TOL
+    assert planes_match(native, yp, y)
+    _, _, yp2 = run_fused_conv(native, impl, B, H, W, Cin, Cout, s, pro, epi, skip, Cres, pool, planes_out=True, raw_out=False)
+    assert torch.equal(yp2, yp)
+
+
+def test_planes_operands_are_refused_where_no_kernel_takes_them(native):
+    with pytest.raises(ValueError):      # 64 channels: no planes kernel
+        run_fused_conv(native, native.IMPL_TCGEN05, 1, 16, 32, 64, 128, 1, 1, 1, planes_in=True)
+    with pytest.raises(ValueError):      # planes output from a stride-1 raw-input conv
+        run_fused_conv(native, native.IMPL_TCGEN05, 1, 32, 64, 8, 16, 1, 1, 1, planes_out=True)
+    with pytest.raises(ValueError):      # CUDA-core implementation asked for
+        run_fused_conv(native, native.IMPL_SIMT, 1, 32, 64, 8, 16, 1, 1, 1, planes_in=True)
+
+
 def test_tcgen05_refuses_shapes_it_has_no_kernel_for(native):
     with pytest.raises(ValueError):
         run_fused_conv(native, native.IMPL_TCGEN05, 1, 16, 16, 1, 8, 1, 0, 0)     # K = 9: CUDA-core layer
@@ -312,10 +391,14 @@ def test_transposed_conv_persistent_vs_generic(native, B, H, W, Cin, Cout):
         for use in (1, 0):
             native.lib.fn_debug_set_use_s1p(use)
             y = torch.full((B, 2 * H, 2 * W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+            # the persistent kernel also writes the planes form of its output (consumed by conv_pl.cu)
+            yp = torch.full((B, Cout // 4, 2 * H, 2 * W, 8), float("nan"), device="cuda", dtype=torch.bfloat16) if use else None
             native.tconv_fwd(x.to("cuda", torch.bfloat16), w16, b.to("cuda", torch.float32), y, B=B, H=H, W=W, Cin=Cin,
-                             Cout=Cout, impl=native.IMPL_TCGEN05, w_tc=w_tc)
+                             Cout=Cout, impl=native.IMPL_TCGEN05, w_tc=w_tc, y_planes=yp)
             torch.cuda.synchronize()
             assert native.tc_status() == 0
+            if yp is not None:
+                assert planes_match(native, yp, y)
             ys.append(y)
     finally:
         native.lib.fn_debug_set_use_s1p(1)
@@ -520,6 +603,30 @@ def test_net_with_and_without_the_fused_level5_kernel(native):
     finally:
         arch.LEVEL5_FUSED = True
     assert rel_l2(y1, y0) < 2e-3
+
+
+@pytest.mark.parametrize("flags", [dict(), dict(nr_res_blocks=2, filter_size=16)], ids=["default", "deeper_wider"])
+def test_net_on_planes_path_vs_raw_path_and_oracle(native, flags):
+    """FLOWNET_PLANES: the same network with the activations of the 8/16/32-channel levels in MMA-ready planes form
+    (csrc/conv_pl.cu, planes-writing epilogues of the head / stride-2 / transposed kernels) against the raw-tensor path
+    (same kernels' arithmetic: bit-identical up to the epilogue's fused multiply-adds) and the fp64 oracle."""
+    import model.flow_architecture as arch
+    x = fo.synth_boundary(2, 128, 256, seed=21)
+    y0 = _net(native, x.astype(np.uint8), "auto", **flags)
+    try:
+        arch.PLANES = True
+        assert arch._planes_usable(torch.from_numpy(x.astype(np.uint8)).cuda(), 1.0, arch.concat_elu, True,
+                                   flags.get("filter_size", 8))
+        y1 = _net(native, x.astype(np.uint8), "auto", **flags)
+    finally:
+        arch.PLANES = False
+    assert rel_l2(y1, y0) < 2e-3
+    vs = fo.VariableStore(1234, torch.float64)
+    ref = fo.inference(vs, torch.from_numpy(x).double(), 1.0, nr_res_blocks=flags.get("nr_res_blocks", 1),
+                       filter_size=flags.get("filter_size", 8))
+    assert rel_l2(y1, ref) < NET_TOL
+    # same variables, created in the same order
+    assert list(arch.global_variables()) == list(vs.vars)
 
 
 def test_compiled_inference_graph_matches_eager(native):

@@ -36,3 +36,46 @@ for B in (8, 64, 148, 256):
         out[name] = e0.elapsed_time(e1) / 100 * 1000
     assert native.tc_status() == 0
     print("B=%d  five launches %.1f us   fused %.1f us" % (B, out["layers"], out["fused"]), flush=True)
+
+# cold-cache timing: an L2 flush (writing 512 MB) before every run, the flush alone subtracted
+if os.environ.get("AB_COLD"):
+    B = 64
+    arch.reset_variables(1)
+    x = torch.randn(B, 16, 32, 64).to("cuda", torch.bfloat16)
+    junk = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    def flush():
+        junk.fill_(1)
+    def timed_graph(body):
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                body()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for _ in range(10):
+                body()
+        gr.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 30 * 1000
+    t_flush = timed_graph(flush)
+    for name, fn in (("layers", layers), ("fused", fused)):
+        t = timed_graph(lambda: (flush(), fn()))
+        print("cold B=64 %s: %.1f us (flush alone %.1f)" % (name, t - t_flush, t_flush), flush=True)
+    # which operand's coldness costs the time: re-warm the weight stream / the input after the flush
+    wstream, bias = arch.VARIABLES.derived(("level5",), None)
+    acc = torch.zeros(1, device="cuda", dtype=torch.float32)
+    def touch_w():
+        acc.add_(wstream.view(torch.int16)[::8].float().sum())
+    def touch_x():
+        acc.add_(x.view(torch.int16)[..., ::8].float().sum())
+    for nm, pre in (("weights re-warmed", touch_w), ("input re-warmed", touch_x)):
+        t0 = timed_graph(lambda: (flush(), pre()))
+        t1 = timed_graph(lambda: (flush(), pre(), fused()))
+        print("cold B=64 fused, %s: %.1f us" % (nm, t1 - t0), flush=True)
