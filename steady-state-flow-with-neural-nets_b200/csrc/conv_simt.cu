@@ -354,6 +354,99 @@ __global__ void __launch_bounds__(256) k_head3x3(const __nv_bfloat16* __restrict
   }
 }
 
+// Round-2 head for 8 output channels: 16 x 64 tile, a thread owns a vertical strip of 4 output pixels and loads its 6 x 3
+// input values once (18 shared loads per 4 pixels instead of 36), 288 FMAs per strip; stores as in k_head3x3.
+__global__ void __launch_bounds__(256) k_head8_v2(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                  __nv_bfloat16* __restrict__ yp, int B, int H, int W, int tiles_x, int tiles_y) {
+  constexpr int TW = 64, TH = 16, PW = TW + 2, PH = TH + 2;
+  __shared__ __align__(16) float ws[9 * 8 + 8];
+  __shared__ float tile[PH][PW + 2];
+  if (threadIdx.x < 72) ws[threadIdx.x] = __bfloat162float(w[threadIdx.x]);
+  if (threadIdx.x < 8) ws[72 + threadIdx.x] = bias[threadIdx.x];
+  int t = blockIdx.x;
+  const int tx = t % tiles_x;
+  t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int y0 = ty * TH, x0 = tx * TW;
+  {
+    constexpr int NPX = PH * PW, NLD = (NPX + 255) / 256;
+    float v[NLD];
+#pragma unroll
+    for (int k = 0; k < NLD; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      const int r = i / PW, c = i - r * PW;
+      const int iy = y0 + r - 1, ix = x0 + c - 1;
+      v[k] = 0.f;
+      if (i < NPX && iy >= 0 && iy < H && ix >= 0 && ix < W) v[k] = __bfloat162float(x[((size_t)b * H + iy) * W + ix]);
+    }
+#pragma unroll
+    for (int k = 0; k < NLD; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      const int r = i / PW, c = i - r * PW;
+      if (i < NPX) tile[r][c] = v[k];
+    }
+  }
+  __syncthreads();
+  const int cx = threadIdx.x & 63, strip = threadIdx.x >> 6;
+  float acc[4][8];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[r][n] = ws[72 + n];
+#pragma unroll
+  for (int dj = 0; dj < 3; ++dj) {
+    float in[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) in[r] = tile[strip * 4 + r][cx + dj];
+#pragma unroll
+    for (int di = 0; di < 3; ++di) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&ws[(di * 3 + dj) * 8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&ws[(di * 3 + dj) * 8 + 4]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float v = in[r + di];
+        acc[r][0] = fmaf(v, w0.x, acc[r][0]); acc[r][1] = fmaf(v, w0.y, acc[r][1]);
+        acc[r][2] = fmaf(v, w0.z, acc[r][2]); acc[r][3] = fmaf(v, w0.w, acc[r][3]);
+        acc[r][4] = fmaf(v, w1.x, acc[r][4]); acc[r][5] = fmaf(v, w1.y, acc[r][5]);
+        acc[r][6] = fmaf(v, w1.z, acc[r][6]); acc[r][7] = fmaf(v, w1.w, acc[r][7]);
+      }
+    }
+  }
+  const int ox = x0 + cx;
+  if (ox >= W) return;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int oy = y0 + strip * 4 + r;
+    if (oy >= H) break;
+    bf16x8 o;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) o.h[n] = __float2bfloat16(acc[r][n]);
+    const size_t pix = ((size_t)b * H + oy) * W + ox;
+    if (y) *reinterpret_cast<uint4*>(y + pix * 8) = o.v;
+    if (yp) {    // planes form of the output (fn_conv_desc.y_planes): [B][2][H][W][8] = concat_elu(y)
+      uint4 e0, e1;
+      concat_elu8(o.v, e0, e1);
+      __nv_bfloat16* d0 = yp + ((((size_t)b * 2) * H + oy) * W + ox) * 8;
+      *reinterpret_cast<uint4*>(d0) = e0;
+      *reinterpret_cast<uint4*>(d0 + (size_t)H * W * 8) = e1;
+    }
+  }
+}
+
+static int g_head_v2 = 1;      // debug / A-B: 0 sends the 8-channel head back to k_head3x3
+
+static int launch_head8_v2(const fn_conv_desc& d, cudaStream_t stream) {
+  const int tiles_x = (d.W + 63) / 64, tiles_y = (d.H + 15) / 16;
+  const long long grid = (long long)d.B * tiles_x * tiles_y;
+  k_head8_v2<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d.x), reinterpret_cast<const __nv_bfloat16*>(d.w),
+                                                 d.bias, reinterpret_cast<__nv_bfloat16*>(d.y), reinterpret_cast<__nv_bfloat16*>(d.y_planes),
+                                                 d.B, d.H, d.W, tiles_x, tiles_y);
+  count_launch();
+  return check_launch("k_head8_v2");
+}
+
 template <int NOUT>
 static int launch_head(const fn_conv_desc& d, cudaStream_t stream) {
   const int tiles_x = (d.W + 127) / 128, tiles_y = (d.H + 7) / 8;
@@ -443,6 +536,105 @@ __global__ void __launch_bounds__(256) k_tail3x3(const __nv_bfloat16* __restrict
   }
 }
 
+// Round-2 tail for 8 channels.  k_tail3x3 above is instruction-bound (33 us at batch 64 against a 7.7 us HBM floor): per
+// pixel it issues 9 shared loads, 72 bf16 -> fp32 unpacks and 144 FMAs.  Here the 16 x 64 (+halo) tile is staged as FP32 in
+// two 4-channel planes (converted once per pixel; consecutive lanes read consecutive 16-byte vectors: conflict-free) and a
+// thread owns a vertical strip of 4 output pixels: the 6 x 3 input pixels of the strip are loaded once and reused by the
+// three filter rows, so a pixel costs 9 shared loads of data + 9 of weights per FOUR pixels, no unpacks, 144 FMAs.
+__global__ void __launch_bounds__(256) k_tail8_v2(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                  const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W,
+                                                  int tiles_x, int tiles_y) {
+  constexpr int TW = 64, TH = 16, PW = TW + 2, PH = TH + 2;
+  __shared__ __align__(16) float ws[9 * 16 + 4];               // [tap][c][n], bias
+  __shared__ float4 tile[2][PH][PW];                           // [channel half][row][col]
+  for (int i = threadIdx.x; i < 144; i += 256) ws[i] = __bfloat162float(w[i]);
+  if (threadIdx.x < 2) ws[144 + threadIdx.x] = bias[threadIdx.x];
+  int t = blockIdx.x;
+  const int tx = t % tiles_x;
+  t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int y0 = ty * TH, x0 = tx * TW;
+  {
+    constexpr int NPX = PH * PW, NLD = (NPX + 255) / 256;      // 1188 pixels, 5 per thread
+    uint4 v[NLD];
+#pragma unroll
+    for (int k = 0; k < NLD; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      const int r = i / PW, c = i - r * PW;
+      const int iy = y0 + r - 1, ix = x0 + c - 1;
+      v[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < NPX && iy >= 0 && iy < H && ix >= 0 && ix < W)
+        v[k] = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + iy) * W + ix) * 8));
+    }
+#pragma unroll
+    for (int k = 0; k < NLD; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      const int r = i / PW, c = i - r * PW;
+      if (i < NPX) {
+        tile[0][r][c] = make_float4(__uint_as_float(v[k].x << 16), __uint_as_float(v[k].x & 0xffff0000u),
+                                    __uint_as_float(v[k].y << 16), __uint_as_float(v[k].y & 0xffff0000u));
+        tile[1][r][c] = make_float4(__uint_as_float(v[k].z << 16), __uint_as_float(v[k].z & 0xffff0000u),
+                                    __uint_as_float(v[k].w << 16), __uint_as_float(v[k].w & 0xffff0000u));
+      }
+    }
+  }
+  __syncthreads();
+  const int cx = threadIdx.x & 63, strip = threadIdx.x >> 6;   // column, 4-row strip
+  float a0[4], a1[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { a0[r] = ws[144]; a1[r] = ws[145]; }
+#pragma unroll
+  for (int dj = 0; dj < 3; ++dj) {
+    float4 lo[6], hi[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      lo[r] = tile[0][strip * 4 + r][cx + dj];
+      hi[r] = tile[1][strip * 4 + r][cx + dj];
+    }
+#pragma unroll
+    for (int di = 0; di < 3; ++di) {
+      float wt[16];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const float4 wv = *reinterpret_cast<const float4*>(&ws[(di * 3 + dj) * 16 + 4 * f]);
+        wt[4 * f] = wv.x; wt[4 * f + 1] = wv.y; wt[4 * f + 2] = wv.z; wt[4 * f + 3] = wv.w;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 p0 = lo[r + di], p1 = hi[r + di];
+        a0[r] = fmaf(p0.x, wt[0], a0[r]);  a1[r] = fmaf(p0.x, wt[1], a1[r]);
+        a0[r] = fmaf(p0.y, wt[2], a0[r]);  a1[r] = fmaf(p0.y, wt[3], a1[r]);
+        a0[r] = fmaf(p0.z, wt[4], a0[r]);  a1[r] = fmaf(p0.z, wt[5], a1[r]);
+        a0[r] = fmaf(p0.w, wt[6], a0[r]);  a1[r] = fmaf(p0.w, wt[7], a1[r]);
+        a0[r] = fmaf(p1.x, wt[8], a0[r]);  a1[r] = fmaf(p1.x, wt[9], a1[r]);
+        a0[r] = fmaf(p1.y, wt[10], a0[r]); a1[r] = fmaf(p1.y, wt[11], a1[r]);
+        a0[r] = fmaf(p1.z, wt[12], a0[r]); a1[r] = fmaf(p1.z, wt[13], a1[r]);
+        a0[r] = fmaf(p1.w, wt[14], a0[r]); a1[r] = fmaf(p1.w, wt[15], a1[r]);
+      }
+    }
+  }
+  const int ox = x0 + cx;
+  if (ox < W) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int oy = y0 + strip * 4 + r;
+      if (oy < H) *reinterpret_cast<float2*>(y + (((size_t)b * H + oy) * W + ox) * 2) = make_float2(tanhf(a0[r]), tanhf(a1[r]));
+    }
+  }
+}
+
+static int g_tail_v2 = 1;      // debug / A-B: 0 sends the 8-channel tail back to k_tail3x3
+
+static int launch_tail8_v2(const fn_conv_desc& d, cudaStream_t stream) {
+  const int tiles_x = (d.W + 63) / 64, tiles_y = (d.H + 15) / 16;
+  const long long grid = (long long)d.B * tiles_x * tiles_y;
+  k_tail8_v2<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d.x), reinterpret_cast<const __nv_bfloat16*>(d.w),
+                                                 d.bias, reinterpret_cast<float*>(d.y), d.B, d.H, d.W, tiles_x, tiles_y);
+  count_launch();
+  return check_launch("k_tail8_v2");
+}
+
 template <int CIN>
 static int launch_tail(const fn_conv_desc& d, cudaStream_t stream) {
   const int tiles_x = (d.W + 127) / 128, tiles_y = (d.H + 7) / 8;
@@ -457,7 +649,7 @@ static int launch_tail(const fn_conv_desc& d, cudaStream_t stream) {
 // returns true (and sets rc) if a specialised head/tail kernel took the launch
 static bool try_direct(const fn_conv_desc& d, cudaStream_t stream, int& rc) {
   if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_NONE || d.skip || d.keep_prob < 1.0f) return false;
-  if (d.epilogue == FN_EPI_BIAS && d.Cin == 1 && d.Cout == 8) { rc = launch_head<8>(d, stream); return true; }
+  if (d.epilogue == FN_EPI_BIAS && d.Cin == 1 && d.Cout == 8) { rc = g_head_v2 ? launch_head8_v2(d, stream) : launch_head<8>(d, stream); return true; }
   if (d.epilogue == FN_EPI_BIAS && d.Cin == 1 && d.Cout == 16) { rc = launch_head<16>(d, stream); return true; }
   if (d.epilogue == FN_EPI_BIAS && d.Cin == 1) {
     if (d.Cout == 8) { rc = launch_direct<1, 8, false>(d, stream); return true; }
@@ -465,7 +657,7 @@ static bool try_direct(const fn_conv_desc& d, cudaStream_t stream, int& rc) {
     if (d.Cout == 32) { rc = launch_direct<1, 32, false>(d, stream); return true; }
   }
   if (d.epilogue == FN_EPI_TANH && d.Cout == 2) {
-    if (d.Cin == 8) { rc = launch_tail<8>(d, stream); return true; }
+    if (d.Cin == 8) { rc = g_tail_v2 ? launch_tail8_v2(d, stream) : launch_tail<8>(d, stream); return true; }
     if (d.Cin == 16) { rc = launch_tail<16>(d, stream); return true; }
     if (d.Cin == 32) { rc = launch_direct<32, 2, true>(d, stream); return true; }
   }
@@ -546,3 +738,7 @@ int tconv_fwd_simt(const fn_tconv_desc& d, cudaStream_t stream) {
 }
 
 }  // namespace fn
+
+extern "C" {
+void fn_debug_set_tail_v2(int v) { fn::g_tail_v2 = v ? 1 : 0; fn::g_head_v2 = v ? 1 : 0; }
+}

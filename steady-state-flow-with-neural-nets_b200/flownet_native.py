@@ -126,6 +126,7 @@ DEBUG_SYMBOLS = [
     ("fn_debug_set_pl_grid_cap", None, [C.c_int]),
     ("fn_debug_set_pl_ne", None, [C.c_int]),
     ("fn_debug_set_pl_j", None, [C.c_int]),
+    ("fn_debug_set_tail_v2", None, [C.c_int]),
     ("fn_debug_set_pl_ni", None, [C.c_int]),
     ("fn_debug_set_pl_knock", None, [C.c_int]),
 ]
