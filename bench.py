@@ -298,6 +298,9 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # the serving loop's pinned buffers should live on the GPU's NUMA node (utils/numa.py); FLOWNET_NUMA=0: leave unpinned
+    from utils.numa import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local) if os.environ.get("FLOWNET_NUMA", "1") != "0" else None
 
     import flownet_native as native
     import model.flow_architecture as arch
@@ -435,7 +438,10 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel()) * world,
                     "d2h_bytes_per_step": int(out_host.numel() * 4) * world, "ms_per_step": ms_e2e / args.steps,
                     "how": "CompiledInference.stream_host: two alternating graphs, uploads / downloads on side streams straight into / out of their static buffers",
-                    "serial_value": world * B * args.steps / (ms_e2e_serial * 1e-3)},
+                    "serial_value": world * B * args.steps / (ms_e2e_serial * 1e-3),
+                    # rank 0's host placement (utils/numa.py): pinned buffers allocated after binding to the GPU's NUMA node;
+                    # tools/copy_ceiling.py measures what the copies alone allow at N ranks (profiles/r2_copy_ceiling*.json)
+                    "host_numa": numa},
             # kernels of libflownet.so launched inside the three timed regions (value, e2e, serial e2e): counted graph
             # replays x the launches the C ABI's counter saw while the graph was captured
             "gpu_launches": launches_per_replay * timed_replays,

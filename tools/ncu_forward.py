@@ -1,0 +1,44 @@
+"""Target of the committed ncu captures (profiles/r2_*): builds the default network at batch 64 on the bench's workload
+(car boundaries tiled to 64), runs WARM eager forwards, then ONE more whose launches ncu records:
+
+  ncu --set full --clock-control none --import-source on --launch-skip $((3*N)) --launch-count N -o out python tools/ncu_forward.py
+  (N = the number of launches per forward, printed by `python tools/ncu_forward.py --count`)
+
+and writes the launch order (layer names, algorithmic bytes / flops) to gpurun_out/ncu_forward_layers.json so that
+tools/ncu_to_json.py can key the ncu rows by layer."""
+import json, os, sys
+import numpy as np
+import torch
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, os.path.join(ROOT, "steady-state-flow-with-neural-nets_b200"))
+import flownet_native as native
+import model.flow_architecture as arch
+import model.flow_net as flow_net
+from utils.synthetic import load_car_boundaries
+
+B = int(os.environ.get("NCU_BATCH", "64"))
+cars = load_car_boundaries(os.path.join(ROOT, "tests", "golden", "cars_128x256.npz"))
+x = torch.from_numpy(np.ascontiguousarray(cars[np.arange(B) % len(cars)])).cuda()
+arch.reset_variables(1234)
+n0 = native.launch_count()
+flow_net.inference(x, 1.0)
+torch.cuda.synchronize()
+# the first forward also packs the weights; count a steady-state one
+n1 = native.launch_count()
+flow_net.inference(x, 1.0)
+torch.cuda.synchronize()
+per_fwd = native.launch_count() - n1
+if "--count" in sys.argv:
+    print(per_fwd)
+    sys.exit(0)
+flow_net.inference(x, 1.0)
+torch.cuda.synchronize()
+arch._PROFILE = []
+flow_net.inference(x, 1.0)          # <- the recorded forward (events add no kernel launches)
+torch.cuda.synchronize()
+rows = [{k: v for k, v in r.items() if k != "events"} for r in arch._PROFILE]
+arch._PROFILE = None
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+with open(os.path.join(ROOT, "gpurun_out", "ncu_forward_layers.json"), "w") as f:
+    json.dump({"batch": B, "launches_per_forward": per_fwd, "setup_launches": n1 - n0, "rows": rows}, f, indent=1)
+print("launches per forward:", per_fwd, " setup:", n1 - n0)
