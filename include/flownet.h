@@ -188,8 +188,15 @@ typedef struct fn_level5_desc {
   const float* bias;
   void*        y;
   void*        y_planes;    /* optional: concat_elu(y) in planes form [B,16,16,32,8] (see fn_conv_desc) */
+  /* 1: two CTAs per image (a thread-block cluster, csrc/conv_l5c.cu), each computing half of every convolution's output
+   * channels.  w_stream then holds rank 0's five images followed by rank 1's (fn_level5_split_weight_bytes() in all), where
+   * rank r's image of a convolution packs its output columns [r F/2, (r+1) F/2) -- for the gated ones the u columns then
+   * the matching v columns -- and bias is fp32 [2][64 | 64+64 | 64 | 64+64 | 32] in the same order. */
+  int32_t      split;
+  int32_t      reserved;
 } fn_level5_desc;
 int64_t fn_level5_weight_bytes(void);
+int64_t fn_level5_split_weight_bytes(void);
 int fn_level5_supported(int32_t H, int32_t W, int32_t C);
 int fn_level5_fwd(const fn_level5_desc* d, void* stream);
 

@@ -58,6 +58,8 @@ int adam_step(float* param, const float* grad, float* m, float* v, long long n, 
               double b2, double eps, cudaStream_t s);
 int level5_fwd(const fn_level5_desc& d, cudaStream_t stream);      // conv_l5.cu
 long long level5_weight_bytes();
+int level5c_fwd(const fn_level5_desc& d, cudaStream_t stream);     // conv_l5c.cu
+long long level5c_weight_bytes();
 
 static int validate_conv(const fn_conv_desc& d) {
   FN_REQUIRE(d.B > 0 && d.H > 0 && d.W > 0 && d.Cin > 0 && d.Cout > 0, FN_E_INVAL,
@@ -203,6 +205,7 @@ int fn_pack_conv_weights_tc(const void* w, const void* w_skip, void* dst, int32_
 }
 
 int64_t fn_level5_weight_bytes(void) { return level5_weight_bytes(); }
+int64_t fn_level5_split_weight_bytes(void) { return level5c_weight_bytes(); }
 int fn_level5_supported(int32_t H, int32_t W, int32_t C) { return (H == 16 && W == 32 && C == 64 && tma::get_encode() != nullptr) ? 1 : 0; }
 int fn_level5_fwd(const fn_level5_desc* d, void* stream) {
   FN_REQUIRE(d != nullptr, FN_E_INVAL, "fn_level5_fwd: null descriptor");
@@ -210,7 +213,7 @@ int fn_level5_fwd(const fn_level5_desc* d, void* stream) {
   FN_REQUIRE(d->H == 16 && d->W == 32 && d->C == 64, FN_E_UNSUPPORTED,
              "fn_level5_fwd: built for the 128x256 grid's level-5 input [B,16,32,64], got [B,%d,%d,%d]", d->H, d->W, d->C);
   FN_REQUIRE(aligned16(d->x) && aligned16(d->y) && aligned16(d->w_stream), FN_E_ALIGN, "fn_level5_fwd: x/y/w_stream must be 16-byte aligned");
-  return level5_fwd(*d, (cudaStream_t)stream);
+  return d->split ? level5c_fwd(*d, (cudaStream_t)stream) : level5_fwd(*d, (cudaStream_t)stream);
 }
 
 int fn_nonlinearity(const void* x, void* y, int64_t n, int32_t C, int32_t kind, void* stream) {

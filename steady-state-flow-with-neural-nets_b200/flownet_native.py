@@ -52,7 +52,7 @@ class LbmDesc(C.Structure):
 class Level5Desc(C.Structure):
     _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
                 ("x", C.c_void_p), ("w_stream", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p),
-                ("y_planes", C.c_void_p)]
+                ("y_planes", C.c_void_p), ("split", C.c_int32), ("reserved", C.c_int32)]
 
 
 class TConvDesc(C.Structure):
@@ -82,6 +82,7 @@ SYMBOLS = [
     ("fn_conv_weights_tc_bytes", C.c_int64, [C.c_int32] * 5),
     ("fn_pack_conv_weights_tc", C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     ("fn_level5_weight_bytes", C.c_int64, []),
+    ("fn_level5_split_weight_bytes", C.c_int64, []),
     ("fn_level5_supported", C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     ("fn_level5_fwd", C.c_int, [C.POINTER(Level5Desc), _P]),
     ("fn_nonlinearity", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
@@ -248,15 +249,18 @@ def level5_supported(H, W, Cc):
     return bool(lib.fn_level5_supported(int(H), int(W), int(Cc)))
 
 
-def level5_fwd(x, w_stream, bias, y, y_planes=None):
-    """x: bf16 [B,16,32,64] -> y: bf16 [B,16,32,64]: the 8x16 level in one launch (fn_level5_fwd)"""
+def level5_fwd(x, w_stream, bias, y, y_planes=None, split=False):
+    """x: bf16 [B,16,32,64] -> y: bf16 [B,16,32,64]: the 8x16 level in one launch (fn_level5_fwd).  split: two CTAs per
+    image, w_stream / bias in the per-rank form (include/flownet.h)"""
     _require_cuda(x, w_stream, bias, y, y_planes)
-    if w_stream.numel() * w_stream.element_size() != int(lib.fn_level5_weight_bytes()) or bias.numel() != 832:
+    want = int(lib.fn_level5_split_weight_bytes() if split else lib.fn_level5_weight_bytes())
+    if w_stream.numel() * w_stream.element_size() != want or bias.numel() != 832:
         raise ValueError("level5_fwd: weight stream / bias size")
     d = Level5Desc()
     d.B, d.H, d.W, d.C = x.shape
     d.x, d.w_stream, d.bias, d.y = x.data_ptr(), w_stream.data_ptr(), bias.data_ptr(), y.data_ptr()
     d.y_planes = y_planes.data_ptr() if y_planes is not None else None
+    d.split = int(bool(split))
     _check(lib.fn_level5_fwd(C.byref(d), stream_ptr()), "fn_level5_fwd")
 
 

@@ -364,6 +364,10 @@ def _level5_fusable(x, nr_res_blocks, keep_prob, nonlinearity, gated, filter_siz
             native.level5_supported(x.shape[1], x.shape[2], x.shape[3]))
 
 
+# two CTAs per image (thread-block cluster, csrc/conv_l5c.cu): FLOWNET_L5_SPLIT=0 goes back to one CTA per image
+LEVEL5_SPLIT = os.environ.get("FLOWNET_L5_SPLIT", "1") != "0"
+
+
 def _level5_fused(x):
     """resnet_5_downsample, resnet_5_0 and up_conv_1 (reference :207-215).  Variables are created in the reference's
     order; the five tensor-core weight images and biases are concatenated once per variable version."""
@@ -381,13 +385,30 @@ def _level5_fused(x):
         return w16, bt.contiguous(), native.pack_conv_weights_tc(w16, None, 3, 128, 0, 64, False)
 
     tpart = VARIABLES.derived(("tconv", scope), make_t)
+    # two CTAs per image while the clusters fit the GPU in one wave (measured: 52 vs 67 us at batch 64, 204 vs 135 us at 256)
+    split = LEVEL5_SPLIT and 2 * x.shape[0] <= torch.cuda.get_device_properties(dev).multi_processor_count
 
     def make():
         wstream = torch.cat([pt[3] for pt in parts] + [tpart[2]])
         bias = torch.cat([pt[2] for pt in parts] + [tpart[1]]).to(torch.float32).contiguous()
         return wstream, bias
 
-    wstream, bias = VARIABLES.derived(("level5",), make)
+    def make_split():
+        # rank r computes output columns [r F/2, (r+1) F/2) of every convolution (gated: those u columns, then the matching v's)
+        ws, bs = [], []
+        for r in range(2):
+            for (w16, _, b, _), (k, c, g) in zip(parts, shapes):
+                f = c // 2 if g else c
+                cols = torch.arange(r * f // 2, (r + 1) * f // 2, device=dev)
+                if g:
+                    cols = torch.cat([cols, cols + f])
+                ws.append(native.pack_conv_weights_tc(w16[:, :, cols].contiguous(), None, 3, k, 0, cols.numel(), g))
+                bs.append(b[cols])
+            ws.append(native.pack_conv_weights_tc(tpart[0][:, :, r * 32:(r + 1) * 32].contiguous(), None, 3, 128, 0, 32, False))
+            bs.append(tpart[1][r * 32:(r + 1) * 32])
+        return torch.cat(ws), torch.cat(bs).to(torch.float32).contiguous()
+
+    wstream, bias = VARIABLES.derived(("level5", split), make_split if split else make)
     x = native.to_bf16(x)
     B = x.shape[0]
     y = torch.empty((B, 16, 32, 64), device=dev, dtype=torch.bfloat16)
@@ -397,7 +418,7 @@ def _level5_fused(x):
         macs = B * 128 * (9 * 128 * 128 + 9 * 256 * 256 + 9 * 256 * 128 + 9 * 256 * 256 + 9 * 128 * 64)
         rec = dict(name="level5_fused(resnet_5_downsample+resnet_5_0+up_conv_1)", kind="fused", out_hw=(16, 32), K_tap=256, N=256,
                    stride=1, alg_bytes=(x.numel() + y.numel()) * 2, flops=2 * macs)
-    _profiled(rec, lambda: native.level5_fwd(x, wstream, bias, y))
+    _profiled(rec, lambda: native.level5_fwd(x, wstream, bias, y, split=split))
     return y
 
 

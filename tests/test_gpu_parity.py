@@ -556,12 +556,14 @@ def test_deeper_wider_variant_at_128x256_vs_oracle(native):
     assert rel_l2(y, ref) < NET_TOL
 
 
+@pytest.mark.parametrize("split", [False, True], ids=["one_cta_per_image", "cluster_of_two"])
 @pytest.mark.parametrize("B", [1, 5, 150])
-def test_level5_fused_kernel_vs_layer_by_layer_and_oracle(native, B):
+def test_level5_fused_kernel_vs_layer_by_layer_and_oracle(native, B, split, monkeypatch):
     """csrc/conv_l5.cu: resnet_5_downsample + resnet_5_0 + up_conv_1 in one launch against the same five convolutions as
     separate launches (same operands, same bf16 rounding points, same MMA order) and against the fp64 oracle on
     bf16-rounded inputs."""
     import model.flow_architecture as arch
+    monkeypatch.setattr(arch, "LEVEL5_SPLIT", split)       # csrc/conv_l5.cu or the channel-split cluster kernel csrc/conv_l5c.cu
     arch.reset_variables(77)
     g = torch.Generator().manual_seed(B)
     x = torch.randn(B, 16, 32, 64, generator=g).to(torch.bfloat16)

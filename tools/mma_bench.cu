@@ -127,6 +127,67 @@ __global__ void __launch_bounds__(128) k_bench(Cfg c, long long* out) {
   }
 }
 
+// ---- cta_group::2: one tcgen05.mma over a CTA pair (M = 256: each SM computes its own 128 rows from its own shared
+// memory, B is split N/2 per CTA), issued by the even CTA.  Question: does a pair instruction cost what a single-SM one
+// costs (then the pair does twice the rows per instruction-slot) or twice that?
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) k_bench2(Cfg c, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(ptx::smem_u32(&bar), 1);
+    ptx::fence_mbar_init();
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before_sync();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = ptx::idesc_bf16_f32(256, c.N);
+  const uint32_t a0 = (ptx::smem_u32(smem) + 1023u) & ~1023u, b0 = a0 + 96 * 1024;
+  const uint32_t barp = ptx::smem_u32(&bar);
+  if (rank == 0 && threadIdx.x == 0) {
+    const uint64_t abase = desc_generic(a0, c.a_lbo, c.a_sbo, c.a_type);
+    const uint64_t bbase = desc_generic(b0, c.b_lbo, c.b_sbo, c.b_type);
+    const uint64_t astep = c.a_step >> 4, bstep = c.b_step >> 4;
+    const long long t0 = clock64();
+    for (int r = 0; r < c.R; r += 8) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint64_t bd = bbase + (uint64_t)q * bstep;
+        const uint64_t ad = abase + (uint64_t)q * astep;
+        for (int j = 0; j < c.J; ++j) {
+          const uint32_t d = tmem + (uint32_t)(j * c.N) % 512u;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(ad + 8u * j), "l"(bd), "r"(idesc), "r"(1u)
+              : "memory");
+        }
+      }
+    }
+    const long long t1 = clock64();
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(barp) : "memory");
+    ptx::mbar_wait(barp, 0);
+    const long long t2 = clock64();
+    out[(blockIdx.x / 2) * 2 + 0] = t1 - t0;
+    out[(blockIdx.x / 2) * 2 + 1] = t2 - t0;
+  }
+  ptx::tc_fence_before_sync();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 0) {
+    ptx::tc_fence_after_sync();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
 int main() {
   long long* d_out;
   cudaMalloc(&d_out, 148 * 2 * sizeof(long long));
@@ -166,6 +227,37 @@ int main() {
       {"mode3 elect unr8 swz128 N256 J1",       {256, R, 1, 16, 1024, 2, 16, 1024, 2, 32, 32, 1, 3}},
       {"mode3 PU34 N16 J4 x148 CTAs",           {16, R, 148, 9808, 544, 0, 16 * 16, 128, 0, 16, 512, 4, 3}},
   };
+  // ---- accumulators in rotation (J) and the CTA-pair instruction, tap-shifted no-swizzle operands as in the conv kernels
+  {
+    cudaFuncSetAttribute(k_bench2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const int Ns[] = {16, 32, 64, 128, 256};
+    const int Js[] = {1, 2, 4, 8, 16};
+    for (int N : Ns)
+      for (int J : Js) {
+        if (J * N > 512 && J > 1) continue;
+        Cfg c = {N, R, 1, 9808, 544, 0, (uint32_t)N * 16, 128, 0, 16, (uint32_t)N * 32, J, 3};
+        long long h1[2] = {0, 0}, h2[2] = {0, 0};
+        cudaMemset(d_out, 0, 148 * 2 * sizeof(long long));
+        k_bench<<<1, 128, 200 * 1024>>>(c, d_out);
+        cudaError_t e1 = cudaDeviceSynchronize();
+        cudaMemcpy(h1, d_out, sizeof(h1), cudaMemcpyDeviceToHost);
+        cudaMemset(d_out, 0, 148 * 2 * sizeof(long long));
+        k_bench2<<<2, 128, 200 * 1024>>>(c, d_out);
+        cudaError_t e2 = cudaDeviceSynchronize();
+        cudaMemcpy(h2, d_out, sizeof(h2), cudaMemcpyDeviceToHost);
+        // all 74 pairs at once
+        long long h3[2] = {0, 0};
+        cudaMemset(d_out, 0, 148 * 2 * sizeof(long long));
+        k_bench2<<<148, 128, 200 * 1024>>>(c, d_out);
+        cudaError_t e3 = cudaDeviceSynchronize();
+        cudaMemcpy(h3, d_out, sizeof(h3), cudaMemcpyDeviceToHost);
+        const int mmas = R * J;
+        printf("N=%3d J=%2d   1-SM M=128: %6.1f clk/MMA   CTA pair M=256: %6.1f clk/MMA  (74 pairs: %6.1f)   %s %s %s\n", N, J,
+               (double)h1[1] / mmas, (double)h2[1] / mmas, (double)h3[1] / mmas, e1 == cudaSuccess ? "" : cudaGetErrorString(e1),
+               e2 == cudaSuccess ? "" : cudaGetErrorString(e2), e3 == cudaSuccess ? "" : cudaGetErrorString(e3));
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return 1;
+      }
+  }
   for (auto& nc : cases) {
     cudaMemset(d_out, 0, 148 * 2 * sizeof(long long));
     k_bench<<<nc.c.ctas, 128, 200 * 1024>>>(nc.c, d_out);
