@@ -4,6 +4,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I steady-state-flow-with-neural-nets_b200/csrc \
 //        -I include tools/mma_bench.cu -o tools/mma_bench
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "ptx.cuh"
 
@@ -188,7 +189,106 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) k_bench2(Cfg c,
   }
 }
 
+
+// ---- what is the fixed cost of a tcgen05.mma made of?  Straight-line issue (compile-time J, descriptors = base + immediates),
+// R outer rounds of 8 k-steps x J MMAs; the slope between two R values removes the start / drain latency.
+//   ACC  0: the J MMAs of a k-step go to J different accumulators (rotation)   1: all MMAs accumulate into ONE accumulator
+//   BSAME 1: the J MMAs of a k-step share the B tile (as the conv kernels' taps do)   0: every MMA names a different B tile
+// launched with 1 or 2 CTAs per SM (smem 96 KB, 256 TMEM columns each) to see whether independent CTAs overlap the cost.
+template <int J, int ACC, int BSAME>
+__global__ void __launch_bounds__(128) k_bench3(int N, int R, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0) {
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), 256);
+    ptx::tmem_relinquish();
+  }
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(ptx::smem_u32(&bar), 1);
+    ptx::fence_mbar_init();
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = ptx::idesc_bf16_f32(128, N);
+  const uint32_t a0 = ptx::smem_u32(smem), b0 = a0 + 32 * 1024;
+  const uint32_t barp = ptx::smem_u32(&bar);
+  if (warp == 1) {
+    const uint32_t leader = elect_one_sync();
+    const uint64_t abase = desc_generic(a0, 9808, 544, 0);
+    const uint64_t bbase = desc_generic(b0, (uint32_t)N * 16, 128, 0);
+    const uint32_t bstep = ((uint32_t)N * 32u) >> 4;      // one k-step of packed weights, in 16-byte units
+    const int nb = 65536 / (N * 32);                      // B tiles that fit behind b0
+    const long long t0 = clock64();
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const int bi = BSAME ? q : (q * J + j) % nb;
+          const uint32_t d = tmem + (ACC ? 0u : (uint32_t)(j * N) % 256u);
+          if (leader) ptx::mma_bf16_ss(d, abase + (uint64_t)(q + 8 * j), bbase + (uint64_t)bi * bstep, idesc, 1u);
+        }
+      }
+    }
+    __syncwarp();
+    if (leader) ptx::mma_commit(barp);
+    __syncwarp();
+    ptx::mbar_wait(barp, 0);
+    const long long t2 = clock64();
+    if (leader) out[blockIdx.x] = t2 - t0;
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem, 256);
+  }
+}
+
+template <int J, int ACC, int BSAME>
+static void run3(int N, long long* d_out) {
+  if (!ACC && J * N > 256) return;
+  cudaFuncSetAttribute(k_bench3<J, ACC, BSAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  double per[2];
+  for (int two = 0; two < 2; ++two) {
+    const int ctas = two ? 296 : 148;
+    long long h[296];
+    double t[2];
+    for (int k = 0; k < 2; ++k) {
+      const int R = k ? 64 : 16;
+      cudaMemset(d_out, 0, 296 * sizeof(long long));
+      k_bench3<J, ACC, BSAME><<<ctas, 128, 96 * 1024>>>(N, R, d_out);
+      if (cudaDeviceSynchronize() != cudaSuccess) { printf("error %s\n", cudaGetErrorString(cudaGetLastError())); return; }
+      cudaMemcpy(h, d_out, ctas * sizeof(long long), cudaMemcpyDeviceToHost);
+      double s = 0;
+      for (int i = 0; i < ctas; ++i) s += (double)h[i];
+      t[k] = s / ctas;
+    }
+    per[two] = (t[1] - t[0]) / (48.0 * 8 * J);
+  }
+  printf("N=%3d J=%2d %s %s   1 CTA/SM: %6.1f clk/MMA   2 CTAs/SM: %6.1f clk/MMA per CTA = %6.1f per SM\n", N, J,
+         ACC ? "one accumulator " : "rotating accs   ", BSAME ? "B shared by J" : "B differs     ", per[0], per[1], per[1] / 2);
+}
+
 int main() {
+  long long* d3;
+  cudaMalloc(&d3, 296 * sizeof(long long));
+  if (getenv("MMA_BENCH3")) {
+    for (int N : {16, 64, 128}) {
+      run3<1, 0, 1>(N, d3); run3<2, 0, 1>(N, d3); run3<4, 0, 1>(N, d3); run3<8, 0, 1>(N, d3);
+      run3<2, 0, 0>(N, d3); run3<4, 0, 0>(N, d3); run3<8, 0, 0>(N, d3);
+      run3<4, 1, 1>(N, d3); run3<4, 1, 0>(N, d3);
+    }
+    run3<1, 0, 1>(256, d3); run3<4, 1, 1>(256, d3);
+    return 0;
+  }
+
   long long* d_out;
   cudaMalloc(&d_out, 148 * 2 * sizeof(long long));
   cudaFuncSetAttribute(k_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -1,8 +1,8 @@
 """Target of the committed ncu captures (profiles/r2_*): builds the default network at batch 64 on the bench's workload
 (car boundaries tiled to 64), runs WARM eager forwards, then ONE more whose launches ncu records:
 
-  ncu --set full --clock-control none --import-source on --launch-skip $((3*N)) --launch-count N -o out python tools/ncu_forward.py
-  (N = the number of launches per forward, printed by `python tools/ncu_forward.py --count`)
+  ncu --set full --clock-control none --import-source on --profile-from-start off -o out python tools/ncu_forward.py
+  (the recorded forward is bracketed by cudaProfilerStart / Stop)
 
 and writes the launch order (layer names, algorithmic bytes / flops) to gpurun_out/ncu_forward_layers.json so that
 tools/ncu_to_json.py can key the ncu rows by layer."""
@@ -34,8 +34,10 @@ if "--count" in sys.argv:
 flow_net.inference(x, 1.0)
 torch.cuda.synchronize()
 arch._PROFILE = []
+torch.cuda.profiler.start()         # ncu --profile-from-start off: only the next forward is recorded
 flow_net.inference(x, 1.0)          # <- the recorded forward (events add no kernel launches)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 rows = [{k: v for k, v in r.items() if k != "events"} for r in arch._PROFILE]
 arch._PROFILE = None
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
