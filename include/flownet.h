@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FN_ABI_VERSION 6
+#define FN_ABI_VERSION 7
 
 /* error codes (negative) */
 #define FN_E_INVAL      (-1)   /* null pointer, bad enum, non-positive dim */
@@ -199,6 +199,26 @@ int64_t fn_level5_weight_bytes(void);
 int64_t fn_level5_split_weight_bytes(void);
 int fn_level5_supported(int32_t H, int32_t W, int32_t C);
 int fn_level5_fwd(const fn_level5_desc* d, void* stream);
+
+/* ---- the 16x32 level of the 128x256 grid in two launches around fn_level5_fwd (csrc/conv_l4.cu), flow_architecture.py:202-205,
+ * 217-222: a cluster of two CTAs per image, activations resident in shared memory between the convolutions.
+ *   up = 0: x = x3 bf16 [B,32,64,32] (output of "resnet_3_0") -> y = x4 bf16 [B,16,32,64] (output of "resnet_4_0");
+ *           w_stream: tensor-core images of resnet_4_downsample_conv_1 / _conv_2, resnet_4_0_conv_1 / _conv_2, back to back;
+ *           bias fp32 [64 | 128 | 64 | 128]
+ *   up = 1: x = z bf16 [B,16,32,64] (output of "up_conv_1"), skip = x4 -> y bf16 [B,32,64,32] (output of "up_conv_2");
+ *           w_stream: resnet_up_1_0_conv_1 with the nin's 8 k-steps appended (fn_pack_conv_weights_tc with w_skip),
+ *           resnet_up_1_0_conv_2, up_conv_2 ([9,64,32] GEMM-B form); bias fp32 [64 (conv_1 + nin) | 128 | 32]
+ * Inference only, default flags; any other shape: FN_E_UNSUPPORTED (the layer-by-layer calls are the general path). */
+typedef struct fn_level4_desc {
+  int32_t B, up;
+  const void*  x;
+  const void*  skip;        /* up = 1 only */
+  const void*  w_stream;    /* fn_level4_weight_bytes(up) bytes */
+  const float* bias;
+  void*        y;
+} fn_level4_desc;
+int64_t fn_level4_weight_bytes(int32_t up);
+int fn_level4_fwd(const fn_level4_desc* d, void* stream);
 
 /* standalone nonlinearity (the public concat_elu()/set_nonlinearity() API) :14-29
  * x: bf16 [n, C] -> y: bf16 [n, C or 2C] */

@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FLOWNET_LIB", os.path.join(_HERE, "libflownet.so"))   # override: A/B builds
 
-FN_ABI_VERSION = 6
+FN_ABI_VERSION = 7
 # enum fn_prologue
 PRO_NONE, PRO_CONCAT_ELU, PRO_ELU, PRO_CONCAT_RELU, PRO_RELU = 0, 1, 2, 3, 4
 # enum fn_epilogue
@@ -55,6 +55,11 @@ class Level5Desc(C.Structure):
                 ("y_planes", C.c_void_p), ("split", C.c_int32), ("reserved", C.c_int32)]
 
 
+class Level4Desc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("up", C.c_int32), ("x", C.c_void_p), ("skip", C.c_void_p), ("w_stream", C.c_void_p),
+                ("bias", C.c_void_p), ("y", C.c_void_p)]
+
+
 class TConvDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
@@ -85,6 +90,8 @@ SYMBOLS = [
     ("fn_level5_split_weight_bytes", C.c_int64, []),
     ("fn_level5_supported", C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     ("fn_level5_fwd", C.c_int, [C.POINTER(Level5Desc), _P]),
+    ("fn_level4_weight_bytes", C.c_int64, [C.c_int32]),
+    ("fn_level4_fwd", C.c_int, [C.POINTER(Level4Desc), _P]),
     ("fn_nonlinearity", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     ("fn_cast_f32_to_bf16", C.c_int, [_P, _P, C.c_int64, _P]),
     ("fn_cast_u8_to_bf16", C.c_int, [_P, _P, C.c_int64, _P]),
@@ -262,6 +269,25 @@ def level5_fwd(x, w_stream, bias, y, y_planes=None, split=False):
     d.y_planes = y_planes.data_ptr() if y_planes is not None else None
     d.split = int(bool(split))
     _check(lib.fn_level5_fwd(C.byref(d), stream_ptr()), "fn_level5_fwd")
+
+
+def level4_fwd(x, w_stream, bias, y, skip=None):
+    """The 16x32 level around fn_level5_fwd (fn_level4_fwd, csrc/conv_l4.cu).  skip is None: x = x3 bf16 [B,32,64,32] ->
+    y = x4 bf16 [B,16,32,64] (resnet_4_downsample + resnet_4_0); with skip = x4: x = up_conv_1's output [B,16,32,64] ->
+    y bf16 [B,32,64,32] (resnet_up_1_0 + up_conv_2)."""
+    _require_cuda(x, w_stream, bias, y, skip)
+    up = skip is not None
+    want_x, want_y = ((16, 32, 64), (32, 64, 32)) if up else ((32, 64, 32), (16, 32, 64))
+    if tuple(x.shape[1:]) != want_x or tuple(y.shape[1:]) != want_y or y.shape[0] != x.shape[0] or \
+            (up and tuple(skip.shape) != tuple(x.shape)):
+        raise ValueError("level4_fwd: tensor shapes")
+    if w_stream.numel() * w_stream.element_size() != int(lib.fn_level4_weight_bytes(int(up))) or bias.numel() != (224 if up else 384):
+        raise ValueError("level4_fwd: weight stream / bias size")
+    d = Level4Desc()
+    d.B, d.up = x.shape[0], int(up)
+    d.x, d.w_stream, d.bias, d.y = x.data_ptr(), w_stream.data_ptr(), bias.data_ptr(), y.data_ptr()
+    d.skip = skip.data_ptr() if up else None
+    _check(lib.fn_level4_fwd(C.byref(d), stream_ptr()), "fn_level4_fwd")
 
 
 def pack_conv_weights_tc(w, w_skip, ksize, Keff, Kskip, Cout, gated):

@@ -422,6 +422,81 @@ def _level5_fused(x):
     return y
 
 
+# --------------------------------------------------------------------------- the 16x32 level in two launches
+LEVEL4_FUSED = os.environ.get("FLOWNET_L4", "1") != "0"
+# clusters of two CTAs per image: used while they fit the GPU in at most this many waves
+LEVEL4_MAX_WAVES = float(os.environ.get("FLOWNET_L4_WAVES", "1"))
+
+
+def _level4_fusable(x, nr_res_blocks, keep_prob, nonlinearity, gated, filter_size):
+    """fn_level4_fwd takes the reference's flags at the 128x256 grid (x = resnet_3_0's output [B,32,64,32]) in inference;
+    it runs together with the fused 8x16 level."""
+    if not (LEVEL4_FUSED and LEVEL5_FUSED and TAPE is None and IMPL == native.IMPL_AUTO and nr_res_blocks == 1 and keep_prob >= 1.0
+            and nonlinearity is concat_elu and gated and filter_size == 64 and tuple(x.shape[1:]) == (32, 64, 32)
+            and native.level5_supported(16, 32, 64)):
+        return False
+    sms = torch.cuda.get_device_properties(x.device).multi_processor_count
+    return 2 * x.shape[0] <= LEVEL4_MAX_WAVES * sms
+
+
+def _tconv_parts(scope, cin, cout, dev):
+    wt = _variable(scope + '/weights', [3, 3, cout, cin], device=dev)
+    bt = _variable(scope + '/biases', [cout], device=dev)
+
+    def make_t():
+        w16 = wt.permute(0, 1, 3, 2).reshape(9, cin, cout).to(torch.bfloat16).contiguous()
+        return w16, bt.contiguous(), native.pack_conv_weights_tc(w16, None, 3, cin, 0, cout, False)
+
+    return VARIABLES.derived(("tconv", scope), make_t)
+
+
+def _level4_down(x):
+    """resnet_4_downsample and resnet_4_0 (reference :202-205) in one launch; variables in the reference's order."""
+    dev = x.device
+    names = ("resnet_4_downsample_conv_1_conv", "resnet_4_downsample_conv_2_conv", "resnet_4_0_conv_1_conv", "resnet_4_0_conv_2_conv")
+    shapes = ((64, 64, False), (128, 128, True), (128, 64, False), (128, 128, True))
+    parts = [_conv_weights(n, 3, k, c, dev, gated=g) for n, (k, c, g) in zip(names, shapes)]
+
+    def make():
+        return torch.cat([pt[3] for pt in parts]), torch.cat([pt[2] for pt in parts]).to(torch.float32).contiguous()
+
+    wstream, bias = VARIABLES.derived(("level4", "down"), make)
+    x = native.to_bf16(x)
+    B = x.shape[0]
+    y = torch.empty((B, 16, 32, 64), device=dev, dtype=torch.bfloat16)
+    rec = None
+    if _PROFILE is not None:
+        macs = B * 512 * 9 * (64 * 64 + 128 * 128 + 128 * 64 + 128 * 128)
+        rec = dict(name="level4_down(resnet_4_downsample+resnet_4_0)", kind="fused", out_hw=(16, 32), K_tap=128, N=128, stride=1,
+                   alg_bytes=(x.numel() + y.numel()) * 2, flops=2 * macs)
+    _profiled(rec, lambda: native.level4_fwd(x, wstream, bias, y))
+    return y
+
+
+def _level4_up(z, a):
+    """resnet_up_1_0 (with the nin on the skip a = resnet_4_0's output) and up_conv_2 (reference :217-222) in one launch.
+    Variable creation order of the reference: up_conv_1 (created by the level-5 kernel's wrapper), the block's conv_1, nin,
+    conv_2, then up_conv_2."""
+    dev = z.device
+    c1 = _conv_weights("resnet_up_1_0_conv_1_conv", 3, 128, 64, dev, skip_scope="resnet_up_1_0_nin_fc", kskip_eff=128)
+    c2 = _conv_weights("resnet_up_1_0_conv_2_conv", 3, 128, 128, dev, gated=True)
+    tp = _tconv_parts("up_conv_2_trans_conv", 64, 32, dev)
+
+    def make():
+        return torch.cat([c1[3], c2[3], tp[2]]), torch.cat([c1[2], c2[2], tp[1]]).to(torch.float32).contiguous()
+
+    wstream, bias = VARIABLES.derived(("level4", "up"), make)
+    B = z.shape[0]
+    y = torch.empty((B, 32, 64, 32), device=dev, dtype=torch.bfloat16)
+    rec = None
+    if _PROFILE is not None:
+        macs = B * 512 * (9 * 128 * 64 + 128 * 64 + 9 * 128 * 128 + 9 * 64 * 32)
+        rec = dict(name="level4_up(resnet_up_1_0+up_conv_2)", kind="fused", out_hw=(32, 64), K_tap=128, N=128, stride=1,
+                   alg_bytes=(z.numel() + a.numel() + y.numel()) * 2, flops=2 * macs)
+    _profiled(rec, lambda: native.level4_fwd(z, wstream, bias, y, skip=a))
+    return y
+
+
 # --------------------------------------------------------------------------- inference on MMA-ready activations
 # "planes" form of an activation t [B,H,W,C] (include/flownet.h, csrc/conv_pl.cu): bf16 [B, 2C/8, H, W, 8] = concat_elu(t)
 # in 8-channel groups.  In inference every producer's epilogue writes what its consumers read: the planes for a stride-1
@@ -594,10 +669,16 @@ def conv_res(inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name='concat_e
     for i in range(nr_res_blocks):
         x = block(x, name="resnet_1_" + str(i))
     # res_2 .. res_5
-    fused5 = False
+    fused5 = fused4 = False
     for lvl in (2, 3, 4, 5):
         a.append(x)
         filter_size = 2 * filter_size
+        if lvl == 4 and _level4_fusable(x, nr_res_blocks, keep_prob, nonlinearity, gated, filter_size):
+            # resnet_4_downsample + resnet_4_0 in one launch (csrc/conv_l4.cu); the matching up half runs after level 5
+            x = _level4_down(x)
+            seed[0] += 2
+            fused4 = True
+            continue
         if lvl == 5 and _level5_fusable(x, nr_res_blocks, keep_prob, nonlinearity, gated, filter_size):
             # the whole 8x16 level (down block, block, up_conv_1) in one launch: csrc/conv_l5.cu
             x = _level5_fused(x)
@@ -610,7 +691,12 @@ def conv_res(inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name='concat_e
     # res_up_1 .. res_up_4
     for k in (1, 2, 3, 4):
         filter_size = int(filter_size / 2)
-        if not (k == 1 and fused5):
+        if k == 1 and fused4 and fused5:
+            # resnet_up_1_0 + up_conv_2 in one launch; level 3's loop turn then skips its transposed conv
+            x = _level4_up(x, a[-1])
+            seed[0] += 1
+            continue
+        if not ((k == 1 and fused5) or (k == 2 and fused4 and fused5)):
             x = transpose_conv_layer(x, 3, 2, filter_size, "up_conv_%d" % k)
         for i in range(nr_res_blocks):
             x = block(x, a=a[-k] if i == 0 else None, name="resnet_up_%d_%d" % (k, i))

@@ -595,6 +595,59 @@ def test_level5_fused_kernel_vs_layer_by_layer_and_oracle(native, B, split, monk
     arch.reset_variables(1234)
 
 
+@pytest.mark.parametrize("B", [1, 3, 80])
+def test_level4_fused_kernels_vs_layer_by_layer_and_oracle(native, B, monkeypatch):
+    """csrc/conv_l4.cu: resnet_4_downsample + resnet_4_0 in one launch, resnet_up_1_0 (+ nin skip) + up_conv_2 in another (a
+    cluster of two CTAs per image, halo columns exchanged through distributed shared memory), against the same
+    convolutions as separate launches and against the fp64 oracle on bf16-rounded inputs."""
+    import model.flow_architecture as arch
+    monkeypatch.setattr(arch, "LEVEL4_MAX_WAVES", 100.0)
+    arch.reset_variables(78)
+    g = torch.Generator().manual_seed(100 + B)
+    x3 = torch.randn(B, 32, 64, 32, generator=g).to(torch.bfloat16)
+    z = torch.randn(B, 16, 32, 64, generator=g).to(torch.bfloat16)
+    x3d, zd = x3.cuda(), z.cuda()
+    conc = arch.concat_elu
+
+    # layer by layer, creating the variables in the order the fused wrappers do
+    t = arch.res_block(x3d, filter_size=64, nonlinearity=conc, stride=2, gated=True, name="resnet_4_downsample")
+    x4_ref = arch.res_block(t, filter_size=64, nonlinearity=conc, gated=True, name="resnet_4_0")
+    u = arch.res_block(zd, a=x4_ref, filter_size=64, nonlinearity=conc, gated=True, name="resnet_up_1_0")
+    y_ref = arch.transpose_conv_layer(u, 3, 2, 32, "up_conv_2")
+
+    assert arch._level4_fusable(x3d, 1, 1.0, conc, True, 64)
+    x4 = arch._level4_down(x3d)
+    y = arch._level4_up(zd, x4_ref)
+    torch.cuda.synchronize()
+    assert native.tc_status() == 0
+    assert tuple(x4.shape) == (B, 16, 32, 64) and tuple(y.shape) == (B, 32, 64, 32)
+    assert rel_l2(x4, x4_ref) < 1e-3
+    assert rel_l2(y, y_ref) < 1e-3
+    if B <= 3:
+        vs = fo.VariableStore(78, torch.float64)
+        t = fo.res_block(vs, x3.double(), filter_size=64, stride=2, gated=True, name="resnet_4_downsample")
+        x4o = fo.res_block(vs, t, filter_size=64, gated=True, name="resnet_4_0")
+        uo = fo.res_block(vs, z.double(), a=x4_ref.cpu().double(), filter_size=64, gated=True, name="resnet_up_1_0")
+        yo = fo.transpose_conv_layer(vs, uo, 3, 2, 32, "up_conv_2")
+        for k, v in vs.vars.items():
+            assert torch.equal(arch.global_variables()[k].cpu().double(), v), k
+        assert rel_l2(x4, x4o) < NET_TOL
+        assert rel_l2(y, yo) < NET_TOL
+    arch.reset_variables(1234)
+
+
+def test_net_with_and_without_the_fused_level4_kernels(native):
+    import model.flow_architecture as arch
+    x = fo.synth_boundary(3, 128, 256, seed=13).astype(np.uint8)
+    y1 = _net(native, x, "auto")
+    try:
+        arch.LEVEL4_FUSED = False
+        y0 = _net(native, x, "auto")
+    finally:
+        arch.LEVEL4_FUSED = True
+    assert rel_l2(y1, y0) < 2e-3
+
+
 def test_net_with_and_without_the_fused_level5_kernel(native):
     import model.flow_architecture as arch
     x = fo.synth_boundary(3, 128, 256, seed=12).astype(np.uint8)
