@@ -241,11 +241,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
       return ptx::smem_desc(sbase + OFF_RING + s * CHUNK, lbo, 128);
     };
     // everybody: this stage's accumulators are complete; the peer learns that this CTA's planes may be overwritten
-    auto stage_done = [&]() {
+    // readers_first: other warps read the operand planes during this stage's MMAs (the shortcut recovered from them), so
+    // nobody -- neither this CTA's epilogue nor the peer -- may overwrite them before every warp has passed this point
+    auto stage_done = [&](bool readers_first = false) {
       ok = ok && ptx::mbar_wait(bar(SB_TF), tf_par);
       if (!ok) atomicCAS(p.status, 0, 83);
       tf_par ^= 1u;
       ptx::tc_fence_after_sync();
+      if (readers_first) worker_barrier();
       if (tid == 0) mbar_arrive_remote(xr_peer);
     };
     // before the first remote write of an epilogue: the peer's MMAs no longer read its planes
@@ -447,7 +450,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
           for (int i = 0; i < 8; ++i) pool[g][i] *= 0.25f;
         }
       }
-      stage_done();
+      stage_done(true);
       stamp();
       // the zero border of the planes (the region held the sub-planes until now): rows 0 / 17 and the image-edge column;
       // the halo column towards the peer is written by the peer

@@ -59,6 +59,8 @@ struct Params {
   __nv_bfloat16* y;             // [B,16,32,64]
   __nv_bfloat16* yp;            // optional planes form of y
   int* status;
+  long long* timing;            // debug: 16 clock64 stamps per CTA (fn_debug_set_timing; nullptr in production)
+  int timing_ctas;
   int B;
 };
 
@@ -161,6 +163,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   bool ok = true;
+  long long* stamps = (p.timing != nullptr && (int)blockIdx.x < p.timing_ctas && tid == 0) ? p.timing + (size_t)blockIdx.x * 16 : nullptr;
+  int nstamp = 0;
+  auto stamp = [&]() { if (stamps) stamps[nstamp++] = clock64(); };
+  stamp();
 
   if (warp == 8) {
     // =========================== producer: this rank's weight stream ===========================
@@ -208,11 +214,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
       return ptx::smem_desc(sbase + OFF_RING + s * CHUNK, lbo, 128);
     };
     // everybody: this stage's accumulators are complete; the peer learns that this CTA's planes may be overwritten
-    auto stage_done = [&]() {
+    // readers_first: other warps read the operand planes during this stage's MMAs (the shortcut recovered from them), so
+    // nobody -- neither this CTA's epilogue nor the peer -- may overwrite them before every warp has passed this point
+    auto stage_done = [&](bool readers_first = false) {
       ok = ok && ptx::mbar_wait(bar(SB_TF), tf_par);
       if (!ok) atomicCAS(p.status, 0, 73);
       tf_par ^= 1u;
       ptx::tc_fence_after_sync();
+      if (readers_first) worker_barrier();
       if (tid == 0) mbar_arrive_remote(xr_peer);
     };
     // before the first remote write of an epilogue: the peer's MMAs no longer read its planes
@@ -243,10 +252,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
     {
       const __nv_bfloat16* xb = p.x + (size_t)b * IH * IW * C4;
       constexpr int ITEMS = (IH + 1) * (IW + 1) * 8;
-      for (int base = tid; base < ITEMS; base += 256 * 4) {
-        uint4 in[4];
+      constexpr int UN = 9;                 // loads in flight per thread (two rounds)
+      for (int base = tid; base < ITEMS; base += 256 * UN) {
+        uint4 in[UN];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < UN; ++k) {
           const int idx = base + 256 * k;
           const int ch = idx & 7, sp = idx >> 3;
           const int h = sp / (IW + 1), w = sp - h * (IW + 1);
@@ -254,7 +264,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
           if (idx < ITEMS && h < IH && w < IW) in[k] = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)h * IW + w) * C4 + ch * 8));
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < UN; ++k) {
           const int idx = base + 256 * k;
           if (idx >= ITEMS) break;
           const int ch = idx & 7, sp = idx >> 3;
@@ -270,6 +280,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
     ptx::fence_proxy_async_smem();
     ptx::tc_fence_before_sync();
     worker_barrier();
+    stamp();
 
     // ---- stage 1 MMAs: stride-2 conv, K = 9 x 128, this CTA's N = 64; a 32 KB chunk = 16 k-steps = two taps
     if (warp == 0) {
@@ -297,7 +308,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
       if (leader) ptx::mma_commit(bar(SB_TF));
       __syncwarp();
     }
-    stage_done();
+    // stage 2's shortcut, front channel pad (reference :158-163): channels 64.. (= rank 1's) take the 2x2 average pool of x4.  The
+    // four input pixels of output pixel (px, py) are entry [px][py] of the four parity sub-planes and x is exactly
+    // recoverable from [elu(x) | elu(-x)], so the pool comes from shared memory while stage 1's MMAs read the same planes
+    // (the scattered global loads it replaces cost the stage-2 epilogue 6 k clocks)
+    float pool[4][8];
+    if (rank == 1) {
+      const uint32_t e0 = A + (uint32_t)(px * PU1 + py) * 16u;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int pl = half * 4 + g;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pool[g][i] = 0.f;
+#pragma unroll
+        for (int sp = 0; sp < 4; ++sp) {
+          bf16x8 pos, neg;
+          pos.v = lds128(e0 + (uint32_t)(sp * SUB1_BYTES + pl * P1 * 16));
+          neg.v = lds128(e0 + (uint32_t)(sp * SUB1_BYTES + (8 + pl) * P1 * 16));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float fp = __bfloat162float(pos.h[i]);
+            pool[g][i] += fp > 0.f ? fp : -__bfloat162float(neg.h[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pool[g][i] *= 0.25f;
+      }
+    }
+    stage_done(true);
+    stamp();
 
     // ---- epilogue of a plain conv (this CTA's 64 channels): acc + bias -> bf16 -> [elu | elu(-.)] planes, both CTAs
     auto epilogue_plain = [&](int boff) {
@@ -327,6 +366,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
     peer_planes_free();
     epilogue_plain(B1);
     planes_exchanged();
+    stamp();
 
     // ---- MMAs of a stride-1 3x3 conv on the 256-channel concat planes (stages 2, 3, 4), this CTA's N columns
     auto issue_s1 = [&](auto nconst, int g0) {
@@ -358,10 +398,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
     // ---- stage 2: conv_2 of the down block, gate, shortcut = 2x2 average pool of x4 in the LAST 64 channels (= rank 1's)
     if (warp == 0) issue_s1(N128{}, G2);
     stage_done();
+    stamp();
     peer_planes_free();
     {
-      const __nv_bfloat16* xb = p.x + (size_t)b * IH * IW * C4;
-#pragma unroll 1
+#pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int cl = half * 32 + g * 8;
         const int cg = (int)rank * CL + cl;
@@ -374,17 +414,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
           const float th = tanh_approx(fmaf(gt[i], 0.5f, bv[i]));
           o[i] = (a[i] + bu[i]) * fmaf(th, 0.5f, 0.5f);
         }
-        if (cg >= C5 - C4) {             // front channel pad (reference :158-163): channels 64.. take the pooled x4
-          const __nv_bfloat16* r00 = xb + ((size_t)(2 * py) * IW + 2 * px) * C4 + (cg - (C5 - C4));
-          bf16x8 q4[4];
-          q4[0].v = __ldg(reinterpret_cast<const uint4*>(r00));
-          q4[1].v = __ldg(reinterpret_cast<const uint4*>(r00 + C4));
-          q4[2].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)IW * C4));
-          q4[3].v = __ldg(reinterpret_cast<const uint4*>(r00 + (size_t)IW * C4 + C4));
+        if (rank == 1) {                 // cg >= C5 - C4: the pooled x4, channel cg - 64 = cl
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            o[i] += 0.25f * (__bfloat162float(q4[0].h[i]) + __bfloat162float(q4[1].h[i]) + __bfloat162float(q4[2].h[i]) +
-                             __bfloat162float(q4[3].h[i]));
+          for (int i = 0; i < 8; ++i) o[i] += pool[g][i];
         }
         const uint4 raw = pack8(o);
         sts128(r1_row + (uint32_t)(((cl >> 3) ^ (r & 7)) * 16), raw);           // kept (own channels) for stage 4's shortcut
@@ -396,18 +428,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
       }
     }
     planes_exchanged();
+    stamp();
 
     // ---- stage 3: conv_1 of resnet_5_0
     if (warp == 0) issue_s1(N64{}, G3);
     stage_done();
+    stamp();
     peer_planes_free();
     epilogue_plain(B3);
     planes_exchanged();
+    stamp();
 
     // ---- stage 4: conv_2 of resnet_5_0, gate, shortcut = the block input kept in shared memory; the result feeds the
     // transposed conv RAW (no nonlinearity, reference :213): 16 planes
     if (warp == 0) issue_s1(N128{}, G4);
     stage_done();
+    stamp();
     peer_planes_free();
 #pragma unroll 1
     for (int g = 0; g < 4; ++g) {
@@ -428,6 +464,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
       put_plane((uint32_t)((cg >> 3) * PPAD * 16) + pp16, pack8(o));
     }
     planes_exchanged();
+    stamp();
 
     // ---- stage 5: transposed conv as four output phases, K = 128 per tap, this CTA's N = 32 per phase;
     // a 32 KB chunk = 32 k-steps = four taps
@@ -460,6 +497,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
       __syncwarp();
     }
     stage_done();
+    stamp();
     {
       __nv_bfloat16* yb = p.y + (size_t)b * IH * IW * C4;
 #pragma unroll 1
@@ -491,6 +529,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
     }
   }
 
+  stamp();
   // ---- neither CTA may leave while the other can still write into it or arrive on its barriers
   ptx::tc_fence_before_sync();
   cluster_sync_all();
@@ -503,6 +542,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
 }  // namespace l5c
 
 int* tc_status_word();   // conv_tc.cu
+void tc_timing_buffer(long long** buf, int* ctas);   // conv_tc.cu: debug stamp buffer (fn_debug_set_timing)
 
 int level5c_fwd(const fn_level5_desc& d, cudaStream_t stream) {
   using namespace l5c;
@@ -515,6 +555,8 @@ int level5c_fwd(const fn_level5_desc& d, cudaStream_t stream) {
   p.status = tc_status_word();
   if (p.status == nullptr) return (int)cudaErrorMemoryAllocation;
   p.B = d.B;
+  tc_timing_buffer(&p.timing, &p.timing_ctas);
+  p.timing_ctas /= 2;           // 16 stamps per CTA out of a buffer of 8 per registered CTA
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_level5c, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
