@@ -383,11 +383,17 @@ def main():
         # ---------------- per-kernel roofline (N=1 semantics: this rank's GPU)
         rows = layer_profile(x_host.cuda())
         ridge = peaks["tc_burst"] * 1e12 / (peaks["hbm"] * 1e9)
+        sm_count = torch.cuda.get_device_properties(0).multi_processor_count
+        sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
         for r in rows:
             r["bound"] = "tensor" if r["flops"] / r["alg_bytes"] > ridge else "hbm"
             r["gbs"] = r["alg_bytes"] / (r["ms"] * 1e-3) / 1e9
             r["tflops"] = r["flops"] / (r["ms"] * 1e-3) / 1e12
             r["frac"] = (r["tflops"] / peaks["tc_burst"]) if r["bound"] == "tensor" else (r["gbs"] / peaks["hbm"])
+            # MMA-rate floor: a tcgen05.mma (M=128, K=16) occupies the MMA unit 39-128 clk depending on N (DESIGN.md section 3,
+            # profiles/r2_mma_bench3.log), whatever its flop count; floor = MMA-unit clocks / (SMs x SM clock)
+            r["mma_floor_us"] = r.get("mma_clk", 0.0) / (sm_count * sm_hz) * 1e6
+            r["floor_us"] = max(r["mma_floor_us"], r["alg_bytes"] / (peaks["hbm"] * 1e9) * 1e6, r["flops"] / (peaks["tc_burst"] * 1e12) * 1e6)
         total_ms = sum(r["ms"] for r in rows)
         top = max(rows, key=lambda r: r["ms"])
         ev = ncu_evidence() or {}
@@ -404,11 +410,18 @@ def main():
             "tensor_pipe_util": ev.get("tensor_pipe_util"),
             "kernel": top["name"], "kernel_ms": top["ms"], "share_of_step": top["ms"] / total_ms,
             "tcgen05": top["tcgen05"], "peak_source": peaks["source"] + " (burst; kernel timed alone)",
+            # the launch against the larger of its three floors (HBM bytes, dense-bf16 flops, MMA-unit occupancy)
+            "kernel_floor_us": top["floor_us"], "kernel_mma_floor_us": top["mma_floor_us"],
+            "floor_frac": top["floor_us"] / (top["ms"] * 1e3),
             "whole_net": {
                 "tflops": value / world * FLOP_PER_IMG / 1e12,
                 "frac_tensor_sustained": value / world * FLOP_PER_IMG / 1e12 / peaks["tc_sustained"],
                 "gbs_algorithmic": value / world * BYTES_PER_IMG / 1e9,
                 "frac_hbm": value / world * BYTES_PER_IMG / 1e9 / peaks["hbm"],
+                # sum over the launches of max(HBM, flop, MMA-unit) floors against the graph's step time
+                "sum_floor_us": sum(r["floor_us"] for r in rows),
+                "sum_mma_floor_us": sum(r["mma_floor_us"] for r in rows),
+                "floor_frac": sum(r["floor_us"] for r in rows) / (ms / args.steps * 1e3),
             },
         }
         if args.layers_out:

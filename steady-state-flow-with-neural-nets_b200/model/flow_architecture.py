@@ -33,6 +33,23 @@ IMPL = _IMPL_NAMES[os.environ.get("FLOWNET_IMPL", "auto")]
 _PROFILE = None
 
 
+# measured execution time of one tcgen05.mma (M = 128, K = 16, bf16) by accumulator width N, in SM clocks
+# (tools/mma_bench.cu, profiles/r2_mma_bench3.log): the A operand's 4 KB shared-memory read bounds the narrow shapes
+_MMA_CLK = {16: 39.0, 32: 42.0, 64: 48.0, 128: 64.0, 256: 128.0}
+
+
+def _mma_clk(blocks, ksteps, n):
+    """MMA-unit clocks of `blocks` M=128 tiles x `ksteps` K=16 steps at accumulator width n (rounded up to a measured
+    width; n > 256 = several instructions) -- the numerator of bench.py's MMA-rate floor."""
+    n16 = -(-int(n) // 16) * 16
+    clk, rem = 0.0, n16
+    while rem > 0:
+        w = min(rem, 256)
+        clk += _MMA_CLK[min(k for k in _MMA_CLK if k >= w)]
+        rem -= w
+    return float(blocks) * float(ksteps) * clk
+
+
 def _profiled(record, launch):
     if _PROFILE is None:
         launch()
@@ -242,8 +259,9 @@ def _fused_conv(x, scope, ksize, stride, cout, prologue, epilogue, skip=None, sk
         nbytes += skip.numel() * 2 if skip is not None else 0
         nbytes += res.numel() * 2 if res is not None else 0
         flops = 2 * B * OH * OW * cout * (ksize * ksize * cin * mult + kskip)
+        ksteps = ksize * ksize * (-(-cin * mult // 16)) + kskip // 16
         rec = dict(name=scope, kind="conv", out_hw=(OH, OW), K_tap=cin * mult, N=cout, stride=stride,
-                   alg_bytes=nbytes, flops=flops)
+                   alg_bytes=nbytes, flops=flops, mma_clk=_mma_clk(B * (-(-OH * OW // 128)), ksteps, cout) if cin > 1 and cout >= 8 else 0.0)
     _profiled(rec, lambda: native.conv_fwd(
         x, w16, bias, y, B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize, stride=stride, prologue=prologue,
         epilogue=epilogue, impl=IMPL, w_tc=w_tc, skip=skip, w_skip=ws16, res=res, res_pool=res_pool,
@@ -282,7 +300,8 @@ def transpose_conv_layer(inputs, kernel_size, stride, num_features, idx, nonline
     rec = None
     if _PROFILE is not None:
         rec = dict(name=scope, kind="tconv", out_hw=(2 * H, 2 * W), K_tap=cin, N=num_features, stride=2,
-                   alg_bytes=(x.numel() + y.numel()) * 2, flops=2 * B * H * W * 9 * cin * num_features)
+                   alg_bytes=(x.numel() + y.numel()) * 2, flops=2 * B * H * W * 9 * cin * num_features,
+                   mma_clk=_mma_clk(B * (-(-H * W // 128)), 9 * (-(-cin // 16)), num_features))
     _profiled(rec, lambda: native.tconv_fwd(x, w16, bias, y, B=B, H=H, W=W, Cin=cin, Cout=num_features, impl=IMPL,
                                             w_tc=w_tc))
     if TAPE is not None:
@@ -416,8 +435,12 @@ def _level5_fused(x):
     if _PROFILE is not None:
         # algorithmic bytes: x read by the stride-2 conv and by the pooled shortcut counts once, y once; flops: the five convs
         macs = B * 128 * (9 * 128 * 128 + 9 * 256 * 256 + 9 * 256 * 128 + 9 * 256 * 256 + 9 * 128 * 64)
+        # per image: one tile; with the channel split every CTA runs the same k-steps at half the width
+        w = (64, 128, 64, 128, 32) if split else (128, 256, 128, 256, 64)
+        k = (72, 144, 144, 144, 72)
+        clk = sum(_mma_clk(B * (2 if split else 1), ks, n) for ks, n in zip(k, w))
         rec = dict(name="level5_fused(resnet_5_downsample+resnet_5_0+up_conv_1)", kind="fused", out_hw=(16, 32), K_tap=256, N=256,
-                   stride=1, alg_bytes=(x.numel() + y.numel()) * 2, flops=2 * macs)
+                   stride=1, alg_bytes=(x.numel() + y.numel()) * 2, flops=2 * macs, mma_clk=clk)
     _profiled(rec, lambda: native.level5_fwd(x, wstream, bias, y, split=split))
     return y
 
@@ -468,7 +491,8 @@ def _level4_down(x):
     if _PROFILE is not None:
         macs = B * 512 * 9 * (64 * 64 + 128 * 128 + 128 * 64 + 128 * 128)
         rec = dict(name="level4_down(resnet_4_downsample+resnet_4_0)", kind="fused", out_hw=(16, 32), K_tap=128, N=128, stride=1,
-                   alg_bytes=(x.numel() + y.numel()) * 2, flops=2 * macs)
+                   alg_bytes=(x.numel() + y.numel()) * 2, flops=2 * macs,
+                   mma_clk=sum(_mma_clk(4 * B, ks, n) for ks, n in ((36, 64), (72, 128), (72, 64), (72, 128))))
     _profiled(rec, lambda: native.level4_fwd(x, wstream, bias, y))
     return y
 
@@ -492,7 +516,8 @@ def _level4_up(z, a):
     if _PROFILE is not None:
         macs = B * 512 * (9 * 128 * 64 + 128 * 64 + 9 * 128 * 128 + 9 * 64 * 32)
         rec = dict(name="level4_up(resnet_up_1_0+up_conv_2)", kind="fused", out_hw=(32, 64), K_tap=128, N=128, stride=1,
-                   alg_bytes=(z.numel() + a.numel() + y.numel()) * 2, flops=2 * macs)
+                   alg_bytes=(z.numel() + a.numel() + y.numel()) * 2, flops=2 * macs,
+                   mma_clk=sum(_mma_clk(4 * B, ks, n) for ks, n in ((80, 64), (72, 128), (36, 32))))
     _profiled(rec, lambda: native.level4_fwd(z, wstream, bias, y, skip=a))
     return y
 

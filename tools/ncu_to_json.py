@@ -28,7 +28,7 @@ def to_bytes(d, k, units):
 
 units = dict(zip(hdr, rows[1]))
 # the conv launches in order: everything except the cast / nonlinearity helpers
-convs = [d for d in data if any(t in d.get("Kernel Name", "") for t in ("k_conv", "k_level5", "k_head", "k_tail"))]
+convs = [d for d in data if any(t in d.get("Kernel Name", "") for t in ("k_conv", "k_level", "k_head", "k_tail"))]
 names = [r["name"] for r in lay["rows"]]
 if len(convs) != len(names):
     print("warning: %d conv launches in the capture, %d layers in the forward" % (len(convs), len(names)), file=sys.stderr)
@@ -48,7 +48,7 @@ for name, d in zip(names, convs):
         "dram_pct": num(d, "dram__throughput.avg.pct_of_peak_sustained_elapsed"),
         "registers": num(d, "launch__registers_per_thread"), "grid": num(d, "launch__grid_size"),
     }
-    if tp is not None and ("k_conv" in d.get("Kernel Name", "") or "k_level5" in d.get("Kernel Name", "")):
+    if tp is not None and ("k_conv" in d.get("Kernel Name", "") or "k_level" in d.get("Kernel Name", "")):
         tens.append(tp * t_us); memt.append((mt or 0) * t_us); dur.append(t_us)
 summary = {
     "source": source, "batch": B,
