@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FN_ABI_VERSION 7
+#define FN_ABI_VERSION 8
 
 /* error codes (negative) */
 #define FN_E_INVAL      (-1)   /* null pointer, bad enum, non-positive dim */
@@ -219,6 +219,26 @@ typedef struct fn_level4_desc {
 } fn_level4_desc;
 int64_t fn_level4_weight_bytes(int32_t up);
 int fn_level4_fwd(const fn_level4_desc* d, void* stream);
+
+/* ---- the stride-1 convolutions of the 32x64 level of the 128x256 grid in two launches (csrc/conv_l3.cu), :198-201, 223-228;
+ * same organisation as fn_level4_fwd, eight tiles per CTA.
+ *   up = 0: x = conv_1 output of "resnet_3_downsample" bf16 [B,32,64,32], aux = x2 bf16 [B,64,128,16] (that block's input,
+ *           for the pooled / front-padded shortcut) -> y = x3 bf16 [B,32,64,32] (output of "resnet_3_0");
+ *           w_stream: tensor-core images of resnet_3_downsample_conv_2, resnet_3_0_conv_1 / _conv_2; bias fp32 [64 | 32 | 64]
+ *   up = 1: x = conv_1 (+ nin) output of "resnet_up_2_0" bf16 [B,32,64,32], aux = z bf16 [B,32,64,32] (the block's input =
+ *           output of "up_conv_2") -> y bf16 [B,64,128,16] (output of "up_conv_3");
+ *           w_stream: resnet_up_2_0_conv_2, up_conv_3 ([9,32,16] GEMM-B form); bias fp32 [64 | 16]
+ * Inference only, default flags. */
+typedef struct fn_level3_desc {
+  int32_t B, up;
+  const void*  x;
+  const void*  aux;
+  const void*  w_stream;    /* fn_level3_weight_bytes(up) bytes */
+  const float* bias;
+  void*        y;
+} fn_level3_desc;
+int64_t fn_level3_weight_bytes(int32_t up);
+int fn_level3_fwd(const fn_level3_desc* d, void* stream);
 
 /* standalone nonlinearity (the public concat_elu()/set_nonlinearity() API) :14-29
  * x: bf16 [n, C] -> y: bf16 [n, C or 2C] */

@@ -62,6 +62,8 @@ int level5c_fwd(const fn_level5_desc& d, cudaStream_t stream);     // conv_l5c.c
 long long level5c_weight_bytes();
 int level4_fwd(const fn_level4_desc& d, cudaStream_t stream);       // conv_l4.cu
 long long level4_weight_bytes(int up);
+int level3_fwd(const fn_level3_desc& d, cudaStream_t stream);       // conv_l3.cu
+long long level3_weight_bytes(int up);
 
 static int validate_conv(const fn_conv_desc& d) {
   FN_REQUIRE(d.B > 0 && d.H > 0 && d.W > 0 && d.Cin > 0 && d.Cout > 0, FN_E_INVAL,
@@ -225,6 +227,15 @@ int fn_level4_fwd(const fn_level4_desc* d, void* stream) {
   FN_REQUIRE(aligned16(d->x) && aligned16(d->y) && aligned16(d->w_stream) && aligned16(d->skip), FN_E_ALIGN,
              "fn_level4_fwd: x/skip/y/w_stream must be 16-byte aligned");
   return level4_fwd(*d, (cudaStream_t)stream);
+}
+
+int64_t fn_level3_weight_bytes(int32_t up) { return level3_weight_bytes(up); }
+int fn_level3_fwd(const fn_level3_desc* d, void* stream) {
+  FN_REQUIRE(d != nullptr, FN_E_INVAL, "fn_level3_fwd: null descriptor");
+  FN_REQUIRE(d->B > 0 && d->x && d->aux && d->w_stream && d->bias && d->y, FN_E_INVAL, "fn_level3_fwd: null pointer or B = %d", d->B);
+  FN_REQUIRE(aligned16(d->x) && aligned16(d->aux) && aligned16(d->y) && aligned16(d->w_stream), FN_E_ALIGN,
+             "fn_level3_fwd: x/aux/y/w_stream must be 16-byte aligned");
+  return level3_fwd(*d, (cudaStream_t)stream);
 }
 
 int fn_nonlinearity(const void* x, void* y, int64_t n, int32_t C, int32_t kind, void* stream) {

@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FLOWNET_LIB", os.path.join(_HERE, "libflownet.so"))   # override: A/B builds
 
-FN_ABI_VERSION = 7
+FN_ABI_VERSION = 8
 # enum fn_prologue
 PRO_NONE, PRO_CONCAT_ELU, PRO_ELU, PRO_CONCAT_RELU, PRO_RELU = 0, 1, 2, 3, 4
 # enum fn_epilogue
@@ -60,6 +60,11 @@ class Level4Desc(C.Structure):
                 ("bias", C.c_void_p), ("y", C.c_void_p)]
 
 
+class Level3Desc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("up", C.c_int32), ("x", C.c_void_p), ("aux", C.c_void_p), ("w_stream", C.c_void_p),
+                ("bias", C.c_void_p), ("y", C.c_void_p)]
+
+
 class TConvDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
@@ -92,6 +97,8 @@ SYMBOLS = [
     ("fn_level5_fwd", C.c_int, [C.POINTER(Level5Desc), _P]),
     ("fn_level4_weight_bytes", C.c_int64, [C.c_int32]),
     ("fn_level4_fwd", C.c_int, [C.POINTER(Level4Desc), _P]),
+    ("fn_level3_weight_bytes", C.c_int64, [C.c_int32]),
+    ("fn_level3_fwd", C.c_int, [C.POINTER(Level3Desc), _P]),
     ("fn_nonlinearity", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     ("fn_cast_f32_to_bf16", C.c_int, [_P, _P, C.c_int64, _P]),
     ("fn_cast_u8_to_bf16", C.c_int, [_P, _P, C.c_int64, _P]),
@@ -288,6 +295,23 @@ def level4_fwd(x, w_stream, bias, y, skip=None):
     d.x, d.w_stream, d.bias, d.y = x.data_ptr(), w_stream.data_ptr(), bias.data_ptr(), y.data_ptr()
     d.skip = skip.data_ptr() if up else None
     _check(lib.fn_level4_fwd(C.byref(d), stream_ptr()), "fn_level4_fwd")
+
+
+def level3_fwd(x1, aux, w_stream, bias, y, up):
+    """The stride-1 convolutions of the 32x64 level (fn_level3_fwd, csrc/conv_l3.cu).  up False: x1 = conv_1 output of
+    resnet_3_downsample [B,32,64,32], aux = x2 [B,64,128,16] -> y = x3 [B,32,64,32]; up True: x1 = conv_1 (+ nin) output of
+    resnet_up_2_0, aux = the block's input z [B,32,64,32] -> y [B,64,128,16] (output of up_conv_3)."""
+    _require_cuda(x1, aux, w_stream, bias, y)
+    want_aux, want_y = ((32, 64, 32), (64, 128, 16)) if up else ((64, 128, 16), (32, 64, 32))
+    if tuple(x1.shape[1:]) != (32, 64, 32) or tuple(aux.shape[1:]) != want_aux or tuple(y.shape[1:]) != want_y or \
+            not (x1.shape[0] == aux.shape[0] == y.shape[0]):
+        raise ValueError("level3_fwd: tensor shapes")
+    if w_stream.numel() * w_stream.element_size() != int(lib.fn_level3_weight_bytes(int(up))) or bias.numel() != (80 if up else 160):
+        raise ValueError("level3_fwd: weight stream / bias size")
+    d = Level3Desc()
+    d.B, d.up = x1.shape[0], int(up)
+    d.x, d.aux, d.w_stream, d.bias, d.y = x1.data_ptr(), aux.data_ptr(), w_stream.data_ptr(), bias.data_ptr(), y.data_ptr()
+    _check(lib.fn_level3_fwd(C.byref(d), stream_ptr()), "fn_level3_fwd")
 
 
 def pack_conv_weights_tc(w, w_skip, ksize, Keff, Kskip, Cout, gated):

@@ -522,6 +522,75 @@ def _level4_up(z, a):
     return y
 
 
+# --------------------------------------------------------------------------- the 32x64 level's stride-1 convs in two launches
+# measured at batch 64 (tools/ab_level3.py): 64.7 -> 60.1 us and 44.6 -> 43.4 us against the layer-by-layer launches, the
+# forward 121.7 k -> 122.8 k img/s; at batch 8 the fused launches are twice as slow (eight serial tiles per CTA at 48 clk per
+# N = 64 MMA are 15 k clocks per stage, which the pipelined per-layer kernels spread over 148 SMs) -- hence the batch gate
+LEVEL3_FUSED = os.environ.get("FLOWNET_L3", "1") != "0"
+LEVEL3_MIN_BATCH = int(os.environ.get("FLOWNET_L3_MIN_BATCH", "48"))
+
+
+def _level3_fusable(x, nr_res_blocks, keep_prob, nonlinearity, gated, filter_size):
+    """fn_level3_fwd takes the reference's flags at the 128x256 grid (x = resnet_2_0's output [B,64,128,16]) in inference."""
+    if not (LEVEL3_FUSED and TAPE is None and IMPL == native.IMPL_AUTO and nr_res_blocks == 1 and keep_prob >= 1.0
+            and nonlinearity is concat_elu and gated and filter_size == 32 and tuple(x.shape[1:]) == (64, 128, 16)
+            and native.level5_supported(16, 32, 64)):
+        return False
+    sms = torch.cuda.get_device_properties(x.device).multi_processor_count
+    return x.shape[0] >= LEVEL3_MIN_BATCH and 2 * x.shape[0] <= LEVEL4_MAX_WAVES * sms
+
+
+def _level3_down(x2):
+    """resnet_3_downsample and resnet_3_0 (reference :198-201): the stride-2 conv_1 as its own launch, then conv_2 and the
+    whole second block in one; variables in the reference's order."""
+    dev = x2.device
+    x2 = native.to_bf16(x2)
+    x1 = _fused_conv(x2, "resnet_3_downsample_conv_1_conv", 3, 2, 32, native.PRO_CONCAT_ELU, native.EPI_BIAS)
+    names = ("resnet_3_downsample_conv_2_conv", "resnet_3_0_conv_1_conv", "resnet_3_0_conv_2_conv")
+    shapes = ((64, 64, True), (64, 32, False), (64, 64, True))
+    parts = [_conv_weights(n, 3, k, c, dev, gated=g) for n, (k, c, g) in zip(names, shapes)]
+
+    def make():
+        return torch.cat([pt[3] for pt in parts]), torch.cat([pt[2] for pt in parts]).to(torch.float32).contiguous()
+
+    wstream, bias = VARIABLES.derived(("level3", "down"), make)
+    B = x2.shape[0]
+    y = torch.empty((B, 32, 64, 32), device=dev, dtype=torch.bfloat16)
+    rec = None
+    if _PROFILE is not None:
+        macs = B * 2048 * 9 * (64 * 64 + 64 * 32 + 64 * 64)
+        rec = dict(name="level3_down(resnet_3_downsample.conv_2+resnet_3_0)", kind="fused", out_hw=(32, 64), K_tap=64, N=64, stride=1,
+                   alg_bytes=(x1.numel() + x2.numel() + y.numel()) * 2, flops=2 * macs,
+                   mma_clk=sum(_mma_clk(16 * B, 36, n) for n in (64, 32, 64)))
+    _profiled(rec, lambda: native.level3_fwd(x1, x2, wstream, bias, y, up=False))
+    return y
+
+
+def _level3_up(z, a):
+    """resnet_up_2_0 and up_conv_3 (reference :223-228): conv_1 with the nin on the skip a = resnet_3_0's output as its own
+    launch, then conv_2 and the transposed conv in one."""
+    dev = z.device
+    x1 = _fused_conv(z, "resnet_up_2_0_conv_1_conv", 3, 1, 32, native.PRO_CONCAT_ELU, native.EPI_BIAS, skip=a,
+                     skip_scope="resnet_up_2_0_nin_fc")
+    c2 = _conv_weights("resnet_up_2_0_conv_2_conv", 3, 64, 64, dev, gated=True)
+    tp = _tconv_parts("up_conv_3_trans_conv", 32, 16, dev)
+
+    def make():
+        return torch.cat([c2[3], tp[2]]), torch.cat([c2[2], tp[1]]).to(torch.float32).contiguous()
+
+    wstream, bias = VARIABLES.derived(("level3", "up"), make)
+    B = z.shape[0]
+    y = torch.empty((B, 64, 128, 16), device=dev, dtype=torch.bfloat16)
+    rec = None
+    if _PROFILE is not None:
+        macs = B * 2048 * (9 * 64 * 64 + 9 * 32 * 16)
+        rec = dict(name="level3_up(resnet_up_2_0.conv_2+up_conv_3)", kind="fused", out_hw=(64, 128), K_tap=64, N=64, stride=1,
+                   alg_bytes=(x1.numel() + z.numel() + y.numel()) * 2, flops=2 * macs,
+                   mma_clk=_mma_clk(16 * B, 36, 64) + _mma_clk(16 * B, 18, 16))
+    _profiled(rec, lambda: native.level3_fwd(x1, z, wstream, bias, y, up=True))
+    return y
+
+
 # --------------------------------------------------------------------------- inference on MMA-ready activations
 # "planes" form of an activation t [B,H,W,C] (include/flownet.h, csrc/conv_pl.cu): bf16 [B, 2C/8, H, W, 8] = concat_elu(t)
 # in 8-channel groups.  In inference every producer's epilogue writes what its consumers read: the planes for a stride-1
@@ -694,10 +763,16 @@ def conv_res(inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name='concat_e
     for i in range(nr_res_blocks):
         x = block(x, name="resnet_1_" + str(i))
     # res_2 .. res_5
-    fused5 = fused4 = False
+    fused5 = fused4 = fused3 = up3_done = False
     for lvl in (2, 3, 4, 5):
         a.append(x)
         filter_size = 2 * filter_size
+        if lvl == 3 and _level3_fusable(x, nr_res_blocks, keep_prob, nonlinearity, gated, filter_size):
+            # resnet_3_downsample + resnet_3_0 in two launches (csrc/conv_l3.cu)
+            x = _level3_down(x)
+            seed[0] += 2
+            fused3 = True
+            continue
         if lvl == 4 and _level4_fusable(x, nr_res_blocks, keep_prob, nonlinearity, gated, filter_size):
             # resnet_4_downsample + resnet_4_0 in one launch (csrc/conv_l4.cu); the matching up half runs after level 5
             x = _level4_down(x)
@@ -721,8 +796,14 @@ def conv_res(inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name='concat_e
             x = _level4_up(x, a[-1])
             seed[0] += 1
             continue
-        if not ((k == 1 and fused5) or (k == 2 and fused4 and fused5)):
+        if not ((k == 1 and fused5) or (k == 2 and fused4 and fused5) or (k == 3 and up3_done)):
             x = transpose_conv_layer(x, 3, 2, filter_size, "up_conv_%d" % k)
+        if k == 2 and fused3 and nr_res_blocks == 1:
+            # resnet_up_2_0 + up_conv_3 in two launches; level 2's loop turn then skips its transposed conv
+            x = _level3_up(x, a[-2])
+            seed[0] += 1
+            up3_done = True
+            continue
         for i in range(nr_res_blocks):
             x = block(x, a=a[-k] if i == 0 else None, name="resnet_up_%d_%d" % (k, i))
     # last_conv + tanh (reference :242-243), one launch

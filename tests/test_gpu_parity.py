@@ -648,6 +648,56 @@ def test_net_with_and_without_the_fused_level4_kernels(native):
     assert rel_l2(y1, y0) < 2e-3
 
 
+@pytest.mark.parametrize("B", [1, 3, 80])
+def test_level3_fused_kernels_vs_layer_by_layer_and_oracle(native, B, monkeypatch):
+    """csrc/conv_l3.cu: conv_2 of resnet_3_downsample + resnet_3_0 in one launch, conv_2 of resnet_up_2_0 + up_conv_3 in
+    another (cluster of two CTAs per image, eight tiles per CTA), against the same convolutions as separate launches and
+    against the fp64 oracle on bf16-rounded inputs."""
+    import model.flow_architecture as arch
+    monkeypatch.setattr(arch, "LEVEL4_MAX_WAVES", 100.0)
+    monkeypatch.setattr(arch, "LEVEL3_MIN_BATCH", 1)
+    arch.reset_variables(79)
+    g = torch.Generator().manual_seed(200 + B)
+    x2 = torch.randn(B, 64, 128, 16, generator=g).to(torch.bfloat16)
+    z = torch.randn(B, 32, 64, 32, generator=g).to(torch.bfloat16)
+    x2d, zd = x2.cuda(), z.cuda()
+    conc = arch.concat_elu
+
+    t = arch.res_block(x2d, filter_size=32, nonlinearity=conc, stride=2, gated=True, name="resnet_3_downsample")
+    x3_ref = arch.res_block(t, filter_size=32, nonlinearity=conc, gated=True, name="resnet_3_0")
+    u = arch.res_block(zd, a=x3_ref, filter_size=32, nonlinearity=conc, gated=True, name="resnet_up_2_0")
+    y_ref = arch.transpose_conv_layer(u, 3, 2, 16, "up_conv_3")
+
+    assert arch._level3_fusable(x2d, 1, 1.0, conc, True, 32)
+    x3 = arch._level3_down(x2d)
+    y = arch._level3_up(zd, x3_ref)
+    torch.cuda.synchronize()
+    assert native.tc_status() == 0
+    assert tuple(x3.shape) == (B, 32, 64, 32) and tuple(y.shape) == (B, 64, 128, 16)
+    assert rel_l2(x3, x3_ref) < 1e-3
+    assert rel_l2(y, y_ref) < 1e-3
+    if B <= 3:
+        vs = fo.VariableStore(79, torch.float64)
+        t = fo.res_block(vs, x2.double(), filter_size=32, stride=2, gated=True, name="resnet_3_downsample")
+        x3o = fo.res_block(vs, t, filter_size=32, gated=True, name="resnet_3_0")
+        uo = fo.res_block(vs, z.double(), a=x3_ref.cpu().double(), filter_size=32, gated=True, name="resnet_up_2_0")
+        yo = fo.transpose_conv_layer(vs, uo, 3, 2, 16, "up_conv_3")
+        for k, v in vs.vars.items():
+            assert torch.equal(arch.global_variables()[k].cpu().double(), v), k
+        assert rel_l2(x3, x3o) < NET_TOL
+        assert rel_l2(y, yo) < NET_TOL
+    arch.reset_variables(1234)
+
+
+def test_net_with_and_without_the_fused_level3_kernels(native, monkeypatch):
+    import model.flow_architecture as arch
+    x = fo.synth_boundary(3, 128, 256, seed=14).astype(np.uint8)
+    y0 = _net(native, x, "auto")                                  # batch 3 is below the fused kernels' batch gate
+    monkeypatch.setattr(arch, "LEVEL3_MIN_BATCH", 1)
+    y1 = _net(native, x, "auto")
+    assert rel_l2(y1, y0) < 2e-3
+
+
 def test_net_with_and_without_the_fused_level5_kernel(native):
     import model.flow_architecture as arch
     x = fo.synth_boundary(3, 128, 256, seed=12).astype(np.uint8)
