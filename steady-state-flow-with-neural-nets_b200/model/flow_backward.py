@@ -1,12 +1,14 @@
 """Backward pass + TF1 Adam for flow_net -- what `AdamOptimizer(lr).minimize(loss)` builds in the
 reference (/root/reference/model/flow_net.py:44-46) for the graph of flow_architecture.py:129-248.
 
-Correctness-first: every gradient is computed by kernels of libflownet.so, but the data gradients of
-the convolutions reuse the FORWARD kernels on the gradient tensor (stride-1 conv: flipped, transposed
-weights; stride-2 conv <-> transposed conv with the same weights), the pre-gate tensor is recomputed
-instead of stored, and the weight/bias gradients are two-stage CUDA-core reductions.  Activation
-gradients are bf16, parameter gradients / Adam state fp32 in flat buffers (one all-reduce in
-data-parallel training, SURVEY 8e: gradients of a SUM loss simply add across ranks).
+Every gradient is computed by kernels of libflownet.so: the data gradients of the convolutions are the FORWARD tensor-core
+kernels on the gradient tensor (stride-1 conv: flipped, transposed weights; stride-2 conv <-> transposed conv with the
+same weights) with the prologue's adjoint fused into their epilogues, the pre-gate tensor is recomputed instead of
+stored (gate adjoint in the recomputing launch's epilogue), weight and bias gradients run on tcgen05 (csrc/wgrad_tc.cu).
+Activation gradients are bf16, parameter gradients / Adam state fp32 in flat buffers.  Data-parallel training: gradients
+of a SUM loss simply add across ranks; the flat gradient is reduced in two buckets -- the decoder + deepest
+level as soon as their part of the backward pass is done, overlapping the encoder's backward (BackwardPass, bucket_split)
+-- or in one call after the pass (allreduce_gradients).
 """
 from __future__ import annotations
 
@@ -47,8 +49,16 @@ class FlatParams:
         return self.grad[off:off + k].view(shape)
 
 
+_ZERO_BIAS = {}
+
+
 def _zeros_bias(n, device):
-    return torch.zeros(n, dtype=torch.float32, device=device)
+    """the zero bias of the bias-free backward convs: one persistent tensor per (width, device), never written"""
+    key = (int(n), str(device))
+    z = _ZERO_BIAS.get(key)
+    if z is None:
+        z = _ZERO_BIAS[key] = torch.zeros(n, dtype=torch.float32, device=device)
+    return z
 
 
 class _BwdWeights:
@@ -98,11 +108,12 @@ def _conv_call(x, wts, y, **kw):
     return True
 
 
-def _conv_plain(x, wts, cout, ksize, stride, device):
-    """bias-free conv through the forward kernels (tcgen05 when the shape allows)."""
+def _conv_plain(x, wts, cout, ksize, stride, device, out=None):
+    """bias-free conv through the forward kernels (tcgen05 when the shape allows); written into `out` when given."""
     B, H, W, cin = x.shape
     OH, OW = -(-H // stride), -(-W // stride)
-    y = torch.empty((B, OH, OW, cout), dtype=torch.bfloat16, device=device)
+    y = out if out is not None else torch.empty((B, OH, OW, cout), dtype=torch.bfloat16, device=device)
+    assert tuple(y.shape) == (B, OH, OW, cout) and y.is_contiguous()
     if not isinstance(wts, _BwdWeights):            # a ready bf16 [T, K, N] tensor
         w_tc = native.pack_conv_weights_tc(wts, None, ksize, cin, 0, cout, False) if (cin % 16 == 0 or cin == 8) else None
         native.conv_fwd(x, wts, _zeros_bias(cout, device), y, B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize, stride=stride,
@@ -177,124 +188,151 @@ class _Grads:
         return ent[1], True
 
 
-def backward(tape, sflow_p, sflow, flat: FlatParams = None, want_input_grad=False):
-    """Fills flat.grad with d(l2_loss)/d(variables) (skipped when flat is None); returns the loss (fp32 [1]), or
-    (loss, d loss / d boundary [B,H,W,1] bf16) with want_input_grad -- the one data gradient training never needs
-    (the first conv's), which the boundary-optimisation use of the network does (README.md:31-36)."""
-    V = arch.VARIABLES.vars
-    dev = sflow_p.device
-    grads = _Grads()
-    loss, dpre = native.tanh_l2_bwd(sflow_p, sflow.to(torch.float32))
-    params = flat is not None
-    d_input = None
+class BackwardPass:
+    """The backward pass over a recorded forward, runnable in pieces: run(records) consumes tape records in reverse order
+    and may be called several times with consecutive slices of the tape (last slice first) -- flow_net.CompiledTraining
+    captures the decoder / deepest-level part and the encoder part into separate CUDA graphs so that the first gradient
+    bucket can be all-reduced while the second part runs.  Fills flat.grad with d(l2_loss)/d(variables) (skipped when flat
+    is None); `loss` is fp32 [1]; with want_input_grad `d_input` is d loss / d boundary [B,H,W,1] bf16 -- the one data
+    gradient training never needs (the first conv's), which the boundary-optimisation use of the network does (SURVEY 8f
+    rank 3, README.md:31-36)."""
 
-    def wgrad_into(name, x, dY, ksize, stride, pro, keep_prob=1.0, seed=0, bias=False):
-        """weight gradient (and, with bias=True, the bias gradient of the same dY in the same launch)"""
-        if params:
-            native.conv_wgrad(x, dY, flat.grad_view(name + '/weights').view(ksize * ksize, -1, dY.shape[-1]), ksize=ksize,
-                              stride=stride, prologue=pro, keep_prob=keep_prob, dropout_seed=seed,
-                              db=flat.grad_view(name + '/biases') if bias else None)
+    def __init__(self, sflow_p, sflow, flat: FlatParams = None, want_input_grad=False):
+        self.flat, self.want_input_grad = flat, want_input_grad
+        self.dev = sflow_p.device
+        self.grads = _Grads()
+        self.loss, self.dpre = native.tanh_l2_bwd(sflow_p, sflow.to(torch.float32))
+        self.d_input = None
 
-    def bgrad_into(name, dY):
-        if params:
-            native.bias_grad(dY, flat.grad_view(name + '/biases'))
+    def run(self, records):
+        V = arch.VARIABLES.vars
+        flat, dev, grads, dpre, want_input_grad = self.flat, self.dev, self.grads, self.dpre, self.want_input_grad
+        params = flat is not None
 
-    for rec in reversed(tape):
-        kind = rec["kind"]
-        if kind == "last":
-            x = rec["x"]                                   # [B,H,W,F] raw block output, no prologue
-            cin = x.shape[3]
-            # weights: [3,3,cin,2]; gradients run as 8-channel launches (dpre channels 2..7 are zero)
+        def wgrad_into(name, x, dY, ksize, stride, pro, keep_prob=1.0, seed=0, bias=False):
+            """weight gradient (and, with bias=True, the bias gradient of the same dY in the same launch)"""
             if params:
-                tmp = torch.empty((9, cin, 8), dtype=torch.float32, device=dev)
-                native.conv_wgrad(x, dpre, tmp, ksize=3, stride=1, prologue=native.PRO_NONE)
-                flat.grad_view('last_conv_conv/weights').copy_(tmp[:, :, :2].reshape(3, 3, cin, 2))
-                tmpb = torch.empty(8, dtype=torch.float32, device=dev)
-                native.bias_grad(dpre, tmpb)
-                flat.grad_view('last_conv_conv/biases').copy_(tmpb[:2])
-            w = V['last_conv_conv/weights']
-            w8 = torch.zeros((3, 3, cin, 8), dtype=torch.float32, device=dev)
-            w8[..., :2] = w
-            dx = _conv_plain(dpre, _dgrad_weights_s1(w8, 3), cin, 3, 1, dev)
-            buf, acc = grads.target(x)
-            assert not acc
-            buf.copy_(dx)
-        elif kind == "tconv":
-            x, y, scope = rec["x"], rec["out"], rec["scope"]
-            g = grads.get(y)
-            cin, cout = x.shape[3], y.shape[3]
+                native.conv_wgrad(x, dY, flat.grad_view(name + '/weights').view(ksize * ksize, -1, dY.shape[-1]), ksize=ksize,
+                                  stride=stride, prologue=pro, keep_prob=keep_prob, dropout_seed=seed,
+                                  db=flat.grad_view(name + '/biases') if bias else None)
+
+        def bgrad_into(name, dY):
             if params:
-                native.tconv_wgrad(x, g, flat.grad_view(scope + '/weights').view(9, cout, cin))
-            bgrad_into(scope, g)
-            # d(x) = stride-2 'SAME' conv of d(y) with the same weights read as HWIO [k,k,Cout,Cin]
-            dx = _conv_plain(g, _BwdWeights(V[scope + '/weights'], 3, cout, cin), cin, 3, 2, dev)
-            buf, acc = grads.target(x)
-            assert not acc
-            buf.copy_(dx)
-        elif kind == "block":
-            name, x, a, x_1, out = rec["name"], rec["x"], rec["a"], rec["x_1"], rec["out"]
-            F_, stride, gated, pro = rec["F"], rec["stride"], rec["gated"], rec["pro"]
-            keep_p, seed, pooled = rec["keep_p"], rec["seed"], rec["pooled"]
-            mult = 2 if pro in (native.PRO_CONCAT_ELU, native.PRO_CONCAT_RELU) else 1
-            g = grads.get(out)
-            cin = x.shape[3]
-            s2 = name + '_conv_2_conv'
-            n2 = 2 * F_ if gated else F_
-            # ---- conv_2 (+gate): recompute the pre-gate tensor, then its adjoint
-            if gated:
-                kw = dict(res=g, keep_prob=keep_p, dropout_seed=seed)
-                if arch._fused_conv(x_1, s2, 3, 1, n2, pro, native.EPI_GATE_BWD, query=True, **kw):
-                    # one launch: recompute [u|v] on the tensor cores, apply the gate's adjoint in the epilogue
-                    dc2 = arch._fused_conv(x_1, s2, 3, 1, n2, pro, native.EPI_GATE_BWD, **kw)
-                else:
-                    c2 = arch._fused_conv(x_1, s2, 3, 1, n2, pro, native.EPI_BIAS, keep_prob=keep_p, dropout_seed=seed)
-                    dc2 = native.gate_bwd(c2, g)
-            else:
-                dc2 = g
-            wgrad_into(s2, x_1, dc2, 3, 1, pro, keep_p, seed, bias=True)
-            dx_1 = _conv_dgrad_adjoint(dc2, _dgrad_weights_s1(V[s2 + '/weights'], 3), mult * F_, x_1, pro, dev,
-                                       keep_prob=keep_p, seed=seed)
-            # ---- conv_1 (+nin skip)
-            s1 = name + '_conv_1_conv'
-            pro1 = native.PRO_NONE if cin == 1 else pro
-            wgrad_into(s1, x, dx_1, 3, stride, pro1, bias=True)
-            if a is not None:
-                sn = name + '_nin_fc'
+                native.bias_grad(dY, flat.grad_view(name + '/biases'))
+
+        for rec in reversed(records):
+            kind = rec["kind"]
+            if kind == "last":
+                x = rec["x"]                                   # [B,H,W,F] raw block output, no prologue
+                cin = x.shape[3]
+                # weights: [3,3,cin,2]; gradients run as 8-channel launches (dpre channels 2..7 are zero)
                 if params:
-                    flat.grad_view(sn + '/biases').copy_(flat.grad_view(s1 + '/biases'))
-                # the skip is zero-padded bottom/right to x_1's size: only the overlapping window contributes
-                if a.shape[1] != dx_1.shape[1] or a.shape[2] != dx_1.shape[2]:
-                    raise ValueError("training with a spatially padded skip (H, W not multiples of 16) is not built")
-                if params:
-                    native.conv_wgrad(a, dx_1, flat.grad_view(sn + '/weights').view(1, -1, F_), ksize=1, stride=1, prologue=pro)
-                wn = V[sn + '/weights']                                   # [mult*Ca, F]
-                buf, acc = grads.target(a)
-                if mult == 2 and F_ in (8, 16, 32, 64) and wn.numel() * 4 <= 64 * 1024 and wn.is_contiguous():
-                    native.nin_bwd(dx_1, wn, a, pro, out=buf, accumulate=acc)       # 1x1 conv + prologue adjoint, one launch
-                else:
-                    dAa = _conv_plain(dx_1, wn.t().reshape(1, F_, -1).to(torch.bfloat16).contiguous(), wn.shape[0], 1, 1, dev)
-                    native.prologue_bwd(dAa, a, pro, out=buf, accumulate=acc)
-            if cin > 1:
-                w1 = V[s1 + '/weights']                                   # [3,3,mult*cin,F]
+                    tmp = torch.empty((9, cin, 8), dtype=torch.float32, device=dev)
+                    native.conv_wgrad(x, dpre, tmp, ksize=3, stride=1, prologue=native.PRO_NONE)
+                    flat.grad_view('last_conv_conv/weights').copy_(tmp[:, :, :2].reshape(3, 3, cin, 2))
+                    tmpb = torch.empty(8, dtype=torch.float32, device=dev)
+                    native.bias_grad(dpre, tmpb)
+                    flat.grad_view('last_conv_conv/biases').copy_(tmpb[:2])
+                w = V['last_conv_conv/weights']
+                w8 = torch.zeros((3, 3, cin, 8), dtype=torch.float32, device=dev)
+                w8[..., :2] = w
                 buf, acc = grads.target(x)
-                if stride == 1:
-                    _conv_dgrad_adjoint(dx_1, _dgrad_weights_s1(w1, 3), mult * cin, x, pro, dev, out=buf, accumulate=acc)
+                assert not acc
+                _conv_plain(dpre, _dgrad_weights_s1(w8, 3), cin, 3, 1, dev, out=buf)
+            elif kind == "tconv":
+                x, y, scope = rec["x"], rec["out"], rec["scope"]
+                g = grads.get(y)
+                cin, cout = x.shape[3], y.shape[3]
+                if params:
+                    native.tconv_wgrad(x, g, flat.grad_view(scope + '/weights').view(9, cout, cin))
+                bgrad_into(scope, g)
+                # d(x) = stride-2 'SAME' conv of d(y) with the same weights read as HWIO [k,k,Cout,Cin]
+                buf, acc = grads.target(x)
+                assert not acc
+                _conv_plain(g, _BwdWeights(V[scope + '/weights'], 3, cout, cin), cin, 3, 2, dev, out=buf)
+            elif kind == "block":
+                name, x, a, x_1, out = rec["name"], rec["x"], rec["a"], rec["x_1"], rec["out"]
+                F_, stride, gated, pro = rec["F"], rec["stride"], rec["gated"], rec["pro"]
+                keep_p, seed, pooled = rec["keep_p"], rec["seed"], rec["pooled"]
+                mult = 2 if pro in (native.PRO_CONCAT_ELU, native.PRO_CONCAT_RELU) else 1
+                g = grads.get(out)
+                cin = x.shape[3]
+                s2 = name + '_conv_2_conv'
+                n2 = 2 * F_ if gated else F_
+                # ---- conv_2 (+gate): recompute the pre-gate tensor, then its adjoint
+                if gated:
+                    kw = dict(res=g, keep_prob=keep_p, dropout_seed=seed)
+                    if arch._fused_conv(x_1, s2, 3, 1, n2, pro, native.EPI_GATE_BWD, query=True, **kw):
+                        # one launch: recompute [u|v] on the tensor cores, apply the gate's adjoint in the epilogue
+                        dc2 = arch._fused_conv(x_1, s2, 3, 1, n2, pro, native.EPI_GATE_BWD, **kw)
+                    else:
+                        c2 = arch._fused_conv(x_1, s2, 3, 1, n2, pro, native.EPI_BIAS, keep_prob=keep_p, dropout_seed=seed)
+                        dc2 = native.gate_bwd(c2, g)
                 else:
-                    if x.shape[1] % 2 or x.shape[2] % 2:
-                        raise ValueError("training a stride-2 block on odd spatial sizes is not built")
-                    _tconv_dgrad_adjoint(dx_1, _BwdWeights(w1, 3, F_, mult * cin, transpose=True), mult * cin, x, pro, dev,
-                                         buf, acc)                                 # weights as [tap, F, Keff]
-                native.shortcut_bwd(g, tuple(x.shape), pooled, out=buf, accumulate=True)
-            elif want_input_grad:
-                # the network input (1 channel, no prologue): conv adjoint with the output padded to 8 channels, plus
-                # the shortcut's front-padded identity (channel F-1 of g)
-                w1 = V[s1 + '/weights']                                   # [3,3,1,F]
-                w8 = torch.zeros((3, 3, 8, F_), dtype=torch.float32, device=dev)
-                w8[:, :, :1, :] = w1
-                dA1 = _conv_plain(dx_1, _dgrad_weights_s1(w8, 3), 8, 3, 1, dev)
-                d_input = dA1[..., :1].contiguous()
-                native.shortcut_bwd(g, tuple(x.shape), pooled, out=d_input, accumulate=True)
-    return (loss, d_input) if want_input_grad else loss
+                    dc2 = g
+                wgrad_into(s2, x_1, dc2, 3, 1, pro, keep_p, seed, bias=True)
+                dx_1 = _conv_dgrad_adjoint(dc2, _dgrad_weights_s1(V[s2 + '/weights'], 3), mult * F_, x_1, pro, dev,
+                                           keep_prob=keep_p, seed=seed)
+                # ---- conv_1 (+nin skip)
+                s1 = name + '_conv_1_conv'
+                pro1 = native.PRO_NONE if cin == 1 else pro
+                wgrad_into(s1, x, dx_1, 3, stride, pro1, bias=True)
+                if a is not None:
+                    sn = name + '_nin_fc'
+                    if params:
+                        flat.grad_view(sn + '/biases').copy_(flat.grad_view(s1 + '/biases'))
+                    # the skip is zero-padded bottom/right to x_1's size: only the overlapping window contributes
+                    if a.shape[1] != dx_1.shape[1] or a.shape[2] != dx_1.shape[2]:
+                        raise ValueError("training with a spatially padded skip (H, W not multiples of 16) is not built")
+                    if params:
+                        native.conv_wgrad(a, dx_1, flat.grad_view(sn + '/weights').view(1, -1, F_), ksize=1, stride=1, prologue=pro)
+                    wn = V[sn + '/weights']                                   # [mult*Ca, F]
+                    buf, acc = grads.target(a)
+                    if mult == 2 and F_ in (8, 16, 32, 64) and wn.numel() * 4 <= 64 * 1024 and wn.is_contiguous():
+                        native.nin_bwd(dx_1, wn, a, pro, out=buf, accumulate=acc)       # 1x1 conv + prologue adjoint, one launch
+                    else:
+                        dAa = _conv_plain(dx_1, wn.t().reshape(1, F_, -1).to(torch.bfloat16).contiguous(), wn.shape[0], 1, 1, dev)
+                        native.prologue_bwd(dAa, a, pro, out=buf, accumulate=acc)
+                if cin > 1:
+                    w1 = V[s1 + '/weights']                                   # [3,3,mult*cin,F]
+                    buf, acc = grads.target(x)
+                    if stride == 1:
+                        _conv_dgrad_adjoint(dx_1, _dgrad_weights_s1(w1, 3), mult * cin, x, pro, dev, out=buf, accumulate=acc)
+                    else:
+                        if x.shape[1] % 2 or x.shape[2] % 2:
+                            raise ValueError("training a stride-2 block on odd spatial sizes is not built")
+                        _tconv_dgrad_adjoint(dx_1, _BwdWeights(w1, 3, F_, mult * cin, transpose=True), mult * cin, x, pro, dev,
+                                             buf, acc)                                 # weights as [tap, F, Keff]
+                    native.shortcut_bwd(g, tuple(x.shape), pooled, out=buf, accumulate=True)
+                elif want_input_grad:
+                    # the network input (1 channel, no prologue): conv adjoint with the output padded to 8 channels, plus
+                    # the shortcut's front-padded identity (channel F-1 of g)
+                    w1 = V[s1 + '/weights']                                   # [3,3,1,F]
+                    w8 = torch.zeros((3, 3, 8, F_), dtype=torch.float32, device=dev)
+                    w8[:, :, :1, :] = w1
+                    dA1 = _conv_plain(dx_1, _dgrad_weights_s1(w8, 3), 8, 3, 1, dev)
+                    self.d_input = d_input = dA1[..., :1].contiguous()
+                    native.shortcut_bwd(g, tuple(x.shape), pooled, out=d_input, accumulate=True)
+
+
+def backward(tape, sflow_p, sflow, flat: FlatParams = None, want_input_grad=False):
+    """The whole backward pass in one go: returns the loss (fp32 [1]), or (loss, d loss / d boundary) with want_input_grad."""
+    bp = BackwardPass(sflow_p, sflow, flat, want_input_grad)
+    bp.run(tape)
+    return (bp.loss, bp.d_input) if want_input_grad else bp.loss
+
+
+def bucket_split(tape, flat: FlatParams, first_block="resnet_5_downsample"):
+    """Where to cut the backward pass for the two-bucket gradient all-reduce: (k, off) such that run(tape[k:]) fills
+    flat.grad[off:] completely -- every variable created from `first_block` on (variables are created, hence laid out,
+    in forward order) -- and run(tape[:k]) fills flat.grad[:off].  With the default cut the first bucket is the deepest
+    level and the decoder: ~2.2 of the 2.56 M parameters, done after ~60 % of the backward pass.  (None, None) if the
+    network has no such block."""
+    k = next((i for i, rec in enumerate(tape) if rec.get("kind") == "block" and rec.get("name") == first_block), None)
+    key = first_block + "_conv_1_conv/weights"
+    if k is None or key not in flat.offsets:
+        return None, None
+    return k, flat.offsets[key][0]
 
 
 def allreduce_gradients(flat_grad):
@@ -307,9 +345,10 @@ def allreduce_gradients(flat_grad):
     return flat_grad
 
 
-def adam_update(flat: FlatParams, lr, beta1=0.9, beta2=0.999, eps=1e-8):
-    """TF1 ApplyAdam on the flat buffers (after the optional gradient all-reduce)."""
-    allreduce_gradients(flat.grad)
+def adam_update(flat: FlatParams, lr, beta1=0.9, beta2=0.999, eps=1e-8, reduced=False):
+    """TF1 ApplyAdam on the flat buffers, after the gradient all-reduce (reduced=True: the caller has done it)."""
+    if not reduced:
+        allreduce_gradients(flat.grad)
     flat.step += 1
     native.adam_step(flat.param, flat.grad, flat.m, flat.v, flat.step, lr, beta1, beta2, eps)
     arch.VARIABLES.touch()

@@ -220,9 +220,15 @@ def train(total_loss, lr):
 
 class CompiledTraining:
     """One training step (forward + backward through the ~370 kernels of libflownet.so, incl. the re-packing of the
-    weights Adam just changed) captured into a CUDA graph for a fixed (B, H, W) and replayed; the gradient all-reduce
-    and the Adam update stay outside (two more launches).  At small per-GPU batches -- BASELINE configs[2] sharded over
-    4-8 GPUs -- the eager step is bound by the host's launch rate, the replay is not.
+    weights Adam just changed) captured into CUDA graphs for a fixed (B, H, W) and replayed; the gradient all-reduce
+    and the Adam update stay outside.  At small per-GPU batches -- BASELINE configs[2] sharded over 4-8 GPUs -- the eager
+    step is bound by the host's launch rate, the replay is not.
+
+    The step is TWO graphs (flow_backward.bucket_split): A = forward + backward of the decoder and the deepest level,
+    after which the tail of the flat gradient (~86 % of the parameters) is final; B = backward of the encoder.  With
+    torch.distributed initialised the first bucket's NCCL all-reduce is issued on a side stream behind A and runs under
+    B; the second, small bucket follows B (bucket / overlap with backward).  Every rank reduces the same two
+    slices in the same order, so the result is the single all-reduce's.
 
     With keep_prob < 1 the kernels add a device-resident counter to their dropout seeds (fn_conv_desc.dropout_seed_dev);
     step() bumps it before every replay, so each replay draws a new mask although the launch arguments are frozen."""
@@ -241,35 +247,78 @@ class CompiledTraining:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(2):
-                self._fwd_bwd()
+                self._part_a()
+                self._part_b()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         flow_architecture.VARIABLES.touch()              # the capture must contain the weight-packing kernels
-        self.graph = torch.cuda.CUDAGraph()
+        self.graph = torch.cuda.CUDAGraph()              # part A
+        self.graph_b = None
         n0 = native.launch_count()
         with torch.cuda.graph(self.graph):
-            self.loss = self._fwd_bwd()
+            self._part_a()
+        self.loss = self._pass.loss
+        if self._cut is not None:
+            self.graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_b, pool=self.graph.pool()):
+                self._part_b()
         self.launches_per_replay = native.launch_count() - n0
+        self.bucket_offset = self._cut[1] if self._cut is not None else 0
+        self._pass = None
         flow_architecture.TAPE = []
+        self._comm = torch.cuda.Stream()
+        self._ev = torch.cuda.Event()
 
-    def _fwd_bwd(self):
+    def _part_a(self):
+        """forward, loss gradient, backward of tape[k:] (everything when the network has no cut point)"""
         flow_architecture.TAPE = []
         native.DROPOUT_SEED_DEV = self.seed_dev
         try:
             sflow_p = inference(self.static_boundary, self.keep_prob, dropout_seed=self.dropout_seed)
             flat = ensure_training_state()
-            return self.fb.backward(flow_architecture.TAPE, sflow_p, self.static_sflow, flat)
+            tape = flow_architecture.TAPE
+            k, off = self.fb.bucket_split(tape, flat)
+            self._cut = None if k is None else (k, off)
+            self._tape = tape
+            self._pass = self.fb.BackwardPass(sflow_p, self.static_sflow, flat)
+            self._pass.run(tape if k is None else tape[k:])
+        finally:
+            native.DROPOUT_SEED_DEV = None
+
+    def _part_b(self):
+        if self._cut is None:
+            return
+        native.DROPOUT_SEED_DEV = self.seed_dev
+        try:
+            self._pass.run(self._tape[:self._cut[0]])
         finally:
             native.DROPOUT_SEED_DEV = None
 
     def step(self, boundary, sflow, lr):
         """boundary / sflow: CUDA or pinned host tensors of the captured shape.  Returns the loss (fp32 [1], device)."""
+        import torch.distributed as dist
+        flat = ensure_training_state()
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.static_boundary.copy_(boundary, non_blocking=True)
         self.static_sflow.copy_(sflow, non_blocking=True)
         if self.seed_dev is not None:
             self.seed_dev.add_(0x1E3779B97F4A7C15)           # new mask for this replay
         self.graph.replay()
-        self.fb.adam_update(ensure_training_state(), lr)
+        if self.graph_b is None:
+            self.fb.adam_update(flat, lr)
+            return self.loss
+        if multi:
+            # bucket 1 (decoder + deepest level) behind graph A on the side stream, under graph B
+            main = torch.cuda.current_stream()
+            self._ev.record(main)
+            self._comm.wait_event(self._ev)
+            with torch.cuda.stream(self._comm):
+                dist.all_reduce(flat.grad[self.bucket_offset:], op=dist.ReduceOp.SUM)
+        self.graph_b.replay()
+        if multi:
+            dist.all_reduce(flat.grad[:self.bucket_offset], op=dist.ReduceOp.SUM)
+            torch.cuda.current_stream().wait_stream(self._comm)
+        self.fb.adam_update(flat, lr, reduced=True)
         return self.loss
 
 

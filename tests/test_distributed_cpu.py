@@ -42,7 +42,28 @@ def _worker(rank, world, port, out_dir):
         per = B // world
         shard = slice(rank * per, (rank + 1) * per)
         g = _flat_oracle_grad(x[shard], tgt[shard])
+        # the two-bucket exchange of flow_net.CompiledTraining (decoder + deepest level first, encoder second) must equal
+        # the single all-reduce: cut from flow_backward.bucket_split on the oracle's variable layout
+        vs = fo.VariableStore(1234, torch.float64)
+        fo.inference(vs, x[:1], 1.0)
+
+        class _Flat:
+            offsets = {}
+        off = 0
+        for name, v in vs.vars.items():
+            _Flat.offsets[name] = (off, v.numel(), tuple(v.shape))
+            off += v.numel()
+        blocks = sorted({n.split("_conv_1_conv/")[0] for n in vs.vars if "_conv_1_conv/weights" in n},
+                        key=lambda b: _Flat.offsets[b + "_conv_1_conv/weights"][0])
+        tape = [dict(kind="block", name=b) for b in blocks] + [dict(kind="last")]
+        k, cut = fb.bucket_split(tape, _Flat)
+        assert tape[k]["name"] == "resnet_5_downsample" and 0 < cut < g.numel()
+        assert cut == sum(v.numel() for n, v in vs.vars.items() if _Flat.offsets[n][0] < _Flat.offsets["resnet_5_downsample_conv_1_conv/weights"][0])
+        g2 = g.clone()
+        dist.all_reduce(g2[cut:], op=dist.ReduceOp.SUM)
+        dist.all_reduce(g2[:cut], op=dist.ReduceOp.SUM)
         g = fb.allreduce_gradients(g)
+        assert torch.equal(g, g2)
         full = _flat_oracle_grad(x, tgt)
         err = ((g - full).norm() / full.norm()).item()
         # bench.py aggregation: every rank times its own steps, value = all images / max time
