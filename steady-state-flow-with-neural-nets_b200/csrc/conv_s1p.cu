@@ -203,6 +203,10 @@ __global__ void __launch_bounds__(SP_THREADS) k_conv_s1p(const __grid_constant__
     return true;
   };
 
+  if (threadIdx.x == 64) {       // descriptor fetch off the first tile's critical path
+    prefetch_tensormap(&p.tm_x);
+    if (SKIP) prefetch_tensormap(&p.tm_skip);
+  }
   // ---- one-time setup
   if (warp == SP_WARP_PRODUCER) {
     ptx::tmem_alloc(sbase + 128, (uint32_t)Cfg::TMEM_COLS);

@@ -127,6 +127,10 @@ __global__ void __launch_bounds__(NWG * 128, MINB) k_conv_wg(const __grid_consta
   const int g = warp >> 2, q = warp & 3;          // warpgroup, TMEM lane quadrant (== warp % 4)
   const int t128 = threadIdx.x & 127;
 
+  if (threadIdx.x == 64) {       // descriptor fetch off the first tile's critical path
+    prefetch_tensormap(&p.tm_x);
+    if (SKIP) prefetch_tensormap(&p.tm_skip);
+  }
   // ---- one-time setup
   if (warp == 0) {
     ptx::tmem_alloc(sbase + 512, (uint32_t)CF::TMEM_COLS);

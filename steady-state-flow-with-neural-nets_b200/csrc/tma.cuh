@@ -41,6 +41,11 @@ static inline bool make_map_nhwc(CUtensorMap* tm, const void* base, int B, int H
 }
 
 #ifdef __CUDACC__
+// the descriptor of a tensor copy is fetched on first use (~0.5-1 us from the kernel's parameter space): requesting it while
+// the CTA sets up its barriers and TMEM takes that off the first tile's critical path
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
