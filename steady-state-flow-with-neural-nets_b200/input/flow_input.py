@@ -98,7 +98,7 @@ class FlowInputQueue:
     whose host->device copies were issued from pinned memory on a side stream."""
 
     def __init__(self, files, batch_size, shape=(128, 256), min_after_dequeue=None, seed=0, device="cuda", shuffle=True,
-                 prefetch=2, parse_threads=8):
+                 prefetch=2, parse_threads=8, shard=(0, 1)):
         if not files:
             raise FileNotFoundError("no .tfrecords files")
         self.files = [TFRecordFile(p) for p in files]
@@ -116,6 +116,14 @@ class FlowInputQueue:
         # buffering parsed examples, but each example is parsed exactly once, straight into its pinned batch slot
         self._pool = []
         self._cursor = (0, 0)                                                   # (file, record)
+        # data-parallel training: rank r of R takes every R-th record of the stream, so the ranks' shuffle windows are
+        # disjoint (with one shared stream and different seeds they would draw from nearly the same window)
+        self._shard = (int(shard[0]), max(1, int(shard[1])))
+        if not 0 <= self._shard[0] < self._shard[1]:
+            raise ValueError("shard = (rank, world) with 0 <= rank < world")
+        if self.total < self._shard[1]:
+            raise ValueError("fewer records than ranks")
+        self._n = 0
         self._q = queue.Queue(maxsize=prefetch)
         self._stop = False
         self._copy_done = {}
@@ -125,11 +133,16 @@ class FlowInputQueue:
         self._thread.start()
 
     def _next_ref(self):
-        fi, ri = self._cursor
-        while ri >= len(self.files[fi]):
-            fi, ri = (fi + 1) % len(self.files), 0
-        self._cursor = (fi, ri + 1)
-        return fi, ri
+        rank, world = self._shard
+        while True:
+            fi, ri = self._cursor
+            while ri >= len(self.files[fi]):
+                fi, ri = (fi + 1) % len(self.files), 0
+            self._cursor = (fi, ri + 1)
+            mine = self._n % world == rank
+            self._n += 1
+            if mine:
+                return fi, ri
 
     def _producer(self):
         H, W = self.shape
@@ -202,6 +215,7 @@ class FlowInputQueue:
             pass
 
 
-def flow_inputs(batch_size, data_glob='../data/*.tfrecords', shape=(128, 256), seed=0, device="cuda"):
-    """reference :42-60.  Returns a FlowInputQueue; `boundarys, sflows = q.next()` per training step."""
-    return FlowInputQueue(sorted(_glob.glob(data_glob)), batch_size, shape=shape, seed=seed, device=device)
+def flow_inputs(batch_size, data_glob='../data/*.tfrecords', shape=(128, 256), seed=0, device="cuda", shard=(0, 1)):
+    """reference :42-60.  Returns a FlowInputQueue; `boundarys, sflows = q.next()` per training step.
+    shard = (rank, world): this process's share of the record stream in data-parallel training."""
+    return FlowInputQueue(sorted(_glob.glob(data_glob)), batch_size, shape=shape, seed=seed, device=device, shard=shard)

@@ -29,17 +29,18 @@ flags.DEFINE_integer('filter_size', 8, """ base number of filters (reference: 8)
 _QUEUES = {}
 
 
-def inputs(batch_size, shape=(128, 256), seed=0, device="cuda", data_glob=None):
+def inputs(batch_size, shape=(128, 256), seed=0, device="cuda", data_glob=None, shard=(0, 1)):
     """reference :29-31 returns a (boundary, sflow) batch from the TFRecord queue.  With `data_glob` (e.g.
     '../data/*.tfrecords', the reference's location) batches come from input.flow_input's shuffle queue over those
-    files; without a dataset (none ships, and there is no network) this yields the synthetic stand-in of the same
-    shapes: boundary uint8 [B,H,W,1], sflow float32 [B,H,W,2]."""
+    files (shard = (rank, world): every world-th record, for data-parallel training); without a dataset (none ships, and
+    there is no network) this yields the synthetic stand-in of the same shapes: boundary uint8 [B,H,W,1], sflow float32
+    [B,H,W,2]."""
     if data_glob is not None:
         import input.flow_input as flow_input
         key = (data_glob, batch_size, tuple(shape), str(device))
         q = _QUEUES.get(key)
         if q is None:
-            q = _QUEUES[key] = flow_input.flow_inputs(batch_size, data_glob, shape=shape, seed=seed, device=device)
+            q = _QUEUES[key] = flow_input.flow_inputs(batch_size, data_glob, shape=shape, seed=seed, device=device, shard=shard)
         return q.next()
     from utils.synthetic import synth_boundary, synth_sflow
     b = synth_boundary(batch_size, shape[0], shape[1], seed=seed)

@@ -46,47 +46,60 @@ def train():
     if rank == 0:
         print(train_dir)
     per_rank = max(1, FLAGS.batch_size // world)
-    flow_architecture.reset_variables(1234)       # every rank starts from the same variables
-    # init from checkpoint (reference :61-72): every rank reads the same file; a checkpoint that does not fit the
-    # graph is discarded and training starts from the random init
-    start_step = 0
+    import glob
+    data_glob = FLAGS.data_glob if glob.glob(FLAGS.data_glob) else None
+    if rank == 0:
+        print("training on " + (FLAGS.data_glob if data_glob else "synthetic boundaries (no dataset found)"))
+
+    def build(restored):
+        """Variables (every rank starts from the same ones), the captured step, and -- reference :61-72 -- the checkpoint.
+        The variables are created lazily, so a checkpoint can only be validated against the graph once a forward (the
+        captured step's warm-up, or one eager inference) has run: everything that can raise ValueError happens in here,
+        and the caller falls back to the random init."""
+        flow_architecture.reset_variables(1234)
+        flow_net.reset_training_state()
+        start = 0
+        if restored is not None:
+            start = checkpoint.restore(restored, flow_architecture.VARIABLES) + 1      # initial values of the lazy variables
+        flow_net.begin_training()
+        comp = None
+        if FLAGS.cuda_graph:
+            # captures one step for this (batch, shape); its warm-up creates the variables and the flat buffers without
+            # changing the parameters
+            comp = flow_net.CompiledTraining(per_rank, (128, 256), keep_prob=FLAGS.keep_prob, dropout_seed=1 + rank)
+        else:
+            b0, _ = flow_net.inputs(per_rank, seed=0)
+            flow_net.inference(b0, 1.0)
+            flow_architecture.TAPE = []
+        if restored is not None:
+            # now that the variables exist: shapes and names are checked (strict), the Adam slots restored
+            checkpoint.restore(restored, flow_architecture.VARIABLES, flow_net.ensure_training_state(), strict=True)
+        return comp, start
+
+    # init from checkpoint (reference :61-72): every rank reads the same file; a checkpoint that does not fit the graph is
+    # discarded and training starts from the random init
     ckpt = checkpoint.get_checkpoint_state(train_dir)
     restored = None
     if ckpt is not None:
         if rank == 0:
             print("init from " + train_dir)
         restored = checkpoint.load(ckpt)
-        try:
-            start_step = checkpoint.restore(restored, flow_architecture.VARIABLES) + 1
-        except ValueError:
-            restored = None
-            flow_architecture.reset_variables(1234)
-            print("there was a problem using variables in checkpoint, random init will be used instead")
-    import glob
-    data_glob = FLAGS.data_glob if glob.glob(FLAGS.data_glob) else None
-    if rank == 0:
-        print("training on " + (FLAGS.data_glob if data_glob else "synthetic boundaries (no dataset found)"))
-    flow_net.begin_training()
-    compiled = None
-    if FLAGS.cuda_graph:
-        # captures one step for this (batch, shape); its warm-up creates the variables and the flat buffers without
-        # changing the parameters, so the checkpoint's Adam slots can be restored right away
-        compiled = flow_net.CompiledTraining(per_rank, (128, 256), keep_prob=FLAGS.keep_prob, dropout_seed=1 + rank)
-        if restored is not None:
-            checkpoint.restore(restored, flow_architecture.VARIABLES, flow_net.ensure_training_state(), strict=False)
-            restored = None
+    try:
+        compiled, start_step = build(restored)
+    except ValueError:
+        if restored is None:
+            raise
+        print("there was a problem using variables in checkpoint, random init will be used instead")
+        compiled, start_step = build(None)
     for step in range(start_step, FLAGS.max_steps):
         t = time.time()
         boundary, sflow = flow_net.inputs(per_rank, seed=(step * world + rank) * per_rank if not data_glob else rank,
-                                          data_glob=data_glob)
+                                          data_glob=data_glob, shard=(rank, world))
         if compiled is not None:
             error = compiled.step(boundary, sflow, FLAGS.learning_rate)
         else:
             sflow_p = flow_net.inference(boundary, FLAGS.keep_prob, dropout_seed=step * 131071 + rank)
             error = flow_net.loss_image_train(sflow_p, sflow)
-            if restored is not None:              # the Adam slots live in the flat buffers, which need the variables
-                checkpoint.restore(restored, flow_architecture.VARIABLES, flow_net.ensure_training_state(), strict=False)
-                restored = None
             flow_net.train(error, FLAGS.learning_rate)
         loss_value = float(error.item())
         elapsed = time.time() - t

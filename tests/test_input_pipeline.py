@@ -144,6 +144,24 @@ def test_input_queue_fifo_and_shuffle(fi, tmp_path):
     assert counts.max() - counts.min() <= 3                  # a sliding shuffle window, not sampling with replacement
 
 
+def test_input_queue_rank_shards_are_disjoint_and_cover_the_stream(fi, tmp_path):
+    """data-parallel training: rank r of R reads every R-th record of the stream (train/flow_train.py passes shard=(rank, world))"""
+    b, s = _examples(12, seed=4)
+    p1, p2 = str(tmp_path / "1.tfrecords"), str(tmp_path / "2.tfrecords")
+    fi.write_tfrecords(p1, b[:7], s[:7])
+    fi.write_tfrecords(p2, b[7:], s[7:])
+    key = {b[i].tobytes(): i for i in range(12)}
+    seen = []
+    for rank in range(3):
+        q = fi.FlowInputQueue([p1, p2], 4, shape=(6, 10), device="cpu", shuffle=False, shard=(rank, 3))
+        gb, _ = q.next()
+        q.close()
+        seen.append([key[x.numpy().tobytes()] for x in gb])
+    assert seen == [[0, 3, 6, 9], [1, 4, 7, 10], [2, 5, 8, 11]]
+    with pytest.raises(ValueError):
+        fi.FlowInputQueue([p1], 1, shape=(6, 10), device="cpu", shard=(3, 3))
+
+
 def test_mechsys_crop_rule():
     from utils import flow_reader
     H, W = 4, 6
