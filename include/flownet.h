@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FN_ABI_VERSION 8
+#define FN_ABI_VERSION 9
 
 /* error codes (negative) */
 #define FN_E_INVAL      (-1)   /* null pointer, bad enum, non-positive dim */
@@ -219,6 +219,22 @@ typedef struct fn_level4_desc {
 } fn_level4_desc;
 int64_t fn_level4_weight_bytes(int32_t up);
 int fn_level4_fwd(const fn_level4_desc* d, void* stream);
+
+/* ---- levels 4 and 5 of the 128x256 grid (twelve convolutions, :202-222) in ONE launch: the stages of fn_level4_fwd(up = 0),
+ * fn_level5_fwd(split = 1) and fn_level4_fwd(up = 1) back to back inside one cluster kernel (csrc/conv_l4.cu, MODE_ALL).
+ *   x = x3 bf16 [B,32,64,32] -> y bf16 [B,32,64,32] (output of "up_conv_2"); x4 and z: bf16 [B,16,32,64] scratch (the outputs of
+ *   "resnet_4_0" and "up_conv_1", valid after the call); weight streams and biases exactly as for the three calls it replaces. */
+typedef struct fn_level45_desc {
+  int32_t B, reserved;
+  const void*  x;
+  void*        x4;
+  void*        z;
+  const void*  w_down;    const float* bias_down;      /* fn_level4_weight_bytes(0), fp32 [384] */
+  const void*  w_level5;  const float* bias_level5;    /* fn_level5_split_weight_bytes(), fp32 [2][416] */
+  const void*  w_up;      const float* bias_up;        /* fn_level4_weight_bytes(1), fp32 [224] */
+  void*        y;
+} fn_level45_desc;
+int fn_level45_fwd(const fn_level45_desc* d, void* stream);
 
 /* ---- the stride-1 convolutions of the 32x64 level of the 128x256 grid in two launches (csrc/conv_l3.cu), :198-201, 223-228;
  * same organisation as fn_level4_fwd, eight tiles per CTA.

@@ -62,6 +62,7 @@ int level5c_fwd(const fn_level5_desc& d, cudaStream_t stream);     // conv_l5c.c
 long long level5c_weight_bytes();
 int level4_fwd(const fn_level4_desc& d, cudaStream_t stream);       // conv_l4.cu
 long long level4_weight_bytes(int up);
+int level45_fwd(const fn_level45_desc& d, cudaStream_t stream);     // conv_l4.cu
 int level3_fwd(const fn_level3_desc& d, cudaStream_t stream);       // conv_l3.cu
 long long level3_weight_bytes(int up);
 
@@ -229,6 +230,15 @@ int fn_level4_fwd(const fn_level4_desc* d, void* stream) {
   return level4_fwd(*d, (cudaStream_t)stream);
 }
 
+int fn_level45_fwd(const fn_level45_desc* d, void* stream) {
+  FN_REQUIRE(d != nullptr, FN_E_INVAL, "fn_level45_fwd: null descriptor");
+  FN_REQUIRE(d->B > 0 && d->x && d->x4 && d->z && d->y && d->w_down && d->bias_down && d->w_level5 && d->bias_level5 && d->w_up && d->bias_up,
+             FN_E_INVAL, "fn_level45_fwd: null pointer or B = %d", d->B);
+  FN_REQUIRE(aligned16(d->x) && aligned16(d->x4) && aligned16(d->z) && aligned16(d->y) && aligned16(d->w_down) && aligned16(d->w_level5) &&
+                 aligned16(d->w_up), FN_E_ALIGN, "fn_level45_fwd: tensors and weight streams must be 16-byte aligned");
+  FN_REQUIRE(tma::get_encode() != nullptr, FN_E_UNSUPPORTED, "fn_level45_fwd: no tensor-map encoder (driver too old)");
+  return level45_fwd(*d, (cudaStream_t)stream);
+}
 int64_t fn_level3_weight_bytes(int32_t up) { return level3_weight_bytes(up); }
 int fn_level3_fwd(const fn_level3_desc* d, void* stream) {
   FN_REQUIRE(d != nullptr, FN_E_INVAL, "fn_level3_fwd: null descriptor");

@@ -21,6 +21,12 @@
 //                          (w >> 2) & 1 and channel half w >> 3 -- TMEM -> bias / gate / shortcut -> bf16 -> [elu | elu(-.)]
 //                          planes of the NEXT stage (own shared memory, border column also into the peer's halo)
 //
+//   MODE_ALL   both halves AND the 8x16 level between them (the stages of conv_l5c_body.cuh run by warps 0-7 on their own
+//              barrier set) in ONE launch: x3 -> [B,32,64,32].  x4 and z still pass through global memory (64 KB per image,
+//              L2), written and re-read on either side of a cluster barrier; what the merge removes is two launches
+//              (8-13 us each inside the forward: 217 KB of shared memory per CTA means the next kernel starts only when
+//              the previous one has drained) -- levels 4 + 5 = 12 convolutions in one launch
+//
 // Planes: [plane = 8 channels][row + 1][col + 1][8] with a zero border (TF 'SAME'), 18 x 18 pixels per plane; UMMA row
 // r = 8 row + (col & 7): a tap is a start-address offset of the shared-memory matrix descriptor, exactly as in the
 // layer-by-layer kernels, whose operands, bf16 rounding points and MMA order per accumulator this kernel reproduces.
@@ -29,6 +35,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "conv_l5c_body.cuh"
 #include "ptx.cuh"
 #include "tma.cuh"
 
@@ -69,14 +76,23 @@ constexpr int G1 = 0, G2 = G1 + chunks_of(W1), G3 = G2 + chunks_of(W2), G4 = G3 
 constexpr int G5 = 0, G6 = G5 + chunks_of(W5), G7 = G6 + chunks_of(W6);
 
 enum { SB_FULL = 0, SB_EMPTY = NST, SB_TF = 2 * NST, SB_XR = 2 * NST + 1, SB_XW = 2 * NST + 2 };
-enum { MODE_DOWN = 0, MODE_UP = 1 };
+enum { MODE_DOWN = 0, MODE_UP = 1, MODE_ALL = 2 };
+constexpr int SMEM_ALL = l5c::SMEM > SMEM_DOWN ? (l5c::SMEM > SMEM_UP ? l5c::SMEM : SMEM_UP) : (SMEM_DOWN > SMEM_UP ? SMEM_DOWN : SMEM_UP);
+static_assert(SMEM_ALL <= 231424, "shared memory");
+constexpr int NCHUNK_DOWN = chunks_of(W1) + chunks_of(W2) + chunks_of(W3) + chunks_of(W4);
+constexpr int BAR5 = 16;                       // MODE_ALL: first mbarrier of the level-5 stages' own set
 
 struct Params {
-  const __nv_bfloat16* x;       // DOWN: x3 [B,32,64,32]; UP: z [B,16,32,64]
+  const __nv_bfloat16* x;       // DOWN / ALL: x3 [B,32,64,32]; UP: z [B,16,32,64]
   const __nv_bfloat16* skip;    // UP: x4 [B,16,32,64]
-  const unsigned char* wstream; // the stage weight images back to back
+  const unsigned char* wstream; // the stage weight images back to back (ALL: the DOWN stages')
   const float* bias;
-  __nv_bfloat16* y;             // DOWN: x4 [B,16,32,64]; UP: [B,32,64,32]
+  __nv_bfloat16* y;             // DOWN: x4 [B,16,32,64]; UP / ALL: [B,32,64,32]
+  // MODE_ALL only
+  __nv_bfloat16* mid;           // x4 [B,16,32,64]: written by the DOWN stages, read by level 5 and (skip) by the UP stages
+  __nv_bfloat16* z;             // [B,16,32,64]: level 5's output, the UP stages' input
+  const unsigned char* wstream5; const float* bias5;        // level 5, per-rank form (fn_level5_desc.split)
+  const unsigned char* wstream_up; const float* bias_up;    // the UP stages
   int* status;
   long long* timing;            // debug: 16 clock64 stamps per CTA (fn_debug_set_timing; nullptr in production)
   int timing_ctas;
@@ -157,7 +173,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
   const int tid = threadIdx.x;
   const int b = (int)blockIdx.x >> 1;
   const uint32_t rank = cluster_rank(), peer = rank ^ 1u;
-  constexpr int NBIAS = MODE == MODE_DOWN ? NBIAS_DOWN : NBIAS_UP;
 
   if (warp == NWORK) {
     ptx::tmem_alloc(sbase + 256, 256u);
@@ -170,51 +185,103 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
       ptx::mbar_init(bar(SB_TF), 2);
       ptx::mbar_init(bar(SB_XR), 1);
       ptx::mbar_init(bar(SB_XW), NWORK);
+      if (MODE == MODE_ALL) l5c::init_barriers(bar(BAR5));
       ptx::fence_mbar_init();
     }
     __syncwarp();
   }
-  for (int i = tid; i < NBIAS; i += THREADS) {
-    float bv = __ldg(p.bias + i);
-    // the v halves of the gated convs: sigmoid(z) = 0.5 + 0.5 tanh(z / 2)
-    const bool vhalf = MODE == MODE_DOWN ? ((i >= B2 + 64 && i < B3) || i >= B4 + 64) : (i >= B6 + 64 && i < B7);
-    if (vhalf) bv *= 0.5f;
-    sbias[i] = bv;
-  }
+  // biases of one half into shared memory, the v halves of the gated convs pre-halved: sigmoid(z) = 0.5 + 0.5 tanh(z / 2)
+  auto load_biases = [&](const float* bias, bool down) {
+    const int n = down ? NBIAS_DOWN : NBIAS_UP;
+    for (int i = tid; i < n; i += THREADS) {
+      float bv = __ldg(bias + i);
+      const bool vhalf = down ? ((i >= B2 + 64 && i < B3) || i >= B4 + 64) : (i >= B6 + 64 && i < B7);
+      if (vhalf) bv *= 0.5f;
+      sbias[i] = bv;
+    }
+  };
+  load_biases(p.bias, MODE != MODE_UP);
+  // MODE_ALL: between two halves every thread of both CTAs passes here -- global writes of the finished half visible to the
+  // cluster, the next half's biases in place, nobody still reading the old ones
+  auto next_half = [&](auto load_next) {
+    __threadfence();
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    load_next();
+    cluster_sync_all();
+    ptx::tc_fence_after_sync();
+  };
   ptx::tc_fence_before_sync();
   cluster_sync_all();                 // both CTAs' barriers exist before anything arrives on them
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   bool ok = true;
-  long long* stamps = (p.timing != nullptr && (int)blockIdx.x < p.timing_ctas && tid == 0) ? p.timing + (size_t)blockIdx.x * 16 : nullptr;
+  long long* stamps = (MODE != MODE_ALL && p.timing != nullptr && (int)blockIdx.x < p.timing_ctas && tid == 0) ? p.timing + (size_t)blockIdx.x * 16 : nullptr;
   int nstamp = 0;
   auto stamp = [&]() { if (stamps) stamps[nstamp++] = clock64(); };
   stamp();
+  // MODE_ALL: the level-5 stages' view of this launch (their own barrier set, the same TMEM columns and ring region)
+  l5c::Ctx c5;
+  c5.sbase = sbase; c5.bar0 = bar(BAR5); c5.sb = sb; c5.tmem_base = tmem_base;
+  c5.warp = warp; c5.lane = lane; c5.tid = tid; c5.b = b; c5.rank = rank;
+  c5.x = p.mid; c5.y = p.z; c5.yp = nullptr; c5.wstream = p.wstream5; c5.status = p.status;
+  c5.stamps = nullptr; c5.nstamp = 0;
+  auto load_biases5 = [&]() { l5c::load_biases(sbias, p.bias5, rank, tid, THREADS); };
+  auto load_biases_up = [&]() { load_biases(p.bias_up, false); };
 
   if (warp == NWORK) {
     // =========================== producer: the weight stream (both CTAs read all of it) ===========================
     if (lane == 0) {
-      constexpr int NSTAGE = MODE == MODE_DOWN ? 4 : 3;
-      const int stage_bytes[4] = {MODE == MODE_DOWN ? W1 : W5, MODE == MODE_DOWN ? W2 : W6, MODE == MODE_DOWN ? W3 : W7, W4};
       const uint64_t pol = ptx::policy_evict_last();
-      int gc = 0;
-      size_t off = 0;
-      for (int st = 0; st < NSTAGE && ok; ++st) {
-        for (int rem = stage_bytes[st]; rem > 0 && ok; ++gc) {
-          const int bytes = rem < CHUNK ? rem : CHUNK;
-          const int s = gc % NST;
-          if (gc >= NST) {
-            ok = ptx::mbar_wait(bar(SB_EMPTY + s), (uint32_t)(((gc / NST) - 1) & 1));
-            if (!ok) { atomicCAS(p.status, 0, 81); break; }
+      int gc = 0;                       // ring chunk counter: runs on from the DOWN stages to the UP stages in MODE_ALL
+      auto stream = [&](const unsigned char* ws, bool down) {
+        const int nstage = down ? 4 : 3;
+        const int stage_bytes[4] = {down ? W1 : W5, down ? W2 : W6, down ? W3 : W7, W4};
+        size_t off = 0;
+        for (int st = 0; st < nstage && ok; ++st) {
+          for (int rem = stage_bytes[st]; rem > 0 && ok; ++gc) {
+            const int bytes = rem < CHUNK ? rem : CHUNK;
+            const int s = gc % NST;
+            if (gc >= NST) {
+              ok = ptx::mbar_wait(bar(SB_EMPTY + s), (uint32_t)(((gc / NST) - 1) & 1));
+              if (!ok) { atomicCAS(p.status, 0, 81); break; }
+            }
+            ptx::mbar_arrive_expect_tx(bar(SB_FULL + s), (uint32_t)bytes);
+            ptx::bulk_g2s_hint(sbase + OFF_RING + s * CHUNK, ws + off, (uint32_t)bytes, bar(SB_FULL + s), pol);
+            off += (size_t)bytes;
+            rem -= bytes;
           }
-          ptx::mbar_arrive_expect_tx(bar(SB_FULL + s), (uint32_t)bytes);
-          ptx::bulk_g2s_hint(sbase + OFF_RING + s * CHUNK, p.wstream + off, (uint32_t)bytes, bar(SB_FULL + s), pol);
-          off += (size_t)bytes;
-          rem -= bytes;
         }
-      }
+      };
+      stream(p.wstream, MODE != MODE_UP);
     }
     __syncwarp();
+    if constexpr (MODE == MODE_ALL) {
+      // the ring region changes hands only when the finished half has consumed all of its chunks: both cluster barriers of
+      // a hand-over are passed by this warp too
+      next_half(load_biases5);
+      l5c::producer(c5, ok);
+      next_half(load_biases_up);
+      if (lane == 0) {
+        const uint64_t pol = ptx::policy_evict_last();
+        int gc = NCHUNK_DOWN;
+        const int stage_bytes[3] = {W5, W6, W7};
+        size_t off = 0;
+        for (int st = 0; st < 3 && ok; ++st) {
+          for (int rem = stage_bytes[st]; rem > 0 && ok; ++gc) {
+            const int bytes = rem < CHUNK ? rem : CHUNK;
+            const int s = gc % NST;
+            ok = ptx::mbar_wait(bar(SB_EMPTY + s), (uint32_t)(((gc / NST) - 1) & 1));
+            if (!ok) { atomicCAS(p.status, 0, 86); break; }
+            ptx::mbar_arrive_expect_tx(bar(SB_FULL + s), (uint32_t)bytes);
+            ptx::bulk_g2s_hint(sbase + OFF_RING + s * CHUNK, p.wstream_up + off, (uint32_t)bytes, bar(SB_FULL + s), pol);
+            off += (size_t)bytes;
+            rem -= bytes;
+          }
+        }
+      }
+      __syncwarp();
+    }
   } else {
     // =========================== workers ===========================
     const uint32_t leader = ptx::elect_one();
@@ -231,7 +298,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
     // the CTA's border column is the peer's halo: rank 0's column 15 -> the peer's plane column 0, rank 1's column 0 -> 17
     const bool border = rank == 0 ? col == CW - 1 : col == 0;
     const uint32_t pp16_peer = (uint32_t)((row + 1) * PU + (rank == 0 ? 0 : PU - 1)) * 16u;
-    uint32_t tf_par = 0, x_par = 0;
+    uint32_t tf_par = 0, xr_par = 0, xw_par = 0;
 
     auto chunk_ready = [&](int gc, uint32_t lbo) -> uint64_t {
       const int s = gc % NST;
@@ -253,8 +320,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
     };
     // before the first remote write of an epilogue: the peer's MMAs no longer read its planes
     auto peer_planes_free = [&]() {
-      ok = ok && mbar_wait_cluster(bar(SB_XR), x_par);
+      ok = ok && mbar_wait_cluster(bar(SB_XR), xr_par);
       if (!ok) atomicCAS(p.status, 0, 84);
+      xr_par ^= 1u;
     };
     // after an epilogue: own writes (local + remote) visible to the tensor-core proxies, the peer told; then wait for the
     // local workers and for the peer's sixteen warps
@@ -264,10 +332,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(xw_peer);
       worker_barrier();
-      ok = ok && mbar_wait_cluster(bar(SB_XW), x_par);
+      ok = ok && mbar_wait_cluster(bar(SB_XW), xw_par);
       if (!ok) atomicCAS(p.status, 0, 85);
       fence_proxy_async_all();            // the peer's generic-proxy writes, acquired above, before this CTA's tensor-core reads
-      x_par ^= 1u;
+      xw_par ^= 1u;
     };
     auto put_plane = [&](int plane, const uint4& v) {
       sts128(A + (uint32_t)(plane * PPAD * 16) + pp16, v);
@@ -376,7 +444,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
       }
     };
 
-    if constexpr (MODE == MODE_DOWN) {
+    constexpr int GB = MODE == MODE_ALL ? NCHUNK_DOWN : 0;      // ring chunk index of the UP stages' first chunk
+    if constexpr (MODE != MODE_UP) {
       // ---- stage 1 operand: x3 -> concat_elu -> parity sub-planes (row 32 / column 64 are TF's zero padding); each CTA
       // reads the 33 columns its 16 output columns touch
       {
@@ -523,7 +592,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
       stamp();
       {
         const uint32_t r1_row = sbase + OFF_R1 + (uint32_t)pix * 128u;
-        __nv_bfloat16* dst = p.y + (((size_t)b * IH + row) * IW + gcol) * C4;
+        __nv_bfloat16* dst = (MODE == MODE_ALL ? p.mid : p.y) + (((size_t)b * IH + row) * IW + gcol) * C4;
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
           const int c = (chalf * 4 + g) * 8;
@@ -537,12 +606,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
           if (ok) *reinterpret_cast<uint4*>(dst + c) = pack8(o);
         }
       }
-    } else {
+    }
+    if constexpr (MODE == MODE_ALL) {
+      peer_planes_free();               // consumes the peer's arrival for stage 4, so that XR's phase matches the UP stages' count
+      next_half(load_biases5);
+      if (warp < 8) l5c::workers<2, true>(c5, ok);
+      next_half(load_biases_up);
+    }
+    if constexpr (MODE != MODE_DOWN) {
       // ---- stage 5 operands from global memory: planes of concat_elu(z) with the halo column read directly (zero outside
       // the image), centre-only planes of concat_elu(a) for the nin
       {
-        const __nv_bfloat16* zb = p.x + (size_t)b * IH * IW * C4;
-        const __nv_bfloat16* ab = p.skip + (size_t)b * IH * IW * C4;
+        const __nv_bfloat16* zb = (MODE == MODE_ALL ? p.z : p.x) + (size_t)b * IH * IW * C4;
+        const __nv_bfloat16* ab = (MODE == MODE_ALL ? p.mid : p.skip) + (size_t)b * IH * IW * C4;
         constexpr int ITEMS_Z = PV * PU * 8, ITEMS = ITEMS_Z + PS * 8;
         constexpr int UN = (ITEMS + WTHREADS - 1) / WTHREADS;       // every load of a thread in flight at once
         for (int base = tid; base < ITEMS; base += WTHREADS * UN) {
@@ -555,12 +631,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
               const int ch = idx & 7, sp = idx >> 3;
               const int pr = sp / PU, pc = sp - pr * PU;
               const int h = pr - 1, w = (int)rank * CW + pc - 1;
-              if (h >= 0 && h < IH && w >= 0 && w < IW) in[k] = __ldg(reinterpret_cast<const uint4*>(zb + ((size_t)h * IW + w) * C4 + ch * 8));
+              if (h >= 0 && h < IH && w >= 0 && w < IW) in[k] = l5c::ld_in<MODE == MODE_ALL>(reinterpret_cast<const uint4*>(zb + ((size_t)h * IW + w) * C4 + ch * 8));
             } else if (idx < ITEMS) {
               const int i2 = idx - ITEMS_Z;
               const int ch = i2 & 7, sp = i2 >> 3;
               const int h = sp >> 4, w = (int)rank * CW + (sp & 15);
-              in[k] = __ldg(reinterpret_cast<const uint4*>(ab + ((size_t)h * IW + w) * C4 + ch * 8));
+              in[k] = l5c::ld_in<MODE == MODE_ALL>(reinterpret_cast<const uint4*>(ab + ((size_t)h * IW + w) * C4 + ch * 8));
             }
           }
 #pragma unroll
@@ -592,9 +668,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
       // ---- stage 5: conv_1 of resnet_up_1_0 on concat_elu(z) plus the nin on concat_elu(a) (8 more k-steps, centre tap)
       if (warp < 2) {
         ptx::tc_fence_after_sync();
-        issue_conv(N64{}, I8{}, I9{}, a_planes, 2u * PPAD * 16u, tap_s1, G5, true);
+        issue_conv(N64{}, I8{}, I9{}, a_planes, 2u * PPAD * 16u, tap_s1, GB + G5, true);
         auto tap_c = [](int) -> uint32_t { return 0u; };
-        issue_conv(N64{}, I8{}, I1{}, ptx::smem_desc(sbase + OFF_S, PSPAD * 16, CW * 16), 2u * PSPAD * 16u, tap_c, G5 + 9, false);
+        issue_conv(N64{}, I8{}, I1{}, ptx::smem_desc(sbase + OFF_S, PSPAD * 16, CW * 16), 2u * PSPAD * 16u, tap_c, GB + G5 + 9, false);
         stage_commit();
       }
       // the shortcut of stage 6 (z, this thread's channels), recovered from the [elu(z) | elu(-z)] planes while stage 5 reads them
@@ -618,7 +694,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
       // nonlinearity, reference :219): 8 planes
       if (warp < 2) {
         ptx::tc_fence_after_sync();
-        issue_conv(N128{}, I8{}, I9{}, a_planes, 2u * PPAD * 16u, tap_s1, G6, true);
+        issue_conv(N128{}, I8{}, I9{}, a_planes, 2u * PPAD * 16u, tap_s1, GB + G6, true);
         stage_commit();
       }
       stage_done();
@@ -646,7 +722,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
         constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, 32);
 #pragma unroll 1
         for (int c = 0; c < chunks_of(W7); ++c) {
-          const uint64_t b_chunk = chunk_ready(G7 + c, 32 * 16);
+          const uint64_t b_chunk = chunk_ready(GB + G7 + c, 32 * 16);
 #pragma unroll
           for (int h4 = 0; h4 < 4; ++h4) {
             const int tap = 4 * c + h4;
@@ -663,7 +739,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
               }
             }
           }
-          if (leader) ptx::mma_commit(bar(SB_EMPTY + (G7 + c) % NST));
+          if (leader) ptx::mma_commit(bar(SB_EMPTY + (GB + G7 + c) % NST));
         }
         stage_commit();
       }
@@ -709,6 +785,7 @@ void tc_timing_buffer(long long** buf, int* ctas);   // conv_tc.cu: debug stamp 
 int level4_fwd(const fn_level4_desc& d, cudaStream_t stream) {
   using namespace l4;
   Params p;
+  memset(&p, 0, sizeof(p));
   p.x = (const __nv_bfloat16*)d.x;
   p.skip = (const __nv_bfloat16*)d.skip;
   p.wstream = (const unsigned char*)d.w_stream;
@@ -731,6 +808,35 @@ int level4_fwd(const fn_level4_desc& d, cudaStream_t stream) {
   count_launch();
   note_tcgen05(true);
   return check_launch("k_level4");
+}
+
+int level45_fwd(const fn_level45_desc& d, cudaStream_t stream) {
+  using namespace l4;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.x = (const __nv_bfloat16*)d.x;
+  p.wstream = (const unsigned char*)d.w_down;
+  p.bias = d.bias_down;
+  p.y = (__nv_bfloat16*)d.y;
+  p.mid = (__nv_bfloat16*)d.x4;
+  p.z = (__nv_bfloat16*)d.z;
+  p.wstream5 = (const unsigned char*)d.w_level5;
+  p.bias5 = d.bias_level5;
+  p.wstream_up = (const unsigned char*)d.w_up;
+  p.bias_up = d.bias_up;
+  p.status = tc_status_word();
+  if (p.status == nullptr) return (int)cudaErrorMemoryAllocation;
+  p.B = d.B;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_level4<MODE_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALL);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(level45): %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  k_level4<MODE_ALL><<<2 * d.B, THREADS, SMEM_ALL, stream>>>(p);
+  count_launch();
+  note_tcgen05(true);
+  return check_launch("k_level45");
 }
 
 long long level4_weight_bytes(int up) {

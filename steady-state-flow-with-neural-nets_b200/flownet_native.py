@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FLOWNET_LIB", os.path.join(_HERE, "libflownet.so"))   # override: A/B builds
 
-FN_ABI_VERSION = 8
+FN_ABI_VERSION = 9
 # enum fn_prologue
 PRO_NONE, PRO_CONCAT_ELU, PRO_ELU, PRO_CONCAT_RELU, PRO_RELU = 0, 1, 2, 3, 4
 # enum fn_epilogue
@@ -60,6 +60,12 @@ class Level4Desc(C.Structure):
                 ("bias", C.c_void_p), ("y", C.c_void_p)]
 
 
+class Level45Desc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("reserved", C.c_int32), ("x", C.c_void_p), ("x4", C.c_void_p), ("z", C.c_void_p),
+                ("w_down", C.c_void_p), ("bias_down", C.c_void_p), ("w_level5", C.c_void_p), ("bias_level5", C.c_void_p),
+                ("w_up", C.c_void_p), ("bias_up", C.c_void_p), ("y", C.c_void_p)]
+
+
 class Level3Desc(C.Structure):
     _fields_ = [("B", C.c_int32), ("up", C.c_int32), ("x", C.c_void_p), ("aux", C.c_void_p), ("w_stream", C.c_void_p),
                 ("bias", C.c_void_p), ("y", C.c_void_p)]
@@ -97,6 +103,7 @@ SYMBOLS = [
     ("fn_level5_fwd", C.c_int, [C.POINTER(Level5Desc), _P]),
     ("fn_level4_weight_bytes", C.c_int64, [C.c_int32]),
     ("fn_level4_fwd", C.c_int, [C.POINTER(Level4Desc), _P]),
+    ("fn_level45_fwd", C.c_int, [C.POINTER(Level45Desc), _P]),
     ("fn_level3_weight_bytes", C.c_int64, [C.c_int32]),
     ("fn_level3_fwd", C.c_int, [C.POINTER(Level3Desc), _P]),
     ("fn_nonlinearity", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
@@ -295,6 +302,26 @@ def level4_fwd(x, w_stream, bias, y, skip=None):
     d.x, d.w_stream, d.bias, d.y = x.data_ptr(), w_stream.data_ptr(), bias.data_ptr(), y.data_ptr()
     d.skip = skip.data_ptr() if up else None
     _check(lib.fn_level4_fwd(C.byref(d), stream_ptr()), "fn_level4_fwd")
+
+
+def level45_fwd(x3, x4, z, w_down, bias_down, w5, bias5, w_up, bias_up, y):
+    """Levels 4 and 5 in one launch (fn_level45_fwd): x3 bf16 [B,32,64,32] -> y bf16 [B,32,64,32] (output of up_conv_2); x4 / z:
+    bf16 [B,16,32,64] scratch; the weight streams / biases of level4_fwd (down), level5_fwd (split form) and level4_fwd (up)."""
+    _require_cuda(x3, x4, z, w_down, bias_down, w5, bias5, w_up, bias_up, y)
+    B = x3.shape[0]
+    if tuple(x3.shape) != (B, 32, 64, 32) or tuple(y.shape) != (B, 32, 64, 32) or tuple(x4.shape) != (B, 16, 32, 64) or tuple(z.shape) != (B, 16, 32, 64):
+        raise ValueError("level45_fwd: tensor shapes")
+    nb = lambda t: t.numel() * t.element_size()
+    if nb(w_down) != int(lib.fn_level4_weight_bytes(0)) or nb(w_up) != int(lib.fn_level4_weight_bytes(1)) or \
+            nb(w5) != int(lib.fn_level5_split_weight_bytes()) or bias_down.numel() != 384 or bias_up.numel() != 224 or bias5.numel() != 832:
+        raise ValueError("level45_fwd: weight stream / bias size")
+    d = Level45Desc()
+    d.B = B
+    d.x, d.x4, d.z, d.y = x3.data_ptr(), x4.data_ptr(), z.data_ptr(), y.data_ptr()
+    d.w_down, d.bias_down = w_down.data_ptr(), bias_down.data_ptr()
+    d.w_level5, d.bias_level5 = w5.data_ptr(), bias5.data_ptr()
+    d.w_up, d.bias_up = w_up.data_ptr(), bias_up.data_ptr()
+    _check(lib.fn_level45_fwd(C.byref(d), stream_ptr()), "fn_level45_fwd")
 
 
 def level3_fwd(x1, aux, w_stream, bias, y, up):

@@ -387,10 +387,9 @@ def _level5_fusable(x, nr_res_blocks, keep_prob, nonlinearity, gated, filter_siz
 LEVEL5_SPLIT = os.environ.get("FLOWNET_L5_SPLIT", "1") != "0"
 
 
-def _level5_fused(x):
-    """resnet_5_downsample, resnet_5_0 and up_conv_1 (reference :207-215).  Variables are created in the reference's
-    order; the five tensor-core weight images and biases are concatenated once per variable version."""
-    dev = x.device
+def _level5_weights(dev, split):
+    """The five tensor-core weight images and biases of the 8x16 level, concatenated once per variable version (split: the
+    per-rank form of the two-CTA kernel); variables are created in the reference's order."""
     names = ("resnet_5_downsample_conv_1_conv", "resnet_5_downsample_conv_2_conv", "resnet_5_0_conv_1_conv",
              "resnet_5_0_conv_2_conv")
     shapes = ((128, 128, False), (256, 256, True), (256, 128, False), (256, 256, True))
@@ -404,8 +403,6 @@ def _level5_fused(x):
         return w16, bt.contiguous(), native.pack_conv_weights_tc(w16, None, 3, 128, 0, 64, False)
 
     tpart = VARIABLES.derived(("tconv", scope), make_t)
-    # two CTAs per image while the clusters fit the GPU in one wave (measured: 52 vs 67 us at batch 64, 204 vs 135 us at 256)
-    split = LEVEL5_SPLIT and 2 * x.shape[0] <= torch.cuda.get_device_properties(dev).multi_processor_count
 
     def make():
         wstream = torch.cat([pt[3] for pt in parts] + [tpart[2]])
@@ -427,7 +424,15 @@ def _level5_fused(x):
             bs.append(tpart[1][r * 32:(r + 1) * 32])
         return torch.cat(ws), torch.cat(bs).to(torch.float32).contiguous()
 
-    wstream, bias = VARIABLES.derived(("level5", split), make_split if split else make)
+    return VARIABLES.derived(("level5", split), make_split if split else make)
+
+
+def _level5_fused(x):
+    """resnet_5_downsample, resnet_5_0 and up_conv_1 (reference :207-215) in one launch."""
+    dev = x.device
+    # two CTAs per image while the clusters fit the GPU in one wave (measured: 52 vs 67 us at batch 64, 204 vs 135 us at 256)
+    split = LEVEL5_SPLIT and 2 * x.shape[0] <= torch.cuda.get_device_properties(dev).multi_processor_count
+    wstream, bias = _level5_weights(dev, split)
     x = native.to_bf16(x)
     B = x.shape[0]
     y = torch.empty((B, 16, 32, 64), device=dev, dtype=torch.bfloat16)
@@ -473,9 +478,7 @@ def _tconv_parts(scope, cin, cout, dev):
     return VARIABLES.derived(("tconv", scope), make_t)
 
 
-def _level4_down(x):
-    """resnet_4_downsample and resnet_4_0 (reference :202-205) in one launch; variables in the reference's order."""
-    dev = x.device
+def _level4_down_weights(dev):
     names = ("resnet_4_downsample_conv_1_conv", "resnet_4_downsample_conv_2_conv", "resnet_4_0_conv_1_conv", "resnet_4_0_conv_2_conv")
     shapes = ((64, 64, False), (128, 128, True), (128, 64, False), (128, 128, True))
     parts = [_conv_weights(n, 3, k, c, dev, gated=g) for n, (k, c, g) in zip(names, shapes)]
@@ -483,7 +486,13 @@ def _level4_down(x):
     def make():
         return torch.cat([pt[3] for pt in parts]), torch.cat([pt[2] for pt in parts]).to(torch.float32).contiguous()
 
-    wstream, bias = VARIABLES.derived(("level4", "down"), make)
+    return VARIABLES.derived(("level4", "down"), make)
+
+
+def _level4_down(x):
+    """resnet_4_downsample and resnet_4_0 (reference :202-205) in one launch; variables in the reference's order."""
+    dev = x.device
+    wstream, bias = _level4_down_weights(dev)
     x = native.to_bf16(x)
     B = x.shape[0]
     y = torch.empty((B, 16, 32, 64), device=dev, dtype=torch.bfloat16)
@@ -497,11 +506,7 @@ def _level4_down(x):
     return y
 
 
-def _level4_up(z, a):
-    """resnet_up_1_0 (with the nin on the skip a = resnet_4_0's output) and up_conv_2 (reference :217-222) in one launch.
-    Variable creation order of the reference: up_conv_1 (created by the level-5 kernel's wrapper), the block's conv_1, nin,
-    conv_2, then up_conv_2."""
-    dev = z.device
+def _level4_up_weights(dev):
     c1 = _conv_weights("resnet_up_1_0_conv_1_conv", 3, 128, 64, dev, skip_scope="resnet_up_1_0_nin_fc", kskip_eff=128)
     c2 = _conv_weights("resnet_up_1_0_conv_2_conv", 3, 128, 128, dev, gated=True)
     tp = _tconv_parts("up_conv_2_trans_conv", 64, 32, dev)
@@ -509,7 +514,15 @@ def _level4_up(z, a):
     def make():
         return torch.cat([c1[3], c2[3], tp[2]]), torch.cat([c1[2], c2[2], tp[1]]).to(torch.float32).contiguous()
 
-    wstream, bias = VARIABLES.derived(("level4", "up"), make)
+    return VARIABLES.derived(("level4", "up"), make)
+
+
+def _level4_up(z, a):
+    """resnet_up_1_0 (with the nin on the skip a = resnet_4_0's output) and up_conv_2 (reference :217-222) in one launch.
+    Variable creation order of the reference: up_conv_1 (created by the level-5 kernel's wrapper), the block's conv_1, nin,
+    conv_2, then up_conv_2."""
+    dev = z.device
+    wstream, bias = _level4_up_weights(dev)
     B = z.shape[0]
     y = torch.empty((B, 32, 64, 32), device=dev, dtype=torch.bfloat16)
     rec = None
@@ -520,6 +533,39 @@ def _level4_up(z, a):
                    mma_clk=sum(_mma_clk(4 * B, ks, n) for ks, n in ((80, 64), (72, 128), (36, 32))))
     _profiled(rec, lambda: native.level4_fwd(z, wstream, bias, y, skip=a))
     return y
+
+
+# levels 4 and 5 in ONE launch (csrc/conv_l4.cu MODE_ALL): the stages of _level4_down, _level5_fused (two-CTA form) and
+# _level4_up inside one cluster kernel, bit-identical to the three launches.  Opt-in (FLOWNET_L45=1): measured at batch 64 it
+# is no faster back to back (106.0 vs 106.6 us, tools/ab_level45.py) and 15 us SLOWER inside the forward (0.5363 vs 0.5216 ms
+# per step) -- inside a CUDA graph the two launches it removes cost far less than the hand-overs it adds (the next half's
+# weight ring starts cold behind a cluster barrier, its operands are re-read through L2)
+LEVEL45_MERGED = os.environ.get("FLOWNET_L45", "0") == "1"
+
+
+def _level45_fused(x3):
+    """resnet_4_downsample ... up_conv_2 (reference :202-222), twelve convolutions, one launch.  Variables are created in the
+    reference's order (level 4 down, level 5, level 4 up)."""
+    dev = x3.device
+    wd, bd = _level4_down_weights(dev)
+    w5, b5 = _level5_weights(dev, True)
+    wu, bu = _level4_up_weights(dev)
+    x3 = native.to_bf16(x3)
+    B = x3.shape[0]
+    x4 = torch.empty((B, 16, 32, 64), device=dev, dtype=torch.bfloat16)
+    z = torch.empty((B, 16, 32, 64), device=dev, dtype=torch.bfloat16)
+    y = torch.empty((B, 32, 64, 32), device=dev, dtype=torch.bfloat16)
+    rec = None
+    if _PROFILE is not None:
+        macs = B * 512 * 9 * (64 * 64 + 128 * 128 + 128 * 64 + 128 * 128) + \
+            B * 128 * (9 * 128 * 128 + 9 * 256 * 256 + 9 * 256 * 128 + 9 * 256 * 256 + 9 * 128 * 64) + \
+            B * 512 * (9 * 128 * 64 + 128 * 64 + 9 * 128 * 128 + 9 * 64 * 32)
+        clk = sum(_mma_clk(4 * B, ks, n) for ks, n in ((36, 64), (72, 128), (72, 64), (72, 128), (80, 64), (72, 128), (36, 32))) + \
+            sum(_mma_clk(2 * B, ks, n) for ks, n in zip((72, 144, 144, 144, 72), (64, 128, 64, 128, 32)))
+        rec = dict(name="levels45_fused(resnet_4_downsample..up_conv_2)", kind="fused", out_hw=(32, 64), K_tap=256, N=256, stride=1,
+                   alg_bytes=(x3.numel() + y.numel()) * 2, flops=2 * macs, mma_clk=clk)
+    _profiled(rec, lambda: native.level45_fwd(x3, x4, z, wd, bd, w5, b5, wu, bu, y))
+    return y, x4
 
 
 # --------------------------------------------------------------------------- the 32x64 level's stride-1 convs in two launches
@@ -763,7 +809,7 @@ def conv_res(inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name='concat_e
     for i in range(nr_res_blocks):
         x = block(x, name="resnet_1_" + str(i))
     # res_2 .. res_5
-    fused5 = fused4 = fused3 = up3_done = False
+    fused5 = fused4 = fused3 = up3_done = fused45 = False
     for lvl in (2, 3, 4, 5):
         a.append(x)
         filter_size = 2 * filter_size
@@ -774,6 +820,13 @@ def conv_res(inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name='concat_e
             fused3 = True
             continue
         if lvl == 4 and _level4_fusable(x, nr_res_blocks, keep_prob, nonlinearity, gated, filter_size):
+            if LEVEL45_MERGED and LEVEL5_SPLIT:
+                # levels 4 and 5 entirely (down half, 8x16 level, up half incl. up_conv_2) in one launch
+                x, x4 = _level45_fused(x)
+                a.append(x4)
+                seed[0] += 5
+                fused45 = True
+                break
             # resnet_4_downsample + resnet_4_0 in one launch (csrc/conv_l4.cu); the matching up half runs after level 5
             x = _level4_down(x)
             seed[0] += 2
@@ -789,14 +842,18 @@ def conv_res(inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name='concat_e
         for i in range(nr_res_blocks):
             x = block(x, name="resnet_%d_%d" % (lvl, i))
     # res_up_1 .. res_up_4
+    if fused45:
+        filter_size = 2 * filter_size          # the loop left before level 5 doubled it
     for k in (1, 2, 3, 4):
         filter_size = int(filter_size / 2)
+        if k == 1 and fused45:
+            continue                            # resnet_up_1_0 and up_conv_2 ran inside the merged launch
         if k == 1 and fused4 and fused5:
             # resnet_up_1_0 + up_conv_2 in one launch; level 3's loop turn then skips its transposed conv
             x = _level4_up(x, a[-1])
             seed[0] += 1
             continue
-        if not ((k == 1 and fused5) or (k == 2 and fused4 and fused5) or (k == 3 and up3_done)):
+        if not ((k == 1 and fused5) or (k == 2 and ((fused4 and fused5) or fused45)) or (k == 3 and up3_done)):
             x = transpose_conv_layer(x, 3, 2, filter_size, "up_conv_%d" % k)
         if k == 2 and fused3 and nr_res_blocks == 1:
             # resnet_up_2_0 + up_conv_3 in two launches; level 2's loop turn then skips its transposed conv

@@ -636,15 +636,39 @@ def test_level4_fused_kernels_vs_layer_by_layer_and_oracle(native, B, monkeypatc
     arch.reset_variables(1234)
 
 
+@pytest.mark.parametrize("B", [1, 5, 74])
+def test_levels45_merged_launch_equals_the_three_launches(native, B):
+    """csrc/conv_l4.cu MODE_ALL: levels 4 and 5 (twelve convolutions) in one launch run the very stages of the three launches
+    they replace -- same operands, same order -- so the result is bit-identical, also when the launch is repeated."""
+    import model.flow_architecture as arch
+    arch.reset_variables(80)
+    g = torch.Generator().manual_seed(300 + B)
+    x3 = torch.randn(B, 32, 64, 32, generator=g).to(torch.bfloat16).cuda()
+    x4_ref = arch._level4_down(x3)
+    z_ref = arch._level5_fused(x4_ref)
+    y_ref = arch._level4_up(z_ref, x4_ref)
+    for _ in range(2):
+        y, x4 = arch._level45_fused(x3)
+        torch.cuda.synchronize()
+        assert native.tc_status() == 0
+        assert torch.equal(x4, x4_ref)
+        assert torch.equal(y, y_ref)
+    arch.reset_variables(1234)
+
+
 def test_net_with_and_without_the_fused_level4_kernels(native):
     import model.flow_architecture as arch
     x = fo.synth_boundary(3, 128, 256, seed=13).astype(np.uint8)
     y1 = _net(native, x, "auto")
     try:
+        arch.LEVEL45_MERGED = True
+        y2 = _net(native, x, "auto")
+        arch.LEVEL45_MERGED = False
         arch.LEVEL4_FUSED = False
         y0 = _net(native, x, "auto")
     finally:
-        arch.LEVEL4_FUSED = True
+        arch.LEVEL4_FUSED, arch.LEVEL45_MERGED = True, False
+    assert torch.equal(y1, y2)               # the opt-in merged launch vs the three it replaces
     assert rel_l2(y1, y0) < 2e-3
 
 
