@@ -255,7 +255,7 @@ def run_train(args, rank, world, dist, native, arch, flow_net, steps=None):
                                "keep_prob %.2f; tcgen05 fwd + dgrad + wgrad; %s" % (
                                    args.keep_prob, "fwd+bwd replayed from a CUDA graph" if compiled is not None else "eager launches"),
                    "batch_per_gpu": B,
-                   "parallelism": f"dp{world}, one flat fp32 gradient all-reduce (%s)" % ("NCCL" if world > 1 else "single GPU: none")},
+                   "parallelism": f"dp{world}, flat fp32 gradient all-reduce in two buckets, the first under the encoder's backward (%s)" % ("NCCL" if world > 1 else "single GPU: none")},
         # kernels of this library per step: those replayed from the graph + the eager ones (Adam) the counter saw
         "gpu_launches": native.launch_count() - n0 + (compiled.launches_per_replay * steps if compiled is not None else 0),
         "loss": float(loss.item()),

@@ -12,3 +12,4 @@ ncu -i /tmp/r2_fwd_full.ncu-rep --page raw --csv > gpurun_out/r2_fwd_full_raw.cs
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches_final.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train > gpurun_out/ncu_launch.log 2>&1
 tail -3 gpurun_out/r2_pytest.log
 head -c 600 gpurun_out/r2_bench_final.json
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
