@@ -63,6 +63,8 @@ long long level5c_weight_bytes();
 int level4_fwd(const fn_level4_desc& d, cudaStream_t stream);       // conv_l4.cu
 long long level4_weight_bytes(int up);
 int level45_fwd(const fn_level45_desc& d, cudaStream_t stream);     // conv_l4.cu
+bool conv_tail_supported(const fn_conv_desc& d);                    // conv_tail.cu
+int conv_tail_fwd(const fn_conv_desc& d, cudaStream_t stream);
 int level3_fwd(const fn_level3_desc& d, cudaStream_t stream);       // conv_l3.cu
 long long level3_weight_bytes(int up);
 
@@ -130,6 +132,7 @@ int fn_conv_fwd(const fn_conv_desc* d, void* stream) {
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const char* why = "";
+  if (d->impl != FN_IMPL_SIMT && conv_tail_supported(*d)) return conv_tail_fwd(*d, s);
   if (d->impl != FN_IMPL_SIMT && conv_tc_supported(*d, &why)) {
     note_tcgen05(true);
     return conv_fwd_tc(*d, s);
@@ -154,7 +157,7 @@ int fn_pack_conv_weights_tc_f32(const float* w, void* dst, int32_t ksize, int32_
 int fn_conv_fwd_has_tcgen05(const fn_conv_desc* d) {
   if (d == nullptr || validate_conv(*d) != 0 || d->impl == FN_IMPL_SIMT) return 0;
   const char* why = "";
-  return conv_tc_supported(*d, &why) ? 1 : 0;
+  return (conv_tail_supported(*d) || conv_tc_supported(*d, &why)) ? 1 : 0;
 }
 
 static int validate_tconv(const fn_tconv_desc* d) {

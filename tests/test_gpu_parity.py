@@ -197,6 +197,10 @@ TC_CASES = [
     ("raw_s2_c32", 3, 32, 32, 32, 64, 2, 0, 0, False, None, False),
     ("raw_s2_c8_ragged_even", 2, 36, 44, 8, 16, 2, 0, 0, False, None, False),
     ("raw_s2_c16_many_tiles", 40, 64, 64, 16, 32, 2, 0, 0, False, None, False),
+    # last_conv + tanh on the tensor cores (csrc/conv_tail.cu: two taps per MMA): whole tiles, ragged edges, many tiles
+    ("tail_tanh_tc", 2, 32, 64, 8, 2, 1, 0, 3, False, None, False),
+    ("tail_tanh_tc_ragged", 3, 45, 70, 8, 2, 1, 0, 3, False, None, False),
+    ("tail_tanh_tc_many_tiles", 20, 128, 256, 8, 2, 1, 0, 3, False, None, False),
 ]
 
 
