@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FN_ABI_VERSION 9
+#define FN_ABI_VERSION 10
 
 /* error codes (negative) */
 #define FN_E_INVAL      (-1)   /* null pointer, bad enum, non-positive dim */
@@ -118,6 +118,11 @@ typedef struct fn_conv_desc {
   int32_t  skip_planes;     /* 1: skip likewise (required with x_planes) */
   void*    y_planes;        /* optional second output: concat_elu(y) in planes form [B, 2Cy/8, OH, OW, 8]; y may then be
                                   NULL.  Taken by the planes kernel, the stride-2 tensor-core kernels and the 1-channel head */
+  /* the network input as it arrives: x (with Cin == 1, FN_PRO_NONE) and / or res (with Cres == 1) are uint8 [B,H,W,1] boundary
+   * masks instead of bf16 -- the head conv and the first block's one-channel shortcut then read the image directly and the
+   * separate cast launch disappears (inference; kernels without a uint8 path answer FN_E_UNSUPPORTED) */
+  int32_t  x_u8;
+  int32_t  res_u8;
 } fn_conv_desc;
 
 /* One transposed convolution launch: tf.nn.conv2d_transpose(k=3, s=2, 'SAME') + bias

@@ -76,6 +76,13 @@ static int validate_conv(const fn_conv_desc& d) {
   if (d.x_planes || d.skip_planes)
     FN_REQUIRE(d.x_planes && (!d.skip || d.skip_planes) && d.prologue == FN_PRO_CONCAT_ELU && d.impl != FN_IMPL_SIMT, FN_E_UNSUPPORTED,
                "fn_conv_fwd: planes operands need x_planes (and skip_planes with a skip), the concat_elu prologue, tcgen05");
+  if (d.x_u8)
+    FN_REQUIRE(d.Cin == 1 && d.Cout == 8 && d.ksize == 3 && d.stride == 1 && d.prologue == FN_PRO_NONE && d.epilogue == FN_EPI_BIAS && !d.skip &&
+                   !d.x_planes && d.keep_prob >= 1.0f,
+               FN_E_UNSUPPORTED, "fn_conv_fwd: a uint8 input is read by the 1 -> 8 channel head conv only");
+  if (d.res_u8)
+    FN_REQUIRE(d.res && d.Cres == 1 && !d.res_pool && d.epilogue == FN_EPI_GATE_RES && d.impl != FN_IMPL_SIMT, FN_E_UNSUPPORTED,
+               "fn_conv_fwd: a uint8 shortcut is the one-channel boundary image under a gated block (tcgen05)");
   FN_REQUIRE(d.ksize == 3 || d.ksize == 1, FN_E_UNSUPPORTED, "fn_conv_fwd: kernel size %d (only 1 and 3)", d.ksize);
   FN_REQUIRE(d.stride == 1 || d.stride == 2, FN_E_UNSUPPORTED, "fn_conv_fwd: stride %d (only 1 and 2)", d.stride);
   FN_REQUIRE(d.prologue >= FN_PRO_NONE && d.prologue <= FN_PRO_RELU, FN_E_INVAL, "fn_conv_fwd: bad prologue %d",

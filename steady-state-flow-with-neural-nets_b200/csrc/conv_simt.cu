@@ -356,7 +356,11 @@ __global__ void __launch_bounds__(256) k_head3x3(const __nv_bfloat16* __restrict
 
 // Round-2 head for 8 output channels: 16 x 64 tile, a thread owns a vertical strip of 4 output pixels and loads its 6 x 3
 // input values once (18 shared loads per 4 pixels instead of 36), 288 FMAs per strip; stores as in k_head3x3.
-__global__ void __launch_bounds__(256) k_head8_v2(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+__device__ __forceinline__ float head_in(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float head_in(unsigned char v) { return (float)v; }
+// TIN = unsigned char: the boundary image as it arrives (fn_conv_desc.x_u8) -- no separate cast launch
+template <typename TIN>
+__global__ void __launch_bounds__(256) k_head8_v2(const TIN* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                                                   __nv_bfloat16* __restrict__ yp, int B, int H, int W, int tiles_x, int tiles_y) {
   constexpr int TW = 64, TH = 16, PW = TW + 2, PH = TH + 2;
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(256) k_head8_v2(const __nv_bfloat16* __restric
       const int r = i / PW, c = i - r * PW;
       const int iy = y0 + r - 1, ix = x0 + c - 1;
       v[k] = 0.f;
-      if (i < NPX && iy >= 0 && iy < H && ix >= 0 && ix < W) v[k] = __bfloat162float(x[((size_t)b * H + iy) * W + ix]);
+      if (i < NPX && iy >= 0 && iy < H && ix >= 0 && ix < W) v[k] = head_in(x[((size_t)b * H + iy) * W + ix]);
     }
 #pragma unroll
     for (int k = 0; k < NLD; ++k) {
@@ -440,9 +444,14 @@ static int g_head_v2 = 1;      // debug / A-B: 0 sends the 8-channel head back t
 static int launch_head8_v2(const fn_conv_desc& d, cudaStream_t stream) {
   const int tiles_x = (d.W + 63) / 64, tiles_y = (d.H + 15) / 16;
   const long long grid = (long long)d.B * tiles_x * tiles_y;
-  k_head8_v2<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d.x), reinterpret_cast<const __nv_bfloat16*>(d.w),
-                                                 d.bias, reinterpret_cast<__nv_bfloat16*>(d.y), reinterpret_cast<__nv_bfloat16*>(d.y_planes),
-                                                 d.B, d.H, d.W, tiles_x, tiles_y);
+  if (d.x_u8)
+    k_head8_v2<unsigned char><<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const unsigned char*>(d.x), reinterpret_cast<const __nv_bfloat16*>(d.w),
+                                                                  d.bias, reinterpret_cast<__nv_bfloat16*>(d.y), reinterpret_cast<__nv_bfloat16*>(d.y_planes),
+                                                                  d.B, d.H, d.W, tiles_x, tiles_y);
+  else
+    k_head8_v2<__nv_bfloat16><<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d.x), reinterpret_cast<const __nv_bfloat16*>(d.w),
+                                                                  d.bias, reinterpret_cast<__nv_bfloat16*>(d.y), reinterpret_cast<__nv_bfloat16*>(d.y_planes),
+                                                                  d.B, d.H, d.W, tiles_x, tiles_y);
   count_launch();
   return check_launch("k_head8_v2");
 }
@@ -649,7 +658,7 @@ static int launch_tail(const fn_conv_desc& d, cudaStream_t stream) {
 // returns true (and sets rc) if a specialised head/tail kernel took the launch
 static bool try_direct(const fn_conv_desc& d, cudaStream_t stream, int& rc) {
   if (d.ksize != 3 || d.stride != 1 || d.prologue != FN_PRO_NONE || d.skip || d.keep_prob < 1.0f) return false;
-  if (d.epilogue == FN_EPI_BIAS && d.Cin == 1 && d.Cout == 8) { rc = g_head_v2 ? launch_head8_v2(d, stream) : launch_head<8>(d, stream); return true; }
+  if (d.epilogue == FN_EPI_BIAS && d.Cin == 1 && d.Cout == 8) { rc = (g_head_v2 || d.x_u8) ? launch_head8_v2(d, stream) : launch_head<8>(d, stream); return true; }
   if (d.epilogue == FN_EPI_BIAS && d.Cin == 1 && d.Cout == 16) { rc = launch_head<16>(d, stream); return true; }
   if (d.epilogue == FN_EPI_BIAS && d.Cin == 1) {
     if (d.Cout == 8) { rc = launch_direct<1, 8, false>(d, stream); return true; }

@@ -739,6 +739,10 @@ int conv_fwd_tc(const fn_conv_desc& d, cudaStream_t stream) {
     return FN_E_UNSUPPORTED;
   }
   if (g_tc_use_s1p && conv_wg_try(d, stream, false, rc_sp)) return rc_sp;
+  if (d.res_u8) {
+    set_error("conv_fwd_tc: only k_conv_wg reads a uint8 shortcut, and it does not take this shape");
+    return FN_E_UNSUPPORTED;
+  }
   if (g_tc_use_s1p && conv_s1p_try(d, stream, false, rc_sp)) return rc_sp;
   if (g_tc_use_s1p && conv_s1d_try(d, stream, false, rc_sp)) return rc_sp;
   if (g_tc_use_s1p && conv_s1w_try(d, stream, false, rc_sp)) return rc_sp;

@@ -41,6 +41,7 @@ struct Params {
   int Cout;
   int res_mode;                        // 0 none, 1 plain tile (Cres == F), 2 generic (pool / channel pad), 3 one channel
   int Cres, RH, RW, res_pool;
+  int res_u8;                          // res_mode 3: the shortcut is the uint8 boundary image itself
   int s_u, s_v, s_b;                   // the tile stride (grid * NWG) as a mixed-radix number over (tiles_u, tiles_v, B)
 };
 
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(NWG * 128, MINB) k_conv_wg(const __grid_consta
         }
       } else if (RESM == 3) {
         // 1-channel shortcut (the boundary image under the first block): lands in the LAST channel (front zero pad, :158-163)
-        if (inside) r1[j] = __bfloat162float(p.res[pix]);
+        if (inside) r1[j] = p.res_u8 ? (float)reinterpret_cast<const unsigned char*>(p.res)[pix] : __bfloat162float(p.res[pix]);
       }
     }
     // ---- raw tile(s) -> concat_elu A planes
@@ -352,6 +353,7 @@ static int launch_m(const fn_conv_desc& d, int* status, cudaStream_t stream) {
   }
   p.res_mode = RESM;
   p.res = (const __nv_bfloat16*)d.res;
+  p.res_u8 = d.res_u8;
   p.wpk = (const __nv_bfloat16*)d.w_tc;
   p.bias = d.bias;
   p.y = (__nv_bfloat16*)d.y;
@@ -417,6 +419,7 @@ bool conv_wg_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& 
   const bool skip = d.skip != nullptr;
   if (skip && (gate || d.Cskip != d.Cin)) return false;
   if (d.H < 16 || d.W < 8) return false;
+  if (d.res_u8 && !(d.res && d.Cres == 1 && !d.res_pool && d.RH == d.H && d.RW == d.W)) return false;
   if (get_encode() == nullptr) return false;
   const int clog = d.Cin == 8 ? 0 : d.Cin == 16 ? 1 : d.Cin == 32 ? 2 : -1;
   if (clog < 0) return false;

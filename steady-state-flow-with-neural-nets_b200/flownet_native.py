@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FLOWNET_LIB", os.path.join(_HERE, "libflownet.so"))   # override: A/B builds
 
-FN_ABI_VERSION = 9
+FN_ABI_VERSION = 10
 # enum fn_prologue
 PRO_NONE, PRO_CONCAT_ELU, PRO_ELU, PRO_CONCAT_RELU, PRO_RELU = 0, 1, 2, 3, 4
 # enum fn_epilogue
@@ -38,6 +38,7 @@ class ConvDesc(C.Structure):
         ("dropout_seed_dev", C.c_void_p),
         ("adj_prologue", C.c_int32), ("adj_accumulate", C.c_int32),
         ("x_planes", C.c_int32), ("skip_planes", C.c_int32), ("y_planes", C.c_void_p),
+        ("x_u8", C.c_int32), ("res_u8", C.c_int32),
     ]
 
 
@@ -231,6 +232,9 @@ def conv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, ksize=3, stride=1, prologue=P
         bias.data_ptr(), (y.data_ptr() if y is not None else None)
     d.x_planes, d.skip_planes = int(bool(x_planes)), int(bool(skip_planes))
     d.y_planes = y_planes.data_ptr() if y_planes is not None else None
+    # the boundary image as it arrives (uint8): read directly by the head conv / the first block's one-channel shortcut
+    d.x_u8 = int(x.dtype == torch.uint8)
+    d.res_u8 = int(res is not None and res.dtype == torch.uint8)
     if skip is not None:
         d.skip, d.w_skip = skip.data_ptr(), w_skip.data_ptr()
         if skip_planes:

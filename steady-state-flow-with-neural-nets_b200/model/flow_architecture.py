@@ -234,7 +234,10 @@ def _conv_weights(scope, ksize, cin_eff, cout, device, skip_scope=None, kskip_ef
 def _fused_conv(x, scope, ksize, stride, cout, prologue, epilogue, skip=None, skip_scope=None, res=None,
                 res_pool=False, keep_prob=1.0, dropout_seed=0, query=False):
     """One fused launch.  query=True returns whether it would run on the tensor cores instead of launching."""
-    x = native.to_bf16(x)
+    # uint8 stays uint8 only for the one launch that reads it directly, the 1 -> 8 channel head conv (fn_conv_desc.x_u8)
+    if not (x.dtype == torch.uint8 and x.shape[3] == 1 and cout == 8 and ksize == 3 and stride == 1 and prologue == native.PRO_NONE
+            and epilogue == native.EPI_BIAS and skip is None and keep_prob >= 1.0):
+        x = native.to_bf16(x)
     B, H, W, cin = int_shape(x)
     mult = _pro_mult(prologue)
     kskip = 0
@@ -255,9 +258,9 @@ def _fused_conv(x, scope, ksize, stride, cout, prologue, epilogue, skip=None, sk
                     dtype=torch.float32 if epilogue == native.EPI_TANH else torch.bfloat16)
     rec = None
     if _PROFILE is not None:
-        nbytes = x.numel() * 2 + y.numel() * y.element_size()
+        nbytes = x.numel() * x.element_size() + y.numel() * y.element_size()
         nbytes += skip.numel() * 2 if skip is not None else 0
-        nbytes += res.numel() * 2 if res is not None else 0
+        nbytes += res.numel() * res.element_size() if res is not None else 0
         flops = 2 * B * OH * OW * cout * (ksize * ksize * cin * mult + kskip)
         ksteps = ksize * ksize * (-(-cin * mult // 16)) + kskip // 16
         rec = dict(name=scope, kind="conv", out_hw=(OH, OW), K_tap=cin * mult, N=cout, stride=stride,
@@ -350,7 +353,12 @@ def res_block(x, a=None, filter_size=16, nonlinearity=concat_elu, keep_p=1.0, st
     pro = _PROLOGUE_OF.get(nonlinearity)
     if pro is None:
         return _res_block_unfused(x, a, filter_size, nonlinearity, keep_p, stride, gated, name)
-    orig_x = native.to_bf16(x)
+    # inference on the boundary image as it arrives (uint8 [B,H,W,1]): the head conv and the gated conv_2's one-channel shortcut
+    # read it directly (fn_conv_desc.x_u8 / res_u8) -- no cast launch, no bf16 copy of the input
+    direct_u8 = (x.dtype == torch.uint8 and x.shape[3] == 1 and TAPE is None and IMPL == native.IMPL_AUTO and gated and stride == 1
+                 and a is None and filter_size == 8 and pro == native.PRO_CONCAT_ELU and keep_p >= 1.0 and x.shape[1] >= 16 and x.shape[2] >= 8
+                 and native.level5_supported(16, 32, 64) and os.environ.get("FLOWNET_WG", "1") != "0")
+    orig_x = x if direct_u8 else native.to_bf16(x)
     cin = orig_x.shape[3]
     if a is not None and cin == 1:
         raise ValueError("res_block: a skip input on a 1-channel block is not supported")
@@ -805,7 +813,7 @@ def conv_res(inputs, nr_res_blocks=1, keep_prob=1.0, nonlinearity_name='concat_e
     # store for as
     a = []
     # res_1
-    x = native.to_bf16(inputs)
+    x = inputs if inputs.dtype == torch.uint8 else native.to_bf16(inputs)      # uint8: see res_block
     for i in range(nr_res_blocks):
         x = block(x, name="resnet_1_" + str(i))
     # res_2 .. res_5
