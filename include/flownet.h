@@ -162,6 +162,10 @@ int         fn_last_used_tcgen05(void);
 int fn_conv_fwd(const fn_conv_desc* d, void* stream);
 /* 1 if fn_conv_fwd(d) would run on the tensor cores (pointers are not dereferenced, only tested for NULL), else 0 */
 int fn_conv_fwd_has_tcgen05(const fn_conv_desc* d);
+/* which tensor-core weight image the kernel that will take this conv reads: 0 = fn_pack_conv_weights_tc of the weights as they are,
+ * 1 = pass-major (the two-pass 256-channel kernel, csrc/conv_s1w.cu: the image of K rows {0..127, 256..383} followed by that of
+ * {128..255, 384..511}).  w_tc may be NULL in the query.  The ONE place this decision is made: callers pack what it says. */
+int fn_conv_weights_layout(const fn_conv_desc* d);
 /* tensor-core weight image (as fn_pack_conv_weights_tc, fn_conv_weights_tc_bytes(ksize, K, 0, Cout, 0) bytes) straight from an
  * fp32 variable: logical weights W'[tap][k][n] = src[flip_taps ? T-1-tap : tap][k][n], or src[..][n][k] if transpose.
  * (flip, transpose) = (1, 1) on an HWIO variable gives the B operand of that conv's data gradient. */

@@ -64,6 +64,7 @@ int level4_fwd(const fn_level4_desc& d, cudaStream_t stream);       // conv_l4.c
 long long level4_weight_bytes(int up);
 int level45_fwd(const fn_level45_desc& d, cudaStream_t stream);     // conv_l4.cu
 bool conv_tail_supported(const fn_conv_desc& d);                    // conv_tail.cu
+bool conv_weights_pass_major(const fn_conv_desc& d);                // conv_tc.cu
 int conv_tail_fwd(const fn_conv_desc& d, cudaStream_t stream);
 int level3_fwd(const fn_level3_desc& d, cudaStream_t stream);       // conv_l3.cu
 long long level3_weight_bytes(int up);
@@ -165,6 +166,14 @@ int fn_conv_fwd_has_tcgen05(const fn_conv_desc* d) {
   if (d == nullptr || validate_conv(*d) != 0 || d->impl == FN_IMPL_SIMT) return 0;
   const char* why = "";
   return (conv_tail_supported(*d) || conv_tc_supported(*d, &why)) ? 1 : 0;
+}
+
+int fn_conv_weights_layout(const fn_conv_desc* d) {
+  if (d == nullptr || d->impl == FN_IMPL_SIMT || d->skip != nullptr || d->x_planes) return 0;
+  fn_conv_desc q = *d;
+  if (q.w_tc == nullptr) q.w_tc = q.w;          // any non-null pointer: the query launches nothing
+  if (validate_conv(q) != 0) return 0;
+  return conv_weights_pass_major(q) ? 1 : 0;
 }
 
 static int validate_tconv(const fn_tconv_desc* d) {

@@ -726,6 +726,15 @@ static int launch_tc(TcParams& p, size_t smem_bytes, cudaStream_t stream) {
 
 bool conv_wg_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& rc);    // conv_wg.cu
 
+// true if the kernel conv_fwd_tc() will pick for d reads the pass-major weight image (k_conv_s1w without a skip operand);
+// follows the dispatch order below
+bool conv_weights_pass_major(const fn_conv_desc& d) {
+  int rc = 0;
+  if (!g_tc_use_s1p || d.x_planes || d.skip_planes || d.y_planes || d.y == nullptr || d.skip != nullptr) return false;
+  if (conv_wg_try(d, nullptr, true, rc) || conv_s1p_try(d, nullptr, true, rc) || conv_s1d_try(d, nullptr, true, rc)) return false;
+  return conv_s1w_try(d, nullptr, true, rc);
+}
+
 int conv_fwd_tc(const fn_conv_desc& d, cudaStream_t stream) {
   int rc_sp = 0;
   if (d.x_planes || d.skip_planes) {

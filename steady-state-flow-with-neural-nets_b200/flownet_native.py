@@ -93,6 +93,7 @@ SYMBOLS = [
     ("fn_last_used_tcgen05", C.c_int, []),
     ("fn_conv_fwd", C.c_int, [C.POINTER(ConvDesc), _P]),
     ("fn_conv_fwd_has_tcgen05", C.c_int, [C.POINTER(ConvDesc)]),
+    ("fn_conv_weights_layout", C.c_int, [C.POINTER(ConvDesc)]),
     ("fn_pack_conv_weights_tc_f32", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     ("fn_tconv_fwd", C.c_int, [C.POINTER(TConvDesc), _P]),
     ("fn_tconv_fwd_has_tcgen05", C.c_int, [C.POINTER(TConvDesc)]),
@@ -249,6 +250,8 @@ def conv_fwd(x, w, bias, y, *, B, H, W, Cin, Cout, ksize=3, stride=1, prologue=P
     d.dropout_seed, d.dropout_offset = int(dropout_seed), int(dropout_offset)
     d.dropout_seed_dev = DROPOUT_SEED_DEV.data_ptr() if DROPOUT_SEED_DEV is not None else None
     d.adj_prologue, d.adj_accumulate = int(adj_prologue), int(bool(adj_accumulate))
+    if query == "layout":            # 1: the kernel that will run reads the pass-major weight image (fn_conv_weights_layout)
+        return int(lib.fn_conv_weights_layout(C.byref(d)))
     if query:
         return bool(lib.fn_conv_fwd_has_tcgen05(C.byref(d)))
     _check(lib.fn_conv_fwd(C.byref(d), stream_ptr()), "fn_conv_fwd")

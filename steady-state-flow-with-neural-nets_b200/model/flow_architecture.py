@@ -245,8 +245,13 @@ def _fused_conv(x, scope, ksize, stride, cout, prologue, epilogue, skip=None, sk
         skip = native.to_bf16(skip)
         kskip = skip.shape[3] * mult
     gated = epilogue in (native.EPI_GATE_RES, native.EPI_GATE_BWD)
-    pass_major = (cin * mult == 512 and ksize == 3 and stride == 1 and skip is None and prologue == native.PRO_CONCAT_ELU
-                  and cout in (256, 512) and H % 8 == 0 and W >= 16)
+    # the two-pass 256-channel kernel reads its weights pass-major: the library says whether it will take this launch
+    # (fn_conv_weights_layout -- the dispatch's own acceptance test; placeholders stand in for the tensors not made yet)
+    pass_major = False
+    if cin * mult == 512 and skip is None and IMPL != native.IMPL_SIMT:
+        pass_major = bool(native.conv_fwd(x, x, x, x, B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize, stride=stride, prologue=prologue,
+                                          epilogue=epilogue, impl=IMPL, w_tc=None, res=res, res_pool=res_pool, keep_prob=keep_prob,
+                                          dropout_seed=dropout_seed, query="layout"))
     w16, ws16, bias, w_tc = _conv_weights(scope, ksize, cin * mult, cout, x.device, skip_scope, kskip, gated, pass_major)
     OH, OW = -(-H // stride), -(-W // stride)
     cy = cout // 2 if epilogue == native.EPI_GATE_RES else cout
