@@ -26,6 +26,7 @@
 namespace fn {
 using namespace tma;
 namespace wg {
+static int g_mma_lock = 1;
 
 constexpr int HDR = 2048;     // [0,512) mbarriers, [512] TMEM base, [1024, 2048) bias (<= 256 floats)
 
@@ -42,6 +43,7 @@ struct Params {
   int res_mode;                        // 0 none, 1 plain tile (Cres == F), 2 generic (pool / channel pad), 3 one channel
   int Cres, RH, RW, res_pool;
   int res_u8;                          // res_mode 3: the shortcut is the uint8 boundary image itself
+  int mma_lock;                        // 1: serialise the MMA bursts of a CTA's issuing warps
   int s_u, s_v, s_b;                   // the tile stride (grid * NWG) as a mixed-radix number over (tiles_u, tiles_v, B)
 };
 
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(NWG * 128, MINB) k_conv_wg(const __grid_consta
     ptx::tmem_alloc(sbase + 512, (uint32_t)CF::TMEM_COLS);
     ptx::tmem_relinquish();
   } else if (warp == 1 && lane == 0) {
+    *reinterpret_cast<volatile int*>(smem + 520) = 0;       // MMA-burst lock (see the issue step)
     ptx::mbar_init(bar(0), 1);
     for (int i = 1; i < 1 + NWG * (1 + J); ++i) ptx::mbar_init(bar(i), 1);
     ptx::fence_mbar_init();
@@ -243,6 +246,13 @@ __global__ void __launch_bounds__(NWG * 128, MINB) k_conv_wg(const __grid_consta
       const uint64_t b_tmpl = ptx::smem_desc(sbase + CF::OFF_W, CF::N * 16, 128);
       const uint32_t d_tmem = acc + (uint32_t)(q * CF::N);
       if (leader) {
+        // one sub-tile's MMAs as a burst: with every issuing warp of the SM feeding the MMA unit round-robin, each
+        // program of nine 39-clock instructions took 3.5 k clocks to get through (processor sharing); serialised per CTA
+        // (two CTAs per SM keep the unit fed) a program completes in ~0.5 k once it starts, and its epilogue with it
+        if (p.mma_lock) {
+          int* lock = reinterpret_cast<int*>(smem + 520);
+          while (atomicCAS(lock, 0, 1) != 0) __nanosleep(40);
+        }
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
@@ -261,6 +271,7 @@ __global__ void __launch_bounds__(NWG * 128, MINB) k_conv_wg(const __grid_consta
           }
         }
         ptx::mma_commit(bar_mma + 8u * (uint32_t)q);
+        if (p.mma_lock) atomicExch(reinterpret_cast<int*>(smem + 520), 0);
       }
       __syncwarp();
     }
@@ -378,6 +389,9 @@ static int launch_m(const fn_conv_desc& d, int* status, cudaStream_t stream) {
   p.s_u = stride % p.tiles_u;
   p.s_v = (stride / p.tiles_u) % p.tiles_v;
   p.s_b = stride / (p.tiles_u * p.tiles_v);
+  // the burst lock pays under contention (batch 64: -3 ... -13 % per launch); with at most a tile or two per warpgroup (batch 8)
+  // its two atomics per burst only add latency (+3 % on the whole forward)
+  p.mma_lock = g_mma_lock && p.ntiles >= 3 * stride;
   launch_pdl(kern, dim3(grid), dim3(NWG * 128), (size_t)CF::SMEM, stream, p);
   count_launch();
   return check_launch("k_conv_wg");
@@ -450,4 +464,5 @@ extern "C" {
 // where it measured faster, 2 wherever it has an instantiation
 void fn_debug_set_wg(int v) { fn::wg::g_enable = v < 0 ? 0 : v > 2 ? 2 : v; }
 void fn_debug_set_wg_j16(int v) { fn::wg::g_j16 = v == 2 ? 2 : 1; }
+void fn_debug_set_wg_lock(int v) { fn::wg::g_mma_lock = v != 0; }
 }

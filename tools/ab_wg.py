@@ -20,11 +20,12 @@ for (H, W, C, gate, skip) in CASES:
     w_tc = native.pack_conv_weights_tc(w16, ws16, 3, 2 * C, 2 * C if skip else 0, N, gate)
     y = torch.empty((B, H, W, C), device="cuda", dtype=torch.bfloat16)
     out = {}
-    for name, wgon, j16 in (("s1p", 0, 1), ("wg", 2, 1), ("wg_j16=2", 2, 2)):
+    for name, wgon, j16, lock in (("s1p", 0, 1, 1), ("wg", 2, 1, 1), ("wg, MMA bursts unserialised", 2, 1, 0), ("wg_j16=2", 2, 2, 1)):
         if j16 == 2 and C != 16:
             continue
         native.lib.fn_debug_set_wg(wgon)
         native.lib.fn_debug_set_wg_j16(j16)
+        native.lib.fn_debug_set_wg_lock(lock)
         def run():
             native.conv_fwd(x, w16, bias, y, B=B, H=H, W=W, Cin=C, Cout=N, ksize=3, stride=1, prologue=1,
                             epilogue=1 if gate else 0, impl=native.IMPL_TCGEN05, w_tc=w_tc, res=res, skip=sk, w_skip=ws16)
@@ -40,5 +41,6 @@ for (H, W, C, gate, skip) in CASES:
         out[name] = e0.elapsed_time(e1) / 20 * 1000
     native.lib.fn_debug_set_wg(1)
     native.lib.fn_debug_set_wg_j16(1)
+    native.lib.fn_debug_set_wg_lock(1)
     assert native.tc_status() == 0
     print("B=%d %dx%d C=%d gate=%d skip=%d  " % (B, H, W, C, gate, skip) + "  ".join("%s %.1f us" % kv for kv in out.items()), flush=True)
