@@ -273,8 +273,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level3
     }
 
     if constexpr (MODE == MODE_DOWN) {
-      // ---- the shortcut of the first stage, front channel pad (reference :158-163): output channels 16.. take the 2x2
-      // average pool of x2; fetched with the operand (global loads during a stage's MMAs would delay the weight ring)
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before_sync();
+      worker_barrier();
+      stamp();
+
+      // ---- stage 2: conv_2 of the down block, gate, pooled shortcut in the last 16 channels
+      if (warp < 2) {
+        ptx::tc_fence_after_sync();
+        issue_conv(N64{}, G2);
+      }
+      // ---- the shortcut of this stage, front channel pad (reference :158-163): output channels 16.. take the 2x2 average pool
+      // of x2.  Fetched while the stage's MMAs run: 16 scattered 16-byte loads per thread cost 8 k clocks of L1 tag time, which
+      // the 15 k clocks of MMAs hide -- at this level the weight ring (74 KB per stage, prefetched four chunks deep) is not
+      // the critical resource the same loads disturbed in conv_l4.cu
       float pool[2][2][8];
       {
         const __nv_bfloat16* x2b = p.aux + (size_t)b * LH2 * LW2 * C2;
@@ -297,16 +309,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level3
               pool[tr][g][i] = 0.25f * (__bfloat162float(q4[g][0].h[i]) + __bfloat162float(q4[g][1].h[i]) + __bfloat162float(q4[g][2].h[i]) +
                                         __bfloat162float(q4[g][3].h[i]));
         }
-      }
-      ptx::fence_proxy_async_smem();
-      ptx::tc_fence_before_sync();
-      worker_barrier();
-      stamp();
-
-      // ---- stage 2: conv_2 of the down block, gate, pooled shortcut in the last 16 channels
-      if (warp < 2) {
-        ptx::tc_fence_after_sync();
-        issue_conv(N64{}, G2);
       }
       stage_done();
       stamp();

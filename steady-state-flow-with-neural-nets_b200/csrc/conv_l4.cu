@@ -185,7 +185,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
       ptx::mbar_init(bar(SB_TF), 2);
       ptx::mbar_init(bar(SB_XR), 1);
       ptx::mbar_init(bar(SB_XW), NWORK);
-      if (MODE == MODE_ALL) l5c::init_barriers(bar(BAR5));
+      if (MODE == MODE_ALL) l5c::init_barriers(bar(BAR5), NWORK);
       ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -610,7 +610,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_level4
     if constexpr (MODE == MODE_ALL) {
       peer_planes_free();               // consumes the peer's arrival for stage 4, so that XR's phase matches the UP stages' count
       next_half(load_biases5);
-      if (warp < 8) l5c::workers<2, true>(c5, ok);
+      l5c::workers<2, true, NWORK>(c5, ok);
       next_half(load_biases_up);
     }
     if constexpr (MODE != MODE_DOWN) {

@@ -16,11 +16,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
   const int tid = threadIdx.x;
   const uint32_t rank = cluster_rank();
 
-  if (warp == 8) {
+  if (warp == NWORK) {
     ptx::tmem_alloc(sbase + 256, 256u);
     ptx::tmem_relinquish();
     if (lane == 0) {
-      init_barriers(sbase);
+      init_barriers(sbase, NWORK);
       ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -39,14 +39,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS) k_level5c(c
   c.nstamp = 0;
   if (c.stamps) c.stamps[c.nstamp++] = clock64();
 
-  if (warp == 8) producer(c, ok);
-  else workers<1, false>(c, ok);
+  if (warp == NWORK) producer(c, ok);
+  else workers<1, false, NWORK>(c, ok);
 
   if (c.stamps) c.stamps[c.nstamp++] = clock64();
   // ---- neither CTA may leave while the other can still write into it or arrive on its barriers
   ptx::tc_fence_before_sync();
   cluster_sync_all();
-  if (warp == 8) {
+  if (warp == NWORK) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, 256u);
   }

@@ -27,7 +27,8 @@ namespace fn {
 using namespace tma;
 namespace l5c {
 
-constexpr int THREADS = 288;
+constexpr int NWORK = 16;                      // worker warps of the stand-alone kernel (the stages take 8 or 16)
+constexpr int THREADS = NWORK * 32 + 32;
 constexpr int NST = 2, CHUNK = 32768;
 constexpr int HDR = 4096;                      // [0,64) mbarriers, [256] TMEM base, [512, 512 + 416*4) biases
 constexpr int C4 = 64, C5 = 128, IH = 16, IW = 32;
@@ -65,8 +66,8 @@ struct Params {
   int B;
 };
 
-template <int ID>
-__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync %0, 256;" ::"n"(ID) : "memory"); }
+template <int ID, int NT>
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NT) : "memory"); }
 // the input of the level: read-only for the whole launch (ld.global.nc), or written earlier in the SAME launch by this
 // cluster (the merged levels-4+5 kernel): then through L2 (ld.global.cg), after a cluster barrier
 template <bool COHERENT>
@@ -149,7 +150,7 @@ struct Ctx {
   int nstamp;
 };
 
-__device__ __forceinline__ void init_barriers(uint32_t bar0) {        // one thread
+__device__ __forceinline__ void init_barriers(uint32_t bar0, int nworkers) {        // one thread; nworkers: worker warps
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   for (int s = 0; s < NST; ++s) {
     ptx::mbar_init(bar(SB_FULL + s), 1);
@@ -157,7 +158,7 @@ __device__ __forceinline__ void init_barriers(uint32_t bar0) {        // one thr
   }
   ptx::mbar_init(bar(SB_TF), 1);
   ptx::mbar_init(bar(SB_XR), 1);
-  ptx::mbar_init(bar(SB_XW), 8);
+  ptx::mbar_init(bar(SB_XW), (uint32_t)nworkers);
 }
 // NBIAS floats of this rank into shared memory, the v halves of the gated convs pre-halved: sigmoid(z) = 0.5 + 0.5 tanh(z / 2)
 __device__ __forceinline__ void load_biases(float* sbias, const float* bias, uint32_t rank, int tid, int nthreads) {
@@ -199,8 +200,9 @@ __device__ __forceinline__ void producer(Ctx& c, bool& ok) {
   __syncwarp();
 }
 
-// warps 0..7: operand build, MMA issue (warp 0), epilogues.  BARID: the named barrier of these 256 threads.
-template <int BARID, bool COHERENT>
+// warps 0..NW-1 (NW = 8 or 16): operand build, MMA issue (warp 0), epilogues -- warp w owns TMEM lane quadrant w & 3 and the
+// (w >> 2)-th part of this CTA's output channels.  BARID: the named barrier of these NW * 32 threads.
+template <int BARID, bool COHERENT, int NW>
 __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
   const uint32_t sbase = c.sbase, sb = c.sb, tmem_base = c.tmem_base, rank = c.rank, peer = c.rank ^ 1u;
   const int warp = c.warp, lane = c.lane, tid = c.tid, b = c.b;
@@ -209,7 +211,9 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
   auto stamp = [&]() { if (c.stamps) c.stamps[c.nstamp++] = clock64(); };
   // =========================== workers ===========================
   const uint32_t leader = ptx::elect_one();
-  const int q = warp & 3, half = warp >> 2;
+  constexpr int WT = NW * 32, NG = 32 / NW, NG5 = 16 / NW;      // worker threads; 8-channel groups per thread (stages 1-4 / stage 5)
+  static_assert(NW == 8 || NW == 16, "8 or 16 worker warps");
+  const int q = warp & 3, part = warp >> 2;
   const int r = q * 32 + lane;                      // accumulator row == TMEM lane
   const int py = r & 7, px = r >> 3;                // pixel (y, x) of the 8 x 16 image
   const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -235,7 +239,7 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
     if (!ok) atomicCAS(p.status, 0, 73);
     tf_par ^= 1u;
     ptx::tc_fence_after_sync();
-    if (readers_first) worker_barrier<BARID>();
+    if (readers_first) worker_barrier<BARID, WT>();
     if (tid == 0) mbar_arrive_remote(xr_peer);
   };
   // before the first remote write of an epilogue: the peer's MMAs no longer read its planes
@@ -250,7 +254,7 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
     ptx::tc_fence_before_sync();
     __syncwarp();
     if (lane == 0) mbar_arrive_remote(xw_peer);
-    worker_barrier<BARID>();
+    worker_barrier<BARID, WT>();
     ok = ok && mbar_wait_cluster(bar(SB_XW), x_par);
     if (!ok) atomicCAS(p.status, 0, 75);
     fence_proxy_async_all();            // the peer's generic-proxy writes, acquired above, before this CTA's tensor-core reads
@@ -267,11 +271,11 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
     const __nv_bfloat16* xb = p.x + (size_t)b * IH * IW * C4;
     constexpr int ITEMS = (IH + 1) * (IW + 1) * 8;
     constexpr int UN = 9;                 // loads in flight per thread (two rounds)
-    for (int base = tid; base < ITEMS; base += 256 * UN) {
+    for (int base = tid; base < ITEMS; base += WT * UN) {
       uint4 in[UN];
 #pragma unroll
       for (int k = 0; k < UN; ++k) {
-        const int idx = base + 256 * k;
+        const int idx = base + WT * k;
         const int ch = idx & 7, sp = idx >> 3;
         const int h = sp / (IW + 1), w = sp - h * (IW + 1);
         in[k] = make_uint4(0u, 0u, 0u, 0u);
@@ -279,7 +283,7 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
       }
 #pragma unroll
       for (int k = 0; k < UN; ++k) {
-        const int idx = base + 256 * k;
+        const int idx = base + WT * k;
         if (idx >= ITEMS) break;
         const int ch = idx & 7, sp = idx >> 3;
         const int h = sp / (IW + 1), w = sp - h * (IW + 1);
@@ -293,7 +297,7 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
   }
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before_sync();
-  worker_barrier<BARID>();
+  worker_barrier<BARID, WT>();
   stamp();
 
   // ---- stage 1 MMAs: stride-2 conv, K = 9 x 128, this CTA's N = 64; a 32 KB chunk = 16 k-steps = two taps
@@ -326,12 +330,12 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
   // four input pixels of output pixel (px, py) are entry [px][py] of the four parity sub-planes and x is exactly
   // recoverable from [elu(x) | elu(-x)], so the pool comes from shared memory while stage 1's MMAs read the same planes
   // (the scattered global loads it replaces cost the stage-2 epilogue 6 k clocks)
-  float pool[4][8];
+  float pool[NG][8];
   if (rank == 1) {
     const uint32_t e0 = A + (uint32_t)(px * PU1 + py) * 16u;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int pl = half * 4 + g;
+    for (int g = 0; g < NG; ++g) {
+      const int pl = part * NG + g;
 #pragma unroll
       for (int i = 0; i < 8; ++i) pool[g][i] = 0.f;
 #pragma unroll
@@ -355,8 +359,8 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
   // ---- epilogue of a plain conv (this CTA's 64 channels): acc + bias -> bf16 -> [elu | elu(-.)] planes, both CTAs
   auto epilogue_plain = [&](int boff) {
 #pragma unroll 1
-    for (int g = 0; g < 4; ++g) {
-      const int cl = half * 32 + g * 8;                 // local channel
+    for (int g = 0; g < NG; ++g) {
+      const int cl = part * (8 * NG) + g * 8;                 // local channel
       const int cg = (int)rank * CL + cl;               // channel of the full tensor
       float o[8], bv[8];
       lds_f8(sb + 4u * (uint32_t)(boff + cl), bv);
@@ -372,7 +376,7 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
   };
   // the zero border of the stage-2..5 planes (the region held stage 1's sub-planes until now); local only: the peer
   // zeroes its own, and remote writes touch interior pixels only
-  for (int idx = tid; idx < P * 32; idx += 256) {
+  for (int idx = tid; idx < P * 32; idx += WT) {
     const int pl = idx / P, pp = idx - pl * P;
     const int pv = pp / PU, pu = pp - pv * PU;
     if (pu == 0 || pu == PU - 1 || pv == 0 || pv == PV - 1) sts128(A + (uint32_t)(pl * PPAD + pp) * 16u, make_uint4(0u, 0u, 0u, 0u));
@@ -416,8 +420,8 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
   peer_planes_free();
   {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int cl = half * 32 + g * 8;
+    for (int g = 0; g < NG; ++g) {
+      const int cl = part * (8 * NG) + g * 8;
       const int cg = (int)rank * CL + cl;
       float a[8], gt[8], bu[8], bv[8], o[8];
       lds_f8(sb + 4u * (uint32_t)(B2 + cl), bu);
@@ -460,8 +464,8 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
   stamp();
   peer_planes_free();
 #pragma unroll 1
-  for (int g = 0; g < 4; ++g) {
-    const int cl = half * 32 + g * 8;
+  for (int g = 0; g < NG; ++g) {
+    const int cl = part * (8 * NG) + g * 8;
     const int cg = (int)rank * CL + cl;
     float a[8], gt[8], bu[8], bv[8], o[8];
     lds_f8(sb + 4u * (uint32_t)(B4 + cl), bu);
@@ -519,8 +523,8 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
       const int oy = 2 * py + (ph >> 1), ox = 2 * px + (ph & 1);
       __nv_bfloat16* dst = yb + ((size_t)oy * IW + ox) * C4;
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int cl = half * 16 + g * 8;               // 0..31
+      for (int g = 0; g < NG5; ++g) {
+        const int cl = part * (8 * NG5) + g * 8;        // 0..31
         const int cg = (int)rank * 32 + cl;             // output channel of up_conv_1
         float o[8], bv[8];
         lds_f8(sb + 4u * (uint32_t)(B5 + cl), bv);
