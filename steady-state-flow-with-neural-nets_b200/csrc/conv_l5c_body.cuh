@@ -29,7 +29,7 @@ namespace l5c {
 
 constexpr int NWORK = 16;                      // worker warps of the stand-alone kernel (the stages take 8 or 16)
 constexpr int THREADS = NWORK * 32 + 32;
-constexpr int NST = 2, CHUNK = 32768;
+constexpr int NST = 2, CHUNK = 32768;     // ring: two 32-KB slots during stage 1, THREE from stage 2 on (see Ring below)
 constexpr int HDR = 4096;                      // [0,64) mbarriers, [256] TMEM base, [512, 512 + 416*4) biases
 constexpr int C4 = 64, C5 = 128, IH = 16, IW = 32;
 constexpr int CL = C5 / 2;                     // channels of a stage-1..4 output this CTA computes
@@ -52,7 +52,23 @@ constexpr long long WTOTAL = (long long)W1 + W2 + W3 + W4 + W5;
 __host__ __device__ constexpr int chunks_of(int bytes) { return (bytes + CHUNK - 1) / CHUNK; }
 constexpr int G1 = 0, G2 = G1 + chunks_of(W1), G3 = G2 + chunks_of(W2), G4 = G3 + chunks_of(W3), G5 = G4 + chunks_of(W4);
 
-enum { SB_FULL = 0, SB_EMPTY = 2, SB_TF = 4, SB_XR = 5, SB_XW = 6 };
+enum { SB_FULL = 0, SB_EMPTY = 2, SB_TF = 4, SB_XR = 5, SB_XW = 6, SB_FULL2 = 7, SB_EMPTY2 = 8 };
+
+// Ring.  An N = 128 stage consumes 4 KB of weights per 64-clock MMA; one 32-KB slot takes ~1000 clocks to refill (round trip
+// measured by tools/ring_bench.cu), so with two slots -- one in flight while the other is multiplied -- the stage ran at
+// ~100 clocks per MMA.  Stage 1's parity sub-planes fill the shared memory; once its MMAs are done, 45 KB behind the
+// stride-1 planes are free and become a third slot: chunk gc of the stream lives in slot ring_slot(gc), which it is the
+// ring_fill(gc)-th chunk to occupy (slot 2's "zeroth occupant" are the sub-planes: its EMPTY barrier gets an arrival once
+// stage 1's MMAs are complete and every warp has read its shortcut from them).
+constexpr int OFF_SLOT2 = OFF_A + PLANES_BYTES + 128 * 128;
+static_assert(OFF_SLOT2 + CHUNK <= SMEM && (OFF_SLOT2 % 128) == 0, "third ring slot");
+__host__ __device__ constexpr int ring_slot(int gc) { return gc < G2 ? (gc & 1) : ((gc - G2) % 3 == 0 ? 1 : ((gc - G2) % 3 == 1 ? 2 : 0)); }
+__host__ __device__ constexpr int ring_fill(int gc) {        // 0-based count of this slot's earlier chunks
+  return gc < G2 ? (gc >> 1) : (gc - G2) / 3 + (ring_slot(gc) == 0 ? (G2 + 1) / 2 : ring_slot(gc) == 1 ? G2 / 2 : 0);
+}
+__host__ __device__ constexpr int ring_offset(int slot) { return slot < 2 ? OFF_RING + slot * CHUNK : OFF_SLOT2; }
+__host__ __device__ constexpr int ring_full(int slot) { return slot < 2 ? SB_FULL + slot : SB_FULL2; }
+__host__ __device__ constexpr int ring_empty(int slot) { return slot < 2 ? SB_EMPTY + slot : SB_EMPTY2; }
 
 struct Params {
   const __nv_bfloat16* x;       // [B,16,32,64]
@@ -152,9 +168,9 @@ struct Ctx {
 
 __device__ __forceinline__ void init_barriers(uint32_t bar0, int nworkers) {        // one thread; nworkers: worker warps
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  for (int s = 0; s < NST; ++s) {
-    ptx::mbar_init(bar(SB_FULL + s), 1);
-    ptx::mbar_init(bar(SB_EMPTY + s), 1);
+  for (int s = 0; s < 3; ++s) {
+    ptx::mbar_init(bar(ring_full(s)), 1);
+    ptx::mbar_init(bar(ring_empty(s)), 1);
   }
   ptx::mbar_init(bar(SB_TF), 1);
   ptx::mbar_init(bar(SB_XR), 1);
@@ -185,13 +201,13 @@ __device__ __forceinline__ void producer(Ctx& c, bool& ok) {
     for (int st = 0; st < 5 && ok; ++st) {
       for (int rem = stage_bytes[st]; rem > 0 && ok; ++gc) {
         const int bytes = rem < CHUNK ? rem : CHUNK;
-        const int s = gc % NST;
-        if (gc >= NST) {
-          ok = ptx::mbar_wait(bar(SB_EMPTY + s), (uint32_t)(((gc / NST) - 1) & 1));
+        const int s = ring_slot(gc), f = ring_fill(gc);
+        if (f >= 1 || s == 2) {       // the slot's previous occupant has been multiplied (slot 2: stage 1's sub-planes are dead)
+          ok = ptx::mbar_wait(bar(ring_empty(s)), (uint32_t)((s == 2 ? f : f - 1) & 1));
           if (!ok) { atomicCAS(p.status, 0, 71); break; }
         }
-        ptx::mbar_arrive_expect_tx(bar(SB_FULL + s), (uint32_t)bytes);
-        ptx::bulk_g2s_hint(sbase + OFF_RING + s * CHUNK, ws + off, (uint32_t)bytes, bar(SB_FULL + s), pol);
+        ptx::mbar_arrive_expect_tx(bar(ring_full(s)), (uint32_t)bytes);
+        ptx::bulk_g2s_hint(sbase + ring_offset(s), ws + off, (uint32_t)bytes, bar(ring_full(s)), pol);
         off += (size_t)bytes;
         rem -= bytes;
       }
@@ -225,11 +241,11 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
   uint32_t tf_par = 0, x_par = 0;
 
   auto chunk_ready = [&](int gc, uint32_t lbo) -> uint64_t {
-    const int s = gc % NST;
-    ok = ok && ptx::mbar_wait(bar(SB_FULL + s), (uint32_t)((gc / NST) & 1));
+    const int s = ring_slot(gc);
+    ok = ok && ptx::mbar_wait(bar(ring_full(s)), (uint32_t)(ring_fill(gc) & 1));
     if (!ok) atomicCAS(p.status, 0, 72);
     ptx::tc_fence_after_sync();
-    return ptx::smem_desc(sbase + OFF_RING + s * CHUNK, lbo, 128);
+    return ptx::smem_desc(sbase + ring_offset(s), lbo, 128);
   };
   // everybody: this stage's accumulators are complete; the peer learns that this CTA's planes may be overwritten
   // readers_first: other warps read the operand planes during this stage's MMAs (the shortcut recovered from them), so
@@ -239,7 +255,12 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
     if (!ok) atomicCAS(p.status, 0, 73);
     tf_par ^= 1u;
     ptx::tc_fence_after_sync();
-    if (readers_first) worker_barrier<BARID, WT>();
+    if (readers_first) {
+      worker_barrier<BARID, WT>();
+      // stage 1 only: its sub-planes are dead now (MMAs complete, every warp has taken its shortcut from them) -- the memory
+      // behind the stride-1 planes becomes the ring's third slot
+      if (tid == 0) ptx::mbar_arrive(bar(SB_EMPTY2));
+    }
     if (tid == 0) mbar_arrive_remote(xr_peer);
   };
   // before the first remote write of an epilogue: the peer's MMAs no longer read its planes
@@ -321,7 +342,7 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
           }
         }
       }
-      if (leader) ptx::mma_commit(bar(SB_EMPTY + (G1 + c) % NST));
+      if (leader) ptx::mma_commit(bar(ring_empty(ring_slot(G1 + c))));
     }
     if (leader) ptx::mma_commit(bar(SB_TF));
     __syncwarp();
@@ -405,7 +426,7 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
         if (leader) ptx::mma_bf16_ss(tmem_base, a_tap + (uint32_t)((i * 2 * PPAD * 16) >> 4), b_chunk + (uint32_t)((i * N * 32) >> 4), idesc,
                                      (c | i) ? 1u : 0u);
       }
-      if (leader) ptx::mma_commit(bar(SB_EMPTY + (g0 + c) % NST));
+      if (leader) ptx::mma_commit(bar(ring_empty(ring_slot(g0 + c))));
     }
     if (leader) ptx::mma_commit(bar(SB_TF));
     __syncwarp();
@@ -509,7 +530,7 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
           }
         }
       }
-      if (leader) ptx::mma_commit(bar(SB_EMPTY + (G5 + c) % NST));
+      if (leader) ptx::mma_commit(bar(ring_empty(ring_slot(G5 + c))));
     }
     if (leader) ptx::mma_commit(bar(SB_TF));
     __syncwarp();
