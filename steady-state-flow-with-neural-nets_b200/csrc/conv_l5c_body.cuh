@@ -172,7 +172,7 @@ __device__ __forceinline__ void init_barriers(uint32_t bar0, int nworkers) {    
     ptx::mbar_init(bar(ring_full(s)), 1);
     ptx::mbar_init(bar(ring_empty(s)), 1);
   }
-  ptx::mbar_init(bar(SB_TF), 1);
+  ptx::mbar_init(bar(SB_TF), 2);        // warps 0 and 1 both commit a stage (see the K split below)
   ptx::mbar_init(bar(SB_XR), 1);
   ptx::mbar_init(bar(SB_XW), (uint32_t)nworkers);
 }
@@ -321,13 +321,19 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
   worker_barrier<BARID, WT>();
   stamp();
 
+  // K split: ONE thread needs ~53 clocks per tcgen05.mma plus ~270 per ring chunk (wait, commit, loop) -- 82 clocks per N = 128 MMA
+  // that executes in 64 (and 67 per N = 64 MMA that executes in 48).  An image is a single M = 128 tile here, so the split
+  // is over K: warp 0 issues the even ring chunks of a stage into accumulator 0, warp 1 the odd ones into accumulator 1
+  // (TMEM columns 128..), each chunk still consumed and released by exactly one of them; the epilogues add the two.
+  const uint32_t acc_mine = tmem_base + (uint32_t)(warp & 1) * 128u;       // issuing warps only
+
   // ---- stage 1 MMAs: stride-2 conv, K = 9 x 128, this CTA's N = 64; a 32 KB chunk = 16 k-steps = two taps
-  if (warp == 0) {
+  if (warp < 2) {
     ptx::tc_fence_after_sync();
     constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, 64);
     const uint64_t a_tmpl = ptx::smem_desc(A, P1 * 16, PU1 * 16);
 #pragma unroll 1
-    for (int c = 0; c < chunks_of(W1); ++c) {
+    for (int c = warp; c < chunks_of(W1); c += 2) {
       const uint64_t b_chunk = chunk_ready(G1 + c, 64 * 16);
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
@@ -337,8 +343,8 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
           const uint64_t a_tap = a_tmpl + (uint64_t)((uint32_t)(((di & 1) * 2 + (dj & 1)) * SUB1_BYTES + ((dj >> 1) * PU1 + (di >> 1)) * 16) >> 4);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
-            if (leader) ptx::mma_bf16_ss(tmem_base, a_tap + (uint32_t)((kk * 2 * P1 * 16) >> 4),
-                                         b_chunk + (uint32_t)(((h2 * 8 + kk) * 64 * 32) >> 4), idesc, (tap | kk) ? 1u : 0u);
+            if (leader) ptx::mma_bf16_ss(acc_mine, a_tap + (uint32_t)((kk * 2 * P1 * 16) >> 4),
+                                         b_chunk + (uint32_t)(((h2 * 8 + kk) * 64 * 32) >> 4), idesc, (c >= 2 || h2 || kk) ? 1u : 0u);
           }
         }
       }
@@ -385,7 +391,12 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
       const int cg = (int)rank * CL + cl;               // channel of the full tensor
       float o[8], bv[8];
       lds_f8(sb + 4u * (uint32_t)(boff + cl), bv);
-      ptx::tmem_ld8(lane_base + (uint32_t)cl, o);
+      {
+        float o2[8];
+        ptx::tmem_ld8x2(lane_base + (uint32_t)cl, lane_base + (uint32_t)(128 + cl), o, o2);       // the two K halves
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += o2[i];
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] += bv[i];
       uint4 o0, o1;
@@ -416,15 +427,15 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
     ptx::tc_fence_after_sync();
     const uint64_t a_tmpl = ptx::smem_desc(A, PPAD * 16, PU * 16);
 #pragma unroll 1
-    for (int c = 0; c < 144 / SPC; ++c) {
+    for (int c = warp; c < 144 / SPC; c += 2) {
       const uint64_t b_chunk = chunk_ready(g0 + c, N * 16);
       const int tap = c / CPT, kk0 = (c - tap * CPT) * SPC;
       const int di = tap / 3, dj = tap - 3 * di;
       const uint64_t a_tap = a_tmpl + (uint64_t)((uint32_t)((dj * PU + di) * 16 + kk0 * 2 * PPAD * 16) >> 4);
 #pragma unroll
       for (int i = 0; i < SPC; ++i) {
-        if (leader) ptx::mma_bf16_ss(tmem_base, a_tap + (uint32_t)((i * 2 * PPAD * 16) >> 4), b_chunk + (uint32_t)((i * N * 32) >> 4), idesc,
-                                     (c | i) ? 1u : 0u);
+        if (leader) ptx::mma_bf16_ss(acc_mine, a_tap + (uint32_t)((i * 2 * PPAD * 16) >> 4), b_chunk + (uint32_t)((i * N * 32) >> 4), idesc,
+                                     (c >= 2 || i) ? 1u : 0u);
       }
       if (leader) ptx::mma_commit(bar(ring_empty(ring_slot(g0 + c))));
     }
@@ -435,7 +446,7 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
   using N128 = std::integral_constant<int, 128>;
 
   // ---- stage 2: conv_2 of the down block, gate, shortcut = 2x2 average pool of x4 in the LAST 64 channels (= rank 1's)
-  if (warp == 0) issue_s1(N128{}, G2);
+  if (warp < 2) issue_s1(N128{}, G2);
   stage_done();
   stamp();
   peer_planes_free();
@@ -448,6 +459,12 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
       lds_f8(sb + 4u * (uint32_t)(B2 + cl), bu);
       lds_f8(sb + 4u * (uint32_t)(B2 + CL + cl), bv);
       ptx::tmem_ld8x2(lane_base + (uint32_t)cl, lane_base + (uint32_t)(CL + cl), a, gt);
+      {
+        float a2[8], gt2[8];
+        ptx::tmem_ld8x2(lane_base + (uint32_t)(128 + cl), lane_base + (uint32_t)(128 + CL + cl), a2, gt2);      // the second K half
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i] += a2[i]; gt[i] += gt2[i]; }
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float th = tanh_approx(fmaf(gt[i], 0.5f, bv[i]));
@@ -470,7 +487,7 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
   stamp();
 
   // ---- stage 3: conv_1 of resnet_5_0
-  if (warp == 0) issue_s1(N64{}, G3);
+  if (warp < 2) issue_s1(N64{}, G3);
   stage_done();
   stamp();
   peer_planes_free();
@@ -480,7 +497,7 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
 
   // ---- stage 4: conv_2 of resnet_5_0, gate, shortcut = the block input kept in shared memory; the result feeds the
   // transposed conv RAW (no nonlinearity, reference :213): 16 planes
-  if (warp == 0) issue_s1(N128{}, G4);
+  if (warp < 2) issue_s1(N128{}, G4);
   stage_done();
   stamp();
   peer_planes_free();
@@ -492,6 +509,12 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
     lds_f8(sb + 4u * (uint32_t)(B4 + cl), bu);
     lds_f8(sb + 4u * (uint32_t)(B4 + CL + cl), bv);
     ptx::tmem_ld8x2(lane_base + (uint32_t)cl, lane_base + (uint32_t)(CL + cl), a, gt);
+    {
+      float a2[8], gt2[8];
+      ptx::tmem_ld8x2(lane_base + (uint32_t)(128 + cl), lane_base + (uint32_t)(128 + CL + cl), a2, gt2);        // the second K half
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a[i] += a2[i]; gt[i] += gt2[i]; }
+    }
     bf16x8 rv;
     rv.v = lds128(r1_row + (uint32_t)(((cl >> 3) ^ (r & 7)) * 16));
 #pragma unroll
@@ -532,6 +555,10 @@ __device__ __forceinline__ void workers(Ctx& c, bool& ok) {
       }
       if (leader) ptx::mma_commit(bar(ring_empty(ring_slot(G5 + c))));
     }
+    if (leader) ptx::mma_commit(bar(SB_TF));
+    __syncwarp();
+  }
+  if (warp == 1) {               // the stage barrier counts both issuing warps; this stage is small enough for one
     if (leader) ptx::mma_commit(bar(SB_TF));
     __syncwarp();
   }

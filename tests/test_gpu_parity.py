@@ -585,7 +585,9 @@ def test_level5_fused_kernel_vs_layer_by_layer_and_oracle(native, B, split, monk
     torch.cuda.synchronize()
     assert native.tc_status() == 0
     assert tuple(y.shape) == (B, 16, 32, 64)
-    assert rel_l2(y, y_ref) < 1e-3
+    # the cluster kernel sums every convolution's K range in two fp32 accumulators (one per issuing warp): a different summation
+    # order than the per-layer kernels', i.e. a few bf16 roundings that flip and propagate through five layers
+    assert rel_l2(y, y_ref) < (2e-3 if split else 1e-3)
     if B <= 5:
         vs = fo.VariableStore(77, torch.float64)
         # same creation order as the device graph above -> same variables
@@ -735,7 +737,9 @@ def test_net_with_and_without_the_fused_level5_kernel(native):
         y0 = _net(native, x, "auto")
     finally:
         arch.LEVEL5_FUSED = True
-    assert rel_l2(y1, y0) < 2e-3
+    # two bf16 pipelines with different fp32 summation orders in twelve convolutions (the fused level-4 / level-5 kernels split K
+    # over two accumulators), each ~3.5e-3 from the fp64 oracle (test_net_vs_golden_*): they differ by bf16 roundings that flip
+    assert rel_l2(y1, y0) < 4e-3
 
 
 @pytest.mark.parametrize("flags", [dict(), dict(nr_res_blocks=2, filter_size=16)], ids=["default", "deeper_wider"])
