@@ -26,7 +26,7 @@
 namespace fn {
 using namespace tma;
 namespace wg {
-static int g_mma_lock = 1;
+static int g_mma_lock = 40;      // 0: off; else the back-off (ns) of a warp waiting for its CTA's MMA-burst lock
 
 constexpr int HDR = 2048;     // [0,512) mbarriers, [512] TMEM base, [1024, 2048) bias (<= 256 floats)
 
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(NWG * 128, MINB) k_conv_wg(const __grid_consta
         // (two CTAs per SM keep the unit fed) a program completes in ~0.5 k once it starts, and its epilogue with it
         if (p.mma_lock) {
           int* lock = reinterpret_cast<int*>(smem + 520);
-          while (atomicCAS(lock, 0, 1) != 0) __nanosleep(40);
+          while (atomicCAS(lock, 0, 1) != 0) __nanosleep((unsigned)p.mma_lock);
         }
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
@@ -391,7 +391,7 @@ static int launch_m(const fn_conv_desc& d, int* status, cudaStream_t stream) {
   p.s_b = stride / (p.tiles_u * p.tiles_v);
   // the burst lock pays under contention (batch 64: -3 ... -13 % per launch); with at most a tile or two per warpgroup (batch 8)
   // its two atomics per burst only add latency (+3 % on the whole forward)
-  p.mma_lock = g_mma_lock && p.ntiles >= 3 * stride;
+  p.mma_lock = p.ntiles >= 3 * stride ? g_mma_lock : 0;
   launch_pdl(kern, dim3(grid), dim3(NWG * 128), (size_t)CF::SMEM, stream, p);
   count_launch();
   return check_launch("k_conv_wg");
@@ -464,5 +464,5 @@ extern "C" {
 // where it measured faster, 2 wherever it has an instantiation
 void fn_debug_set_wg(int v) { fn::wg::g_enable = v < 0 ? 0 : v > 2 ? 2 : v; }
 void fn_debug_set_wg_j16(int v) { fn::wg::g_j16 = v == 2 ? 2 : 1; }
-void fn_debug_set_wg_lock(int v) { fn::wg::g_mma_lock = v != 0; }
+void fn_debug_set_wg_lock(int v) { fn::wg::g_mma_lock = v < 0 ? 0 : v; }
 }

@@ -20,7 +20,8 @@ for (H, W, C, gate, skip) in CASES:
     w_tc = native.pack_conv_weights_tc(w16, ws16, 3, 2 * C, 2 * C if skip else 0, N, gate)
     y = torch.empty((B, H, W, C), device="cuda", dtype=torch.bfloat16)
     out = {}
-    for name, wgon, j16, lock in (("s1p", 0, 1, 1), ("wg", 2, 1, 1), ("wg, MMA bursts unserialised", 2, 1, 0), ("wg_j16=2", 2, 2, 1)):
+    for name, wgon, j16, lock in (("s1p", 0, 1, 40), ("wg", 2, 1, 40), ("wg, MMA bursts unserialised", 2, 1, 0), ("wg back-off 1 ns", 2, 1, 1),
+                                  ("wg back-off 20 ns", 2, 1, 20), ("wg back-off 100 ns", 2, 1, 100), ("wg_j16=2", 2, 2, 40)):
         if j16 == 2 and C != 16:
             continue
         native.lib.fn_debug_set_wg(wgon)
@@ -41,6 +42,6 @@ for (H, W, C, gate, skip) in CASES:
         out[name] = e0.elapsed_time(e1) / 20 * 1000
     native.lib.fn_debug_set_wg(1)
     native.lib.fn_debug_set_wg_j16(1)
-    native.lib.fn_debug_set_wg_lock(1)
+    native.lib.fn_debug_set_wg_lock(40)
     assert native.tc_status() == 0
     print("B=%d %dx%d C=%d gate=%d skip=%d  " % (B, H, W, C, gate, skip) + "  ".join("%s %.1f us" % kv for kv in out.items()), flush=True)
