@@ -449,7 +449,11 @@ bool conv_wg_try(const fn_conv_desc& d, cudaStream_t stream, bool dry_run, int& 
     }                                                                                    \
     return true;                                                                         \
   }
-  WG_CASE(0, 2, true, false, 4, 2) WG_CASE(0, 2, false, false, 4, 2) WG_CASE(0, 2, false, true, 3, 2)
+  // warpgroups per CTA x CTAs per SM, measured at batch 64 (round 2, with the MMA-burst lock): the 8-channel level wants more
+  // resident warpgroups than registers comfortably allow -- gate 4x2 42.4 us, 3x3 38.5 (53 registers, 32 bytes of spill),
+  // 3x4 46.6, 2x5 51.8, 5x2 46.3; plain 4x2 38.4, 3x3 35.7, 3x4 33.4; with the skip operand 3x2 43.0, 2x3 41.3.  The
+  // 16-channel level stays at 4x2 (gate 22.7 us against 24.0 for 3x3).
+  WG_CASE(0, 2, true, false, 3, 3) WG_CASE(0, 2, false, false, 3, 4) WG_CASE(0, 2, false, true, 2, 3)
   WG_CASE(1, 1, true, false, 4, 2) WG_CASE(1, 1, false, false, 4, 2) WG_CASE(1, 1, false, true, 3, 2)
   WG_CASE(1, 2, true, false, 4, 1) WG_CASE(1, 2, false, false, 4, 1) WG_CASE(1, 2, false, true, 3, 1)
   WG_CASE(2, 1, false, false, 4, 1) WG_CASE(2, 1, false, true, 3, 1)
