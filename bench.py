@@ -198,7 +198,7 @@ def run_train(args, rank, world, dist, native, arch, flow_net, steps=None):
     """BASELINE configs[2]: training step (L2 loss, fwd+bwd+Adam), global batch 256 synthetic 128x256,
     batch-sharded with one NCCL all-reduce of the flat fp32 gradient.  keep_prob = 1.0 (the parity setting) unless
     --keep-prob.  Returns the record (rank 0) or None."""
-    global_batch = 256
+    global_batch = args.train_batch
     steps = steps or args.steps
     B = global_batch // world
     arch.reset_variables(1234)
@@ -276,6 +276,8 @@ def main():
     ap.add_argument("--mode", default="inference", choices=["inference", "train"],
                     help="train: only BASELINE configs[2] (fwd+bwd+Adam at global batch 256); the default run carries it as the `train` sub-record")
     ap.add_argument("--no-train", action="store_true", help="skip the `train` sub-record of the default run")
+    ap.add_argument("--train-batch", type=int, default=256,
+                    help="global batch of the training step (configs[2]: 256; 32 on one GPU = the per-GPU load of an 8-GPU run)")
     ap.add_argument("--train-steps", type=int, default=10, help="timed steps of the `train` sub-record")
     ap.add_argument("--keep-prob", type=float, default=1.0,
                     help="train mode: dropout keep probability (1.0 = the parity setting; the reference trains with 0.7)")

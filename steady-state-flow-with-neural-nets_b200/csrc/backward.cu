@@ -339,30 +339,44 @@ __global__ void k_tanh_l2_bwd(const float* __restrict__ p, const float* __restri
   }
 }
 
-// ---- deterministic second stage: out[i] = sum_s partial[s][i]
-// block = 32 outputs x 8 split lanes: lane y adds partials y, y+8, .. (4 loads in flight), then the 8 lane sums are
-// added in a fixed order -- the result does not depend on the launch geometry of stage 1 beyond S itself.
-__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ partial, float* __restrict__ out, long long n, int S) {
-  __shared__ float sm[8][33];
+// ---- deterministic second stage: out[i] = sum_s partial[s][i], for one or two (partial, out) pairs in one launch (a
+// conv's weight and bias gradients).  block = 32 outputs x TY split lanes: lane y adds partials y, y+TY, .. with four
+// independent loads in flight, then the TY lane sums are added in a fixed order -- the result depends on S and TY
+// only, not on the launch geometry of stage 1.  TY = 32 for small jobs (a lone block walking 592 partials eight lanes
+// wide took 15 us: 18 dependent round trips to memory), TY = 8 for the large ones.
+struct ReduceJob {
+  const float* partial;
+  float* out;
+  long long n;
+  int S;
+};
+template <int TY>
+__global__ void __launch_bounds__(32 * TY) k_reduce_partials(ReduceJob j0, ReduceJob j1, unsigned nb0) {
+  __shared__ float sm[TY][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const long long i = (long long)blockIdx.x * 32 + tx;
+  const bool second = blockIdx.x >= nb0;
+  const float* __restrict__ partial = second ? j1.partial : j0.partial;
+  float* __restrict__ out = second ? j1.out : j0.out;
+  const long long n = second ? j1.n : j0.n;
+  const int S = second ? j1.S : j0.S;
+  const long long i = (long long)(blockIdx.x - (second ? nb0 : 0u)) * 32 + tx;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (i < n) {
     int k = ty;
-    for (; k + 24 < S; k += 32) {
+    for (; k + 3 * TY < S; k += 4 * TY) {
       a0 += partial[(long long)k * n + i];
-      a1 += partial[(long long)(k + 8) * n + i];
-      a2 += partial[(long long)(k + 16) * n + i];
-      a3 += partial[(long long)(k + 24) * n + i];
+      a1 += partial[(long long)(k + TY) * n + i];
+      a2 += partial[(long long)(k + 2 * TY) * n + i];
+      a3 += partial[(long long)(k + 3 * TY) * n + i];
     }
-    for (; k < S; k += 8) a0 += partial[(long long)k * n + i];
+    for (; k < S; k += TY) a0 += partial[(long long)k * n + i];
   }
   sm[ty][tx] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (ty == 0 && i < n) {
     float s = 0.f;
 #pragma unroll
-    for (int y = 0; y < 8; ++y) s += sm[y][tx];
+    for (int y = 0; y < TY; ++y) s += sm[y][tx];
     out[i] = s;
   }
 }
@@ -531,8 +545,14 @@ __global__ void __launch_bounds__(256) k_wgrad_cin1(const __nv_bfloat16* __restr
   }
 }
 
-static int reduce_partials(const float* partial, float* out, long long n, int S, cudaStream_t s) {
-  k_reduce_partials<<<(unsigned)((n + 31) / 32), 256, 0, s>>>(partial, out, n, S);
+static int reduce_partials(const float* partial, float* out, long long n, int S, cudaStream_t s, const float* partial2 = nullptr,
+                           float* out2 = nullptr, long long n2 = 0, int S2 = 0) {
+  const ReduceJob j0{partial, out, n, S}, j1{partial2, out2, partial2 ? n2 : 0, S2};
+  const unsigned nb0 = (unsigned)((n + 31) / 32), nb1 = (unsigned)((j1.n + 31) / 32);
+  if (nb0 + nb1 <= 592 && (S > 32 || S2 > 32))
+    k_reduce_partials<32><<<nb0 + nb1, 1024, 0, s>>>(j0, j1, nb0);
+  else
+    k_reduce_partials<8><<<nb0 + nb1, 256, 0, s>>>(j0, j1, nb0);
   count_launch();
   return check_launch("k_reduce_partials");
 }
@@ -740,10 +760,11 @@ static int conv_wgrad_impl(const fn_conv_desc* d, const void* dY, float* dW, flo
                      d->dropout_seed, &S, (cudaStream_t)stream, rc, db != nullptr, &bias_partial,
                      (const unsigned long long*)d->dropout_seed_dev)) {
       if (rc) return rc;
-      rc = reduce_partials(workspace, dW, (long long)d->ksize * d->ksize * d->Cin * pro_mult(d->prologue) * d->Cout, S,
-                           (cudaStream_t)stream);
+      const long long nw = (long long)d->ksize * d->ksize * d->Cin * pro_mult(d->prologue) * d->Cout;
+      if (db && bias_partial)        // both second stages in one launch
+        return reduce_partials(workspace, dW, nw, S, (cudaStream_t)stream, bias_partial, db, d->Cout, S);
+      rc = reduce_partials(workspace, dW, nw, S, (cudaStream_t)stream);
       if (rc || !db) return rc;
-      if (bias_partial) return reduce_partials(bias_partial, db, d->Cout, S, (cudaStream_t)stream);
       return bias_grad(dY, db, workspace, (long long)d->B * OH * OW, d->Cout, (cudaStream_t)stream);
     }
     FN_REQUIRE(d->impl != FN_IMPL_TCGEN05, FN_E_UNSUPPORTED, "fn_conv_wgrad: no tcgen05 kernel for this shape");

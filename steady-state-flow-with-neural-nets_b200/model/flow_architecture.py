@@ -125,9 +125,52 @@ class _VariableStore:
     def derived(self, key, make):
         ent = self._derived.get(key)
         if ent is None:
-            ent = make()
+            ent = weight_prep(make)
             self._derived[key] = ent
         return ent
+
+
+# ---- weight preparation on a side stream of the training graphs
+# The bf16 / tensor-core images of the variables depend on nothing but the variables, yet traced in place they sit
+# between the convs as ~120 dependent 3-us launches per training step (ncu launch list, profiles/r2_launches_train.csv).
+# While a training graph is being captured they are issued on a side stream forked at the graph's start: in the graph
+# they form a chain of their own that runs ahead of (and beside) the conv chain; each consumer waits only for its image.
+_PREP = {"stream": None, "keep": None}
+
+
+def weight_prep(make):
+    """Run make() (casts, packs: anything that reads variables only) on the capture's side stream when there is one."""
+    side = _PREP["stream"]
+    if side is None:
+        return make()
+    with torch.cuda.stream(side):
+        ent = make()
+        ev = torch.cuda.Event()
+        ev.record(side)
+    torch.cuda.current_stream().wait_event(ev)
+    # the side stream's allocator must not hand these blocks to a later image while a conv on the main chain reads them
+    _PREP["keep"].append(ent)
+    return ent
+
+
+class prep_stream:
+    """with prep_stream(keep): ... inside a torch.cuda.graph capture -- forks the weight-preparation stream at entry and
+    joins it at exit; `keep` (a list owned by the graph's holder) receives every tensor made on it."""
+
+    def __init__(self, keep):
+        self.keep = keep
+
+    def __enter__(self):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        _PREP["stream"], _PREP["keep"] = side, self.keep
+        return self
+
+    def __exit__(self, *exc):
+        side = _PREP["stream"]
+        _PREP["stream"] = _PREP["keep"] = None
+        torch.cuda.current_stream().wait_stream(side)
+        return False
 
 
 def xavier_limit(shape):

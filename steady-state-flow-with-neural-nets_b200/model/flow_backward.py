@@ -74,7 +74,8 @@ class _BwdWeights:
     def tc(self):
         if self.K % 16 and self.K != 8:
             return None
-        return native.pack_conv_weights_tc_f32(self.src, self.ksize, self.K, self.N, self.flip, self.transpose)
+        return arch.weight_prep(
+            lambda: native.pack_conv_weights_tc_f32(self.src, self.ksize, self.K, self.N, self.flip, self.transpose))
 
     def w16(self):
         T = self.ksize * self.ksize
@@ -84,6 +85,15 @@ class _BwdWeights:
         if self.transpose:
             w = w.permute(0, 2, 1)
         return w.to(torch.bfloat16).contiguous()
+
+
+def _pad_channels(w, axis, n):
+    """the fp32 variable w zero-padded to n entries along `axis` (the 2-channel tail / 1-channel head run as 8-channel launches)"""
+    shape = list(w.shape)
+    shape[axis] = n
+    out = torch.zeros(shape, dtype=torch.float32, device=w.device)
+    out.narrow(axis, 0, w.shape[axis]).copy_(w)
+    return out
 
 
 def _dgrad_weights_s1(w, ksize):
@@ -203,6 +213,30 @@ class BackwardPass:
         self.grads = _Grads()
         self.loss, self.dpre = native.tanh_l2_bwd(sflow_p, sflow.to(torch.float32))
         self.d_input = None
+        # parameter gradients on a stream of their own (flow_net.CompiledTraining sets it while capturing): nothing in the
+        # pass reads them, so in the graph the weight / bias gradient launches leave the data-gradient chain -- at small
+        # per-GPU batches, where every launch is latency, the step then costs its critical path only
+        self.wstream = None
+        self._wkeep = []
+
+    def _param_grad(self, fn, *operands):
+        """run fn (weight / bias gradient launches; they share native's reduction workspace, so all of them go here) on
+        the parameter-gradient stream, ordered after everything issued so far"""
+        W = self.wstream
+        if W is None:
+            fn()
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        W.wait_event(ev)
+        with torch.cuda.stream(W):
+            fn()
+        self._wkeep.extend(operands)          # allocated on the main stream, read on W: not to be recycled before the join
+
+    def join(self):
+        """the pieces run so far are complete on the current stream once this returns (call at the end of every run slice)"""
+        if self.wstream is not None:
+            torch.cuda.current_stream().wait_stream(self.wstream)
 
     def run(self, records):
         V = arch.VARIABLES.vars
@@ -212,13 +246,14 @@ class BackwardPass:
         def wgrad_into(name, x, dY, ksize, stride, pro, keep_prob=1.0, seed=0, bias=False):
             """weight gradient (and, with bias=True, the bias gradient of the same dY in the same launch)"""
             if params:
-                native.conv_wgrad(x, dY, flat.grad_view(name + '/weights').view(ksize * ksize, -1, dY.shape[-1]), ksize=ksize,
-                                  stride=stride, prologue=pro, keep_prob=keep_prob, dropout_seed=seed,
-                                  db=flat.grad_view(name + '/biases') if bias else None)
+                self._param_grad(lambda: native.conv_wgrad(
+                    x, dY, flat.grad_view(name + '/weights').view(ksize * ksize, -1, dY.shape[-1]), ksize=ksize, stride=stride,
+                    prologue=pro, keep_prob=keep_prob, dropout_seed=seed, db=flat.grad_view(name + '/biases') if bias else None),
+                    x, dY)
 
         def bgrad_into(name, dY):
             if params:
-                native.bias_grad(dY, flat.grad_view(name + '/biases'))
+                self._param_grad(lambda: native.bias_grad(dY, flat.grad_view(name + '/biases')), dY)
 
         for rec in reversed(records):
             kind = rec["kind"]
@@ -227,15 +262,16 @@ class BackwardPass:
                 cin = x.shape[3]
                 # weights: [3,3,cin,2]; gradients run as 8-channel launches (dpre channels 2..7 are zero)
                 if params:
-                    tmp = torch.empty((9, cin, 8), dtype=torch.float32, device=dev)
-                    native.conv_wgrad(x, dpre, tmp, ksize=3, stride=1, prologue=native.PRO_NONE)
-                    flat.grad_view('last_conv_conv/weights').copy_(tmp[:, :, :2].reshape(3, 3, cin, 2))
-                    tmpb = torch.empty(8, dtype=torch.float32, device=dev)
-                    native.bias_grad(dpre, tmpb)
-                    flat.grad_view('last_conv_conv/biases').copy_(tmpb[:2])
+                    def last_grads():
+                        tmp = torch.empty((9, cin, 8), dtype=torch.float32, device=dev)
+                        native.conv_wgrad(x, dpre, tmp, ksize=3, stride=1, prologue=native.PRO_NONE)
+                        flat.grad_view('last_conv_conv/weights').copy_(tmp[:, :, :2].reshape(3, 3, cin, 2))
+                        tmpb = torch.empty(8, dtype=torch.float32, device=dev)
+                        native.bias_grad(dpre, tmpb)
+                        flat.grad_view('last_conv_conv/biases').copy_(tmpb[:2])
+                    self._param_grad(last_grads, x, dpre)
                 w = V['last_conv_conv/weights']
-                w8 = torch.zeros((3, 3, cin, 8), dtype=torch.float32, device=dev)
-                w8[..., :2] = w
+                w8 = arch.weight_prep(lambda: _pad_channels(w, 3, 8))      # reads the variable only: side stream of a capture
                 buf, acc = grads.target(x)
                 assert not acc
                 _conv_plain(dpre, _dgrad_weights_s1(w8, 3), cin, 3, 1, dev, out=buf)
@@ -244,7 +280,7 @@ class BackwardPass:
                 g = grads.get(y)
                 cin, cout = x.shape[3], y.shape[3]
                 if params:
-                    native.tconv_wgrad(x, g, flat.grad_view(scope + '/weights').view(9, cout, cin))
+                    self._param_grad(lambda: native.tconv_wgrad(x, g, flat.grad_view(scope + '/weights').view(9, cout, cin)), x, g)
                 bgrad_into(scope, g)
                 # d(x) = stride-2 'SAME' conv of d(y) with the same weights read as HWIO [k,k,Cout,Cin]
                 buf, acc = grads.target(x)
@@ -279,13 +315,14 @@ class BackwardPass:
                 wgrad_into(s1, x, dx_1, 3, stride, pro1, bias=True)
                 if a is not None:
                     sn = name + '_nin_fc'
-                    if params:
-                        flat.grad_view(sn + '/biases').copy_(flat.grad_view(s1 + '/biases'))
+                    if params:      # behind conv_1's bias gradient, i.e. on its stream
+                        self._param_grad(lambda: flat.grad_view(sn + '/biases').copy_(flat.grad_view(s1 + '/biases')))
                     # the skip is zero-padded bottom/right to x_1's size: only the overlapping window contributes
                     if a.shape[1] != dx_1.shape[1] or a.shape[2] != dx_1.shape[2]:
                         raise ValueError("training with a spatially padded skip (H, W not multiples of 16) is not built")
                     if params:
-                        native.conv_wgrad(a, dx_1, flat.grad_view(sn + '/weights').view(1, -1, F_), ksize=1, stride=1, prologue=pro)
+                        self._param_grad(lambda: native.conv_wgrad(a, dx_1, flat.grad_view(sn + '/weights').view(1, -1, F_), ksize=1,
+                                                                   stride=1, prologue=pro), a, dx_1)
                     wn = V[sn + '/weights']                                   # [mult*Ca, F]
                     buf, acc = grads.target(a)
                     if mult == 2 and F_ in (8, 16, 32, 64) and wn.numel() * 4 <= 64 * 1024 and wn.is_contiguous():
@@ -308,8 +345,7 @@ class BackwardPass:
                     # the network input (1 channel, no prologue): conv adjoint with the output padded to 8 channels, plus
                     # the shortcut's front-padded identity (channel F-1 of g)
                     w1 = V[s1 + '/weights']                                   # [3,3,1,F]
-                    w8 = torch.zeros((3, 3, 8, F_), dtype=torch.float32, device=dev)
-                    w8[:, :, :1, :] = w1
+                    w8 = arch.weight_prep(lambda: _pad_channels(w1, 2, 8))
                     dA1 = _conv_plain(dx_1, _dgrad_weights_s1(w8, 3), 8, 3, 1, dev)
                     self.d_input = d_input = dA1[..., :1].contiguous()
                     native.shortcut_bwd(g, tuple(x.shape), pooled, out=d_input, accumulate=True)

@@ -8,6 +8,9 @@ CPU or PyTorch fallback.
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import numpy as np
 import torch
 
@@ -241,6 +244,8 @@ class CompiledTraining:
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device="cuda") if keep_prob < 1.0 else None
         self.static_boundary = torch.zeros((batch_size, shape[0], shape[1], 1), dtype=in_dtype, device="cuda")
         self.static_sflow = torch.zeros((batch_size, shape[0], shape[1], 2), dtype=torch.float32, device="cuda")
+        self._side_streams = os.environ.get("FLOWNET_TRAIN_STREAMS", "1") != "0"
+        self._wstream = torch.cuda.Stream()
         begin_training()
         # warm-up: creates the variables, the flat buffers, the workspace and the allocator pool; gradients only (no
         # Adam), so the parameters are exactly what they were
@@ -256,13 +261,19 @@ class CompiledTraining:
         self.graph = torch.cuda.CUDAGraph()              # part A
         self.graph_b = None
         n0 = native.launch_count()
+        # inside the graphs: the weight images on one side stream (flow_architecture.prep_stream), the parameter gradients
+        # on another (flow_backward.BackwardPass.wstream) -- the main chain is forward + data gradients only
+        self._prep_keep = []
+        prep = flow_architecture.prep_stream if self._side_streams else (lambda keep: contextlib.nullcontext())
         with torch.cuda.graph(self.graph):
-            self._part_a()
+            with prep(self._prep_keep):
+                self._part_a()
         self.loss = self._pass.loss
         if self._cut is not None:
             self.graph_b = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_b, pool=self.graph.pool()):
-                self._part_b()
+                with prep(self._prep_keep):
+                    self._part_b()
         self.launches_per_replay = native.launch_count() - n0
         self.bucket_offset = self._cut[1] if self._cut is not None else 0
         self._pass = None
@@ -282,7 +293,10 @@ class CompiledTraining:
             self._cut = None if k is None else (k, off)
             self._tape = tape
             self._pass = self.fb.BackwardPass(sflow_p, self.static_sflow, flat)
+            if self._side_streams and torch.cuda.is_current_stream_capturing():
+                self._pass.wstream = self._wstream
             self._pass.run(tape if k is None else tape[k:])
+            self._pass.join()
         finally:
             native.DROPOUT_SEED_DEV = None
 
@@ -292,6 +306,7 @@ class CompiledTraining:
         native.DROPOUT_SEED_DEV = self.seed_dev
         try:
             self._pass.run(self._tape[:self._cut[0]])
+            self._pass.join()
         finally:
             native.DROPOUT_SEED_DEV = None
 

@@ -1637,6 +1637,41 @@ def test_compiled_training_step_matches_eager(native):
         arch.reset_variables(1234)
 
 
+def test_compiled_training_side_streams_change_nothing(native, monkeypatch):
+    """The captured step issues the weight images and the parameter gradients on side streams of the graph
+    (flow_architecture.prep_stream, BackwardPass.wstream).  At the full 128x256 size -- the persistent wgrad / dgrad kernels,
+    several tiles per CTA -- the parameters after three steps must equal, bit for bit, those of the same graph captured
+    on one stream (FLOWNET_TRAIN_STREAMS=0): a missing dependency or a recycled buffer would show."""
+    import model.flow_architecture as arch
+    import model.flow_net as flow_net
+
+    def run(streams):
+        monkeypatch.setenv("FLOWNET_TRAIN_STREAMS", streams)
+        arch.reset_variables(1234)
+        flow_net.reset_training_state()
+        ct = flow_net.CompiledTraining(4, (128, 256))
+        for k in range(3):
+            b, s = flow_net.inputs(4, shape=(128, 256), seed=300 + k)
+            ct.step(b, s, 1e-3)
+        torch.cuda.synchronize()
+        assert native.tc_status() == 0
+        out = {k: v.clone() for k, v in arch.global_variables().items()}
+        flow_net.end_training()
+        flow_net.reset_training_state()
+        return out
+
+    try:
+        want = run("0")
+        for rep in range(2):
+            got = run("1")
+            for k in want:
+                assert torch.equal(got[k], want[k]), (rep, k)
+    finally:
+        flow_net.end_training()
+        flow_net.reset_training_state()
+        arch.reset_variables(1234)
+
+
 def test_compiled_training_with_dropout_draws_a_new_mask_per_replay(native):
     """keep_prob < 1 inside the captured step: the device-resident seed counter changes the mask on every replay (same
     inputs, different gradients), and the same counter value reproduces the same gradients."""
