@@ -299,6 +299,8 @@ def main():
     import torch.distributed as dist
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries the one JSON line: NCCL's own log (its version banner when NCCL_DEBUG is set in the environment) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # the serving loop's pinned buffers should live on the GPU's NUMA node (utils/numa.py); FLOWNET_NUMA=0: leave unpinned
     from utils.numa import bind_to_gpu_numa_node
