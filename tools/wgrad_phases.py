@@ -27,7 +27,7 @@ shapes = {"L1 c8 n16": (128, 128, 256, 8, 16, 3, 1, 1), "L2 c16 n32": (128, 64, 
           "L4 c64 n128": (256, 16, 32, 64, 128, 3, 1, 1), "L5 c128 n256": (256, 8, 16, 128, 256, 3, 1, 1)}
 for name, sh in shapes.items():
     row = []
-    for flags in (0, 128, 2, 4, 8, 16, 2 | 16, 4 | 8, 2 | 4 | 8 | 16):
+    for flags in [int(f) for f in os.environ.get('WGRAD_FLAGS', '0,128,2,4,8,16,18,12,30').split(',')]:
         t, st = run(*sh, flags)
         row.append("%d:%.0fus" % (flags, t))
     print(name, " ".join(row), flush=True)
