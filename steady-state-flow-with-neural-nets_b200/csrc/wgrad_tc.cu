@@ -67,6 +67,13 @@ struct Params {
   int ksize, swap, m64;
   int nt;               // accumulators per CTA
   int a3;               // 1: three column-shifted copies of every plane, the 3 taps of a filter row share one MMA
+  int n3;               // a3 and: the three filter ROWS share the MMA too -- the dY tile lands as [row][chunk][x][8] (one tensor copy), so
+                        // the chunks of consecutive rows are equidistant and one B descriptor (chunk stride = one x-extent) reads the
+                        // N = 3 * nchunks * 8 columns of dY rows r-2, r-1, r against activation row r: nine taps per instruction,
+                        // TV + 2 instructions per K-step column instead of 3 TV (the first / last two activation rows pair with 1 / 2 rows)
+  int n3_cols;          // accumulator columns of that MMA; the bias accumulator follows
+  uint32_t idesc_rows[3];   // instruction descriptors for 1 / 2 / 3 dY rows
+  uint32_t idesc_bias;
   float keep_prob;
   unsigned long long seed;
   const unsigned long long* seed_dev;
@@ -193,6 +200,7 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
     __syncwarp();
   }
   const bool do_bias = p.bias_partial != nullptr && grp == 0;
+  const uint32_t n3_rp = (uint32_t)(p.nchunks * TU * 16);        // n3: bytes of one dY row (all chunks)
   if (tid < 16) sts128(sbase + OFF_ONES + (uint32_t)tid * 16u, make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u));
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before_sync();
@@ -220,8 +228,11 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
           else tma_load_4d(st, &p.tm_x, bar(SB_X + s), 0, x0 - 1, y0 - 1, b);
         }
         const uint32_t dy = sbase + p.off_dy + (uint32_t)s * p.dy_bytes;
-        if (!skip_dy)
-          for (int c = 0; c < p.nchunks; ++c) tma_load_5d(dy + (uint32_t)(c * DY_PLANE), &p.tm_dy, bar(SB_X + s), 0, c, x0, y0, b);
+        if (!skip_dy) {
+          if (p.n3) tma_load_5d(dy, &p.tm_dy, bar(SB_X + s), 0, x0, 0, y0, b);     // (8, x, chunk, y, b): one request per tile
+          else
+            for (int c = 0; c < p.nchunks; ++c) tma_load_5d(dy + (uint32_t)(c * DY_PLANE), &p.tm_dy, bar(SB_X + s), 0, c, x0, y0, b);
+        }
       }
     }
     __syncwarp();
@@ -251,6 +262,39 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
       ptx::tc_fence_after_sync();
       const uint64_t a_tmpl = ptx::smem_desc(sbase + p.off_a + (uint32_t)s * p.a_bytes, lbo_a, sbo_a);
       const uint64_t b_tmpl = ptx::smem_desc(sbase + p.off_dy + (uint32_t)s * p.dy_bytes, lbo_b, sbo_b);
+      if (p.n3) {
+        // activation row r (image row y0 - 1 + r) pairs with the dY tile rows r-2 .. r (filter rows 2 .. 0) that exist; column
+        // block j of the accumulator = filter row 2 - j.  The full rows come first so that the very first instruction
+        // initialises all columns.
+        const uint64_t b3 = ptx::smem_desc(sbase + p.off_dy + (uint32_t)s * p.dy_bytes, swp ? (uint32_t)(TU * 16) : 128u,
+                                           swp ? 128u : (uint32_t)(TU * 16));
+        const uint32_t blk = (uint32_t)(p.nchunks * 8);
+#pragma unroll
+        for (int rr = 0; rr < TV + 2; ++rr) {
+          const int r = rr < TV - 2 ? rr + 2 : (rr < TV ? rr - (TV - 2) : rr);       // 2 .. TV-1, 0, 1, TV, TV+1
+          const int lo = r < 2 ? 2 - r : 0, hi = r > TV - 1 ? TV + 1 - r : 2;        // block range [lo, hi]
+          const int t0 = r + lo - 2;                                                 // first dY tile row
+#pragma unroll
+          for (int ub = 0; ub < G::KSU; ++ub)
+            if (do_mma)
+              ptx::mma_bf16_ss(tmem_base + (uint32_t)lo * blk, a_tmpl + (uint32_t)((r * G::ROW_BYTES + ub * 256) >> 4),
+                               b3 + (uint32_t)(((uint32_t)t0 * n3_rp + (uint32_t)ub * 256u) >> 4), p.idesc_rows[hi - lo],
+                               (it == 0 && rr == 0 && ub == 0) ? 0u : 1u);
+        }
+        if (do_bias) {
+          const uint64_t ones = ptx::smem_desc(sbase + OFF_ONES, 128u, 0u);
+#pragma unroll
+          for (int v = 0; v < TV; ++v)
+#pragma unroll
+            for (int ub = 0; ub < G::KSU; ++ub)
+              if (do_mma)
+                ptx::mma_bf16_ss(tmem_base + (uint32_t)p.n3_cols, ones, b3 + (uint32_t)(((uint32_t)v * n3_rp + (uint32_t)ub * 256u) >> 4),
+                                 p.idesc_bias, (it == 0 && v == 0 && ub == 0) ? 0u : 1u);
+        }
+        if (leader) ptx::mma_commit(bar(SB_TF + s));
+        __syncwarp();
+        continue;
+      }
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         if (t >= ntaps) break;
@@ -323,10 +367,11 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
       krow = row_local - du_row * kpl * 8;
     }
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int bias_col = p.n3 ? p.n3_cols : NT * p.Npad;
     if (do_bias && warp == 0) {          // accumulator row 0 = TMEM lane 0 for M = 128 and M = 64 alike
       for (int n0 = 0; n0 < p.N; n0 += 8) {
         float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (n_local > 0) ptx::tmem_ld8(tmem_base + (uint32_t)(NT * p.Npad + n0), o);
+        if (n_local > 0) ptx::tmem_ld8(tmem_base + (uint32_t)(bias_col + n0), o);
         if (lane == 0 && ok) {
           float* dst = p.bias_partial + (size_t)s_idx * p.N + n0;
           *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
@@ -334,6 +379,21 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
         }
       }
     }
+    if (p.n3) {
+      // column block j (dY rows r-2+j) holds filter row 2 - j
+      for (int j = 0; j < 3; ++j) {
+        const int tap = 3 * (2 - j) + du_row;
+        float* dst = p.partial + (((size_t)s_idx * p.T + tap) * p.Keff + krow) * p.N;
+        for (int n0 = 0; n0 < p.N; n0 += 8) {
+          float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (n_local > 0) ptx::tmem_ld8(lane_base + (uint32_t)(j * p.nchunks * 8 + n0), o);
+          if (du_row < 3 && krow < p.Keff && ok) {
+            *reinterpret_cast<float4*>(dst + n0) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(dst + n0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int t = 0; t < ntaps; ++t) {
       const int tap = p.a3 ? 3 * t + du_row : tap0 + t;
@@ -346,6 +406,7 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
           *reinterpret_cast<float4*>(dst + n0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
         }
       }
+    }
     }
   }
 
@@ -407,6 +468,16 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
   p.nt = pl.NT;
   pl.bias_fits = (pl.NT + 1) * p.Npad <= 512;             // room for the bias accumulator next to the tap accumulators
   int cols = (pl.NT + (pl.bias_fits ? 1 : 0)) * p.Npad;
+  // nine taps per MMA (see Params::n3): flag 1024 keeps the three-accumulator form (A/B, tools/wgrad_phases.py)
+  p.n3_cols = 3 * p.nchunks * 8;
+  {
+    const bool m64_later = p.Keff <= 16 && !(g_swap & 32);         // M = 64 takes N % 8 == 0, M = 128 needs N % 16 == 0 per row count
+    p.n3 = (p.a3 && p.n3_cols <= 256 && (m64_later || (p.nchunks & 1) == 0) && !(g_swap & 1024)) ? 1 : 0;
+  }
+  if (p.n3) {
+    pl.bias_fits = true;
+    cols = p.n3_cols + p.Npad;
+  }
   p.tmem_cols = 32;
   while ((int)p.tmem_cols < cols) p.tmem_cols *= 2;
   // narrow stride-1 layers on wide images: 8 x 32 tiles halve the per-tile hand-shakes, which is what those launches
@@ -462,6 +533,8 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
   // (M = 64, N % 8 == 0) when the CTA's channel block is at most 64 wide.  Flag 32 forces M = 128 (experiments).
   p.m64 = ((p.a3 ? 3 : 1) * p.kpl <= 8 && !(g_swap & 32)) ? 1 : 0;
   p.idesc = idesc_mn(p.m64 ? 64 : 128, p.Npad);
+  for (int c = 1; c <= 3; ++c) p.idesc_rows[c - 1] = idesc_mn(p.m64 ? 64 : 128, c * p.nchunks * 8);
+  p.idesc_bias = p.idesc;
   return true;
 }
 
@@ -513,9 +586,14 @@ bool wgrad_tc_try(const void* x, const void* dY, float* partial, int B, int H, i
       return false;
   }
   {
-    const cuuint64_t dims[5] = {8, (cuuint64_t)(N / 8), (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)B};
-    const cuuint64_t strides[4] = {16, (cuuint64_t)N * 2, (cuuint64_t)OW * N * 2, (cuuint64_t)OH * OW * N * 2};
-    const cuuint32_t box[5] = {8, 1, (cuuint32_t)pl.tu, (cuuint32_t)TV, 1};
+    cuuint64_t dims[5] = {8, (cuuint64_t)(N / 8), (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)B};
+    cuuint64_t strides[4] = {16, (cuuint64_t)N * 2, (cuuint64_t)OW * N * 2, (cuuint64_t)OH * OW * N * 2};
+    cuuint32_t box[5] = {8, 1, (cuuint32_t)pl.tu, (cuuint32_t)TV, 1};
+    if (p.n3) {      // x before the chunk: the box lands as [row][chunk][x][8]
+      dims[1] = (cuuint64_t)OW; dims[2] = (cuuint64_t)(N / 8);
+      strides[0] = (cuuint64_t)N * 2; strides[1] = 16;
+      box[1] = (cuuint32_t)pl.tu; box[2] = (cuuint32_t)(N / 8);
+    }
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     if (enc(&p.tm_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dY), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
