@@ -12,6 +12,11 @@
 // consecutive pixels of one tile row, and a filter tap is once more only a start-address offset into
 // the haloed activation planes (stride 2: parity sub-planes, as in conv_s2t.cu).
 //
+// Narrow stride-1 3x3 layers (Keff <= 32) fold the nine taps into ONE instruction per 16 pixels: the three filter
+// columns as three column-shifted copies of the activation planes stacked along M (a3), the three filter rows as the
+// dY rows r-2, r-1, r stacked along N -- the dY tile is loaded as [row][chunk][x][8], which makes the chunks of
+// consecutive rows equidistant, so one B descriptor spans them (n3).
+//
 // Persistent CTAs: CTA (g, s) owns one group g of taps / one 128-channel block of K and every S-th
 // pixel tile; its accumulators stay in TMEM for the whole kernel and are written once, as an fp32
 // partial `[s][tap][k][n]`; a second kernel adds the S partials in a fixed order (deterministic).
