@@ -154,7 +154,9 @@ __device__ __forceinline__ void transform_tile(const Params& p, uint32_t stage, 
   }
 }
 
-template <int MODE, int TU = 16>
+// N3: the nine-taps-per-instruction form, a kernel of its own so that the other shapes' code is what it was (folded into one
+// kernel behind a run-time flag the M = 64 launches of the other shapes ran 15-50 % slower: the issue loop is what bounds them)
+template <int MODE, int TU = 16, bool N3 = false>
 __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Params p) {
   using G = Geo<MODE, TU>;
   constexpr int DY_PLANE = G::DY_PLANE;
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
         }
         const uint32_t dy = sbase + p.off_dy + (uint32_t)s * p.dy_bytes;
         if (!skip_dy) {
-          if (p.n3) tma_load_5d(dy, &p.tm_dy, bar(SB_X + s), 0, x0, 0, y0, b);     // (8, x, chunk, y, b): one request per tile
+          if (N3) tma_load_5d(dy, &p.tm_dy, bar(SB_X + s), 0, x0, 0, y0, b);     // (8, x, chunk, y, b): one request per tile
           else
             for (int c = 0; c < p.nchunks; ++c) tma_load_5d(dy + (uint32_t)(c * DY_PLANE), &p.tm_dy, bar(SB_X + s), 0, c, x0, y0, b);
         }
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
       ptx::tc_fence_after_sync();
       const uint64_t a_tmpl = ptx::smem_desc(sbase + p.off_a + (uint32_t)s * p.a_bytes, lbo_a, sbo_a);
       const uint64_t b_tmpl = ptx::smem_desc(sbase + p.off_dy + (uint32_t)s * p.dy_bytes, lbo_b, sbo_b);
-      if (p.n3) {
+      if (N3) {
         // activation row r (image row y0 - 1 + r) pairs with the dY tile rows r-2 .. r (filter rows 2 .. 0) that exist; column
         // block j of the accumulator = filter row 2 - j.  The full rows come first so that the very first instruction
         // initialises all columns.
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
       krow = row_local - du_row * kpl * 8;
     }
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const int bias_col = p.n3 ? p.n3_cols : NT * p.Npad;
+    const int bias_col = N3 ? p.n3_cols : NT * p.Npad;
     if (do_bias && warp == 0) {          // accumulator row 0 = TMEM lane 0 for M = 128 and M = 64 alike
       for (int n0 = 0; n0 < p.N; n0 += 8) {
         float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
         }
       }
     }
-    if (p.n3) {
+    if (N3) {
       // column block j (dY rows r-2+j) holds filter row 2 - j
       for (int j = 0; j < 3; ++j) {
         const int tap = 3 * (2 - j) + du_row;
@@ -543,9 +545,9 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
   return true;
 }
 
-template <int MODE, int TU = 16>
+template <int MODE, int TU = 16, bool N3 = false>
 static int launch_k(const Plan& pl, cudaStream_t stream) {
-  auto kern = k_wgrad_tc<MODE, TU>;
+  auto kern = k_wgrad_tc<MODE, TU, N3>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
@@ -613,7 +615,8 @@ bool wgrad_tc_try(const void* x, const void* dY, float* partial, int B, int H, i
   p.status = tc_status_word();
   if (!p.status) { rc = (int)cudaErrorMemoryAllocation; return true; }
   *S_out = pl.S;
-  if (pl.mode == MODE_S1 && pl.tu == 32) rc = launch_k<MODE_S1, 32>(pl, stream);
+  if (p.n3) rc = pl.tu == 32 ? launch_k<MODE_S1, 32, true>(pl, stream) : launch_k<MODE_S1, 16, true>(pl, stream);
+  else if (pl.mode == MODE_S1 && pl.tu == 32) rc = launch_k<MODE_S1, 32>(pl, stream);
   else if (pl.mode == MODE_S1) rc = launch_k<MODE_S1>(pl, stream);
   else rc = launch_k<MODE_S2>(pl, stream);
   return true;

@@ -24,6 +24,8 @@ def run(B, H, W, C, N, k, s, pro, flags):
     return e0.elapsed_time(e1) / 5 * 1000, native.tc_status()
 
 shapes = {"L1 c8 n16": (128, 128, 256, 8, 16, 3, 1, 1), "L2 c16 n32": (128, 64, 128, 16, 32, 3, 1, 1),
+          "L3 c32 n64": (256, 32, 64, 32, 64, 3, 1, 1), "L3 c32 n32": (256, 32, 64, 32, 32, 3, 1, 1),
+          "S2 c8 n16": (256, 128, 256, 8, 16, 3, 2, 1), "S2 c16 n32": (256, 64, 128, 16, 32, 3, 2, 1),
           "L4 c64 n128": (256, 16, 32, 64, 128, 3, 1, 1), "L5 c128 n256": (256, 8, 16, 128, 256, 3, 1, 1)}
 for name, sh in shapes.items():
     row = []
