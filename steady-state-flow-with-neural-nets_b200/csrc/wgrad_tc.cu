@@ -16,6 +16,8 @@
 // columns as three column-shifted copies of the activation planes stacked along M (a3), the three filter rows as the
 // dY rows r-2, r-1, r stacked along N -- the dY tile is loaded as [row][chunk][x][8], which makes the chunks of
 // consecutive rows equidistant, so one B descriptor spans them (n3).
+// Stride-2 layers with Keff <= 32 start every instruction in parity sub-plane 0 and let its M rows run through all
+// four sub-planes (s4): four accumulators (tap pair offsets) instead of nine.
 //
 // Persistent CTAs: CTA (g, s) owns one group g of taps / one 128-channel block of K and every S-th
 // pixel tile; its accumulators stay in TMEM for the whole kernel and are written once, as an fp32
@@ -72,6 +74,9 @@ struct Params {
   int ksize, swap, m64;
   int nt;               // accumulators per CTA
   int a3;               // 1: three column-shifted copies of every plane, the 3 taps of a filter row share one MMA
+  int s4;               // stride 2, Keff <= 32: the four parity sub-planes lie one behind the other with the same chunk stride, so an
+                        // M = 64 / 128 instruction started in sub-plane 0 covers all four -- the taps (2a+p, 2b+q) for the four
+                        // parities (p, q) at once; four accumulators (a, b) instead of nine, rows = (parity, channel)
   int n3;               // a3 and: the three filter ROWS share the MMA too -- the dY tile lands as [row][chunk][x][8] (one tensor copy), so
                         // the chunks of consecutive rows are equidistant and one B descriptor (chunk stride = one x-extent) reads the
                         // N = 3 * nchunks * 8 columns of dY rows r-2, r-1, r against activation row r: nine taps per instruction,
@@ -256,6 +261,7 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
       tapoff[t] = G::S2 ? (uint32_t)((di & 1) * 2 + (dj & 1)) * p.sub_bytes + (uint32_t)(((di >> 1) * G::PU + (dj >> 1)) * 16)
                         : (uint32_t)((di * G::PU + dj) * 16);
       if (p.a3) tapoff[t] = (uint32_t)(t * G::ROW_BYTES);       // accumulator t = filter row t; columns are M groups
+      if (p.s4) tapoff[t] = (uint32_t)((((t >> 1) & 1) * G::PU + (t & 1)) * 16);      // accumulator t = (a, b): offset inside every sub-plane
     }
     const bool swp = p.swap & 1;
     const uint32_t lbo_a = swp ? (uint32_t)(G::PPAD * 16) : 128u, sbo_a = swp ? 128u : (uint32_t)(G::PPAD * 16);
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
     const int row_local = p.m64 ? (lane < 16 ? warp * 16 + lane : 1 << 20) : warp * 32 + lane;
     int krow = mb * kpl * 8 + row_local;
     int du_row = 0;                                   // a3: accumulator row = (column shift du, channel k)
-    if (p.a3) {
+    if (p.a3 || p.s4) {                                // s4: du_row = parity sub-plane
       du_row = row_local / (kpl * 8);
       krow = row_local - du_row * kpl * 8;
     }
@@ -403,12 +409,18 @@ __global__ void __launch_bounds__(THREADS) k_wgrad_tc(const __grid_constant__ Pa
     } else {
 #pragma unroll 1
     for (int t = 0; t < ntaps; ++t) {
-      const int tap = p.a3 ? 3 * t + du_row : tap0 + t;
+      int tap = p.a3 ? 3 * t + du_row : tap0 + t;
+      bool row_ok = p.a3 ? du_row < 3 : row_local < kpl * 8;
+      if (p.s4) {
+        const int di = 2 * (t >> 1) + (du_row >> 1), dj = 2 * (t & 1) + (du_row & 1);
+        row_ok = du_row < 4 && di < 3 && dj < 3;
+        tap = row_ok ? di * 3 + dj : 0;
+      }
       float* dst = p.partial + (((size_t)s_idx * p.T + tap) * p.Keff + krow) * p.N;
       for (int n0 = 0; n0 < p.N; n0 += 8) {
         float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (n_local > 0) ptx::tmem_ld8(lane_base + (uint32_t)(t * p.Npad + n0), o);
-        if ((p.a3 ? du_row < 3 : row_local < kpl * 8) && krow < p.Keff && ok) {
+        if (row_ok && krow < p.Keff && ok) {
           *reinterpret_cast<float4*>(dst + n0) = make_float4(o[0], o[1], o[2], o[3]);
           *reinterpret_cast<float4*>(dst + n0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
         }
@@ -461,8 +473,12 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
   p.a3 = (pl.mode == MODE_S1 && ksize == 3 && p.Keff <= 32 && !(g_swap & 64)) ? 1 : 0;
   // taps per CTA: as many accumulators as TMEM holds next to the bias accumulator (every tap group re-loads and
   // re-transforms the tile, so fewer groups is what counts), evened out over the groups; N = 256 gives the bias up
+  p.s4 = (pl.mode == MODE_S2 && ksize == 3 && p.Keff <= 32 && !(g_swap & 2048)) ? 1 : 0;
   if (p.a3) {
     pl.NT = 3;
+    p.tap_groups = 1;
+  } else if (p.s4) {
+    pl.NT = 4;
     p.tap_groups = 1;
   } else {
     int cap = 512 / p.Npad - 1;
@@ -516,7 +532,7 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
     p.off_dy = p.off_a + p.nbuf * p.a_bytes;
     p.off_stage = p.off_dy + p.nbuf * p.dy_bytes + DY_PLANE;
     uint32_t total = p.off_stage + p.nbuf * p.stage_bytes;
-    const bool m64 = (p.a3 ? 3 : 1) * p.kpl <= 8 && !(g_swap & 32);
+    const bool m64 = (p.a3 ? 3 : (p.s4 ? 4 : 1)) * p.kpl <= 8 && !(g_swap & 32);
     const uint32_t overread = (m64 ? 8u : 16u) * PPAD * 16u + 4096u;
     const uint32_t need = p.off_a + (p.nbuf - 1) * p.a_bytes + (NSUB - 1) * p.sub_bytes + overread;
     if (total < need) total = need;
@@ -538,7 +554,7 @@ static bool plan(Plan& pl, int B, int H, int W, int C, int OH, int OW, int N, in
   p.swap = g_swap;
   // the A operand is read from shared memory at 128 rows x 32 B per MMA whatever the real channel count: half of that
   // (M = 64, N % 8 == 0) when the CTA's channel block is at most 64 wide.  Flag 32 forces M = 128 (experiments).
-  p.m64 = ((p.a3 ? 3 : 1) * p.kpl <= 8 && !(g_swap & 32)) ? 1 : 0;
+  p.m64 = ((p.a3 ? 3 : (p.s4 ? 4 : 1)) * p.kpl <= 8 && !(g_swap & 32)) ? 1 : 0;
   p.idesc = idesc_mn(p.m64 ? 64 : 128, p.Npad);
   for (int c = 1; c <= 3; ++c) p.idesc_rows[c - 1] = idesc_mn(p.m64 ? 64 : 128, c * p.nchunks * 8);
   p.idesc_bias = p.idesc;
