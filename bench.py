@@ -147,7 +147,7 @@ def run_reference(args, rank, world):
     v = b * args.steps / dt
     sample = (f"each step = one forward of the {b}-image workload batch; oracle/flow_oracle.py "
               f"torch-CPU fp32, {cores} threads (TF-1.x reference not installable: SURVEY F11)")
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": v / PUBLISHED_IMG_S, "dtype": "f32", "data": "bundled car masks (fixture), random-init weights",
@@ -265,7 +265,22 @@ def run_train(args, rank, world, dist, native, arch, flow_net, steps=None):
     }
 
 
+_OUT = None
+
+
+def emit(record):
+    """the one JSON line, on the process's original stdout"""
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(record) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries exactly one JSON line: whatever the libraries print there (NCCL's version banner under torchrun) is
+    # sent to stderr by pointing descriptor 1 at it and keeping a private copy of the original for emit()
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -313,7 +328,7 @@ def main():
     if args.mode == "train":
         rec = run_train(args, rank, world, dist, native, arch, flow_net)
         if rec is not None:
-            print(json.dumps(rec))
+            emit(rec)
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -469,7 +484,7 @@ def main():
             line["cpu_baseline"] = cpu
         if train is not None:
             line["train"] = train
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
