@@ -87,6 +87,12 @@ class _BwdWeights:
         return w.to(torch.bfloat16).contiguous()
 
 
+# the nin skip's data gradient: one CUDA-core launch (1x1 conv + prologue adjoint) on the wide, shallow levels, the 1x1 conv on
+# the tensor cores + fn_prologue_bwd where the channel count makes the CUDA-core product the cost (tools/ab_nin_bwd.py, batch
+# 256: F = 8 157 vs 265 us, F = 16 100 vs 121, F = 32 102 vs 80, F = 64 126 vs 38)
+NIN_BWD_FUSED_WIDTHS = (8, 16)
+
+
 def _pad_channels(w, axis, n):
     """the fp32 variable w zero-padded to n entries along `axis` (the 2-channel tail / 1-channel head run as 8-channel launches)"""
     shape = list(w.shape)
@@ -125,7 +131,8 @@ def _conv_plain(x, wts, cout, ksize, stride, device, out=None):
     y = out if out is not None else torch.empty((B, OH, OW, cout), dtype=torch.bfloat16, device=device)
     assert tuple(y.shape) == (B, OH, OW, cout) and y.is_contiguous()
     if not isinstance(wts, _BwdWeights):            # a ready bf16 [T, K, N] tensor
-        w_tc = native.pack_conv_weights_tc(wts, None, ksize, cin, 0, cout, False) if (cin % 16 == 0 or cin == 8) else None
+        w_tc = (arch.weight_prep(lambda: native.pack_conv_weights_tc(wts, None, ksize, cin, 0, cout, False))
+                if (cin % 16 == 0 or cin == 8) else None)
         native.conv_fwd(x, wts, _zeros_bias(cout, device), y, B=B, H=H, W=W, Cin=cin, Cout=cout, ksize=ksize, stride=stride,
                         prologue=native.PRO_NONE, epilogue=native.EPI_BIAS, impl=arch.IMPL, w_tc=w_tc)
         return y
@@ -325,10 +332,11 @@ class BackwardPass:
                                                                    stride=1, prologue=pro), a, dx_1)
                     wn = V[sn + '/weights']                                   # [mult*Ca, F]
                     buf, acc = grads.target(a)
-                    if mult == 2 and F_ in (8, 16, 32, 64) and wn.numel() * 4 <= 64 * 1024 and wn.is_contiguous():
+                    if mult == 2 and F_ in NIN_BWD_FUSED_WIDTHS and wn.numel() * 4 <= 64 * 1024 and wn.is_contiguous():
                         native.nin_bwd(dx_1, wn, a, pro, out=buf, accumulate=acc)       # 1x1 conv + prologue adjoint, one launch
                     else:
-                        dAa = _conv_plain(dx_1, wn.t().reshape(1, F_, -1).to(torch.bfloat16).contiguous(), wn.shape[0], 1, 1, dev)
+                        wts = arch.weight_prep(lambda: wn.t().reshape(1, F_, -1).to(torch.bfloat16).contiguous())
+                        dAa = _conv_plain(dx_1, wts, wn.shape[0], 1, 1, dev)             # 1x1 conv on the tensor cores
                         native.prologue_bwd(dAa, a, pro, out=buf, accumulate=acc)
                 if cin > 1:
                     w1 = V[s1 + '/weights']                                   # [3,3,mult*cin,F]
