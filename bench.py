@@ -287,8 +287,12 @@ def main():
     # stdout carries exactly one JSON line: whatever the libraries print there (NCCL's version banner under torchrun) is
     # sent to stderr by pointing descriptor 1 at it and keeping a private copy of the original for emit()
     global _OUT
-    _OUT = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
+    try:
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        _OUT = os.fdopen(keep, "w")
+    except OSError:              # no usable stderr: leave stdout as it is
+        _OUT = None
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
