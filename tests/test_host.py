@@ -171,3 +171,21 @@ def test_experiment_manager_paths_follow_the_flags(tmp_path):
         assert flags.FLAGS.nr_res_blocks == 3
     finally:
         flags.FLAGS.nr_res_blocks = old
+
+
+def test_weight_prep_is_transparent_outside_a_capture(built_lib):
+    """flow_architecture.weight_prep / flow_backward._pad_channels (host logic of the training graphs' side streams): with no
+    capture in progress the image is made in place, on the caller's stream, and returned unchanged."""
+    import model.flow_architecture as arch
+    import model.flow_backward as fb
+    assert arch._PREP["stream"] is None
+    made = []
+    out = arch.weight_prep(lambda: made.append(1) or "image")
+    assert out == "image" and made == [1]
+    w = torch.arange(3 * 3 * 4 * 2, dtype=torch.float32).reshape(3, 3, 4, 2)
+    w8 = fb._pad_channels(w, 3, 8)
+    assert w8.shape == (3, 3, 4, 8) and torch.equal(w8[..., :2], w) and float(w8[..., 2:].abs().sum()) == 0.0
+    h8 = fb._pad_channels(torch.ones(3, 3, 1, 8), 2, 8)
+    assert h8.shape == (3, 3, 8, 8) and float(h8.sum()) == 72.0
+    # the fused CUDA-core nin adjoint only where it measured faster than the tensor-core route (tools/ab_nin_bwd.py)
+    assert set(fb.NIN_BWD_FUSED_WIDTHS) <= {8, 16, 32, 64}
